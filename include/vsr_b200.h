@@ -1,0 +1,117 @@
+/* vsr_b200 — C ABI of the B200-native STTN inpainting engine.
+ *
+ * The reference (YaoFANGUK/video-subtitle-remover) has no FFI: its plug-in boundary is a set of Python
+ * callables.  Each entry point below names the reference call it replaces (paths relative to the
+ * reference root); the ctypes binding that a maintainer adds is in INTEGRATION.md and
+ * vsr_b200/_capi.py.  Plain pointers and sizes only — no torch / numpy types cross this boundary.
+ *
+ * All functions return 0 on success and a negative code on failure; vsr_last_error() returns a
+ * human-readable message for the calling thread.  There is no CPU fallback: every compute entry
+ * point fails with VSR_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef VSR_B200_H
+#define VSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSR_OK 0
+#define VSR_ERR_ARG (-1)
+#define VSR_ERR_CUDA (-2)
+#define VSR_ERR_STATE (-3)
+#define VSR_ERR_NOMEM (-4)
+
+typedef struct vsr_sttn vsr_sttn_t;
+
+/* Network geometry + window schedule (backend/inpaint/sttn/auto_sttn.py:64-95 and
+ * backend/inpaint/sttn_auto_inpaint.py:38-41). */
+typedef struct vsr_sttn_config {
+  int32_t model_w, model_h;      /* 640, 120  (sttn_auto_inpaint.py:38) */
+  int32_t n_patch;               /* 4 */
+  int32_t patch_w[4], patch_h[4];/* (80,15) (32,6) (10,5) (5,3)  (auto_sttn.py:69) */
+  int32_t neighbor_stride;       /* config.sttnNeighborStride = 5 (backend/config.py:89) */
+  int32_t ref_length;            /* config.sttnReferenceLength = 10 (backend/config.py:91) */
+} vsr_sttn_config;
+
+const char* vsr_last_error(void);
+const char* vsr_version(void);
+/* number of CUDA devices with compute capability 10.x visible to the process */
+int vsr_device_count(void);
+
+/* ---- engine life cycle: replaces STTNInpaint.__init__ (sttn_auto_inpaint.py:29-41) ------------- */
+void vsr_sttn_default_config(vsr_sttn_config* cfg);
+int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg);
+void vsr_sttn_destroy(vsr_sttn_t* h);
+/* One call per tensor of ckpt['netG'] (name as in the state dict, e.g.
+ * "transformer.3.attention.query_embedding.weight"); fp32, C-contiguous, torch layout
+ * [Cout,Cin,kh,kw] / [Cout].  Replaces model.load_state_dict (sttn_auto_inpaint.py:34). */
+int vsr_sttn_set_weight(vsr_sttn_t* h, const char* name, const float* data, const int64_t* shape, int ndim);
+/* Packs the weights into the device layout (fp16, tap-major K); fails if any tensor is missing. */
+int vsr_sttn_finalize_weights(vsr_sttn_t* h);
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+/* STTNInpaint.inpaint (sttn_auto_inpaint.py:122-164): T strip frames [T,model_h,model_w,3] u8 BGR
+ * (host) -> comps [T,model_h,model_w,3] fp32 RGB (host) and visits[T] (1 = the comp is the reference's
+ * uint8 single-visit case, >1 = float32 blended). */
+int vsr_sttn_inpaint_strip(vsr_sttn_t* h, const uint8_t* frames_bgr, int T, float* comps_out, int32_t* visits_out);
+
+/* STTNInpaint.__call__ (sttn_auto_inpaint.py:43-97): T frames of H x W x 3 u8 BGR given as host
+ * pointers, mask H x W u8 (>127 = subtitle).  frames_out[i] may equal frames_in[i] (in place, the
+ * STTNAutoInpaint chunk loop :242-328) or be distinct buffers (the copy made at :58). */
+int vsr_sttn_inpaint_frames(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask,
+                            uint8_t* const* frames_out);
+
+/* Split form of the call above for device-resident timing (bench.py `value`):
+ *   stage  : host frames -> device strips (H2D)            [also computes the strips from the mask]
+ *   compute: everything on the device, returns after the work has been enqueued
+ *   fetch  : device strips -> host frames (D2H), synchronises                                      */
+int vsr_sttn_stage(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask);
+int vsr_sttn_compute(vsr_sttn_t* h);
+int vsr_sttn_fetch(vsr_sttn_t* h, uint8_t* const* frames_out);
+int vsr_sttn_sync(vsr_sttn_t* h);
+/* CUDA stream of the engine (cudaStream_t as void*) so callers can bracket it with events. */
+void* vsr_sttn_stream(vsr_sttn_t* h);
+/* kernels launched by this engine since creation (bench.py `gpu_launches`) */
+int64_t vsr_sttn_launch_count(vsr_sttn_t* h);
+/* Time the dominant kernel family of the last compute: fills ms_out[0..n) with CUDA-event durations
+ * of n back-to-back launches of the transformer-block 3x3 conv (tcgen05 implicit GEMM) on T frames. */
+int vsr_sttn_time_conv(vsr_sttn_t* h, int T, int n, float* ms_out);
+
+/* ---- integer mask / index path (host C++, bit-exact) ------------------------------------------ */
+/* create_mask (backend/tools/inpaint_tools.py:31-47): boxes = n x (xmin,xmax,ymin,ymax). */
+int vsr_create_mask(uint8_t* mask, int H, int W, const int32_t* boxes, int n, int deviation);
+/* get_inpaint_area_by_mask (inpaint_tools.py:49-242): mask non-zero = subtitle.  areas = up to
+ * max_areas x (ymin,ymax,xmin,xmax); returns the count (>= 0) or a negative error. */
+int vsr_inpaint_area_by_mask(int W, int H, int h, const uint8_t* mask, int multiple, int32_t* areas, int max_areas);
+/* batch_generator (inpaint_tools.py:7-29) on a length: writes batch sizes, returns their count. */
+int vsr_batch_sizes(int n_samples, int max_batch_size, int32_t* sizes, int max_sizes);
+/* window schedule (sttn_auto_inpaint.py:142-146 + get_ref_index :107-120): for window w of a T-frame
+ * chunk writes neighbour ids then reference ids into ids[] and their counts; returns #windows. */
+int vsr_window_schedule(int T, int stride, int ref_length, int32_t* ids, int32_t* n_neighbors, int32_t* n_refs, int max_windows,
+                        int max_ids_per_window);
+
+/* ---- operator-level entry points (parity tests call the kernels in isolation) ------------------ */
+/* cv2.resize(src_u8 HxWx3, (dw,dh)) INTER_LINEAR on the device (sttn_auto_inpaint.py:72,270). */
+int vsr_op_resize_u8(int device, const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);
+/* NHWC conv on the tcgen05 implicit-GEMM kernel: in [T,H,W,Cin] fp32 (host), weight [Cout,Cin,k,k]
+ * fp32, k in {1,3}, stride 1, padding = dilation*(k/2); flags bit0 = LeakyReLU(0.2), bit1 = add
+ * residual `res` [T,H,W,Cout] fp32.  out [T,H,W,Cout] fp32 (host). */
+int vsr_op_conv2d(int device, const float* in, int T, int H, int W, int Cin, const float* weight, const float* bias, int Cout,
+                  int ksize, int dilation, int flags, const float* res, float* out);
+/* conv3x3 stride 2 pad 1 through the space-to-depth route used for encoder.4 (Cin = 64). */
+int vsr_op_conv2d_s2(int device, const float* in, int T, int H, int W, int Cin, const float* weight, const float* bias, int Cout,
+                     int flags, float* out);
+/* Multi-head patch attention (auto_sttn.py:167-203 without the 1x1/3x3 convs): q,k,v [T,H,W,C] fp32
+ * (host), n_patch heads of C/n_patch channels with patches (pw[i], ph[i]); out [T,H,W,C] fp32. */
+int vsr_op_patch_attention(int device, const float* q, const float* k, const float* v, int T, int H, int W, int C, int n_patch,
+                           const int32_t* pw, const int32_t* ph, float* out);
+/* F.interpolate(x, scale_factor=2, 'bilinear', align_corners=True) on NHWC (auto_sttn.py:124-126). */
+int vsr_op_upsample2x(int device, const float* in, int T, int H, int W, int C, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSR_B200_H */

@@ -1,0 +1,95 @@
+"""CPU: the product's host C++ integer path (through the C ABI) against the oracle, property-style, plus
+that the library loads and exports every symbol include/vsr_b200.h declares."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import sttn_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(capi):
+    L = capi.lib()
+    hdr = open(os.path.join(ROOT, "include", "vsr_b200.h")).read()
+    declared = set(re.findall(r"\b(vsr_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/vsr_b200.h but not exported"
+    assert declared == set(capi.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in L.vsr_version()
+
+
+def test_compute_fails_loudly_without_gpu(capi):
+    import ctypes as C
+
+    L = capi.lib()
+    if L.vsr_device_count() > 0:
+        pytest.skip("a B200 is present")
+    h = C.c_void_p()
+    rc = L.vsr_sttn_create(C.byref(h), 0, None)
+    assert rc < 0 and b"no CPU fallback" in L.vsr_last_error()
+    from vsr_b200 import STTNInpaint
+
+    with pytest.raises(capi.VsrError):
+        STTNInpaint("cuda:0", {k: v.numpy() for k, v in O.random_weights(0).items()})
+    with pytest.raises(capi.VsrError):
+        STTNInpaint("cpu", {})
+
+
+def test_create_mask_matches_oracle(capi):
+    from vsr_b200 import create_mask
+
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        H, W = int(rng.integers(8, 300)), int(rng.integers(8, 400))
+        boxes = []
+        for _ in range(int(rng.integers(0, 5))):
+            x0 = int(rng.integers(-5, W)); x1 = int(rng.integers(x0, W + 30))
+            y0 = int(rng.integers(-5, H)); y1 = int(rng.integers(y0, H + 30))
+            boxes.append((x0, x1, y0, y1))
+        assert np.array_equal(create_mask((H, W), boxes), O.create_mask((H, W), boxes))
+
+
+def test_inpaint_areas_match_oracle(capi):
+    cv2 = pytest.importorskip("cv2")
+    from vsr_b200 import get_inpaint_area_by_mask
+
+    rng = np.random.default_rng(4)
+    for it in range(400):
+        H, W = int(rng.integers(20, 200)), int(rng.integers(20, 300))
+        if it % 2:
+            m = ((rng.random((H, W)) < rng.choice([0.01, 0.03, 0.08])) * 255).astype(np.uint8)
+            m = cv2.dilate(m, np.ones((3, 3), np.uint8), iterations=int(rng.integers(0, 3)))
+        else:
+            boxes = [(int(rng.integers(0, W)), int(rng.integers(0, W)), int(rng.integers(0, H)), int(rng.integers(0, H)))
+                     for _ in range(int(rng.integers(1, 4)))]
+            m = O.create_mask((H, W), [(min(a, b), max(a, b), min(c, d), max(c, d)) for a, b, c, d in boxes])
+        h = max(1, int(W * 3 / 16))
+        for mult in (1, 8):
+            assert get_inpaint_area_by_mask(W, H, h, (m > 127).astype(np.uint8)[:, :, None], mult) == \
+                O.get_inpaint_area_by_mask(W, H, h, (m > 127).astype(np.uint8), mult), (H, W, it, mult)
+    assert get_inpaint_area_by_mask(64, 32, 12, np.zeros((32, 64), np.uint8)) == []
+
+
+def test_default_1080p_strip(capi):
+    from vsr_b200 import get_inpaint_area_by_mask
+
+    m = O.default_mask(1080, 1920)
+    assert int((m > 0).sum()) == 191100
+    assert get_inpaint_area_by_mask(1920, 1080, 360, m) == [(720, 1080, 0, 1920)]
+
+
+def test_batch_generator_and_schedule_match_oracle(capi):
+    from vsr_b200 import batch_generator
+    from vsr_b200.inpaint_tools import window_schedule
+
+    for n in (0, 1, 7, 49, 50, 100, 299, 300, 500, 1200):
+        for mb in (1, 3, 50, 70):
+            got = [len(b) for b in batch_generator(list(range(n)), mb)]
+            assert got == [b - a for a, b in O.batch_generator(n, mb)], (n, mb)
+    for T in (1, 4, 5, 6, 11, 24, 46, 50, 77):
+        for stride, ref in ((5, 10), (3, 7), (1, 1)):
+            assert window_schedule(T, stride, ref) == [(a, b) for a, b in O.window_schedule(T, stride, ref)]

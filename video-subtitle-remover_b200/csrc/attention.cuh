@@ -1,0 +1,236 @@
+// Multi-geometry patch attention of STTN (auto_sttn.py:140-206) on tcgen05, reading Q/K/V straight
+// out of the NHWC [T,H,W,3*256] fp16 projection buffer — the reference's view/permute/contiguous
+// soft-split copies (auto_sttn.py:182-190, 201-202) do not exist here.
+//
+// Head i owns channels [64 i, 64 i + 64) and patch (pw, ph): token = (t, oh, ow), feature = the
+// ph*pw pixels of the patch x 64 channels.  A dot product over the feature axis is order-invariant,
+// so K-chunk `pos = py*pw + px` of a token is simply the 64 contiguous channels of patch pixel
+// (py, px): a 5-D TMA view {64 ch, px, ow, py, t*oh} of the buffer turns "pixel (py,px) of 128 tokens"
+// into one box {64,1,owp,1,128/owp}.  owp = ow rounded up to a power of two; the padded token index is
+// kp = toh*owp + owi (pad slots are zero-filled by TMA and masked in the softmax).
+//
+//   scores : S[qp, kp]   = sum_pos Q_pos[qp,:] . K_pos[kp,:]          (fp32, split-K where tiles are few)
+//   softmax: P[qp, kp]   = exp((S - rowmax) / sqrt(D)) (fp16, un-normalised), rowsum[qp]
+//   pv     : O[qp, pos,:] = (sum_kp P[qp,kp] V_pos[kp,:]) / rowsum[qp]  -> written back in NHWC
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace vsr {
+
+struct AttnHead {
+  int pw, ph, ow, oh, owp;
+  int npos;        // ph*pw K-chunks of the score GEMM / 64-wide column groups of the PV GEMM
+  int toh_total;   // T*oh
+  int ntt;         // token tiles of 128 padded tokens
+  int nk64;        // 64-token K-chunks of the PV GEMM that contain real tokens
+  int splits, chunks_per_split;  // score GEMM split-K
+  int score_work_begin, pv_work_begin;
+  int pv_ntiles;   // ceil(npos / 4)
+  int ldS, ldP;    // row pitches (elements)
+  float scale_log2e;  // log2(e) / sqrt(64*ph*pw)
+  float* S;
+  __half* P;
+  float* rowsum;
+};
+
+struct ScoreParams {
+  CUtensorMap qmap[4], kmap[4];
+  AttnHead h[4];
+  int nheads, total_work;
+};
+
+struct ScorePolicy {
+  static constexpr int BN = 128;
+  static constexpr int STAGES = 6;
+  static constexpr int B_MN_MAJOR = 0;
+  using Params = ScoreParams;
+  struct Tile {
+    int num_k, n_cols;
+    int head, qi, kj, kbeg, atomic;
+  };
+  struct RowCtx {
+    float* dst;
+  };
+  __device__ static void prefetch(const Params& p) {
+    for (int i = 0; i < p.nheads; ++i) {
+      tma_prefetch_desc(&p.qmap[i]);
+      tma_prefetch_desc(&p.kmap[i]);
+    }
+  }
+  __device__ static int num_tiles(const Params& p) { return p.total_work; }
+  __device__ static Tile get_tile(const Params& p, int idx) {
+    int hd = 0;
+    while (hd + 1 < p.nheads && idx >= p.h[hd + 1].score_work_begin) ++hd;
+    const AttnHead& h = p.h[hd];
+    idx -= h.score_work_begin;
+    Tile t;
+    t.head = hd;
+    const int sp = idx % h.splits;
+    idx /= h.splits;
+    t.kj = idx % h.ntt;
+    t.qi = idx / h.ntt;
+    t.kbeg = sp * h.chunks_per_split;
+    t.num_k = min(h.chunks_per_split, h.npos - t.kbeg);
+    t.n_cols = BN;
+    t.atomic = h.splits > 1;
+    return t;
+  }
+  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
+    const AttnHead& h = p.h[t.head];
+    const int pos = t.kbeg + k;
+    const int py = pos / h.pw, px = pos - py * h.pw;
+    const int rows = 128 / h.owp;
+    mbar_expect_tx(bar, 2 * TC_A_BYTES);
+    tma_load_5d(sA, &p.qmap[t.head], bar, 0, px, 0, py, t.qi * rows);
+    tma_load_5d(sB, &p.kmap[t.head], bar, 0, px, 0, py, t.kj * rows);
+  }
+  __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
+    const AttnHead& h = p.h[t.head];
+    RowCtx c;
+    c.dst = h.S + (size_t)(t.qi * 128 + row) * h.ldS + t.kj * 128;
+    return c;
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
+    float* d = c.dst + col0;
+    if (t.atomic) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(d + i, v[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+};
+
+// One block per (padded) query row.  Invalid rows (pad slots) are skipped: they only feed accumulator
+// rows that the PV epilogue never stores.  Pad *columns* get P = 0.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
+  const AttnHead& h = p.h[blockIdx.y];
+  const int qp = blockIdx.x;
+  if (qp >= h.ntt * 128) return;
+  const int toh = qp / h.owp, owi = qp - toh * h.owp;
+  if (owi >= h.ow || toh >= h.toh_total) return;
+  const float* s = h.S + (size_t)qp * h.ldS;
+  __half* pr = h.P + (size_t)qp * h.ldP;
+  const int ncols = h.nk64 * 64;
+  const int nvalid = h.toh_total * h.owp;
+  __shared__ float red[8];
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < nvalid; c += 256) {
+    if ((c % h.owp) < h.ow) m = fmaxf(m, s[c]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < ncols; c += 256) {
+    float e = 0.f;
+    if (c < nvalid && (c % h.owp) < h.ow) e = exp2f((s[c] - m) * h.scale_log2e);
+    const __half eh = __float2half_rn(e);
+    pr[c] = eh;
+    sum += __half2float(eh);  // normalise by what the PV GEMM will actually multiply with
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    h.rowsum[qp] = tot;
+  }
+}
+
+struct PVParams {
+  CUtensorMap pmap[4], vmap[4];
+  AttnHead h[4];
+  int nheads, total_work;
+  int T, H, W;       // feature map geometry
+  __half* out;       // NHWC fp16 [T,H,W,out_pitch]; (sorted) head s writes channels [coff[s], coff[s] + 64)
+  int out_pitch;
+  int coff[4];
+};
+
+struct PVPolicy {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 4;
+  static constexpr int B_MN_MAJOR = 1;
+  using Params = PVParams;
+  struct Tile {
+    int num_k, n_cols;
+    int head, mi, ni, nvalid;
+  };
+  struct RowCtx {
+    bool valid;
+    float inv;
+    __half* base;
+  };
+  __device__ static void prefetch(const Params& p) {
+    for (int i = 0; i < p.nheads; ++i) {
+      tma_prefetch_desc(&p.pmap[i]);
+      tma_prefetch_desc(&p.vmap[i]);
+    }
+  }
+  __device__ static int num_tiles(const Params& p) { return p.total_work; }
+  __device__ static Tile get_tile(const Params& p, int idx) {
+    int hd = 0;
+    while (hd + 1 < p.nheads && idx >= p.h[hd + 1].pv_work_begin) ++hd;
+    const AttnHead& h = p.h[hd];
+    idx -= h.pv_work_begin;
+    Tile t;
+    t.head = hd;
+    t.ni = idx % h.pv_ntiles;
+    t.mi = idx / h.pv_ntiles;
+    t.nvalid = min(4, h.npos - t.ni * 4);
+    t.num_k = h.nk64;
+    t.n_cols = t.nvalid * 64;
+    return t;
+  }
+  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
+    const AttnHead& h = p.h[t.head];
+    mbar_expect_tx(bar, (uint32_t)(TC_A_BYTES + t.nvalid * 8192));
+    tma_load_2d(sA, &p.pmap[t.head], bar, k * 64, t.mi * 128);
+    const int rows = 64 / h.owp;
+    for (int j = 0; j < t.nvalid; ++j) {
+      const int pos = t.ni * 4 + j;
+      const int py = pos / h.pw, px = pos - py * h.pw;
+      tma_load_5d(sB + j * 8192, &p.vmap[t.head], bar, 0, px, 0, py, k * rows);
+    }
+  }
+  __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
+    const AttnHead& h = p.h[t.head];
+    RowCtx c;
+    const int qp = t.mi * 128 + row;
+    const int toh = qp / h.owp, owi = qp - toh * h.owp;
+    c.valid = owi < h.ow && toh < h.toh_total;
+    c.inv = 0.f;
+    c.base = nullptr;
+    if (c.valid) {
+      c.inv = 1.0f / h.rowsum[qp];
+      const int tt = toh / h.oh, ohi = toh - tt * h.oh;
+      c.base = p.out + (((size_t)tt * p.H + ohi * h.ph) * p.W + owi * h.pw) * p.out_pitch + p.coff[t.head];
+    }
+    return c;
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
+    if (!c.valid) return;
+    const AttnHead& h = p.h[t.head];
+    const int pos = t.ni * 4 + (col0 >> 6);
+    const int py = pos / h.pw, px = pos - py * h.pw;
+    __half* o = c.base + ((size_t)py * p.W + px) * p.out_pitch + (col0 & 63);
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      __align__(16) __half2 hh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(v[i + 2 * j] * c.inv, v[i + 2 * j + 1] * c.inv);
+      *reinterpret_cast<uint4*>(o + i) = *reinterpret_cast<const uint4*>(hh);
+    }
+  }
+};
+
+}  // namespace vsr

@@ -1,0 +1,151 @@
+// Implicit-GEMM convolution on tcgen05 for NHWC fp16 activations (stride 1, arbitrary tap offsets).
+//   M = output pixels (tiles of tile_w x tile_h <= 128 pixels of one frame)
+//   N = output channels (BN per tile), K = taps x Cin in chunks of 64 channels
+// The A operand of tap (dy,dx) is the activation tensor shifted by (dy,dx): one 4-D TMA box
+// {64 ch, tile_w, tile_h, 1 frame} whose out-of-range pixels are zero-filled by the TMA unit, which
+// is exactly the zero padding of the reference convs (auto_sttn.py:76-95,156-164,215-218).
+// Stride-2 convs are run as stride-1 2x2-tap convs over a space-to-depth input (see weights.cuh).
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace vsr {
+
+enum ConvFlags : int {
+  CONV_LRELU = 1,      // LeakyReLU(0.2) after bias
+  CONV_RESIDUAL = 2,   // out32 = res32 + act ; out16 = fp16(out32)
+  CONV_S2D_STORE = 4,  // store out16 space-to-depth: [T, H/2, W/2, 4*Cout], channel = (y&1)*2*Cout + (x&1)*Cout + c
+  CONV_FINAL = 8,      // decoder.6: tanh -> (x+1)/2*255 -> trunc u8 -> first visit store / 0.5-0.5 blend into comps
+};
+
+struct ConvParams {
+  CUtensorMap in_map;  // 4-D {C, W, H, T} fp16, box {64, tile_w, tile_h, 1}, SWIZZLE_128B
+  CUtensorMap w_map;   // 2-D {K_total, Cout_pad} fp16, box {64, BN}, SWIZZLE_128B
+  int T, H, W;         // output (= input) spatial size
+  int tile_w, tile_h, tiles_x, tiles_y;
+  int n_tiles;         // Cout_pad / BN
+  int ntaps, cin_chunks;
+  int cout;            // real output channels
+  int flags;
+  int8_t tap_dy[9], tap_dx[9];
+  const float* bias;   // [Cout_pad]
+  __half* out16;       // NHWC fp16, pixel pitch out16_pitch (elements), channel offset out16_coff
+  int out16_pitch, out16_coff;
+  float* out32;        // NHWC fp32 residual stream [T,H,W,cout] (CONV_RESIDUAL)
+  const float* res32;
+  // CONV_FINAL
+  float* comps;        // [chunk_T, H, W, 3] fp32 RGB running composites
+  const int* frame_idx;   // window-local frame -> chunk frame
+  const int* first_visit; // window-local frame -> 1 if this is the first time the frame is decoded
+};
+
+template <int BN_>
+struct ConvPolicy {
+  static constexpr int BN = BN_;
+  static constexpr int STAGES = (BN_ == 256) ? 4 : 6;
+  static constexpr int B_MN_MAJOR = 0;
+  using Params = ConvParams;
+  struct Tile {
+    int num_k, n_cols;
+    int t, y0, x0, n0;
+  };
+  struct RowCtx {
+    bool valid;
+    int t, y, x;
+    size_t pix;  // (t*H + y)*W + x
+  };
+
+  __device__ static void prefetch(const Params& p) {
+    tma_prefetch_desc(&p.in_map);
+    tma_prefetch_desc(&p.w_map);
+  }
+  __device__ static int num_tiles(const Params& p) { return p.T * p.tiles_y * p.tiles_x * p.n_tiles; }
+  __device__ static Tile get_tile(const Params& p, int idx) {
+    Tile t;
+    const int n = idx % p.n_tiles;
+    idx /= p.n_tiles;
+    const int tx = idx % p.tiles_x;
+    idx /= p.tiles_x;
+    const int ty = idx % p.tiles_y;
+    t.t = idx / p.tiles_y;
+    t.x0 = tx * p.tile_w;
+    t.y0 = ty * p.tile_h;
+    t.n0 = n * BN;
+    t.num_k = p.ntaps * p.cin_chunks;
+    t.n_cols = BN;
+    return t;
+  }
+  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
+    const int tap = k / p.cin_chunks;
+    const int kc = k - tap * p.cin_chunks;
+    mbar_expect_tx(bar, (uint32_t)(p.tile_w * p.tile_h * 128 + BN * 128));
+    tma_load_4d(sA, &p.in_map, bar, kc * 64, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.t);
+    tma_load_2d(sB, &p.w_map, bar, k * 64, t.n0);
+  }
+  __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
+    RowCtx c;
+    const int ry = row / p.tile_w, rx = row - ry * p.tile_w;
+    c.t = t.t;
+    c.y = t.y0 + ry;
+    c.x = t.x0 + rx;
+    c.valid = (ry < p.tile_h) && (c.y < p.H) && (c.x < p.W);
+    c.pix = ((size_t)t.t * p.H + c.y) * p.W + c.x;
+    return c;
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
+    if (!c.valid) return;
+    constexpr int NV = (BN >= 32) ? 32 : 16;
+    const int ch0 = t.n0 + col0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(p.bias + ch0 + i);
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+    if (p.flags & CONV_LRELU) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
+    }
+    if (p.flags & CONV_FINAL) {
+      if (col0 != 0) return;
+      const int f = p.frame_idx[c.t];
+      float* dst = p.comps + (((size_t)f * p.H + c.y) * p.W + c.x) * 3;
+      const bool first = p.first_visit[c.t] != 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        // sttn_auto_inpaint.py:150-158: tanh -> (x+1)/2 -> *255 -> astype(uint8) (truncation)
+        float y = (tanhf(v[i]) + 1.0f) * 0.5f;
+        y = y * 255.0f;
+        const float q = (float)(unsigned char)fminf(fmaxf(y, 0.f), 255.f);
+        dst[i] = first ? q : (dst[i] * 0.5f + q * 0.5f);  // :159-162
+      }
+      return;
+    }
+    if (p.flags & CONV_RESIDUAL) {
+      const float* r = p.res32 + c.pix * p.cout + ch0;
+      float* o = p.out32 + c.pix * p.cout + ch0;
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(r + i);
+        v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+        *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+    if (p.out16) {
+      __half* o;
+      if (p.flags & CONV_S2D_STORE) {
+        const size_t opix = ((size_t)c.t * (p.H >> 1) + (c.y >> 1)) * (p.W >> 1) + (c.x >> 1);
+        o = p.out16 + opix * p.out16_pitch + ((c.y & 1) * 2 + (c.x & 1)) * p.cout + ch0;
+      } else {
+        o = p.out16 + c.pix * p.out16_pitch + p.out16_coff + ch0;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; i += 8) {
+        __align__(16) __half2 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+        *reinterpret_cast<uint4*>(o + i) = *reinterpret_cast<const uint4*>(h);
+      }
+    }
+  }
+};
+
+}  // namespace vsr

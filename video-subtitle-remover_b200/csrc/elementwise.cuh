@@ -1,0 +1,182 @@
+// HBM-bound elementwise kernels either side of the network: strip pre-processing (cv2-exact u8
+// bilinear down-scale), the 3->64 stride-2 stem conv, bilinear x2 (align_corners=True), and the
+// post-processing (cv2-exact up-scale of the composites, u8 truncation, channel swap, mask select).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vsr {
+
+// cv::resize INTER_LINEAR tap table for one axis (built on the host, see resize_tables() in engine.cu)
+struct ResizeTaps {
+  const int* i0;      // first source index
+  const int* i1;      // second source index
+  const float* a;     // fractional weight of i1 (float path)
+  const short* w0;    // rint((1-a)*2048)  (u8 path)
+  const short* w1;    // rint(a*2048)
+};
+
+// A3/A4: crop is implicit (src points at the strip rows), cv2.resize u8 -> [T, dh, dw] RGBA8 with
+// channels swapped to RGB (Stack(), utils/sttn_utils.py:73).  One thread per output pixel.
+__global__ void __launch_bounds__(256) strip_downscale_kernel(const uint8_t* __restrict__ src, size_t src_frame_stride, int sw,
+                                                              int sh, uint8_t* __restrict__ dst, int dw, int dh, int T,
+                                                              ResizeTaps tx, ResizeTaps ty) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int t = blockIdx.z;
+  if (x >= dw) return;
+  const uint8_t* f = src + (size_t)t * src_frame_stride;
+  const int x0 = tx.i0[x] * 3, x1 = tx.i1[x] * 3;
+  const int wx0 = tx.w0[x], wx1 = tx.w1[x];
+  const int wy0 = ty.w0[y], wy1 = ty.w1[y];
+  const uint8_t* r0 = f + (size_t)ty.i0[y] * sw * 3;
+  const uint8_t* r1 = f + (size_t)ty.i1[y] * sw * 3;
+  uchar4 o;
+  uint8_t* op = reinterpret_cast<uint8_t*>(&o);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int s0 = r0[x0 + c] * wx0 + r0[x1 + c] * wx1;
+    const int s1 = r1[x0 + c] * wx0 + r1[x1 + c] * wx1;
+    const int v = (((wy0 * (s0 >> 4)) >> 16) + ((wy1 * (s1 >> 4)) >> 16) + 2) >> 2;
+    op[2 - c] = (uint8_t)min(max(v, 0), 255);  // BGR -> RGB
+  }
+  op[3] = 0;
+  reinterpret_cast<uchar4*>(dst)[((size_t)t * dh + y) * dw + x] = o;
+}
+
+// A5 first layer (auto_sttn.py:76-77): conv3x3 stride 2 pad 1, 3 -> 64, LeakyReLU(0.2), computed in
+// fp32 from the RGBA8 image with the `/255*2-1` normalisation of sttn_auto_inpaint.py:128 folded in.
+// in [T,H,W] RGBA8 -> out NHWC fp16 [T,H/2,W/2,64].  Block = 64 output pixels x 4 channel groups.
+__global__ void __launch_bounds__(256) stem_conv_kernel(const uchar4* __restrict__ in, int H, int W, const float* __restrict__ wgt,
+                                                        const float* __restrict__ bias, __half* __restrict__ out, int total_pix) {
+  __shared__ float sw[27 * 64];  // [tap*3+ci][co]
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) sw[i] = wgt[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int OW = W >> 1, OH = H >> 1;
+  const int pix = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int cg = threadIdx.x >> 6;  // 16 output channels each
+  if (pix >= total_pix) return;
+  const int ox = pix % OW;
+  const int oy = (pix / OW) % OH;
+  const int t = pix / (OW * OH);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = sb[cg * 16 + i];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 + ky - 1;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 + kx - 1;
+      if (ix < 0 || ix >= W) continue;
+      const uchar4 px = in[((size_t)t * H + iy) * W + ix];
+      const float v[3] = {(float)px.x / 255.0f * 2.0f - 1.0f, (float)px.y / 255.0f * 2.0f - 1.0f,
+                          (float)px.z / 255.0f * 2.0f - 1.0f};
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* wr = sw + ((ky * 3 + kx) * 3 + ci) * 64 + cg * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(v[ci], wr[i], acc[i]);
+      }
+    }
+  }
+  __align__(16) __half2 h[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = acc[2 * i], b = acc[2 * i + 1];
+    a = a > 0.f ? a : 0.2f * a;
+    b = b > 0.f ? b : 0.2f * b;
+    h[i] = __floats2half2_rn(a, b);
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)pix * 64 + cg * 16);
+  o[0] = reinterpret_cast<const uint4*>(h)[0];
+  o[1] = reinterpret_cast<const uint4*>(h)[1];
+}
+
+// deconv's F.interpolate(scale_factor=2, mode='bilinear', align_corners=True) (auto_sttn.py:124-126)
+// on NHWC fp16; one thread = 8 channels of one output pixel.
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ in, int T, int h, int w, int C,
+                                                         __half* __restrict__ out) {
+  const int cg = C >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)T * (2 * h) * (2 * w) * cg;
+  if (idx >= total) return;
+  const int c8 = idx % cg;
+  size_t r = idx / cg;
+  const int ox = r % (2 * w);
+  r /= (2 * w);
+  const int oy = r % (2 * h);
+  const int t = r / (2 * h);
+  const float sy = (float)(h - 1) / (float)(2 * h - 1), sx = (float)(w - 1) / (float)(2 * w - 1);
+  const float fy = sy * oy, fx = sx * ox;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const __half* base = in + (size_t)t * h * w * C + c8 * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x0) * C);
+  const uint4 b = *reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x1) * C);
+  const uint4 c = *reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x0) * C);
+  const uint4 d = *reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x1) * C);
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+  const __half2* pc = reinterpret_cast<const __half2*>(&c);
+  const __half2* pd = reinterpret_cast<const __half2*>(&d);
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __half22float2(pa[i]), fb = __half22float2(pb[i]), fc = __half22float2(pc[i]), fd = __half22float2(pd[i]);
+    const float u = hy * (hx * fa.x + lx * fb.x) + ly * (hx * fc.x + lx * fd.x);
+    const float v = hy * (hx * fa.y + lx * fb.y) + ly * (hx * fc.y + lx * fd.y);
+    o[i] = __floats2half2_rn(u, v);
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)t * 2 * h + oy) * 2 * w + ox) * C + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// A3 tail (sttn_auto_inpaint.py:86-91 / 312-315): comp = cv2.resize(comp, (W, split_h)) [u8 fixed-point
+// path when the frame was decoded once, float path otherwise] -> astype(uint8) -> RGB->BGR ->
+// strip = mask ? comp : strip.  comps [T, ch, cw, 3] fp32 RGB; strips [T, sh, sw, 3] u8 BGR in place.
+__global__ void __launch_bounds__(256) strip_composite_kernel(const float* __restrict__ comps, int cw, int ch,
+                                                              const int* __restrict__ visits, const uint8_t* __restrict__ mask,
+                                                              int mask_pitch, uint8_t* __restrict__ strips, size_t strip_frame_stride,
+                                                              int sw, int sh, int T, ResizeTaps tx, ResizeTaps ty) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int t = blockIdx.z;
+  if (x >= sw) return;
+  if (mask[(size_t)y * mask_pitch + x] == 0) return;
+  const float* f = comps + (size_t)t * ch * cw * 3;
+  const int x0 = tx.i0[x], x1 = tx.i1[x], y0 = ty.i0[y], y1 = ty.i1[y];
+  const float* p00 = f + ((size_t)y0 * cw + x0) * 3;
+  const float* p01 = f + ((size_t)y0 * cw + x1) * 3;
+  const float* p10 = f + ((size_t)y1 * cw + x0) * 3;
+  const float* p11 = f + ((size_t)y1 * cw + x1) * 3;
+  uint8_t* o = strips + (size_t)t * strip_frame_stride + ((size_t)y * sw + x) * 3;
+  if (visits[t] <= 1) {
+    const int wx0 = tx.w0[x], wx1 = tx.w1[x], wy0 = ty.w0[y], wy1 = ty.w1[y];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int s0 = (int)p00[c] * wx0 + (int)p01[c] * wx1;
+      const int s1 = (int)p10[c] * wx0 + (int)p11[c] * wx1;
+      const int v = (((wy0 * (s0 >> 4)) >> 16) + ((wy1 * (s1 >> 4)) >> 16) + 2) >> 2;
+      o[2 - c] = (uint8_t)min(max(v, 0), 255);
+    }
+  } else {
+    const float ax = tx.a[x], ay = ty.a[y];
+    const float bx = 1.0f - ax, by = 1.0f - ay;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // cv::resize float path: horizontal then vertical, separate roundings (no contraction)
+      const float h0 = __fadd_rn(__fmul_rn(p00[c], bx), __fmul_rn(p01[c], ax));
+      const float h1 = __fadd_rn(__fmul_rn(p10[c], bx), __fmul_rn(p11[c], ax));
+      const float v = __fadd_rn(__fmul_rn(h0, by), __fmul_rn(h1, ay));
+      o[2 - c] = (uint8_t)fminf(fmaxf(v, 0.f), 255.f);  // astype(uint8): truncation
+    }
+  }
+}
+
+}  // namespace vsr

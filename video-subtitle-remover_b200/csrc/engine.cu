@@ -1,0 +1,1129 @@
+// vsr_b200 engine: C-ABI, weight packing, workspace, window schedule and kernel launches for the
+// STTN-auto hot path.  Single translation unit: the .cuh files hold the
+// sm_100a kernels, this file is the host runtime around them.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vsr_b200.h"
+#include "attention.cuh"
+#include "conv_igemm.cuh"
+#include "elementwise.cuh"
+#include "host_index.h"
+
+namespace vsr {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define CK(expr)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (expr);                                                                                  \
+    if (e_ != cudaSuccess)                                                                                    \
+      throw Error(VSR_ERR_CUDA, std::string(#expr) + " -> " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                    std::to_string(__LINE__) + ")");                                          \
+  } while (0)
+#define REQUIRE(cond, msg) \
+  do {                     \
+    if (!(cond)) throw Error(VSR_ERR_ARG, std::string(msg) + " [" #cond "]"); \
+  } while (0)
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return VSR_OK;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return VSR_ERR_STATE;
+  }
+}
+
+static std::string device_error_report() {
+  unsigned int h[4] = {0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(h, g_dev_error, sizeof(h)) != cudaSuccess) return "";
+  if (!h[0]) return "";
+  char buf[160];
+  snprintf(buf, sizeof(buf), " [device watchdog: code 0x%x block %u bar 0x%x thread %u]", h[0], h[1], h[2], h[3]);
+  return buf;
+}
+
+// ------------------------------------------------------------------------------------------------ device memory
+struct DevBuf {
+  void* p = nullptr;
+  size_t n = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= n) return;
+    if (p) CK(cudaFree(p));
+    p = nullptr;
+    n = 0;
+    const size_t want = (bytes + 255) & ~(size_t)255;
+    CK(cudaMalloc(&p, want));
+    CK(cudaMemset(p, 0, want));
+    CK(cudaDeviceSynchronize());  // the memset runs on the legacy stream; engine streams are non-blocking
+    n = want;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+template <class T>
+static void upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s = nullptr) {
+  b.ensure(v.size() * sizeof(T) + 16);
+  CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+}
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) throw Error(VSR_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// fp16 tensor, dims innermost-first, strides in BYTES for dims 1..rank-1, SWIZZLE_128B, zero OOB fill.
+static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  CUtensorMap m;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gs[i] = strides_bytes[i];
+  }
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string s = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") rank " + std::to_string(rank) + " dims";
+    for (int i = 0; i < rank; ++i) s += " " + std::to_string(dims[i]);
+    s += " box";
+    for (int i = 0; i < rank; ++i) s += " " + std::to_string(box[i]);
+    throw Error(VSR_ERR_CUDA, s);
+  }
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------------ launch helpers
+struct Ctx {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+};
+
+template <class P>
+static void launch_tc(Ctx& c, const typename P::Params& prm, int ntiles) {
+  static bool configured = false;
+  constexpr int smem = tc_smem_bytes<P>();
+  if (!configured) {
+    CK(cudaFuncSetAttribute(tc_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  if (ntiles <= 0) return;
+  const int grid = ntiles < c.sms ? ntiles : c.sms;
+  tc_gemm_kernel<P><<<grid, TC_THREADS, smem, c.stream>>>(prm);
+  CK(cudaGetLastError());
+  ++c.launches;
+}
+
+// ------------------------------------------------------------------------------------------------ conv layers
+struct ConvLayer {
+  DevBuf w, b;
+  int cin = 0, cout = 0, cout_pad = 0, ntaps = 0, K = 0, bn = 0;
+  int8_t dy[9] = {0}, dx[9] = {0};
+};
+
+static int pad_cout(int cout) {
+  if (cout <= 16) return 16;
+  if (cout <= 64) return 64;
+  if (cout <= 128) return 128;
+  return (cout + 255) / 256 * 256;
+}
+
+// torch [Cout,Cin,k,k] fp32 -> fp16 [Cout_pad][tap][Cin], tap = ky*k+kx, offsets (ky-k/2)*dil.
+static void pack_conv(ConvLayer& L, const float* w, const float* bias, int cout, int cin, int k, int dil, cudaStream_t s) {
+  REQUIRE(cin % 64 == 0, "tcgen05 conv needs Cin multiple of 64");
+  REQUIRE(k == 1 || k == 3, "kernel size 1 or 3");
+  L.cin = cin; L.cout = cout; L.cout_pad = pad_cout(cout); L.ntaps = k * k; L.K = k * k * cin;
+  L.bn = L.cout_pad < 256 ? L.cout_pad : 256;
+  std::vector<__half> hw((size_t)L.cout_pad * L.K, __float2half(0.f));
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx)
+          hw[(size_t)co * L.K + (ky * k + kx) * cin + ci] = __float2half_rn(w[(((size_t)co * cin + ci) * k + ky) * k + kx]);
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      L.dy[ky * k + kx] = (int8_t)((ky - k / 2) * dil);
+      L.dx[ky * k + kx] = (int8_t)((kx - k / 2) * dil);
+    }
+  std::vector<float> hb(L.cout_pad, 0.f);
+  for (int i = 0; i < cout; ++i) hb[i] = bias ? bias[i] : 0.f;
+  upload(L.w, hw, s);
+  upload(L.b, hb, s);
+}
+
+// conv3x3 stride 2 pad 1 over [H,W,Cin] == conv 2x2 (taps dy,dx in {-1,0}) stride 1 over the
+// space-to-depth tensor [H/2,W/2,4*Cin] (channel = (py*2+px)*Cin + ci): input row 2*yo+ky-1 =
+// 2*(yo+dyb)+py  =>  ky = 2*dyb + py + 1.  Unused (tap, parity) combinations get zero weights.
+static void pack_conv_s2d(ConvLayer& L, const float* w, const float* bias, int cout, int cin, cudaStream_t s) {
+  REQUIRE((4 * cin) % 64 == 0, "s2d conv needs 4*Cin multiple of 64");
+  L.cin = 4 * cin; L.cout = cout; L.cout_pad = pad_cout(cout); L.ntaps = 4; L.K = 16 * cin;
+  L.bn = L.cout_pad < 256 ? L.cout_pad : 256;
+  std::vector<__half> hw((size_t)L.cout_pad * L.K, __float2half(0.f));
+  for (int co = 0; co < cout; ++co)
+    for (int dyb = -1; dyb <= 0; ++dyb)
+      for (int dxb = -1; dxb <= 0; ++dxb)
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px) {
+            const int ky = 2 * dyb + py + 1, kx = 2 * dxb + px + 1;
+            if (ky < 0 || ky > 2 || kx < 0 || kx > 2) continue;
+            const int tap = (dyb + 1) * 2 + (dxb + 1);
+            for (int ci = 0; ci < cin; ++ci)
+              hw[(size_t)co * L.K + (size_t)tap * 4 * cin + (py * 2 + px) * cin + ci] =
+                  __float2half_rn(w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx]);
+          }
+  for (int dyb = -1; dyb <= 0; ++dyb)
+    for (int dxb = -1; dxb <= 0; ++dxb) {
+      L.dy[(dyb + 1) * 2 + (dxb + 1)] = (int8_t)dyb;
+      L.dx[(dyb + 1) * 2 + (dxb + 1)] = (int8_t)dxb;
+    }
+  std::vector<float> hb(L.cout_pad, 0.f);
+  for (int i = 0; i < cout; ++i) hb[i] = bias ? bias[i] : 0.f;
+  upload(L.w, hw, s);
+  upload(L.b, hb, s);
+}
+
+static void choose_tile(int H, int W, int& tw, int& th) {
+  double best = -1;
+  tw = 32; th = 4;
+  for (int w = 1; w <= 128 && w <= 256; ++w) {
+    if (w > W && w != 1) break;
+    const int h = 128 / w;
+    if (h < 1) break;
+    const int hh = h > H ? H : h;
+    const long long covered = (long long)((W + w - 1) / w) * ((H + hh - 1) / hh);
+    const double util = (double)W * H / (double)(covered * 128);
+    if (util >= best - 1e-9) { best = util; tw = w; th = hh; }  // ties: prefer the widest tile
+  }
+}
+
+struct ConvIO {
+  const __half* in = nullptr;
+  int T = 0, H = 0, W = 0;
+  int flags = 0;
+  __half* out16 = nullptr;
+  int out16_pitch = 0, out16_coff = 0;
+  float* out32 = nullptr;
+  const float* res32 = nullptr;
+  float* comps = nullptr;
+  const int* frame_idx = nullptr;
+  const int* first_visit = nullptr;
+};
+
+static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  int tw, th;
+  choose_tile(io.H, io.W, tw, th);
+  {
+    const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)io.W, (uint64_t)io.H, (uint64_t)io.T};
+    const uint64_t str[3] = {(uint64_t)L.cin * 2, (uint64_t)io.W * L.cin * 2, (uint64_t)io.H * io.W * L.cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
+    p.in_map = make_map_f16(io.in, 4, dims, str, box);
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)L.K, (uint64_t)L.cout_pad};
+    const uint64_t str[1] = {(uint64_t)L.K * 2};
+    const uint32_t box[2] = {64, (uint32_t)L.bn};
+    p.w_map = make_map_f16(L.w.p, 2, dims, str, box);
+  }
+  p.T = io.T; p.H = io.H; p.W = io.W;
+  p.tile_w = tw; p.tile_h = th;
+  p.tiles_x = (io.W + tw - 1) / tw;
+  p.tiles_y = (io.H + th - 1) / th;
+  p.n_tiles = L.cout_pad / L.bn;
+  p.ntaps = L.ntaps;
+  p.cin_chunks = L.cin / 64;
+  p.cout = L.cout;
+  p.flags = io.flags;
+  memcpy(p.tap_dy, L.dy, 9);
+  memcpy(p.tap_dx, L.dx, 9);
+  p.bias = L.b.as<float>();
+  p.out16 = io.out16;
+  p.out16_pitch = io.out16_pitch ? io.out16_pitch : L.cout;
+  p.out16_coff = io.out16_coff;
+  p.out32 = io.out32;
+  p.res32 = io.res32;
+  p.comps = io.comps;
+  p.frame_idx = io.frame_idx;
+  p.first_visit = io.first_visit;
+  if (io.flags & CONV_S2D_STORE) {
+    REQUIRE(io.H % 2 == 0 && io.W % 2 == 0, "s2d store needs even H, W");
+    p.out16_pitch = 4 * L.cout;
+  }
+  if (!(io.flags & CONV_FINAL)) REQUIRE(L.cout == L.cout_pad, "Cout must be 64, 128 or a multiple of 256");
+  const int ntiles = p.T * p.tiles_y * p.tiles_x * p.n_tiles;
+  switch (L.bn) {
+    case 256: launch_tc<ConvPolicy<256>>(c, p, ntiles); break;
+    case 128: launch_tc<ConvPolicy<128>>(c, p, ntiles); break;
+    case 64: launch_tc<ConvPolicy<64>>(c, p, ntiles); break;
+    case 16: launch_tc<ConvPolicy<16>>(c, p, ntiles); break;
+    default: throw Error(VSR_ERR_STATE, "unsupported BN");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+struct AttnWorkspace {
+  DevBuf S[4], P[4], rowsum[4];
+};
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// qkv: NHWC fp16 [T,H,W,pitch]; q/k/v channel offsets q_off/k_off/v_off; head i uses +i*dk.
+static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitch, int q_off, int k_off, int v_off, int T, int H,
+                          int W, int C, int n_patch, const int* pw, const int* ph, __half* out, int out_pitch) {
+  REQUIRE(n_patch >= 1 && n_patch <= 4, "1..4 heads");
+  const int dk = C / n_patch;
+  REQUIRE(dk == 64, "head width must be 64 channels (one SWIZZLE_128B row)");
+  ScoreParams sp;
+  PVParams pp;
+  memset(&sp, 0, sizeof(sp));
+  memset(&pp, 0, sizeof(pp));
+  // order heads by descending work so the long tiles are scheduled first
+  std::vector<int> order(n_patch);
+  for (int i = 0; i < n_patch; ++i) order[i] = i;
+  auto work = [&](int i) {
+    const double n = (double)T * (H / ph[i]) * (W / pw[i]);
+    return n * n * 64.0 * pw[i] * ph[i];
+  };
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return work(a) > work(b); });
+  int score_work = 0, pv_work = 0, max_rows = 0;
+  for (int s = 0; s < n_patch; ++s) {
+    const int i = order[s];
+    AttnHead h;
+    memset(&h, 0, sizeof(h));
+    REQUIRE(W % pw[i] == 0 && H % ph[i] == 0, "patch must divide the feature map");
+    h.pw = pw[i]; h.ph = ph[i];
+    h.ow = W / pw[i]; h.oh = H / ph[i];
+    h.owp = next_pow2(h.ow);
+    REQUIRE(h.owp <= 64, "more than 64 patches per row is not supported");
+    h.npos = pw[i] * ph[i];
+    h.toh_total = T * h.oh;
+    const int ntok_p = h.toh_total * h.owp;
+    h.ntt = (ntok_p + 127) / 128;
+    h.nk64 = (ntok_p + 63) / 64;
+    const int tiles = h.ntt * h.ntt;
+    int splits = 1;
+    if (tiles < 2 * c.sms) {
+      splits = (4 * c.sms + tiles - 1) / tiles;
+      const int max_splits = (h.npos + 7) / 8;
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+    h.chunks_per_split = (h.npos + splits - 1) / splits;
+    h.splits = (h.npos + h.chunks_per_split - 1) / h.chunks_per_split;
+    h.score_work_begin = score_work;
+    score_work += tiles * h.splits;
+    h.pv_ntiles = (h.npos + 3) / 4;
+    h.pv_work_begin = pv_work;
+    pv_work += h.ntt * h.pv_ntiles;
+    h.ldS = h.ntt * 128;
+    h.ldP = h.ntt * 128;
+    h.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)dk * h.npos));
+    const size_t rows = (size_t)h.ntt * 128;
+    ws.S[s].ensure(rows * h.ldS * sizeof(float));
+    ws.P[s].ensure(rows * h.ldP * sizeof(__half));
+    ws.rowsum[s].ensure(rows * sizeof(float));
+    h.S = ws.S[s].as<float>();
+    h.P = ws.P[s].as<__half>();
+    h.rowsum = ws.rowsum[s].as<float>();
+    if ((int)rows > max_rows) max_rows = (int)rows;
+    // 5-D views {64 ch, px, ow, py, toh}
+    const uint64_t dims[5] = {64, (uint64_t)h.pw, (uint64_t)h.ow, (uint64_t)h.ph, (uint64_t)h.toh_total};
+    const uint64_t str[4] = {(uint64_t)pitch * 2, (uint64_t)h.pw * pitch * 2, (uint64_t)W * pitch * 2,
+                             (uint64_t)h.ph * W * pitch * 2};
+    const uint32_t box_qk[5] = {64, 1, (uint32_t)h.owp, 1, (uint32_t)(128 / h.owp)};
+    const uint32_t box_v[5] = {64, 1, (uint32_t)h.owp, 1, (uint32_t)(64 / h.owp)};
+    sp.qmap[s] = make_map_f16(qkv + q_off + i * dk, 5, dims, str, box_qk);
+    sp.kmap[s] = make_map_f16(qkv + k_off + i * dk, 5, dims, str, box_qk);
+    pp.vmap[s] = make_map_f16(qkv + v_off + i * dk, 5, dims, str, box_v);
+    const uint64_t pd[2] = {(uint64_t)h.ldP, (uint64_t)rows};
+    const uint64_t ps[1] = {(uint64_t)h.ldP * 2};
+    const uint32_t pb[2] = {64, 128};
+    pp.pmap[s] = make_map_f16(h.P, 2, pd, ps, pb);
+    sp.h[s] = h;
+    pp.h[s] = h;
+    // channel offset of this head in the output: stored through `head` index -> use coff table below
+    if (h.splits > 1) CK(cudaMemsetAsync(h.S, 0, rows * h.ldS * sizeof(float), c.stream));
+  }
+  sp.nheads = pp.nheads = n_patch;
+  sp.total_work = score_work;
+  pp.total_work = pv_work;
+  pp.T = T; pp.H = H; pp.W = W;
+  pp.out = out;
+  pp.out_pitch = out_pitch;
+  for (int s = 0; s < n_patch; ++s) pp.coff[s] = order[s] * dk;
+  launch_tc<ScorePolicy>(c, sp, score_work);
+  softmax_rows_kernel<<<dim3(max_rows, n_patch), 256, 0, c.stream>>>(sp);
+  CK(cudaGetLastError());
+  ++c.launches;
+  launch_tc<PVPolicy>(c, pp, pv_work);
+}
+
+// ------------------------------------------------------------------------------------------------ resize tables on device
+struct DevTaps {
+  DevBuf i0, i1, a, w0, w1;
+  int src = -1, dst = -1;
+  ResizeTaps view() const { return ResizeTaps{i0.as<int>(), i1.as<int>(), a.as<float>(), w0.as<short>(), w1.as<short>()}; }
+  void build(int src_n, int dst_n, bool vertical, cudaStream_t s) {
+    if (src_n == src && dst_n == dst) return;
+    HostTaps t = host_resize_taps(src_n, dst_n, vertical);
+    upload(i0, t.i0, s); upload(i1, t.i1, s); upload(a, t.a, s); upload(w0, t.w0, s); upload(w1, t.w1, s);
+    src = src_n; dst = dst_n;
+  }
+};
+
+}  // namespace vsr
+
+// ================================================================================================= engine
+using namespace vsr;
+
+struct vsr_sttn {
+  Ctx ctx;
+  vsr_sttn_config cfg;
+  int FH = 0, FW = 0;  // feature map (model/4)
+  std::map<std::string, std::vector<float>> host_w;
+  std::map<std::string, std::vector<int64_t>> host_shape;
+  bool ready = false;
+  // layers
+  DevBuf stem_w, stem_b;
+  ConvLayer enc2, enc3, enc4, dec0, dec2, dec4, dec6;
+  ConvLayer qkv[8], outl[8], ff0[8], ff1[8];
+  // activations
+  DevBuf strips, rgb8, e1, e2s, e3, feats16, feats32, xw16, xw32, qkvb, att16, ffn16, up1, d1, d2, up2, d3, comps, visits_d,
+      sched_d, mask_d;
+  AttnWorkspace attn;
+  DevTaps pre_x, pre_y, post_x, post_y;
+  // staged job
+  int T = 0, H = 0, W = 0, split_h = 0;
+  std::vector<std::array<int, 4>> areas;
+  std::vector<const uint8_t*> in_ptrs;
+  int staged_area = -1;
+  std::vector<int> visits_h;
+  int sched_T = -1;
+  std::vector<Window> sched;
+  DevBuf pinned_dummy;
+  uint8_t* pinned = nullptr;
+  size_t pinned_n = 0;
+  ~vsr_sttn() {
+    if (pinned) cudaFreeHost(pinned);
+    if (ctx.stream) cudaStreamDestroy(ctx.stream);
+  }
+};
+
+namespace vsr {
+
+static const float* get_w(vsr_sttn* h, const std::string& name, std::vector<int64_t> shape) {
+  auto it = h->host_w.find(name);
+  if (it == h->host_w.end()) throw Error(VSR_ERR_STATE, "missing weight tensor: " + name);
+  if (h->host_shape[name] != shape) throw Error(VSR_ERR_ARG, "unexpected shape for " + name);
+  return it->second.data();
+}
+
+static void finalize(vsr_sttn* h) {
+  CK(cudaSetDevice(h->ctx.device));
+  cudaStream_t s = h->ctx.stream;
+  // stem: [64,3,3,3] -> [tap*3+ci][co] fp32
+  {
+    const float* w = get_w(h, "encoder.0.weight", {64, 3, 3, 3});
+    const float* b = get_w(h, "encoder.0.bias", {64});
+    std::vector<float> sw(27 * 64);
+    for (int co = 0; co < 64; ++co)
+      for (int ci = 0; ci < 3; ++ci)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) sw[((ky * 3 + kx) * 3 + ci) * 64 + co] = w[((co * 3 + ci) * 3 + ky) * 3 + kx];
+    upload(h->stem_w, sw, s);
+    upload(h->stem_b, std::vector<float>(b, b + 64), s);
+  }
+  pack_conv(h->enc2, get_w(h, "encoder.2.weight", {64, 64, 3, 3}), get_w(h, "encoder.2.bias", {64}), 64, 64, 3, 1, s);
+  pack_conv_s2d(h->enc3, get_w(h, "encoder.4.weight", {128, 64, 3, 3}), get_w(h, "encoder.4.bias", {128}), 128, 64, s);
+  pack_conv(h->enc4, get_w(h, "encoder.6.weight", {256, 128, 3, 3}), get_w(h, "encoder.6.bias", {256}), 256, 128, 3, 1, s);
+  for (int b = 0; b < 8; ++b) {
+    const std::string p = "transformer." + std::to_string(b) + ".";
+    std::vector<float> w(768 * 256), bias(768);
+    const char* names[3] = {"query_embedding", "key_embedding", "value_embedding"};
+    for (int j = 0; j < 3; ++j) {
+      const float* wj = get_w(h, p + "attention." + names[j] + ".weight", {256, 256, 1, 1});
+      const float* bj = get_w(h, p + "attention." + names[j] + ".bias", {256});
+      memcpy(w.data() + (size_t)j * 256 * 256, wj, 256 * 256 * sizeof(float));
+      memcpy(bias.data() + j * 256, bj, 256 * sizeof(float));
+    }
+    pack_conv(h->qkv[b], w.data(), bias.data(), 768, 256, 1, 1, s);
+    pack_conv(h->outl[b], get_w(h, p + "attention.output_linear.0.weight", {256, 256, 3, 3}),
+              get_w(h, p + "attention.output_linear.0.bias", {256}), 256, 256, 3, 1, s);
+    pack_conv(h->ff0[b], get_w(h, p + "feed_forward.conv.0.weight", {256, 256, 3, 3}),
+              get_w(h, p + "feed_forward.conv.0.bias", {256}), 256, 256, 3, 2, s);
+    pack_conv(h->ff1[b], get_w(h, p + "feed_forward.conv.2.weight", {256, 256, 3, 3}),
+              get_w(h, p + "feed_forward.conv.2.bias", {256}), 256, 256, 3, 1, s);
+  }
+  pack_conv(h->dec0, get_w(h, "decoder.0.conv.weight", {128, 256, 3, 3}), get_w(h, "decoder.0.conv.bias", {128}), 128, 256, 3, 1, s);
+  pack_conv(h->dec2, get_w(h, "decoder.2.weight", {64, 128, 3, 3}), get_w(h, "decoder.2.bias", {64}), 64, 128, 3, 1, s);
+  pack_conv(h->dec4, get_w(h, "decoder.4.conv.weight", {64, 64, 3, 3}), get_w(h, "decoder.4.conv.bias", {64}), 64, 64, 3, 1, s);
+  pack_conv(h->dec6, get_w(h, "decoder.6.weight", {3, 64, 3, 3}), get_w(h, "decoder.6.bias", {3}), 3, 64, 3, 1, s);
+  h->host_w.clear();
+  h->host_shape.clear();
+  h->ready = true;
+}
+
+// Encoder + window loop + decoder on T strip frames already on the device as u8 [T, sh, sw, 3] BGR
+// (sttn_auto_inpaint.py:122-164).  Leaves comps [T,MH,MW,3] fp32 and visits on the device.
+static void run_network(vsr_sttn* h, int T, int sw, int sh) {
+  Ctx& c = h->ctx;
+  const int MW = h->cfg.model_w, MH = h->cfg.model_h, FH = h->FH, FW = h->FW, C = 256;
+  cudaStream_t s = c.stream;
+  REQUIRE(T >= 1, "need at least one frame");
+  if (h->sched_T != T) {
+    h->sched = host_window_schedule(T, h->cfg.neighbor_stride, h->cfg.ref_length);
+    // per window: frame_idx[32], first_visit[32]
+    std::vector<int> tab(h->sched.size() * 64, 0);
+    std::vector<int> visits(T, 0);
+    for (size_t wi = 0; wi < h->sched.size(); ++wi) {
+      REQUIRE(h->sched[wi].neighbors.size() <= 32, "neighbour window larger than 32 frames");
+      for (size_t i = 0; i < h->sched[wi].neighbors.size(); ++i) {
+        const int f = h->sched[wi].neighbors[i];
+        tab[wi * 64 + i] = f;
+        tab[wi * 64 + 32 + i] = visits[f] == 0;
+        ++visits[f];
+      }
+    }
+    upload(h->sched_d, tab, s);
+    upload(h->visits_d, visits, s);
+    h->visits_h = visits;
+    h->sched_T = T;
+  }
+  size_t maxw = 0;
+  for (auto& w : h->sched) maxw = std::max(maxw, w.neighbors.size() + w.refs.size());
+  size_t maxn = 0;
+  for (auto& w : h->sched) maxn = std::max(maxn, w.neighbors.size());
+  const size_t fpix = (size_t)FH * FW;
+  h->rgb8.ensure((size_t)T * MH * MW * 4);
+  h->e1.ensure((size_t)T * (MH / 2) * (MW / 2) * 64 * 2);
+  h->e2s.ensure((size_t)T * fpix * 256 * 2);
+  h->e3.ensure((size_t)T * fpix * 128 * 2);
+  h->feats16.ensure((size_t)T * fpix * C * 2);
+  h->feats32.ensure((size_t)T * fpix * C * 4);
+  h->xw16.ensure(maxw * fpix * C * 2);
+  h->xw32.ensure(maxw * fpix * C * 4);
+  h->qkvb.ensure(maxw * fpix * 3 * C * 2);
+  h->att16.ensure(maxw * fpix * C * 2);
+  h->ffn16.ensure(maxw * fpix * C * 2);
+  h->up1.ensure(maxn * fpix * 4 * C * 2);
+  h->d1.ensure(maxn * fpix * 4 * 128 * 2);
+  h->d2.ensure(maxn * fpix * 4 * 64 * 2);
+  h->up2.ensure(maxn * fpix * 16 * 64 * 2);
+  h->d3.ensure(maxn * fpix * 16 * 64 * 2);
+  h->comps.ensure((size_t)T * MH * MW * 3 * 4);
+
+  // A3/A4 pre-processing
+  h->pre_x.build(sw, MW, false, s);
+  h->pre_y.build(sh, MH, true, s);
+  strip_downscale_kernel<<<dim3((MW + 255) / 256, MH, T), 256, 0, s>>>(h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh,
+                                                                        h->rgb8.as<uint8_t>(), MW, MH, T, h->pre_x.view(),
+                                                                        h->pre_y.view());
+  CK(cudaGetLastError());
+  ++c.launches;
+  // A5 encoder
+  {
+    const int total = T * (MH / 2) * (MW / 2);
+    stem_conv_kernel<<<(total + 63) / 64, 256, 0, s>>>(h->rgb8.as<uchar4>(), MH, MW, h->stem_w.as<float>(), h->stem_b.as<float>(),
+                                                        h->e1.as<__half>(), total);
+    CK(cudaGetLastError());
+    ++c.launches;
+    ConvIO io;
+    io.in = h->e1.as<__half>(); io.T = T; io.H = MH / 2; io.W = MW / 2;
+    io.flags = CONV_LRELU | CONV_S2D_STORE; io.out16 = h->e2s.as<__half>();
+    run_conv(c, h->enc2, io);
+    ConvIO io3;
+    io3.in = h->e2s.as<__half>(); io3.T = T; io3.H = FH; io3.W = FW;
+    io3.flags = CONV_LRELU; io3.out16 = h->e3.as<__half>();
+    run_conv(c, h->enc3, io3);
+    ConvIO io4;
+    io4.in = h->e3.as<__half>(); io4.T = T; io4.H = FH; io4.W = FW;
+    io4.flags = CONV_LRELU; io4.out16 = h->feats16.as<__half>(); io4.out32 = h->feats32.as<float>();
+    run_conv(c, h->enc4, io4);
+  }
+  // A6-A11 window loop
+  const size_t f16b = fpix * C * 2, f32b = fpix * C * 4;
+  for (size_t wi = 0; wi < h->sched.size(); ++wi) {
+    const Window& w = h->sched[wi];
+    const int nn = (int)w.neighbors.size();
+    const int Tw = nn + (int)w.refs.size();
+    // gather feats[neighbor_ids + ref_ids] (sttn_auto_inpaint.py:148)
+    CK(cudaMemcpyAsync(h->xw16.p, h->feats16.as<uint8_t>() + (size_t)w.neighbors[0] * f16b, (size_t)nn * f16b,
+                       cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(h->xw32.p, h->feats32.as<uint8_t>() + (size_t)w.neighbors[0] * f32b, (size_t)nn * f32b,
+                       cudaMemcpyDeviceToDevice, s));
+    for (size_t r = 0; r < w.refs.size(); ++r) {
+      CK(cudaMemcpyAsync(h->xw16.as<uint8_t>() + (nn + r) * f16b, h->feats16.as<uint8_t>() + (size_t)w.refs[r] * f16b, f16b,
+                         cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(h->xw32.as<uint8_t>() + (nn + r) * f32b, h->feats32.as<uint8_t>() + (size_t)w.refs[r] * f32b, f32b,
+                         cudaMemcpyDeviceToDevice, s));
+    }
+    for (int b = 0; b < 8; ++b) {
+      // A7: Q,K,V 1x1 projections in one GEMM (auto_sttn.py:172-174)
+      ConvIO q;
+      q.in = h->xw16.as<__half>(); q.T = Tw; q.H = FH; q.W = FW; q.out16 = h->qkvb.as<__half>(); q.out16_pitch = 3 * C;
+      run_conv(c, h->qkv[b], q);
+      // A8: patch attention
+      run_attention(c, h->attn, h->qkvb.as<__half>(), 3 * C, 0, C, 2 * C, Tw, FH, FW, C, h->cfg.n_patch, h->cfg.patch_w,
+                    h->cfg.patch_h, h->att16.as<__half>(), C);
+      // output_linear + residual (auto_sttn.py:163-164, 237)
+      ConvIO o;
+      o.in = h->att16.as<__half>(); o.T = Tw; o.H = FH; o.W = FW; o.flags = CONV_LRELU | CONV_RESIDUAL;
+      o.out16 = h->xw16.as<__half>(); o.out32 = h->xw32.as<float>(); o.res32 = h->xw32.as<float>();
+      run_conv(c, h->outl[b], o);
+      // A9: feed forward + residual (auto_sttn.py:215-218, 238)
+      ConvIO f0;
+      f0.in = h->xw16.as<__half>(); f0.T = Tw; f0.H = FH; f0.W = FW; f0.flags = CONV_LRELU; f0.out16 = h->ffn16.as<__half>();
+      run_conv(c, h->ff0[b], f0);
+      ConvIO f1;
+      f1.in = h->ffn16.as<__half>(); f1.T = Tw; f1.H = FH; f1.W = FW; f1.flags = CONV_LRELU | CONV_RESIDUAL;
+      f1.out16 = h->xw16.as<__half>(); f1.out32 = h->xw32.as<float>(); f1.res32 = h->xw32.as<float>();
+      run_conv(c, h->ff1[b], f1);
+    }
+    // A10 decoder on the neighbour frames only (sttn_auto_inpaint.py:150)
+    {
+      size_t total = (size_t)nn * (2 * FH) * (2 * FW) * (C / 8);
+      upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->xw16.as<__half>(), nn, FH, FW, C, h->up1.as<__half>());
+      CK(cudaGetLastError());
+      ++c.launches;
+      ConvIO a;
+      a.in = h->up1.as<__half>(); a.T = nn; a.H = 2 * FH; a.W = 2 * FW; a.flags = CONV_LRELU; a.out16 = h->d1.as<__half>();
+      run_conv(c, h->dec0, a);
+      ConvIO b2;
+      b2.in = h->d1.as<__half>(); b2.T = nn; b2.H = 2 * FH; b2.W = 2 * FW; b2.flags = CONV_LRELU; b2.out16 = h->d2.as<__half>();
+      run_conv(c, h->dec2, b2);
+      total = (size_t)nn * (4 * FH) * (4 * FW) * (64 / 8);
+      upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->d2.as<__half>(), nn, 2 * FH, 2 * FW, 64, h->up2.as<__half>());
+      CK(cudaGetLastError());
+      ++c.launches;
+      ConvIO d;
+      d.in = h->up2.as<__half>(); d.T = nn; d.H = MH; d.W = MW; d.flags = CONV_LRELU; d.out16 = h->d3.as<__half>();
+      run_conv(c, h->dec4, d);
+      // A11: tanh + quantise + blend fused into the last conv's epilogue
+      ConvIO e;
+      e.in = h->d3.as<__half>(); e.T = nn; e.H = MH; e.W = MW; e.flags = CONV_FINAL;
+      e.comps = h->comps.as<float>();
+      e.frame_idx = h->sched_d.as<int>() + wi * 64;
+      e.first_visit = h->sched_d.as<int>() + wi * 64 + 32;
+      run_conv(c, h->dec6, e);
+    }
+  }
+}
+
+static void ensure_pinned(vsr_sttn* h, size_t bytes) {
+  if (bytes <= h->pinned_n) return;
+  if (h->pinned) CK(cudaFreeHost(h->pinned));
+  h->pinned = nullptr;
+  h->pinned_n = 0;
+  CK(cudaMallocHost(&h->pinned, bytes));
+  h->pinned_n = bytes;
+}
+
+static void check_ready(vsr_sttn* h) {
+  if (!h) throw Error(VSR_ERR_ARG, "null engine");
+  if (!h->ready) throw Error(VSR_ERR_STATE, "weights not finalized");
+  CK(cudaSetDevice(h->ctx.device));
+}
+
+static void sync_stream(vsr_sttn* h) {
+  cudaError_t e = cudaStreamSynchronize(h->ctx.stream);
+  if (e != cudaSuccess)
+    throw Error(VSR_ERR_CUDA, std::string("cudaStreamSynchronize -> ") + cudaGetErrorString(e) + device_error_report());
+}
+
+// upload strip k of the staged frames, run, composite, leave strips on device
+static void stage_area(vsr_sttn* h, int k) {
+  const int y0 = h->areas[k][0], y1 = h->areas[k][1];
+  const int sh = y1 - y0, sw = h->W;
+  const size_t sb = (size_t)sh * sw * 3;
+  h->strips.ensure(sb * h->T);
+  ensure_pinned(h, sb * h->T);
+  for (int t = 0; t < h->T; ++t) memcpy(h->pinned + t * sb, h->in_ptrs[t] + (size_t)y0 * sw * 3, sb);
+  CK(cudaMemcpyAsync(h->strips.p, h->pinned, sb * h->T, cudaMemcpyHostToDevice, h->ctx.stream));
+  h->staged_area = k;
+}
+
+static void compute_area(vsr_sttn* h, int k) {
+  const int y0 = h->areas[k][0], y1 = h->areas[k][1];
+  const int sh = y1 - y0, sw = h->W;
+  cudaStream_t s = h->ctx.stream;
+  run_network(h, h->T, sw, sh);
+  h->post_x.build(h->cfg.model_w, sw, false, s);
+  h->post_y.build(h->cfg.model_h, sh, true, s);
+  strip_composite_kernel<<<dim3((sw + 255) / 256, sh, h->T), 256, 0, s>>>(
+      h->comps.as<float>(), h->cfg.model_w, h->cfg.model_h, h->visits_d.as<int>(), h->mask_d.as<uint8_t>() + (size_t)y0 * sw, sw,
+      h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh, h->T, h->post_x.view(), h->post_y.view());
+  CK(cudaGetLastError());
+  ++h->ctx.launches;
+}
+
+static void fetch_area(vsr_sttn* h, int k, uint8_t* const* out) {
+  const int y0 = h->areas[k][0], y1 = h->areas[k][1];
+  const int sh = y1 - y0, sw = h->W;
+  const size_t sb = (size_t)sh * sw * 3;
+  CK(cudaMemcpyAsync(h->pinned, h->strips.p, sb * h->T, cudaMemcpyDeviceToHost, h->ctx.stream));
+  sync_stream(h);
+  for (int t = 0; t < h->T; ++t) memcpy(out[t] + (size_t)y0 * sw * 3, h->pinned + t * sb, sb);
+}
+
+static void stage(vsr_sttn* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask) {
+  check_ready(h);
+  REQUIRE(T >= 1 && H >= 1 && W >= 1 && frames_in && mask, "bad frame batch");
+  h->T = T; h->H = H; h->W = W;
+  h->split_h = (int)((double)W * 3 / 16);  // sttn_auto_inpaint.py:54
+  std::vector<uint8_t> m01((size_t)H * W);
+  for (size_t i = 0; i < m01.size(); ++i) m01[i] = mask[i] > 127 ? 1 : 0;  // cv2.threshold(mask,127,1,BINARY) :48
+  h->areas = host_inpaint_areas(W, H, h->split_h, m01.data(), 1);
+  h->in_ptrs.assign(frames_in, frames_in + T);
+  h->mask_d.ensure(m01.size());
+  CK(cudaMemcpyAsync(h->mask_d.p, m01.data(), m01.size(), cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  h->staged_area = -1;
+  if (!h->areas.empty()) stage_area(h, 0);
+}
+
+}  // namespace vsr
+
+// ================================================================================================= C ABI
+extern "C" {
+
+const char* vsr_last_error(void) { return g_err.c_str(); }
+const char* vsr_version(void) { return "vsr_b200 0.1 (sm_100a, tcgen05/TMA)"; }
+
+int vsr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+void vsr_sttn_default_config(vsr_sttn_config* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->model_w = 640;
+  cfg->model_h = 120;
+  cfg->n_patch = 4;
+  const int pw[4] = {80, 32, 10, 5}, ph[4] = {15, 6, 5, 3};
+  for (int i = 0; i < 4; ++i) {
+    cfg->patch_w[i] = pw[i];
+    cfg->patch_h[i] = ph[i];
+  }
+  cfg->neighbor_stride = 5;
+  cfg->ref_length = 10;
+}
+
+int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
+  return guarded([&] {
+    REQUIRE(out, "out pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      throw Error(VSR_ERR_CUDA, "no CUDA device: vsr_b200 has no CPU fallback");
+    }
+    REQUIRE(device >= 0 && device < n, "device index");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw Error(VSR_ERR_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                    "; vsr_b200 kernels are sm_100a only");
+    CK(cudaSetDevice(device));
+    auto* h = new vsr_sttn();
+    h->ctx.device = device;
+    h->ctx.sms = prop.multiProcessorCount;
+    if (cfg) h->cfg = *cfg; else vsr_sttn_default_config(&h->cfg);
+    if (h->cfg.model_w % 32 || h->cfg.model_h % 8) {
+      delete h;
+      throw Error(VSR_ERR_ARG, "model size must be a multiple of (32, 8)");
+    }
+    h->FW = h->cfg.model_w / 4;
+    h->FH = h->cfg.model_h / 4;
+    CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
+    *out = h;
+  });
+}
+
+void vsr_sttn_destroy(vsr_sttn_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->ctx.device);
+  cudaStreamSynchronize(h->ctx.stream);
+  delete h;
+}
+
+int vsr_sttn_set_weight(vsr_sttn_t* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+  return guarded([&] {
+    REQUIRE(h && name && data && shape && ndim >= 1 && ndim <= 4, "bad weight tensor");
+    size_t n = 1;
+    std::vector<int64_t> shp(shape, shape + ndim);
+    for (auto d : shp) n *= (size_t)d;
+    h->host_w[name].assign(data, data + n);
+    h->host_shape[name] = shp;
+    h->ready = false;
+  });
+}
+
+int vsr_sttn_finalize_weights(vsr_sttn_t* h) {
+  return guarded([&] {
+    REQUIRE(h, "null engine");
+    finalize(h);
+  });
+}
+
+int vsr_sttn_inpaint_strip(vsr_sttn_t* h, const uint8_t* frames_bgr, int T, float* comps_out, int32_t* visits_out) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(frames_bgr && comps_out && T >= 1, "bad arguments");
+    const int MW = h->cfg.model_w, MH = h->cfg.model_h;
+    const size_t sb = (size_t)MH * MW * 3;
+    h->strips.ensure(sb * T);
+    CK(cudaMemcpyAsync(h->strips.p, frames_bgr, sb * T, cudaMemcpyHostToDevice, h->ctx.stream));
+    run_network(h, T, MW, MH);
+    CK(cudaMemcpyAsync(comps_out, h->comps.p, sb * T * sizeof(float), cudaMemcpyDeviceToHost, h->ctx.stream));
+    sync_stream(h);
+    if (visits_out)
+      for (int t = 0; t < T; ++t) visits_out[t] = h->visits_h[t];
+  });
+}
+
+int vsr_sttn_stage(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask) {
+  return guarded([&] { stage(h, frames_in, T, H, W, mask); });
+}
+
+int vsr_sttn_compute(vsr_sttn_t* h) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(h->T > 0, "nothing staged");
+    if (h->areas.empty()) return;
+    if (h->staged_area != 0) stage_area(h, 0);
+    compute_area(h, 0);
+  });
+}
+
+int vsr_sttn_fetch(vsr_sttn_t* h, uint8_t* const* frames_out) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(h->T > 0 && frames_out, "nothing staged");
+    const size_t fb = (size_t)h->H * h->W * 3;
+    for (int t = 0; t < h->T; ++t)
+      if (frames_out[t] != h->in_ptrs[t]) memcpy(frames_out[t], h->in_ptrs[t], fb);  // the copy at sttn_auto_inpaint.py:58
+    if (h->areas.empty()) return;
+    fetch_area(h, 0, frames_out);
+    // further strips (rare: several disjoint subtitle bands) run back to back
+    for (size_t k = 1; k < h->areas.size(); ++k) {
+      stage_area(h, (int)k);
+      compute_area(h, (int)k);
+      fetch_area(h, (int)k, frames_out);
+    }
+  });
+}
+
+int vsr_sttn_inpaint_frames(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask,
+                            uint8_t* const* frames_out) {
+  int r = vsr_sttn_stage(h, frames_in, T, H, W, mask);
+  if (r) return r;
+  r = vsr_sttn_compute(h);
+  if (r) return r;
+  return vsr_sttn_fetch(h, frames_out);
+}
+
+int vsr_sttn_sync(vsr_sttn_t* h) {
+  return guarded([&] {
+    REQUIRE(h, "null engine");
+    CK(cudaSetDevice(h->ctx.device));
+    sync_stream(h);
+  });
+}
+void* vsr_sttn_stream(vsr_sttn_t* h) { return h ? (void*)h->ctx.stream : nullptr; }
+int64_t vsr_sttn_launch_count(vsr_sttn_t* h) { return h ? h->ctx.launches : 0; }
+
+int vsr_sttn_time_conv(vsr_sttn_t* h, int T, int n, float* ms_out) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(T >= 1 && n >= 1 && ms_out, "bad arguments");
+    const size_t fpix = (size_t)h->FH * h->FW;
+    h->xw16.ensure((size_t)T * fpix * 256 * 2);
+    h->ffn16.ensure((size_t)T * fpix * 256 * 2);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    ConvIO f0;
+    f0.in = h->xw16.as<__half>(); f0.T = T; f0.H = h->FH; f0.W = h->FW; f0.flags = CONV_LRELU; f0.out16 = h->ffn16.as<__half>();
+    run_conv(h->ctx, h->ff1[0], f0);  // warm-up
+    CK(cudaEventRecord(ev[0], h->ctx.stream));
+    for (int i = 0; i < n; ++i) {
+      run_conv(h->ctx, h->ff1[i % 8], f0);
+      CK(cudaEventRecord(ev[i + 1], h->ctx.stream));
+    }
+    sync_stream(h);
+    for (int i = 0; i < n; ++i) CK(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));
+    for (auto& e : ev) cudaEventDestroy(e);
+  });
+}
+
+// ---- integer path ---------------------------------------------------------------------------------
+int vsr_create_mask(uint8_t* mask, int H, int W, const int32_t* boxes, int n, int deviation) {
+  return guarded([&] {
+    REQUIRE(mask && H > 0 && W > 0 && (n == 0 || boxes), "bad arguments");
+    host_create_mask(mask, H, W, boxes, n, deviation);
+  });
+}
+int vsr_inpaint_area_by_mask(int W, int H, int hh, const uint8_t* mask, int multiple, int32_t* areas, int max_areas) {
+  int count = 0;
+  int r = guarded([&] {
+    REQUIRE(mask && H > 0 && W > 0 && hh > 0 && areas, "bad arguments");
+    auto a = host_inpaint_areas(W, H, hh, mask, multiple);
+    REQUIRE((int)a.size() <= max_areas, "areas buffer too small");
+    for (size_t i = 0; i < a.size(); ++i)
+      for (int j = 0; j < 4; ++j) areas[4 * i + j] = a[i][j];
+    count = (int)a.size();
+  });
+  return r ? r : count;
+}
+int vsr_batch_sizes(int n_samples, int max_batch_size, int32_t* sizes, int max_sizes) {
+  int count = 0;
+  int r = guarded([&] {
+    auto v = host_batch_sizes(n_samples, max_batch_size);
+    REQUIRE((int)v.size() <= max_sizes, "sizes buffer too small");
+    for (size_t i = 0; i < v.size(); ++i) sizes[i] = v[i];
+    count = (int)v.size();
+  });
+  return r ? r : count;
+}
+int vsr_window_schedule(int T, int stride, int ref_length, int32_t* ids, int32_t* n_neighbors, int32_t* n_refs, int max_windows,
+                        int max_ids_per_window) {
+  int count = 0;
+  int r = guarded([&] {
+    REQUIRE(T >= 0 && stride >= 1 && ref_length >= 1 && ids && n_neighbors && n_refs, "bad arguments");
+    auto s = host_window_schedule(T, stride, ref_length);
+    REQUIRE((int)s.size() <= max_windows, "too many windows");
+    for (size_t w = 0; w < s.size(); ++w) {
+      REQUIRE((int)(s[w].neighbors.size() + s[w].refs.size()) <= max_ids_per_window, "ids buffer too small");
+      int j = 0;
+      for (int v : s[w].neighbors) ids[w * max_ids_per_window + j++] = v;
+      for (int v : s[w].refs) ids[w * max_ids_per_window + j++] = v;
+      n_neighbors[w] = (int)s[w].neighbors.size();
+      n_refs[w] = (int)s[w].refs.size();
+    }
+    count = (int)s.size();
+  });
+  return r ? r : count;
+}
+
+// ---- operator-level entry points -------------------------------------------------------------------
+namespace {
+struct OpCtx {
+  Ctx c;
+  OpCtx(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      throw Error(VSR_ERR_CUDA, "no CUDA device: vsr_b200 has no CPU fallback");
+    }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw Error(VSR_ERR_CUDA, "vsr_b200 kernels are sm_100a only");
+    c.device = device;
+    c.sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  }
+  ~OpCtx() {
+    if (c.stream) cudaStreamDestroy(c.stream);
+  }
+  void sync() {
+    cudaError_t e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess)
+      throw Error(VSR_ERR_CUDA, std::string("cudaStreamSynchronize -> ") + cudaGetErrorString(e) + device_error_report());
+  }
+};
+static void to_half_dev(DevBuf& d, const float* src, size_t n, cudaStream_t s) {
+  std::vector<__half> hbuf(n);
+  for (size_t i = 0; i < n; ++i) hbuf[i] = __float2half_rn(src[i]);
+  upload(d, hbuf, s);
+}
+static void from_half_dev(const __half* dptr, float* dst, size_t n, cudaStream_t s) {
+  std::vector<__half> hbuf(n);
+  CK(cudaMemcpyAsync(hbuf.data(), dptr, n * 2, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < n; ++i) dst[i] = __half2float(hbuf[i]);
+}
+}  // namespace
+
+int vsr_op_resize_u8(int device, const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw) {
+  return guarded([&] {
+    OpCtx o(device);
+    REQUIRE(src && dst && sh > 0 && sw > 0 && dh > 0 && dw > 0, "bad arguments");
+    DevBuf s, d;
+    DevTaps tx, ty;
+    s.ensure((size_t)sh * sw * 3);
+    d.ensure((size_t)dh * dw * 4);
+    CK(cudaMemcpyAsync(s.p, src, (size_t)sh * sw * 3, cudaMemcpyHostToDevice, o.c.stream));
+    tx.build(sw, dw, false, o.c.stream);
+    ty.build(sh, dh, true, o.c.stream);
+    strip_downscale_kernel<<<dim3((dw + 255) / 256, dh, 1), 256, 0, o.c.stream>>>(s.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh,
+                                                                                   d.as<uint8_t>(), dw, dh, 1, tx.view(), ty.view());
+    CK(cudaGetLastError());
+    std::vector<uint8_t> rgba((size_t)dh * dw * 4);
+    CK(cudaMemcpyAsync(rgba.data(), d.p, rgba.size(), cudaMemcpyDeviceToHost, o.c.stream));
+    o.sync();
+    for (size_t i = 0; i < (size_t)dh * dw; ++i) {  // kernel writes RGB(A); give BGR back like cv2
+      dst[3 * i + 0] = rgba[4 * i + 2];
+      dst[3 * i + 1] = rgba[4 * i + 1];
+      dst[3 * i + 2] = rgba[4 * i + 0];
+    }
+  });
+}
+
+int vsr_op_conv2d(int device, const float* in, int T, int H, int W, int Cin, const float* weight, const float* bias, int Cout,
+                  int ksize, int dilation, int flags, const float* res, float* out) {
+  return guarded([&] {
+    OpCtx o(device);
+    REQUIRE(in && weight && out && T > 0 && H > 0 && W > 0, "bad arguments");
+    ConvLayer L;
+    pack_conv(L, weight, bias, Cout, Cin, ksize, dilation, o.c.stream);
+    const size_t npix = (size_t)T * H * W;
+    DevBuf din, dout16, dout32, dres;
+    to_half_dev(din, in, npix * Cin, o.c.stream);
+    dout16.ensure(npix * Cout * 2);
+    ConvIO io;
+    io.in = din.as<__half>(); io.T = T; io.H = H; io.W = W;
+    io.flags = (flags & 1 ? CONV_LRELU : 0);
+    io.out16 = dout16.as<__half>();
+    if (flags & 2) {
+      REQUIRE(res, "residual requested without tensor");
+      dres.ensure(npix * Cout * 4);
+      dout32.ensure(npix * Cout * 4);
+      CK(cudaMemcpyAsync(dres.p, res, npix * Cout * 4, cudaMemcpyHostToDevice, o.c.stream));
+      io.flags |= CONV_RESIDUAL;
+      io.res32 = dres.as<float>();
+      io.out32 = dout32.as<float>();
+    }
+    run_conv(o.c, L, io);
+    o.sync();
+    if (flags & 2) {
+      CK(cudaMemcpy(out, dout32.p, npix * Cout * 4, cudaMemcpyDeviceToHost));
+    } else {
+      from_half_dev(dout16.as<__half>(), out, npix * Cout, o.c.stream);
+    }
+  });
+}
+
+int vsr_op_conv2d_s2(int device, const float* in, int T, int H, int W, int Cin, const float* weight, const float* bias, int Cout,
+                     int flags, float* out) {
+  return guarded([&] {
+    OpCtx o(device);
+    REQUIRE(in && weight && out && T > 0 && H % 2 == 0 && W % 2 == 0, "bad arguments");
+    // host space-to-depth of the input: [T,H,W,Cin] -> [T,H/2,W/2,4*Cin]
+    const int OH = H / 2, OW = W / 2;
+    std::vector<float> s2d((size_t)T * OH * OW * 4 * Cin);
+    for (int t = 0; t < T; ++t)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+          memcpy(&s2d[((((size_t)t * OH + y / 2) * OW + x / 2) * 4 + (y & 1) * 2 + (x & 1)) * Cin],
+                 &in[(((size_t)t * H + y) * W + x) * Cin], Cin * sizeof(float));
+    ConvLayer L;
+    pack_conv_s2d(L, weight, bias, Cout, Cin, o.c.stream);
+    const size_t npix = (size_t)T * OH * OW;
+    DevBuf din, dout16;
+    to_half_dev(din, s2d.data(), s2d.size(), o.c.stream);
+    dout16.ensure(npix * Cout * 2);
+    ConvIO io;
+    io.in = din.as<__half>(); io.T = T; io.H = OH; io.W = OW;
+    io.flags = (flags & 1 ? CONV_LRELU : 0);
+    io.out16 = dout16.as<__half>();
+    run_conv(o.c, L, io);
+    o.sync();
+    from_half_dev(dout16.as<__half>(), out, npix * Cout, o.c.stream);
+  });
+}
+
+int vsr_op_patch_attention(int device, const float* q, const float* k, const float* v, int T, int H, int W, int C, int n_patch,
+                           const int32_t* pw, const int32_t* ph, float* out) {
+  return guarded([&] {
+    OpCtx o(device);
+    REQUIRE(q && k && v && out && pw && ph, "bad arguments");
+    const size_t npix = (size_t)T * H * W;
+    std::vector<float> qkv(npix * 3 * C);
+    for (size_t p = 0; p < npix; ++p) {
+      memcpy(&qkv[p * 3 * C], &q[p * C], C * sizeof(float));
+      memcpy(&qkv[p * 3 * C + C], &k[p * C], C * sizeof(float));
+      memcpy(&qkv[p * 3 * C + 2 * C], &v[p * C], C * sizeof(float));
+    }
+    DevBuf dq, dout;
+    to_half_dev(dq, qkv.data(), qkv.size(), o.c.stream);
+    dout.ensure(npix * C * 2);
+    AttnWorkspace ws;
+    int pwi[4], phi[4];
+    for (int i = 0; i < n_patch && i < 4; ++i) { pwi[i] = pw[i]; phi[i] = ph[i]; }
+    run_attention(o.c, ws, dq.as<__half>(), 3 * C, 0, C, 2 * C, T, H, W, C, n_patch, pwi, phi, dout.as<__half>(), C);
+    o.sync();
+    from_half_dev(dout.as<__half>(), out, npix * C, o.c.stream);
+  });
+}
+
+int vsr_op_upsample2x(int device, const float* in, int T, int H, int W, int C, float* out) {
+  return guarded([&] {
+    OpCtx o(device);
+    REQUIRE(in && out && C % 8 == 0, "bad arguments");
+    const size_t npix = (size_t)T * H * W;
+    DevBuf din, dout;
+    to_half_dev(din, in, npix * C, o.c.stream);
+    dout.ensure(npix * 4 * C * 2);
+    const size_t total = npix * 4 * (C / 8);
+    upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, o.c.stream>>>(din.as<__half>(), T, H, W, C, dout.as<__half>());
+    CK(cudaGetLastError());
+    o.sync();
+    from_half_dev(dout.as<__half>(), out, npix * 4 * C, o.c.stream);
+  });
+}
+
+}  // extern "C"

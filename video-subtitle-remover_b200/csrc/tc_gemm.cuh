@@ -1,0 +1,140 @@
+// Persistent warp-specialised tcgen05 GEMM skeleton (one CTA per SM, 192 threads):
+//   warp 0  lane 0 : TMA producer      (full/empty mbarrier ring over STAGES smem stages)
+//   warp 1  lane 0 : MMA issuer        (tcgen05.mma, accumulators double-buffered in TMEM)
+//   warps 2..5     : epilogue          (tcgen05.ld -> registers -> policy epilogue -> global)
+// A tile is always 128 rows (UMMA M = 128, one TMEM lane per row) x 64 fp16 of K per stage
+// (one SWIZZLE_128B row per tile row).  The policy P supplies the problem-specific parts:
+//   P::BN, P::STAGES, P::B_MN_MAJOR, P::Params, P::Tile
+//   P::num_tiles(prm), P::get_tile(prm, idx)            -> Tile (with .num_k and .n_cols)
+//   P::load(prm, tile, k, sA, sB, bar)                  -> issue TMA + expect_tx for k-chunk k
+//   P::epilogue(prm, tile, row, col0, v[32], ncols)     -> consume 32 (or 16) accumulator columns
+#pragma once
+#include "tc_common.cuh"
+
+namespace vsr {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = 128 * 128;  // 128 rows x 128 B
+
+template <class P>
+constexpr int tc_smem_bytes() {
+  return P::STAGES * (TC_A_BYTES + P::BN * 128) + 1024;
+}
+
+enum : uint32_t { ERR_PRODUCER = 0x100, ERR_MMA_FULL = 0x200, ERR_MMA_TEMPTY = 0x300, ERR_EPI = 0x400 };
+
+template <class P>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ typename P::Params prm) {
+  constexpr int BN = P::BN;
+  constexpr int STAGES = P::STAGES;
+  constexpr uint32_t STAGE_BYTES = TC_A_BYTES + BN * 128;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    P::prefetch(prm);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int ntiles = P::num_tiles(prm);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const typename P::Tile tile = P::get_tile(prm, t);
+        for (int k = 0; k < tile.num_k; ++k) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
+          const uint32_t sA = smem_base + stage * STAGE_BYTES;
+          P::load(prm, tile, k, sA, sA + TC_A_BYTES, smem_u32(&bar_full[stage]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const typename P::Tile tile = P::get_tile(prm, t);
+        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t idesc = umma_idesc_f16(128, BN, 0, P::B_MN_MAJOR);
+        for (int k = 0; k < tile.num_k; ++k) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase, ERR_MMA_FULL | stage);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * STAGE_BYTES;
+          const uint32_t sB = sA + TC_A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // 4 x UMMA_K(16) = 64
+            const uint64_t adesc = umma_desc_sw128(sA + kk * 32, 16, 1024);
+            const uint64_t bdesc = P::B_MN_MAJOR ? umma_desc_sw128(sB + kk * 2048, 8192, 1024)
+                                                 : umma_desc_sw128(sB + kk * 32, 16, 1024);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (k | kk) != 0);
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&bar_tfull[as]));  // accumulator ready for the epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const uint32_t row = quarter * 32 + lane;
+    uint32_t as = 0, aphase = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const typename P::Tile tile = P::get_tile(prm, t);
+      mbar_wait(smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
+      typename P::RowCtx ctx = P::row_begin(prm, tile, row);
+      if constexpr (BN >= 32) {
+        for (int c = 0; c < tile.n_cols; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          P::epilogue(prm, tile, ctx, row, c, v);
+        }
+      } else {
+        float v[32];
+        tmem_ld16(taddr, v);
+        P::epilogue(prm, tile, ctx, row, 0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace vsr

@@ -1,0 +1,273 @@
+"""Host-side mirror of backend/inpaint/sttn_auto_inpaint.py on top of the C-ABI engine.
+
+`STTNInpaint` and `STTNAutoInpaint` keep the reference's constructor signatures, call conventions and
+hyper-parameter sources (config.sttnNeighborStride / sttnReferenceLength / getSttnMaxLoadNum read at
+construction, sttn_auto_inpaint.py:40-41,195); everything between "list of BGR frames + mask" and
+"list of BGR frames" runs on the B200 through include/vsr_b200.h.  There is no CPU path.
+"""
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _capi
+from .config import config
+from .inpaint_tools import get_inpaint_area_by_mask, window_schedule
+
+
+def _device_index(device) -> int:
+    """Accepts torch.device('cuda:0') (what HardwareAccelerator.device hands out), 'cuda:1', or an int."""
+    if isinstance(device, int):
+        return device
+    idx = getattr(device, "index", None)
+    typ = getattr(device, "type", None)
+    if typ is not None:
+        if typ != "cuda":
+            raise _capi.VsrError(f"vsr_b200 runs on CUDA sm_100a only; got device '{device}' (no CPU fallback)")
+        return 0 if idx is None else int(idx)
+    s = str(device)
+    if s.startswith("cuda"):
+        return int(s.split(":")[1]) if ":" in s else 0
+    raise _capi.VsrError(f"vsr_b200 runs on CUDA sm_100a only; got device '{device}' (no CPU fallback)")
+
+
+def load_state_dict(model_path) -> Dict[str, np.ndarray]:
+    """ckpt['netG'] of the reference checkpoint (sttn_auto_inpaint.py:34), an .npz, or a ready dict."""
+    if isinstance(model_path, dict):
+        sd = model_path
+    elif str(model_path).endswith(".npz"):
+        z = np.load(model_path)
+        sd = {k: z[k] for k in z.files}
+    else:
+        import torch  # unpickling only
+
+        sd = torch.load(model_path, map_location="cpu", weights_only=False)
+        sd = sd["netG"] if "netG" in sd else sd
+    out = {}
+    for k, v in sd.items():
+        if hasattr(v, "detach"):
+            v = v.detach().cpu().float().numpy()
+        out[k] = np.ascontiguousarray(v, dtype=np.float32)
+    return out
+
+
+class STTNInpaint:
+    """Drop-in for backend/inpaint/sttn_auto_inpaint.py:28 `STTNInpaint`."""
+
+    def __init__(self, device, model_path):
+        self.device = device
+        self._dev = _device_index(device)
+        self.model_input_width, self.model_input_height = 640, 120  # :38
+        self.neighbor_stride = config.sttnNeighborStride.value      # :40
+        self.ref_length = config.sttnReferenceLength.value          # :41
+        L = _capi.lib()
+        cfg = _capi.Config()
+        L.vsr_sttn_default_config(C.byref(cfg))
+        cfg.neighbor_stride = int(self.neighbor_stride)
+        cfg.ref_length = int(self.ref_length)
+        h = C.c_void_p()
+        _capi.check(L.vsr_sttn_create(C.byref(h), self._dev, C.byref(cfg)))
+        self._h = h
+        for name, arr in load_state_dict(model_path).items():
+            if not (name.startswith("encoder.") or name.startswith("decoder.") or name.startswith("transformer.")):
+                continue
+            shape = np.asarray(arr.shape, dtype=np.int64)
+            _capi.check(L.vsr_sttn_set_weight(self._h, name.encode(), _capi.ptr(arr, C.c_float), _capi.ptr(shape, C.c_int64),
+                                              arr.ndim))
+        _capi.check(L.vsr_sttn_finalize_weights(self._h))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _capi.lib().vsr_sttn_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- reference API -------------------------------------------------------------------------
+    def __call__(self, input_frames: List[np.ndarray], input_mask: np.ndarray) -> List[np.ndarray]:
+        """sttn_auto_inpaint.py:43-97: BGR uint8 frames [H,W,3] + mask [H,W] (0/255) -> new frames."""
+        if len(input_frames) == 0:
+            return []
+        outs = [np.empty_like(np.ascontiguousarray(f, dtype=np.uint8)) for f in input_frames]
+        self._run(input_frames, input_mask, outs)
+        return outs
+
+    def inpaint_inplace(self, frames: Sequence[np.ndarray], input_mask: np.ndarray) -> None:
+        """Same computation writing the result strips into `frames` themselves (what the chunk loop of
+        STTNAutoInpaint.__call__ does with `frames_hr`, sttn_auto_inpaint.py:299-315)."""
+        if len(frames):
+            self._run(frames, input_mask, frames)
+
+    def inpaint(self, frames: List[np.ndarray]):
+        """sttn_auto_inpaint.py:122-164 on already-scaled strip frames [120,640,3] BGR.  Returns comps in
+        RGB: uint8 for frames decoded once, float32 (running 0.5/0.5 blend) otherwise."""
+        T = len(frames)
+        x = np.ascontiguousarray(np.stack(frames), dtype=np.uint8)
+        if x.shape[1:] != (self.model_input_height, self.model_input_width, 3):
+            raise ValueError(f"strip frames must be {(self.model_input_height, self.model_input_width, 3)}, got {x.shape[1:]}")
+        comps = np.empty(x.shape, np.float32)
+        visits = np.zeros(T, np.int32)
+        _capi.check(_capi.lib().vsr_sttn_inpaint_strip(self._h, _capi.ptr(x, C.c_uint8), T, _capi.ptr(comps, C.c_float),
+                                                       _capi.ptr(visits, C.c_int32)))
+        return [comps[i].astype(np.uint8) if visits[i] <= 1 else comps[i] for i in range(T)]
+
+    def get_ref_index(self, neighbor_ids, length):
+        """sttn_auto_inpaint.py:107-120."""
+        return [i for i in range(0, length, self.ref_length) if i not in neighbor_ids]
+
+    @staticmethod
+    def read_mask(path):
+        """sttn_auto_inpaint.py:99-105."""
+        import cv2
+
+        img = cv2.imread(path, 0)
+        _, img = cv2.threshold(img, 127, 1, cv2.THRESH_BINARY)
+        return img[:, :, None]
+
+    # ---- engine plumbing -----------------------------------------------------------------------
+    def _ptr_array(self, frames):
+        arr = (C.c_void_p * len(frames))()
+        keep = []
+        for i, f in enumerate(frames):
+            if not (isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.flags["C_CONTIGUOUS"]):
+                raise ValueError("frames must be C-contiguous uint8 arrays")
+            keep.append(f)
+            arr[i] = f.ctypes.data
+        return arr, keep
+
+    def _check_batch(self, frames, mask):
+        H, W = frames[0].shape[:2]
+        for f in frames:
+            if f.shape != (H, W, 3):
+                raise ValueError("all frames must share one [H,W,3] shape")
+        m = np.asarray(mask)
+        if m.ndim == 3:
+            m = m[:, :, 0]
+        if m.shape != (H, W):
+            raise ValueError(f"mask shape {m.shape} != frame shape {(H, W)}")
+        return H, W, np.ascontiguousarray(m, dtype=np.uint8)
+
+    def _run(self, frames_in, mask, frames_out):
+        frames_in = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames_in]
+        H, W, m = self._check_batch(frames_in, mask)
+        pin, keep_in = self._ptr_array(frames_in)
+        pout, keep_out = self._ptr_array(list(frames_out))
+        L = _capi.lib()
+        _capi.check(L.vsr_sttn_inpaint_frames(self._h, C.cast(pin, C.POINTER(C.c_void_p)), len(frames_in), H, W,
+                                              _capi.ptr(m, C.c_uint8), C.cast(pout, C.POINTER(C.c_void_p))))
+
+    # split form used by bench.py
+    def stage(self, frames_in, mask):
+        frames_in = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames_in]
+        H, W, m = self._check_batch(frames_in, mask)
+        pin, keep = self._ptr_array(frames_in)
+        self._staged = (pin, keep, m)
+        _capi.check(_capi.lib().vsr_sttn_stage(self._h, C.cast(pin, C.POINTER(C.c_void_p)), len(frames_in), H, W,
+                                               _capi.ptr(m, C.c_uint8)))
+
+    def compute(self):
+        _capi.check(_capi.lib().vsr_sttn_compute(self._h))
+
+    def fetch(self, frames_out):
+        pout, keep = self._ptr_array(list(frames_out))
+        _capi.check(_capi.lib().vsr_sttn_fetch(self._h, C.cast(pout, C.POINTER(C.c_void_p))))
+
+    def sync(self):
+        _capi.check(_capi.lib().vsr_sttn_sync(self._h))
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(_capi.lib().vsr_sttn_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(_capi.lib().vsr_sttn_launch_count(self._h))
+
+    def time_conv(self, T: int, n: int) -> np.ndarray:
+        ms = np.zeros(n, np.float32)
+        _capi.check(_capi.lib().vsr_sttn_time_conv(self._h, T, n, _capi.ptr(ms, C.c_float)))
+        return ms
+
+
+def _in_ab_sections(frame_no, ab_sections) -> bool:
+    """backend/tools/inpaint_tools.py:303-321."""
+    if not ab_sections:
+        return True
+    return any(frame_no in s for s in ab_sections)
+
+
+class STTNAutoInpaint:
+    """Drop-in for backend/inpaint/sttn_auto_inpaint.py:167 `STTNAutoInpaint` (whole-video driver)."""
+
+    def __init__(self, device, model_path, video_path, mask_path=None, clip_gap=None):
+        self.sttn_inpaint = STTNInpaint(device, model_path)
+        self.video_path = video_path
+        self.mask_path = mask_path
+        self.video_out_path = os.path.join(os.path.dirname(os.path.abspath(self.video_path)),
+                                           f"{os.path.basename(self.video_path).rsplit('.', 1)[0]}_no_sub.mp4")
+        self.clip_gap = config.getSttnMaxLoadNum() if clip_gap is None else clip_gap  # :194-197
+
+    def read_frame_info_from_video(self):
+        import cv2
+
+        reader = cv2.VideoCapture(self.video_path)
+        info = {"W_ori": int(reader.get(cv2.CAP_PROP_FRAME_WIDTH) + 0.5), "H_ori": int(reader.get(cv2.CAP_PROP_FRAME_HEIGHT) + 0.5),
+                "fps": reader.get(cv2.CAP_PROP_FPS), "len": int(reader.get(cv2.CAP_PROP_FRAME_COUNT) + 0.5)}
+        return reader, info
+
+    def __call__(self, input_mask=None, input_sub_remover=None, tbar=None):
+        """sttn_auto_inpaint.py:199-336.  Chunks of clip_gap frames are independent (:242-245); frames
+        outside the A/B sections pass through untouched; the writer receives every frame in order."""
+        import cv2
+
+        reader = writer = None
+        try:
+            reader, info = self.read_frame_info_from_video()
+            if input_sub_remover is not None:
+                ab_sections = input_sub_remover.ab_sections
+                writer = input_sub_remover.video_writer
+            else:
+                ab_sections = None
+                writer = cv2.VideoWriter(self.video_out_path, cv2.VideoWriter_fourcc(*"mp4v"), info["fps"],
+                                         (info["W_ori"], info["H_ori"]))
+            if input_mask is None:
+                mask = self.sttn_inpaint.read_mask(self.mask_path)[:, :, 0] * 255
+            else:
+                mask = input_mask
+            n, gap = info["len"], self.clip_gap
+            for start in range(0, n, gap):
+                end = min(start + gap, n)
+                frames = []
+                for j in range(start, end):
+                    ok, image = reader.read()
+                    if not ok:
+                        print(f"Warning: Failed to read frame {j}.")
+                        break
+                    frames.append(image)
+                if not frames:
+                    print(f"Warning: No valid frames found in range {start + 1}-{end}. Skipping this segment.")
+                    continue
+                gui = input_sub_remover is not None and getattr(input_sub_remover, "gui_mode", False)
+                originals = [f.copy() for f in frames] if gui else None
+                sel = [i for i in range(len(frames)) if _in_ab_sections(start + i, ab_sections)]
+                if sel:
+                    self.sttn_inpaint.inpaint_inplace([frames[i] for i in sel], mask)
+                for i, frame in enumerate(frames):
+                    writer.write(frame)
+                    if input_sub_remover is not None:
+                        if tbar is not None:
+                            input_sub_remover.update_progress(tbar, increment=1)
+                        if gui:
+                            input_sub_remover.update_preview_with_comp(originals[i], frame)
+        except _capi.VsrError:
+            raise  # engine / CUDA failures are never swallowed
+        except Exception as e:  # the reference prints and carries on (:329-331)
+            print(f"Error during video processing: {str(e)}")
+        finally:
+            if reader is not None:
+                reader.release()
+            if writer is not None:
+                writer.release()
