@@ -80,6 +80,10 @@ int64_t vsr_sttn_launch_count(vsr_sttn_t* h);
  * of n back-to-back launches of the transformer-block 3x3 conv (tcgen05 implicit GEMM) on T frames. */
 int vsr_sttn_time_conv(vsr_sttn_t* h, int T, int n, float* ms_out);
 
+/* Debug/parity hook: copy an internal activation buffer (NHWC, converted to fp32) to the host.
+ * name in {e1,e2s,e3,feats16,feats32,xw16,xw32,att16,comps}; contents are those left by the last compute. */
+int vsr_sttn_debug_read(vsr_sttn_t* h, const char* name, float* out, int64_t n);
+
 /* ---- integer mask / index path (host C++, bit-exact) ------------------------------------------ */
 /* create_mask (backend/tools/inpaint_tools.py:31-47): boxes = n x (xmin,xmax,ymin,ymax). */
 int vsr_create_mask(uint8_t* mask, int H, int W, const int32_t* boxes, int n, int deviation);

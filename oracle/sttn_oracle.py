@@ -283,13 +283,14 @@ def weight_shapes() -> Dict[str, Tuple[int, ...]]:
 
 def random_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
     """Seeded random-init weights of the sttn-auto architecture (numpy RNG so the same tensors can be
-    rebuilt anywhere).  Scale is fan-in normalised so activations stay O(1) through 8 blocks."""
+    rebuilt anywhere).  Gain 1/sqrt(fan_in): the decoded images use the full 0..255 range (std ~44) while the
+    features stay < 64, so the random network is a meaningful, if chaotic, parity target."""
     rng = np.random.default_rng(seed)
     out = {}
     for name, shape in weight_shapes().items():
         if name.endswith(".weight"):
             fan_in = shape[1] * shape[2] * shape[3]
-            w = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.7 / math.sqrt(fan_in))
+            w = rng.standard_normal(shape, dtype=np.float32) * np.float32(1.0 / math.sqrt(fan_in))
         else:
             w = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.05)
         out[name] = torch.from_numpy(w)

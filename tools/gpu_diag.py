@@ -135,7 +135,10 @@ def strip_case(name, T, real=False):
     t0 = time.time()
     got = eng.inpaint([s.copy() for s in strip])
     t1 = time.time()
-    want = O.inpaint_strip(w, strip)
+    taps = {}
+    want = O.inpaint_strip(w, strip, taps=taps)
+    enc = taps["encoder"].permute(0, 2, 3, 1).numpy()
+    report(name + ":encoder(feats32)", eng.debug_read("feats32", enc.shape), enc, 4e-3)
     g = np.stack([c.astype(np.float32) for c in got])
     wv = np.stack([c.astype(np.float32) for c in want])
     print(json.dumps(dict(case=name, gpu_s=t1 - t0, psnr=O.psnr_u8(g, wv), launches=eng.launch_count,
@@ -183,7 +186,10 @@ CASES = {
 
 
 def main():
-    if len(sys.argv) > 1:
+    only = None
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":
+        only = sys.argv[2].split(",")
+    elif len(sys.argv) > 1:
         name = sys.argv[1]
         ok = CASES[name](name)
         sys.exit(0 if ok else 1)
@@ -191,6 +197,8 @@ def main():
     log = open(os.path.join(ROOT, "gpurun_out", "diag.log"), "w")
     summary = {}
     for name in CASES:
+        if only and not any(name.startswith(o) for o in only):
+            continue
         t0 = time.time()
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True, timeout=240)

@@ -12,7 +12,7 @@ namespace vsr {
 
 enum ConvFlags : int {
   CONV_LRELU = 1,      // LeakyReLU(0.2) after bias
-  CONV_RESIDUAL = 2,   // out32 = res32 + act ; out16 = fp16(out32)
+  CONV_RESIDUAL = 2,   // act += res32 (fp32) before the stores; out32 (if set) gets the fp32 value, out16 its fp16 rounding
   CONV_S2D_STORE = 4,  // store out16 space-to-depth: [T, H/2, W/2, 4*Cout], channel = (y&1)*2*Cout + (x&1)*Cout + c
   CONV_FINAL = 8,      // decoder.6: tanh -> (x+1)/2*255 -> trunc u8 -> first visit store / 0.5-0.5 blend into comps
 };
@@ -119,15 +119,18 @@ struct ConvPolicy {
       }
       return;
     }
-    if (p.flags & CONV_RESIDUAL) {
-      const float* r = p.res32 + c.pix * p.cout + ch0;
+    if (p.out32) {
       float* o = p.out32 + c.pix * p.cout + ch0;
+      if (p.flags & CONV_RESIDUAL) {
+        const float* r = p.res32 + c.pix * p.cout + ch0;
 #pragma unroll
-      for (int i = 0; i < NV; i += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(r + i);
-        v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
-        *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < NV; i += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(r + i);
+          v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+        }
       }
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
     if (p.out16) {
       __half* o;

@@ -886,6 +886,35 @@ int vsr_sttn_sync(vsr_sttn_t* h) {
 void* vsr_sttn_stream(vsr_sttn_t* h) { return h ? (void*)h->ctx.stream : nullptr; }
 int64_t vsr_sttn_launch_count(vsr_sttn_t* h) { return h ? h->ctx.launches : 0; }
 
+int vsr_sttn_debug_read(vsr_sttn_t* h, const char* name, float* out, int64_t n) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(name && out && n > 0, "bad arguments");
+    sync_stream(h);
+    const std::string nm(name);
+    const DevBuf* b = nullptr;
+    bool is_half = true;
+    if (nm == "e1") b = &h->e1;
+    else if (nm == "e2s") b = &h->e2s;
+    else if (nm == "e3") b = &h->e3;
+    else if (nm == "feats16") b = &h->feats16;
+    else if (nm == "xw16") b = &h->xw16;
+    else if (nm == "att16") b = &h->att16;
+    else if (nm == "feats32") { b = &h->feats32; is_half = false; }
+    else if (nm == "xw32") { b = &h->xw32; is_half = false; }
+    else if (nm == "comps") { b = &h->comps; is_half = false; }
+    else throw Error(VSR_ERR_ARG, "unknown debug buffer " + nm);
+    REQUIRE((size_t)n * (is_half ? 2 : 4) <= b->n, "debug read larger than the buffer");
+    if (is_half) {
+      std::vector<__half> tmp((size_t)n);
+      CK(cudaMemcpy(tmp.data(), b->p, (size_t)n * 2, cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < n; ++i) out[i] = __half2float(tmp[i]);
+    } else {
+      CK(cudaMemcpy(out, b->p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+  });
+}
+
 int vsr_sttn_time_conv(vsr_sttn_t* h, int T, int n, float* ms_out) {
   return guarded([&] {
     check_ready(h);

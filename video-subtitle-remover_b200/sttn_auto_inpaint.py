@@ -186,6 +186,11 @@ class STTNInpaint:
     def launch_count(self) -> int:
         return int(_capi.lib().vsr_sttn_launch_count(self._h))
 
+    def debug_read(self, name: str, shape) -> np.ndarray:
+        out = np.empty(shape, np.float32)
+        _capi.check(_capi.lib().vsr_sttn_debug_read(self._h, name.encode(), _capi.ptr(out, C.c_float), out.size))
+        return out
+
     def time_conv(self, T: int, n: int) -> np.ndarray:
         ms = np.zeros(n, np.float32)
         _capi.check(_capi.lib().vsr_sttn_time_conv(self._h, T, n, _capi.ptr(ms, C.c_float)))
