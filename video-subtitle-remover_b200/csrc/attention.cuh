@@ -9,7 +9,8 @@
 // into one box {64,1,owp,1,128/owp}.  owp = ow rounded up to a power of two; the padded token index is
 // kp = toh*owp + owi (pad slots are zero-filled by TMA and masked in the softmax).
 //
-//   scores : S[qp, kp]   = sum_pos Q_pos[qp,:] . K_pos[kp,:]          (fp32, split-K where tiles are few)
+//   scores : S[qp, kp]   = sum_pos Q_pos[qp,:] . K_pos[kp,:]          (fp32; split-K where tiles are few: each
+//            split writes its own slab and the softmax adds the slabs in a fixed order -> deterministic)
 //   softmax: P[qp, kp]   = exp((S - rowmax) / sqrt(D)) (fp16, un-normalised), rowsum[qp]
 //   pv     : O[qp, pos,:] = (sum_kp P[qp,kp] V_pos[kp,:]) / rowsum[qp]  -> written back in NHWC
 #pragma once
@@ -27,6 +28,7 @@ struct AttnHead {
   int score_work_begin, pv_work_begin;
   int pv_ntiles;   // ceil(npos / 4)
   int ldS, ldP;    // row pitches (elements)
+  long long slabS; // elements between split-K slabs of S (ntt*128*ldS)
   float scale_log2e;  // log2(e) / sqrt(64*ph*pw)
   float* S;
   __half* P;
@@ -46,7 +48,7 @@ struct ScorePolicy {
   using Params = ScoreParams;
   struct Tile {
     int num_k, n_cols;
-    int head, qi, kj, kbeg, atomic;
+    int head, qi, kj, kbeg, split;
   };
   struct RowCtx {
     float* dst;
@@ -72,7 +74,7 @@ struct ScorePolicy {
     t.kbeg = sp * h.chunks_per_split;
     t.num_k = min(h.chunks_per_split, h.npos - t.kbeg);
     t.n_cols = BN;
-    t.atomic = h.splits > 1;
+    t.split = sp;
     return t;
   }
   __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
@@ -87,18 +89,13 @@ struct ScorePolicy {
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
     const AttnHead& h = p.h[t.head];
     RowCtx c;
-    c.dst = h.S + (size_t)(t.qi * 128 + row) * h.ldS + t.kj * 128;
+    c.dst = h.S + (size_t)t.split * h.slabS + (size_t)(t.qi * 128 + row) * h.ldS + t.kj * 128;
     return c;
   }
   __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
     float* d = c.dst + col0;
-    if (t.atomic) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(d + i, v[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
 };
 
@@ -116,6 +113,15 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
   const int nvalid = h.toh_total * h.owp;
   __shared__ float red[8];
   float m = -INFINITY;
+  if (h.splits > 1) {  // fold the split-K slabs into slab 0 (fixed order)
+    float* s0 = h.S + (size_t)qp * h.ldS;
+    for (int c = threadIdx.x; c < nvalid; c += 256) {
+      float acc = s0[c];
+      for (int sp = 1; sp < h.splits; ++sp) acc += s0[(size_t)sp * h.slabS + c];
+      s0[c] = acc;
+    }
+    __syncthreads();
+  }
   for (int c = threadIdx.x; c < nvalid; c += 256) {
     if ((c % h.owp) < h.ow) m = fmaxf(m, s[c]);
   }

@@ -364,7 +364,8 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     h.ldP = h.ntt * 128;
     h.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)dk * h.npos));
     const size_t rows = (size_t)h.ntt * 128;
-    ws.S[s].ensure(rows * h.ldS * sizeof(float));
+    h.slabS = (long long)rows * h.ldS;
+    ws.S[s].ensure((size_t)h.splits * rows * h.ldS * sizeof(float));
     ws.P[s].ensure(rows * h.ldP * sizeof(__half));
     ws.rowsum[s].ensure(rows * sizeof(float));
     h.S = ws.S[s].as<float>();
@@ -387,7 +388,6 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     sp.h[s] = h;
     pp.h[s] = h;
     // channel offset of this head in the output: stored through `head` index -> use coff table below
-    if (h.splits > 1) CK(cudaMemsetAsync(h.S, 0, rows * h.ldS * sizeof(float), c.stream));
   }
   sp.nheads = pp.nheads = n_patch;
   sp.total_work = score_work;
