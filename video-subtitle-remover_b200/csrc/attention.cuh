@@ -42,13 +42,13 @@ struct ScoreParams {
 };
 
 struct ScorePolicy {
-  static constexpr int BN = 128;
-  static constexpr int STAGES = 6;
+  static constexpr int BN = 256;  // two 128-token key tiles per CTA tile: 96 B/clk of operand fill instead of 128
+  static constexpr int STAGES = 4;
   static constexpr int B_MN_MAJOR = 0;
   using Params = ScoreParams;
   struct Tile {
     int num_k, n_cols;
-    int head, qi, kj, kbeg, split;
+    int head, qi, kj, kbeg, split, nkt;  // nkt = key tiles (1 or 2) in this CTA tile
   };
   struct RowCtx {
     float* dst;
@@ -69,11 +69,13 @@ struct ScorePolicy {
     t.head = hd;
     const int sp = idx % h.splits;
     idx /= h.splits;
-    t.kj = idx % h.ntt;
-    t.qi = idx / h.ntt;
+    const int nkt2 = (h.ntt + 1) >> 1;
+    t.kj = idx % nkt2;
+    t.qi = idx / nkt2;
     t.kbeg = sp * h.chunks_per_split;
     t.num_k = min(h.chunks_per_split, h.npos - t.kbeg);
-    t.n_cols = BN;
+    t.nkt = min(2, h.ntt - 2 * t.kj);
+    t.n_cols = 128 * t.nkt;
     t.split = sp;
     return t;
   }
@@ -82,14 +84,15 @@ struct ScorePolicy {
     const int pos = t.kbeg + k;
     const int py = pos / h.pw, px = pos - py * h.pw;
     const int rows = 128 / h.owp;
-    mbar_expect_tx(bar, 2 * TC_A_BYTES);
+    mbar_expect_tx(bar, (uint32_t)((1 + t.nkt) * TC_A_BYTES));
     tma_load_5d(sA, &p.qmap[t.head], bar, 0, px, 0, py, t.qi * rows);
-    tma_load_5d(sB, &p.kmap[t.head], bar, 0, px, 0, py, t.kj * rows);
+    tma_load_5d(sB, &p.kmap[t.head], bar, 0, px, 0, py, (2 * t.kj) * rows);
+    if (t.nkt == 2) tma_load_5d(sB + TC_A_BYTES, &p.kmap[t.head], bar, 0, px, 0, py, (2 * t.kj + 1) * rows);
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
     const AttnHead& h = p.h[t.head];
     RowCtx c;
-    c.dst = h.S + (size_t)t.split * h.slabS + (size_t)(t.qi * 128 + row) * h.ldS + t.kj * 128;
+    c.dst = h.S + (size_t)t.split * h.slabS + (size_t)(t.qi * 128 + row) * h.ldS + t.kj * 256;
     return c;
   }
   __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
@@ -99,8 +102,10 @@ struct ScorePolicy {
   }
 };
 
-// One block per (padded) query row.  Invalid rows (pad slots) are skipped: they only feed accumulator
-// rows that the PV epilogue never stores.  Pad *columns* get P = 0.
+// One block per (padded) query row; the row is read once (float4, coalesced) and kept in registers.
+// Invalid rows (pad slots) are skipped: they only feed accumulator rows that the PV epilogue never
+// stores.  Pad *columns* get P = 0.  NV4 = float4 per thread (row length <= 1024*NV4).
+template <int NV4>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
   const AttnHead& h = p.h[blockIdx.y];
   const int qp = blockIdx.x;
@@ -109,21 +114,28 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
   if (owi >= h.ow || toh >= h.toh_total) return;
   const float* s = h.S + (size_t)qp * h.ldS;
   __half* pr = h.P + (size_t)qp * h.ldP;
-  const int ncols = h.nk64 * 64;
+  const int ncols = h.nk64 * 64;               // multiple of 64
   const int nvalid = h.toh_total * h.owp;
+  const int owm = h.owp - 1, ow = h.ow;
   __shared__ float red[8];
+  float4 v[NV4];
   float m = -INFINITY;
-  if (h.splits > 1) {  // fold the split-K slabs into slab 0 (fixed order)
-    float* s0 = h.S + (size_t)qp * h.ldS;
-    for (int c = threadIdx.x; c < nvalid; c += 256) {
-      float acc = s0[c];
-      for (int sp = 1; sp < h.splits; ++sp) acc += s0[(size_t)sp * h.slabS + c];
-      s0[c] = acc;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = (i * 256 + threadIdx.x) * 4;
+    v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (c < ncols) {
+      float4 a = *reinterpret_cast<const float4*>(s + c);
+      for (int sp = 1; sp < h.splits; ++sp) {  // split-K slabs, fixed order -> deterministic
+        const float4 b = *reinterpret_cast<const float4*>(s + (size_t)sp * h.slabS + c);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      v[i].x = (c + 0 < nvalid && ((c + 0) & owm) < ow) ? a.x : -INFINITY;
+      v[i].y = (c + 1 < nvalid && ((c + 1) & owm) < ow) ? a.y : -INFINITY;
+      v[i].z = (c + 2 < nvalid && ((c + 2) & owm) < ow) ? a.z : -INFINITY;
+      v[i].w = (c + 3 < nvalid && ((c + 3) & owm) < ow) ? a.w : -INFINITY;
+      m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
     }
-    __syncthreads();
-  }
-  for (int c = threadIdx.x; c < nvalid; c += 256) {
-    if ((c % h.owp) < h.ow) m = fmaxf(m, s[c]);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -134,12 +146,21 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
   for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
   __syncthreads();
   float sum = 0.f;
-  for (int c = threadIdx.x; c < ncols; c += 256) {
-    float e = 0.f;
-    if (c < nvalid && (c % h.owp) < h.ow) e = exp2f((s[c] - m) * h.scale_log2e);
-    const __half eh = __float2half_rn(e);
-    pr[c] = eh;
-    sum += __half2float(eh);  // normalise by what the PV GEMM will actually multiply with
+  const float sc = h.scale_log2e;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = (i * 256 + threadIdx.x) * 4;
+    if (c < ncols) {
+      // exp2f(-inf) = 0 for the masked slots
+      const __half2 h01 = __floats2half2_rn(exp2f((v[i].x - m) * sc), exp2f((v[i].y - m) * sc));
+      const __half2 h23 = __floats2half2_rn(exp2f((v[i].z - m) * sc), exp2f((v[i].w - m) * sc));
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      sum += (f01.x + f01.y) + (f23.x + f23.y);  // normalise by what the PV GEMM will actually multiply with
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+      *reinterpret_cast<uint2*>(pr + c) = pk;
+    }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);

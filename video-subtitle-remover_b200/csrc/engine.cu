@@ -5,6 +5,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -61,11 +62,14 @@ static std::string device_error_report() {
 }
 
 // ------------------------------------------------------------------------------------------------ device memory
+static uint64_t g_alloc_generation = 0;  // bumped on every (re)allocation: captured CUDA graphs bake pointers in
+
 struct DevBuf {
   void* p = nullptr;
   size_t n = 0;
   void ensure(size_t bytes) {
     if (bytes <= n) return;
+    ++g_alloc_generation;
     if (p) CK(cudaFree(p));
     p = nullptr;
     n = 0;
@@ -345,7 +349,7 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     const int ntok_p = h.toh_total * h.owp;
     h.ntt = (ntok_p + 127) / 128;
     h.nk64 = (ntok_p + 63) / 64;
-    const int tiles = h.ntt * h.ntt;
+    const int tiles = h.ntt * ((h.ntt + 1) / 2);  // 128 queries x 256 keys per CTA tile
     int splits = 1;
     if (tiles < 2 * c.sms) {
       splits = (4 * c.sms + tiles - 1) / tiles;
@@ -397,7 +401,17 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   pp.out_pitch = out_pitch;
   for (int s = 0; s < n_patch; ++s) pp.coff[s] = order[s] * dk;
   launch_tc<ScorePolicy>(c, sp, score_work);
-  softmax_rows_kernel<<<dim3(max_rows, n_patch), 256, 0, c.stream>>>(sp);
+  {
+    int max_cols = 0;
+    for (int s2 = 0; s2 < n_patch; ++s2) max_cols = std::max(max_cols, sp.h[s2].nk64 * 64);
+    const dim3 grid(max_rows, n_patch);
+    if (max_cols <= 1024) softmax_rows_kernel<1><<<grid, 256, 0, c.stream>>>(sp);
+    else if (max_cols <= 2048) softmax_rows_kernel<2><<<grid, 256, 0, c.stream>>>(sp);
+    else if (max_cols <= 5120) softmax_rows_kernel<5><<<grid, 256, 0, c.stream>>>(sp);
+    else if (max_cols <= 10240) softmax_rows_kernel<10><<<grid, 256, 0, c.stream>>>(sp);
+    else if (max_cols <= 20480) softmax_rows_kernel<20><<<grid, 256, 0, c.stream>>>(sp);
+    else throw Error(VSR_ERR_ARG, "attention rows longer than 20480 tokens are not supported");
+  }
   CK(cudaGetLastError());
   ++c.launches;
   launch_tc<PVPolicy>(c, pp, pv_work);
@@ -445,10 +459,16 @@ struct vsr_sttn {
   std::vector<int> visits_h;
   int sched_T = -1;
   std::vector<Window> sched;
-  DevBuf pinned_dummy;
   uint8_t* pinned = nullptr;
   size_t pinned_n = 0;
+  // CUDA graph of one chunk's compute (launch-bound inner loop: ~630 kernels + ~200 D2D copies)
+  bool use_graph = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  std::array<int, 4> graph_key{{-1, -1, -1, -1}}, warm_key{{-1, -1, -1, -1}};
+  uint64_t graph_gen = 0, warm_gen = 0;
+  int64_t graph_launches = 0;
   ~vsr_sttn() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (pinned) cudaFreeHost(pinned);
     if (ctx.stream) cudaStreamDestroy(ctx.stream);
   }
@@ -687,7 +707,7 @@ static void stage_area(vsr_sttn* h, int k) {
   h->staged_area = k;
 }
 
-static void compute_area(vsr_sttn* h, int k) {
+static void enqueue_area(vsr_sttn* h, int k) {
   const int y0 = h->areas[k][0], y1 = h->areas[k][1];
   const int sh = y1 - y0, sw = h->W;
   cudaStream_t s = h->ctx.stream;
@@ -699,6 +719,53 @@ static void compute_area(vsr_sttn* h, int k) {
       h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh, h->T, h->post_x.view(), h->post_y.view());
   CK(cudaGetLastError());
   ++h->ctx.launches;
+}
+
+// First call with a given (T, strip geometry): eager (sizes the workspace, uploads tables).  Second call:
+// captured into a CUDA graph.  Later calls: one cudaGraphLaunch.  Any reallocation invalidates the graph.
+static void compute_area(vsr_sttn* h, int k) {
+  const std::array<int, 4> key{{h->T, h->W, h->areas[k][0], h->areas[k][1]}};
+  cudaStream_t s = h->ctx.stream;
+  if (!h->use_graph) {
+    enqueue_area(h, k);
+    return;
+  }
+  if (h->graph_exec && h->graph_key == key && h->graph_gen == g_alloc_generation) {
+    CK(cudaGraphLaunch(h->graph_exec, s));
+    h->ctx.launches += h->graph_launches;
+    return;
+  }
+  if (h->warm_key == key && h->warm_gen == g_alloc_generation) {
+    if (h->graph_exec) {
+      cudaGraphExecDestroy(h->graph_exec);
+      h->graph_exec = nullptr;
+    }
+    const int64_t l0 = h->ctx.launches;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueue_area(h, k);
+    } catch (...) {
+      cudaStreamEndCapture(s, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    CK(cudaStreamEndCapture(s, &g));
+    h->graph_launches = h->ctx.launches - l0;
+    cudaError_t e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      h->graph_exec = nullptr;
+      throw Error(VSR_ERR_CUDA, std::string("cudaGraphInstantiate -> ") + cudaGetErrorString(e));
+    }
+    h->graph_key = key;
+    h->graph_gen = g_alloc_generation;
+    CK(cudaGraphLaunch(h->graph_exec, s));
+    return;
+  }
+  enqueue_area(h, k);
+  h->warm_key = key;
+  h->warm_gen = g_alloc_generation;
 }
 
 static void fetch_area(vsr_sttn* h, int k, uint8_t* const* out) {
@@ -789,6 +856,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->FW = h->cfg.model_w / 4;
     h->FH = h->cfg.model_h / 4;
     CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
+    h->use_graph = !(getenv("VSR_NO_GRAPH") && atoi(getenv("VSR_NO_GRAPH")));
     *out = h;
   });
 }

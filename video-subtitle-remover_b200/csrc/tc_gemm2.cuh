@@ -1,0 +1,128 @@
+// CTA-pair variant of the skeleton in tc_gemm.cuh (tcgen05 cta_group::2): two CTAs of a cluster (= two
+// SMs of a TPC) own one 256 x 256 tile.  Each CTA TMA-loads its own 128 rows of A and its own half
+// (128 rows) of B, so the L2->SM operand traffic per FLOP drops to 2/3 of the single-CTA 128x256
+// tile — the single-CTA conv kernel was measured L2-fill-bound (1.06 GB of operands in 82 us).
+// The leader CTA (cluster rank 0) issues the MMAs for the pair; every CTA keeps 128 rows of the
+// accumulator in its own TMEM and runs its own epilogue.
+//   full[s]    : in the leader, 2 arrivals (one expect_tx per CTA) + all TMA bytes of both CTAs
+//   empty[s]   : per CTA, released by a multicast tcgen05.commit from the leader
+//   tfull[a]   : per CTA, multicast commit;   tempty[a] : in the leader, 8 arrivals (4 warps x 2 CTAs)
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace vsr {
+
+template <class P>
+constexpr int tc2_smem_bytes() {
+  return P::STAGES * (2 * TC_A_BYTES) + 1024;
+}
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
+  constexpr int BN = 256;
+  constexpr int STAGES = P::STAGES;
+  constexpr uint32_t STAGE_BYTES = 2 * TC_A_BYTES;  // A: 128 rows, B: this CTA's 128 of the 256 rows
+  constexpr uint32_t TMEM_COLS = 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 2);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 8);
+    }
+    fence_barrier_init();
+    P::prefetch(prm);
+  }
+  if (warp == 1) tmem_alloc_2cta(smem_u32(&tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int ntiles = P::num_tiles(prm);
+  const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = first; t < ntiles; t += step) {
+        const typename P::Tile tile = P::get_tile(prm, t, rank);
+        for (int k = 0; k < tile.num_k; ++k) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
+          const uint32_t sA = smem_base + stage * STAGE_BYTES;
+          const uint32_t leader_full = mapa_cluster(smem_u32(&bar_full[stage]), 0);
+          P::load(prm, tile, k, sA, sA + TC_A_BYTES, leader_full, rank);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      const uint32_t idesc = umma_idesc_f16(256, BN, 0, 0);
+      for (int t = first; t < ntiles; t += step) {
+        const typename P::Tile tile = P::get_tile(prm, t, 0);
+        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int k = 0; k < tile.num_k; ++k) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase, ERR_MMA_FULL | stage);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * STAGE_BYTES;
+          const uint32_t sB = sA + TC_A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16_2cta(d_tmem, umma_desc_sw128(sA + kk * 32, 16, 1024), umma_desc_sw128(sB + kk * 32, 16, 1024), idesc,
+                          (k | kk) != 0);
+          umma_commit_2cta(smem_u32(&bar_empty[stage]), 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(smem_u32(&bar_tfull[as]), 3);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t quarter = warp & 3;
+    const uint32_t row = quarter * 32 + lane;
+    uint32_t as = 0, aphase = 0;
+    for (int t = first; t < ntiles; t += step) {
+      const typename P::Tile tile = P::get_tile(prm, t, rank);
+      mbar_wait(smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
+      typename P::RowCtx ctx = P::row_begin(prm, tile, row);
+      for (int c = 0; c < tile.n_cols; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        P::epilogue(prm, tile, ctx, row, c, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_tempty[as]), 0));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be signalling our barriers / reading our smem until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace vsr
