@@ -80,6 +80,10 @@ int64_t vsr_sttn_launch_count(vsr_sttn_t* h);
  * of n back-to-back launches of the transformer-block 3x3 conv (tcgen05 implicit GEMM) on T frames. */
 int vsr_sttn_time_conv(vsr_sttn_t* h, int T, int n, float* ms_out);
 
+/* Role-level wait accounting of the tcgen05 kernels (all zeros unless the library was built with
+ * -DVSR_TC_PROFILE): out64[kernel_id*8 + slot], see csrc/tc_common.cuh.  reset != 0 clears the counters. */
+int vsr_debug_tc_profile(uint64_t* out64, int reset);
+
 /* Debug/parity hook: copy an internal activation buffer (NHWC, converted to fp32) to the host.
  * name in {e1,e2s,e3,feats16,feats32,xw16,xw32,att16,comps}; contents are those left by the last compute. */
 int vsr_sttn_debug_read(vsr_sttn_t* h, const char* name, float* out, int64_t n);

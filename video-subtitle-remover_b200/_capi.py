@@ -9,7 +9,7 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 CSRC = _HERE / "csrc"
-LIB_PATH = CSRC / "build" / "libvsr_b200.so"
+LIB_PATH = Path(os.environ["VSR_B200_LIB"]) if os.environ.get("VSR_B200_LIB") else CSRC / "build" / "libvsr_b200.so"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -66,6 +66,7 @@ _PROTOS = {
     "vsr_sttn_sync": (C.c_int, [C.c_void_p]),
     "vsr_sttn_stream": (C.c_void_p, [C.c_void_p]),
     "vsr_sttn_launch_count": (C.c_int64, [C.c_void_p]),
+    "vsr_debug_tc_profile": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "vsr_sttn_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64]),
     "vsr_sttn_time_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p]),
     "vsr_create_mask": (C.c_int, [_u8p, C.c_int, C.c_int, _i32p, C.c_int, C.c_int]),

@@ -45,6 +45,7 @@ struct ScorePolicy {
   static constexpr int BN = 256;  // two 128-token key tiles per CTA tile: 96 B/clk of operand fill instead of 128
   static constexpr int STAGES = 4;
   static constexpr int B_MN_MAJOR = 0;
+  static constexpr int PROF_ID = 2;
   using Params = ScoreParams;
   struct Tile {
     int num_k, n_cols;
@@ -187,6 +188,7 @@ struct PVPolicy {
   static constexpr int BN = 256;
   static constexpr int STAGES = 4;
   static constexpr int B_MN_MAJOR = 1;
+  static constexpr int PROF_ID = 3;
   using Params = PVParams;
   struct Tile {
     int num_k, n_cols;

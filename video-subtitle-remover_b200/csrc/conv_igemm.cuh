@@ -7,6 +7,7 @@
 // Stride-2 convs are run as stride-1 2x2-tap convs over a space-to-depth input (see weights.cuh).
 #pragma once
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 
 namespace vsr {
 
@@ -20,6 +21,7 @@ enum ConvFlags : int {
 struct ConvParams {
   CUtensorMap in_map;  // 4-D {C, W, H, T} fp16, box {64, tile_w, tile_h, 1}, SWIZZLE_128B
   CUtensorMap w_map;   // 2-D {K_total, Cout_pad} fp16, box {64, BN}, SWIZZLE_128B
+  CUtensorMap w_map_half;  // same tensor, box {64, 128}: the half of B each CTA of a pair loads (Conv2Policy)
   int T, H, W;         // output (= input) spatial size
   int tile_w, tile_h, tiles_x, tiles_y;
   int n_tiles;         // Cout_pad / BN
@@ -43,6 +45,7 @@ struct ConvPolicy {
   static constexpr int BN = BN_;
   static constexpr int STAGES = (BN_ == 256) ? 4 : 6;
   static constexpr int B_MN_MAJOR = 0;
+  static constexpr int PROF_ID = (BN_ == 256) ? 0 : 4;
   using Params = ConvParams;
   struct Tile {
     int num_k, n_cols;
@@ -148,6 +151,55 @@ struct ConvPolicy {
         *reinterpret_cast<uint4*>(o + i) = *reinterpret_cast<const uint4*>(h);
       }
     }
+  }
+};
+
+// CTA-pair version of ConvPolicy<256>: pair-tile = two consecutive 128-pixel sub-tiles x 256 channels.
+struct Conv2Policy {
+  static constexpr int STAGES = 6;
+  static constexpr int PROF_ID = 1;
+  using Base = ConvPolicy<256>;
+  using Params = ConvParams;
+  using Tile = Base::Tile;
+  using RowCtx = Base::RowCtx;
+  __device__ static void prefetch(const Params& p) {
+    tma_prefetch_desc(&p.in_map);
+    tma_prefetch_desc(&p.w_map_half);
+  }
+  __device__ static int num_tiles(const Params& p) { return ((p.T * p.tiles_y * p.tiles_x + 1) >> 1) * p.n_tiles; }
+  __device__ static Tile get_tile(const Params& p, int idx, uint32_t rank) {
+    Tile t;
+    const int n = idx % p.n_tiles;
+    int sub = (idx / p.n_tiles) * 2 + (int)rank;
+    const int total = p.T * p.tiles_y * p.tiles_x;
+    t.n0 = n * 256;
+    t.num_k = p.ntaps * p.cin_chunks;
+    t.n_cols = 256;
+    if (sub >= total) {  // odd tile count: the pair's second half is a dummy (TMA zero-fills frame index T)
+      t.t = p.T; t.y0 = 0; t.x0 = 0;
+      return t;
+    }
+    const int tx = sub % p.tiles_x;
+    sub /= p.tiles_x;
+    t.x0 = tx * p.tile_w;
+    t.y0 = (sub % p.tiles_y) * p.tile_h;
+    t.t = sub / p.tiles_y;
+    return t;
+  }
+  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t leader_full, uint32_t rank) {
+    const int tap = k / p.cin_chunks;
+    const int kc = k - tap * p.cin_chunks;
+    mbar_expect_tx_cluster(leader_full, (uint32_t)(p.tile_w * p.tile_h * 128 + 128 * 128));
+    tma_load_4d_2sm(sA, &p.in_map, leader_full, kc * 64, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.t);
+    tma_load_2d_2sm(sB, &p.w_map_half, leader_full, k * 64, t.n0 + (int)rank * 128);
+  }
+  __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
+    RowCtx c = Base::row_begin(p, t, row);
+    c.valid = c.valid && (t.t < p.T);
+    return c;
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
+    Base::epilogue(p, t, c, row, col0, v);
   }
 };
 

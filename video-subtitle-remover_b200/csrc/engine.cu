@@ -141,7 +141,13 @@ struct Ctx {
   int sms = 148;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
 };
+
+static bool env_flag(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) != 0 : dflt;
+}
 
 template <class P>
 static void launch_tc(Ctx& c, const typename P::Params& prm, int ntiles) {
@@ -154,6 +160,21 @@ static void launch_tc(Ctx& c, const typename P::Params& prm, int ntiles) {
   if (ntiles <= 0) return;
   const int grid = ntiles < c.sms ? ntiles : c.sms;
   tc_gemm_kernel<P><<<grid, TC_THREADS, smem, c.stream>>>(prm);
+  CK(cudaGetLastError());
+  ++c.launches;
+}
+
+static void launch_tc2_conv(Ctx& c, const ConvParams& prm, int ntiles) {
+  static bool configured = false;
+  constexpr int smem = tc2_smem_bytes<Conv2Policy>();
+  if (!configured) {
+    CK(cudaFuncSetAttribute(tc_gemm2_kernel<Conv2Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  if (ntiles <= 0) return;
+  const int pairs = c.sms / 2;
+  const int grid = 2 * (ntiles < pairs ? ntiles : pairs);
+  tc_gemm2_kernel<Conv2Policy><<<grid, TC_THREADS, smem, c.stream>>>(prm);
   CK(cudaGetLastError());
   ++c.launches;
 }
@@ -296,6 +317,14 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   }
   if (!(io.flags & CONV_FINAL)) REQUIRE(L.cout == L.cout_pad, "Cout must be 64, 128 or a multiple of 256");
   const int ntiles = p.T * p.tiles_y * p.tiles_x * p.n_tiles;
+  if (L.bn == 256 && c.conv_2cta && !(io.flags & CONV_FINAL)) {
+    const uint64_t dims[2] = {(uint64_t)L.K, (uint64_t)L.cout_pad};
+    const uint64_t str[1] = {(uint64_t)L.K * 2};
+    const uint32_t box[2] = {64, 128};
+    p.w_map_half = make_map_f16(L.w.p, 2, dims, str, box);
+    launch_tc2_conv(c, p, ((p.T * p.tiles_y * p.tiles_x + 1) / 2) * p.n_tiles);
+    return;
+  }
   switch (L.bn) {
     case 256: launch_tc<ConvPolicy<256>>(c, p, ntiles); break;
     case 128: launch_tc<ConvPolicy<128>>(c, p, ntiles); break;
@@ -856,7 +885,8 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->FW = h->cfg.model_w / 4;
     h->FH = h->cfg.model_h / 4;
     CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
-    h->use_graph = !(getenv("VSR_NO_GRAPH") && atoi(getenv("VSR_NO_GRAPH")));
+    h->use_graph = !env_flag("VSR_NO_GRAPH", false);
+    h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     *out = h;
   });
 }
@@ -953,6 +983,20 @@ int vsr_sttn_sync(vsr_sttn_t* h) {
 }
 void* vsr_sttn_stream(vsr_sttn_t* h) { return h ? (void*)h->ctx.stream : nullptr; }
 int64_t vsr_sttn_launch_count(vsr_sttn_t* h) { return h ? h->ctx.launches : 0; }
+
+int vsr_debug_tc_profile(uint64_t* out64, int reset) {
+  return guarded([&] {
+    REQUIRE(out64, "out pointer");
+    unsigned long long hbuf[64];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(hbuf, g_tc_prof, sizeof(hbuf)));
+    for (int i = 0; i < 64; ++i) out64[i] = hbuf[i];
+    if (reset) {
+      memset(hbuf, 0, sizeof(hbuf));
+      CK(cudaMemcpyToSymbol(g_tc_prof, hbuf, sizeof(hbuf)));
+    }
+  });
+}
 
 int vsr_sttn_debug_read(vsr_sttn_t* h, const char* name, float* out, int64_t n) {
   return guarded([&] {
@@ -1071,6 +1115,7 @@ struct OpCtx {
     if (prop.major != 10) throw Error(VSR_ERR_CUDA, "vsr_b200 kernels are sm_100a only");
     c.device = device;
     c.sms = prop.multiProcessorCount;
+    c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   }
   ~OpCtx() {

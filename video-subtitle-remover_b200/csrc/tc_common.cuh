@@ -61,6 +61,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
   }
 }
 
+// Optional role-level wait accounting (build with -DVSR_TC_PROFILE, see tools/wait_profile.py):
+// g_tc_prof[kernel_id*8 + slot] accumulates SM cycles: 0 producer waits for a free stage, 1 MMA waits
+// for operands, 2 MMA waits for a free accumulator, 3 epilogue waits for an accumulator, 4 epilogue busy,
+// 5 total kernel cycles (one sample per CTA), 6 CTAs.
+__device__ unsigned long long g_tc_prof[8 * 8];
+#ifdef VSR_TC_PROFILE
+#define TC_PROF_DECL(name) long long name = 0
+#define TC_PROF_WAIT(acc, ...)        \
+  do {                                \
+    const long long t0_ = clock64();  \
+    mbar_wait(__VA_ARGS__);           \
+    acc += clock64() - t0_;           \
+  } while (0)
+#define TC_PROF_ADD(kid, slot, v) atomicAdd(&g_tc_prof[(kid) * 8 + (slot)], (unsigned long long)(v))
+#define TC_PROF_NOW() clock64()
+#define TC_PROF_ACC(acc, t0) acc += clock64() - (t0)
+#else
+#define TC_PROF_DECL(name)
+#define TC_PROF_WAIT(acc, ...) mbar_wait(__VA_ARGS__)
+#define TC_PROF_ADD(kid, slot, v)
+#define TC_PROF_NOW() 0
+#define TC_PROF_ACC(acc, t0)
+#endif
+
 // ------------------------------------------------------------------------------------------ TMA loads
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");

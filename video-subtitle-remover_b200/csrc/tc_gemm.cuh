@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
 
+  const long long t_kernel0 = TC_PROF_NOW();
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -61,28 +62,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      TC_PROF_DECL(w_empty);
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const typename P::Tile tile = P::get_tile(prm, t);
         for (int k = 0; k < tile.num_k; ++k) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
+          TC_PROF_WAIT(w_empty, smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
           P::load(prm, tile, k, sA, sA + TC_A_BYTES, smem_u32(&bar_full[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      TC_PROF_ADD(P::PROF_ID, 0, w_empty);
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      TC_PROF_DECL(w_full);
+      TC_PROF_DECL(w_tempty);
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const typename P::Tile tile = P::get_tile(prm, t);
-        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
+        TC_PROF_WAIT(w_tempty, smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         const uint32_t idesc = umma_idesc_f16(128, BN, 0, P::B_MN_MAJOR);
         for (int k = 0; k < tile.num_k; ++k) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase, ERR_MMA_FULL | stage);
+          TC_PROF_WAIT(w_full, smem_u32(&bar_full[stage]), phase, ERR_MMA_FULL | stage);
           tc_fence_after();
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
           const uint32_t sB = sA + TC_A_BYTES;
@@ -99,16 +104,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         umma_commit(smem_u32(&bar_tfull[as]));  // accumulator ready for the epilogue
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
+      TC_PROF_ADD(P::PROF_ID, 1, w_full);
+      TC_PROF_ADD(P::PROF_ID, 2, w_tempty);
     }
     __syncwarp();
   } else {
     const uint32_t quarter = warp & 3;  // TMEM lane quarter this warp may read
     const uint32_t row = quarter * 32 + lane;
     uint32_t as = 0, aphase = 0;
+    TC_PROF_DECL(w_tfull);
+    TC_PROF_DECL(busy);
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const typename P::Tile tile = P::get_tile(prm, t);
-      mbar_wait(smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
+      TC_PROF_WAIT(w_tfull, smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
       tc_fence_after();
+      const long long e0 = TC_PROF_NOW();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
       typename P::RowCtx ctx = P::row_begin(prm, tile, row);
       if constexpr (BN >= 32) {
@@ -124,13 +134,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
+      TC_PROF_ACC(busy, e0);
       if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (warp == 2 && lane == 0) {
+      TC_PROF_ADD(P::PROF_ID, 3, w_tfull);
+      TC_PROF_ADD(P::PROF_ID, 4, busy);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    TC_PROF_ADD(P::PROF_ID, 5, TC_PROF_NOW() - t_kernel0);
+    TC_PROF_ADD(P::PROF_ID, 6, 1);
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);

@@ -29,6 +29,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
 
+  const long long t_kernel0 = TC_PROF_NOW();
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -57,29 +58,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      TC_PROF_DECL(w_empty);
       for (int t = first; t < ntiles; t += step) {
         const typename P::Tile tile = P::get_tile(prm, t, rank);
         for (int k = 0; k < tile.num_k; ++k) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
+          TC_PROF_WAIT(w_empty, smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
           const uint32_t leader_full = mapa_cluster(smem_u32(&bar_full[stage]), 0);
           P::load(prm, tile, k, sA, sA + TC_A_BYTES, leader_full, rank);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      TC_PROF_ADD(P::PROF_ID, 0, w_empty);
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      TC_PROF_DECL(w_full);
+      TC_PROF_DECL(w_tempty);
       const uint32_t idesc = umma_idesc_f16(256, BN, 0, 0);
       for (int t = first; t < ntiles; t += step) {
         const typename P::Tile tile = P::get_tile(prm, t, 0);
-        mbar_wait(smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
+        TC_PROF_WAIT(w_tempty, smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int k = 0; k < tile.num_k; ++k) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase, ERR_MMA_FULL | stage);
+          TC_PROF_WAIT(w_full, smem_u32(&bar_full[stage]), phase, ERR_MMA_FULL | stage);
           tc_fence_after();
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
           const uint32_t sB = sA + TC_A_BYTES;
@@ -93,16 +98,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         umma_commit_2cta(smem_u32(&bar_tfull[as]), 3);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
+      TC_PROF_ADD(P::PROF_ID, 1, w_full);
+      TC_PROF_ADD(P::PROF_ID, 2, w_tempty);
     }
     __syncwarp();
   } else {
     const uint32_t quarter = warp & 3;
     const uint32_t row = quarter * 32 + lane;
     uint32_t as = 0, aphase = 0;
+    TC_PROF_DECL(w_tfull);
+    TC_PROF_DECL(busy);
     for (int t = first; t < ntiles; t += step) {
       const typename P::Tile tile = P::get_tile(prm, t, rank);
-      mbar_wait(smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
+      TC_PROF_WAIT(w_tfull, smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
       tc_fence_after();
+      const long long e0 = TC_PROF_NOW();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
       typename P::RowCtx ctx = P::row_begin(prm, tile, row);
       for (int c = 0; c < tile.n_cols; c += 32) {
@@ -112,13 +122,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
       tc_fence_before();
       __syncwarp();
+      TC_PROF_ACC(busy, e0);
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_tempty[as]), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (warp == 2 && lane == 0) {
+      TC_PROF_ADD(P::PROF_ID, 3, w_tfull);
+      TC_PROF_ADD(P::PROF_ID, 4, busy);
     }
   }
 
   tc_fence_before();
   cluster_sync_all();  // the peer may still be signalling our barriers / reading our smem until here
+  if (threadIdx.x == 0) {
+    TC_PROF_ADD(P::PROF_ID, 5, TC_PROF_NOW() - t_kernel0);
+    TC_PROF_ADD(P::PROF_ID, 6, 1);
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, TMEM_COLS);
