@@ -224,12 +224,13 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel (3x3 conv 256->256 on a 15-frame window) --------------
-    Tw = 15
+    group = int(os.environ.get("VSR_WINDOW_GROUP", "2"))
+    Tw = 29 if group >= 2 else 15  # frames per conv launch in the steady state (windows of 15 + 14 share a launch)
     ms = eng.time_conv(Tw, 20)
     conv_ms = float(np.median(ms))
     conv_flop = 2.0 * Tw * 30 * 160 * 2304 * 256
     burst, sustained, hbm, src = peaks()
-    roof = {"bound": "tensor", "kernel": "tc_gemm_kernel<ConvPolicy<256>> (3x3 conv 256->256, 15x30x160 px)",
+    roof = {"bound": "tensor", "kernel": f"tcgen05 implicit-GEMM 3x3 conv 256->256, {Tw}x30x160 px ({'CTA-pair 256x256' if os.environ.get('VSR_CONV_2CTA', '1') != '0' else '128x256'} tiles)",
             "achieved": conv_flop / (conv_ms * 1e-3) / 1e12, "peak": burst, "unit": "TFLOP/s",
             "frac": conv_flop / (conv_ms * 1e-3) / 1e12 / burst, "traffic": None, "peak_source": f"{src} (burst bf16)",
             "ms_per_launch": conv_ms, "flop_per_launch": conv_flop,

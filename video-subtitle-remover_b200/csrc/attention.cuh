@@ -35,9 +35,11 @@ struct AttnHead {
   float* rowsum;
 };
 
+constexpr int ATTN_MAX_HEADS = 8;  // (windows in a group) x (patch geometries)
+
 struct ScoreParams {
-  CUtensorMap qmap[4], kmap[4];
-  AttnHead h[4];
+  CUtensorMap qmap[ATTN_MAX_HEADS], kmap[ATTN_MAX_HEADS];
+  AttnHead h[ATTN_MAX_HEADS];
   int nheads, total_work;
 };
 
@@ -46,6 +48,7 @@ struct ScorePolicy {
   static constexpr int STAGES = 4;
   static constexpr int B_MN_MAJOR = 0;
   static constexpr int PROF_ID = 2;
+  static constexpr bool EPI_SCRATCH = true;
   using Params = ScoreParams;
   struct Tile {
     int num_k, n_cols;
@@ -96,10 +99,24 @@ struct ScorePolicy {
     c.dst = h.S + (size_t)t.split * h.slabS + (size_t)(t.qi * 128 + row) * h.ldS + t.kj * 256;
     return c;
   }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
-    float* d = c.dst + col0;
+  // The accumulator arrives one row per thread; storing it like that scatters every 16-byte store over 32
+  // different rows (measured: the epilogue was 84 % of this kernel).  Transpose 32x32 blocks through smem so
+  // that each store instruction writes 4 rows x 128 contiguous bytes.
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float* scr) {
+    const int lane = row & 31;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(d + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+    __syncwarp();
+    const AttnHead& h = p.h[t.head];
+    float* base = c.dst - (size_t)lane * h.ldS + col0;  // row 0 of this warp's 32 rows
+    const int r4 = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rr = j * 4 + r4;
+      const float* sp = scr + rr * 33 + c4;
+      *reinterpret_cast<float4*>(base + (size_t)rr * h.ldS + c4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    }
+    __syncwarp();
   }
 };
 
@@ -175,13 +192,14 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
 }
 
 struct PVParams {
-  CUtensorMap pmap[4], vmap[4];
-  AttnHead h[4];
+  CUtensorMap pmap[ATTN_MAX_HEADS], vmap[ATTN_MAX_HEADS];
+  AttnHead h[ATTN_MAX_HEADS];
   int nheads, total_work;
   int T, H, W;       // feature map geometry
-  __half* out;       // NHWC fp16 [T,H,W,out_pitch]; (sorted) head s writes channels [coff[s], coff[s] + 64)
-  int out_pitch;
-  int coff[4];
+  __half* out;       // NHWC fp16 [T,H,W,out_pitch]; entry s writes channels [coff[s], coff[s]+64) of the frames
+  int out_pitch;     // starting at element offset out_off[s] (its window's first frame)
+  int coff[ATTN_MAX_HEADS];
+  long long out_off[ATTN_MAX_HEADS];
 };
 
 struct PVPolicy {
@@ -189,6 +207,7 @@ struct PVPolicy {
   static constexpr int STAGES = 4;
   static constexpr int B_MN_MAJOR = 1;
   static constexpr int PROF_ID = 3;
+  static constexpr bool EPI_SCRATCH = false;
   using Params = PVParams;
   struct Tile {
     int num_k, n_cols;
@@ -242,11 +261,11 @@ struct PVPolicy {
     if (c.valid) {
       c.inv = 1.0f / h.rowsum[qp];
       const int tt = toh / h.oh, ohi = toh - tt * h.oh;
-      c.base = p.out + (((size_t)tt * p.H + ohi * h.ph) * p.W + owi * h.pw) * p.out_pitch + p.coff[t.head];
+      c.base = p.out + p.out_off[t.head] + (((size_t)tt * p.H + ohi * h.ph) * p.W + owi * h.pw) * p.out_pitch + p.coff[t.head];
     }
     return c;
   }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float*) {
     if (!c.valid) return;
     const AttnHead& h = p.h[t.head];
     const int pos = t.ni * 4 + (col0 >> 6);

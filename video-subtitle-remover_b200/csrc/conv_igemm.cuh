@@ -46,6 +46,7 @@ struct ConvPolicy {
   static constexpr int STAGES = (BN_ == 256) ? 4 : 6;
   static constexpr int B_MN_MAJOR = 0;
   static constexpr int PROF_ID = (BN_ == 256) ? 0 : 4;
+  static constexpr bool EPI_SCRATCH = false;
   using Params = ConvParams;
   struct Tile {
     int num_k, n_cols;
@@ -94,7 +95,7 @@ struct ConvPolicy {
     c.pix = ((size_t)t.t * p.H + c.y) * p.W + c.x;
     return c;
   }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float*) {
     if (!c.valid) return;
     constexpr int NV = (BN >= 32) ? 32 : 16;
     const int ch0 = t.n0 + col0;
@@ -158,6 +159,7 @@ struct ConvPolicy {
 struct Conv2Policy {
   static constexpr int STAGES = 6;
   static constexpr int PROF_ID = 1;
+  static constexpr bool EPI_SCRATCH = false;
   using Base = ConvPolicy<256>;
   using Params = ConvParams;
   using Tile = Base::Tile;
@@ -186,10 +188,12 @@ struct Conv2Policy {
     t.t = sub / p.tiles_y;
     return t;
   }
-  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t leader_full, uint32_t rank) {
+  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t local_full, uint32_t leader_full,
+                              uint32_t rank) {
     const int tap = k / p.cin_chunks;
     const int kc = k - tap * p.cin_chunks;
-    mbar_expect_tx_cluster(leader_full, (uint32_t)(p.tile_w * p.tile_h * 128 + 128 * 128));
+    // the leader registers the bytes of both CTAs; the peer's loads may land first (tx-count is signed)
+    if (rank == 0) mbar_expect_tx(local_full, 2u * (uint32_t)(p.tile_w * p.tile_h * 128 + 128 * 128));
     tma_load_4d_2sm(sA, &p.in_map, leader_full, kc * 64, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.t);
     tma_load_2d_2sm(sB, &p.w_map_half, leader_full, k * 64, t.n0 + (int)rank * 128);
   }
@@ -198,8 +202,8 @@ struct Conv2Policy {
     c.valid = c.valid && (t.t < p.T);
     return c;
   }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v) {
-    Base::epilogue(p, t, c, row, col0, v);
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float* scr) {
+    Base::epilogue(p, t, c, row, col0, v, scr);
   }
 };
 

@@ -336,7 +336,7 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
 
 // ------------------------------------------------------------------------------------------------ attention
 struct AttnWorkspace {
-  DevBuf S[4], P[4], rowsum[4];
+  DevBuf S[ATTN_MAX_HEADS], P[ATTN_MAX_HEADS], rowsum[ATTN_MAX_HEADS];
 };
 
 static int next_pow2(int v) {
@@ -345,27 +345,39 @@ static int next_pow2(int v) {
   return p;
 }
 
-// qkv: NHWC fp16 [T,H,W,pitch]; q/k/v channel offsets q_off/k_off/v_off; head i uses +i*dk.
-static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitch, int q_off, int k_off, int v_off, int T, int H,
-                          int W, int C, int n_patch, const int* pw, const int* ph, __half* out, int out_pitch) {
+struct AttnSegment {  // one attention problem: frames [first, first + T) of the buffers (a window of the schedule)
+  int first, T;
+};
+
+// qkv: NHWC fp16 [frames,H,W,pitch]; q/k/v channel offsets q_off/k_off/v_off; head i uses +i*dk.  Every
+// (segment, patch geometry) pair is an independent attention problem; all of them run in the same three
+// launches (scores, softmax, PV).
+static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitch, int q_off, int k_off, int v_off,
+                          const std::vector<AttnSegment>& segs, int H, int W, int C, int n_patch, const int* pw, const int* ph,
+                          __half* out, int out_pitch) {
   REQUIRE(n_patch >= 1 && n_patch <= 4, "1..4 heads");
   const int dk = C / n_patch;
   REQUIRE(dk == 64, "head width must be 64 channels (one SWIZZLE_128B row)");
+  const int nent = (int)segs.size() * n_patch;
+  REQUIRE(nent >= 1 && nent <= ATTN_MAX_HEADS, "too many attention problems in one launch");
   ScoreParams sp;
   PVParams pp;
   memset(&sp, 0, sizeof(sp));
   memset(&pp, 0, sizeof(pp));
-  // order heads by descending work so the long tiles are scheduled first
-  std::vector<int> order(n_patch);
-  for (int i = 0; i < n_patch; ++i) order[i] = i;
-  auto work = [&](int i) {
-    const double n = (double)T * (H / ph[i]) * (W / pw[i]);
-    return n * n * 64.0 * pw[i] * ph[i];
-  };
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return work(a) > work(b); });
+  // order the problems by descending work so the long tiles are scheduled first
+  struct Ent { int seg, patch; double work; };
+  std::vector<Ent> ents;
+  for (int g = 0; g < (int)segs.size(); ++g)
+    for (int i = 0; i < n_patch; ++i) {
+      const double n = (double)segs[g].T * (H / ph[i]) * (W / pw[i]);
+      ents.push_back({g, i, n * n * 64.0 * pw[i] * ph[i]});
+    }
+  std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.work > b.work; });
   int score_work = 0, pv_work = 0, max_rows = 0;
-  for (int s = 0; s < n_patch; ++s) {
-    const int i = order[s];
+  for (int s = 0; s < nent; ++s) {
+    const int i = ents[s].patch;
+    const AttnSegment& sg = segs[ents[s].seg];
+    const size_t frame_elems = (size_t)H * W * pitch;
     AttnHead h;
     memset(&h, 0, sizeof(h));
     REQUIRE(W % pw[i] == 0 && H % ph[i] == 0, "patch must divide the feature map");
@@ -374,7 +386,7 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     h.owp = next_pow2(h.ow);
     REQUIRE(h.owp <= 64, "more than 64 patches per row is not supported");
     h.npos = pw[i] * ph[i];
-    h.toh_total = T * h.oh;
+    h.toh_total = sg.T * h.oh;
     const int ntok_p = h.toh_total * h.owp;
     h.ntt = (ntok_p + 127) / 128;
     h.nk64 = (ntok_p + 63) / 64;
@@ -405,35 +417,36 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     h.P = ws.P[s].as<__half>();
     h.rowsum = ws.rowsum[s].as<float>();
     if ((int)rows > max_rows) max_rows = (int)rows;
-    // 5-D views {64 ch, px, ow, py, toh}
+    // 5-D views {64 ch, px, ow, py, toh} of this segment's frames
+    const __half* base = qkv + (size_t)sg.first * frame_elems;
     const uint64_t dims[5] = {64, (uint64_t)h.pw, (uint64_t)h.ow, (uint64_t)h.ph, (uint64_t)h.toh_total};
     const uint64_t str[4] = {(uint64_t)pitch * 2, (uint64_t)h.pw * pitch * 2, (uint64_t)W * pitch * 2,
                              (uint64_t)h.ph * W * pitch * 2};
     const uint32_t box_qk[5] = {64, 1, (uint32_t)h.owp, 1, (uint32_t)(128 / h.owp)};
     const uint32_t box_v[5] = {64, 1, (uint32_t)h.owp, 1, (uint32_t)(64 / h.owp)};
-    sp.qmap[s] = make_map_f16(qkv + q_off + i * dk, 5, dims, str, box_qk);
-    sp.kmap[s] = make_map_f16(qkv + k_off + i * dk, 5, dims, str, box_qk);
-    pp.vmap[s] = make_map_f16(qkv + v_off + i * dk, 5, dims, str, box_v);
+    sp.qmap[s] = make_map_f16(base + q_off + i * dk, 5, dims, str, box_qk);
+    sp.kmap[s] = make_map_f16(base + k_off + i * dk, 5, dims, str, box_qk);
+    pp.vmap[s] = make_map_f16(base + v_off + i * dk, 5, dims, str, box_v);
     const uint64_t pd[2] = {(uint64_t)h.ldP, (uint64_t)rows};
     const uint64_t ps[1] = {(uint64_t)h.ldP * 2};
     const uint32_t pb[2] = {64, 128};
     pp.pmap[s] = make_map_f16(h.P, 2, pd, ps, pb);
     sp.h[s] = h;
     pp.h[s] = h;
-    // channel offset of this head in the output: stored through `head` index -> use coff table below
+    pp.coff[s] = i * dk;
+    pp.out_off[s] = (long long)sg.first * H * W * out_pitch;
   }
-  sp.nheads = pp.nheads = n_patch;
+  sp.nheads = pp.nheads = nent;
   sp.total_work = score_work;
   pp.total_work = pv_work;
-  pp.T = T; pp.H = H; pp.W = W;
+  pp.T = 0; pp.H = H; pp.W = W;
   pp.out = out;
   pp.out_pitch = out_pitch;
-  for (int s = 0; s < n_patch; ++s) pp.coff[s] = order[s] * dk;
   launch_tc<ScorePolicy>(c, sp, score_work);
   {
     int max_cols = 0;
-    for (int s2 = 0; s2 < n_patch; ++s2) max_cols = std::max(max_cols, sp.h[s2].nk64 * 64);
-    const dim3 grid(max_rows, n_patch);
+    for (int s2 = 0; s2 < nent; ++s2) max_cols = std::max(max_cols, sp.h[s2].nk64 * 64);
+    const dim3 grid(max_rows, nent);
     if (max_cols <= 1024) softmax_rows_kernel<1><<<grid, 256, 0, c.stream>>>(sp);
     else if (max_cols <= 2048) softmax_rows_kernel<2><<<grid, 256, 0, c.stream>>>(sp);
     else if (max_cols <= 5120) softmax_rows_kernel<5><<<grid, 256, 0, c.stream>>>(sp);
@@ -492,6 +505,7 @@ struct vsr_sttn {
   size_t pinned_n = 0;
   // CUDA graph of one chunk's compute (launch-bound inner loop: ~630 kernels + ~200 D2D copies)
   bool use_graph = true;
+  size_t window_group = 2;  // windows sharing each launch (VSR_WINDOW_GROUP, 1..2)
   cudaGraphExec_t graph_exec = nullptr;
   std::array<int, 4> graph_key{{-1, -1, -1, -1}}, warm_key{{-1, -1, -1, -1}};
   uint64_t graph_gen = 0, warm_gen = 0;
@@ -584,7 +598,12 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh) {
     h->sched_T = T;
   }
   size_t maxw = 0;
-  for (auto& w : h->sched) maxw = std::max(maxw, w.neighbors.size() + w.refs.size());
+  for (size_t w0 = 0; w0 < h->sched.size(); w0 += h->window_group) {
+    size_t sum = 0;
+    for (size_t wi = w0; wi < std::min(h->sched.size(), w0 + h->window_group); ++wi)
+      sum += h->sched[wi].neighbors.size() + h->sched[wi].refs.size();
+    maxw = std::max(maxw, sum);
+  }
   size_t maxn = 0;
   for (auto& w : h->sched) maxn = std::max(maxn, w.neighbors.size());
   const size_t fpix = (size_t)FH * FW;
@@ -634,49 +653,60 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh) {
     io4.flags = CONV_LRELU; io4.out16 = h->feats16.as<__half>(); io4.out32 = h->feats32.as<float>();
     run_conv(c, h->enc4, io4);
   }
-  // A6-A11 window loop
+  // A6-A11 window loop.  The transformer passes of different windows are independent (only the blend
+  // into comps is ordered), so `group` consecutive windows share every conv / attention launch: at T=15 a
+  // single window is 4.05 waves of 128x256 tiles (81 % wave efficiency), two windows are 7.8 (98 %).
   const size_t f16b = fpix * C * 2, f32b = fpix * C * 4;
-  for (size_t wi = 0; wi < h->sched.size(); ++wi) {
-    const Window& w = h->sched[wi];
-    const int nn = (int)w.neighbors.size();
-    const int Tw = nn + (int)w.refs.size();
-    // gather feats[neighbor_ids + ref_ids] (sttn_auto_inpaint.py:148)
-    CK(cudaMemcpyAsync(h->xw16.p, h->feats16.as<uint8_t>() + (size_t)w.neighbors[0] * f16b, (size_t)nn * f16b,
-                       cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(h->xw32.p, h->feats32.as<uint8_t>() + (size_t)w.neighbors[0] * f32b, (size_t)nn * f32b,
-                       cudaMemcpyDeviceToDevice, s));
-    for (size_t r = 0; r < w.refs.size(); ++r) {
-      CK(cudaMemcpyAsync(h->xw16.as<uint8_t>() + (nn + r) * f16b, h->feats16.as<uint8_t>() + (size_t)w.refs[r] * f16b, f16b,
-                         cudaMemcpyDeviceToDevice, s));
-      CK(cudaMemcpyAsync(h->xw32.as<uint8_t>() + (nn + r) * f32b, h->feats32.as<uint8_t>() + (size_t)w.refs[r] * f32b, f32b,
-                         cudaMemcpyDeviceToDevice, s));
+  for (size_t w0 = 0; w0 < h->sched.size(); w0 += h->window_group) {
+    const size_t w1 = std::min(h->sched.size(), w0 + h->window_group);
+    std::vector<AttnSegment> segs;
+    int Tg = 0;
+    for (size_t wi = w0; wi < w1; ++wi) {
+      const Window& w = h->sched[wi];
+      const int nn = (int)w.neighbors.size();
+      // gather feats[neighbor_ids + ref_ids] (sttn_auto_inpaint.py:148)
+      CK(cudaMemcpyAsync(h->xw16.as<uint8_t>() + (size_t)Tg * f16b, h->feats16.as<uint8_t>() + (size_t)w.neighbors[0] * f16b,
+                         (size_t)nn * f16b, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(h->xw32.as<uint8_t>() + (size_t)Tg * f32b, h->feats32.as<uint8_t>() + (size_t)w.neighbors[0] * f32b,
+                         (size_t)nn * f32b, cudaMemcpyDeviceToDevice, s));
+      for (size_t r = 0; r < w.refs.size(); ++r) {
+        CK(cudaMemcpyAsync(h->xw16.as<uint8_t>() + (Tg + nn + r) * f16b, h->feats16.as<uint8_t>() + (size_t)w.refs[r] * f16b, f16b,
+                           cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(h->xw32.as<uint8_t>() + (Tg + nn + r) * f32b, h->feats32.as<uint8_t>() + (size_t)w.refs[r] * f32b, f32b,
+                           cudaMemcpyDeviceToDevice, s));
+      }
+      segs.push_back({Tg, nn + (int)w.refs.size()});
+      Tg += nn + (int)w.refs.size();
     }
     for (int b = 0; b < 8; ++b) {
       // A7: Q,K,V 1x1 projections in one GEMM (auto_sttn.py:172-174)
       ConvIO q;
-      q.in = h->xw16.as<__half>(); q.T = Tw; q.H = FH; q.W = FW; q.out16 = h->qkvb.as<__half>(); q.out16_pitch = 3 * C;
+      q.in = h->xw16.as<__half>(); q.T = Tg; q.H = FH; q.W = FW; q.out16 = h->qkvb.as<__half>(); q.out16_pitch = 3 * C;
       run_conv(c, h->qkv[b], q);
-      // A8: patch attention
-      run_attention(c, h->attn, h->qkvb.as<__half>(), 3 * C, 0, C, 2 * C, Tw, FH, FW, C, h->cfg.n_patch, h->cfg.patch_w,
+      // A8: patch attention, one problem per (window, patch geometry)
+      run_attention(c, h->attn, h->qkvb.as<__half>(), 3 * C, 0, C, 2 * C, segs, FH, FW, C, h->cfg.n_patch, h->cfg.patch_w,
                     h->cfg.patch_h, h->att16.as<__half>(), C);
       // output_linear + residual (auto_sttn.py:163-164, 237)
       ConvIO o;
-      o.in = h->att16.as<__half>(); o.T = Tw; o.H = FH; o.W = FW; o.flags = CONV_LRELU | CONV_RESIDUAL;
+      o.in = h->att16.as<__half>(); o.T = Tg; o.H = FH; o.W = FW; o.flags = CONV_LRELU | CONV_RESIDUAL;
       o.out16 = h->xw16.as<__half>(); o.out32 = h->xw32.as<float>(); o.res32 = h->xw32.as<float>();
       run_conv(c, h->outl[b], o);
       // A9: feed forward + residual (auto_sttn.py:215-218, 238)
       ConvIO f0;
-      f0.in = h->xw16.as<__half>(); f0.T = Tw; f0.H = FH; f0.W = FW; f0.flags = CONV_LRELU; f0.out16 = h->ffn16.as<__half>();
+      f0.in = h->xw16.as<__half>(); f0.T = Tg; f0.H = FH; f0.W = FW; f0.flags = CONV_LRELU; f0.out16 = h->ffn16.as<__half>();
       run_conv(c, h->ff0[b], f0);
       ConvIO f1;
-      f1.in = h->ffn16.as<__half>(); f1.T = Tw; f1.H = FH; f1.W = FW; f1.flags = CONV_LRELU | CONV_RESIDUAL;
+      f1.in = h->ffn16.as<__half>(); f1.T = Tg; f1.H = FH; f1.W = FW; f1.flags = CONV_LRELU | CONV_RESIDUAL;
       f1.out16 = h->xw16.as<__half>(); f1.out32 = h->xw32.as<float>(); f1.res32 = h->xw32.as<float>();
       run_conv(c, h->ff1[b], f1);
     }
-    // A10 decoder on the neighbour frames only (sttn_auto_inpaint.py:150)
-    {
+    // A10 decoder on the neighbour frames only (sttn_auto_inpaint.py:150), window by window in schedule
+    // order (the 0.5/0.5 blend of :159-162 is order dependent)
+    for (size_t wi = w0; wi < w1; ++wi) {
+      const int nn = (int)h->sched[wi].neighbors.size();
+      const __half* xin = h->xw16.as<__half>() + (size_t)segs[wi - w0].first * fpix * C;
       size_t total = (size_t)nn * (2 * FH) * (2 * FW) * (C / 8);
-      upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->xw16.as<__half>(), nn, FH, FW, C, h->up1.as<__half>());
+      upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(xin, nn, FH, FW, C, h->up1.as<__half>());
       CK(cudaGetLastError());
       ++c.launches;
       ConvIO a;
@@ -887,6 +917,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
     h->use_graph = !env_flag("VSR_NO_GRAPH", false);
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
+    if (getenv("VSR_WINDOW_GROUP")) h->window_group = (size_t)std::min(2, std::max(1, atoi(getenv("VSR_WINDOW_GROUP"))));
     *out = h;
   });
 }
@@ -1246,7 +1277,8 @@ int vsr_op_patch_attention(int device, const float* q, const float* k, const flo
     AttnWorkspace ws;
     int pwi[4], phi[4];
     for (int i = 0; i < n_patch && i < 4; ++i) { pwi[i] = pw[i]; phi[i] = ph[i]; }
-    run_attention(o.c, ws, dq.as<__half>(), 3 * C, 0, C, 2 * C, T, H, W, C, n_patch, pwi, phi, dout.as<__half>(), C);
+    run_attention(o.c, ws, dq.as<__half>(), 3 * C, 0, C, 2 * C, std::vector<AttnSegment>{{0, T}}, H, W, C, n_patch, pwi, phi,
+                  dout.as<__half>(), C);
     o.sync();
     from_half_dev(dout.as<__half>(), out, npix * C, o.c.stream);
   });

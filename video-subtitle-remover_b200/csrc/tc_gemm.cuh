@@ -34,8 +34,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
+  // per-epilogue-warp 32x33 fp32 transpose scratch (policies that store row-scattered data coalesce through it)
+  __shared__ float epi_scratch[P::EPI_SCRATCH ? 4 * 32 * 33 : 1];
 
   const long long t_kernel0 = TC_PROF_NOW();
+  (void)t_kernel0;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -119,18 +122,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       TC_PROF_WAIT(w_tfull, smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
       tc_fence_after();
       const long long e0 = TC_PROF_NOW();
+      (void)e0;
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
       typename P::RowCtx ctx = P::row_begin(prm, tile, row);
       if constexpr (BN >= 32) {
         for (int c = 0; c < tile.n_cols; c += 32) {
           float v[32];
           tmem_ld32(taddr + c, v);
-          P::epilogue(prm, tile, ctx, row, c, v);
+          P::epilogue(prm, tile, ctx, row, c, v, epi_scratch + (P::EPI_SCRATCH ? quarter * 32 * 33 : 0));
         }
       } else {
         float v[32];
         tmem_ld16(taddr, v);
-        P::epilogue(prm, tile, ctx, row, 0, v);
+        P::epilogue(prm, tile, ctx, row, 0, v, epi_scratch + (P::EPI_SCRATCH ? quarter * 32 * 33 : 0));
       }
       tc_fence_before();
       __syncwarp();

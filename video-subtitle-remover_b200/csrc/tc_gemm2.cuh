@@ -4,7 +4,8 @@
 // tile — the single-CTA conv kernel was measured L2-fill-bound (1.06 GB of operands in 82 us).
 // The leader CTA (cluster rank 0) issues the MMAs for the pair; every CTA keeps 128 rows of the
 // accumulator in its own TMEM and runs its own epilogue.
-//   full[s]    : in the leader, 2 arrivals (one expect_tx per CTA) + all TMA bytes of both CTAs
+//   full[s]    : in the leader, 1 arrival (the leader's expect_tx for the bytes of BOTH CTAs); the peer's TMA
+//                loads complete_tx on it directly (no remote arrive on the critical path)
 //   empty[s]   : per CTA, released by a multicast tcgen05.commit from the leader
 //   tfull[a]   : per CTA, multicast commit;   tempty[a] : in the leader, 8 arrivals (4 warps x 2 CTAs)
 #pragma once
@@ -28,8 +29,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
+  // per-epilogue-warp 32x33 fp32 transpose scratch (policies that store row-scattered data coalesce through it)
+  __shared__ float epi_scratch[P::EPI_SCRATCH ? 4 * 32 * 33 : 1];
 
   const long long t_kernel0 = TC_PROF_NOW();
+  (void)t_kernel0;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -37,7 +41,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 2);
+      mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -65,7 +69,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           TC_PROF_WAIT(w_empty, smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
           const uint32_t leader_full = mapa_cluster(smem_u32(&bar_full[stage]), 0);
-          P::load(prm, tile, k, sA, sA + TC_A_BYTES, leader_full, rank);
+          P::load(prm, tile, k, sA, sA + TC_A_BYTES, smem_u32(&bar_full[stage]), leader_full, rank);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -113,12 +117,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       TC_PROF_WAIT(w_tfull, smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
       tc_fence_after();
       const long long e0 = TC_PROF_NOW();
+      (void)e0;
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
       typename P::RowCtx ctx = P::row_begin(prm, tile, row);
       for (int c = 0; c < tile.n_cols; c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
-        P::epilogue(prm, tile, ctx, row, c, v);
+        P::epilogue(prm, tile, ctx, row, c, v, epi_scratch + (P::EPI_SCRATCH ? quarter * 32 * 33 : 0));
       }
       tc_fence_before();
       __syncwarp();
