@@ -207,20 +207,32 @@ def main():
     dev_ms = float(t.item())
 
     # ---- end-to-end leg: host numpy frames in, host numpy frames out --------------------------
+    # (a) the chunk loop of STTNAutoInpaint.__call__: two chunks in flight (submit / collect), every step
+    #     still pays its own host->pinned copy, H2D, kernels, D2H and pinned->host copy
     for _ in range(2):
         eng.inpaint_inplace([f.copy() for f in frames], mask)
     batches = [[f.copy() for f in frames] for _ in range(args.steps)]
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    prev = None
+    for b in batches:
+        t = eng.submit(b, mask)
+        if prev is not None:
+            eng.collect(prev[0], prev[1])
+        prev = (t, b)
+    eng.collect(prev[0], prev[1])
+    e2e_s = time.perf_counter() - t0
+    # (b) strictly synchronous calls, one chunk at a time
+    batches = [[f.copy() for f in frames] for _ in range(args.steps)]
+    t0 = time.perf_counter()
     for b in batches:
         eng.inpaint_inplace(b, mask)
-    eng.sync()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    e2e_sync_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s, e2e_sync_s = float(t[0].item()), float(t[1].item())
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel (3x3 conv 256->256 on a 15-frame window) --------------
@@ -260,7 +272,9 @@ def main():
                        "l2": "per-step working set (104 MB strips + ~0.9 GB activations) exceeds the 126 MB L2",
                        "parallelism": f"chunk-per-rank x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": total_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": strip_bytes,
-                    "d2h_bytes_per_step": strip_bytes, "api": "STTNInpaint.inpaint_inplace(frames, mask) on numpy frames"},
+                    "d2h_bytes_per_step": strip_bytes,
+                    "api": "STTNInpaint.submit/collect on numpy frames (the chunk loop of STTNAutoInpaint.__call__, two chunks in flight)",
+                    "sync_value": total_frames / e2e_sync_s, "sync_api": "STTNInpaint.inpaint_inplace(frames, mask), one chunk at a time"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -72,6 +72,14 @@ int vsr_sttn_stage(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H,
 int vsr_sttn_compute(vsr_sttn_t* h);
 int vsr_sttn_fetch(vsr_sttn_t* h, uint8_t* const* frames_out);
 int vsr_sttn_sync(vsr_sttn_t* h);
+/* Asynchronous form of vsr_sttn_inpaint_frames for the chunk loop of STTNAutoInpaint.__call__
+ * (sttn_auto_inpaint.py:242-328): submit() copies the strips to pinned memory and enqueues H2D, kernels and
+ * D2H, returning a ticket (>= 0) without waiting; collect() waits for that chunk and writes the result into
+ * frames_out (which may be the submitted frames).  At most two chunks may be in flight; the frames passed
+ * to submit() must stay valid and unmodified until their collect(); the mask must produce exactly one strip
+ * and may only change while nothing is in flight. */
+int64_t vsr_sttn_submit(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask);
+int vsr_sttn_collect(vsr_sttn_t* h, int64_t ticket, uint8_t* const* frames_out);
 /* CUDA stream of the engine (cudaStream_t as void*) so callers can bracket it with events. */
 void* vsr_sttn_stream(vsr_sttn_t* h);
 /* kernels launched by this engine since creation (bench.py `gpu_launches`) */

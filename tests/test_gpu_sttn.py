@@ -102,6 +102,25 @@ def test_call_inplace_equals_copy(rand_engine):
     _check_images(out, O.sttn_call(w, frames, mask))
 
 
+def test_async_pipeline_equals_sync(rand_engine):
+    """submit/collect (two chunks in flight) returns the same bytes as the synchronous call."""
+    eng, _ = rand_engine
+    H, W, T = 270, 480, 7
+    mask = O.default_mask(H, W)
+    chunks = [O.synthetic_clip(T, H, W, seed=40 + i) for i in range(4)]
+    want = [eng(c, mask) for c in chunks]
+    work = [[f.copy() for f in c] for c in chunks]
+    prev = None
+    for wk in work:
+        t = eng.submit(wk, mask)
+        if prev is not None:
+            eng.collect(prev[0], prev[1])
+        prev = (t, wk)
+    eng.collect(prev[0], prev[1])
+    for a, b in zip(want, work):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_edge_cases(rand_engine):
     eng, w = rand_engine
     H, W = 270, 480

@@ -63,6 +63,8 @@ _PROTOS = {
     "vsr_sttn_stage": (C.c_int, [C.c_void_p, _pp, C.c_int, C.c_int, C.c_int, _u8p]),
     "vsr_sttn_compute": (C.c_int, [C.c_void_p]),
     "vsr_sttn_fetch": (C.c_int, [C.c_void_p, _pp]),
+    "vsr_sttn_submit": (C.c_int64, [C.c_void_p, _pp, C.c_int, C.c_int, C.c_int, _u8p]),
+    "vsr_sttn_collect": (C.c_int, [C.c_void_p, C.c_int64, _pp]),
     "vsr_sttn_sync": (C.c_int, [C.c_void_p]),
     "vsr_sttn_stream": (C.c_void_p, [C.c_void_p]),
     "vsr_sttn_launch_count": (C.c_int64, [C.c_void_p]),

@@ -10,6 +10,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vsr_b200.h"
@@ -497,12 +498,28 @@ struct vsr_sttn {
   int T = 0, H = 0, W = 0, split_h = 0;
   std::vector<std::array<int, 4>> areas;
   std::vector<const uint8_t*> in_ptrs;
+  std::vector<uint8_t> mask_h;  // last mask seen (host copy) — the whole-video driver passes the same mask per chunk
+  int mask_H = 0;
   int staged_area = -1;
   std::vector<int> visits_h;
   int sched_T = -1;
   std::vector<Window> sched;
   uint8_t* pinned = nullptr;
   size_t pinned_n = 0;
+  // two-deep asynchronous pipeline (vsr_sttn_submit / vsr_sttn_collect): H2D of chunk i+1 and D2H of chunk i-1
+  // overlap the kernels of chunk i on a separate copy stream
+  struct Slot {
+    DevBuf dev_in, dev_out;
+    uint8_t* pin_in = nullptr;
+    uint8_t* pin_out = nullptr;
+    size_t pin_n = 0;
+    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
+    bool busy = false;
+    int T = 0, y0 = 0, sh = 0, sw = 0;
+    std::vector<const uint8_t*> in_ptrs;
+  } slot[2];
+  cudaStream_t copy_stream = nullptr;
+  int64_t next_ticket = 0;
   // CUDA graph of one chunk's compute (launch-bound inner loop: ~630 kernels + ~200 D2D copies)
   bool use_graph = true;
   size_t window_group = 2;  // windows sharing each launch (VSR_WINDOW_GROUP, 1..2)
@@ -512,6 +529,14 @@ struct vsr_sttn {
   int64_t graph_launches = 0;
   ~vsr_sttn() {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (auto& sl : slot) {
+      if (sl.pin_in) cudaFreeHost(sl.pin_in);
+      if (sl.pin_out) cudaFreeHost(sl.pin_out);
+      if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+      if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+      if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (pinned) cudaFreeHost(pinned);
     if (ctx.stream) cudaStreamDestroy(ctx.stream);
   }
@@ -733,6 +758,25 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh) {
   }
 }
 
+// Strided host copies (frame strips <-> pinned staging) on a few threads: one thread moves ~10 GB/s, the
+// 104 MB of a 1080p chunk would otherwise cost ~10 ms each way.
+template <class F>
+static void parallel_for(int n, F&& f) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<unsigned>(8, hw ? hw : 1);
+  if (nt > n) nt = n;
+  if (nt <= 1) {
+    for (int i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&, t] {
+      for (int i = t; i < n; i += nt) f(i);
+    });
+  for (auto& x : th) x.join();
+}
+
 static void ensure_pinned(vsr_sttn* h, size_t bytes) {
   if (bytes <= h->pinned_n) return;
   if (h->pinned) CK(cudaFreeHost(h->pinned));
@@ -761,7 +805,7 @@ static void stage_area(vsr_sttn* h, int k) {
   const size_t sb = (size_t)sh * sw * 3;
   h->strips.ensure(sb * h->T);
   ensure_pinned(h, sb * h->T);
-  for (int t = 0; t < h->T; ++t) memcpy(h->pinned + t * sb, h->in_ptrs[t] + (size_t)y0 * sw * 3, sb);
+  parallel_for(h->T, [&](int t) { memcpy(h->pinned + t * sb, h->in_ptrs[t] + (size_t)y0 * sw * 3, sb); });
   CK(cudaMemcpyAsync(h->strips.p, h->pinned, sb * h->T, cudaMemcpyHostToDevice, h->ctx.stream));
   h->staged_area = k;
 }
@@ -833,7 +877,7 @@ static void fetch_area(vsr_sttn* h, int k, uint8_t* const* out) {
   const size_t sb = (size_t)sh * sw * 3;
   CK(cudaMemcpyAsync(h->pinned, h->strips.p, sb * h->T, cudaMemcpyDeviceToHost, h->ctx.stream));
   sync_stream(h);
-  for (int t = 0; t < h->T; ++t) memcpy(out[t] + (size_t)y0 * sw * 3, h->pinned + t * sb, sb);
+  parallel_for(h->T, [&](int t) { memcpy(out[t] + (size_t)y0 * sw * 3, h->pinned + t * sb, sb); });
 }
 
 static void stage(vsr_sttn* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask) {
@@ -841,15 +885,100 @@ static void stage(vsr_sttn* h, const uint8_t* const* frames_in, int T, int H, in
   REQUIRE(T >= 1 && H >= 1 && W >= 1 && frames_in && mask, "bad frame batch");
   h->T = T; h->H = H; h->W = W;
   h->split_h = (int)((double)W * 3 / 16);  // sttn_auto_inpaint.py:54
-  std::vector<uint8_t> m01((size_t)H * W);
-  for (size_t i = 0; i < m01.size(); ++i) m01[i] = mask[i] > 127 ? 1 : 0;  // cv2.threshold(mask,127,1,BINARY) :48
-  h->areas = host_inpaint_areas(W, H, h->split_h, m01.data(), 1);
   h->in_ptrs.assign(frames_in, frames_in + T);
-  h->mask_d.ensure(m01.size());
-  CK(cudaMemcpyAsync(h->mask_d.p, m01.data(), m01.size(), cudaMemcpyHostToDevice, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  const size_t mb = (size_t)H * W;
+  if (h->mask_h.size() != mb || h->mask_H != H || memcmp(h->mask_h.data(), mask, mb) != 0) {  // same mask: keep strips + device copy
+    h->mask_h.assign(mask, mask + mb);
+    h->mask_H = H;
+    std::vector<uint8_t> m01(mb);
+    for (size_t i = 0; i < mb; ++i) m01[i] = mask[i] > 127 ? 1 : 0;  // cv2.threshold(mask,127,1,BINARY) :48
+    h->areas = host_inpaint_areas(W, H, h->split_h, m01.data(), 1);
+    h->mask_d.ensure(mb);
+    CK(cudaMemcpyAsync(h->mask_d.p, m01.data(), mb, cudaMemcpyHostToDevice, h->ctx.stream));
+    CK(cudaStreamSynchronize(h->ctx.stream));
+  }
   h->staged_area = -1;
   if (!h->areas.empty()) stage_area(h, 0);
+}
+
+// ---- asynchronous chunk pipeline ------------------------------------------------------------------
+static int64_t submit(vsr_sttn* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask) {
+  check_ready(h);
+  REQUIRE(T >= 1 && H >= 1 && W >= 1 && frames_in && mask, "bad frame batch");
+  const int64_t ticket = h->next_ticket;
+  vsr_sttn::Slot& sl = h->slot[ticket & 1];
+  if (sl.busy) throw Error(VSR_ERR_STATE, "vsr_sttn_submit: two chunks already in flight, collect one first");
+  // mask analysis (cached) — same as the synchronous path
+  h->T = T; h->H = H; h->W = W;
+  h->split_h = (int)((double)W * 3 / 16);
+  const size_t mb = (size_t)H * W;
+  if (h->mask_h.size() != mb || h->mask_H != H || memcmp(h->mask_h.data(), mask, mb) != 0) {
+    // a new mask re-uploads on the compute stream: drain the pipeline first
+    for (auto& o : h->slot)
+      if (o.busy) throw Error(VSR_ERR_STATE, "vsr_sttn_submit: the mask may only change when no chunk is in flight");
+    h->mask_h.assign(mask, mask + mb);
+    h->mask_H = H;
+    std::vector<uint8_t> m01(mb);
+    for (size_t i = 0; i < mb; ++i) m01[i] = mask[i] > 127 ? 1 : 0;
+    h->areas = host_inpaint_areas(W, H, h->split_h, m01.data(), 1);
+    h->mask_d.ensure(mb);
+    CK(cudaMemcpyAsync(h->mask_d.p, m01.data(), mb, cudaMemcpyHostToDevice, h->ctx.stream));
+    CK(cudaStreamSynchronize(h->ctx.stream));
+  }
+  if (h->areas.size() != 1) throw Error(VSR_ERR_STATE, "vsr_sttn_submit handles exactly one strip; use vsr_sttn_inpaint_frames");
+  if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (!sl.ev_h2d) {
+    CK(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.ev_d2h, cudaEventDisableTiming));
+  }
+  const int y0 = h->areas[0][0], sh = h->areas[0][1] - y0, sw = W;
+  const size_t sb = (size_t)sh * sw * 3, total = sb * T;
+  if (total > sl.pin_n) {
+    if (sl.pin_in) CK(cudaFreeHost(sl.pin_in));
+    if (sl.pin_out) CK(cudaFreeHost(sl.pin_out));
+    sl.pin_in = sl.pin_out = nullptr;
+    CK(cudaMallocHost(&sl.pin_in, total));
+    CK(cudaMallocHost(&sl.pin_out, total));
+    sl.pin_n = total;
+  }
+  sl.dev_in.ensure(total);
+  sl.dev_out.ensure(total);
+  h->strips.ensure(total);
+  sl.T = T; sl.y0 = y0; sl.sh = sh; sl.sw = sw;
+  sl.in_ptrs.assign(frames_in, frames_in + T);
+  parallel_for(T, [&](int t) { memcpy(sl.pin_in + t * sb, frames_in[t] + (size_t)y0 * sw * 3, sb); });
+  CK(cudaMemcpyAsync(sl.dev_in.p, sl.pin_in, total, cudaMemcpyHostToDevice, h->copy_stream));
+  CK(cudaEventRecord(sl.ev_h2d, h->copy_stream));
+  CK(cudaStreamWaitEvent(h->ctx.stream, sl.ev_h2d, 0));
+  CK(cudaMemcpyAsync(h->strips.p, sl.dev_in.p, total, cudaMemcpyDeviceToDevice, h->ctx.stream));
+  h->in_ptrs = sl.in_ptrs;
+  h->staged_area = 0;
+  compute_area(h, 0);
+  CK(cudaMemcpyAsync(sl.dev_out.p, h->strips.p, total, cudaMemcpyDeviceToDevice, h->ctx.stream));
+  CK(cudaEventRecord(sl.ev_done, h->ctx.stream));
+  CK(cudaStreamWaitEvent(h->copy_stream, sl.ev_done, 0));
+  CK(cudaMemcpyAsync(sl.pin_out, sl.dev_out.p, total, cudaMemcpyDeviceToHost, h->copy_stream));
+  CK(cudaEventRecord(sl.ev_d2h, h->copy_stream));
+  sl.busy = true;
+  ++h->next_ticket;
+  return ticket;
+}
+
+static void collect(vsr_sttn* h, int64_t ticket, uint8_t* const* frames_out) {
+  check_ready(h);
+  REQUIRE(ticket >= 0 && ticket < h->next_ticket && frames_out, "bad ticket");
+  vsr_sttn::Slot& sl = h->slot[ticket & 1];
+  if (!sl.busy) throw Error(VSR_ERR_STATE, "vsr_sttn_collect: ticket already collected");
+  cudaError_t e = cudaEventSynchronize(sl.ev_d2h);
+  if (e != cudaSuccess)
+    throw Error(VSR_ERR_CUDA, std::string("cudaEventSynchronize -> ") + cudaGetErrorString(e) + device_error_report());
+  const size_t sb = (size_t)sl.sh * sl.sw * 3, fb = (size_t)h->H * h->W * 3;
+  parallel_for(sl.T, [&](int t) {
+    if (frames_out[t] != sl.in_ptrs[t]) memcpy(frames_out[t], sl.in_ptrs[t], fb);
+    memcpy(frames_out[t] + (size_t)sl.y0 * sl.sw * 3, sl.pin_out + t * sb, sb);
+  });
+  sl.busy = false;
 }
 
 }  // namespace vsr
@@ -983,8 +1112,9 @@ int vsr_sttn_fetch(vsr_sttn_t* h, uint8_t* const* frames_out) {
     check_ready(h);
     REQUIRE(h->T > 0 && frames_out, "nothing staged");
     const size_t fb = (size_t)h->H * h->W * 3;
-    for (int t = 0; t < h->T; ++t)
+    parallel_for(h->T, [&](int t) {
       if (frames_out[t] != h->in_ptrs[t]) memcpy(frames_out[t], h->in_ptrs[t], fb);  // the copy at sttn_auto_inpaint.py:58
+    });
     if (h->areas.empty()) return;
     fetch_area(h, 0, frames_out);
     // further strips (rare: several disjoint subtitle bands) run back to back
@@ -1003,6 +1133,16 @@ int vsr_sttn_inpaint_frames(vsr_sttn_t* h, const uint8_t* const* frames_in, int 
   r = vsr_sttn_compute(h);
   if (r) return r;
   return vsr_sttn_fetch(h, frames_out);
+}
+
+int64_t vsr_sttn_submit(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask) {
+  int64_t ticket = -1;
+  int r = guarded([&] { ticket = submit(h, frames_in, T, H, W, mask); });
+  return r ? (int64_t)r : ticket;
+}
+
+int vsr_sttn_collect(vsr_sttn_t* h, int64_t ticket, uint8_t* const* frames_out) {
+  return guarded([&] { collect(h, ticket, frames_out); });
 }
 
 int vsr_sttn_sync(vsr_sttn_t* h) {

@@ -175,6 +175,25 @@ class STTNInpaint:
         pout, keep = self._ptr_array(list(frames_out))
         _capi.check(_capi.lib().vsr_sttn_fetch(self._h, C.cast(pout, C.POINTER(C.c_void_p))))
 
+    # asynchronous chunk pipeline (two chunks in flight)
+    def submit(self, frames, mask) -> int:
+        """Enqueue one chunk (strips H2D, kernels, D2H) and return a ticket; `frames` must stay alive and
+        unmodified until `collect(ticket, ...)`."""
+        frames = list(frames)
+        H, W, m = self._check_batch(frames, mask)
+        pin, keep = self._ptr_array(frames)
+        t = int(_capi.lib().vsr_sttn_submit(self._h, C.cast(pin, C.POINTER(C.c_void_p)), len(frames), H, W,
+                                            _capi.ptr(m, C.c_uint8)))
+        _capi.check(t)
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t] = (keep, m)
+        return t
+
+    def collect(self, ticket: int, frames_out) -> None:
+        pout, keep = self._ptr_array(list(frames_out))
+        _capi.check(_capi.lib().vsr_sttn_collect(self._h, ticket, C.cast(pout, C.POINTER(C.c_void_p))))
+        self._inflight.pop(ticket, None)
+
     def sync(self):
         _capi.check(_capi.lib().vsr_sttn_sync(self._h))
 
@@ -243,6 +262,24 @@ class STTNAutoInpaint:
             else:
                 mask = input_mask
             n, gap = info["len"], self.clip_gap
+            gui = input_sub_remover is not None and getattr(input_sub_remover, "gui_mode", False)
+            eng = self.sttn_inpaint
+            single_strip = len(get_inpaint_area_by_mask(info["W_ori"], info["H_ori"], int(info["W_ori"] * 3 / 16),
+                                                       (np.asarray(mask) > 127).astype(np.uint8))) == 1
+
+            def finish(job):
+                frames, originals, sel, ticket = job
+                if ticket is not None:
+                    eng.collect(ticket, [frames[i] for i in sel])
+                for i, frame in enumerate(frames):
+                    writer.write(frame)
+                    if input_sub_remover is not None:
+                        if tbar is not None:
+                            input_sub_remover.update_progress(tbar, increment=1)
+                        if gui:
+                            input_sub_remover.update_preview_with_comp(originals[i], frame)
+
+            pending = None  # chunk whose kernels are running while the next one is decoded and uploaded
             for start in range(0, n, gap):
                 end = min(start + gap, n)
                 frames = []
@@ -255,18 +292,19 @@ class STTNAutoInpaint:
                 if not frames:
                     print(f"Warning: No valid frames found in range {start + 1}-{end}. Skipping this segment.")
                     continue
-                gui = input_sub_remover is not None and getattr(input_sub_remover, "gui_mode", False)
                 originals = [f.copy() for f in frames] if gui else None
                 sel = [i for i in range(len(frames)) if _in_ab_sections(start + i, ab_sections)]
+                ticket = None
                 if sel:
-                    self.sttn_inpaint.inpaint_inplace([frames[i] for i in sel], mask)
-                for i, frame in enumerate(frames):
-                    writer.write(frame)
-                    if input_sub_remover is not None:
-                        if tbar is not None:
-                            input_sub_remover.update_progress(tbar, increment=1)
-                        if gui:
-                            input_sub_remover.update_preview_with_comp(originals[i], frame)
+                    if single_strip:
+                        ticket = eng.submit([frames[i] for i in sel], mask)
+                    else:
+                        eng.inpaint_inplace([frames[i] for i in sel], mask)
+                if pending is not None:
+                    finish(pending)
+                pending = (frames, originals, sel, ticket)
+            if pending is not None:
+                finish(pending)
         except _capi.VsrError:
             raise  # engine / CUDA failures are never swallowed
         except Exception as e:  # the reference prints and carries on (:329-331)
