@@ -14,7 +14,7 @@ import numpy as np  # noqa: E402
 from oracle import sttn_oracle as O  # noqa: E402
 from vsr_b200 import STTNInpaint, _capi, ops  # noqa: E402
 
-NAMES = {0: "conv256 1-CTA", 1: "conv256 2-CTA pair", 2: "scores", 3: "pv", 4: "conv BN<256"}
+NAMES = {0: "conv256 1-CTA", 1: "conv256 2-CTA pair", 2: "scores", 3: "pv", 4: "conv BN<256", 5: "scores 2-CTA", 6: "pv 2-CTA"}
 SLOTS = ["producer waits empty", "mma waits operands", "mma waits accumulator", "epilogue waits accumulator", "epilogue busy",
          "kernel cycles"]
 

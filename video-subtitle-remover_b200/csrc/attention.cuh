@@ -15,6 +15,7 @@
 //   pv     : O[qp, pos,:] = (sum_kp P[qp,kp] V_pos[kp,:]) / rowsum[qp]  -> written back in NHWC
 #pragma once
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 
 namespace vsr {
 
@@ -26,6 +27,7 @@ struct AttnHead {
   int nk64;        // 64-token K-chunks of the PV GEMM that contain real tokens
   int splits, chunks_per_split;  // score GEMM split-K
   int score_work_begin, pv_work_begin;
+  int score_work_begin2, pv_work_begin2;  // CTA-pair work lists
   int pv_ntiles;   // ceil(npos / 4)
   int ldS, ldP;    // row pitches (elements)
   long long slabS; // elements between split-K slabs of S (ntt*128*ldS)
@@ -40,7 +42,7 @@ constexpr int ATTN_MAX_HEADS = 8;  // (windows in a group) x (patch geometries)
 struct ScoreParams {
   CUtensorMap qmap[ATTN_MAX_HEADS], kmap[ATTN_MAX_HEADS];
   AttnHead h[ATTN_MAX_HEADS];
-  int nheads, total_work;
+  int nheads, total_work, total_work2;
 };
 
 struct ScorePolicy {
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
 struct PVParams {
   CUtensorMap pmap[ATTN_MAX_HEADS], vmap[ATTN_MAX_HEADS];
   AttnHead h[ATTN_MAX_HEADS];
-  int nheads, total_work;
+  int nheads, total_work, total_work2;
   int T, H, W;       // feature map geometry
   __half* out;       // NHWC fp16 [T,H,W,out_pitch]; entry s writes channels [coff[s], coff[s]+64) of the frames
   int out_pitch;     // starting at element offset out_off[s] (its window's first frame)
@@ -278,6 +280,100 @@ struct PVPolicy {
       for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(v[i + 2 * j] * c.inv, v[i + 2 * j + 1] * c.inv);
       *reinterpret_cast<uint4*>(o + i) = *reinterpret_cast<const uint4*>(hh);
     }
+  }
+};
+
+// ---- CTA-pair (cta_group::2) versions: 256 queries x 256 keys / 256 queries x 4 positions per pair -------
+// Same math and epilogues as ScorePolicy / PVPolicy; each CTA loads its own 128 query rows and its own half
+// of the B operand (one 128-key tile / two of the four value positions): 32 KB instead of 48 KB per stage
+// and six stages in flight instead of four.
+struct Score2Policy {
+  static constexpr int STAGES = 6;
+  static constexpr int B_MN_MAJOR = 0;
+  static constexpr int PROF_ID = 5;
+  static constexpr bool EPI_SCRATCH = true;
+  using Params = ScoreParams;
+  using Tile = ScorePolicy::Tile;
+  using RowCtx = ScorePolicy::RowCtx;
+  __device__ static void prefetch(const Params& p) { ScorePolicy::prefetch(p); }
+  __device__ static int num_tiles(const Params& p) { return p.total_work2; }
+  __device__ static Tile get_tile(const Params& p, int idx, uint32_t rank) {
+    int hd = 0;
+    while (hd + 1 < p.nheads && idx >= p.h[hd + 1].score_work_begin2) ++hd;
+    const AttnHead& h = p.h[hd];
+    idx -= h.score_work_begin2;
+    Tile t;
+    t.head = hd;
+    const int sp = idx % h.splits;
+    idx /= h.splits;
+    const int nkt2 = (h.ntt + 1) >> 1;
+    t.kj = idx % nkt2;
+    t.qi = (idx / nkt2) * 2 + (int)rank;   // this CTA's 128-query tile (may be == ntt: dummy, zero-filled)
+    t.kbeg = sp * h.chunks_per_split;
+    t.num_k = min(h.chunks_per_split, h.npos - t.kbeg);
+    t.nkt = min(2, h.ntt - 2 * t.kj);
+    t.n_cols = (t.qi < h.ntt) ? 128 * t.nkt : 0;
+    t.split = sp;
+    return t;
+  }
+  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t local_full,
+                              uint32_t leader_full, uint32_t rank) {
+    const AttnHead& h = p.h[t.head];
+    const int pos = t.kbeg + k;
+    const int py = pos / h.pw, px = pos - py * h.pw;
+    const int rows = 128 / h.owp;
+    if (rank == 0) mbar_expect_tx(local_full, (uint32_t)((2 + t.nkt) * TC_A_BYTES));
+    tma_load_5d_2sm(sA, &p.qmap[t.head], leader_full, 0, px, 0, py, t.qi * rows);
+    if ((int)rank < t.nkt) tma_load_5d_2sm(sB, &p.kmap[t.head], leader_full, 0, px, 0, py, (2 * t.kj + (int)rank) * rows);
+  }
+  __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) { return ScorePolicy::row_begin(p, t, row); }
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float* scr) {
+    ScorePolicy::epilogue(p, t, c, row, col0, v, scr);
+  }
+};
+
+struct PV2Policy {
+  static constexpr int STAGES = 6;
+  static constexpr int B_MN_MAJOR = 1;
+  static constexpr int PROF_ID = 6;
+  static constexpr bool EPI_SCRATCH = false;
+  using Params = PVParams;
+  using Tile = PVPolicy::Tile;
+  using RowCtx = PVPolicy::RowCtx;
+  __device__ static void prefetch(const Params& p) { PVPolicy::prefetch(p); }
+  __device__ static int num_tiles(const Params& p) { return p.total_work2; }
+  __device__ static Tile get_tile(const Params& p, int idx, uint32_t rank) {
+    int hd = 0;
+    while (hd + 1 < p.nheads && idx >= p.h[hd + 1].pv_work_begin2) ++hd;
+    const AttnHead& h = p.h[hd];
+    idx -= h.pv_work_begin2;
+    Tile t;
+    t.head = hd;
+    t.ni = idx % h.pv_ntiles;
+    t.mi = (idx / h.pv_ntiles) * 2 + (int)rank;  // dummy when == ntt: P rows beyond the tensor are zero-filled
+    t.nvalid = min(4, h.npos - t.ni * 4);
+    t.num_k = h.nk64;
+    t.n_cols = t.nvalid * 64;
+    return t;
+  }
+  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t local_full,
+                              uint32_t leader_full, uint32_t rank) {
+    const AttnHead& h = p.h[t.head];
+    if (rank == 0) mbar_expect_tx(local_full, (uint32_t)(2 * TC_A_BYTES + t.nvalid * 8192));
+    tma_load_2d_2sm(sA, &p.pmap[t.head], leader_full, k * 64, t.mi * 128);
+    const int rows = 64 / h.owp;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int pos = t.ni * 4 + 2 * (int)rank + j;
+      if (pos < h.npos) {
+        const int py = pos / h.pw, px = pos - py * h.pw;
+        tma_load_5d_2sm(sB + j * 8192, &p.vmap[t.head], leader_full, 0, px, 0, py, k * rows);
+      }
+    }
+  }
+  __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) { return PVPolicy::row_begin(p, t, row); }
+  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float* scr) {
+    PVPolicy::epilogue(p, t, c, row, col0, v, scr);
   }
 };
 

@@ -160,6 +160,7 @@ struct Conv2Policy {
   static constexpr int STAGES = 6;
   static constexpr int PROF_ID = 1;
   static constexpr bool EPI_SCRATCH = false;
+  static constexpr int B_MN_MAJOR = 0;
   using Base = ConvPolicy<256>;
   using Params = ConvParams;
   using Tile = Base::Tile;

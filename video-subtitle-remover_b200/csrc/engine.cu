@@ -143,6 +143,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
+  bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
 };
 
 static bool env_flag(const char* name, bool dflt) {
@@ -165,17 +166,18 @@ static void launch_tc(Ctx& c, const typename P::Params& prm, int ntiles) {
   ++c.launches;
 }
 
-static void launch_tc2_conv(Ctx& c, const ConvParams& prm, int ntiles) {
+template <class P>
+static void launch_tc2(Ctx& c, const typename P::Params& prm, int ntiles) {
   static bool configured = false;
-  constexpr int smem = tc2_smem_bytes<Conv2Policy>();
+  constexpr int smem = tc2_smem_bytes<P>();
   if (!configured) {
-    CK(cudaFuncSetAttribute(tc_gemm2_kernel<Conv2Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(tc_gemm2_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   if (ntiles <= 0) return;
   const int pairs = c.sms / 2;
   const int grid = 2 * (ntiles < pairs ? ntiles : pairs);
-  tc_gemm2_kernel<Conv2Policy><<<grid, TC_THREADS, smem, c.stream>>>(prm);
+  tc_gemm2_kernel<P><<<grid, TC_THREADS, smem, c.stream>>>(prm);
   CK(cudaGetLastError());
   ++c.launches;
 }
@@ -323,7 +325,7 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
     const uint64_t str[1] = {(uint64_t)L.K * 2};
     const uint32_t box[2] = {64, 128};
     p.w_map_half = make_map_f16(L.w.p, 2, dims, str, box);
-    launch_tc2_conv(c, p, ((p.T * p.tiles_y * p.tiles_x + 1) / 2) * p.n_tiles);
+    launch_tc2<Conv2Policy>(c, p, ((p.T * p.tiles_y * p.tiles_x + 1) / 2) * p.n_tiles);
     return;
   }
   switch (L.bn) {
@@ -374,7 +376,7 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
       ents.push_back({g, i, n * n * 64.0 * pw[i] * ph[i]});
     }
   std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.work > b.work; });
-  int score_work = 0, pv_work = 0, max_rows = 0;
+  int score_work = 0, pv_work = 0, score_work2 = 0, pv_work2 = 0, max_rows = 0;
   for (int s = 0; s < nent; ++s) {
     const int i = ents[s].patch;
     const AttnSegment& sg = segs[ents[s].seg];
@@ -403,9 +405,13 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     h.splits = (h.npos + h.chunks_per_split - 1) / h.chunks_per_split;
     h.score_work_begin = score_work;
     score_work += tiles * h.splits;
+    h.score_work_begin2 = score_work2;
+    score_work2 += ((h.ntt + 1) / 2) * ((h.ntt + 1) / 2) * h.splits;
     h.pv_ntiles = (h.npos + 3) / 4;
     h.pv_work_begin = pv_work;
     pv_work += h.ntt * h.pv_ntiles;
+    h.pv_work_begin2 = pv_work2;
+    pv_work2 += ((h.ntt + 1) / 2) * h.pv_ntiles;
     h.ldS = h.ntt * 128;
     h.ldP = h.ntt * 128;
     h.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)dk * h.npos));
@@ -440,10 +446,13 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   sp.nheads = pp.nheads = nent;
   sp.total_work = score_work;
   pp.total_work = pv_work;
+  sp.total_work2 = score_work2;
+  pp.total_work2 = pv_work2;
   pp.T = 0; pp.H = H; pp.W = W;
   pp.out = out;
   pp.out_pitch = out_pitch;
-  launch_tc<ScorePolicy>(c, sp, score_work);
+  if (c.attn_2cta) launch_tc2<Score2Policy>(c, sp, score_work2);
+  else launch_tc<ScorePolicy>(c, sp, score_work);
   {
     int max_cols = 0;
     for (int s2 = 0; s2 < nent; ++s2) max_cols = std::max(max_cols, sp.h[s2].nk64 * 64);
@@ -457,7 +466,8 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   }
   CK(cudaGetLastError());
   ++c.launches;
-  launch_tc<PVPolicy>(c, pp, pv_work);
+  if (c.attn_2cta) launch_tc2<PV2Policy>(c, pp, pv_work2);
+  else launch_tc<PVPolicy>(c, pp, pv_work);
 }
 
 // ------------------------------------------------------------------------------------------------ resize tables on device
@@ -1046,6 +1056,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
     h->use_graph = !env_flag("VSR_NO_GRAPH", false);
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
+    h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     if (getenv("VSR_WINDOW_GROUP")) h->window_group = (size_t)std::min(2, std::max(1, atoi(getenv("VSR_WINDOW_GROUP"))));
     *out = h;
   });
@@ -1287,6 +1298,7 @@ struct OpCtx {
     c.device = device;
     c.sms = prop.multiProcessorCount;
     c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
+    c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   }
   ~OpCtx() {

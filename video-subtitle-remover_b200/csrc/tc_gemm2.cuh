@@ -81,7 +81,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       TC_PROF_DECL(w_full);
       TC_PROF_DECL(w_tempty);
-      const uint32_t idesc = umma_idesc_f16(256, BN, 0, 0);
+      const uint32_t idesc = umma_idesc_f16(256, BN, 0, P::B_MN_MAJOR);
       for (int t = first; t < ntiles; t += step) {
         const typename P::Tile tile = P::get_tile(prm, t, 0);
         TC_PROF_WAIT(w_tempty, smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
@@ -93,9 +93,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
           const uint32_t sB = sA + TC_A_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_f16_2cta(d_tmem, umma_desc_sw128(sA + kk * 32, 16, 1024), umma_desc_sw128(sB + kk * 32, 16, 1024), idesc,
-                          (k | kk) != 0);
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bdesc = P::B_MN_MAJOR ? umma_desc_sw128(sB + kk * 2048, 8192, 1024)
+                                                 : umma_desc_sw128(sB + kk * 32, 16, 1024);
+            umma_f16_2cta(d_tmem, umma_desc_sw128(sA + kk * 32, 16, 1024), bdesc, idesc, (k | kk) != 0);
+          }
           umma_commit_2cta(smem_u32(&bar_empty[stage]), 3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
