@@ -9,9 +9,13 @@
 // into one box {64,1,owp,1,128/owp}.  owp = ow rounded up to a power of two; the padded token index is
 // kp = toh*owp + owi (pad slots are zero-filled by TMA and masked in the softmax).
 //
-//   scores : S[qp, kp]   = sum_pos Q_pos[qp,:] . K_pos[kp,:]          (fp32; split-K where tiles are few: each
-//            split writes its own slab and the softmax adds the slabs in a fixed order -> deterministic)
-//   softmax: P[qp, kp]   = exp((S - rowmax) / sqrt(D)) (fp16, un-normalised), rowsum[qp]
+//   Big problems (many tiles, `fused`): the scores never leave the SM.  Pass A computes S tiles and keeps
+//   only the per-(row, key-tile) max; pass B recomputes S and writes P = exp((S - rowmax)/sqrt(D)) in fp16 plus
+//   per-(row, key-tile) partial row sums (plain stores, fixed summation order -> deterministic).  Recomputing
+//   Q.K^T costs 2/3 more tensor work than storing S, but the fp32 S round trip (write + two reads + a
+//   softmax kernel) was measured to cost more than twice that.
+//   Small problems (few tiles but a huge feature dim, e.g. 60 tokens x 76 800): split-K, each split writes
+//   its own fp32 slab of S; softmax_rows_kernel adds the slabs in a fixed order and writes P / rowsum.
 //   pv     : O[qp, pos,:] = (sum_kp P[qp,kp] V_pos[kp,:]) / rowsum[qp]  -> written back in NHWC
 #pragma once
 #include "tc_gemm.cuh"
@@ -35,6 +39,11 @@ struct AttnHead {
   float* S;
   __half* P;
   float* rowsum;
+  int fused;            // 1: two-pass score kernels (rowmax_part / rowsum_part), 0: split-K slabs + softmax kernel
+  int npairs;           // key tile pairs = ceil(ntt / 2)
+  float* rowmax_part;   // [ntt*128][npairs]
+  float* rowsum_part;   // [ntt*128][npairs]
+  int scoreB_begin, scoreB_begin2;  // pass-B work lists (fused problems only)
 };
 
 constexpr int ATTN_MAX_HEADS = 8;  // (windows in a group) x (patch geometries)
@@ -43,6 +52,8 @@ struct ScoreParams {
   CUtensorMap qmap[ATTN_MAX_HEADS], kmap[ATTN_MAX_HEADS];
   AttnHead h[ATTN_MAX_HEADS];
   int nheads, total_work, total_work2;
+  int pass;  // 0 = pass A (max / S slabs), 1 = pass B (P)
+  int totalB, totalB2;
 };
 
 struct ScorePolicy {
@@ -58,6 +69,7 @@ struct ScorePolicy {
   };
   struct RowCtx {
     float* dst;
+    float m, sum;  // pass A: running max of this row over the tile; pass B: row max, running sum
   };
   __device__ static void prefetch(const Params& p) {
     for (int i = 0; i < p.nheads; ++i) {
@@ -65,12 +77,17 @@ struct ScorePolicy {
       tma_prefetch_desc(&p.kmap[i]);
     }
   }
-  __device__ static int num_tiles(const Params& p) { return p.total_work; }
+  __device__ static int num_tiles(const Params& p) { return p.pass ? p.totalB : p.total_work; }
   __device__ static Tile get_tile(const Params& p, int idx) {
     int hd = 0;
-    while (hd + 1 < p.nheads && idx >= p.h[hd + 1].score_work_begin) ++hd;
+    if (p.pass) {
+      while (hd + 1 < p.nheads && idx >= p.h[hd + 1].scoreB_begin) ++hd;
+      idx -= p.h[hd].scoreB_begin;
+    } else {
+      while (hd + 1 < p.nheads && idx >= p.h[hd + 1].score_work_begin) ++hd;
+      idx -= p.h[hd].score_work_begin;
+    }
     const AttnHead& h = p.h[hd];
-    idx -= h.score_work_begin;
     Tile t;
     t.head = hd;
     const int sp = idx % h.splits;
@@ -99,26 +116,81 @@ struct ScorePolicy {
     const AttnHead& h = p.h[t.head];
     RowCtx c;
     c.dst = h.S + (size_t)t.split * h.slabS + (size_t)(t.qi * 128 + row) * h.ldS + t.kj * 256;
+    c.m = -INFINITY;
+    c.sum = 0.f;
+    if (h.fused && p.pass == 1 && t.n_cols > 0) {  // row max = max over the key-tile partials of pass A
+      const float* pm = h.rowmax_part + (size_t)(t.qi * 128 + row) * h.npairs;
+      float m = pm[0];
+      for (int j = 1; j < h.npairs; ++j) m = fmaxf(m, pm[j]);
+      c.m = m;
+    }
     return c;
   }
   // The accumulator arrives one row per thread; storing it like that scatters every 16-byte store over 32
   // different rows (measured: the epilogue was 84 % of this kernel).  Transpose 32x32 blocks through smem so
-  // that each store instruction writes 4 rows x 128 contiguous bytes.
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float* scr) {
-    const int lane = row & 31;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
-    __syncwarp();
+  // that each store instruction writes whole 64/128-byte row segments.
+  __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float* scr) {
     const AttnHead& h = p.h[t.head];
-    float* base = c.dst - (size_t)lane * h.ldS + col0;  // row 0 of this warp's 32 rows
-    const int r4 = lane >> 3, c4 = (lane & 7) * 4;
+    const int lane = row & 31;
+    if (!h.fused) {  // split-K problem: fp32 slab of S
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int rr = j * 4 + r4;
-      const float* sp = scr + rr * 33 + c4;
-      *reinterpret_cast<float4*>(base + (size_t)rr * h.ldS + c4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+      for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = v[i];
+      __syncwarp();
+      float* base = c.dst - (size_t)lane * h.ldS + col0;  // row 0 of this warp's 32 rows
+      const int r4 = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int rr = j * 4 + r4;
+        const float* sp = scr + rr * 33 + c4;
+        *reinterpret_cast<float4*>(base + (size_t)rr * h.ldS + c4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+      }
+      __syncwarp();
+      return;
+    }
+    const int kp0 = t.kj * 256 + col0;
+    const int nvalid = h.toh_total * h.owp, owm = h.owp - 1;
+    if (p.pass == 0) {  // pass A: only the max of the valid columns survives
+      float m = c.m;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int kp = kp0 + i;
+        if (kp < nvalid && (kp & owm) < h.ow) m = fmaxf(m, v[i]);
+      }
+      c.m = m;
+      return;
+    }
+    // pass B: P = exp2((s - max) * log2(e)/sqrt(D)) in fp16, masked slots = 0; row sums of the rounded values
+    uint32_t* scw = reinterpret_cast<uint32_t*>(scr);
+    float sum = c.sum;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const int kp = kp0 + i;
+      const float e0 = (kp < nvalid && (kp & owm) < h.ow) ? exp2f((v[i] - c.m) * h.scale_log2e) : 0.f;
+      const float e1 = (kp + 1 < nvalid && ((kp + 1) & owm) < h.ow) ? exp2f((v[i + 1] - c.m) * h.scale_log2e) : 0.f;
+      const __half2 hh = __floats2half2_rn(e0, e1);
+      const float2 f = __half22float2(hh);
+      sum += f.x + f.y;
+      scw[lane * 17 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    c.sum = sum;
+    __syncwarp();
+    // 32 rows x 64 bytes: each store instruction writes 8 rows x 64 contiguous bytes
+    __half* pbase = h.P + (size_t)(t.qi * 128 + (row & ~31)) * h.ldP + kp0;
+    const int r8 = lane >> 2, c4 = (lane & 3) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = j * 8 + r8;
+      const uint32_t* sp = scw + rr * 17 + c4;
+      *reinterpret_cast<uint4*>(pbase + (size_t)rr * h.ldP + c4 * 2) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
     }
     __syncwarp();
+  }
+  __device__ static void row_end(const Params& p, const Tile& t, RowCtx& c, int row) {
+    const AttnHead& h = p.h[t.head];
+    if (!h.fused || t.n_cols == 0) return;
+    const size_t idx = (size_t)(t.qi * 128 + row) * h.npairs + t.kj;
+    if (p.pass == 0) h.rowmax_part[idx] = c.m;
+    else h.rowsum_part[idx] = c.sum;
   }
 };
 
@@ -129,7 +201,7 @@ template <int NV4>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
   const AttnHead& h = p.h[blockIdx.y];
   const int qp = blockIdx.x;
-  if (qp >= h.ntt * 128) return;
+  if (h.fused || qp >= h.ntt * 128) return;
   const int toh = qp / h.owp, owi = qp - toh * h.owp;
   if (owi >= h.ow || toh >= h.toh_total) return;
   const float* s = h.S + (size_t)qp * h.ldS;
@@ -261,13 +333,22 @@ struct PVPolicy {
     c.inv = 0.f;
     c.base = nullptr;
     if (c.valid) {
-      c.inv = 1.0f / h.rowsum[qp];
+      float rs;
+      if (h.fused) {
+        const float* ps = h.rowsum_part + (size_t)qp * h.npairs;
+        rs = ps[0];
+        for (int j = 1; j < h.npairs; ++j) rs += ps[j];  // fixed order: deterministic
+      } else {
+        rs = h.rowsum[qp];
+      }
+      c.inv = 1.0f / rs;
       const int tt = toh / h.oh, ohi = toh - tt * h.oh;
       c.base = p.out + p.out_off[t.head] + (((size_t)tt * p.H + ohi * h.ph) * p.W + owi * h.pw) * p.out_pitch + p.coff[t.head];
     }
     return c;
   }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float*) {
+  __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}
+  __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float*) {
     if (!c.valid) return;
     const AttnHead& h = p.h[t.head];
     const int pos = t.ni * 4 + (col0 >> 6);
@@ -296,12 +377,17 @@ struct Score2Policy {
   using Tile = ScorePolicy::Tile;
   using RowCtx = ScorePolicy::RowCtx;
   __device__ static void prefetch(const Params& p) { ScorePolicy::prefetch(p); }
-  __device__ static int num_tiles(const Params& p) { return p.total_work2; }
+  __device__ static int num_tiles(const Params& p) { return p.pass ? p.totalB2 : p.total_work2; }
   __device__ static Tile get_tile(const Params& p, int idx, uint32_t rank) {
     int hd = 0;
-    while (hd + 1 < p.nheads && idx >= p.h[hd + 1].score_work_begin2) ++hd;
+    if (p.pass) {
+      while (hd + 1 < p.nheads && idx >= p.h[hd + 1].scoreB_begin2) ++hd;
+      idx -= p.h[hd].scoreB_begin2;
+    } else {
+      while (hd + 1 < p.nheads && idx >= p.h[hd + 1].score_work_begin2) ++hd;
+      idx -= p.h[hd].score_work_begin2;
+    }
     const AttnHead& h = p.h[hd];
-    idx -= h.score_work_begin2;
     Tile t;
     t.head = hd;
     const int sp = idx % h.splits;
@@ -327,9 +413,10 @@ struct Score2Policy {
     if ((int)rank < t.nkt) tma_load_5d_2sm(sB, &p.kmap[t.head], leader_full, 0, px, 0, py, (2 * t.kj + (int)rank) * rows);
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) { return ScorePolicy::row_begin(p, t, row); }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float* scr) {
+  __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float* scr) {
     ScorePolicy::epilogue(p, t, c, row, col0, v, scr);
   }
+  __device__ static void row_end(const Params& p, const Tile& t, RowCtx& c, int row) { ScorePolicy::row_end(p, t, c, row); }
 };
 
 struct PV2Policy {
@@ -372,9 +459,10 @@ struct PV2Policy {
     }
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) { return PVPolicy::row_begin(p, t, row); }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float* scr) {
+  __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float* scr) {
     PVPolicy::epilogue(p, t, c, row, col0, v, scr);
   }
+  __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}
 };
 
 }  // namespace vsr

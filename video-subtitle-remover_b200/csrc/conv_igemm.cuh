@@ -95,7 +95,8 @@ struct ConvPolicy {
     c.pix = ((size_t)t.t * p.H + c.y) * p.W + c.x;
     return c;
   }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float*) {
+  __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}
+  __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float*) {
     if (!c.valid) return;
     constexpr int NV = (BN >= 32) ? 32 : 16;
     const int ch0 = t.n0 + col0;
@@ -203,7 +204,8 @@ struct Conv2Policy {
     c.valid = c.valid && (t.t < p.T);
     return c;
   }
-  __device__ static void epilogue(const Params& p, const Tile& t, const RowCtx& c, int row, int col0, float* v, float* scr) {
+  __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}
+  __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float* scr) {
     Base::epilogue(p, t, c, row, col0, v, scr);
   }
 };

@@ -144,6 +144,7 @@ struct Ctx {
   int64_t launches = 0;
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
+  bool attn_fused = true; // VSR_ATTN_FUSED=0: always materialise S (fp32) and run the softmax kernel
 };
 
 static bool env_flag(const char* name, bool dflt) {
@@ -339,7 +340,7 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
 
 // ------------------------------------------------------------------------------------------------ attention
 struct AttnWorkspace {
-  DevBuf S[ATTN_MAX_HEADS], P[ATTN_MAX_HEADS], rowsum[ATTN_MAX_HEADS];
+  DevBuf S[ATTN_MAX_HEADS], P[ATTN_MAX_HEADS], rowsum[ATTN_MAX_HEADS], rowmax_part[ATTN_MAX_HEADS], rowsum_part[ATTN_MAX_HEADS];
 };
 
 static int next_pow2(int v) {
@@ -376,7 +377,17 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
       ents.push_back({g, i, n * n * 64.0 * pw[i] * ph[i]});
     }
   std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.work > b.work; });
-  int score_work = 0, pv_work = 0, score_work2 = 0, pv_work2 = 0, max_rows = 0;
+  // split-K only where one tile would be a large share of a CTA's fair load (in 64-wide K-chunk units)
+  double total_units = 0;
+  for (const Ent& e : ents) {
+    const int i = e.patch;
+    const int ntok_p = segs[e.seg].T * (H / ph[i]) * next_pow2(W / pw[i]);
+    const int ntt = (ntok_p + 127) / 128;
+    total_units += (double)ntt * ((ntt + 1) / 2) * pw[i] * ph[i];
+  }
+  const int split_target = std::max(8, (int)(total_units / c.sms / 4.0));
+  int score_work = 0, pv_work = 0, score_work2 = 0, pv_work2 = 0, max_rows = 0, workB = 0, workB2 = 0;
+  bool any_unfused = false;
   for (int s = 0; s < nent; ++s) {
     const int i = ents[s].patch;
     const AttnSegment& sg = segs[ents[s].seg];
@@ -394,15 +405,12 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     h.ntt = (ntok_p + 127) / 128;
     h.nk64 = (ntok_p + 63) / 64;
     const int tiles = h.ntt * ((h.ntt + 1) / 2);  // 128 queries x 256 keys per CTA tile
-    int splits = 1;
-    if (tiles < 2 * c.sms) {
-      splits = (4 * c.sms + tiles - 1) / tiles;
-      const int max_splits = (h.npos + 7) / 8;
-      if (splits > max_splits) splits = max_splits;
-      if (splits < 1) splits = 1;
-    }
+    const int splits = h.npos > split_target ? (h.npos + split_target - 1) / split_target : 1;
     h.chunks_per_split = (h.npos + splits - 1) / splits;
     h.splits = (h.npos + h.chunks_per_split - 1) / h.chunks_per_split;
+    h.fused = (h.splits == 1 && c.attn_fused) ? 1 : 0;
+    h.npairs = (h.ntt + 1) / 2;
+    any_unfused |= !h.fused;
     h.score_work_begin = score_work;
     score_work += tiles * h.splits;
     h.score_work_begin2 = score_work2;
@@ -412,17 +420,27 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     pv_work += h.ntt * h.pv_ntiles;
     h.pv_work_begin2 = pv_work2;
     pv_work2 += ((h.ntt + 1) / 2) * h.pv_ntiles;
+    h.scoreB_begin = workB;
+    h.scoreB_begin2 = workB2;
+    if (h.fused) {
+      workB += tiles;
+      workB2 += ((h.ntt + 1) / 2) * ((h.ntt + 1) / 2);
+    }
     h.ldS = h.ntt * 128;
     h.ldP = h.ntt * 128;
     h.scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)dk * h.npos));
     const size_t rows = (size_t)h.ntt * 128;
     h.slabS = (long long)rows * h.ldS;
-    ws.S[s].ensure((size_t)h.splits * rows * h.ldS * sizeof(float));
+    if (!h.fused) ws.S[s].ensure((size_t)h.splits * rows * h.ldS * sizeof(float));
     ws.P[s].ensure(rows * h.ldP * sizeof(__half));
     ws.rowsum[s].ensure(rows * sizeof(float));
-    h.S = ws.S[s].as<float>();
+    ws.rowmax_part[s].ensure(rows * h.npairs * sizeof(float));
+    ws.rowsum_part[s].ensure(rows * h.npairs * sizeof(float));
+    h.S = h.fused ? nullptr : ws.S[s].as<float>();
     h.P = ws.P[s].as<__half>();
     h.rowsum = ws.rowsum[s].as<float>();
+    h.rowmax_part = ws.rowmax_part[s].as<float>();
+    h.rowsum_part = ws.rowsum_part[s].as<float>();
     if ((int)rows > max_rows) max_rows = (int)rows;
     // 5-D views {64 ch, px, ow, py, toh} of this segment's frames
     const __half* base = qkv + (size_t)sg.first * frame_elems;
@@ -451,21 +469,33 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   pp.T = 0; pp.H = H; pp.W = W;
   pp.out = out;
   pp.out_pitch = out_pitch;
+  sp.totalB = workB;
+  sp.totalB2 = workB2;
+  sp.pass = 0;  // pass A: per-tile row maxima (fused problems) / fp32 S slabs (split-K problems)
   if (c.attn_2cta) launch_tc2<Score2Policy>(c, sp, score_work2);
   else launch_tc<ScorePolicy>(c, sp, score_work);
-  {
-    int max_cols = 0;
-    for (int s2 = 0; s2 < nent; ++s2) max_cols = std::max(max_cols, sp.h[s2].nk64 * 64);
-    const dim3 grid(max_rows, nent);
+  if (any_unfused) {
+    int max_cols = 0, rows_unfused = 0;
+    for (int s2 = 0; s2 < nent; ++s2)
+      if (!sp.h[s2].fused) {
+        max_cols = std::max(max_cols, sp.h[s2].nk64 * 64);
+        rows_unfused = std::max(rows_unfused, sp.h[s2].ntt * 128);
+      }
+    const dim3 grid(rows_unfused, nent);
     if (max_cols <= 1024) softmax_rows_kernel<1><<<grid, 256, 0, c.stream>>>(sp);
     else if (max_cols <= 2048) softmax_rows_kernel<2><<<grid, 256, 0, c.stream>>>(sp);
     else if (max_cols <= 5120) softmax_rows_kernel<5><<<grid, 256, 0, c.stream>>>(sp);
     else if (max_cols <= 10240) softmax_rows_kernel<10><<<grid, 256, 0, c.stream>>>(sp);
     else if (max_cols <= 20480) softmax_rows_kernel<20><<<grid, 256, 0, c.stream>>>(sp);
     else throw Error(VSR_ERR_ARG, "attention rows longer than 20480 tokens are not supported");
+    CK(cudaGetLastError());
+    ++c.launches;
   }
-  CK(cudaGetLastError());
-  ++c.launches;
+  if (workB > 0) {
+    sp.pass = 1;  // pass B: recompute the scores, write P and partial row sums
+    if (c.attn_2cta) launch_tc2<Score2Policy>(c, sp, workB2);
+    else launch_tc<ScorePolicy>(c, sp, workB);
+  }
   if (c.attn_2cta) launch_tc2<PV2Policy>(c, pp, pv_work2);
   else launch_tc<PVPolicy>(c, pp, pv_work);
 }
@@ -1057,6 +1087,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->use_graph = !env_flag("VSR_NO_GRAPH", false);
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
+    h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", true);
     if (getenv("VSR_WINDOW_GROUP")) h->window_group = (size_t)std::min(2, std::max(1, atoi(getenv("VSR_WINDOW_GROUP"))));
     *out = h;
   });
@@ -1299,6 +1330,7 @@ struct OpCtx {
     c.sms = prop.multiProcessorCount;
     c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
+    c.attn_fused = env_flag("VSR_ATTN_FUSED", true);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   }
   ~OpCtx() {

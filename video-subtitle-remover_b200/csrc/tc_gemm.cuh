@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         tmem_ld16(taddr, v);
         P::epilogue(prm, tile, ctx, row, 0, v, epi_scratch + (P::EPI_SCRATCH ? quarter * 32 * 33 : 0));
       }
+      P::row_end(prm, tile, ctx, row);
       tc_fence_before();
       __syncwarp();
       TC_PROF_ACC(busy, e0);

@@ -127,6 +127,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         tmem_ld32(taddr + c, v);
         P::epilogue(prm, tile, ctx, row, c, v, epi_scratch + (P::EPI_SCRATCH ? quarter * 32 * 33 : 0));
       }
+      P::row_end(prm, tile, ctx, row);
       tc_fence_before();
       __syncwarp();
       TC_PROF_ACC(busy, e0);
