@@ -1,0 +1,66 @@
+"""CPU: the N>1 host logic (chunk sharding + max-over-ranks) with a real 2-process gloo group."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vsr_b200.distributed import chunk_ranges, chunks_for_rank, inpaint_clip_sharded, max_over_ranks
+
+
+def test_chunk_ranges_match_reference_loop():
+    # sttn_auto_inpaint.py:240-245: rec_time = ceil(len / clip_gap), exact clip_gap chunks, last one shorter
+    assert chunk_ranges(300, 50) == [(i * 50, i * 50 + 50) for i in range(6)]
+    assert chunk_ranges(299, 50)[-1] == (250, 299)
+    assert chunk_ranges(0, 50) == []
+    assert chunk_ranges(7, 50) == [(0, 7)]
+    with pytest.raises(ValueError):
+        chunk_ranges(10, 0)
+
+
+@pytest.mark.parametrize("n,gap,world", [(300, 50, 1), (300, 50, 2), (300, 50, 4), (300, 50, 8), (1200, 50, 8), (49, 50, 8)])
+def test_sharding_is_a_partition(n, gap, world):
+    seen = []
+    for r in range(world):
+        seen += chunks_for_rank(n, gap, r, world)
+    seen.sort()
+    assert [c for c, _ in seen] == list(range(len(chunk_ranges(n, gap))))
+    assert [rg for _, rg in seen] == chunk_ranges(n, gap)
+
+
+class _MarkEngine:
+    """Stand-in for STTNInpaint: writes the rank into the frames it is given (in place)."""
+
+    def __init__(self, rank):
+        self.rank = rank
+
+    def inpaint_inplace(self, frames, mask):
+        for f in frames:
+            f.fill_(self.rank + 1)
+
+
+def _worker(rank, world, port, n, gap):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        frames = [torch.zeros(4, dtype=torch.int32) for _ in range(n)]
+        mine = inpaint_clip_sharded(_MarkEngine(rank), frames, None, gap, rank, world)
+        owner = torch.stack(frames)[:, 0].clone()  # 0 = untouched here
+        dist.all_reduce(owner, op=dist.ReduceOp.SUM)  # test-only collective: every frame painted exactly once
+        expect = torch.tensor([(c % world) + 1 for c, (s, e) in enumerate(chunk_ranges(n, gap)) for _ in range(s, e)], dtype=torch.int32)
+        assert torch.equal(owner, expect)
+        assert all(c % world == rank for c, _ in mine)
+        assert max_over_ranks(float(rank + 1)) == float(world)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, 230, 50), nprocs=2, join=True)

@@ -102,15 +102,30 @@ struct ScorePolicy {
     t.split = sp;
     return t;
   }
-  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
+  struct LoadCtx {
+    int px, py, pw;          // patch pixel of the next k-chunk (advanced without divisions)
+    int qrow, krow0, krow1;  // 5th TMA coordinate of the query tile and of the key tile(s)
+    uint32_t tx_bytes;
+  };
+  __device__ static LoadCtx load_begin(const Params& p, const Tile& t) {
     const AttnHead& h = p.h[t.head];
-    const int pos = t.kbeg + k;
-    const int py = pos / h.pw, px = pos - py * h.pw;
     const int rows = 128 / h.owp;
-    mbar_expect_tx(bar, (uint32_t)((1 + t.nkt) * TC_A_BYTES));
-    tma_load_5d(sA, &p.qmap[t.head], bar, 0, px, 0, py, t.qi * rows);
-    tma_load_5d(sB, &p.kmap[t.head], bar, 0, px, 0, py, (2 * t.kj) * rows);
-    if (t.nkt == 2) tma_load_5d(sB + TC_A_BYTES, &p.kmap[t.head], bar, 0, px, 0, py, (2 * t.kj + 1) * rows);
+    LoadCtx lc;
+    lc.pw = h.pw;
+    lc.py = t.kbeg / h.pw;
+    lc.px = t.kbeg - lc.py * h.pw;
+    lc.qrow = t.qi * rows;
+    lc.krow0 = (2 * t.kj) * rows;
+    lc.krow1 = (2 * t.kj + 1) * rows;
+    lc.tx_bytes = (uint32_t)((1 + t.nkt) * TC_A_BYTES);
+    return lc;
+  }
+  __device__ static void load(const Params& p, const Tile& t, LoadCtx& lc, int, uint32_t sA, uint32_t sB, uint32_t bar) {
+    mbar_expect_tx(bar, lc.tx_bytes);
+    tma_load_5d(sA, &p.qmap[t.head], bar, 0, lc.px, 0, lc.py, lc.qrow);
+    tma_load_5d(sB, &p.kmap[t.head], bar, 0, lc.px, 0, lc.py, lc.krow0);
+    if (t.nkt == 2) tma_load_5d(sB + TC_A_BYTES, &p.kmap[t.head], bar, 0, lc.px, 0, lc.py, lc.krow1);
+    if (++lc.px == lc.pw) { lc.px = 0; ++lc.py; }
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
     const AttnHead& h = p.h[t.head];
@@ -313,16 +328,31 @@ struct PVPolicy {
     t.n_cols = t.nvalid * 64;
     return t;
   }
-  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
+  struct LoadCtx {
+    int px[4], py[4];  // patch pixel of each value position of this tile (fixed over k)
+    int prow, rows;    // P row coordinate, value token rows per 64-token chunk
+    uint32_t tx_bytes;
+  };
+  __device__ static LoadCtx load_begin(const Params& p, const Tile& t) {
     const AttnHead& h = p.h[t.head];
-    mbar_expect_tx(bar, (uint32_t)(TC_A_BYTES + t.nvalid * 8192));
-    tma_load_2d(sA, &p.pmap[t.head], bar, k * 64, t.mi * 128);
-    const int rows = 64 / h.owp;
-    for (int j = 0; j < t.nvalid; ++j) {
+    LoadCtx lc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       const int pos = t.ni * 4 + j;
-      const int py = pos / h.pw, px = pos - py * h.pw;
-      tma_load_5d(sB + j * 8192, &p.vmap[t.head], bar, 0, px, 0, py, k * rows);
+      lc.py[j] = pos / h.pw;
+      lc.px[j] = pos - lc.py[j] * h.pw;
     }
+    lc.prow = t.mi * 128;
+    lc.rows = 64 / h.owp;
+    lc.tx_bytes = (uint32_t)(TC_A_BYTES + t.nvalid * 8192);
+    return lc;
+  }
+  __device__ static void load(const Params& p, const Tile& t, LoadCtx& lc, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
+    mbar_expect_tx(bar, lc.tx_bytes);
+    tma_load_2d(sA, &p.pmap[t.head], bar, k * 64, lc.prow);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < t.nvalid) tma_load_5d(sB + j * 8192, &p.vmap[t.head], bar, 0, lc.px[j], 0, lc.py[j], k * lc.rows);
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
     const AttnHead& h = p.h[t.head];
@@ -402,15 +432,19 @@ struct Score2Policy {
     t.split = sp;
     return t;
   }
-  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t local_full,
+  using LoadCtx = ScorePolicy::LoadCtx;
+  __device__ static LoadCtx load_begin(const Params& p, const Tile& t, uint32_t rank) {
+    LoadCtx lc = ScorePolicy::load_begin(p, t);
+    lc.krow0 = (2 * t.kj + (int)rank) * (128 / p.h[t.head].owp);  // this CTA's key tile
+    lc.tx_bytes = (uint32_t)((2 + t.nkt) * TC_A_BYTES);          // registered by the leader for both CTAs
+    return lc;
+  }
+  __device__ static void load(const Params& p, const Tile& t, LoadCtx& lc, int, uint32_t sA, uint32_t sB, uint32_t local_full,
                               uint32_t leader_full, uint32_t rank) {
-    const AttnHead& h = p.h[t.head];
-    const int pos = t.kbeg + k;
-    const int py = pos / h.pw, px = pos - py * h.pw;
-    const int rows = 128 / h.owp;
-    if (rank == 0) mbar_expect_tx(local_full, (uint32_t)((2 + t.nkt) * TC_A_BYTES));
-    tma_load_5d_2sm(sA, &p.qmap[t.head], leader_full, 0, px, 0, py, t.qi * rows);
-    if ((int)rank < t.nkt) tma_load_5d_2sm(sB, &p.kmap[t.head], leader_full, 0, px, 0, py, (2 * t.kj + (int)rank) * rows);
+    if (rank == 0) mbar_expect_tx(local_full, lc.tx_bytes);
+    tma_load_5d_2sm(sA, &p.qmap[t.head], leader_full, 0, lc.px, 0, lc.py, lc.qrow);
+    if ((int)rank < t.nkt) tma_load_5d_2sm(sB, &p.kmap[t.head], leader_full, 0, lc.px, 0, lc.py, lc.krow0);
+    if (++lc.px == lc.pw) { lc.px = 0; ++lc.py; }
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) { return ScorePolicy::row_begin(p, t, row); }
   __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float* scr) {
@@ -443,20 +477,24 @@ struct PV2Policy {
     t.n_cols = t.nvalid * 64;
     return t;
   }
-  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t local_full,
-                              uint32_t leader_full, uint32_t rank) {
-    const AttnHead& h = p.h[t.head];
-    if (rank == 0) mbar_expect_tx(local_full, (uint32_t)(2 * TC_A_BYTES + t.nvalid * 8192));
-    tma_load_2d_2sm(sA, &p.pmap[t.head], leader_full, k * 64, t.mi * 128);
-    const int rows = 64 / h.owp;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int pos = t.ni * 4 + 2 * (int)rank + j;
-      if (pos < h.npos) {
-        const int py = pos / h.pw, px = pos - py * h.pw;
-        tma_load_5d_2sm(sB + j * 8192, &p.vmap[t.head], leader_full, 0, px, 0, py, k * rows);
-      }
+  using LoadCtx = PVPolicy::LoadCtx;
+  __device__ static LoadCtx load_begin(const Params& p, const Tile& t, uint32_t rank) {
+    LoadCtx lc = PVPolicy::load_begin(p, t);
+    if (rank) {  // this CTA owns value positions 2 and 3 of the tile: keep them in slots 0 and 1
+      lc.px[0] = lc.px[2]; lc.py[0] = lc.py[2];
+      lc.px[1] = lc.px[3]; lc.py[1] = lc.py[3];
     }
+    lc.tx_bytes = (uint32_t)(2 * TC_A_BYTES + t.nvalid * 8192);  // registered by the leader for both CTAs
+    return lc;
+  }
+  __device__ static void load(const Params& p, const Tile& t, LoadCtx& lc, int k, uint32_t sA, uint32_t sB, uint32_t local_full,
+                              uint32_t leader_full, uint32_t rank) {
+    if (rank == 0) mbar_expect_tx(local_full, lc.tx_bytes);
+    tma_load_2d_2sm(sA, &p.pmap[t.head], leader_full, k * 64, lc.prow);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (2 * (int)rank + j < t.nvalid)
+        tma_load_5d_2sm(sB + j * 8192, &p.vmap[t.head], leader_full, 0, lc.px[j], 0, lc.py[j], k * lc.rows);
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) { return PVPolicy::row_begin(p, t, row); }
   __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float* scr) {

@@ -78,12 +78,18 @@ struct ConvPolicy {
     t.n_cols = BN;
     return t;
   }
-  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
-    const int tap = k / p.cin_chunks;
-    const int kc = k - tap * p.cin_chunks;
-    mbar_expect_tx(bar, (uint32_t)(p.tile_w * p.tile_h * 128 + BN * 128));
-    tma_load_4d(sA, &p.in_map, bar, kc * 64, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.t);
+  struct LoadCtx {
+    int tap, kc;        // running (tap, channel chunk) of the next k-chunk
+    uint32_t tx_bytes;
+  };
+  __device__ static LoadCtx load_begin(const Params& p, const Tile&) {
+    return LoadCtx{0, 0, (uint32_t)(p.tile_w * p.tile_h * 128 + BN * 128)};
+  }
+  __device__ static void load(const Params& p, const Tile& t, LoadCtx& lc, int k, uint32_t sA, uint32_t sB, uint32_t bar) {
+    mbar_expect_tx(bar, lc.tx_bytes);
+    tma_load_4d(sA, &p.in_map, bar, lc.kc * 64, t.x0 + p.tap_dx[lc.tap], t.y0 + p.tap_dy[lc.tap], t.t);
     tma_load_2d(sB, &p.w_map, bar, k * 64, t.n0);
+    if (++lc.kc == p.cin_chunks) { lc.kc = 0; ++lc.tap; }
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
     RowCtx c;
@@ -190,14 +196,17 @@ struct Conv2Policy {
     t.t = sub / p.tiles_y;
     return t;
   }
-  __device__ static void load(const Params& p, const Tile& t, int k, uint32_t sA, uint32_t sB, uint32_t local_full, uint32_t leader_full,
-                              uint32_t rank) {
-    const int tap = k / p.cin_chunks;
-    const int kc = k - tap * p.cin_chunks;
+  using LoadCtx = Base::LoadCtx;
+  __device__ static LoadCtx load_begin(const Params& p, const Tile&, uint32_t) {
     // the leader registers the bytes of both CTAs; the peer's loads may land first (tx-count is signed)
-    if (rank == 0) mbar_expect_tx(local_full, 2u * (uint32_t)(p.tile_w * p.tile_h * 128 + 128 * 128));
-    tma_load_4d_2sm(sA, &p.in_map, leader_full, kc * 64, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.t);
+    return LoadCtx{0, 0, 2u * (uint32_t)(p.tile_w * p.tile_h * 128 + 128 * 128)};
+  }
+  __device__ static void load(const Params& p, const Tile& t, LoadCtx& lc, int k, uint32_t sA, uint32_t sB, uint32_t local_full,
+                              uint32_t leader_full, uint32_t rank) {
+    if (rank == 0) mbar_expect_tx(local_full, lc.tx_bytes);
+    tma_load_4d_2sm(sA, &p.in_map, leader_full, lc.kc * 64, t.x0 + p.tap_dx[lc.tap], t.y0 + p.tap_dy[lc.tap], t.t);
     tma_load_2d_2sm(sB, &p.w_map_half, leader_full, k * 64, t.n0 + (int)rank * 128);
+    if (++lc.kc == p.cin_chunks) { lc.kc = 0; ++lc.tap; }
   }
   __device__ static RowCtx row_begin(const Params& p, const Tile& t, int row) {
     RowCtx c = Base::row_begin(p, t, row);

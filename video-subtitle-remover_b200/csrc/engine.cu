@@ -144,7 +144,7 @@ struct Ctx {
   int64_t launches = 0;
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
-  bool attn_fused = true; // VSR_ATTN_FUSED=0: always materialise S (fp32) and run the softmax kernel
+  bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
 };
 
 static bool env_flag(const char* name, bool dflt) {
@@ -1087,7 +1087,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->use_graph = !env_flag("VSR_NO_GRAPH", false);
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
-    h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", true);
+    h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     if (getenv("VSR_WINDOW_GROUP")) h->window_group = (size_t)std::min(2, std::max(1, atoi(getenv("VSR_WINDOW_GROUP"))));
     *out = h;
   });
@@ -1330,7 +1330,7 @@ struct OpCtx {
     c.sms = prop.multiProcessorCount;
     c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
-    c.attn_fused = env_flag("VSR_ATTN_FUSED", true);
+    c.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   }
   ~OpCtx() {

@@ -14,6 +14,13 @@ __device__ unsigned int g_dev_error[4];
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of a converged warp.  Unlike `lane == 0`, ptxas knows the result is a single thread and keeps the
+// TMA / tcgen05 operands in uniform registers instead of wrapping every issue in a BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;

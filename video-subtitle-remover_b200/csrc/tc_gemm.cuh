@@ -6,7 +6,8 @@
 // (one SWIZZLE_128B row per tile row).  The policy P supplies the problem-specific parts:
 //   P::BN, P::STAGES, P::B_MN_MAJOR, P::Params, P::Tile
 //   P::num_tiles(prm), P::get_tile(prm, idx)            -> Tile (with .num_k and .n_cols)
-//   P::load(prm, tile, k, sA, sB, bar)                  -> issue TMA + expect_tx for k-chunk k
+//   P::load_begin(prm, tile) -> LoadCtx ; P::load(prm, tile, lctx, k, sA, sB, bar) -> TMA + expect_tx for chunk k
+//     (the producer is ONE thread: anything but adds and a compare per chunk shows up as idle tensor pipes)
 //   P::epilogue(prm, tile, row, col0, v[32], ncols)     -> consume 32 (or 16) accumulator columns
 #pragma once
 #include "tc_common.cuh"
@@ -63,15 +64,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const int ntiles = P::num_tiles(prm);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       TC_PROF_DECL(w_empty);
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const typename P::Tile tile = P::get_tile(prm, t);
+        typename P::LoadCtx lc = P::load_begin(prm, tile);  // per-tile invariants: the k loop must stay division-free
         for (int k = 0; k < tile.num_k; ++k) {
           TC_PROF_WAIT(w_empty, smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
-          P::load(prm, tile, k, sA, sA + TC_A_BYTES, smem_u32(&bar_full[stage]));
+          P::load(prm, tile, lc, k, sA, sA + TC_A_BYTES, smem_u32(&bar_full[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       TC_PROF_DECL(w_full);
       TC_PROF_DECL(w_tempty);

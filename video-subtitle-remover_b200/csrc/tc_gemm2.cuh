@@ -60,16 +60,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       TC_PROF_DECL(w_empty);
       for (int t = first; t < ntiles; t += step) {
         const typename P::Tile tile = P::get_tile(prm, t, rank);
+        typename P::LoadCtx lc = P::load_begin(prm, tile, rank);
         for (int k = 0; k < tile.num_k; ++k) {
           TC_PROF_WAIT(w_empty, smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
           const uint32_t leader_full = mapa_cluster(smem_u32(&bar_full[stage]), 0);
-          P::load(prm, tile, k, sA, sA + TC_A_BYTES, smem_u32(&bar_full[stage]), leader_full, rank);
+          P::load(prm, tile, lc, k, sA, sA + TC_A_BYTES, smem_u32(&bar_full[stage]), leader_full, rank);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -77,7 +78,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       TC_PROF_DECL(w_full);
       TC_PROF_DECL(w_tempty);
