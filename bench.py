@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 H, W, CHUNK = 1080, 1920, 50
 FLOP_PER_FRAME = 642.8e9  # SURVEY.md §8d / BASELINE.md §3 (2*MAC of conv+matmul per output frame)
 METRIC = "inpainted frames/sec at 1080p (STTN, window=5)"
+CPU_SAMPLE = ("one 50-frame 1080p chunk sampled as: encoder on 50 frames + 3 of its 10 windows (T=10,14,15; 8 blocks + decoder) "
+              "+ pre/post on 5 frames, extrapolated by counts (1,5,4 windows; x10 pre/post)")
 
 
 def peaks():
@@ -91,17 +93,72 @@ def load_weights():
     return O.random_weights(0), "seeded random-init weights of the sttn-auto architecture"
 
 
-def cpu_port_fps(w, frames, mask, sample_frames, threads):
-    """The oracle port driven like STTNAutoInpaint drives the reference, on the first `sample_frames`
-    frames of the chunk (per-frame cost grows mildly with chunk length: more reference frames)."""
+def cpu_port_fps(w, frames, mask, threads, calibrate=False):
+    """CPU port (oracle = torch-CPU restatement of the reference) on a BOUNDED sample of one 50-frame 1080p
+    chunk.  Per-frame cost depends on the window length (attention is quadratic in it), so a short clip would
+    flatter the CPU; instead time the real pieces of the chunk and extrapolate by their counts:
+      encoder on all 50 frames + 3 of the 10 windows (T = 10, 14, 15: 8 transformer blocks + decoder +
+      quantise, with their full reference-frame sets) + crop/resize/composite on 5 frames (cv2, as the
+      reference does).  chunk = enc + t10 + 5*t14 + 4*t15 + 10*prepost5   (window lengths
+      10,14,15,14,15,14,15,14,15,14)."""
     import torch
     from oracle import sttn_oracle as O
 
     torch.set_num_threads(threads)
-    t0 = time.perf_counter()
-    O.sttn_call(w, frames[:sample_frames], mask)
-    dt = time.perf_counter() - t0
-    return sample_frames / dt, dt
+    t_all0 = time.perf_counter()
+    strip = [np.ascontiguousarray(f[720:1080]) for f in frames]
+    try:
+        import cv2
+        resize = lambda a, w_, h_: cv2.resize(a, (w_, h_))  # noqa: E731
+    except ImportError:  # pragma: no cover
+        resize = lambda a, w_, h_: O.cv2_resize_linear_u8(a, w_, h_)  # noqa: E731
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        small = [resize(s, 640, 120) for s in strip[:5]]
+        t_pre5 = time.perf_counter() - t0
+        small += [resize(s, 640, 120) for s in strip[5:]]
+        if calibrate:  # one 6-frame window is enough to rank thread counts
+            t0 = time.perf_counter()
+            feats = O.encoder(w, O.frames_to_tensor(small[:6]))
+            O.quantise(O.decoder(w, O.infer(w, feats)[:6]))
+            return 1.0 / (time.perf_counter() - t0), 0.0
+        t0 = time.perf_counter()
+        feats = O.encoder(w, O.frames_to_tensor(small))
+        t_enc = time.perf_counter() - t0
+        sched = O.window_schedule(len(frames))
+        t_win, img = {}, None
+        for nb, refs in sched:
+            T = len(nb) + len(refs)
+            if T in t_win or len(t_win) >= 3:
+                continue
+            t0 = time.perf_counter()
+            img = O.quantise(O.decoder(w, O.infer(w, feats[nb + refs])[:len(nb)]))
+            t_win[T] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for i in range(5):
+            up = resize(img[i % len(img)].astype(np.float32), W, 360).astype(np.uint8)[:, :, ::-1]
+            m = (mask[720:1080] > 127)[:, :, None]
+            strip[i][:] = np.where(m, up, strip[i])
+        t_post5 = time.perf_counter() - t0
+    counts = {}
+    for nb, refs in sched:
+        counts[len(nb) + len(refs)] = counts.get(len(nb) + len(refs), 0) + 1
+    avg = float(np.mean(list(t_win.values())))
+    chunk = t_enc + sum(n * t_win.get(T, avg * T / np.mean(list(t_win))) for T, n in counts.items()) + (t_pre5 + t_post5) * len(frames) / 5
+    return len(frames) / chunk, time.perf_counter() - t_all0
+
+
+def best_cpu_threads(w, frames, mask):
+    """torch's CPU convs do not scale to every core of a 100+-thread host: time one 6-frame window at a few
+    thread counts and keep the fastest, so the baseline is the best the host can do, not the most threads."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} | {ncpu})
+    best, best_fps = ncpu, 0.0
+    for c in cands:
+        fps, _ = cpu_port_fps(w, frames, mask, c, calibrate=True)
+        if fps > best_fps:
+            best, best_fps = c, fps
+    return best
 
 
 def run_reference(args, rank, world):
@@ -110,16 +167,13 @@ def run_reference(args, rank, world):
 
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
     w, wdesc = load_weights()
     frames = O.synthetic_clip(CHUNK, H, W, seed=0)
     mask = O.default_mask(H, W)
-    sample = args.cpu_frames
-    for _ in range(min(args.warmup, 1)):
-        cpu_port_fps(w, frames, mask, 2, threads)
+    threads = best_cpu_threads(w, frames, mask)  # doubles as warm-up
     vals, dts = [], []
     for _ in range(args.steps):
-        fps, dt = cpu_port_fps(w, frames, mask, sample, threads)
+        fps, dt = cpu_port_fps(w, frames, mask, threads)
         vals.append(fps)
         dts.append(dt)
     value = float(np.mean(vals))
@@ -129,8 +183,8 @@ def run_reference(args, rank, world):
             "config": {"workload": "STTN sttn-auto 1080p synthetic clip, fixed subtitle bbox, neighbor_stride=5 (BASELINE config 2)",
                        "frame": [H, W], "chunk": CHUNK, "neighbor_stride": 5, "ref_length": 10},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} of the {CHUNK} frames of one 1080p chunk per step through oracle.sttn_call "
-                                       f"(torch {torch.__version__} CPU fp32)"},
+                             "sample": CPU_SAMPLE + f" (torch {torch.__version__} CPU fp32, {threads} of {os.cpu_count()} threads: "
+                                       "fastest of a sweep)"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -142,7 +196,6 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-frames", type=int, default=10, help="frames of the chunk the CPU port is timed on")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
 
@@ -265,11 +318,11 @@ def main():
     # ---- CPU port on a bounded sample (rank 0, N = 1 only) -------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        fps, dt = cpu_port_fps(w, frames, mask, args.cpu_frames, threads)
+        threads = best_cpu_threads(w, frames, mask)
+        fps, dt = cpu_port_fps(w, frames, mask, threads)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"first {args.cpu_frames} frames of the 1080p chunk through oracle.sttn_call ({dt:.1f} s, "
-                         f"torch {torch.__version__} CPU fp32)"}
+               "sample": CPU_SAMPLE + f" ({dt:.1f} s of CPU work, torch {torch.__version__} CPU fp32, {threads} of {os.cpu_count()} "
+                         "threads: fastest of a sweep)"}
 
     total_frames = world * args.steps * CHUNK
     line = {"metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
