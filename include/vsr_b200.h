@@ -34,6 +34,8 @@ typedef struct vsr_sttn_config {
   int32_t patch_w[4], patch_h[4];/* (80,15) (32,6) (10,5) (5,3)  (auto_sttn.py:69) */
   int32_t neighbor_stride;       /* config.sttnNeighborStride = 5 (backend/config.py:89) */
   int32_t ref_length;            /* config.sttnReferenceLength = 10 (backend/config.py:91) */
+  int32_t mode;                  /* 0 = sttn-auto (sttn_auto_inpaint.py), 1 = sttn-det (sttn_det_inpaint.py): masked encoder
+                                    input, low-res composite with the resized mask, whole strip replaced */
 } vsr_sttn_config;
 
 const char* vsr_last_error(void);
@@ -43,6 +45,9 @@ int vsr_device_count(void);
 
 /* ---- engine life cycle: replaces STTNInpaint.__init__ (sttn_auto_inpaint.py:29-41) ------------- */
 void vsr_sttn_default_config(vsr_sttn_config* cfg);
+/* STTNDetInpaint geometry: 432x240, patches (108,60) (36,20) (18,10) (9,5), mode 1
+ * (sttn_det_inpaint.py:33, sttn/network_sttn.py:70). */
+void vsr_sttn_det_config(vsr_sttn_config* cfg);
 int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg);
 void vsr_sttn_destroy(vsr_sttn_t* h);
 /* One call per tensor of ckpt['netG'] (name as in the state dict, e.g.
@@ -57,6 +62,10 @@ int vsr_sttn_finalize_weights(vsr_sttn_t* h);
  * (host) -> comps [T,model_h,model_w,3] fp32 RGB (host) and visits[T] (1 = the comp is the reference's
  * uint8 single-visit case, >1 = float32 blended). */
 int vsr_sttn_inpaint_strip(vsr_sttn_t* h, const uint8_t* frames_bgr, int T, float* comps_out, int32_t* visits_out);
+/* STTNDetInpaint.inpaint (sttn_det_inpaint.py:124-174): as above plus the resized mask [model_h,model_w] u8
+ * (0..255, one mask for all frames as STTNDetInpaint.__call__ builds it); mode 1 engines only. */
+int vsr_sttn_inpaint_strip_masked(vsr_sttn_t* h, const uint8_t* frames_bgr, const uint8_t* mask_small, int T, float* comps_out,
+                                  int32_t* visits_out);
 
 /* STTNInpaint.__call__ (sttn_auto_inpaint.py:43-97): T frames of H x W x 3 u8 BGR given as host
  * pointers, mask H x W u8 (>127 = subtitle).  frames_out[i] may equal frames_in[i] (in place, the

@@ -98,3 +98,29 @@ def test_call_real_weights_matches_reference(real_weights_path):
     assert d_ipp.max() <= 1 and (d_ipp > 0).mean() < 0.06
     for o, f in zip(out, frames):  # rows outside the strip are untouched
         assert np.array_equal(o[:y0], f[:y0]) and np.array_equal(o[y1:], f[y1:])
+
+
+@pytest.mark.slow
+def test_det_oracle_matches_reference():
+    """STTN-det (D1-D3): oracle vs the unmodified reference's comps and final strips (plain-C++ cv2 path)."""
+    from oracle import sttn_det_oracle as D
+
+    p = os.path.join(os.path.dirname(GOLDEN), "..", "weights", "sttn-det", "sttn.pth")
+    if not os.path.exists(p):
+        pytest.skip("sttn-det checkpoint not staged under weights/")
+    z = np.load(os.path.join(GOLDEN, "sttn_det_real.npz"))
+    H, W, T = int(z["H"]), int(z["W"]), int(z["T"])
+    w = O.load_weights(p)
+    frames = O.synthetic_clip(T, H, W, seed=int(z["seed"]))
+    mask = O.default_mask(H, W)
+    assert D.split_height(H, W) == int(W * 5 / 18)
+    y0, y1 = z["areas"][0][:2]
+    scaled = [O.cv2_resize_linear_u8(np.ascontiguousarray(f[y0:y1]), 432, 240) for f in frames]
+    msmall = O.cv2_resize_linear_u8(np.ascontiguousarray(mask[y0:y1]), 432, 240)
+    assert np.array_equal(msmall, z["mask_small"])
+    comps = D.inpaint_strip(w, scaled, [msmall] * T)
+    got = np.stack([c.astype(np.float32) for c in comps])
+    assert np.abs(got - z["comps"]).max() <= 1.0 and (got != z["comps"]).mean() < 1e-3
+    out = D.det_call(w, frames, mask)
+    d = np.abs(np.stack([o[y0:y1] for o in out]).astype(np.int32) - z["strip_out_plain"].astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3

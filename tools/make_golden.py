@@ -8,6 +8,7 @@ small taps are stored):
   sttn_auto_strip_real.npz   STTNInpaint.inpaint() on 7 strip frames [120,640,3], real weights
   sttn_auto_call_real.npz    STTNInpaint.__call__() on 8 frames 800x450 + default mask, real weights
   sttn_auto_strip_rand.npz   same network class loaded with oracle.random_weights(seed=0)
+  sttn_det_real.npz          STTNDetInpaint.inpaint() + __call__() on 7 frames 640x360, real sttn-det weights
   mask_index.npz             create_mask / get_inpaint_area_by_mask / batch_generator vectors
 """
 import os
@@ -92,6 +93,26 @@ def main():
     strip = [cv2.resize(f, (640, 120)) for f in O.synthetic_clip(T, 360, 1920, seed=12)]
     c, once = comps_pack(rnd.inpaint([s.copy() for s in strip]))
     np.savez_compressed(os.path.join(OUT, "sttn_auto_strip_rand.npz"), seed=12, T=T, wseed=0, comps=c, once=once)
+
+    # ---- sttn-det (D1-D3): strip level + full call, real weights
+    from backend.inpaint.sttn_det_inpaint import STTNDetInpaint
+    from oracle import sttn_det_oracle as D
+
+    det = STTNDetInpaint(dev, ref_import.weights_path("sttn-det"))
+    H, W, T = 360, 640, 7
+    frames = O.synthetic_clip(T, H, W, seed=9)
+    mask = O.default_mask(H, W)
+    sh = D.split_height(H, W)
+    areas = RT.get_inpaint_area_by_mask(W, H, sh, mask[:, :, None])
+    y0, y1 = areas[0][:2]
+    scaled = [cv2.resize(f[y0:y1], (432, 240)) for f in frames]
+    msmall = cv2.resize(mask[y0:y1], (432, 240))
+    c, once = comps_pack(det.inpaint([s_.copy() for s_ in scaled], [msmall.copy() for _ in scaled]))
+    cv2.setUseOptimized(False)
+    out_plain = det([f.copy() for f in frames], mask)
+    cv2.setUseOptimized(True)
+    np.savez_compressed(os.path.join(OUT, "sttn_det_real.npz"), seed=9, H=H, W=W, T=T, areas=np.array(areas), comps=c, once=once,
+                        mask_small=msmall, strip_out_plain=np.stack([o[y0:y1] for o in out_plain]))
 
     # ---- integer path vectors
     rng = np.random.default_rng(5)

@@ -7,7 +7,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("VSR_REFERENCE_ROOT", "/root/reference")
-FILES = {"sttn-auto/infer_model.pth": "backend/models/sttn-auto/infer_model.pth"}
+FILES = {"sttn-auto/infer_model.pth": "backend/models/sttn-auto/infer_model.pth",
+         "sttn-det/sttn.pth": "backend/models/sttn-det/sttn.pth"}
 
 
 def main(quiet=False):

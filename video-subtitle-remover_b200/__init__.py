@@ -4,6 +4,7 @@ YaoFANGUK/video-subtitle-remover, behind the reference's own plug-in interface.
 Public surface (same names / call conventions as the reference back-ends):
     STTNInpaint(device, model_path)(frames, mask)                 backend/inpaint/sttn_auto_inpaint.py:28
     STTNAutoInpaint(device, model_path, video_path, ...)(...)     backend/inpaint/sttn_auto_inpaint.py:167
+    STTNDetInpaint(device, model_path)(frames, mask)              backend/inpaint/sttn_det_inpaint.py:23
     create_mask / get_inpaint_area_by_mask / batch_generator      backend/tools/inpaint_tools.py
     InpaintMode                                                   backend/tools/constant.py:4
 All compute goes through the C-ABI library built from csrc/ (include/vsr_b200.h); importing the
@@ -13,6 +14,7 @@ from .constant import InpaintMode  # noqa: F401
 from .config import config  # noqa: F401
 from .inpaint_tools import batch_generator, create_mask, get_inpaint_area_by_mask  # noqa: F401
 from .sttn_auto_inpaint import STTNAutoInpaint, STTNInpaint  # noqa: F401
+from .sttn_det_inpaint import STTNDetInpaint  # noqa: F401
 
-__all__ = ["STTNInpaint", "STTNAutoInpaint", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
+__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
            "batch_generator"]

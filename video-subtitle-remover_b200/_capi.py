@@ -38,7 +38,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
 class Config(C.Structure):
     _fields_ = [("model_w", C.c_int32), ("model_h", C.c_int32), ("n_patch", C.c_int32), ("patch_w", C.c_int32 * 4),
-                ("patch_h", C.c_int32 * 4), ("neighbor_stride", C.c_int32), ("ref_length", C.c_int32)]
+                ("patch_h", C.c_int32 * 4), ("neighbor_stride", C.c_int32), ("ref_length", C.c_int32), ("mode", C.c_int32)]
 
 
 _lib = None
@@ -54,11 +54,13 @@ _PROTOS = {
     "vsr_version": (C.c_char_p, []),
     "vsr_device_count": (C.c_int, []),
     "vsr_sttn_default_config": (None, [C.POINTER(Config)]),
+    "vsr_sttn_det_config": (None, [C.POINTER(Config)]),
     "vsr_sttn_create": (C.c_int, [_pp, C.c_int, C.POINTER(Config)]),
     "vsr_sttn_destroy": (None, [C.c_void_p]),
     "vsr_sttn_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, _i64p, C.c_int]),
     "vsr_sttn_finalize_weights": (C.c_int, [C.c_void_p]),
     "vsr_sttn_inpaint_strip": (C.c_int, [C.c_void_p, _u8p, C.c_int, _f32p, _i32p]),
+    "vsr_sttn_inpaint_strip_masked": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, _f32p, _i32p]),
     "vsr_sttn_inpaint_frames": (C.c_int, [C.c_void_p, _pp, C.c_int, C.c_int, C.c_int, _u8p, _pp]),
     "vsr_sttn_stage": (C.c_int, [C.c_void_p, _pp, C.c_int, C.c_int, C.c_int, _u8p]),
     "vsr_sttn_compute": (C.c_int, [C.c_void_p]),

@@ -38,6 +38,9 @@ struct ConvParams {
   float* comps;        // [chunk_T, H, W, 3] fp32 RGB running composites
   const int* frame_idx;   // window-local frame -> chunk frame
   const int* first_visit; // window-local frame -> 1 if this is the first time the frame is decoded
+  // sttn-det low-res composite (sttn_det_inpaint.py:168): comp = mask>0 ? pred : input frame (RGB)
+  const uint8_t* det_mask;  // [H,W] resized mask, nullptr for sttn-auto
+  const uchar4* det_rgb;    // [chunk_T,H,W] RGBA8 input frames at model resolution
 };
 
 template <int BN_>
@@ -120,12 +123,20 @@ struct ConvPolicy {
       const int f = p.frame_idx[c.t];
       float* dst = p.comps + (((size_t)f * p.H + c.y) * p.W + c.x) * 3;
       const bool first = p.first_visit[c.t] != 0;
+      bool keep_input = false;
+      uchar4 in_px = make_uchar4(0, 0, 0, 0);
+      if (p.det_mask) {
+        keep_input = p.det_mask[(size_t)c.y * p.W + c.x] == 0;
+        in_px = p.det_rgb[((size_t)f * p.H + c.y) * p.W + c.x];
+      }
+      const float in_rgb[3] = {(float)in_px.x, (float)in_px.y, (float)in_px.z};
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         // sttn_auto_inpaint.py:150-158: tanh -> (x+1)/2 -> *255 -> astype(uint8) (truncation)
         float y = (tanhf(v[i]) + 1.0f) * 0.5f;
         y = y * 255.0f;
-        const float q = (float)(unsigned char)fminf(fmaxf(y, 0.f), 255.f);
+        float q = (float)(unsigned char)fminf(fmaxf(y, 0.f), 255.f);
+        if (keep_input) q = in_rgb[i];
         dst[i] = first ? q : (dst[i] * 0.5f + q * 0.5f);  // :159-162
       }
       return;

@@ -45,11 +45,28 @@ __global__ void __launch_bounds__(256) strip_downscale_kernel(const uint8_t* __r
   reinterpret_cast<uchar4*>(dst)[((size_t)t * dh + y) * dw + x] = o;
 }
 
+// cv2.resize of the single-channel mask strip (sttn_det_inpaint.py:73), same fixed-point arithmetic.
+__global__ void __launch_bounds__(256) mask_downscale_kernel(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst,
+                                                             int dw, int dh, ResizeTaps tx, ResizeTaps ty) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= dw) return;
+  const uint8_t* r0 = src + (size_t)ty.i0[y] * sw;
+  const uint8_t* r1 = src + (size_t)ty.i1[y] * sw;
+  const int s0 = r0[tx.i0[x]] * tx.w0[x] + r0[tx.i1[x]] * tx.w1[x];
+  const int s1 = r1[tx.i0[x]] * tx.w0[x] + r1[tx.i1[x]] * tx.w1[x];
+  const int v = (((ty.w0[y] * (s0 >> 4)) >> 16) + ((ty.w1[y] * (s1 >> 4)) >> 16) + 2) >> 2;
+  dst[(size_t)y * dw + x] = (uint8_t)min(max(v, 0), 255);
+}
+
 // A5 first layer (auto_sttn.py:76-77): conv3x3 stride 2 pad 1, 3 -> 64, LeakyReLU(0.2), computed in
 // fp32 from the RGBA8 image with the `/255*2-1` normalisation of sttn_auto_inpaint.py:128 folded in.
 // in [T,H,W] RGBA8 -> out NHWC fp16 [T,H/2,W/2,64].  Block = 64 output pixels x 4 channel groups.
+// sttn-det: `det_mask` [H,W] u8 (the resized mask); pixels with mask/255 > 0.5 enter the encoder as 0
+// (feats*(1-masks_tensor), sttn_det_inpaint.py:134,143).
 __global__ void __launch_bounds__(256) stem_conv_kernel(const uchar4* __restrict__ in, int H, int W, const float* __restrict__ wgt,
-                                                        const float* __restrict__ bias, __half* __restrict__ out, int total_pix) {
+                                                        const float* __restrict__ bias, __half* __restrict__ out, int total_pix,
+                                                        const uint8_t* __restrict__ det_mask) {
   __shared__ float sw[27 * 64];  // [tap*3+ci][co]
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 27 * 64; i += 256) sw[i] = wgt[i];
@@ -74,8 +91,9 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const uchar4* __restrict
       const int ix = ox * 2 + kx - 1;
       if (ix < 0 || ix >= W) continue;
       const uchar4 px = in[((size_t)t * H + iy) * W + ix];
-      const float v[3] = {(float)px.x / 255.0f * 2.0f - 1.0f, (float)px.y / 255.0f * 2.0f - 1.0f,
-                          (float)px.z / 255.0f * 2.0f - 1.0f};
+      float v[3] = {(float)px.x / 255.0f * 2.0f - 1.0f, (float)px.y / 255.0f * 2.0f - 1.0f,
+                    (float)px.z / 255.0f * 2.0f - 1.0f};
+      if (det_mask && det_mask[(size_t)iy * W + ix] >= 128) v[0] = v[1] = v[2] = 0.f;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float* wr = sw + ((ky * 3 + kx) * 3 + ci) * 64 + cg * 16;
@@ -148,7 +166,7 @@ __global__ void __launch_bounds__(256) strip_composite_kernel(const float* __res
   const int y = blockIdx.y;
   const int t = blockIdx.z;
   if (x >= sw) return;
-  if (mask[(size_t)y * mask_pitch + x] == 0) return;
+  if (mask && mask[(size_t)y * mask_pitch + x] == 0) return;  // mask == nullptr (sttn-det): the whole strip is replaced
   const float* f = comps + (size_t)t * ch * cw * 3;
   const int x0 = tx.i0[x], x1 = tx.i1[x], y0 = ty.i0[y], y1 = ty.i1[y];
   const float* p00 = f + ((size_t)y0 * cw + x0) * 3;

@@ -276,6 +276,8 @@ struct ConvIO {
   float* comps = nullptr;
   const int* frame_idx = nullptr;
   const int* first_visit = nullptr;
+  const uint8_t* det_mask = nullptr;
+  const uchar4* det_rgb = nullptr;
 };
 
 static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
@@ -315,6 +317,8 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   p.comps = io.comps;
   p.frame_idx = io.frame_idx;
   p.first_visit = io.first_visit;
+  p.det_mask = io.det_mask;
+  p.det_rgb = io.det_rgb;
   if (io.flags & CONV_S2D_STORE) {
     REQUIRE(io.H % 2 == 0 && io.W % 2 == 0, "s2d store needs even H, W");
     p.out16_pitch = 4 * L.cout;
@@ -531,9 +535,9 @@ struct vsr_sttn {
   ConvLayer qkv[8], outl[8], ff0[8], ff1[8];
   // activations
   DevBuf strips, rgb8, e1, e2s, e3, feats16, feats32, xw16, xw32, qkvb, att16, ffn16, up1, d1, d2, up2, d3, comps, visits_d,
-      sched_d, mask_d;
+      sched_d, mask_d, msmall;  // msmall: sttn-det resized mask [model_h, model_w]
   AttnWorkspace attn;
-  DevTaps pre_x, pre_y, post_x, post_y;
+  DevTaps pre_x, pre_y, post_x, post_y, mpre_x, mpre_y;
   // staged job
   int T = 0, H = 0, W = 0, split_h = 0;
   std::vector<std::array<int, 4>> areas;
@@ -638,7 +642,9 @@ static void finalize(vsr_sttn* h) {
 
 // Encoder + window loop + decoder on T strip frames already on the device as u8 [T, sh, sw, 3] BGR
 // (sttn_auto_inpaint.py:122-164).  Leaves comps [T,MH,MW,3] fp32 and visits on the device.
-static void run_network(vsr_sttn* h, int T, int sw, int sh) {
+// `mask_strip` (sttn-det only): the strip rows of the full-resolution mask on the device, pitch sw; when null in
+// det mode the resized mask is taken from h->msmall as is (vsr_sttn_inpaint_strip_masked).
+static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_strip = nullptr) {
   Ctx& c = h->ctx;
   const int MW = h->cfg.model_w, MH = h->cfg.model_h, FH = h->FH, FW = h->FW, C = 256;
   cudaStream_t s = c.stream;
@@ -689,6 +695,7 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh) {
   h->up2.ensure(maxn * fpix * 16 * 64 * 2);
   h->d3.ensure(maxn * fpix * 16 * 64 * 2);
   h->comps.ensure((size_t)T * MH * MW * 3 * 4);
+  if (h->cfg.mode == 1) h->msmall.ensure((size_t)MH * MW);
 
   // A3/A4 pre-processing
   h->pre_x.build(sw, MW, false, s);
@@ -698,11 +705,24 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh) {
                                                                         h->pre_y.view());
   CK(cudaGetLastError());
   ++c.launches;
+  const bool det = h->cfg.mode == 1;
+  if (det) {
+    h->msmall.ensure((size_t)MH * MW);
+    if (mask_strip) {  // D1: the mask strip goes through the same cv2.resize as the frames (sttn_det_inpaint.py:73)
+      h->mpre_x.build(sw, MW, false, s);
+      h->mpre_y.build(sh, MH, true, s);
+      mask_downscale_kernel<<<dim3((MW + 255) / 256, MH), 256, 0, s>>>(mask_strip, sw, sh, h->msmall.as<uint8_t>(), MW, MH,
+                                                                       h->mpre_x.view(), h->mpre_y.view());
+      CK(cudaGetLastError());
+      ++c.launches;
+    }
+  }
+  const uint8_t* det_mask = det ? h->msmall.as<uint8_t>() : nullptr;
   // A5 encoder
   {
     const int total = T * (MH / 2) * (MW / 2);
     stem_conv_kernel<<<(total + 63) / 64, 256, 0, s>>>(h->rgb8.as<uchar4>(), MH, MW, h->stem_w.as<float>(), h->stem_b.as<float>(),
-                                                        h->e1.as<__half>(), total);
+                                                        h->e1.as<__half>(), total, det_mask);
     CK(cudaGetLastError());
     ++c.launches;
     ConvIO io;
@@ -793,6 +813,8 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh) {
       e.comps = h->comps.as<float>();
       e.frame_idx = h->sched_d.as<int>() + wi * 64;
       e.first_visit = h->sched_d.as<int>() + wi * 64 + 32;
+      e.det_mask = det_mask;
+      e.det_rgb = h->rgb8.as<uchar4>();
       run_conv(c, h->dec6, e);
     }
   }
@@ -854,11 +876,14 @@ static void enqueue_area(vsr_sttn* h, int k) {
   const int y0 = h->areas[k][0], y1 = h->areas[k][1];
   const int sh = y1 - y0, sw = h->W;
   cudaStream_t s = h->ctx.stream;
-  run_network(h, h->T, sw, sh);
+  const bool det = h->cfg.mode == 1;
+  const uint8_t* mask_strip = h->mask_d.as<uint8_t>() + (size_t)y0 * sw;
+  run_network(h, h->T, sw, sh, det ? mask_strip : nullptr);
   h->post_x.build(h->cfg.model_w, sw, false, s);
   h->post_y.build(h->cfg.model_h, sh, true, s);
+  // sttn-auto: mask ? comp : frame (sttn_auto_inpaint.py:91);  sttn-det: the whole strip is replaced (sttn_det_inpaint.py:93)
   strip_composite_kernel<<<dim3((sw + 255) / 256, sh, h->T), 256, 0, s>>>(
-      h->comps.as<float>(), h->cfg.model_w, h->cfg.model_h, h->visits_d.as<int>(), h->mask_d.as<uint8_t>() + (size_t)y0 * sw, sw,
+      h->comps.as<float>(), h->cfg.model_w, h->cfg.model_h, h->visits_d.as<int>(), det ? nullptr : mask_strip, sw,
       h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh, h->T, h->post_x.view(), h->post_y.view());
   CK(cudaGetLastError());
   ++h->ctx.launches;
@@ -920,23 +945,36 @@ static void fetch_area(vsr_sttn* h, int k, uint8_t* const* out) {
   parallel_for(h->T, [&](int t) { memcpy(out[t] + (size_t)y0 * sw * 3, h->pinned + t * sb, sb); });
 }
 
+// Mask analysis shared by the synchronous and the asynchronous entry points.  sttn-auto thresholds the mask
+// (cv2.threshold(mask,127,1,BINARY), sttn_auto_inpaint.py:48) and uses split_h = int(W*3/16) (:54); sttn-det
+// keeps the raw mask (its resized copy gates the encoder input and the low-res composite) and uses
+// int(W*5/18) / int(H*5/9) (sttn_det_inpaint.py:48-51).  Returns true when the mask changed.
+static bool analyze_mask(vsr_sttn* h, int H, int W, const uint8_t* mask) {
+  const bool det = h->cfg.mode == 1;
+  h->split_h = det ? (H > W ? (int)((double)H * 5 / 9) : (int)((double)W * 5 / 18)) : (int)((double)W * 3 / 16);
+  const size_t mb = (size_t)H * W;
+  if (h->mask_h.size() == mb && h->mask_H == H && memcmp(h->mask_h.data(), mask, mb) == 0) return false;
+  h->mask_h.assign(mask, mask + mb);
+  h->mask_H = H;
+  std::vector<uint8_t> m01(mb);
+  if (det) {
+    for (size_t i = 0; i < mb; ++i) m01[i] = mask[i] != 0;  // get_inpaint_area_by_mask binarises with `mask > 0`
+  } else {
+    for (size_t i = 0; i < mb; ++i) m01[i] = mask[i] > 127 ? 1 : 0;
+  }
+  h->areas = host_inpaint_areas(W, H, h->split_h, m01.data(), 1);
+  h->mask_d.ensure(mb);
+  CK(cudaMemcpyAsync(h->mask_d.p, det ? mask : m01.data(), mb, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return true;
+}
+
 static void stage(vsr_sttn* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask) {
   check_ready(h);
   REQUIRE(T >= 1 && H >= 1 && W >= 1 && frames_in && mask, "bad frame batch");
   h->T = T; h->H = H; h->W = W;
-  h->split_h = (int)((double)W * 3 / 16);  // sttn_auto_inpaint.py:54
   h->in_ptrs.assign(frames_in, frames_in + T);
-  const size_t mb = (size_t)H * W;
-  if (h->mask_h.size() != mb || h->mask_H != H || memcmp(h->mask_h.data(), mask, mb) != 0) {  // same mask: keep strips + device copy
-    h->mask_h.assign(mask, mask + mb);
-    h->mask_H = H;
-    std::vector<uint8_t> m01(mb);
-    for (size_t i = 0; i < mb; ++i) m01[i] = mask[i] > 127 ? 1 : 0;  // cv2.threshold(mask,127,1,BINARY) :48
-    h->areas = host_inpaint_areas(W, H, h->split_h, m01.data(), 1);
-    h->mask_d.ensure(mb);
-    CK(cudaMemcpyAsync(h->mask_d.p, m01.data(), mb, cudaMemcpyHostToDevice, h->ctx.stream));
-    CK(cudaStreamSynchronize(h->ctx.stream));
-  }
+  analyze_mask(h, H, W, mask);
   h->staged_area = -1;
   if (!h->areas.empty()) stage_area(h, 0);
 }
@@ -950,20 +988,13 @@ static int64_t submit(vsr_sttn* h, const uint8_t* const* frames_in, int T, int H
   if (sl.busy) throw Error(VSR_ERR_STATE, "vsr_sttn_submit: two chunks already in flight, collect one first");
   // mask analysis (cached) — same as the synchronous path
   h->T = T; h->H = H; h->W = W;
-  h->split_h = (int)((double)W * 3 / 16);
-  const size_t mb = (size_t)H * W;
-  if (h->mask_h.size() != mb || h->mask_H != H || memcmp(h->mask_h.data(), mask, mb) != 0) {
-    // a new mask re-uploads on the compute stream: drain the pipeline first
-    for (auto& o : h->slot)
-      if (o.busy) throw Error(VSR_ERR_STATE, "vsr_sttn_submit: the mask may only change when no chunk is in flight");
-    h->mask_h.assign(mask, mask + mb);
-    h->mask_H = H;
-    std::vector<uint8_t> m01(mb);
-    for (size_t i = 0; i < mb; ++i) m01[i] = mask[i] > 127 ? 1 : 0;
-    h->areas = host_inpaint_areas(W, H, h->split_h, m01.data(), 1);
-    h->mask_d.ensure(mb);
-    CK(cudaMemcpyAsync(h->mask_d.p, m01.data(), mb, cudaMemcpyHostToDevice, h->ctx.stream));
-    CK(cudaStreamSynchronize(h->ctx.stream));
+  {
+    const size_t mb = (size_t)H * W;
+    const bool same = h->mask_h.size() == mb && h->mask_H == H && memcmp(h->mask_h.data(), mask, mb) == 0;
+    if (!same)  // a new mask re-uploads on the compute stream: only with an empty pipeline
+      for (auto& o : h->slot)
+        if (o.busy) throw Error(VSR_ERR_STATE, "vsr_sttn_submit: the mask may only change when no chunk is in flight");
+    analyze_mask(h, H, W, mask);
   }
   if (h->areas.size() != 1) throw Error(VSR_ERR_STATE, "vsr_sttn_submit handles exactly one strip; use vsr_sttn_inpaint_frames");
   if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -1058,6 +1089,19 @@ void vsr_sttn_default_config(vsr_sttn_config* cfg) {
   cfg->ref_length = 10;
 }
 
+void vsr_sttn_det_config(vsr_sttn_config* cfg) {
+  if (!cfg) return;
+  vsr_sttn_default_config(cfg);
+  cfg->model_w = 432;
+  cfg->model_h = 240;
+  const int pw[4] = {108, 36, 18, 9}, ph[4] = {60, 20, 10, 5};
+  for (int i = 0; i < 4; ++i) {
+    cfg->patch_w[i] = pw[i];
+    cfg->patch_h[i] = ph[i];
+  }
+  cfg->mode = 1;
+}
+
 int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
   return guarded([&] {
     REQUIRE(out, "out pointer");
@@ -1077,9 +1121,9 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->ctx.device = device;
     h->ctx.sms = prop.multiProcessorCount;
     if (cfg) h->cfg = *cfg; else vsr_sttn_default_config(&h->cfg);
-    if (h->cfg.model_w % 32 || h->cfg.model_h % 8) {
+    if (h->cfg.model_w % 8 || h->cfg.model_h % 8 || h->cfg.mode < 0 || h->cfg.mode > 1) {
       delete h;
-      throw Error(VSR_ERR_ARG, "model size must be a multiple of (32, 8)");
+      throw Error(VSR_ERR_ARG, "model size must be a multiple of 8 and mode 0 or 1");
     }
     h->FW = h->cfg.model_w / 4;
     h->FH = h->cfg.model_h / 4;
@@ -1123,11 +1167,32 @@ int vsr_sttn_inpaint_strip(vsr_sttn_t* h, const uint8_t* frames_bgr, int T, floa
   return guarded([&] {
     check_ready(h);
     REQUIRE(frames_bgr && comps_out && T >= 1, "bad arguments");
+    REQUIRE(h->cfg.mode == 0, "sttn-det engines take the resized mask: use vsr_sttn_inpaint_strip_masked");
     const int MW = h->cfg.model_w, MH = h->cfg.model_h;
     const size_t sb = (size_t)MH * MW * 3;
     h->strips.ensure(sb * T);
     CK(cudaMemcpyAsync(h->strips.p, frames_bgr, sb * T, cudaMemcpyHostToDevice, h->ctx.stream));
     run_network(h, T, MW, MH);
+    CK(cudaMemcpyAsync(comps_out, h->comps.p, sb * T * sizeof(float), cudaMemcpyDeviceToHost, h->ctx.stream));
+    sync_stream(h);
+    if (visits_out)
+      for (int t = 0; t < T; ++t) visits_out[t] = h->visits_h[t];
+  });
+}
+
+int vsr_sttn_inpaint_strip_masked(vsr_sttn_t* h, const uint8_t* frames_bgr, const uint8_t* mask_small, int T, float* comps_out,
+                                  int32_t* visits_out) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(h->cfg.mode == 1, "vsr_sttn_inpaint_strip_masked needs an sttn-det engine (mode 1)");
+    REQUIRE(frames_bgr && mask_small && comps_out && T >= 1, "bad arguments");
+    const int MW = h->cfg.model_w, MH = h->cfg.model_h;
+    const size_t sb = (size_t)MH * MW * 3;
+    h->strips.ensure(sb * T);
+    h->msmall.ensure((size_t)MH * MW);
+    CK(cudaMemcpyAsync(h->strips.p, frames_bgr, sb * T, cudaMemcpyHostToDevice, h->ctx.stream));
+    CK(cudaMemcpyAsync(h->msmall.p, mask_small, (size_t)MH * MW, cudaMemcpyHostToDevice, h->ctx.stream));
+    run_network(h, T, MW, MH, nullptr);
     CK(cudaMemcpyAsync(comps_out, h->comps.p, sb * T * sizeof(float), cudaMemcpyDeviceToHost, h->ctx.stream));
     sync_stream(h);
     if (visits_out)

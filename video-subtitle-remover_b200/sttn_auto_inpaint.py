@@ -55,15 +55,17 @@ def load_state_dict(model_path) -> Dict[str, np.ndarray]:
 class STTNInpaint:
     """Drop-in for backend/inpaint/sttn_auto_inpaint.py:28 `STTNInpaint`."""
 
+    _DET = False  # STTNDetInpaint flips this: 432x240 geometry, masked encoder input, low-res composite
+
     def __init__(self, device, model_path):
         self.device = device
         self._dev = _device_index(device)
-        self.model_input_width, self.model_input_height = 640, 120  # :38
         self.neighbor_stride = config.sttnNeighborStride.value      # :40
         self.ref_length = config.sttnReferenceLength.value          # :41
         L = _capi.lib()
         cfg = _capi.Config()
-        L.vsr_sttn_default_config(C.byref(cfg))
+        (L.vsr_sttn_det_config if self._DET else L.vsr_sttn_default_config)(C.byref(cfg))
+        self.model_input_width, self.model_input_height = int(cfg.model_w), int(cfg.model_h)  # :38 / sttn_det_inpaint.py:33
         cfg.neighbor_stride = int(self.neighbor_stride)
         cfg.ref_length = int(self.ref_length)
         h = C.c_void_p()
