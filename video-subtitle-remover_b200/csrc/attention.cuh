@@ -46,6 +46,13 @@ struct AttnHead {
   int scoreB_begin, scoreB_begin2;  // pass-B work lists (fused problems only)
 };
 
+// 2^x on the SFU (ex2.approx: 2 ulp, exact 0 for -inf) — the softmax is bandwidth-bound only if its math stays cheap
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int ATTN_MAX_HEADS = 8;  // (windows in a group) x (patch geometries)
 
 struct ScoreParams {
@@ -54,6 +61,10 @@ struct ScoreParams {
   int nheads, total_work, total_work2;
   int pass;  // 0 = pass A (max / S slabs), 1 = pass B (P)
   int totalB, totalB2;
+  // LPT schedule of pass A (tiles cost between 1 and >100 K-chunks): order[who*order_stride + i], -1 terminated;
+  // nullptr = round robin
+  const int* order;
+  int order_stride;
 };
 
 struct ScorePolicy {
@@ -78,6 +89,9 @@ struct ScorePolicy {
     }
   }
   __device__ static int num_tiles(const Params& p) { return p.pass ? p.totalB : p.total_work; }
+  __device__ static int tile_at(const Params& p, int who, int n_who, int i, int ntiles) {
+    return (p.order && p.pass == 0) ? tc_tile_listed(p.order, p.order_stride, who, i) : tc_tile_round_robin(who, n_who, i, ntiles);
+  }
   __device__ static Tile get_tile(const Params& p, int idx) {
     int hd = 0;
     if (p.pass) {
@@ -259,8 +273,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
     const int c = (i * 256 + threadIdx.x) * 4;
     if (c < ncols) {
       // exp2f(-inf) = 0 for the masked slots
-      const __half2 h01 = __floats2half2_rn(exp2f((v[i].x - m) * sc), exp2f((v[i].y - m) * sc));
-      const __half2 h23 = __floats2half2_rn(exp2f((v[i].z - m) * sc), exp2f((v[i].w - m) * sc));
+      const __half2 h01 = __floats2half2_rn(fast_exp2((v[i].x - m) * sc), fast_exp2((v[i].y - m) * sc));
+      const __half2 h23 = __floats2half2_rn(fast_exp2((v[i].z - m) * sc), fast_exp2((v[i].w - m) * sc));
       const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
       sum += (f01.x + f01.y) + (f23.x + f23.y);  // normalise by what the PV GEMM will actually multiply with
       uint2 pk;
@@ -289,6 +303,8 @@ struct PVParams {
   int out_pitch;     // starting at element offset out_off[s] (its window's first frame)
   int coff[ATTN_MAX_HEADS];
   long long out_off[ATTN_MAX_HEADS];
+  const int* order;  // LPT schedule, see ScoreParams
+  int order_stride;
 };
 
 struct PVPolicy {
@@ -314,6 +330,9 @@ struct PVPolicy {
     }
   }
   __device__ static int num_tiles(const Params& p) { return p.total_work; }
+  __device__ static int tile_at(const Params& p, int who, int n_who, int i, int ntiles) {
+    return (p.order) ? tc_tile_listed(p.order, p.order_stride, who, i) : tc_tile_round_robin(who, n_who, i, ntiles);
+  }
   __device__ static Tile get_tile(const Params& p, int idx) {
     int hd = 0;
     while (hd + 1 < p.nheads && idx >= p.h[hd + 1].pv_work_begin) ++hd;
@@ -408,6 +427,9 @@ struct Score2Policy {
   using RowCtx = ScorePolicy::RowCtx;
   __device__ static void prefetch(const Params& p) { ScorePolicy::prefetch(p); }
   __device__ static int num_tiles(const Params& p) { return p.pass ? p.totalB2 : p.total_work2; }
+  __device__ static int tile_at(const Params& p, int who, int n_who, int i, int ntiles) {
+    return (p.order && p.pass == 0) ? tc_tile_listed(p.order, p.order_stride, who, i) : tc_tile_round_robin(who, n_who, i, ntiles);
+  }
   __device__ static Tile get_tile(const Params& p, int idx, uint32_t rank) {
     int hd = 0;
     if (p.pass) {
@@ -463,6 +485,9 @@ struct PV2Policy {
   using RowCtx = PVPolicy::RowCtx;
   __device__ static void prefetch(const Params& p) { PVPolicy::prefetch(p); }
   __device__ static int num_tiles(const Params& p) { return p.total_work2; }
+  __device__ static int tile_at(const Params& p, int who, int n_who, int i, int ntiles) {
+    return (p.order) ? tc_tile_listed(p.order, p.order_stride, who, i) : tc_tile_round_robin(who, n_who, i, ntiles);
+  }
   __device__ static Tile get_tile(const Params& p, int idx, uint32_t rank) {
     int hd = 0;
     while (hd + 1 < p.nheads && idx >= p.h[hd + 1].pv_work_begin2) ++hd;

@@ -66,6 +66,7 @@ struct ConvPolicy {
     tma_prefetch_desc(&p.w_map);
   }
   __device__ static int num_tiles(const Params& p) { return p.T * p.tiles_y * p.tiles_x * p.n_tiles; }
+  __device__ static int tile_at(const Params&, int who, int n_who, int i, int ntiles) { return tc_tile_round_robin(who, n_who, i, ntiles); }
   __device__ static Tile get_tile(const Params& p, int idx) {
     Tile t;
     const int n = idx % p.n_tiles;
@@ -188,6 +189,7 @@ struct Conv2Policy {
     tma_prefetch_desc(&p.w_map_half);
   }
   __device__ static int num_tiles(const Params& p) { return ((p.T * p.tiles_y * p.tiles_x + 1) >> 1) * p.n_tiles; }
+  __device__ static int tile_at(const Params&, int who, int n_who, int i, int ntiles) { return tc_tile_round_robin(who, n_who, i, ntiles); }
   __device__ static Tile get_tile(const Params& p, int idx, uint32_t rank) {
     Tile t;
     const int n = idx % p.n_tiles;

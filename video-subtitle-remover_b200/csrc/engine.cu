@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <queue>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -144,6 +146,7 @@ struct Ctx {
   int64_t launches = 0;
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
+  bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
   bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
 };
 
@@ -343,9 +346,46 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
 }
 
 // ------------------------------------------------------------------------------------------------ attention
+struct TileSchedule {
+  DevBuf dev;
+  int stride = 0;
+};
 struct AttnWorkspace {
   DevBuf S[ATTN_MAX_HEADS], P[ATTN_MAX_HEADS], rowsum[ATTN_MAX_HEADS], rowmax_part[ATTN_MAX_HEADS], rowsum_part[ATTN_MAX_HEADS];
+  std::map<std::string, std::unique_ptr<TileSchedule>> schedules;  // LPT tile orders, keyed by the problem shapes
 };
+
+// Longest-processing-time-first assignment of tiles (cost in K-chunks + a fixed per-tile overhead) to `bins`
+// CTAs / CTA pairs.  The attention launches mix tiles of 1 to >100 chunks; round robin left the busiest CTA
+// ~28 % above the mean.  Cached per shape signature so the device pointer is stable under CUDA graphs.
+static const TileSchedule& lpt_schedule(AttnWorkspace& ws, const std::string& key, const std::vector<int>& cost, int bins,
+                                        cudaStream_t stream) {
+  auto it = ws.schedules.find(key);
+  if (it != ws.schedules.end()) return *it->second;
+  const int n = (int)cost.size();
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  std::vector<std::vector<int>> lists(bins);
+  typedef std::pair<long long, int> LB;  // (load, bin)
+  std::priority_queue<LB, std::vector<LB>, std::greater<LB>> pq;
+  for (int b = 0; b < bins; ++b) pq.push({0, b});
+  for (int i : idx) {
+    LB lb = pq.top();
+    pq.pop();
+    lists[lb.second].push_back(i);
+    pq.push({lb.first + cost[i], lb.second});
+  }
+  size_t maxlen = 1;
+  for (auto& l : lists) maxlen = std::max(maxlen, l.size() + 1);
+  std::vector<int> flat((size_t)bins * maxlen, -1);
+  for (int b = 0; b < bins; ++b)
+    for (size_t j = 0; j < lists[b].size(); ++j) flat[(size_t)b * maxlen + j] = lists[b][j];
+  auto sch = std::make_unique<TileSchedule>();
+  sch->stride = (int)maxlen;
+  upload(sch->dev, flat, stream);
+  return *(ws.schedules[key] = std::move(sch));
+}
 
 static int next_pow2(int v) {
   int p = 1;
@@ -473,6 +513,28 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   pp.T = 0; pp.H = H; pp.W = W;
   pp.out = out;
   pp.out_pitch = out_pitch;
+  if (c.attn_lpt) {
+    const bool two = c.attn_2cta;
+    const int bins = two ? c.sms / 2 : c.sms;
+    std::string key = two ? "2" : "1";
+    std::vector<int> cs, cp;
+    for (int s2 = 0; s2 < nent; ++s2) {
+      const AttnHead& h = sp.h[s2];
+      key += "|" + std::to_string(h.ntt) + "," + std::to_string(h.npos) + "," + std::to_string(h.splits) + "," + std::to_string(h.nk64);
+      const int nq = two ? (h.ntt + 1) / 2 : h.ntt, nk2 = (h.ntt + 1) / 2;
+      for (int q = 0; q < nq; ++q)
+        for (int kj = 0; kj < nk2; ++kj)
+          for (int spl = 0; spl < h.splits; ++spl) cs.push_back(std::min(h.chunks_per_split, h.npos - spl * h.chunks_per_split) + 8);
+      for (int m = 0; m < nq; ++m)
+        for (int ni = 0; ni < h.pv_ntiles; ++ni) cp.push_back(h.nk64 + 3);
+    }
+    const TileSchedule& ss = lpt_schedule(ws, "S" + key, cs, std::min(bins, (int)cs.size()), c.stream);
+    const TileSchedule& ps = lpt_schedule(ws, "P" + key, cp, std::min(bins, (int)cp.size()), c.stream);
+    sp.order = ss.dev.as<int>();
+    sp.order_stride = ss.stride;
+    pp.order = ps.dev.as<int>();
+    pp.order_stride = ps.stride;
+  }
   sp.totalB = workB;
   sp.totalB2 = workB2;
   sp.pass = 0;  // pass A: per-tile row maxima (fused problems) / fp32 S slabs (split-K problems)
@@ -1132,6 +1194,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", false);
+    h->ctx.attn_lpt = env_flag("VSR_ATTN_LPT", true);
     if (getenv("VSR_WINDOW_GROUP")) h->window_group = (size_t)std::min(2, std::max(1, atoi(getenv("VSR_WINDOW_GROUP"))));
     *out = h;
   });
@@ -1396,6 +1459,7 @@ struct OpCtx {
     c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     c.attn_fused = env_flag("VSR_ATTN_FUSED", false);
+    c.attn_lpt = env_flag("VSR_ATTN_LPT", true);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   }
   ~OpCtx() {

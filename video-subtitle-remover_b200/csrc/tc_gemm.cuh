@@ -22,6 +22,16 @@ constexpr int tc_smem_bytes() {
   return P::STAGES * (TC_A_BYTES + P::BN * 128) + 1024;
 }
 
+// i-th tile of CTA (or CTA pair) `who` out of `n_who`: round robin, or a host-computed LPT list
+// order[who*stride + i] (-1 terminated) when the tiles have very different costs.
+__device__ __forceinline__ int tc_tile_round_robin(int who, int n_who, int i, int ntiles) {
+  const int t = who + i * n_who;
+  return t < ntiles ? t : -1;
+}
+__device__ __forceinline__ int tc_tile_listed(const int* order, int stride, int who, int i) {
+  return i < stride ? order[(size_t)who * stride + i] : -1;
+}
+
 enum : uint32_t { ERR_PRODUCER = 0x100, ERR_MMA_FULL = 0x200, ERR_MMA_TEMPTY = 0x300, ERR_EPI = 0x400 };
 
 template <class P>
@@ -67,7 +77,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       TC_PROF_DECL(w_empty);
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int it = 0;; ++it) {
+        const int t = P::tile_at(prm, (int)blockIdx.x, (int)gridDim.x, it, ntiles);
+        if (t < 0) break;
         const typename P::Tile tile = P::get_tile(prm, t);
         typename P::LoadCtx lc = P::load_begin(prm, tile);  // per-tile invariants: the k loop must stay division-free
         for (int k = 0; k < tile.num_k; ++k) {
@@ -85,7 +97,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       TC_PROF_DECL(w_full);
       TC_PROF_DECL(w_tempty);
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      for (int it = 0;; ++it) {
+        const int t = P::tile_at(prm, (int)blockIdx.x, (int)gridDim.x, it, ntiles);
+        if (t < 0) break;
         const typename P::Tile tile = P::get_tile(prm, t);
         TC_PROF_WAIT(w_tempty, smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
         tc_fence_after();
@@ -119,7 +133,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     uint32_t as = 0, aphase = 0;
     TC_PROF_DECL(w_tfull);
     TC_PROF_DECL(busy);
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int it = 0;; ++it) {
+      const int t = P::tile_at(prm, (int)blockIdx.x, (int)gridDim.x, it, ntiles);
+      if (t < 0) break;
       const typename P::Tile tile = P::get_tile(prm, t);
       TC_PROF_WAIT(w_tfull, smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
       tc_fence_after();

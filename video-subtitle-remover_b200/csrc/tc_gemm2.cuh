@@ -63,7 +63,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       TC_PROF_DECL(w_empty);
-      for (int t = first; t < ntiles; t += step) {
+      for (int it = 0;; ++it) {
+        const int t = P::tile_at(prm, first, step, it, ntiles);
+        if (t < 0) break;
         const typename P::Tile tile = P::get_tile(prm, t, rank);
         typename P::LoadCtx lc = P::load_begin(prm, tile, rank);
         for (int k = 0; k < tile.num_k; ++k) {
@@ -83,7 +85,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       TC_PROF_DECL(w_full);
       TC_PROF_DECL(w_tempty);
       const uint32_t idesc = umma_idesc_f16(256, BN, 0, P::B_MN_MAJOR);
-      for (int t = first; t < ntiles; t += step) {
+      for (int it = 0;; ++it) {
+        const int t = P::tile_at(prm, first, step, it, ntiles);
+        if (t < 0) break;
         const typename P::Tile tile = P::get_tile(prm, t, 0);
         TC_PROF_WAIT(w_tempty, smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
         tc_fence_after();
@@ -115,7 +119,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     uint32_t as = 0, aphase = 0;
     TC_PROF_DECL(w_tfull);
     TC_PROF_DECL(busy);
-    for (int t = first; t < ntiles; t += step) {
+    for (int it = 0;; ++it) {
+      const int t = P::tile_at(prm, first, step, it, ntiles);
+      if (t < 0) break;
       const typename P::Tile tile = P::get_tile(prm, t, rank);
       TC_PROF_WAIT(w_tfull, smem_u32(&bar_tfull[as]), aphase, ERR_EPI | as);
       tc_fence_after();
