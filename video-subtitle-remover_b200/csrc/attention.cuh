@@ -116,6 +116,7 @@ struct ScorePolicy {
     t.split = sp;
     return t;
   }
+  __device__ static void prefetch_tile(const Params&, const Tile&) {}
   struct LoadCtx {
     int px, py, pw;          // patch pixel of the next k-chunk (advanced without divisions)
     int qrow, krow0, krow1;  // 5th TMA coordinate of the query tile and of the key tile(s)
@@ -347,6 +348,7 @@ struct PVPolicy {
     t.n_cols = t.nvalid * 64;
     return t;
   }
+  __device__ static void prefetch_tile(const Params&, const Tile&) {}
   struct LoadCtx {
     int px[4], py[4];  // patch pixel of each value position of this tile (fixed over k)
     int prow, rows;    // P row coordinate, value token rows per 64-token chunk
@@ -454,6 +456,7 @@ struct Score2Policy {
     t.split = sp;
     return t;
   }
+  __device__ static void prefetch_tile(const Params&, const Tile&) {}
   using LoadCtx = ScorePolicy::LoadCtx;
   __device__ static LoadCtx load_begin(const Params& p, const Tile& t, uint32_t rank) {
     LoadCtx lc = ScorePolicy::load_begin(p, t);
@@ -502,6 +505,7 @@ struct PV2Policy {
     t.n_cols = t.nvalid * 64;
     return t;
   }
+  __device__ static void prefetch_tile(const Params&, const Tile&) {}
   using LoadCtx = PVPolicy::LoadCtx;
   __device__ static LoadCtx load_begin(const Params& p, const Tile& t, uint32_t rank) {
     LoadCtx lc = PVPolicy::load_begin(p, t);

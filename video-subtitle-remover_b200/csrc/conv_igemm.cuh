@@ -28,6 +28,7 @@ struct ConvParams {
   int ntaps, cin_chunks;
   int cout;            // real output channels
   int flags;
+  int prefetch;        // 1: L2-prefetch the next tile's activations (VSR_CONV_PREFETCH)
   int8_t tap_dy[9], tap_dx[9];
   const float* bias;   // [Cout_pad]
   __half* out16;       // NHWC fp16, pixel pitch out16_pitch (elements), channel offset out16_coff
@@ -81,6 +82,11 @@ struct ConvPolicy {
     t.num_k = p.ntaps * p.cin_chunks;
     t.n_cols = BN;
     return t;
+  }
+  // first-touch activations of a tile: the un-shifted box of every 64-channel chunk (the taps re-read it from L2)
+  __device__ static void prefetch_tile(const Params& p, const Tile& t) {
+    if (!p.prefetch || t.t >= p.T) return;
+    for (int kc = 0; kc < p.cin_chunks; ++kc) tma_prefetch_4d(&p.in_map, kc * 64, t.x0, t.y0, t.t);
   }
   struct LoadCtx {
     int tap, kc;        // running (tap, channel chunk) of the next k-chunk
@@ -209,6 +215,7 @@ struct Conv2Policy {
     t.t = sub / p.tiles_y;
     return t;
   }
+  __device__ static void prefetch_tile(const Params& p, const Tile& t) { Base::prefetch_tile(p, t); }
   using LoadCtx = Base::LoadCtx;
   __device__ static LoadCtx load_begin(const Params& p, const Tile&, uint32_t) {
     // the leader registers the bytes of both CTAs; the peer's loads may land first (tx-count is signed)

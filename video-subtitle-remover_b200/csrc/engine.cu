@@ -146,6 +146,7 @@ struct Ctx {
   int64_t launches = 0;
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
+  bool conv_prefetch = true;  // VSR_CONV_PREFETCH=0: no next-tile L2 prefetch in the conv producers
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
   bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
 };
@@ -309,6 +310,7 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   p.cin_chunks = L.cin / 64;
   p.cout = L.cout;
   p.flags = io.flags;
+  p.prefetch = c.conv_prefetch ? 1 : 0;
   memcpy(p.tap_dy, L.dy, 9);
   memcpy(p.tap_dx, L.dx, 9);
   p.bias = L.b.as<float>();
@@ -1195,6 +1197,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     h->ctx.attn_lpt = env_flag("VSR_ATTN_LPT", true);
+    h->ctx.conv_prefetch = env_flag("VSR_CONV_PREFETCH", true);
     if (getenv("VSR_WINDOW_GROUP")) h->window_group = (size_t)std::min(2, std::max(1, atoi(getenv("VSR_WINDOW_GROUP"))));
     *out = h;
   });
@@ -1460,6 +1463,7 @@ struct OpCtx {
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     c.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     c.attn_lpt = env_flag("VSR_ATTN_LPT", true);
+    c.conv_prefetch = env_flag("VSR_CONV_PREFETCH", true);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   }
   ~OpCtx() {

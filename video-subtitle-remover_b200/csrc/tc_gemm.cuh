@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (t < 0) break;
         const typename P::Tile tile = P::get_tile(prm, t);
         typename P::LoadCtx lc = P::load_begin(prm, tile);  // per-tile invariants: the k loop must stay division-free
+        {
+          const int tn = P::tile_at(prm, (int)blockIdx.x, (int)gridDim.x, it + 1, ntiles);
+          if (tn >= 0) P::prefetch_tile(prm, P::get_tile(prm, tn));  // pull the next tile's activations into L2
+        }
         for (int k = 0; k < tile.num_k; ++k) {
           TC_PROF_WAIT(w_empty, smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;

@@ -68,6 +68,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         if (t < 0) break;
         const typename P::Tile tile = P::get_tile(prm, t, rank);
         typename P::LoadCtx lc = P::load_begin(prm, tile, rank);
+        {
+          const int tn = P::tile_at(prm, first, step, it + 1, ntiles);
+          if (tn >= 0) P::prefetch_tile(prm, P::get_tile(prm, tn, rank));  // pull the next tile's activations into L2
+        }
         for (int k = 0; k < tile.num_k; ++k) {
           TC_PROF_WAIT(w_empty, smem_u32(&bar_empty[stage]), phase ^ 1, ERR_PRODUCER | stage);
           const uint32_t sA = smem_base + stage * STAGE_BYTES;
