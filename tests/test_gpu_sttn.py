@@ -160,3 +160,69 @@ def test_full_size_properties_1080p(real_engine):
     a = eng(frames[:10], mask)
     b = eng([f.copy() for f in frames[:10]], mask)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+class _FakeWriter:
+    def __init__(self):
+        self.frames = []
+        self.released = False
+
+    def write(self, frame):
+        assert frame.dtype == np.uint8
+        self.frames.append(frame.copy())
+
+    def release(self):
+        self.released = True
+
+
+class _FakeRemover:
+    """The slice of SubtitleRemover that STTNAutoInpaint.__call__ touches (sttn_auto_inpaint.py:207-323)."""
+
+    def __init__(self, ab_sections=None):
+        self.ab_sections = ab_sections
+        self.video_writer = _FakeWriter()
+        self.gui_mode = False
+        self.progress = 0
+
+    def update_progress(self, tbar, increment):
+        self.progress += increment
+
+
+def test_whole_video_driver(rand_engine, tmp_path):
+    """A3: STTNAutoInpaint(device, model, video)(input_mask, input_sub_remover) — chunks of clip_gap frames,
+    pipelined, every frame written in order; A/B sections pass frames through untouched."""
+    cv2 = pytest.importorskip("cv2")
+    from vsr_b200 import STTNAutoInpaint
+
+    _, w = rand_engine
+    H, W, N = 270, 480, 64
+    path = str(tmp_path / "clip.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25, (W, H))
+    if not vw.isOpened():
+        pytest.skip("cv2.VideoWriter cannot write mp4v here")
+    for f in O.synthetic_clip(N, H, W, seed=77):
+        vw.write(f)
+    vw.release()
+    cap = cv2.VideoCapture(path)
+    decoded = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        decoded.append(f)
+    cap.release()
+    assert len(decoded) == N
+    mask = O.default_mask(H, W)
+    drv = STTNAutoInpaint("cuda:0", {k: v.numpy() for k, v in w.items()}, path, clip_gap=25)
+    rem = _FakeRemover()
+    drv(input_mask=mask, input_sub_remover=rem, tbar=object())
+    assert rem.video_writer.released and rem.progress == N and len(rem.video_writer.frames) == N
+    _check_images(rem.video_writer.frames, O.sttn_video(w, decoded, mask, clip_gap=25))
+    # A/B sections: only frames 10..29 are processed, the rest is written through unchanged
+    rem2 = _FakeRemover(ab_sections=[range(10, 30)])
+    drv(input_mask=mask, input_sub_remover=rem2, tbar=None)
+    out = rem2.video_writer.frames
+    assert len(out) == N
+    for i in list(range(0, 10)) + list(range(30, N)):
+        assert np.array_equal(out[i], decoded[i])
+    assert any(not np.array_equal(out[i], decoded[i]) for i in range(10, 30))

@@ -146,7 +146,7 @@ struct Ctx {
   int64_t launches = 0;
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
-  bool conv_prefetch = true;  // VSR_CONV_PREFETCH=0: no next-tile L2 prefetch in the conv producers
+  bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
   bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
 };
@@ -1197,7 +1197,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     h->ctx.attn_lpt = env_flag("VSR_ATTN_LPT", true);
-    h->ctx.conv_prefetch = env_flag("VSR_CONV_PREFETCH", true);
+    h->ctx.conv_prefetch = env_flag("VSR_CONV_PREFETCH", false);
     if (getenv("VSR_WINDOW_GROUP")) h->window_group = (size_t)std::min(2, std::max(1, atoi(getenv("VSR_WINDOW_GROUP"))));
     *out = h;
   });
@@ -1463,7 +1463,7 @@ struct OpCtx {
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     c.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     c.attn_lpt = env_flag("VSR_ATTN_LPT", true);
-    c.conv_prefetch = env_flag("VSR_CONV_PREFETCH", true);
+    c.conv_prefetch = env_flag("VSR_CONV_PREFETCH", false);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   }
   ~OpCtx() {
