@@ -192,6 +192,77 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_det(args, rank, world, local):
+    """Secondary line: STTNDetInpaint on 46-frame 1080p batches (what `video_inpaint` feeds it for a 300-frame
+    interval, batch_generator 46x6+24 — SURVEY §8a D-rows), device-resident and through the host call."""
+    import torch
+    import torch.distributed as dist
+    from oracle import sttn_oracle as O
+    from vsr_b200 import STTNDetInpaint
+
+    p = os.path.join(ROOT, "weights", "sttn-det", "sttn.pth")
+    if os.path.exists(p):
+        eng, wdesc = STTNDetInpaint(torch.device("cuda", local), p), "reference checkpoint sttn-det/sttn.pth"
+    else:
+        eng = STTNDetInpaint(torch.device("cuda", local), {k: v.numpy() for k, v in O.random_weights(1).items()})
+        wdesc = "seeded random-init weights of the sttn-det architecture"
+    T = 46
+    frames = O.synthetic_clip(T, H, W, seed=100 + rank)
+    mask = O.default_mask(H, W)
+    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local))
+    work = [f.copy() for f in frames]
+    for _ in range(max(args.warmup, 3)):
+        eng.stage(work, mask)
+        eng.compute()
+    eng.sync()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launch_count
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for a, b in evs:
+        eng.stage(work, mask)
+        eng.sync()
+        a.record(stream)
+        eng.compute()
+        b.record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = eng.launch_count - l0
+    batches = [[f.copy() for f in frames] for _ in range(args.steps)]
+    eng.inpaint_inplace([f.copy() for f in frames], mask)
+    t0 = time.perf_counter()
+    for b in batches:
+        eng.inpaint_inplace(b, mask)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    Tw = 29
+    conv_ms = float(np.median(eng.time_conv(Tw, 20)))
+    conv_flop = 2.0 * Tw * 60 * 108 * 2304 * 256
+    burst, sustained, _, src = peaks()
+    if rank == 0:
+        n = world * args.steps * T
+        sh = int(W * 5 / 18)
+        print(json.dumps({
+            "metric": "inpainted frames/sec at 1080p (STTN-det, window=5)", "value": n / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": f"synthetic 1080p clip; {wdesc}",
+            "config": {"workload": "STTN sttn-det inpaint on 46-frame 1080p batches (inpaint half of BASELINE config 4; detection not included)",
+                       "frame": [H, W], "batch": T, "strip_h": sh},
+            "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": T * sh * W * 3, "d2h_bytes_per_step": T * sh * W * 3,
+                    "api": "STTNDetInpaint.inpaint_inplace(frames, mask), synchronous"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": f"tcgen05 implicit-GEMM 3x3 conv 256->256, {Tw}x60x108 px", "achieved": conv_flop / conv_ms / 1e9,
+                         "peak": burst, "unit": "TFLOP/s", "frac": conv_flop / conv_ms / 1e9 / burst, "traffic": None, "peak_source": f"{src} (burst bf16)",
+                         "whole_step_frac_of_sustained": 758.2e9 * n / world / (dev_ms * 1e-3) / 1e12 / sustained}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,6 +270,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det"],
+                    help="sttn-auto = BASELINE config 2 (the contract line); sttn-det = the inpaint half of config 4 (46-frame batches)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -224,6 +297,8 @@ def main():
             dist.barrier()
 
     _capi.build_library()
+    if args.workload == "sttn-det":
+        return run_det(args, rank, world, local)
     w, wdesc = load_weights()
     eng = STTNInpaint(torch.device("cuda", local), {k: v.numpy() for k, v in w.items()})
     frames = O.synthetic_clip(CHUNK, H, W, seed=rank)  # each rank its own chunk (weak scaling)

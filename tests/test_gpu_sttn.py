@@ -226,3 +226,29 @@ def test_whole_video_driver(rand_engine, tmp_path):
     for i in list(range(0, 10)) + list(range(30, N)):
         assert np.array_equal(out[i], decoded[i])
     assert any(not np.array_equal(out[i], decoded[i]) for i in range(10, 30))
+
+
+def test_non_default_schedule_and_long_chunk(capi):
+    """config.sttnNeighborStride / sttnReferenceLength are read at construction (sttn_auto_inpaint.py:40-41);
+    a 61-frame batch makes 17-frame windows (7 reference frames): 5440-token rows, second softmax variant."""
+    from vsr_b200 import STTNInpaint, config
+
+    w = O.random_weights(0)
+    wd = {k: v.numpy() for k, v in w.items()}
+    old = (config.sttnNeighborStride.value, config.sttnReferenceLength.value)
+    try:
+        config.sttnNeighborStride.value, config.sttnReferenceLength.value = 3, 7
+        eng = STTNInpaint("cuda:0", wd)
+        assert (eng.neighbor_stride, eng.ref_length) == (3, 7)
+        strip = _strip(61, 23)
+        got = eng.inpaint([s.copy() for s in strip])
+        want = O.inpaint_strip(w, strip, stride=3, ref_length=7)
+        assert [g.dtype for g in got] == [x.dtype for x in want]
+        _check_images(got, want)
+    finally:
+        config.sttnNeighborStride.value, config.sttnReferenceLength.value = old
+    eng = STTNInpaint("cuda:0", wd)
+    H, W, T = 180, 320, 61
+    frames = O.synthetic_clip(T, H, W, seed=62)
+    mask = O.default_mask(H, W)
+    _check_images(eng(frames, mask), O.sttn_call(w, frames, mask))

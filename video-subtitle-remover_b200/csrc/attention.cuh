@@ -65,6 +65,7 @@ struct ScoreParams {
   // nullptr = round robin
   const int* order;
   int order_stride;
+  int softmax_row_begin[ATTN_MAX_HEADS + 1];  // first softmax block of each problem (fused problems: empty range)
 };
 
 struct ScorePolicy {
@@ -229,8 +230,11 @@ struct ScorePolicy {
 // stores.  Pad *columns* get P = 0.  NV4 = float4 per thread (row length <= 1024*NV4).
 template <int NV4>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
-  const AttnHead& h = p.h[blockIdx.y];
-  const int qp = blockIdx.x;
+  // blockIdx.x enumerates the rows of all un-fused problems back to back (softmax_row_begin prefix sums)
+  int e = 0;
+  while (e + 1 < p.nheads && (int)blockIdx.x >= p.softmax_row_begin[e + 1]) ++e;
+  const AttnHead& h = p.h[e];
+  const int qp = (int)blockIdx.x - p.softmax_row_begin[e];
   if (h.fused || qp >= h.ntt * 128) return;
   const int toh = qp / h.owp, owi = qp - toh * h.owp;
   if (owi >= h.ow || toh >= h.toh_total) return;

@@ -543,13 +543,16 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   if (c.attn_2cta) launch_tc2<Score2Policy>(c, sp, score_work2);
   else launch_tc<ScorePolicy>(c, sp, score_work);
   if (any_unfused) {
-    int max_cols = 0, rows_unfused = 0;
-    for (int s2 = 0; s2 < nent; ++s2)
+    int max_cols = 0, rows_total = 0;
+    for (int s2 = 0; s2 < nent; ++s2) {
+      sp.softmax_row_begin[s2] = rows_total;
       if (!sp.h[s2].fused) {
         max_cols = std::max(max_cols, sp.h[s2].nk64 * 64);
-        rows_unfused = std::max(rows_unfused, sp.h[s2].ntt * 128);
+        rows_total += sp.h[s2].ntt * 128;
       }
-    const dim3 grid(rows_unfused, nent);
+    }
+    for (int s2 = nent; s2 <= ATTN_MAX_HEADS; ++s2) sp.softmax_row_begin[s2] = rows_total;
+    const dim3 grid(rows_total);
     if (max_cols <= 1024) softmax_rows_kernel<1><<<grid, 256, 0, c.stream>>>(sp);
     else if (max_cols <= 2048) softmax_rows_kernel<2><<<grid, 256, 0, c.stream>>>(sp);
     else if (max_cols <= 5120) softmax_rows_kernel<5><<<grid, 256, 0, c.stream>>>(sp);
