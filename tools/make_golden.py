@@ -114,6 +114,50 @@ def main():
     np.savez_compressed(os.path.join(OUT, "sttn_det_real.npz"), seed=9, H=H, W=W, T=T, areas=np.array(areas), comps=c, once=once,
                         mask_small=msmall, strip_out_plain=np.stack([o[y0:y1] for o in out_plain]))
 
+    # ---- T1/T3/T4 planning functions of SubtitleDetect + expand_frame_ranges
+    from backend.tools.ocr import get_coordinates as ref_get_coordinates
+    from backend.tools.subtitle_detect import SubtitleDetect
+    import json as _json
+
+    prng = np.random.default_rng(8)
+    sd = SubtitleDetect.__new__(SubtitleDetect)
+    plan = []
+    for _ in range(60):
+        step = int(prng.choice([2, 3, 4]))
+        n = int(prng.integers(20, 200))
+        sampled = {}
+        for f in range(1, n + 1, step):
+            if prng.random() < 0.6:
+                base = (int(prng.integers(100, 140)), int(prng.integers(500, 560)), int(prng.integers(400, 420)), int(prng.integers(440, 470)))
+                boxes = [base]
+                if prng.random() < 0.3:
+                    boxes.append((base[0] + 5, base[1] - 5, base[2] - 60, base[3] - 60))
+                sampled[f] = boxes
+        if not sampled:
+            continue
+        # phase 2 of find_subtitle_frame_no (subtitle_detect.py:112-132), verbatim calls into the reference helpers
+        d, nos = {}, sorted(sampled)
+        for a, b in zip(nos, nos[1:]):
+            d[a] = sampled[a]
+            if b - a <= step * 2:
+                for ff in range(a + 1, b):
+                    d[ff] = sampled[a]
+        d[nos[-1]] = sampled[nos[-1]]
+        uni = sd.unify_regions(dict(d))
+        uni = {k: v for k, v in uni.items() if len(v) > 0}
+        ranges = SubtitleDetect.find_continuous_ranges_with_same_mask(uni)
+        ranges0 = SubtitleDetect.find_continuous_ranges(uni)
+        expanded = RT.expand_frame_ranges(ranges, 3, 3)
+        merged = SubtitleDetect.filter_and_merge_intervals(expanded, 10)
+        pts = sorted(int(x) for x in prng.integers(1, n, size=int(prng.integers(0, 5))))
+        split = SubtitleDetect.split_range_by_scene(list(merged), list(pts))
+        plan.append(dict(step=step, sampled={str(k): v for k, v in sampled.items()}, filled={str(k): v for k, v in d.items()},
+                         unified={str(k): v for k, v in uni.items()}, ranges=ranges, ranges0=ranges0, expanded=expanded, merged=merged,
+                         points=pts, split=split))
+    quads = prng.integers(0, 1000, size=(30, 4, 2)).tolist()
+    np.savez_compressed(os.path.join(OUT, "subtitle_plan.npz"), plan=_json.dumps(plan), quads=_json.dumps(quads),
+                        coords=_json.dumps(ref_get_coordinates(quads)))
+
     # ---- integer path vectors
     rng = np.random.default_rng(5)
     cases = []

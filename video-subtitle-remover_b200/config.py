@@ -19,12 +19,18 @@ class _Config:
         self.sttnMaxLoadNum = _v(50)             # :93
         self.subtitleAreaDeviationPixel = _v(10)  # :61
         self.subtitleSelectionAreas = _v("0.88,0.99,0.15,0.85")  # :43
+        self.subtitleAreaPixelToleranceYPixel = _v(20)  # :65
+        self.subtitleAreaPixelToleranceXPixel = _v(20)  # :66
+        self.subtitleTimelineBackwardFrameCount = _v(3)  # :67
+        self.subtitleTimelineForwardFrameCount = _v(3)   # :68
 
     def getSttnMaxLoadNum(self):                 # :94
         return max(self.sttnMaxLoadNum.value, self.sttnNeighborStride.value * self.sttnReferenceLength.value)
 
     def adopt(self, other):
-        for k in ("sttnNeighborStride", "sttnReferenceLength", "sttnMaxLoadNum", "subtitleAreaDeviationPixel"):
+        for k in ("sttnNeighborStride", "sttnReferenceLength", "sttnMaxLoadNum", "subtitleAreaDeviationPixel",
+                  "subtitleAreaPixelToleranceYPixel", "subtitleAreaPixelToleranceXPixel", "subtitleTimelineBackwardFrameCount",
+                  "subtitleTimelineForwardFrameCount"):
             if hasattr(other, k):
                 getattr(self, k).value = getattr(other, k).value
 
