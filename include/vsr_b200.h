@@ -118,6 +118,34 @@ int vsr_batch_sizes(int n_samples, int max_batch_size, int32_t* sizes, int max_s
 int vsr_window_schedule(int T, int stride, int ref_length, int32_t* ids, int32_t* n_neighbors, int32_t* n_refs, int max_windows,
                         int max_ids_per_window);
 
+/* ---- device-tensor graph runtime: the DBNet text detector ----------------------------------
+ * The reference runs `paddleocr.TextDetection.predict` (backend/tools/subtitle_detect.py:43-58) on the CPU;
+ * vsr_b200/dbnet.py compiles the same Paddle PIR program (backend/models/V5/ch_det/inference.json) into calls on
+ * these entry points.  Tensors are NHWC fp16 device buffers addressed by raw device pointers (uint64). */
+typedef struct vsr_rt vsr_rt_t;
+int vsr_rt_create(vsr_rt_t** out, int device);
+void vsr_rt_destroy(vsr_rt_t* h);
+int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr);             /* zero-initialised, freed with the runtime */
+int vsr_rt_upload(vsr_rt_t* h, uint64_t dev_ptr, const void* host, int64_t bytes);
+int vsr_rt_download(vsr_rt_t* h, uint64_t dev_ptr, void* host, int64_t bytes);
+int vsr_rt_sync(vsr_rt_t* h);
+int64_t vsr_rt_launch_count(vsr_rt_t* h);
+/* conv2d / depthwise_conv2d / conv2d_transpose of the PIR program with batch-norm and bias already folded into
+ * (w, bias): w fp32 in the framework layout ([Cout,Cin/groups,kh,kw]; transposed: [Cin,Cout,2,2]); cin_pitch =
+ * channel pitch of the input tensor.  Dense convs with >= 16 input and >= 8 output channels run on the tcgen05
+ * implicit-GEMM kernel (stride 2 through space-to-depth), the rest on small direct kernels. */
+int vsr_rt_conv_create(vsr_rt_t* h, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw, int stride,
+                       int pad_t, int pad_l, int dil, int groups, int transposed, int* layer_id);
+int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu);
+/* op: 0 add, 1 relu, 2 add+relu, 3 sigmoid, 4 per-channel affine, 5 affine+relu, 6 a*alpha+beta, 7 (a+b)*alpha */
+int vsr_rt_elementwise(vsr_rt_t* h, int op, uint64_t a, uint64_t b, uint64_t out, int64_t n_elems, int cp, uint64_t scale_dev,
+                       uint64_t shift_dev, float alpha, float beta);   /* scale/shift: device fp32 [cp] (op 4, 5) */
+int vsr_rt_upsample_nearest(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, int scale, uint64_t out, int out_pitch, int out_coff);
+int vsr_rt_maxpool2x2s1(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out);
+int vsr_rt_copy_channels(vsr_rt_t* h, uint64_t src, int src_pitch, uint64_t dst, int dst_pitch, int dst_coff, int channels, int64_t pixels);
+/* DetResizeForTest + NormalizeImage (inference.yml:22-40): BGR u8 host image -> NHWC fp16 [dh,dw,cp] on the device */
+int vsr_rt_det_preprocess(vsr_rt_t* h, const uint8_t* bgr, int sh, int sw, uint64_t out, int dh, int dw, int cp);
+
 /* ---- operator-level entry points (parity tests call the kernels in isolation) ------------------ */
 /* cv2.resize(src_u8 HxWx3, (dw,dh)) INTER_LINEAR on the device (sttn_auto_inpaint.py:72,270). */
 int vsr_op_resize_u8(int device, const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);

@@ -1,0 +1,52 @@
+"""CPU: the host-side pieces of the detector (model-file parsing, resize rule, DB post-process) against the oracle;
+the oracle's forward pass on the reference's real program produces a sane text map (pins the interpreter to the
+model files — SURVEY §8c: there is no paddleocr here to compare with)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import dbnet_oracle as D
+
+MODEL_DIR = os.path.join(ROOT, "weights", "V5", "ch_det")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(MODEL_DIR, "inference.pdiparams")),
+                                reason="detector model not staged under weights/V5/ch_det")
+
+
+def test_model_files_parse_identically():
+    from vsr_b200 import dbnet
+
+    nodes, params = dbnet._load_program(MODEL_DIR)
+    g = D.Graph(MODEL_DIR)
+    assert len(nodes) == len(g.ops) == 1052 and len(params) == len(g.params) == 539
+    for k, v in g.params.items():
+        assert np.array_equal(params[k], v)
+    kinds = {}
+    for n in nodes:
+        kinds[n.kind] = kinds.get(n.kind, 0) + 1
+    assert kinds["conv2d"] == 115 and kinds["depthwise_conv2d"] == 27 and kinds["batch_norm_"] == 87
+
+
+def test_resize_rule():
+    from vsr_b200.dbnet import TextDetector
+
+    for hw, want in (((1080, 1920), (544, 960)), ((720, 1280), (544, 960)), ((2160, 3840), (544, 960)), ((480, 852), (480, 864)),
+                     ((1280, 720), (960, 544)), ((20, 20), (32, 32))):
+        assert TextDetector.resize_shape(*hw) == want == D.resize_shape(*hw)
+
+
+@pytest.mark.slow
+def test_oracle_forward_and_postprocess():
+    cv2 = pytest.importorskip("cv2")
+    from vsr_b200.dbnet import db_postprocess
+
+    img = np.full((360, 640, 3), 90, np.uint8)
+    cv2.putText(img, "HELLO WORLD 42", (120, 320), cv2.FONT_HERSHEY_SIMPLEX, 1.2, (255, 255, 255), 3, cv2.LINE_AA)
+    prob = D.forward(D.Graph(MODEL_DIR), D.preprocess(img))[0, 0].numpy()
+    assert prob.shape == (352, 640) and 0.0 <= prob.min() and prob.max() <= 1.0
+    want = D.postprocess(prob, 360, 640)
+    got = db_postprocess(prob, 360, 640)
+    assert np.array_equal(got, want) and len(want) == 1
+    (xmin, xmax, ymin, ymax), = D.get_coordinates(want.tolist())
+    assert 90 <= xmin <= 125 and 400 <= xmax <= 460 and 270 <= ymin <= 300 and 320 <= ymax <= 345

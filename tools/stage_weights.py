@@ -8,7 +8,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("VSR_REFERENCE_ROOT", "/root/reference")
 FILES = {"sttn-auto/infer_model.pth": "backend/models/sttn-auto/infer_model.pth",
-         "sttn-det/sttn.pth": "backend/models/sttn-det/sttn.pth"}
+         "sttn-det/sttn.pth": "backend/models/sttn-det/sttn.pth",
+         "V5/ch_det/inference.json": "backend/models/V5/ch_det/inference.json",
+         "V5/ch_det/inference.pdiparams": "backend/models/V5/ch_det/inference.pdiparams",
+         "V5/ch_det/inference.yml": "backend/models/V5/ch_det/inference.yml"}
 
 
 def main(quiet=False):

@@ -77,6 +77,22 @@ _PROTOS = {
     "vsr_inpaint_area_by_mask": (C.c_int, [C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _i32p, C.c_int]),
     "vsr_batch_sizes": (C.c_int, [C.c_int, C.c_int, _i32p, C.c_int]),
     "vsr_window_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, C.c_int, C.c_int]),
+    "vsr_rt_create": (C.c_int, [_pp, C.c_int]),
+    "vsr_rt_destroy": (None, [C.c_void_p]),
+    "vsr_rt_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
+    "vsr_rt_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]),
+    "vsr_rt_download": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]),
+    "vsr_rt_sync": (C.c_int, [C.c_void_p]),
+    "vsr_rt_launch_count": (C.c_int64, [C.c_void_p]),
+    "vsr_rt_conv_create": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, _i32p]),
+    "vsr_rt_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]),
+    "vsr_rt_elementwise": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_uint64, C.c_uint64,
+                                     C.c_float, C.c_float]),
+    "vsr_rt_upsample_nearest": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int]),
+    "vsr_rt_maxpool2x2s1": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_copy_channels": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int64]),
+    "vsr_rt_det_preprocess": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]),
     "vsr_op_resize_u8": (C.c_int, [C.c_int, _u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]),
     "vsr_op_conv2d": (C.c_int, [C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
                                 C.c_int, _f32p, _f32p]),

@@ -15,6 +15,7 @@ enum ConvFlags : int {
   CONV_LRELU = 1,      // LeakyReLU(0.2) after bias
   CONV_RESIDUAL = 2,   // act += res32 (fp32) before the stores; out32 (if set) gets the fp32 value, out16 its fp16 rounding
   CONV_S2D_STORE = 4,  // store out16 space-to-depth: [T, H/2, W/2, 4*Cout], channel = (y&1)*2*Cout + (x&1)*Cout + c
+  CONV_RELU = 0x100,   // plain ReLU after bias (graph runtime)
   CONV_FINAL = 8,      // decoder.6: tanh -> (x+1)/2*255 -> trunc u8 -> first visit store / 0.5-0.5 blend into comps
 };
 
@@ -29,7 +30,7 @@ struct ConvParams {
   int cout;            // real output channels
   int flags;
   int prefetch;        // 1: L2-prefetch the next tile's activations (VSR_CONV_PREFETCH)
-  int8_t tap_dy[9], tap_dx[9];
+  int8_t tap_dy[81], tap_dx[81];  // up to 9x9 kernels
   const float* bias;   // [Cout_pad]
   __half* out16;       // NHWC fp16, pixel pitch out16_pitch (elements), channel offset out16_coff
   int out16_pitch, out16_coff;
@@ -125,6 +126,10 @@ struct ConvPolicy {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
     }
+    if (p.flags & CONV_RELU) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
     if (p.flags & CONV_FINAL) {
       if (col0 != 0) return;
       const int f = p.frame_idx[c.t];
@@ -171,6 +176,7 @@ struct ConvPolicy {
       }
 #pragma unroll
       for (int i = 0; i < NV; i += 8) {
+        if (ch0 + i >= p.cout) break;  // Cout padded up to the tile width: only the real channels are stored
         __align__(16) __half2 h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);

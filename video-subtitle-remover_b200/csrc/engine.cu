@@ -20,6 +20,7 @@
 #include "conv_igemm.cuh"
 #include "elementwise.cuh"
 #include "host_index.h"
+#include "rt_ops.cuh"
 
 namespace vsr {
 
@@ -191,7 +192,7 @@ static void launch_tc2(Ctx& c, const typename P::Params& prm, int ntiles) {
 struct ConvLayer {
   DevBuf w, b;
   int cin = 0, cout = 0, cout_pad = 0, ntaps = 0, K = 0, bn = 0;
-  int8_t dy[9] = {0}, dx[9] = {0};
+  int8_t dy[81] = {0}, dx[81] = {0};
 };
 
 static int pad_cout(int cout) {
@@ -242,6 +243,60 @@ static void pack_conv_s2d(ConvLayer& L, const float* w, const float* bias, int c
             const int tap = (dyb + 1) * 2 + (dxb + 1);
             for (int ci = 0; ci < cin; ++ci)
               hw[(size_t)co * L.K + (size_t)tap * 4 * cin + (py * 2 + px) * cin + ci] =
+                  __float2half_rn(w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx]);
+          }
+  for (int dyb = -1; dyb <= 0; ++dyb)
+    for (int dxb = -1; dxb <= 0; ++dxb) {
+      L.dy[(dyb + 1) * 2 + (dxb + 1)] = (int8_t)dyb;
+      L.dx[(dyb + 1) * 2 + (dxb + 1)] = (int8_t)dxb;
+    }
+  std::vector<float> hb(L.cout_pad, 0.f);
+  for (int i = 0; i < cout; ++i) hb[i] = bias ? bias[i] : 0.f;
+  upload(L.w, hw, s);
+  upload(L.b, hb, s);
+}
+
+// General stride-1 dense conv for the graph runtime: kernel kh x kw, dilation, explicit top/left padding; the
+// input tensor has `cin_pitch` (multiple of 64) channels of which the first `cin` are real.
+static void pack_conv_general(ConvLayer& L, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw,
+                              int dil, int pad_t, int pad_l, cudaStream_t s) {
+  REQUIRE(cin_pitch % 64 == 0 && cin <= cin_pitch, "input channel pitch must be a multiple of 64");
+  REQUIRE(kh * kw <= 81, "kernels up to 81 taps");
+  L.cin = cin_pitch; L.cout = cout; L.cout_pad = pad_cout(cout); L.ntaps = kh * kw; L.K = kh * kw * cin_pitch;
+  L.bn = L.cout_pad < 256 ? L.cout_pad : 256;
+  std::vector<__half> hw((size_t)L.cout_pad * L.K, __float2half(0.f));
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int ky = 0; ky < kh; ++ky)
+        for (int kx = 0; kx < kw; ++kx)
+          hw[(size_t)co * L.K + (size_t)(ky * kw + kx) * cin_pitch + ci] = __float2half_rn(w[(((size_t)co * cin + ci) * kh + ky) * kw + kx]);
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      L.dy[ky * kw + kx] = (int8_t)(ky * dil - pad_t);
+      L.dx[ky * kw + kx] = (int8_t)(kx * dil - pad_l);
+    }
+  std::vector<float> hb(L.cout_pad, 0.f);
+  for (int i = 0; i < cout; ++i) hb[i] = bias ? bias[i] : 0.f;
+  upload(L.w, hw, s);
+  upload(L.b, hb, s);
+}
+
+// conv3x3 stride 2 pad 1 over a tensor with channel pitch cin_pitch, as 2x2 taps over its space-to-depth form
+static void pack_conv_s2d_pitch(ConvLayer& L, const float* w, const float* bias, int cout, int cin, int cin_pitch, cudaStream_t s) {
+  REQUIRE((4 * cin_pitch) % 64 == 0, "s2d conv needs 4*pitch multiple of 64");
+  L.cin = 4 * cin_pitch; L.cout = cout; L.cout_pad = pad_cout(cout); L.ntaps = 4; L.K = 16 * cin_pitch;
+  L.bn = L.cout_pad < 256 ? L.cout_pad : 256;
+  std::vector<__half> hw((size_t)L.cout_pad * L.K, __float2half(0.f));
+  for (int co = 0; co < cout; ++co)
+    for (int dyb = -1; dyb <= 0; ++dyb)
+      for (int dxb = -1; dxb <= 0; ++dxb)
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px) {
+            const int ky = 2 * dyb + py + 1, kx = 2 * dxb + px + 1;
+            if (ky < 0 || ky > 2 || kx < 0 || kx > 2) continue;
+            const int tap = (dyb + 1) * 2 + (dxb + 1);
+            for (int ci = 0; ci < cin; ++ci)
+              hw[(size_t)co * L.K + (size_t)tap * 4 * cin_pitch + (py * 2 + px) * cin_pitch + ci] =
                   __float2half_rn(w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx]);
           }
   for (int dyb = -1; dyb <= 0; ++dyb)
@@ -311,8 +366,8 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   p.cout = L.cout;
   p.flags = io.flags;
   p.prefetch = c.conv_prefetch ? 1 : 0;
-  memcpy(p.tap_dy, L.dy, 9);
-  memcpy(p.tap_dx, L.dx, 9);
+  memcpy(p.tap_dy, L.dy, 81);
+  memcpy(p.tap_dx, L.dx, 81);
   p.bias = L.b.as<float>();
   p.out16 = io.out16;
   p.out16_pitch = io.out16_pitch ? io.out16_pitch : L.cout;
@@ -328,7 +383,8 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
     REQUIRE(io.H % 2 == 0 && io.W % 2 == 0, "s2d store needs even H, W");
     p.out16_pitch = 4 * L.cout;
   }
-  if (!(io.flags & CONV_FINAL)) REQUIRE(L.cout == L.cout_pad, "Cout must be 64, 128 or a multiple of 256");
+  if (!(io.flags & CONV_FINAL)) REQUIRE(L.cout % 8 == 0, "Cout must be a multiple of 8");
+  if (io.out32) REQUIRE(L.cout == L.cout_pad, "fp32 stream needs Cout == padded Cout");
   const int ntiles = p.T * p.tiles_y * p.tiles_x * p.n_tiles;
   if (L.bn == 256 && c.conv_2cta && !(io.flags & CONV_FINAL)) {
     const uint64_t dims[2] = {(uint64_t)L.K, (uint64_t)L.cout_pad};
@@ -1121,6 +1177,38 @@ static void collect(vsr_sttn* h, int64_t ticket, uint8_t* const* frames_out) {
 
 }  // namespace vsr
 
+
+// ================================================================================================= graph runtime
+// Device-tensor runtime behind the DBNet text detector.  Python (vsr_b200/dbnet.py) compiles the
+// reference's Paddle PIR program into a list of calls on these entry points; tensors are NHWC fp16 device buffers.
+struct RtLayer {
+  enum Kind { DENSE, DENSE_S2, DEPTHWISE, DIRECT, DECONV } kind = DENSE;
+  ConvLayer tc;          // DENSE / DENSE_S2
+  DevBuf w32, b32;       // DEPTHWISE / DIRECT / DECONV
+  int cin = 0, cout = 0, cin_pitch = 0, cout_pitch = 0, kh = 0, kw = 0, stride = 1, pad_t = 0, pad_l = 0;
+};
+
+struct vsr_rt {
+  Ctx ctx;
+  std::vector<std::unique_ptr<DevBuf>> bufs;
+  std::vector<std::unique_ptr<RtLayer>> layers;
+  DevBuf scratch;  // space-to-depth staging of the stride-2 convs
+  DevTaps px, py;  // resize tables of the pre-processing
+};
+
+namespace vsr {
+static void rt_check(vsr_rt* h) {
+  if (!h) throw Error(VSR_ERR_ARG, "null runtime");
+  CK(cudaSetDevice(h->ctx.device));
+}
+static void rt_sync(vsr_rt* h) {
+  cudaError_t e = cudaStreamSynchronize(h->ctx.stream);
+  if (e != cudaSuccess)
+    throw Error(VSR_ERR_CUDA, std::string("cudaStreamSynchronize -> ") + cudaGetErrorString(e) + device_error_report());
+}
+static unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
+}  // namespace vsr
+
 // ================================================================================================= C ABI
 extern "C" {
 
@@ -1444,6 +1532,255 @@ int vsr_window_schedule(int T, int stride, int ref_length, int32_t* ids, int32_t
     count = (int)s.size();
   });
   return r ? r : count;
+}
+
+
+// ---- graph runtime ---------------------------------------------------------------------------------------
+int vsr_rt_create(vsr_rt_t** out, int device) {
+  return guarded([&] {
+    REQUIRE(out, "out pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      throw Error(VSR_ERR_CUDA, "no CUDA device: vsr_b200 has no CPU fallback");
+    }
+    REQUIRE(device >= 0 && device < n, "device index");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw Error(VSR_ERR_CUDA, "vsr_b200 kernels are sm_100a only");
+    CK(cudaSetDevice(device));
+    auto* h = new vsr_rt();
+    h->ctx.device = device;
+    h->ctx.sms = prop.multiProcessorCount;
+    h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
+    CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
+    *out = h;
+  });
+}
+void vsr_rt_destroy(vsr_rt_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->ctx.device);
+  cudaStreamSynchronize(h->ctx.stream);
+  cudaStreamDestroy(h->ctx.stream);
+  delete h;
+}
+int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(bytes > 0 && dev_ptr, "bad arguments");
+    auto b = std::make_unique<DevBuf>();
+    b->ensure((size_t)bytes);
+    *dev_ptr = (uint64_t)(uintptr_t)b->p;
+    h->bufs.push_back(std::move(b));
+  });
+}
+int vsr_rt_upload(vsr_rt_t* h, uint64_t dev_ptr, const void* host, int64_t bytes) {
+  return guarded([&] {
+    rt_check(h);
+    CK(cudaMemcpyAsync((void*)(uintptr_t)dev_ptr, host, (size_t)bytes, cudaMemcpyHostToDevice, h->ctx.stream));
+    rt_sync(h);
+  });
+}
+int vsr_rt_download(vsr_rt_t* h, uint64_t dev_ptr, void* host, int64_t bytes) {
+  return guarded([&] {
+    rt_check(h);
+    CK(cudaMemcpyAsync(host, (const void*)(uintptr_t)dev_ptr, (size_t)bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
+    rt_sync(h);
+  });
+}
+int vsr_rt_sync(vsr_rt_t* h) {
+  return guarded([&] {
+    rt_check(h);
+    rt_sync(h);
+  });
+}
+int64_t vsr_rt_launch_count(vsr_rt_t* h) { return h ? h->ctx.launches : 0; }
+
+int vsr_rt_conv_create(vsr_rt_t* h, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw, int stride,
+                       int pad_t, int pad_l, int dil, int groups, int transposed, int* layer_id) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(w && layer_id && cout > 0 && cin > 0 && cin_pitch >= cin && cin_pitch % 8 == 0, "bad conv description");
+    auto L = std::make_unique<RtLayer>();
+    L->cin = cin; L->cout = cout; L->cin_pitch = cin_pitch; L->kh = kh; L->kw = kw; L->stride = stride; L->pad_t = pad_t; L->pad_l = pad_l;
+    cudaStream_t s = h->ctx.stream;
+    if (transposed) {  // conv2d_transpose 2x2 stride 2: w is [cin][cout][2][2]
+      REQUIRE(kh == 2 && kw == 2 && stride == 2 && groups == 1, "only 2x2 stride-2 transposed convs");
+      L->kind = RtLayer::DECONV;
+      L->cout_pitch = (cout + 7) / 8 * 8;
+      std::vector<float> pw((size_t)4 * cin * L->cout_pitch, 0.f), pb(L->cout_pitch, 0.f);
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx)
+              pw[((size_t)(dy * 2 + dx) * cin + ci) * L->cout_pitch + co] = w[(((size_t)ci * cout + co) * 2 + dy) * 2 + dx];
+      for (int co = 0; co < cout; ++co) pb[co] = bias ? bias[co] : 0.f;
+      upload(L->w32, pw, s);
+      upload(L->b32, pb, s);
+    } else if (groups > 1) {
+      REQUIRE(groups == cin && cout == cin && kh == kw && dil == 1, "only depthwise grouped convs");
+      L->kind = RtLayer::DEPTHWISE;
+      L->cout_pitch = cin_pitch;
+      std::vector<float> pw((size_t)kh * kw * cin_pitch, 0.f), pb(cin_pitch, 0.f);
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < kh * kw; ++t) pw[(size_t)t * cin_pitch + c] = w[(size_t)c * kh * kw + t];
+      for (int c = 0; c < cin; ++c) pb[c] = bias ? bias[c] : 0.f;
+      upload(L->w32, pw, s);
+      upload(L->b32, pb, s);
+    } else if (cin < 16 || cout < 8) {
+      L->kind = RtLayer::DIRECT;
+      REQUIRE(dil == 1, "direct conv without dilation");
+      L->cout_pitch = (cout + 7) / 8 * 8;
+      std::vector<float> pw((size_t)kh * kw * cin * L->cout_pitch, 0.f), pb(L->cout_pitch, 0.f);
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int t = 0; t < kh * kw; ++t) pw[((size_t)t * cin + ci) * L->cout_pitch + co] = w[((size_t)co * cin + ci) * kh * kw + t];
+      for (int co = 0; co < cout; ++co) pb[co] = bias ? bias[co] : 0.f;
+      upload(L->w32, pw, s);
+      upload(L->b32, pb, s);
+    } else if (stride == 2) {
+      REQUIRE(kh == 3 && kw == 3 && pad_t == 1 && pad_l == 1 && dil == 1, "stride-2 dense convs must be 3x3 pad 1");
+      REQUIRE(cin_pitch % 16 == 0 && cout % 8 == 0, "channel alignment");
+      L->kind = RtLayer::DENSE_S2;
+      pack_conv_s2d_pitch(L->tc, w, bias, cout, cin, cin_pitch, s);
+      L->cout_pitch = cout;
+    } else {
+      REQUIRE(stride == 1 && cout % 8 == 0, "dense convs: stride 1, Cout multiple of 8");
+      L->kind = RtLayer::DENSE;
+      pack_conv_general(L->tc, w, bias, cout, cin, cin_pitch, kh, kw, dil, pad_t, pad_l, s);
+      L->cout_pitch = cout;
+    }
+    *layer_id = (int)h->layers.size();
+    h->layers.push_back(std::move(L));
+  });
+}
+
+int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(layer_id >= 0 && layer_id < (int)h->layers.size(), "layer id");
+    RtLayer& L = *h->layers[layer_id];
+    const __half* in = (const __half*)(uintptr_t)in_ptr;
+    __half* out = (__half*)(uintptr_t)out_ptr;
+    cudaStream_t s = h->ctx.stream;
+    Ctx& c = h->ctx;
+    switch (L.kind) {
+      case RtLayer::DENSE: {
+        ConvIO io;
+        io.in = in; io.T = T; io.H = H; io.W = W; io.flags = relu ? 0x100 : 0; io.out16 = out; io.out16_pitch = out_pitch; io.out16_coff = out_coff;
+        run_conv(c, L.tc, io);
+        break;
+      }
+      case RtLayer::DENSE_S2: {
+        REQUIRE(H % 2 == 0 && W % 2 == 0, "stride-2 conv needs even input size");
+        const size_t n = (size_t)T * H * W * L.cin_pitch;
+        h->scratch.ensure(n * 2);
+        rt_space_to_depth_kernel<<<blocks_for(n / 8), 256, 0, s>>>(in, T, H, W, L.cin_pitch, h->scratch.as<__half>());
+        CK(cudaGetLastError());
+        ++c.launches;
+        ConvIO io;
+        io.in = h->scratch.as<__half>(); io.T = T; io.H = H / 2; io.W = W / 2; io.flags = relu ? 0x100 : 0; io.out16 = out;
+        io.out16_pitch = out_pitch; io.out16_coff = out_coff;
+        run_conv(c, L.tc, io);
+        break;
+      }
+      case RtLayer::DEPTHWISE: {
+        REQUIRE(out_coff == 0 && out_pitch == L.cin_pitch, "depthwise output must be a plain tensor of the same pitch");
+        const int OH = (H + 2 * L.pad_t - L.kh) / L.stride + 1, OW = (W + 2 * L.pad_l - L.kw) / L.stride + 1;
+        const size_t n = (size_t)T * OH * OW * (L.cin_pitch / 8);
+        rt_depthwise_kernel<<<blocks_for(n), 256, 0, s>>>(in, T, H, W, L.cin_pitch, L.w32.as<float>(), L.b32.as<float>(), L.kh, L.stride, L.pad_t,
+                                                          relu, out, OH, OW);
+        CK(cudaGetLastError());
+        ++c.launches;
+        break;
+      }
+      case RtLayer::DIRECT: {
+        REQUIRE(out_coff == 0 && out_pitch >= L.cout_pitch && out_pitch % 8 == 0, "direct conv output pitch");
+        const int OH = (H + 2 * L.pad_t - L.kh) / L.stride + 1, OW = (W + 2 * L.pad_l - L.kw) / L.stride + 1;
+        const size_t n = (size_t)T * OH * OW * (L.cout_pitch / 8);
+        rt_direct_conv_kernel<<<blocks_for(n), 256, 0, s>>>(in, T, H, W, L.cin_pitch, L.cin, L.w32.as<float>(), L.b32.as<float>(), L.kh, L.kw,
+                                                            L.stride, L.pad_t, L.pad_l, relu, out, OH, OW, L.cout_pitch, out_pitch);
+        CK(cudaGetLastError());
+        ++c.launches;
+        break;
+      }
+      case RtLayer::DECONV: {
+        REQUIRE(out_coff == 0 && out_pitch >= L.cout_pitch && out_pitch % 8 == 0, "deconv output pitch");
+        const size_t n = (size_t)T * 2 * H * 2 * W * (L.cout_pitch / 8);
+        rt_deconv2x2_kernel<<<blocks_for(n), 256, 0, s>>>(in, T, H, W, L.cin_pitch, L.cin, L.w32.as<float>(), L.b32.as<float>(), relu, out,
+                                                          L.cout_pitch, out_pitch);
+        CK(cudaGetLastError());
+        ++c.launches;
+        break;
+      }
+    }
+  });
+}
+
+int vsr_rt_elementwise(vsr_rt_t* h, int op, uint64_t a, uint64_t b, uint64_t out, int64_t n_elems, int cp, uint64_t scale_dev,
+                       uint64_t shift_dev, float alpha, float beta) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(n_elems > 0 && n_elems % 8 == 0 && cp % 8 == 0, "element count must be a multiple of 8");
+    if (op == RT_AFFINE || op == RT_AFFINE_RELU) REQUIRE(scale_dev && shift_dev, "affine needs device scale and shift [cp] fp32");
+    rt_elementwise_kernel<<<blocks_for((size_t)n_elems / 8), 256, 0, h->ctx.stream>>>(
+        op, (const __half*)(uintptr_t)a, (const __half*)(uintptr_t)b, (__half*)(uintptr_t)out, (size_t)n_elems / 8, cp,
+        (const float*)(uintptr_t)scale_dev, (const float*)(uintptr_t)shift_dev, alpha, beta);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_upsample_nearest(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, int scale, uint64_t out, int out_pitch, int out_coff) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(scale >= 1 && cp % 8 == 0, "bad arguments");
+    const size_t n = (size_t)T * H * scale * W * scale * (cp / 8);
+    rt_upsample_nearest_kernel<<<blocks_for(n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, T, H, W, cp, scale, (__half*)(uintptr_t)out,
+                                                                        out_pitch, out_coff);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_maxpool2x2s1(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    const size_t n = (size_t)T * H * W * (cp / 8);
+    rt_maxpool2x2s1_kernel<<<blocks_for(n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, T, H, W, cp, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_copy_channels(vsr_rt_t* h, uint64_t src, int src_pitch, uint64_t dst, int dst_pitch, int dst_coff, int channels, int64_t pixels) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(channels % 8 == 0 && dst_coff % 8 == 0 && src_pitch % 8 == 0 && dst_pitch % 8 == 0, "8-channel granularity");
+    rt_copy_channels_kernel<<<blocks_for((size_t)pixels * (channels / 8)), 256, 0, h->ctx.stream>>>(
+        (const __half*)(uintptr_t)src, src_pitch, (__half*)(uintptr_t)dst, dst_pitch, dst_coff, channels / 8, (size_t)pixels);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_det_preprocess(vsr_rt_t* h, const uint8_t* bgr, int sh, int sw, uint64_t out, int dh, int dw, int cp) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(bgr && sh > 0 && sw > 0 && dh > 0 && dw > 0 && cp >= 8, "bad arguments");
+    cudaStream_t s = h->ctx.stream;
+    h->scratch.ensure((size_t)sh * sw * 3);
+    CK(cudaMemcpyAsync(h->scratch.p, bgr, (size_t)sh * sw * 3, cudaMemcpyHostToDevice, s));
+    h->px.build(sw, dw, false, s);
+    h->py.build(sh, dh, true, s);
+    CK(cudaMemsetAsync((void*)(uintptr_t)out, 0, (size_t)dh * dw * cp * 2, s));
+    rt_det_preprocess_kernel<<<dim3((dw + 255) / 256, dh), 256, 0, s>>>(h->scratch.as<uint8_t>(), sw, sh, (__half*)(uintptr_t)out, dw, dh, cp,
+                                                                       h->px.i0.as<int>(), h->px.i1.as<int>(), h->px.w0.as<short>(),
+                                                                       h->px.w1.as<short>(), h->py.i0.as<int>(), h->py.i1.as<int>(),
+                                                                       h->py.w0.as<short>(), h->py.w1.as<short>());
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
 }
 
 // ---- operator-level entry points -------------------------------------------------------------------

@@ -1,0 +1,277 @@
+// Generic NHWC fp16 operators for graph-driven networks (the DBNet text detector): the
+// dense convolutions go through the tcgen05 implicit-GEMM kernel of conv_igemm.cuh; this file holds the
+// HBM-bound rest (depthwise conv, small-Cin stem, space-to-depth, element-wise, nearest up-sampling, max
+// pooling, channel copies for concat, 2x2 stride-2 transposed conv, image normalisation).
+// Every tensor is [T, H, W, Cp] with the channel pitch Cp a multiple of 8 (64 for tensors that feed a TMA
+// conv); channels >= C are padding that the consumers multiply with zero weights.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vsr {
+
+enum RtEltOp : int { RT_ADD = 0, RT_RELU = 1, RT_ADD_RELU = 2, RT_SIGMOID = 3, RT_AFFINE = 4, RT_AFFINE_RELU = 5, RT_SCALE = 6,
+                     RT_AVG2 = 7 };
+
+// 8 channels per thread.  a, b, out may alias.  AFFINE: out = a*scale[c] + shift[c]; SCALE: out = a*alpha + beta;
+// AVG2: out = (a + b) * alpha.
+__global__ void __launch_bounds__(256) rt_elementwise_kernel(int op, const __half* __restrict__ a, const __half* __restrict__ b,
+                                                             __half* __restrict__ out, size_t n8, int cp, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, float alpha, float beta) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 va = reinterpret_cast<const uint4*>(a)[i];
+  uint4 vb = make_uint4(0, 0, 0, 0);
+  if (op == RT_ADD || op == RT_ADD_RELU || op == RT_AVG2) vb = reinterpret_cast<const uint4*>(b)[i];
+  const __half2* pa = reinterpret_cast<const __half2*>(&va);
+  const __half2* pb = reinterpret_cast<const __half2*>(&vb);
+  const int c0 = (int)((i * 8) % (size_t)cp);
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 x = __half22float2(pa[j]);
+    const float2 y = __half22float2(pb[j]);
+    switch (op) {
+      case RT_ADD: x.x += y.x; x.y += y.y; break;
+      case RT_RELU: x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); break;
+      case RT_ADD_RELU: x.x = fmaxf(x.x + y.x, 0.f); x.y = fmaxf(x.y + y.y, 0.f); break;
+      case RT_SIGMOID: x.x = 1.f / (1.f + __expf(-x.x)); x.y = 1.f / (1.f + __expf(-x.y)); break;
+      case RT_AFFINE:
+      case RT_AFFINE_RELU:
+        x.x = x.x * scale[c0 + 2 * j] + shift[c0 + 2 * j];
+        x.y = x.y * scale[c0 + 2 * j + 1] + shift[c0 + 2 * j + 1];
+        if (op == RT_AFFINE_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
+        break;
+      case RT_SCALE: x.x = x.x * alpha + beta; x.y = x.y * alpha + beta; break;
+      case RT_AVG2: x.x = (x.x + y.x) * alpha; x.y = (x.y + y.y) * alpha; break;
+    }
+    o[j] = __floats2half2_rn(x.x, x.y);
+  }
+  reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
+}
+
+// nearest_interp (align_corners False) by an integer factor: out[y][x] = in[y / s][x / s].
+__global__ void __launch_bounds__(256) rt_upsample_nearest_kernel(const __half* __restrict__ in, int T, int h, int w, int cp, int s,
+                                                                  __half* __restrict__ out, int out_pitch, int out_coff) {
+  const int c8n = cp >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)T * h * s * w * s * c8n;
+  if (idx >= total) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int ox = r % (w * s);
+  r /= (w * s);
+  const int oy = r % (h * s);
+  const int t = r / (h * s);
+  const uint4 v = *reinterpret_cast<const uint4*>(in + (((size_t)t * h + oy / s) * w + ox / s) * cp + c8 * 8);
+  *reinterpret_cast<uint4*>(out + (((size_t)t * h * s + oy) * w * s + ox) * out_pitch + out_coff + c8 * 8) = v;
+}
+
+// pool2d max 2x2 stride 1, SAME (pad bottom/right with -inf): out[y][x] = max over y..y+1, x..x+1 inside the image.
+__global__ void __launch_bounds__(256) rt_maxpool2x2s1_kernel(const __half* __restrict__ in, int T, int h, int w, int cp,
+                                                              __half* __restrict__ out) {
+  const int c8n = cp >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)T * h * w * c8n;
+  if (idx >= total) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int x = r % w;
+  r /= w;
+  const int y = r % h;
+  const int t = r / h;
+  const __half* base = in + (size_t)t * h * w * cp + c8 * 8;
+  uint4 acc = *reinterpret_cast<const uint4*>(base + ((size_t)y * w + x) * cp);
+  __half2* pa = reinterpret_cast<__half2*>(&acc);
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      if ((dy | dx) == 0 || y + dy >= h || x + dx >= w) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(base + ((size_t)(y + dy) * w + x + dx) * cp);
+      const __half2* pv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pa[j] = __hmax2(pa[j], pv[j]);
+    }
+  *reinterpret_cast<uint4*>(out + idx * 8) = acc;
+}
+
+// copy C (multiple of 8) channels of every pixel into a channel slice of another tensor (concat)
+__global__ void __launch_bounds__(256) rt_copy_channels_kernel(const __half* __restrict__ src, int src_pitch, __half* __restrict__ dst,
+                                                               int dst_pitch, int dst_coff, int c8n, size_t pixels) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pixels * c8n) return;
+  const int c8 = idx % c8n;
+  const size_t p = idx / c8n;
+  *reinterpret_cast<uint4*>(dst + p * dst_pitch + dst_coff + c8 * 8) = *reinterpret_cast<const uint4*>(src + p * src_pitch + c8 * 8);
+}
+
+// [T,H,W,cp] -> [T,H/2,W/2,4*cp], channel = ((y&1)*2 + (x&1))*cp + c : input layout of the stride-2 convs
+__global__ void __launch_bounds__(256) rt_space_to_depth_kernel(const __half* __restrict__ in, int T, int H, int W, int cp,
+                                                                __half* __restrict__ out) {
+  const int c8n = cp >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)T * H * W * c8n;
+  if (idx >= total) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int x = r % W;
+  r /= W;
+  const int y = r % H;
+  const int t = r / H;
+  const uint4 v = *reinterpret_cast<const uint4*>(in + idx * 8);
+  const size_t opix = ((size_t)t * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+  *reinterpret_cast<uint4*>(out + opix * 4 * cp + ((y & 1) * 2 + (x & 1)) * cp + c8 * 8) = v;
+}
+
+// depthwise conv (groups == channels), any odd kernel, stride 1 or 2, zero padding; weights [k*k][cp] fp32,
+// bias [cp]; 8 channels per thread, fp32 accumulation; optional ReLU.
+__global__ void __launch_bounds__(256) rt_depthwise_kernel(const __half* __restrict__ in, int T, int H, int W, int cp,
+                                                           const float* __restrict__ wgt, const float* __restrict__ bias, int k, int stride,
+                                                           int pad, int relu, __half* __restrict__ out, int OH, int OW) {
+  const int c8n = cp >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)T * OH * OW * c8n;
+  if (idx >= total) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int ox = r % OW;
+  r /= OW;
+  const int oy = r % OH;
+  const int t = r / OH;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bias[c8 * 8 + j];
+  for (int ky = 0; ky < k; ++ky) {
+    const int iy = oy * stride + ky - pad;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < k; ++kx) {
+      const int ix = ox * stride + kx - pad;
+      if (ix < 0 || ix >= W) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(in + (((size_t)t * H + iy) * W + ix) * cp + c8 * 8);
+      const __half2* pv = reinterpret_cast<const __half2*>(&v);
+      const float* wr = wgt + (size_t)(ky * k + kx) * cp + c8 * 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(pv[j]);
+        acc[2 * j] = fmaf(f.x, wr[2 * j], acc[2 * j]);
+        acc[2 * j + 1] = fmaf(f.y, wr[2 * j + 1], acc[2 * j + 1]);
+      }
+    }
+  }
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = acc[2 * j], b = acc[2 * j + 1];
+    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    o[j] = __floats2half2_rn(a, b);
+  }
+  *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// Direct conv for tiny channel counts on either side (the 3-channel stem, the 64->1 head): one thread per
+// (output pixel, 8 output channels); in [T,H,W,cin_p] fp16, weights [k*k*cin][cout_p] fp32 (cout_p multiple of 8).
+__global__ void __launch_bounds__(256) rt_direct_conv_kernel(const __half* __restrict__ in, int T, int H, int W, int cin_p, int cin,
+                                                             const float* __restrict__ wgt, const float* __restrict__ bias, int kh, int kw,
+                                                             int stride, int pad_t, int pad_l, int relu, __half* __restrict__ out, int OH,
+                                                             int OW, int cout_p, int out_pitch) {
+  const int c8n = cout_p >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)T * OH * OW * c8n;
+  if (idx >= total) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int ox = r % OW;
+  r /= OW;
+  const int oy = r % OH;
+  const int t = r / OH;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bias[c8 * 8 + j];
+  for (int ky = 0; ky < kh; ++ky) {
+    const int iy = oy * stride + ky - pad_t;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int ix = ox * stride + kx - pad_l;
+      if (ix < 0 || ix >= W) continue;
+      const __half* px = in + (((size_t)t * H + iy) * W + ix) * cin_p;
+      const float* wr = wgt + (size_t)((ky * kw + kx) * cin) * cout_p + c8 * 8;
+      for (int ci = 0; ci < cin; ++ci) {
+        const float v = __half2float(px[ci]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[(size_t)ci * cout_p + j], acc[j]);
+      }
+    }
+  }
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = acc[2 * j], b = acc[2 * j + 1];
+    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    o[j] = __floats2half2_rn(a, b);
+  }
+  *reinterpret_cast<uint4*>(out + (idx / c8n) * out_pitch + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// conv2d_transpose 2x2 stride 2 (no overlap): out[2y+dy][2x+dx][co] = bias[co] + sum_ci in[y][x][ci] * w[ci][co][dy][dx].
+// weights repacked as [dy*2+dx][cin][cout_p] fp32.  One thread per (output pixel, 8 output channels).
+__global__ void __launch_bounds__(256) rt_deconv2x2_kernel(const __half* __restrict__ in, int T, int H, int W, int cin_p, int cin,
+                                                           const float* __restrict__ wgt, const float* __restrict__ bias, int relu,
+                                                           __half* __restrict__ out, int cout_p, int out_pitch) {
+  const int c8n = cout_p >> 3;
+  const int OH = 2 * H, OW = 2 * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)T * OH * OW * c8n;
+  if (idx >= total) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int ox = r % OW;
+  r /= OW;
+  const int oy = r % OH;
+  const int t = r / OH;
+  const __half* px = in + (((size_t)t * H + (oy >> 1)) * W + (ox >> 1)) * cin_p;
+  const float* wr = wgt + (size_t)(((oy & 1) * 2 + (ox & 1)) * cin) * cout_p + c8 * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bias[c8 * 8 + j];
+  for (int ci = 0; ci < cin; ++ci) {
+    const float v = __half2float(px[ci]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[(size_t)ci * cout_p + j], acc[j]);
+  }
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = acc[2 * j], b = acc[2 * j + 1];
+    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    o[j] = __floats2half2_rn(a, b);
+  }
+  *reinterpret_cast<uint4*>(out + (idx / c8n) * out_pitch + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// DetResizeForTest + NormalizeImage + ToCHW of the detector (inference.yml:22-40): BGR u8 [sh,sw,3] ->
+// cv2-exact bilinear resize -> (x/255 - mean[c]) / std[c] in BGR order -> NHWC fp16 [dh,dw,cp] (3 real channels).
+struct ResizeTaps;
+__global__ void __launch_bounds__(256) rt_det_preprocess_kernel(const uint8_t* __restrict__ src, int sw, int sh, __half* __restrict__ dst,
+                                                                int dw, int dh, int cp, const int* __restrict__ xi0,
+                                                                const int* __restrict__ xi1, const short* __restrict__ xw0,
+                                                                const short* __restrict__ xw1, const int* __restrict__ yi0,
+                                                                const int* __restrict__ yi1, const short* __restrict__ yw0,
+                                                                const short* __restrict__ yw1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= dw) return;
+  const uint8_t* r0 = src + (size_t)yi0[y] * sw * 3;
+  const uint8_t* r1 = src + (size_t)yi1[y] * sw * 3;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  __half* o = dst + ((size_t)y * dw + x) * cp;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int s0 = r0[xi0[x] * 3 + c] * xw0[x] + r0[xi1[x] * 3 + c] * xw1[x];
+    const int s1 = r1[xi0[x] * 3 + c] * xw0[x] + r1[xi1[x] * 3 + c] * xw1[x];
+    int v = (((yw0[y] * (s0 >> 4)) >> 16) + ((yw1[y] * (s1 >> 4)) >> 16) + 2) >> 2;
+    v = min(max(v, 0), 255);
+    o[c] = __float2half_rn(((float)v * (1.0f / 255.0f) - mean[c]) / stdv[c]);
+  }
+}
+
+}  // namespace vsr

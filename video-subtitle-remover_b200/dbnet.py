@@ -1,0 +1,440 @@
+"""PP-OCRv5 DBNet text detector on the B200.
+
+The reference calls third-party `paddleocr.TextDetection(model_dir=...).predict(img)` on the CPU
+(backend/tools/subtitle_detect.py:43-58).  What the reference ships and pins is the model itself:
+`backend/models/V5/ch_det/inference.json` (Paddle PIR program), `inference.pdiparams`, `inference.yml`.
+This module compiles that program into calls on the device-tensor runtime of the C ABI (`vsr_rt_*`,
+include/vsr_b200.h): batch-norm, bias and ReLU are folded into the convolutions, dense convolutions run on the
+tcgen05 implicit-GEMM kernel, everything stays in NHWC fp16 on the device until the probability map.
+`TextDetector.predict` returns `[{"dt_polys": ndarray[N,4,2]}]` like the paddleocr object it replaces.
+
+Pre/post-processing follow PaddleX's DetResizeForTest / NormalizeImage / DBPostProcess as published (SURVEY
+Appendix A.5 — the reference has no test or golden vector for them).
+"""
+import ctypes as C
+import json
+import os
+import struct
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _capi
+from .sttn_auto_inpaint import _device_index
+
+THRESH, BOX_THRESH, MAX_CANDIDATES, UNCLIP_RATIO, RESIZE_LONG = 0.3, 0.6, 1000, 1.5, 960  # inference.yml:22-53
+
+
+# ------------------------------------------------------------------------------------------------ model files
+def _read_params(path: str) -> List[np.ndarray]:
+    """inference.pdiparams: records {u32, u64 lod levels, u32, i32 desc_len, TensorDesc proto, raw fp32} in
+    sorted(parameter name) order."""
+    buf = open(path, "rb").read()
+    pos, out = 0, []
+
+    def varint(b, j):
+        v = s = 0
+        while True:
+            c = b[j]
+            j += 1
+            v |= (c & 127) << s
+            s += 7
+            if c < 128:
+                return v, j
+
+    while pos < len(buf):
+        pos += 4
+        (lod,) = struct.unpack_from("<Q", buf, pos)
+        pos += 8
+        for _ in range(lod):
+            (n,) = struct.unpack_from("<Q", buf, pos)
+            pos += 8 + n
+        pos += 4
+        (dlen,) = struct.unpack_from("<i", buf, pos)
+        pos += 4
+        desc, j, dims = buf[pos:pos + dlen], 0, []
+        pos += dlen
+        while j < len(desc):
+            tag = desc[j]
+            j += 1
+            if tag & 7 == 0:
+                v, j = varint(desc, j)
+                if tag >> 3 != 1:
+                    dims.append(v)
+            else:
+                ln, j = varint(desc, j)
+                end = j + ln
+                while j < end:
+                    v, j = varint(desc, j)
+                    dims.append(v)
+        cnt = int(np.prod(dims)) if dims else 1
+        out.append(np.frombuffer(buf, "<f4", cnt, pos).reshape(dims).copy())
+        pos += 4 * cnt
+    return out
+
+
+class _Node:
+    __slots__ = ("kind", "ins", "out", "attrs", "name")
+
+    def __init__(self, kind, ins, out, attrs, name=None):
+        self.kind, self.ins, self.out, self.attrs, self.name = kind, ins, out, attrs, name
+
+
+def _load_program(model_dir: str):
+    prog = json.load(open(os.path.join(model_dir, "inference.json")))
+    nodes = []
+    for o in prog["program"]["regions"][0]["blocks"][0]["ops"]:
+        kind = o["#"].split(".", 1)[-1]
+        outs = o.get("O", [])
+        out = outs["%"] if isinstance(outs, dict) else (outs[0]["%"] if outs else None)
+        attrs = {}
+        for a in o.get("A", []):
+            if isinstance(a, dict):
+                t = a["AT"]
+                attrs[a["N"]] = [x["D"] for x in t["D"]] if t["#"] == "0.a_array" else t.get("D")
+        nodes.append(_Node(kind, [i["%"] for i in o.get("I", [])], out, attrs, o["A"][3] if kind == "p" else None))
+    names = sorted(n.name for n in nodes if n.kind == "p")
+    tensors = _read_params(os.path.join(model_dir, "inference.pdiparams"))
+    if len(names) != len(tensors):
+        raise _capi.VsrError(f"{model_dir}: {len(names)} parameters in the program, {len(tensors)} in pdiparams")
+    return nodes, dict(zip(names, tensors))
+
+
+def _r(x, m):
+    return (x + m - 1) // m * m
+
+
+class _Tensor:
+    """NHWC fp16 device tensor; `c` real channels, pitch `cp`; `perm[l]` = physical channel of logical channel l."""
+
+    def __init__(self, ptr, c, h, w, cp, perm=None):
+        self.ptr, self.c, self.h, self.w, self.cp, self.perm = ptr, c, h, w, cp, perm
+
+    @property
+    def pixels(self):
+        return self.h * self.w
+
+
+class _Compiled:
+    def __init__(self):
+        self.steps = []      # closures over the C ABI
+        self.inp = None
+        self.out = None
+
+
+class TextDetector:
+    """Stand-in for `paddleocr.TextDetection(model_name, model_dir, device=...)` (subtitle_detect.py:47-52)."""
+
+    def __init__(self, model_dir: str, device="cuda:0", model_name: Optional[str] = None):
+        self.model_dir, self.model_name = model_dir, model_name
+        self._nodes, self._params = _load_program(model_dir)
+        L = _capi.lib()
+        h = C.c_void_p()
+        _capi.check(L.vsr_rt_create(C.byref(h), _device_index(device)))
+        self._h = h
+        self._programs: Dict[tuple, _Compiled] = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _capi.lib().vsr_rt_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -------------------------------------------------------------------------------------------- runtime helpers
+    def _alloc(self, nbytes: int) -> int:
+        p = C.c_uint64()
+        _capi.check(_capi.lib().vsr_rt_alloc(self._h, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def _new(self, c, h, w, perm=None) -> _Tensor:
+        cp = _r(max(c, 1), 64)
+        return _Tensor(self._alloc(h * w * cp * 2), c, h, w, cp, perm)
+
+    def _upload_f32(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr, np.float32)
+        p = self._alloc(arr.nbytes)
+        _capi.check(_capi.lib().vsr_rt_upload(self._h, p, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        return p
+
+    # -------------------------------------------------------------------------------------------- graph compiler
+    def _compile(self, H: int, W: int) -> _Compiled:
+        L, rt = _capi.lib(), self._h
+        nodes, params = self._nodes, self._params
+        prod = {n.out: n for n in nodes if n.out is not None}
+        users: Dict[int, List[_Node]] = {}
+        for n in nodes:
+            for i in n.ins:
+                users.setdefault(i, []).append(n)
+        val: Dict[int, object] = {}   # value id -> _Tensor | ndarray | python constant
+        done = set()
+        prog = _Compiled()
+        f32p = C.POINTER(C.c_float)
+
+        def single_user(v, kind):
+            u = users.get(v, [])
+            return u[0] if len(u) == 1 and u[0].kind == kind else None
+
+        def const_of(v):
+            x = val[v]
+            return x if not isinstance(x, _Tensor) else None
+
+        def bias_operand(add_node, act_id):
+            """`add(x, reshape(param))`: the per-channel bias vector, else None."""
+            other = [i for i in add_node.ins if i != act_id]
+            if len(other) != 1:
+                return None
+            c = const_of(other[0])
+            return np.asarray(c, np.float32).reshape(-1) if isinstance(c, np.ndarray) else None
+
+        def emit_conv(n: _Node):
+            x: _Tensor = val[n.ins[0]]
+            w = np.asarray(val[n.ins[1]], np.float32)
+            a = n.attrs
+            transposed = n.kind == "conv2d_transpose"
+            groups = int(a.get("groups", 1))
+            cout = w.shape[1] if transposed else w.shape[0]
+            kh, kw = int(w.shape[2]), int(w.shape[3])
+            stride, dil = int(a["strides"][0]), int(a["dilations"][0])
+            if a.get("padding_algorithm") == "SAME":  # out = ceil(in/stride); extra pixel on the bottom / right
+                tot_h = max((-(-x.h // stride) - 1) * stride + (kh - 1) * dil + 1 - x.h, 0)
+                tot_w = max((-(-x.w // stride) - 1) * stride + (kw - 1) * dil + 1 - x.w, 0)
+                pad_t, pad_l = tot_h // 2, tot_w // 2
+            else:
+                pad_t, pad_l = int(a["paddings"][0]), int(a["paddings"][1])
+            bias = np.zeros(cout, np.float32)
+            w = w.copy()
+            cur, relu = n.out, 0
+            # fold: [+ bias add] [-> batch_norm] [-> relu], each only when it is the single consumer
+            u = single_user(cur, "add")
+            if u is not None:
+                b = bias_operand(u, cur)
+                if b is not None and b.size == cout:
+                    bias += b
+                    done.add(id(u))
+                    cur = u.out
+            u = single_user(cur, "batch_norm_")
+            if u is not None and u.ins[0] == cur:
+                mean, var, gamma, beta = (np.asarray(val[i], np.float32) for i in u.ins[1:5])
+                s = gamma / np.sqrt(var + np.float32(u.attrs["epsilon"]))
+                if transposed:
+                    w *= s[None, :, None, None]
+                else:
+                    w *= s[:, None, None, None]
+                bias = (bias - mean) * s + beta
+                done.add(id(u))
+                cur = u.out
+            u = single_user(cur, "relu")
+            if u is not None:
+                relu = 1
+                done.add(id(u))
+                cur = u.out
+            cin_l = w.shape[0] if transposed else w.shape[1] * (groups if groups > 1 else 1)
+            if groups == 1 and x.perm is not None:  # logical input channel l lives at physical channel perm[l]
+                wp = np.zeros((w.shape[0], x.cp) + w.shape[2:], np.float32) if not transposed else None
+                if transposed:
+                    raise _capi.VsrError("permuted input into a transposed conv is not supported")
+                wp[:, x.perm] = w
+                w, cin_eff = wp, x.cp
+            else:
+                cin_eff = x.c if groups == 1 else x.c
+            if stride == 2 and not transposed:
+                oh, ow = (x.h + 2 * pad_t - (kh - 1) * dil - 1) // 2 + 1, (x.w + 2 * pad_l - (kw - 1) * dil - 1) // 2 + 1
+            elif transposed:
+                oh, ow = 2 * x.h, 2 * x.w
+            else:
+                oh, ow = x.h, x.w
+            y = self._new(cout, oh, ow)
+            lid = C.c_int32()
+            w = np.ascontiguousarray(w, np.float32)
+            _capi.check(L.vsr_rt_conv_create(rt, w.ctypes.data_as(f32p), bias.ctypes.data_as(f32p), cout, int(cin_eff), x.cp, kh, kw, stride,
+                                             pad_t, pad_l, dil, groups, 1 if transposed else 0, C.byref(lid)))
+            lid = int(lid.value)
+            prog.steps.append(lambda x=x, y=y, lid=lid, relu=relu: _capi.check(
+                L.vsr_rt_conv(rt, lid, x.ptr, 1, x.h, x.w, y.ptr, y.cp, 0, relu)))
+            val[cur] = y
+
+        def emit_elt(op, a: _Tensor, b: Optional[_Tensor], out_id, alpha=0.0, beta=0.0, scale=0, shift=0):
+            y = self._new(a.c, a.h, a.w, a.perm)
+            prog.steps.append(lambda: _capi.check(L.vsr_rt_elementwise(rt, op, a.ptr, b.ptr if b else 0, y.ptr, a.pixels * a.cp, a.cp, scale,
+                                                                       shift, alpha, beta)))
+            val[out_id] = y
+
+        for n in nodes:
+            if id(n) in done:
+                continue
+            k = n.kind
+            if k == "p":
+                val[n.out] = self._params[n.name]
+            elif k == "data":
+                prog.inp = self._new(3, H, W)
+                val[n.out] = prog.inp
+            elif k in ("full_int_array", "full"):
+                val[n.out] = n.attrs["value"]
+            elif k == "reshape":
+                src = val[n.ins[0]]
+                if isinstance(src, _Tensor):
+                    raise _capi.VsrError("reshape of an activation is not supported")
+                val[n.out] = np.asarray(src).reshape([int(d) for d in val[n.ins[1]]])
+            elif k == "combine":
+                val[n.out] = [val[i] for i in n.ins]
+            elif k in ("conv2d", "depthwise_conv2d", "conv2d_transpose"):
+                emit_conv(n)
+            elif k == "batch_norm_":  # not preceded by a conv: per-channel affine (+ relu)
+                x = val[n.ins[0]]
+                mean, var, gamma, beta = (np.asarray(val[i], np.float32) for i in n.ins[1:5])
+                s = gamma / np.sqrt(var + np.float32(n.attrs["epsilon"]))
+                sc, sh = np.zeros(x.cp, np.float32), np.zeros(x.cp, np.float32)
+                idx = x.perm if x.perm is not None else np.arange(x.c)
+                sc[idx], sh[idx] = s, beta - mean * s
+                cur, op = n.out, 4
+                u = single_user(cur, "relu")
+                if u is not None:
+                    op, cur = 5, u.out
+                    done.add(id(u))
+                emit_elt(op, x, None, cur, scale=self._upload_f32(sc), shift=self._upload_f32(sh))
+            elif k == "relu":
+                emit_elt(1, val[n.ins[0]], None, n.out)
+            elif k == "sigmoid":
+                emit_elt(3, val[n.ins[0]], None, n.out)
+            elif k == "add":
+                a, b = val[n.ins[0]], val[n.ins[1]]
+                if isinstance(a, _Tensor) and isinstance(b, _Tensor):
+                    if (a.c, a.h, a.w) != (b.c, b.h, b.w) or a.perm is not None or b.perm is not None:
+                        raise _capi.VsrError("add of mismatching activations")
+                    cur, op = n.out, 0
+                    u = single_user(cur, "relu")
+                    if u is not None:
+                        op, cur = 2, u.out
+                        done.add(id(u))
+                    emit_elt(op, a, b, cur)
+                else:  # activation + per-channel constant that was not folded into a conv
+                    x, cst = (a, b) if isinstance(a, _Tensor) else (b, a)
+                    cst = np.asarray(cst, np.float32).reshape(-1)
+                    sc, sh = np.zeros(x.cp, np.float32), np.zeros(x.cp, np.float32)
+                    idx = x.perm if x.perm is not None else np.arange(x.c)
+                    sc[idx] = 1.0
+                    sh[idx] = cst if cst.size == x.c else float(cst[0])
+                    emit_elt(4, x, None, n.out, scale=self._upload_f32(sc), shift=self._upload_f32(sh))
+            elif k == "scale":
+                emit_elt(6, val[n.ins[0]], None, n.out, alpha=float(np.asarray(val[n.ins[1]]).reshape(-1)[0]), beta=float(n.attrs.get("bias", 0.0)))
+            elif k == "concat":
+                parts: List[_Tensor] = val[n.ins[0]]
+                if int(np.asarray(val[n.ins[1]]).reshape(-1)[0]) != 1:
+                    raise _capi.VsrError("only channel concat is supported")
+                total = sum(p.c for p in parts)
+                # physical layout: 8-aligned parts first, ragged parts (the 1-channel probability map) last
+                order = sorted(range(len(parts)), key=lambda i: (parts[i].c % 8 != 0, i))
+                perm, off, phys = np.zeros(total, np.int64), 0, {}
+                for i in order:
+                    phys[i] = off
+                    off += _r(parts[i].c, 8)
+                lo = 0
+                for i, p in enumerate(parts):
+                    src = p.perm if p.perm is not None else np.arange(p.c)
+                    perm[lo:lo + p.c] = phys[i] + src
+                    lo += p.c
+                y = _Tensor(self._alloc(parts[0].pixels * _r(off, 64) * 2), total, parts[0].h, parts[0].w, _r(off, 64),
+                            None if np.array_equal(perm, np.arange(total)) else perm)
+                for i, p in enumerate(parts):
+                    prog.steps.append(lambda p=p, dst=phys[i]: _capi.check(
+                        L.vsr_rt_copy_channels(rt, p.ptr, p.cp, y.ptr, y.cp, dst, _r(p.c, 8), p.pixels)))
+                val[n.out] = y
+            elif k == "nearest_interp":
+                x = val[n.ins[0]]
+                s = int(round(float((n.attrs.get("scale") or [2.0])[0])))
+                y = _Tensor(self._alloc(x.pixels * s * s * x.cp * 2), x.c, x.h * s, x.w * s, x.cp, x.perm)
+                prog.steps.append(lambda x=x, y=y, s=s: _capi.check(L.vsr_rt_upsample_nearest(rt, x.ptr, 1, x.h, x.w, x.cp, s, y.ptr, y.cp, 0)))
+                val[n.out] = y
+            elif k == "pool2d":
+                x = val[n.ins[0]]
+                ks = [int(v) for v in val[n.ins[1]]]
+                a = n.attrs
+                if not (a["pooling_type"] == "max" and ks == [2, 2] and a["strides"] == [1, 1] and a["padding_algorithm"] == "SAME" and not a.get("adaptive")):
+                    raise _capi.VsrError(f"unsupported pool2d {a} (the mobile detector's SE blocks are not compiled yet)")
+                y = self._new(x.c, x.h, x.w, x.perm)
+                prog.steps.append(lambda x=x, y=y: _capi.check(L.vsr_rt_maxpool2x2s1(rt, x.ptr, 1, x.h, x.w, x.cp, y.ptr)))
+                val[n.out] = y
+            elif k == "fetch":
+                prog.out = val[n.ins[0]]
+            else:
+                raise _capi.VsrError(f"PIR op '{k}' is not supported by the B200 detector")
+        if prog.inp is None or prog.out is None:
+            raise _capi.VsrError("program without data/fetch")
+        return prog
+
+    # -------------------------------------------------------------------------------------------- inference
+    @staticmethod
+    def resize_shape(h: int, w: int):
+        """DetResizeForTest(resize_long=960): long side <= 960, both sides rounded to multiples of 32."""
+        ratio = RESIZE_LONG / max(h, w) if max(h, w) > RESIZE_LONG else 1.0
+        rh, rw = int(h * ratio), int(w * ratio)
+        return max(int(round(rh / 32) * 32), 32), max(int(round(rw / 32) * 32), 32)
+
+    def probability_map(self, img_bgr: np.ndarray) -> np.ndarray:
+        """BGR uint8 image -> DB probability map [rh, rw] fp32 (device: resize, normalise, network)."""
+        img = np.ascontiguousarray(img_bgr, np.uint8)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("expected a BGR uint8 image [H,W,3]")
+        rh, rw = self.resize_shape(img.shape[0], img.shape[1])
+        prog = self._programs.get((rh, rw))
+        if prog is None:
+            prog = self._programs[(rh, rw)] = self._compile(rh, rw)
+        L = _capi.lib()
+        _capi.check(L.vsr_rt_det_preprocess(self._h, _capi.ptr(img, C.c_uint8), img.shape[0], img.shape[1], prog.inp.ptr, rh, rw, prog.inp.cp))
+        for step in prog.steps:
+            step()
+        out = prog.out
+        host = np.empty((out.h, out.w, out.cp), np.float16)
+        _capi.check(L.vsr_rt_download(self._h, out.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))
+        ch = int(out.perm[0]) if out.perm is not None else 0
+        return host[:, :, ch].astype(np.float32)
+
+    @property
+    def launch_count(self) -> int:
+        return int(_capi.lib().vsr_rt_launch_count(self._h))
+
+    def predict(self, img_bgr: np.ndarray):
+        """Like paddleocr's TextDetection.predict: one result dict per image with `dt_polys` [N,4,2] int16."""
+        prob = self.probability_map(img_bgr)
+        return [{"dt_polys": db_postprocess(prob, img_bgr.shape[0], img_bgr.shape[1]), "prob_shape": prob.shape}]
+
+
+def _order_quad(pts):
+    p = sorted(np.asarray(pts).tolist(), key=lambda q: q[0])
+    a, d = (0, 1) if p[1][1] > p[0][1] else (1, 0)
+    b, c = (2, 3) if p[3][1] > p[2][1] else (3, 2)
+    return np.array([p[a], p[b], p[c], p[d]], np.float32)
+
+
+def db_postprocess(prob: np.ndarray, src_h: int, src_w: int) -> np.ndarray:
+    """DBPostProcess (thresh 0.3, box_thresh 0.6, unclip 1.5, quad boxes, fast score; inference.yml:48-53) with
+    OpenCV, the library PaddleOCR itself uses for it; the Clipper offset of the min-area rectangle is computed as
+    that rectangle grown by area*ratio/perimeter on every side."""
+    import cv2
+
+    H, W = prob.shape
+    contours, _ = cv2.findContours((prob > THRESH).astype(np.uint8) * 255, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    quads = []
+    for cnt in contours[:MAX_CANDIDATES]:
+        rect = cv2.minAreaRect(cnt)
+        if min(rect[1]) < 3:
+            continue
+        q = _order_quad(cv2.boxPoints(rect))
+        x0, x1 = int(np.clip(np.floor(q[:, 0].min()), 0, W - 1)), int(np.clip(np.ceil(q[:, 0].max()), 0, W - 1))
+        y0, y1 = int(np.clip(np.floor(q[:, 1].min()), 0, H - 1)), int(np.clip(np.ceil(q[:, 1].max()), 0, H - 1))
+        m = np.zeros((y1 - y0 + 1, x1 - x0 + 1), np.uint8)
+        cv2.fillPoly(m, [(q - np.array([x0, y0], np.float32)).astype(np.int32)], 1)
+        if cv2.mean(prob[y0:y1 + 1, x0:x1 + 1], m)[0] < BOX_THRESH:
+            continue
+        (cx, cy), (rw, rh), ang = rect
+        d = rw * rh * UNCLIP_RATIO / (2 * (rw + rh))
+        if min(rw, rh) + 2 * d < 5:
+            continue
+        g = _order_quad(cv2.boxPoints(((cx, cy), (rw + 2 * d, rh + 2 * d), ang)))
+        g[:, 0] = np.clip(np.round(g[:, 0] / W * src_w), 0, src_w)
+        g[:, 1] = np.clip(np.round(g[:, 1] / H * src_h), 0, src_h)
+        quads.append(g.astype(np.int16))
+    return np.array(quads, np.int16).reshape(-1, 4, 2)
