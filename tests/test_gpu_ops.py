@@ -88,6 +88,7 @@ def _attention_ref(q, k, v, patches):
     (3, 30, 160, 64, [(80, 15)], 1.0),         # 6 tokens x 76800 dims: split-K
     (5, 30, 160, 256, AUTO, 1.0),
     (5, 30, 160, 256, AUTO, 4.0),              # peaked softmax
+    (17, 30, 160, 128, [(10, 5), (5, 3)], 1.0), # 17-frame window: 5440-token rows (second softmax variant)
     (2, 60, 108, 256, [(108, 60), (36, 20), (18, 10), (9, 5)], 1.0),   # sttn-det geometry
 ])
 def test_patch_attention(ops, T, H, W, C, patches, sharp):

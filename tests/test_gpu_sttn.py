@@ -228,9 +228,8 @@ def test_whole_video_driver(rand_engine, tmp_path):
     assert any(not np.array_equal(out[i], decoded[i]) for i in range(10, 30))
 
 
-def test_non_default_schedule_and_long_chunk(capi):
-    """config.sttnNeighborStride / sttnReferenceLength are read at construction (sttn_auto_inpaint.py:40-41);
-    a 61-frame batch makes 17-frame windows (7 reference frames): 5440-token rows, second softmax variant."""
+def test_non_default_schedule(capi):
+    """config.sttnNeighborStride / sttnReferenceLength are read at construction (sttn_auto_inpaint.py:40-41)."""
     from vsr_b200 import STTNInpaint, config
 
     w = O.random_weights(0)
@@ -247,8 +246,3 @@ def test_non_default_schedule_and_long_chunk(capi):
         _check_images(got, want)
     finally:
         config.sttnNeighborStride.value, config.sttnReferenceLength.value = old
-    eng = STTNInpaint("cuda:0", wd)
-    H, W, T = 180, 320, 61
-    frames = O.synthetic_clip(T, H, W, seed=62)
-    mask = O.default_mask(H, W)
-    _check_images(eng(frames, mask), O.sttn_call(w, frames, mask))
