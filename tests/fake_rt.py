@@ -1,0 +1,129 @@
+"""CPU stand-in for the `vsr_rt_*` device runtime (test infrastructure, never shipped): implements the interface
+of `vsr_b200.dbnet._DeviceRuntime` with fp32 numpy/torch on NHWC buffers that have the SAME pitches, channel
+permutations and folded weights the graph compiler hands to the C ABI.  It lets `-m "not gpu"` tests check the
+compiler (constant folding, BN/bias/ReLU fusion, concat layout, padding rules) against the oracle's interpreter
+of the same program; the kernels themselves are checked on the GPU (tests/test_gpu_dbnet.py)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import dbnet_oracle as D
+
+
+class FakeRuntime:
+    def __init__(self, enforce_device_limits=True):
+        self.bufs, self.layers, self.launches = {}, [], 0
+        self.enforce = enforce_device_limits
+        self._next = 0x1000
+
+    def close(self):
+        self.bufs.clear()
+
+    def alloc(self, nbytes):
+        h = self._next
+        self._next += 0x1000
+        self.bufs[h] = np.zeros(int(nbytes) // 2, np.float32)   # one fp32 per fp16 element of the real buffer
+        return h
+
+    def upload_f32(self, arr):
+        h = self._next
+        self._next += 0x1000
+        self.bufs[h] = np.array(arr, np.float32)
+        return h
+
+    def _view(self, t):
+        return self.bufs[t.ptr][: t.h * t.w * t.cp].reshape(t.h, t.w, t.cp)
+
+    def conv_create(self, w, bias, cout, cin, cin_pitch, kh, kw, stride, pad_t, pad_l, dil, groups, transposed):
+        w = np.array(w, np.float32)
+        assert cin_pitch >= cin and cin_pitch % 8 == 0
+        if self.enforce:   # the restrictions of vsr_rt_conv_create (engine.cu), so that violations show up on the CPU
+            if transposed:
+                assert (kh, kw, stride, groups) == (2, 2, 2, 1) and w.shape == (cin, cout, 2, 2)
+            elif groups > 1:
+                assert groups == cin == cout and kh == kw and dil == 1 and w.shape == (cin, 1, kh, kw)
+                assert pad_t == pad_l
+            elif cin < 16 or cout < 8:
+                assert dil == 1 and w.shape == (cout, cin, kh, kw)
+            elif stride == 2:
+                assert (kh, kw, pad_t, pad_l, dil) == (3, 3, 1, 1, 1) and cin_pitch % 16 == 0 and cout % 8 == 0
+            else:
+                assert stride == 1 and cout % 8 == 0 and w.shape == (cout, cin, kh, kw)
+        self.layers.append(dict(w=torch.from_numpy(w), b=torch.from_numpy(np.array(bias, np.float32)), cout=cout, cin=cin, kh=kh, kw=kw,
+                                stride=stride, pad_t=pad_t, pad_l=pad_l, dil=dil, groups=groups, transposed=transposed))
+        return len(self.layers) - 1
+
+    def conv(self, lid, x, y, relu):
+        L = self.layers[lid]
+        xin = torch.from_numpy(self._view(x)[:, :, : L["cin"]].copy()).permute(2, 0, 1)[None]
+        if L["transposed"]:
+            out = F.conv_transpose2d(xin, L["w"], L["b"], stride=2)
+        else:
+            eff_h, eff_w = (L["kh"] - 1) * L["dil"] + 1, (L["kw"] - 1) * L["dil"] + 1
+            pad_b = max((y.h - 1) * L["stride"] + eff_h - x.h - L["pad_t"], 0)
+            pad_r = max((y.w - 1) * L["stride"] + eff_w - x.w - L["pad_l"], 0)
+            if self.enforce and L["stride"] == 2 and L["groups"] == 1 and L["cin"] >= 16:
+                assert x.h % 2 == 0 and x.w % 2 == 0
+            xin = F.pad(xin, (L["pad_l"], pad_r, L["pad_t"], pad_b))
+            out = F.conv2d(xin, L["w"], L["b"], stride=L["stride"], dilation=L["dil"], groups=L["groups"])
+        assert out.shape[2:] == (y.h, y.w), (out.shape, y.h, y.w)
+        if relu:
+            out = out.relu()
+        v = self._view(y)
+        v[:] = 0
+        v[:, :, : L["cout"]] = out[0].permute(1, 2, 0).numpy()
+        self.launches += 1
+
+    def elementwise(self, op, a, b, y, scale=0, shift=0, alpha=0.0, beta=0.0):
+        va = self._view(a)
+        vb = self._view(b) if b is not None else None
+        if op == 0:
+            r = va + vb
+        elif op == 1:
+            r = np.maximum(va, 0)
+        elif op == 2:
+            r = np.maximum(va + vb, 0)
+        elif op == 3:
+            r = 1.0 / (1.0 + np.exp(-va))
+        elif op in (4, 5):
+            r = va * self.bufs[scale][None, None, : a.cp] + self.bufs[shift][None, None, : a.cp]
+            if op == 5:
+                r = np.maximum(r, 0)
+        elif op == 6:
+            r = va * alpha + beta
+        elif op == 7:
+            r = (va + vb) * alpha
+        else:
+            raise AssertionError(op)
+        self._view(y)[:] = r
+        self.launches += 1
+
+    def upsample(self, x, y, s):
+        self._view(y)[:] = self._view(x).repeat(s, axis=0).repeat(s, axis=1)
+        self.launches += 1
+
+    def maxpool(self, x, y):   # 2x2 stride 1, SAME: pad 0 top/left, 1 bottom/right
+        v = self._view(x)
+        p = np.pad(v, ((0, 1), (0, 1), (0, 0)), constant_values=-np.inf)
+        self._view(y)[:] = np.maximum(np.maximum(p[:-1, :-1], p[1:, :-1]), np.maximum(p[:-1, 1:], p[1:, 1:]))
+        self.launches += 1
+
+    def copy_channels(self, src, dst, dst_off, channels):
+        assert channels % 8 == 0 and dst_off % 8 == 0 and dst_off + channels <= dst.cp and channels <= src.cp
+        self._view(dst)[:, :, dst_off:dst_off + channels] = self._view(src)[:, :, :channels]
+        self.launches += 1
+
+    def preprocess(self, img, inp, rh, rw):
+        x = D.preprocess(img)[0].permute(1, 2, 0).numpy()
+        assert x.shape[:2] == (rh, rw)
+        v = self._view(inp)
+        v[:] = 0
+        v[:, :, :3] = x
+        self.launches += 1
+
+    def download(self, t):
+        return self._view(t).copy()
+
+    @property
+    def launch_count(self):
+        return self.launches

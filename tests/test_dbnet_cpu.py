@@ -50,3 +50,23 @@ def test_oracle_forward_and_postprocess():
     assert np.array_equal(got, want) and len(want) == 1
     (xmin, xmax, ymin, ymax), = D.get_coordinates(want.tolist())
     assert 90 <= xmin <= 125 and 400 <= xmax <= 460 and 270 <= ymin <= 300 and 320 <= ymax <= 345
+
+
+@pytest.mark.parametrize("hw", [(96, 160), (64, 224)])
+def test_graph_compiler_on_cpu_runtime(hw):
+    """The PIR -> runtime compiler (BN / bias / ReLU folding, concat layout and channel permutations, SAME padding,
+    stride-2 and transposed convs) driven on a CPU stand-in of the device runtime equals the oracle interpreter."""
+    import cv2
+    from fake_rt import FakeRuntime
+    from vsr_b200.dbnet import TextDetector
+
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 255, hw + (3,), dtype=np.uint8)
+    cv2.putText(img, "Ab3", (10, hw[0] - 20), cv2.FONT_HERSHEY_SIMPLEX, 1.5, (255, 255, 255), 3)
+    rt = FakeRuntime()
+    det = TextDetector(MODEL_DIR, runtime=rt)
+    got = det.probability_map(img)
+    want = D.forward(D.Graph(MODEL_DIR), D.preprocess(img))[0, 0].numpy()
+    assert got.shape == want.shape == hw
+    assert np.abs(got - want).max() < 2e-4
+    assert rt.launch_count < 330   # 1052 PIR ops -> one launch per fused conv / add / pool / concat part

@@ -122,46 +122,96 @@ class _Compiled:
         self.out = None
 
 
-class TextDetector:
-    """Stand-in for `paddleocr.TextDetection(model_name, model_dir, device=...)` (subtitle_detect.py:47-52)."""
+class _DeviceRuntime:
+    """The `vsr_rt_*` C ABI behind a small interface, so that the graph compiler can also be driven by a CPU
+    stand-in in the tests (tests/fake_rt.py) and its folding / layout logic checked without a GPU."""
 
-    def __init__(self, model_dir: str, device="cuda:0", model_name: Optional[str] = None):
-        self.model_dir, self.model_name = model_dir, model_name
-        self._nodes, self._params = _load_program(model_dir)
+    def __init__(self, device):
         L = _capi.lib()
         h = C.c_void_p()
         _capi.check(L.vsr_rt_create(C.byref(h), _device_index(device)))
-        self._h = h
+        self.h, self.L = h, L
+
+    def close(self):
+        if self.h:
+            self.L.vsr_rt_destroy(self.h)
+            self.h = None
+
+    def alloc(self, nbytes: int) -> int:
+        p = C.c_uint64()
+        _capi.check(self.L.vsr_rt_alloc(self.h, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def upload_f32(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr, np.float32)
+        p = self.alloc(arr.nbytes)
+        _capi.check(self.L.vsr_rt_upload(self.h, p, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        return p
+
+    def conv_create(self, w, bias, cout, cin, cin_pitch, kh, kw, stride, pad_t, pad_l, dil, groups, transposed) -> int:
+        w = np.ascontiguousarray(w, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        lid = C.c_int32()
+        f32p = C.POINTER(C.c_float)
+        _capi.check(self.L.vsr_rt_conv_create(self.h, w.ctypes.data_as(f32p), bias.ctypes.data_as(f32p), cout, cin, cin_pitch, kh, kw, stride,
+                                              pad_t, pad_l, dil, groups, 1 if transposed else 0, C.byref(lid)))
+        return int(lid.value)
+
+    def conv(self, lid, x, y, relu):
+        _capi.check(self.L.vsr_rt_conv(self.h, lid, x.ptr, 1, x.h, x.w, y.ptr, y.cp, 0, relu))
+
+    def elementwise(self, op, a, b, y, scale=0, shift=0, alpha=0.0, beta=0.0):
+        _capi.check(self.L.vsr_rt_elementwise(self.h, op, a.ptr, b.ptr if b is not None else 0, y.ptr, a.pixels * a.cp, a.cp, scale, shift,
+                                              alpha, beta))
+
+    def upsample(self, x, y, s):
+        _capi.check(self.L.vsr_rt_upsample_nearest(self.h, x.ptr, 1, x.h, x.w, x.cp, s, y.ptr, y.cp, 0))
+
+    def maxpool(self, x, y):
+        _capi.check(self.L.vsr_rt_maxpool2x2s1(self.h, x.ptr, 1, x.h, x.w, x.cp, y.ptr))
+
+    def copy_channels(self, src, dst, dst_off, channels):
+        _capi.check(self.L.vsr_rt_copy_channels(self.h, src.ptr, src.cp, dst.ptr, dst.cp, dst_off, channels, src.pixels))
+
+    def preprocess(self, img, inp, rh, rw):
+        _capi.check(self.L.vsr_rt_det_preprocess(self.h, _capi.ptr(img, C.c_uint8), img.shape[0], img.shape[1], inp.ptr, rh, rw, inp.cp))
+
+    def download(self, t) -> np.ndarray:
+        host = np.empty((t.h, t.w, t.cp), np.float16)
+        _capi.check(self.L.vsr_rt_download(self.h, t.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))
+        return host
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.vsr_rt_launch_count(self.h))
+
+
+class TextDetector:
+    """Stand-in for `paddleocr.TextDetection(model_name, model_dir, device=...)` (subtitle_detect.py:47-52)."""
+
+    def __init__(self, model_dir: str, device="cuda:0", model_name: Optional[str] = None, runtime=None):
+        self.model_dir, self.model_name = model_dir, model_name
+        self._nodes, self._params = _load_program(model_dir)
+        self._rt = runtime if runtime is not None else _DeviceRuntime(device)
         self._programs: Dict[tuple, _Compiled] = {}
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
+        rt = getattr(self, "_rt", None)
+        if rt is not None:
             try:
-                _capi.lib().vsr_rt_destroy(h)
+                rt.close()
             except Exception:
                 pass
-            self._h = None
+            self._rt = None
 
     # -------------------------------------------------------------------------------------------- runtime helpers
-    def _alloc(self, nbytes: int) -> int:
-        p = C.c_uint64()
-        _capi.check(_capi.lib().vsr_rt_alloc(self._h, int(nbytes), C.byref(p)))
-        return int(p.value)
-
     def _new(self, c, h, w, perm=None) -> _Tensor:
         cp = _r(max(c, 1), 64)
-        return _Tensor(self._alloc(h * w * cp * 2), c, h, w, cp, perm)
-
-    def _upload_f32(self, arr: np.ndarray) -> int:
-        arr = np.ascontiguousarray(arr, np.float32)
-        p = self._alloc(arr.nbytes)
-        _capi.check(_capi.lib().vsr_rt_upload(self._h, p, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
-        return p
+        return _Tensor(self._rt.alloc(h * w * cp * 2), c, h, w, cp, perm)
 
     # -------------------------------------------------------------------------------------------- graph compiler
     def _compile(self, H: int, W: int) -> _Compiled:
-        L, rt = _capi.lib(), self._h
+        rt = self._rt
         nodes, params = self._nodes, self._params
         prod = {n.out: n for n in nodes if n.out is not None}
         users: Dict[int, List[_Node]] = {}
@@ -171,15 +221,25 @@ class TextDetector:
         val: Dict[int, object] = {}   # value id -> _Tensor | ndarray | python constant
         done = set()
         prog = _Compiled()
-        f32p = C.POINTER(C.c_float)
+        # constants first: the program lists `reshape(param)` bias operands AFTER the conv they are added to
+        for n in nodes:
+            if n.kind == "p":
+                val[n.out] = params[n.name]
+            elif n.kind in ("full_int_array", "full"):
+                val[n.out] = n.attrs["value"]
+            elif n.kind == "reshape" and isinstance(val.get(n.ins[0]), np.ndarray) and n.ins[1] in val:
+                val[n.out] = np.asarray(val[n.ins[0]]).reshape([int(d) for d in val[n.ins[1]]])
+            else:
+                continue
+            done.add(id(n))
 
         def single_user(v, kind):
             u = users.get(v, [])
             return u[0] if len(u) == 1 and u[0].kind == kind else None
 
         def const_of(v):
-            x = val[v]
-            return x if not isinstance(x, _Tensor) else None
+            x = val.get(v)
+            return x if x is not None and not isinstance(x, _Tensor) else None
 
         def bias_operand(add_node, act_id):
             """`add(x, reshape(param))`: the per-channel bias vector, else None."""
@@ -247,37 +307,24 @@ class TextDetector:
             else:
                 oh, ow = x.h, x.w
             y = self._new(cout, oh, ow)
-            lid = C.c_int32()
-            w = np.ascontiguousarray(w, np.float32)
-            _capi.check(L.vsr_rt_conv_create(rt, w.ctypes.data_as(f32p), bias.ctypes.data_as(f32p), cout, int(cin_eff), x.cp, kh, kw, stride,
-                                             pad_t, pad_l, dil, groups, 1 if transposed else 0, C.byref(lid)))
-            lid = int(lid.value)
-            prog.steps.append(lambda x=x, y=y, lid=lid, relu=relu: _capi.check(
-                L.vsr_rt_conv(rt, lid, x.ptr, 1, x.h, x.w, y.ptr, y.cp, 0, relu)))
+            lid = rt.conv_create(w, bias, cout, int(cin_eff), x.cp, kh, kw, stride, pad_t, pad_l, dil, groups, transposed)
+            prog.steps.append(lambda x=x, y=y, lid=lid, relu=relu: rt.conv(lid, x, y, relu))
             val[cur] = y
 
         def emit_elt(op, a: _Tensor, b: Optional[_Tensor], out_id, alpha=0.0, beta=0.0, scale=0, shift=0):
             y = self._new(a.c, a.h, a.w, a.perm)
-            prog.steps.append(lambda: _capi.check(L.vsr_rt_elementwise(rt, op, a.ptr, b.ptr if b else 0, y.ptr, a.pixels * a.cp, a.cp, scale,
-                                                                       shift, alpha, beta)))
+            prog.steps.append(lambda: rt.elementwise(op, a, b, y, scale, shift, alpha, beta))
             val[out_id] = y
 
         for n in nodes:
             if id(n) in done:
                 continue
             k = n.kind
-            if k == "p":
-                val[n.out] = self._params[n.name]
-            elif k == "data":
+            if k == "data":
                 prog.inp = self._new(3, H, W)
                 val[n.out] = prog.inp
-            elif k in ("full_int_array", "full"):
-                val[n.out] = n.attrs["value"]
             elif k == "reshape":
-                src = val[n.ins[0]]
-                if isinstance(src, _Tensor):
-                    raise _capi.VsrError("reshape of an activation is not supported")
-                val[n.out] = np.asarray(src).reshape([int(d) for d in val[n.ins[1]]])
+                raise _capi.VsrError("reshape of an activation is not supported")
             elif k == "combine":
                 val[n.out] = [val[i] for i in n.ins]
             elif k in ("conv2d", "depthwise_conv2d", "conv2d_transpose"):
@@ -294,7 +341,7 @@ class TextDetector:
                 if u is not None:
                     op, cur = 5, u.out
                     done.add(id(u))
-                emit_elt(op, x, None, cur, scale=self._upload_f32(sc), shift=self._upload_f32(sh))
+                emit_elt(op, x, None, cur, scale=rt.upload_f32(sc), shift=rt.upload_f32(sh))
             elif k == "relu":
                 emit_elt(1, val[n.ins[0]], None, n.out)
             elif k == "sigmoid":
@@ -317,7 +364,7 @@ class TextDetector:
                     idx = x.perm if x.perm is not None else np.arange(x.c)
                     sc[idx] = 1.0
                     sh[idx] = cst if cst.size == x.c else float(cst[0])
-                    emit_elt(4, x, None, n.out, scale=self._upload_f32(sc), shift=self._upload_f32(sh))
+                    emit_elt(4, x, None, n.out, scale=rt.upload_f32(sc), shift=rt.upload_f32(sh))
             elif k == "scale":
                 emit_elt(6, val[n.ins[0]], None, n.out, alpha=float(np.asarray(val[n.ins[1]]).reshape(-1)[0]), beta=float(n.attrs.get("bias", 0.0)))
             elif k == "concat":
@@ -336,17 +383,16 @@ class TextDetector:
                     src = p.perm if p.perm is not None else np.arange(p.c)
                     perm[lo:lo + p.c] = phys[i] + src
                     lo += p.c
-                y = _Tensor(self._alloc(parts[0].pixels * _r(off, 64) * 2), total, parts[0].h, parts[0].w, _r(off, 64),
+                y = _Tensor(rt.alloc(parts[0].pixels * _r(off, 64) * 2), total, parts[0].h, parts[0].w, _r(off, 64),
                             None if np.array_equal(perm, np.arange(total)) else perm)
                 for i, p in enumerate(parts):
-                    prog.steps.append(lambda p=p, dst=phys[i]: _capi.check(
-                        L.vsr_rt_copy_channels(rt, p.ptr, p.cp, y.ptr, y.cp, dst, _r(p.c, 8), p.pixels)))
+                    prog.steps.append(lambda p=p, y=y, dst=phys[i]: rt.copy_channels(p, y, dst, _r(p.c, 8)))
                 val[n.out] = y
             elif k == "nearest_interp":
                 x = val[n.ins[0]]
                 s = int(round(float((n.attrs.get("scale") or [2.0])[0])))
-                y = _Tensor(self._alloc(x.pixels * s * s * x.cp * 2), x.c, x.h * s, x.w * s, x.cp, x.perm)
-                prog.steps.append(lambda x=x, y=y, s=s: _capi.check(L.vsr_rt_upsample_nearest(rt, x.ptr, 1, x.h, x.w, x.cp, s, y.ptr, y.cp, 0)))
+                y = _Tensor(rt.alloc(x.pixels * s * s * x.cp * 2), x.c, x.h * s, x.w * s, x.cp, x.perm)
+                prog.steps.append(lambda x=x, y=y, s=s: rt.upsample(x, y, s))
                 val[n.out] = y
             elif k == "pool2d":
                 x = val[n.ins[0]]
@@ -355,7 +401,7 @@ class TextDetector:
                 if not (a["pooling_type"] == "max" and ks == [2, 2] and a["strides"] == [1, 1] and a["padding_algorithm"] == "SAME" and not a.get("adaptive")):
                     raise _capi.VsrError(f"unsupported pool2d {a} (the mobile detector's SE blocks are not compiled yet)")
                 y = self._new(x.c, x.h, x.w, x.perm)
-                prog.steps.append(lambda x=x, y=y: _capi.check(L.vsr_rt_maxpool2x2s1(rt, x.ptr, 1, x.h, x.w, x.cp, y.ptr)))
+                prog.steps.append(lambda x=x, y=y: rt.maxpool(x, y))
                 val[n.out] = y
             elif k == "fetch":
                 prog.out = val[n.ins[0]]
@@ -382,19 +428,17 @@ class TextDetector:
         prog = self._programs.get((rh, rw))
         if prog is None:
             prog = self._programs[(rh, rw)] = self._compile(rh, rw)
-        L = _capi.lib()
-        _capi.check(L.vsr_rt_det_preprocess(self._h, _capi.ptr(img, C.c_uint8), img.shape[0], img.shape[1], prog.inp.ptr, rh, rw, prog.inp.cp))
+        self._rt.preprocess(img, prog.inp, rh, rw)
         for step in prog.steps:
             step()
         out = prog.out
-        host = np.empty((out.h, out.w, out.cp), np.float16)
-        _capi.check(L.vsr_rt_download(self._h, out.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))
+        host = self._rt.download(out)
         ch = int(out.perm[0]) if out.perm is not None else 0
         return host[:, :, ch].astype(np.float32)
 
     @property
     def launch_count(self) -> int:
-        return int(_capi.lib().vsr_rt_launch_count(self._h))
+        return self._rt.launch_count
 
     def predict(self, img_bgr: np.ndarray):
         """Like paddleocr's TextDetection.predict: one result dict per image with `dt_polys` [N,4,2] int16."""
