@@ -136,8 +136,23 @@ int64_t vsr_rt_launch_count(vsr_rt_t* h);
  * implicit-GEMM kernel (stride 2 through space-to-depth), the rest on small direct kernels. */
 int vsr_rt_conv_create(vsr_rt_t* h, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw, int stride,
                        int pad_t, int pad_l, int dil, int groups, int transposed, int* layer_id);
-int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu);
-/* op: 0 add, 1 relu, 2 add+relu, 3 sigmoid, 4 per-channel affine, 5 affine+relu, 6 a*alpha+beta, 7 (a+b)*alpha */
+/* Per-tensor power-of-two scaling keeps un-normalised activations (the LKPAN neck reaches |x| ~ 1e5) inside fp16: a
+ * tensor stores value * s; the layer computes out = acc * alpha + bias * bias_scale with alpha = s_out / s_in and
+ * bias_scale = s_out (1, 1 for unscaled tensors).  Every scaled store that leaves fp16 raises the overflow flag. */
+int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu,
+                float alpha, float bias_scale);
+/* max |x| of a tensor (inf when it holds a non-finite value): calibration of the scales.  Synchronises. */
+int vsr_rt_absmax(vsr_rt_t* h, uint64_t dev_ptr, int64_t n_elems, float* out);
+/* reads and clears the overflow flag.  Synchronises. */
+int vsr_rt_overflow(vsr_rt_t* h, int* raised);
+/* Record the launches issued between begin and end into a CUDA graph and replay them with one call; every buffer a
+ * recorded launch touches must already exist (run the sequence once before capturing it). */
+int vsr_rt_capture_begin(vsr_rt_t* h);
+int vsr_rt_capture_end(vsr_rt_t* h, int* graph_id);
+int vsr_rt_graph_launch(vsr_rt_t* h, int graph_id);
+int vsr_rt_graph_destroy(vsr_rt_t* h, int graph_id);
+/* op: 0 a*alpha+b*beta, 1 relu, 2 relu(a*alpha+b*beta), 3 sigmoid(a*alpha), 4 per-channel affine, 5 affine+relu,
+ * 6 a*alpha+beta, 7 (a+b)*alpha */
 int vsr_rt_elementwise(vsr_rt_t* h, int op, uint64_t a, uint64_t b, uint64_t out, int64_t n_elems, int cp, uint64_t scale_dev,
                        uint64_t shift_dev, float alpha, float beta);   /* scale/shift: device fp32 [cp] (op 4, 5) */
 int vsr_rt_upsample_nearest(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, int scale, uint64_t out, int out_pitch, int out_coff);

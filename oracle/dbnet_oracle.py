@@ -113,8 +113,9 @@ def _same_pad(n, k, s, d=1):
     return max((out - 1) * s + (k - 1) * d + 1 - n, 0)
 
 
-def forward(graph: Graph, x: torch.Tensor, taps: Dict[str, torch.Tensor] | None = None) -> torch.Tensor:
-    """Execute the program on x [N,3,H,W] fp32 -> probability map [N,1,H,W] (op table: SURVEY A.6)."""
+def forward(graph: Graph, x: torch.Tensor, taps: Dict[str, torch.Tensor] | None = None, values: Dict[int, torch.Tensor] | None = None) -> torch.Tensor:
+    """Execute the program on x [N,3,H,W] fp32 -> probability map [N,1,H,W] (op table: SURVEY A.6).
+    `values`, when given, receives every activation by PIR value id (layer-by-layer diagnosis of the device path)."""
     v: Dict[int, object] = {}
     with torch.no_grad():
         for o in graph.ops:
@@ -187,6 +188,8 @@ def forward(graph: Graph, x: torch.Tensor, taps: Dict[str, torch.Tensor] | None 
                 raise NotImplementedError(kind)
             if oid is not None:
                 v[oid] = r
+                if values is not None and isinstance(r, torch.Tensor) and r.dim() == 4 and kind != "p":
+                    values[oid] = r
                 if taps is not None and isinstance(r, torch.Tensor) and "struct_name" in at and kind.startswith("1.conv"):
                     taps[f"{oid}:{at['struct_name']}"] = r
     raise RuntimeError("program has no fetch op")

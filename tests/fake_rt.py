@@ -15,17 +15,65 @@ class FakeRuntime:
         self.bufs, self.layers, self.launches = {}, [], 0
         self.enforce = enforce_device_limits
         self._next = 0x1000
+        self._flag = False
+        self._rec = None          # list of (method, args) while a capture is open
+        self.graphs = []
+        self.rescaled = 0         # absmax calls that reported a value above fp16
+
+    # ---- graph capture: like a CUDA stream capture, calls are recorded with their argument VALUES and not executed
+    def capture_begin(self):
+        assert self._rec is None
+        self._rec = []
+
+    def capture_end(self):
+        self.graphs.append(self._rec)
+        self._rec = None
+        return len(self.graphs) - 1
+
+    def graph_launch(self, g):
+        assert self._rec is None and self.graphs[g] is not None
+        for name, args, kw in self.graphs[g]:
+            getattr(self, name)(*args, **kw)
+
+    def graph_destroy(self, g):
+        self.graphs[g] = None
+
+    def _recording(self, name, *args, **kw):
+        if self._rec is None:
+            return False
+        self._rec.append((name, args, kw))
+        return True
+
+    def _store(self, y, values):
+        if np.abs(values).max(initial=0.0) > 65504.0 or not np.isfinite(values).all():
+            self._flag = True
+        self._view(y)[...] = values
+
+    def absmax(self, t):
+        assert self._rec is None
+        m = float(np.abs(self._view(t)).max())
+        if m > 65504.0:
+            self.rescaled += 1
+            return float("inf")    # what the fp16 buffer of the device would report
+        return m
+
+    def overflow(self):
+        assert self._rec is None
+        f, self._flag = self._flag, False
+        return f
 
     def close(self):
         self.bufs.clear()
 
     def alloc(self, nbytes):
+        assert self._rec is None, "allocation during graph capture"
         h = self._next
         self._next += 0x1000
         self.bufs[h] = np.zeros(int(nbytes) // 2, np.float32)   # one fp32 per fp16 element of the real buffer
         return h
 
     def upload_f32(self, arr):
+        assert self._rec is None, "upload during graph capture"
         h = self._next
         self._next += 0x1000
         self.bufs[h] = np.array(arr, np.float32)
@@ -53,11 +101,13 @@ class FakeRuntime:
                                 stride=stride, pad_t=pad_t, pad_l=pad_l, dil=dil, groups=groups, transposed=transposed))
         return len(self.layers) - 1
 
-    def conv(self, lid, x, y, relu):
+    def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0):
+        if self._recording("conv", lid, x, y, relu, alpha, bias_scale):
+            return
         L = self.layers[lid]
         xin = torch.from_numpy(self._view(x)[:, :, : L["cin"]].copy()).permute(2, 0, 1)[None]
         if L["transposed"]:
-            out = F.conv_transpose2d(xin, L["w"], L["b"], stride=2)
+            out = F.conv_transpose2d(xin, L["w"], None, stride=2)
         else:
             eff_h, eff_w = (L["kh"] - 1) * L["dil"] + 1, (L["kw"] - 1) * L["dil"] + 1
             pad_b = max((y.h - 1) * L["stride"] + eff_h - x.h - L["pad_t"], 0)
@@ -65,26 +115,30 @@ class FakeRuntime:
             if self.enforce and L["stride"] == 2 and L["groups"] == 1 and L["cin"] >= 16:
                 assert x.h % 2 == 0 and x.w % 2 == 0
             xin = F.pad(xin, (L["pad_l"], pad_r, L["pad_t"], pad_b))
-            out = F.conv2d(xin, L["w"], L["b"], stride=L["stride"], dilation=L["dil"], groups=L["groups"])
+            out = F.conv2d(xin, L["w"], None, stride=L["stride"], dilation=L["dil"], groups=L["groups"])
         assert out.shape[2:] == (y.h, y.w), (out.shape, y.h, y.w)
+        out = out * alpha + (L["b"] * bias_scale)[None, :, None, None]
         if relu:
             out = out.relu()
-        v = self._view(y)
-        v[:] = 0
-        v[:, :, : L["cout"]] = out[0].permute(1, 2, 0).numpy()
+        full = np.zeros((y.h, y.w, y.cp), np.float32)
+        full[:, :, : L["cout"]] = out[0].permute(1, 2, 0).numpy()
+        self._store(y, full)
         self.launches += 1
 
-    def elementwise(self, op, a, b, y, scale=0, shift=0, alpha=0.0, beta=0.0):
+    def elementwise(self, op, a, b, y, scale=0, shift=0, alpha=1.0, beta=1.0):
+        if self._recording("elementwise", op, a, b, y, scale, shift, alpha, beta):
+            return
         va = self._view(a)
         vb = self._view(b) if b is not None else None
         if op == 0:
-            r = va + vb
+            r = va * alpha + vb * beta
         elif op == 1:
             r = np.maximum(va, 0)
         elif op == 2:
-            r = np.maximum(va + vb, 0)
+            r = np.maximum(va * alpha + vb * beta, 0)
         elif op == 3:
-            r = 1.0 / (1.0 + np.exp(-va))
+            with np.errstate(over="ignore"):
+                r = 1.0 / (1.0 + np.exp(-va * alpha))
         elif op in (4, 5):
             r = va * self.bufs[scale][None, None, : a.cp] + self.bufs[shift][None, None, : a.cp]
             if op == 5:
@@ -95,25 +149,32 @@ class FakeRuntime:
             r = (va + vb) * alpha
         else:
             raise AssertionError(op)
-        self._view(y)[:] = r
+        self._store(y, r)
         self.launches += 1
 
     def upsample(self, x, y, s):
+        if self._recording("upsample", x, y, s):
+            return
         self._view(y)[:] = self._view(x).repeat(s, axis=0).repeat(s, axis=1)
         self.launches += 1
 
     def maxpool(self, x, y):   # 2x2 stride 1, SAME: pad 0 top/left, 1 bottom/right
+        if self._recording("maxpool", x, y):
+            return
         v = self._view(x)
         p = np.pad(v, ((0, 1), (0, 1), (0, 0)), constant_values=-np.inf)
         self._view(y)[:] = np.maximum(np.maximum(p[:-1, :-1], p[1:, :-1]), np.maximum(p[:-1, 1:], p[1:, 1:]))
         self.launches += 1
 
     def copy_channels(self, src, dst, dst_off, channels):
+        if self._recording("copy_channels", src, dst, dst_off, channels):
+            return
         assert channels % 8 == 0 and dst_off % 8 == 0 and dst_off + channels <= dst.cp and channels <= src.cp
         self._view(dst)[:, :, dst_off:dst_off + channels] = self._view(src)[:, :, :channels]
         self.launches += 1
 
     def preprocess(self, img, inp, rh, rw):
+        assert self._rec is None
         x = D.preprocess(img)[0].permute(1, 2, 0).numpy()
         assert x.shape[:2] == (rh, rw)
         v = self._view(inp)

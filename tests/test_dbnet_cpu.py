@@ -65,8 +65,28 @@ def test_graph_compiler_on_cpu_runtime(hw):
     cv2.putText(img, "Ab3", (10, hw[0] - 20), cv2.FONT_HERSHEY_SIMPLEX, 1.5, (255, 255, 255), 3)
     rt = FakeRuntime()
     det = TextDetector(MODEL_DIR, runtime=rt)
-    got = det.probability_map(img)
+    got = det.probability_map(img)           # first call: calibration of the tensor scales, layer by layer
     want = D.forward(D.Graph(MODEL_DIR), D.preprocess(img))[0, 0].numpy()
     assert got.shape == want.shape == hw
     assert np.abs(got - want).max() < 2e-4
-    assert rt.launch_count < 330   # 1052 PIR ops -> one launch per fused conv / add / pool / concat part
+    prog = det._programs[hw]
+    scales = sorted({t.scale for t in prog.values.values()})
+    assert rt.rescaled > 0 and scales[0] < 1.0 and scales[-1] == 1.0   # the neck does not fit fp16 unscaled
+    assert all(float(np.log2(s)).is_integer() for s in scales)
+    n0 = rt.launch_count
+    again = det.probability_map(img)         # second call: the recorded graph
+    assert np.array_equal(again, got)
+    assert rt.launch_count - n0 < 330        # 1052 PIR ops -> one launch per fused conv / add / pool / concat part
+    # scales that are too large for a frame (here: tampered with) overflow fp16 in the recorded graph -> the flag of the
+    # scaled epilogues -> recalibration on that frame, still the right answer
+    for t in prog.values.values():
+        if t.follow is None and t.scale < 1.0:
+            t.scale = min(t.scale * 4096.0, 1.0)
+    rt.capture_begin()
+    for st in prog.steps:
+        st.run(rt)
+    prog.graph = rt.capture_end()
+    n1 = rt.launch_count
+    third = det.probability_map(img)
+    assert rt.launch_count - n1 > 400        # the graph run plus the layer-by-layer recalibration
+    assert np.abs(third - want).max() < 2e-4

@@ -86,7 +86,14 @@ _PROTOS = {
     "vsr_rt_launch_count": (C.c_int64, [C.c_void_p]),
     "vsr_rt_conv_create": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_int, _i32p]),
-    "vsr_rt_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]),
+    "vsr_rt_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
+                              C.c_float]),
+    "vsr_rt_absmax": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.POINTER(C.c_float)]),
+    "vsr_rt_overflow": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "vsr_rt_capture_begin": (C.c_int, [C.c_void_p]),
+    "vsr_rt_capture_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "vsr_rt_graph_launch": (C.c_int, [C.c_void_p, C.c_int]),
+    "vsr_rt_graph_destroy": (C.c_int, [C.c_void_p, C.c_int]),
     "vsr_rt_elementwise": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_uint64, C.c_uint64,
                                      C.c_float, C.c_float]),
     "vsr_rt_upsample_nearest": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int]),

@@ -16,6 +16,7 @@ enum ConvFlags : int {
   CONV_RESIDUAL = 2,   // act += res32 (fp32) before the stores; out32 (if set) gets the fp32 value, out16 its fp16 rounding
   CONV_S2D_STORE = 4,  // store out16 space-to-depth: [T, H/2, W/2, 4*Cout], channel = (y&1)*2*Cout + (x&1)*Cout + c
   CONV_RELU = 0x100,   // plain ReLU after bias (graph runtime)
+  CONV_SCALED = 0x200, // out = acc * alpha + bias * bias_scale, fp16 overflow reported through *overflow (graph runtime)
   CONV_FINAL = 8,      // decoder.6: tanh -> (x+1)/2*255 -> trunc u8 -> first visit store / 0.5-0.5 blend into comps
 };
 
@@ -43,6 +44,10 @@ struct ConvParams {
   // sttn-det low-res composite (sttn_det_inpaint.py:168): comp = mask>0 ? pred : input frame (RGB)
   const uint8_t* det_mask;  // [H,W] resized mask, nullptr for sttn-auto
   const uchar4* det_rgb;    // [chunk_T,H,W] RGBA8 input frames at model resolution
+  // CONV_SCALED (graph runtime, rt_ops.cuh RtScale): out = acc * alpha + bias * bias_scale; *overflow = 1 when a
+  // stored fp16 value leaves the format
+  float alpha, bias_scale;
+  int* overflow;
 };
 
 template <int BN_>
@@ -117,10 +122,21 @@ struct ConvPolicy {
     if (!c.valid) return;
     constexpr int NV = (BN >= 32) ? 32 : 16;
     const int ch0 = t.n0 + col0;
+    if (p.flags & CONV_SCALED) {
 #pragma unroll
-    for (int i = 0; i < NV; i += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(p.bias + ch0 + i);
-      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      for (int i = 0; i < NV; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + ch0 + i);
+        v[i] = fmaf(v[i], p.alpha, b.x * p.bias_scale);
+        v[i + 1] = fmaf(v[i + 1], p.alpha, b.y * p.bias_scale);
+        v[i + 2] = fmaf(v[i + 2], p.alpha, b.z * p.bias_scale);
+        v[i + 3] = fmaf(v[i + 3], p.alpha, b.w * p.bias_scale);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + ch0 + i);
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
     }
     if (p.flags & CONV_LRELU) {
 #pragma unroll
@@ -129,6 +145,12 @@ struct ConvPolicy {
     if (p.flags & CONV_RELU) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if ((p.flags & CONV_SCALED) && p.overflow) {
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) bad |= !(fabsf(v[i]) <= 65504.f);
+      if (bad) *p.overflow = 1;
     }
     if (p.flags & CONV_FINAL) {
       if (col0 != 0) return;

@@ -337,6 +337,8 @@ struct ConvIO {
   const int* first_visit = nullptr;
   const uint8_t* det_mask = nullptr;
   const uchar4* det_rgb = nullptr;
+  float alpha = 1.f, bias_scale = 1.f;  // CONV_SCALED (graph runtime)
+  int* overflow = nullptr;
 };
 
 static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
@@ -379,6 +381,9 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   p.first_visit = io.first_visit;
   p.det_mask = io.det_mask;
   p.det_rgb = io.det_rgb;
+  p.alpha = io.alpha;
+  p.bias_scale = io.bias_scale;
+  p.overflow = io.overflow;
   if (io.flags & CONV_S2D_STORE) {
     REQUIRE(io.H % 2 == 0 && io.W % 2 == 0, "s2d store needs even H, W");
     p.out16_pitch = 4 * L.cout;
@@ -1185,6 +1190,7 @@ struct RtLayer {
   enum Kind { DENSE, DENSE_S2, DEPTHWISE, DIRECT, DECONV } kind = DENSE;
   ConvLayer tc;          // DENSE / DENSE_S2
   DevBuf w32, b32;       // DEPTHWISE / DIRECT / DECONV
+  std::map<size_t, std::unique_ptr<DevBuf>> s2d;  // DENSE_S2: space-to-depth staging per input size (stable addresses for graphs)
   int cin = 0, cout = 0, cin_pitch = 0, cout_pitch = 0, kh = 0, kw = 0, stride = 1, pad_t = 0, pad_l = 0;
 };
 
@@ -1192,8 +1198,16 @@ struct vsr_rt {
   Ctx ctx;
   std::vector<std::unique_ptr<DevBuf>> bufs;
   std::vector<std::unique_ptr<RtLayer>> layers;
-  DevBuf scratch;  // space-to-depth staging of the stride-2 convs
+  DevBuf image;    // BGR u8 staging of the pre-processing
+  DevBuf flag;     // [0] int overflow flag raised by the scaled epilogues, [1] uint absmax bits
   DevTaps px, py;  // resize tables of the pre-processing
+  std::vector<cudaGraphExec_t> graphs;
+  bool capturing = false;
+  int* overflow() { return flag.as<int>(); }
+  ~vsr_rt() {
+    for (auto g : graphs)
+      if (g) cudaGraphExecDestroy(g);
+  }
 };
 
 namespace vsr {
@@ -1554,6 +1568,7 @@ int vsr_rt_create(vsr_rt_t** out, int device) {
     h->ctx.sms = prop.multiProcessorCount;
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
+    h->flag.ensure(16);
     *out = h;
   });
 }
@@ -1595,6 +1610,80 @@ int vsr_rt_sync(vsr_rt_t* h) {
   });
 }
 int64_t vsr_rt_launch_count(vsr_rt_t* h) { return h ? h->ctx.launches : 0; }
+
+int vsr_rt_absmax(vsr_rt_t* h, uint64_t dev_ptr, int64_t n_elems, float* out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(out && n_elems > 0 && n_elems % 8 == 0 && !h->capturing, "bad arguments");
+    unsigned int* slot = h->flag.as<unsigned int>() + 1;
+    cudaStream_t s = h->ctx.stream;
+    CK(cudaMemsetAsync(slot, 0, 4, s));
+    const size_t n8 = (size_t)n_elems / 8;
+    rt_absmax_kernel<<<(unsigned)std::min<size_t>((n8 + 255) / 256, (size_t)h->ctx.sms * 8), 256, 0, s>>>((const __half*)(uintptr_t)dev_ptr, n8, slot);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+    unsigned int bits = 0;
+    CK(cudaMemcpyAsync(&bits, slot, 4, cudaMemcpyDeviceToHost, s));
+    rt_sync(h);
+    memcpy(out, &bits, 4);
+  });
+}
+
+int vsr_rt_overflow(vsr_rt_t* h, int* raised) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(raised && !h->capturing, "bad arguments");
+    cudaStream_t s = h->ctx.stream;
+    CK(cudaMemcpyAsync(raised, h->overflow(), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemsetAsync(h->overflow(), 0, 4, s));
+    rt_sync(h);
+  });
+}
+
+int vsr_rt_capture_begin(vsr_rt_t* h) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(!h->capturing, "capture already in progress");
+    CK(cudaStreamBeginCapture(h->ctx.stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
+  });
+}
+
+int vsr_rt_capture_end(vsr_rt_t* h, int* graph_id) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(h->capturing && graph_id, "no capture in progress");
+    h->capturing = false;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamEndCapture(h->ctx.stream, &g));
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    CK(e);
+    *graph_id = (int)h->graphs.size();
+    h->graphs.push_back(ex);
+  });
+}
+
+int vsr_rt_graph_launch(vsr_rt_t* h, int graph_id) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(graph_id >= 0 && graph_id < (int)h->graphs.size() && h->graphs[graph_id], "graph id");
+    CK(cudaGraphLaunch(h->graphs[graph_id], h->ctx.stream));
+  });
+}
+
+int vsr_rt_graph_destroy(vsr_rt_t* h, int graph_id) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(graph_id >= 0 && graph_id < (int)h->graphs.size(), "graph id");
+    if (h->graphs[graph_id]) {
+      rt_sync(h);
+      cudaGraphExecDestroy(h->graphs[graph_id]);
+      h->graphs[graph_id] = nullptr;
+    }
+  });
+}
 
 int vsr_rt_conv_create(vsr_rt_t* h, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw, int stride,
                        int pad_t, int pad_l, int dil, int groups, int transposed, int* layer_id) {
@@ -1655,7 +1744,8 @@ int vsr_rt_conv_create(vsr_rt_t* h, const float* w, const float* bias, int cout,
   });
 }
 
-int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu) {
+int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu,
+                float alpha, float bias_scale) {
   return guarded([&] {
     rt_check(h);
     REQUIRE(layer_id >= 0 && layer_id < (int)h->layers.size(), "layer id");
@@ -1664,23 +1754,32 @@ int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W,
     __half* out = (__half*)(uintptr_t)out_ptr;
     cudaStream_t s = h->ctx.stream;
     Ctx& c = h->ctx;
+    const RtScale sc{alpha, bias_scale, h->overflow()};
+    const int tc_flags = (relu ? CONV_RELU : 0) | CONV_SCALED;
     switch (L.kind) {
       case RtLayer::DENSE: {
         ConvIO io;
-        io.in = in; io.T = T; io.H = H; io.W = W; io.flags = relu ? 0x100 : 0; io.out16 = out; io.out16_pitch = out_pitch; io.out16_coff = out_coff;
+        io.in = in; io.T = T; io.H = H; io.W = W; io.flags = tc_flags; io.out16 = out; io.out16_pitch = out_pitch; io.out16_coff = out_coff;
+        io.alpha = alpha; io.bias_scale = bias_scale; io.overflow = sc.overflow;
         run_conv(c, L.tc, io);
         break;
       }
       case RtLayer::DENSE_S2: {
         REQUIRE(H % 2 == 0 && W % 2 == 0, "stride-2 conv needs even input size");
         const size_t n = (size_t)T * H * W * L.cin_pitch;
-        h->scratch.ensure(n * 2);
-        rt_space_to_depth_kernel<<<blocks_for(n / 8), 256, 0, s>>>(in, T, H, W, L.cin_pitch, h->scratch.as<__half>());
+        auto& stage = L.s2d[n];
+        if (!stage) {
+          REQUIRE(!h->capturing, "stride-2 conv staging must be allocated by a run before graph capture");
+          stage = std::make_unique<DevBuf>();
+          stage->ensure(n * 2);
+        }
+        rt_space_to_depth_kernel<<<blocks_for(n / 8), 256, 0, s>>>(in, T, H, W, L.cin_pitch, stage->as<__half>());
         CK(cudaGetLastError());
         ++c.launches;
         ConvIO io;
-        io.in = h->scratch.as<__half>(); io.T = T; io.H = H / 2; io.W = W / 2; io.flags = relu ? 0x100 : 0; io.out16 = out;
+        io.in = stage->as<__half>(); io.T = T; io.H = H / 2; io.W = W / 2; io.flags = tc_flags; io.out16 = out;
         io.out16_pitch = out_pitch; io.out16_coff = out_coff;
+        io.alpha = alpha; io.bias_scale = bias_scale; io.overflow = sc.overflow;
         run_conv(c, L.tc, io);
         break;
       }
@@ -1689,7 +1788,7 @@ int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W,
         const int OH = (H + 2 * L.pad_t - L.kh) / L.stride + 1, OW = (W + 2 * L.pad_l - L.kw) / L.stride + 1;
         const size_t n = (size_t)T * OH * OW * (L.cin_pitch / 8);
         rt_depthwise_kernel<<<blocks_for(n), 256, 0, s>>>(in, T, H, W, L.cin_pitch, L.w32.as<float>(), L.b32.as<float>(), L.kh, L.stride, L.pad_t,
-                                                          relu, out, OH, OW);
+                                                          relu, out, OH, OW, sc);
         CK(cudaGetLastError());
         ++c.launches;
         break;
@@ -1699,7 +1798,7 @@ int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W,
         const int OH = (H + 2 * L.pad_t - L.kh) / L.stride + 1, OW = (W + 2 * L.pad_l - L.kw) / L.stride + 1;
         const size_t n = (size_t)T * OH * OW * (L.cout_pitch / 8);
         rt_direct_conv_kernel<<<blocks_for(n), 256, 0, s>>>(in, T, H, W, L.cin_pitch, L.cin, L.w32.as<float>(), L.b32.as<float>(), L.kh, L.kw,
-                                                            L.stride, L.pad_t, L.pad_l, relu, out, OH, OW, L.cout_pitch, out_pitch);
+                                                            L.stride, L.pad_t, L.pad_l, relu, out, OH, OW, L.cout_pitch, out_pitch, sc);
         CK(cudaGetLastError());
         ++c.launches;
         break;
@@ -1708,7 +1807,7 @@ int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W,
         REQUIRE(out_coff == 0 && out_pitch >= L.cout_pitch && out_pitch % 8 == 0, "deconv output pitch");
         const size_t n = (size_t)T * 2 * H * 2 * W * (L.cout_pitch / 8);
         rt_deconv2x2_kernel<<<blocks_for(n), 256, 0, s>>>(in, T, H, W, L.cin_pitch, L.cin, L.w32.as<float>(), L.b32.as<float>(), relu, out,
-                                                          L.cout_pitch, out_pitch);
+                                                          L.cout_pitch, out_pitch, sc);
         CK(cudaGetLastError());
         ++c.launches;
         break;
@@ -1725,7 +1824,7 @@ int vsr_rt_elementwise(vsr_rt_t* h, int op, uint64_t a, uint64_t b, uint64_t out
     if (op == RT_AFFINE || op == RT_AFFINE_RELU) REQUIRE(scale_dev && shift_dev, "affine needs device scale and shift [cp] fp32");
     rt_elementwise_kernel<<<blocks_for((size_t)n_elems / 8), 256, 0, h->ctx.stream>>>(
         op, (const __half*)(uintptr_t)a, (const __half*)(uintptr_t)b, (__half*)(uintptr_t)out, (size_t)n_elems / 8, cp,
-        (const float*)(uintptr_t)scale_dev, (const float*)(uintptr_t)shift_dev, alpha, beta);
+        (const float*)(uintptr_t)scale_dev, (const float*)(uintptr_t)shift_dev, alpha, beta, h->overflow());
     CK(cudaGetLastError());
     ++h->ctx.launches;
   });
@@ -1769,12 +1868,12 @@ int vsr_rt_det_preprocess(vsr_rt_t* h, const uint8_t* bgr, int sh, int sw, uint6
     rt_check(h);
     REQUIRE(bgr && sh > 0 && sw > 0 && dh > 0 && dw > 0 && cp >= 8, "bad arguments");
     cudaStream_t s = h->ctx.stream;
-    h->scratch.ensure((size_t)sh * sw * 3);
-    CK(cudaMemcpyAsync(h->scratch.p, bgr, (size_t)sh * sw * 3, cudaMemcpyHostToDevice, s));
+    h->image.ensure((size_t)sh * sw * 3);
+    CK(cudaMemcpyAsync(h->image.p, bgr, (size_t)sh * sw * 3, cudaMemcpyHostToDevice, s));
     h->px.build(sw, dw, false, s);
     h->py.build(sh, dh, true, s);
     CK(cudaMemsetAsync((void*)(uintptr_t)out, 0, (size_t)dh * dw * cp * 2, s));
-    rt_det_preprocess_kernel<<<dim3((dw + 255) / 256, dh), 256, 0, s>>>(h->scratch.as<uint8_t>(), sw, sh, (__half*)(uintptr_t)out, dw, dh, cp,
+    rt_det_preprocess_kernel<<<dim3((dw + 255) / 256, dh), 256, 0, s>>>(h->image.as<uint8_t>(), sw, sh, (__half*)(uintptr_t)out, dw, dh, cp,
                                                                        h->px.i0.as<int>(), h->px.i1.as<int>(), h->px.w0.as<short>(),
                                                                        h->px.w1.as<short>(), h->py.i0.as<int>(), h->py.i1.as<int>(),
                                                                        h->py.w0.as<short>(), h->py.w1.as<short>());

@@ -14,11 +14,34 @@ namespace vsr {
 enum RtEltOp : int { RT_ADD = 0, RT_RELU = 1, RT_ADD_RELU = 2, RT_SIGMOID = 3, RT_AFFINE = 4, RT_AFFINE_RELU = 5, RT_SCALE = 6,
                      RT_AVG2 = 7 };
 
-// 8 channels per thread.  a, b, out may alias.  AFFINE: out = a*scale[c] + shift[c]; SCALE: out = a*alpha + beta;
-// AVG2: out = (a + b) * alpha.
+// Per-tensor power-of-two scaling: a tensor stores value * s so that networks without normalisation
+// (the detector's LKPAN neck reaches |x| ~ 1e5) stay inside fp16.  A layer computes out = acc * alpha + bias *
+// bias_scale with alpha = s_out / s_in, bias_scale = s_out, and raises *overflow when a stored value leaves fp16.
+struct RtScale {
+  float alpha, bias_scale;
+  int* overflow;
+};
+
+__device__ __forceinline__ void rt_store8(const float* acc, const float* __restrict__ bias, const RtScale& sc, int relu, __half* dst) {
+  __align__(16) __half2 o[4];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = fmaf(acc[2 * j], sc.alpha, bias[2 * j] * sc.bias_scale);
+    float b = fmaf(acc[2 * j + 1], sc.alpha, bias[2 * j + 1] * sc.bias_scale);
+    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    bad |= !(fabsf(a) <= 65504.f) | !(fabsf(b) <= 65504.f);
+    o[j] = __floats2half2_rn(a, b);
+  }
+  if (bad && sc.overflow) *sc.overflow = 1;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+}
+
+// 8 channels per thread.  a, b, out may alias.  ADD / ADD_RELU: out = a*alpha + b*beta (operands at different scales);
+// SIGMOID: out = sigmoid(a*alpha); AFFINE: out = a*scale[c] + shift[c]; SCALE: out = a*alpha + beta; AVG2: out = (a + b) * alpha.
 __global__ void __launch_bounds__(256) rt_elementwise_kernel(int op, const __half* __restrict__ a, const __half* __restrict__ b,
                                                              __half* __restrict__ out, size_t n8, int cp, const float* __restrict__ scale,
-                                                             const float* __restrict__ shift, float alpha, float beta) {
+                                                             const float* __restrict__ shift, float alpha, float beta, int* overflow) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const uint4 va = reinterpret_cast<const uint4*>(a)[i];
@@ -28,15 +51,16 @@ __global__ void __launch_bounds__(256) rt_elementwise_kernel(int op, const __hal
   const __half2* pb = reinterpret_cast<const __half2*>(&vb);
   const int c0 = (int)((i * 8) % (size_t)cp);
   __align__(16) __half2 o[4];
+  bool bad = false;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float2 x = __half22float2(pa[j]);
     const float2 y = __half22float2(pb[j]);
     switch (op) {
-      case RT_ADD: x.x += y.x; x.y += y.y; break;
+      case RT_ADD: x.x = fmaf(x.x, alpha, y.x * beta); x.y = fmaf(x.y, alpha, y.y * beta); break;
       case RT_RELU: x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); break;
-      case RT_ADD_RELU: x.x = fmaxf(x.x + y.x, 0.f); x.y = fmaxf(x.y + y.y, 0.f); break;
-      case RT_SIGMOID: x.x = 1.f / (1.f + __expf(-x.x)); x.y = 1.f / (1.f + __expf(-x.y)); break;
+      case RT_ADD_RELU: x.x = fmaxf(fmaf(x.x, alpha, y.x * beta), 0.f); x.y = fmaxf(fmaf(x.y, alpha, y.y * beta), 0.f); break;
+      case RT_SIGMOID: x.x = 1.f / (1.f + __expf(-x.x * alpha)); x.y = 1.f / (1.f + __expf(-x.y * alpha)); break;
       case RT_AFFINE:
       case RT_AFFINE_RELU:
         x.x = x.x * scale[c0 + 2 * j] + shift[c0 + 2 * j];
@@ -46,9 +70,32 @@ __global__ void __launch_bounds__(256) rt_elementwise_kernel(int op, const __hal
       case RT_SCALE: x.x = x.x * alpha + beta; x.y = x.y * alpha + beta; break;
       case RT_AVG2: x.x = (x.x + y.x) * alpha; x.y = (x.y + y.y) * alpha; break;
     }
+    bad |= !(fabsf(x.x) <= 65504.f) | !(fabsf(x.y) <= 65504.f);
     o[j] = __floats2half2_rn(x.x, x.y);
   }
+  if (bad && overflow) *overflow = 1;
   reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
+}
+
+// max |x| over a tensor (calibration of the per-tensor scales): *out is the bit pattern of a non-negative float, so
+// an unsigned atomicMax orders it; inf / NaN patterns compare above every finite value.
+__global__ void __launch_bounds__(256) rt_absmax_kernel(const __half* __restrict__ x, size_t n8, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+    const __half2* pv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(pv[j]);
+      bad |= !(fabsf(f.x) <= 65504.f) | !(fabsf(f.y) <= 65504.f);
+      m = fmaxf(m, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  if (bad) m = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
 // nearest_interp (align_corners False) by an integer factor: out[y][x] = in[y / s][x / s].
@@ -127,7 +174,7 @@ __global__ void __launch_bounds__(256) rt_space_to_depth_kernel(const __half* __
 // bias [cp]; 8 channels per thread, fp32 accumulation; optional ReLU.
 __global__ void __launch_bounds__(256) rt_depthwise_kernel(const __half* __restrict__ in, int T, int H, int W, int cp,
                                                            const float* __restrict__ wgt, const float* __restrict__ bias, int k, int stride,
-                                                           int pad, int relu, __half* __restrict__ out, int OH, int OW) {
+                                                           int pad, int relu, __half* __restrict__ out, int OH, int OW, RtScale sc) {
   const int c8n = cp >> 3;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)T * OH * OW * c8n;
@@ -140,7 +187,7 @@ __global__ void __launch_bounds__(256) rt_depthwise_kernel(const __half* __restr
   const int t = r / OH;
   float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bias[c8 * 8 + j];
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (int ky = 0; ky < k; ++ky) {
     const int iy = oy * stride + ky - pad;
     if (iy < 0 || iy >= H) continue;
@@ -158,14 +205,7 @@ __global__ void __launch_bounds__(256) rt_depthwise_kernel(const __half* __restr
       }
     }
   }
-  __align__(16) __half2 o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float a = acc[2 * j], b = acc[2 * j + 1];
-    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-    o[j] = __floats2half2_rn(a, b);
-  }
-  *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(o);
+  rt_store8(acc, bias + c8 * 8, sc, relu, out + idx * 8);
 }
 
 // Direct conv for tiny channel counts on either side (the 3-channel stem, the 64->1 head): one thread per
@@ -173,7 +213,7 @@ __global__ void __launch_bounds__(256) rt_depthwise_kernel(const __half* __restr
 __global__ void __launch_bounds__(256) rt_direct_conv_kernel(const __half* __restrict__ in, int T, int H, int W, int cin_p, int cin,
                                                              const float* __restrict__ wgt, const float* __restrict__ bias, int kh, int kw,
                                                              int stride, int pad_t, int pad_l, int relu, __half* __restrict__ out, int OH,
-                                                             int OW, int cout_p, int out_pitch) {
+                                                             int OW, int cout_p, int out_pitch, RtScale sc) {
   const int c8n = cout_p >> 3;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)T * OH * OW * c8n;
@@ -186,7 +226,7 @@ __global__ void __launch_bounds__(256) rt_direct_conv_kernel(const __half* __res
   const int t = r / OH;
   float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bias[c8 * 8 + j];
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (int ky = 0; ky < kh; ++ky) {
     const int iy = oy * stride + ky - pad_t;
     if (iy < 0 || iy >= H) continue;
@@ -202,21 +242,14 @@ __global__ void __launch_bounds__(256) rt_direct_conv_kernel(const __half* __res
       }
     }
   }
-  __align__(16) __half2 o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float a = acc[2 * j], b = acc[2 * j + 1];
-    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-    o[j] = __floats2half2_rn(a, b);
-  }
-  *reinterpret_cast<uint4*>(out + (idx / c8n) * out_pitch + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+  rt_store8(acc, bias + c8 * 8, sc, relu, out + (idx / c8n) * out_pitch + c8 * 8);
 }
 
 // conv2d_transpose 2x2 stride 2 (no overlap): out[2y+dy][2x+dx][co] = bias[co] + sum_ci in[y][x][ci] * w[ci][co][dy][dx].
 // weights repacked as [dy*2+dx][cin][cout_p] fp32.  One thread per (output pixel, 8 output channels).
 __global__ void __launch_bounds__(256) rt_deconv2x2_kernel(const __half* __restrict__ in, int T, int H, int W, int cin_p, int cin,
                                                            const float* __restrict__ wgt, const float* __restrict__ bias, int relu,
-                                                           __half* __restrict__ out, int cout_p, int out_pitch) {
+                                                           __half* __restrict__ out, int cout_p, int out_pitch, RtScale sc) {
   const int c8n = cout_p >> 3;
   const int OH = 2 * H, OW = 2 * W;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,20 +265,13 @@ __global__ void __launch_bounds__(256) rt_deconv2x2_kernel(const __half* __restr
   const float* wr = wgt + (size_t)(((oy & 1) * 2 + (ox & 1)) * cin) * cout_p + c8 * 8;
   float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bias[c8 * 8 + j];
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (int ci = 0; ci < cin; ++ci) {
     const float v = __half2float(px[ci]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[(size_t)ci * cout_p + j], acc[j]);
   }
-  __align__(16) __half2 o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float a = acc[2 * j], b = acc[2 * j + 1];
-    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-    o[j] = __floats2half2_rn(a, b);
-  }
-  *reinterpret_cast<uint4*>(out + (idx / c8n) * out_pitch + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+  rt_store8(acc, bias + c8 * 8, sc, relu, out + (idx / c8n) * out_pitch + c8 * 8);
 }
 
 // DetResizeForTest + NormalizeImage + ToCHW of the detector (inference.yml:22-40): BGR u8 [sh,sw,3] ->

@@ -23,6 +23,7 @@ from . import _capi
 from .sttn_auto_inpaint import _device_index
 
 THRESH, BOX_THRESH, MAX_CANDIDATES, UNCLIP_RATIO, RESIZE_LONG = 0.3, 0.6, 1000, 1.5, 960  # inference.yml:22-53
+_STORE_LIMIT, _STORE_TARGET = 4096.0, 1024.0   # fp16 storage: rescale a tensor above LIMIT so that its max lands near TARGET
 
 
 # ------------------------------------------------------------------------------------------------ model files
@@ -105,21 +106,120 @@ def _r(x, m):
 
 
 class _Tensor:
-    """NHWC fp16 device tensor; `c` real channels, pitch `cp`; `perm[l]` = physical channel of logical channel l."""
+    """NHWC fp16 device tensor; `c` real channels, pitch `cp`; `perm[l]` = physical channel of logical channel l.
+    The buffer holds value * scale (a power of two, see `_calibrate`); `follow` ties the scale to another tensor's
+    (ReLU, pooling, up-sampling and concat are positively homogeneous: they keep the scale of their input)."""
 
-    def __init__(self, ptr, c, h, w, cp, perm=None):
+    def __init__(self, ptr, c, h, w, cp, perm=None, follow=None):
         self.ptr, self.c, self.h, self.w, self.cp, self.perm = ptr, c, h, w, cp, perm
+        self._scale, self.follow = 1.0, follow
 
     @property
     def pixels(self):
         return self.h * self.w
 
+    @property
+    def scale(self):
+        return self.follow.scale if self.follow is not None else self._scale
+
+    @scale.setter
+    def scale(self, v):
+        if self.follow is not None:
+            raise _capi.VsrError("the scale of this tensor is tied to its producer's input")
+        self._scale = float(v)
+
+
+class _Conv:
+    """conv (+ folded bias / BN / ReLU): stored out = acc * (s_out / s_in) + bias * s_out."""
+    rescalable = True
+
+    def __init__(self, lid, x, y, relu):
+        self.lid, self.x, self.y, self.relu = lid, x, y, relu
+
+    def run(self, rt):
+        rt.conv(self.lid, self.x, self.y, self.relu, self.y.scale / self.x.scale, self.y.scale)
+
+
+class _Add:
+    """a + b (+ ReLU) of two activations that may sit at different scales."""
+    rescalable = True
+
+    def __init__(self, op, a, b, y):
+        self.op, self.a, self.b, self.y = op, a, b, y
+
+    def run(self, rt):
+        rt.elementwise(self.op, self.a, self.b, self.y, alpha=self.y.scale / self.a.scale, beta=self.y.scale / self.b.scale)
+
+
+class _Unary:
+    """relu (op 1, output follows the input scale), sigmoid (op 3, output at scale 1), x*alpha+beta (op 6)."""
+    rescalable = False
+
+    def __init__(self, op, x, y, alpha=1.0, beta=0.0):
+        self.op, self.x, self.y, self.alpha, self.beta = op, x, y, alpha, beta
+
+    def run(self, rt):
+        if self.op == 3:
+            rt.elementwise(3, self.x, None, self.y, alpha=1.0 / self.x.scale)
+        elif self.op == 6:
+            rt.elementwise(6, self.x, None, self.y, alpha=self.alpha, beta=self.beta * self.x.scale)
+        else:
+            rt.elementwise(self.op, self.x, None, self.y)
+
+
+class _Affine:
+    """per-channel x*sc + sh (+ ReLU) for a batch-norm / bias that has no convolution to fold into."""
+    rescalable = False
+
+    def __init__(self, op, x, y, sc, sh):
+        self.op, self.x, self.y, self.sc, self.sh = op, x, y, sc, sh
+        self._dev = None   # (scale the shift was uploaded for, scale ptr, shift ptr)
+
+    def run(self, rt):
+        if self._dev is None or self._dev[0] != self.x.scale:
+            self._dev = (self.x.scale, rt.upload_f32(self.sc), rt.upload_f32(self.sh * self.x.scale))
+        rt.elementwise(self.op, self.x, None, self.y, scale=self._dev[1], shift=self._dev[2])
+
+
+class _Concat:
+    """channel concat: every part is copied into its slice of the output, which takes the smallest scale among the
+    parts (parts stored at a larger scale are multiplied down on the way)."""
+    rescalable = False
+
+    def __init__(self, parts, offsets, y, new_like):
+        self.parts, self.offsets, self.y, self._new_like = parts, offsets, y, new_like
+        self._tmp = {}
+
+    def run(self, rt):
+        for i, p in enumerate(self.parts):
+            src = p
+            if p.scale != self.y.scale:
+                if i not in self._tmp:
+                    self._tmp[i] = self._new_like(p)
+                src = self._tmp[i]
+                rt.elementwise(6, p, None, src, alpha=self.y.scale / p.scale, beta=0.0)
+            rt.copy_channels(src, self.y, self.offsets[i], _r(p.c, 8))
+
+
+class _Call:
+    """scale-preserving single launch (nearest up-sampling, max pooling)."""
+    rescalable = False
+
+    def __init__(self, fn, *args):
+        self.fn, self.args = fn, args
+
+    def run(self, rt):
+        getattr(rt, self.fn)(*self.args)
+
 
 class _Compiled:
     def __init__(self):
-        self.steps = []      # closures over the C ABI
+        self.steps = []      # _Conv / _Add / _Unary / _Affine / _Concat / _Call in execution order
         self.inp = None
         self.out = None
+        self.values = {}     # PIR value id -> _Tensor (diagnosis: tools/dbnet_diag.py)
+        self.graph = None    # CUDA graph of `steps` at the current scales
+        self.calibrated = False
 
 
 class _DeviceRuntime:
@@ -157,10 +257,34 @@ class _DeviceRuntime:
                                               pad_t, pad_l, dil, groups, 1 if transposed else 0, C.byref(lid)))
         return int(lid.value)
 
-    def conv(self, lid, x, y, relu):
-        _capi.check(self.L.vsr_rt_conv(self.h, lid, x.ptr, 1, x.h, x.w, y.ptr, y.cp, 0, relu))
+    def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0):
+        _capi.check(self.L.vsr_rt_conv(self.h, lid, x.ptr, 1, x.h, x.w, y.ptr, y.cp, 0, relu, alpha, bias_scale))
 
-    def elementwise(self, op, a, b, y, scale=0, shift=0, alpha=0.0, beta=0.0):
+    def absmax(self, t) -> float:
+        out = C.c_float()
+        _capi.check(self.L.vsr_rt_absmax(self.h, t.ptr, t.pixels * t.cp, C.byref(out)))
+        return float(out.value)
+
+    def overflow(self) -> bool:
+        f = C.c_int()
+        _capi.check(self.L.vsr_rt_overflow(self.h, C.byref(f)))
+        return bool(f.value)
+
+    def capture_begin(self):
+        _capi.check(self.L.vsr_rt_capture_begin(self.h))
+
+    def capture_end(self) -> int:
+        g = C.c_int()
+        _capi.check(self.L.vsr_rt_capture_end(self.h, C.byref(g)))
+        return int(g.value)
+
+    def graph_launch(self, g):
+        _capi.check(self.L.vsr_rt_graph_launch(self.h, g))
+
+    def graph_destroy(self, g):
+        _capi.check(self.L.vsr_rt_graph_destroy(self.h, g))
+
+    def elementwise(self, op, a, b, y, scale=0, shift=0, alpha=1.0, beta=1.0):
         _capi.check(self.L.vsr_rt_elementwise(self.h, op, a.ptr, b.ptr if b is not None else 0, y.ptr, a.pixels * a.cp, a.cp, scale, shift,
                                               alpha, beta))
 
@@ -205,9 +329,12 @@ class TextDetector:
             self._rt = None
 
     # -------------------------------------------------------------------------------------------- runtime helpers
-    def _new(self, c, h, w, perm=None) -> _Tensor:
+    def _new(self, c, h, w, perm=None, follow=None) -> _Tensor:
         cp = _r(max(c, 1), 64)
-        return _Tensor(self._rt.alloc(h * w * cp * 2), c, h, w, cp, perm)
+        return _Tensor(self._rt.alloc(h * w * cp * 2), c, h, w, cp, perm, follow)
+
+    def _new_like(self, t: _Tensor) -> _Tensor:
+        return _Tensor(self._rt.alloc(t.pixels * t.cp * 2), t.c, t.h, t.w, t.cp, t.perm)
 
     # -------------------------------------------------------------------------------------------- graph compiler
     def _compile(self, H: int, W: int) -> _Compiled:
@@ -308,13 +435,14 @@ class TextDetector:
                 oh, ow = x.h, x.w
             y = self._new(cout, oh, ow)
             lid = rt.conv_create(w, bias, cout, int(cin_eff), x.cp, kh, kw, stride, pad_t, pad_l, dil, groups, transposed)
-            prog.steps.append(lambda x=x, y=y, lid=lid, relu=relu: rt.conv(lid, x, y, relu))
+            prog.steps.append(_Conv(lid, x, y, relu))
             val[cur] = y
 
-        def emit_elt(op, a: _Tensor, b: Optional[_Tensor], out_id, alpha=0.0, beta=0.0, scale=0, shift=0):
-            y = self._new(a.c, a.h, a.w, a.perm)
-            prog.steps.append(lambda: rt.elementwise(op, a, b, y, scale, shift, alpha, beta))
-            val[out_id] = y
+        def channel_vectors(x: _Tensor, mul, add):
+            sc, sh = np.zeros(x.cp, np.float32), np.zeros(x.cp, np.float32)
+            idx = x.perm if x.perm is not None else np.arange(x.c)
+            sc[idx], sh[idx] = mul, add
+            return sc, sh
 
         for n in nodes:
             if id(n) in done:
@@ -332,20 +460,23 @@ class TextDetector:
             elif k == "batch_norm_":  # not preceded by a conv: per-channel affine (+ relu)
                 x = val[n.ins[0]]
                 mean, var, gamma, beta = (np.asarray(val[i], np.float32) for i in n.ins[1:5])
-                s = gamma / np.sqrt(var + np.float32(n.attrs["epsilon"]))
-                sc, sh = np.zeros(x.cp, np.float32), np.zeros(x.cp, np.float32)
-                idx = x.perm if x.perm is not None else np.arange(x.c)
-                sc[idx], sh[idx] = s, beta - mean * s
+                g = gamma / np.sqrt(var + np.float32(n.attrs["epsilon"]))
+                sc, sh = channel_vectors(x, g, beta - mean * g)
                 cur, op = n.out, 4
                 u = single_user(cur, "relu")
                 if u is not None:
                     op, cur = 5, u.out
                     done.add(id(u))
-                emit_elt(op, x, None, cur, scale=rt.upload_f32(sc), shift=rt.upload_f32(sh))
+                val[cur] = self._new(x.c, x.h, x.w, x.perm, follow=x)
+                prog.steps.append(_Affine(op, x, val[cur], sc, sh))
             elif k == "relu":
-                emit_elt(1, val[n.ins[0]], None, n.out)
+                x = val[n.ins[0]]
+                val[n.out] = self._new(x.c, x.h, x.w, x.perm, follow=x)
+                prog.steps.append(_Unary(1, x, val[n.out]))
             elif k == "sigmoid":
-                emit_elt(3, val[n.ins[0]], None, n.out)
+                x = val[n.ins[0]]
+                val[n.out] = self._new(x.c, x.h, x.w, x.perm)
+                prog.steps.append(_Unary(3, x, val[n.out]))
             elif k == "add":
                 a, b = val[n.ins[0]], val[n.ins[1]]
                 if isinstance(a, _Tensor) and isinstance(b, _Tensor):
@@ -356,17 +487,19 @@ class TextDetector:
                     if u is not None:
                         op, cur = 2, u.out
                         done.add(id(u))
-                    emit_elt(op, a, b, cur)
+                    val[cur] = self._new(a.c, a.h, a.w)
+                    prog.steps.append(_Add(op, a, b, val[cur]))
                 else:  # activation + per-channel constant that was not folded into a conv
                     x, cst = (a, b) if isinstance(a, _Tensor) else (b, a)
                     cst = np.asarray(cst, np.float32).reshape(-1)
-                    sc, sh = np.zeros(x.cp, np.float32), np.zeros(x.cp, np.float32)
-                    idx = x.perm if x.perm is not None else np.arange(x.c)
-                    sc[idx] = 1.0
-                    sh[idx] = cst if cst.size == x.c else float(cst[0])
-                    emit_elt(4, x, None, n.out, scale=rt.upload_f32(sc), shift=rt.upload_f32(sh))
+                    sc, sh = channel_vectors(x, 1.0, cst if cst.size == x.c else float(cst[0]))
+                    val[n.out] = self._new(x.c, x.h, x.w, x.perm, follow=x)
+                    prog.steps.append(_Affine(4, x, val[n.out], sc, sh))
             elif k == "scale":
-                emit_elt(6, val[n.ins[0]], None, n.out, alpha=float(np.asarray(val[n.ins[1]]).reshape(-1)[0]), beta=float(n.attrs.get("bias", 0.0)))
+                x = val[n.ins[0]]
+                val[n.out] = self._new(x.c, x.h, x.w, x.perm, follow=x)
+                prog.steps.append(_Unary(6, x, val[n.out], alpha=float(np.asarray(val[n.ins[1]]).reshape(-1)[0]),
+                                         beta=float(n.attrs.get("bias", 0.0))))
             elif k == "concat":
                 parts: List[_Tensor] = val[n.ins[0]]
                 if int(np.asarray(val[n.ins[1]]).reshape(-1)[0]) != 1:
@@ -385,14 +518,13 @@ class TextDetector:
                     lo += p.c
                 y = _Tensor(rt.alloc(parts[0].pixels * _r(off, 64) * 2), total, parts[0].h, parts[0].w, _r(off, 64),
                             None if np.array_equal(perm, np.arange(total)) else perm)
-                for i, p in enumerate(parts):
-                    prog.steps.append(lambda p=p, y=y, dst=phys[i]: rt.copy_channels(p, y, dst, _r(p.c, 8)))
+                prog.steps.append(_Concat(parts, [phys[i] for i in range(len(parts))], y, self._new_like))
                 val[n.out] = y
             elif k == "nearest_interp":
                 x = val[n.ins[0]]
                 s = int(round(float((n.attrs.get("scale") or [2.0])[0])))
-                y = _Tensor(rt.alloc(x.pixels * s * s * x.cp * 2), x.c, x.h * s, x.w * s, x.cp, x.perm)
-                prog.steps.append(lambda x=x, y=y, s=s: rt.upsample(x, y, s))
+                y = _Tensor(rt.alloc(x.pixels * s * s * x.cp * 2), x.c, x.h * s, x.w * s, x.cp, x.perm, follow=x)
+                prog.steps.append(_Call("upsample", x, y, s))
                 val[n.out] = y
             elif k == "pool2d":
                 x = val[n.ins[0]]
@@ -400,8 +532,8 @@ class TextDetector:
                 a = n.attrs
                 if not (a["pooling_type"] == "max" and ks == [2, 2] and a["strides"] == [1, 1] and a["padding_algorithm"] == "SAME" and not a.get("adaptive")):
                     raise _capi.VsrError(f"unsupported pool2d {a} (the mobile detector's SE blocks are not compiled yet)")
-                y = self._new(x.c, x.h, x.w, x.perm)
-                prog.steps.append(lambda x=x, y=y: rt.maxpool(x, y))
+                y = self._new(x.c, x.h, x.w, x.perm, follow=x)
+                prog.steps.append(_Call("maxpool", x, y))
                 val[n.out] = y
             elif k == "fetch":
                 prog.out = val[n.ins[0]]
@@ -409,6 +541,7 @@ class TextDetector:
                 raise _capi.VsrError(f"PIR op '{k}' is not supported by the B200 detector")
         if prog.inp is None or prog.out is None:
             raise _capi.VsrError("program without data/fetch")
+        prog.values = {k: t for k, t in val.items() if isinstance(t, _Tensor)}
         return prog
 
     # -------------------------------------------------------------------------------------------- inference
@@ -428,13 +561,62 @@ class TextDetector:
         prog = self._programs.get((rh, rw))
         if prog is None:
             prog = self._programs[(rh, rw)] = self._compile(rh, rw)
-        self._rt.preprocess(img, prog.inp, rh, rw)
-        for step in prog.steps:
-            step()
+        rt = self._rt
+        rt.preprocess(img, prog.inp, rh, rw)
+        if not prog.calibrated:
+            self._calibrate(prog)        # runs the network once, layer by layer
+        else:
+            rt.graph_launch(prog.graph)
+        host = rt.download(prog.out)
+        if rt.overflow():                # a frame whose activations outgrew the calibrated scales: shrink them and redo
+            self._calibrate(prog)
+            host = rt.download(prog.out)
+            if rt.overflow():
+                raise _capi.VsrError("detector activations overflow fp16 even after rescaling")
         out = prog.out
-        host = self._rt.download(out)
         ch = int(out.perm[0]) if out.perm is not None else 0
         return host[:, :, ch].astype(np.float32)
+
+    def _calibrate(self, prog: _Compiled):
+        """Choose the per-tensor scales on the frame that is in `prog.inp` and record the CUDA graph.
+
+        The detector's neck has no normalisation and reaches |x| ~ 1e5 in fp32, beyond fp16.  Everything between the
+        stem and the final sigmoid is positively homogeneous (conv, ReLU, add, max-pool, nearest up-sampling, concat),
+        so a tensor may be stored multiplied by a power of two without changing the result: convolutions and adds pick
+        the scale of their output (a multiplier in their epilogue), everything else passes it through and the sigmoid
+        divides it out.  Layers run in order; a layer whose stored output exceeds _STORE_LIMIT gets a smaller scale and
+        runs again, so every later layer sees finite inputs.  Scales only ever shrink; the limit leaves 16x headroom for
+        other frames, and the scaled epilogues raise a flag when a later frame still overflows (-> recalibration)."""
+        rt = self._rt
+        if prog.graph is not None:
+            rt.graph_destroy(prog.graph)
+            prog.graph = None
+        for st in prog.steps:
+            if isinstance(st, _Add):
+                st.y.scale = min(st.y.scale, st.a.scale, st.b.scale)
+            elif isinstance(st, _Concat):
+                st.y.scale = min([st.y.scale] + [p.scale for p in st.parts])
+            st.run(rt)
+            if not st.rescalable:
+                if rt.overflow():
+                    raise _capi.VsrError(f"detector calibration: {type(st).__name__} step overflows fp16")
+                continue
+            for _ in range(12):
+                m = rt.absmax(st.y)
+                if m <= _STORE_LIMIT:
+                    break
+                st.y.scale = st.y.scale * (2.0 ** -8 if not np.isfinite(m) else 2.0 ** -int(np.ceil(np.log2(m / _STORE_TARGET))))
+                st.run(rt)
+            else:
+                raise _capi.VsrError("detector calibration did not converge (non-finite input?)")
+            rt.overflow()   # clear what the discarded attempts raised
+        rt.capture_begin()
+        try:
+            for st in prog.steps:
+                st.run(rt)
+        finally:
+            prog.graph = rt.capture_end()
+        prog.calibrated = True
 
     @property
     def launch_count(self) -> int:
