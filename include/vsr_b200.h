@@ -143,6 +143,8 @@ int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W,
                 float alpha, float bias_scale);
 /* max |x| of a tensor (inf when it holds a non-finite value): calibration of the scales.  Synchronises. */
 int vsr_rt_absmax(vsr_rt_t* h, uint64_t dev_ptr, int64_t n_elems, float* out);
+/* host[i] = tensor[i][channel] * mul as fp32, i < pixels (the probability map: one channel of a 64-pitch tensor). */
+int vsr_rt_download_channel(vsr_rt_t* h, uint64_t dev_ptr, int64_t pixels, int cp, int channel, float mul, float* host);
 /* reads and clears the overflow flag.  Synchronises. */
 int vsr_rt_overflow(vsr_rt_t* h, int* raised);
 /* Record the launches issued between begin and end into a CUDA graph and replay them with one call; every buffer a

@@ -1,8 +1,11 @@
 """GPU: the DBNet text detector compiled from the reference's PIR program against the oracle
 interpreter of the same program (oracle/dbnet_oracle.py).  Forward parity is pinned to the reference's model files;
 box post-processing is 'parity unpinned' (no paddleocr here) and compared against the restatement.
-Tolerance: the device network multiplies in fp16 (fp32 accumulate) through ~150 layers: |prob diff| <= 0.06 max,
-<= 2e-3 mean; boxes within 3 px."""
+Tolerance (stated): the device network multiplies fp16 operands (fp32 accumulate) through ~150 layers, which
+leaves ~1e-2 relative RMS error on the head's features (measured layer by layer, profiles/dbnet_layer_error_r1.txt);
+the local-refinement logits span +-250, so a few dozen text-edge pixels out of 522k move by up to ~0.4 while everything
+else agrees to 1e-4.  Bar: mean |diff| <= 5e-4, fraction(|diff| > 0.05) <= 5e-4, binarised map mismatch < 1e-3,
+boxes within 3 px of the oracle's."""
 import os
 
 import numpy as np
@@ -45,9 +48,34 @@ def test_probability_map_matches_oracle(detector):
     want = D.forward(graph, x)[0, 0].numpy()
     assert got.shape == want.shape == (544, 960)
     d = np.abs(got - want)
-    assert np.isfinite(got).all()
-    assert d.mean() <= 2e-3 and d.max() <= 0.06, (float(d.mean()), float(d.max()))
-    assert ((got > 0.3) != (want > 0.3)).mean() < 2e-3  # the binarised map the boxes come from
+    assert np.isfinite(got).all() and 0.0 <= got.min() and got.max() <= 1.0
+    assert d.mean() <= 5e-4 and (d > 0.05).mean() <= 5e-4, (float(d.mean()), float((d > 0.05).mean()), float(d.max()))
+    assert ((got > 0.3) != (want > 0.3)).mean() < 1e-3  # the binarised map the boxes come from
+    # the neck does not fit fp16 unscaled: calibration picked power-of-two scales below 1 there, and only there
+    prog = det._programs[(544, 960)]
+    scales = {t.scale for t in prog.values.values()}
+    assert min(scales) < 1.0 and max(scales) == 1.0 and prog.graph is not None
+    again = det.probability_map(img)            # the recorded CUDA graph
+    assert np.array_equal(again, got)
+
+
+def test_other_resolutions_and_recalibration(detector):
+    det, graph = detector
+    img = _text_frame(360, 640, seed=3)
+    got = det.probability_map(img)
+    want = D.forward(graph, D.preprocess(img))[0, 0].numpy()
+    assert got.shape == want.shape == (352, 640)
+    d = np.abs(got - want)
+    assert d.mean() <= 5e-4 and (d > 0.05).mean() <= 5e-4
+    # a much harsher frame (saturated noise) after calibration on a mild one: either the scales hold or the overflow flag
+    # triggers recalibration; the result must stay finite and close to the oracle either way
+    rng = np.random.default_rng(9)
+    harsh = (rng.integers(0, 2, (360, 640, 3)) * 255).astype(np.uint8)
+    got2 = det.probability_map(harsh)
+    want2 = D.forward(graph, D.preprocess(harsh))[0, 0].numpy()
+    assert np.isfinite(got2).all()
+    d2 = np.abs(got2 - want2)
+    assert d2.mean() <= 2e-3 and (d2 > 0.05).mean() <= 5e-3, (float(d2.mean()), float((d2 > 0.05).mean()))
 
 
 def test_boxes_and_filtering(detector):
@@ -65,3 +93,50 @@ def test_boxes_and_filtering(detector):
     sd._detector = det
     boxes = sd.detect_subtitle(img)
     assert len(boxes) == 1 and boxes[0][2] >= int(720 * 0.8)  # only the bottom line is inside the selected area
+
+
+def test_config4_chain_detect_plan_mask_inpaint(detector, capi):
+    """BASELINE config 4 end to end on an in-memory clip: DBNet on the sampled frames -> gap fill / unify -> ranges with
+    one mask each -> create_mask -> STTN-det.  The frame dictionary must equal the oracle chain's up to 3 px; the
+    inpainted frames are compared with the oracle's STTN-det on the SAME mask (PSNR >= 45 dB, tests/test_gpu_sttn_det.py)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import sttn_det_oracle as DET
+    from oracle import sttn_oracle as O
+    from vsr_b200 import STTNDetInpaint, SubtitleDetect, create_mask
+    from vsr_b200 import subtitle_plan as P
+
+    det, graph = detector
+    H, W, T = 360, 640, 14
+    clip = O.synthetic_clip(T, H, W, seed=21)
+    for i, f in enumerate(clip):
+        if 2 <= i <= 11:   # a subtitle on frames 3..12 (1-based)
+            cv2.putText(f, "subtitle text 42", (150, 330), cv2.FONT_HERSHEY_SIMPLEX, 1.1, (0, 0, 0), 6, cv2.LINE_AA)
+            cv2.putText(f, "subtitle text 42", (150, 330), cv2.FONT_HERSHEY_SIMPLEX, 1.1, (255, 255, 255), 2, cv2.LINE_AA)
+    sd = SubtitleDetect("", model_dir=MODEL_DIR)
+    sd._detector = det
+    sd.SAMPLE_STEP = 2
+    found = sd.scan_frames(clip)
+    # oracle chain: same sampling, oracle network + post-process, the reference's own dictionary logic (pinned bit-exact
+    # in tests/test_subtitle_plan.py)
+    sampled = {}
+    for no in range(1, T + 1):
+        if P.is_sampled(no, 2):
+            b = D.detect_subtitle(graph, clip[no - 1])
+            if b:
+                sampled[no] = [tuple(x) for x in b]
+    want = P.drop_empty(P.unify_regions(P.gap_fill(sampled, 2)))
+    assert sorted(found) == sorted(want) and min(found) in (3, 4) and max(found) in (11, 12)
+    for k in found:
+        assert len(found[k]) == len(want[k]) == 1
+        assert max(abs(a - b) for a, b in zip(found[k][0], want[k][0])) <= 3
+    ranges = sd.find_continuous_ranges_with_same_mask(found)
+    assert len(ranges) == 1            # unify_regions snapped the per-frame jitter to one box
+    (s, e), = ranges
+    mask = create_mask((H, W), found[s])
+    w = O.random_weights(1)
+    eng = STTNDetInpaint("cuda:0", {k: v.numpy() for k, v in w.items()})
+    frames = clip[s - 1:e]
+    out = eng(frames, mask)
+    ref = DET.det_call(w, frames, mask)
+    got, exp = np.stack(out).astype(np.float32), np.stack(ref).astype(np.float32)
+    assert O.psnr_u8(got, exp) >= 45.0 and np.abs(got - exp).max() <= 6

@@ -89,6 +89,7 @@ _PROTOS = {
     "vsr_rt_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
                               C.c_float]),
     "vsr_rt_absmax": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.POINTER(C.c_float)]),
+    "vsr_rt_download_channel": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_float, _f32p]),
     "vsr_rt_overflow": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "vsr_rt_capture_begin": (C.c_int, [C.c_void_p]),
     "vsr_rt_capture_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

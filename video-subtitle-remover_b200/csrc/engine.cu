@@ -1199,6 +1199,9 @@ struct vsr_rt {
   std::vector<std::unique_ptr<DevBuf>> bufs;
   std::vector<std::unique_ptr<RtLayer>> layers;
   DevBuf image;    // BGR u8 staging of the pre-processing
+  DevBuf plane;    // fp32 single-channel staging of vsr_rt_download_channel
+  void* plane_host = nullptr;  // pinned mirror of `plane`
+  size_t plane_host_bytes = 0;
   DevBuf flag;     // [0] int overflow flag raised by the scaled epilogues, [1] uint absmax bits
   DevTaps px, py;  // resize tables of the pre-processing
   std::vector<cudaGraphExec_t> graphs;
@@ -1207,6 +1210,7 @@ struct vsr_rt {
   ~vsr_rt() {
     for (auto g : graphs)
       if (g) cudaGraphExecDestroy(g);
+    if (plane_host) cudaFreeHost(plane_host);
   }
 };
 
@@ -1626,6 +1630,28 @@ int vsr_rt_absmax(vsr_rt_t* h, uint64_t dev_ptr, int64_t n_elems, float* out) {
     CK(cudaMemcpyAsync(&bits, slot, 4, cudaMemcpyDeviceToHost, s));
     rt_sync(h);
     memcpy(out, &bits, 4);
+  });
+}
+
+int vsr_rt_download_channel(vsr_rt_t* h, uint64_t dev_ptr, int64_t pixels, int cp, int channel, float mul, float* host) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(host && pixels > 0 && channel >= 0 && channel < cp && !h->capturing, "bad arguments");
+    cudaStream_t s = h->ctx.stream;
+    h->plane.ensure((size_t)pixels * 4);
+    if (h->plane_host_bytes < (size_t)pixels * 4) {
+      if (h->plane_host) cudaFreeHost(h->plane_host);
+      h->plane_host = nullptr;
+      CK(cudaMallocHost(&h->plane_host, (size_t)pixels * 4));
+      h->plane_host_bytes = (size_t)pixels * 4;
+    }
+    rt_extract_channel_kernel<<<blocks_for((size_t)pixels), 256, 0, s>>>((const __half*)(uintptr_t)dev_ptr, (size_t)pixels, cp, channel, mul,
+                                                                        h->plane.as<float>());
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+    CK(cudaMemcpyAsync(h->plane_host, h->plane.p, (size_t)pixels * 4, cudaMemcpyDeviceToHost, s));
+    rt_sync(h);
+    memcpy(host, h->plane_host, (size_t)pixels * 4);
   });
 }
 

@@ -77,6 +77,14 @@ __global__ void __launch_bounds__(256) rt_elementwise_kernel(int op, const __hal
   reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
 }
 
+// one channel of an NHWC fp16 tensor -> dense fp32 [pixels], divided by the tensor scale (the probability map leaves the
+// device as 4 bytes per pixel instead of the whole 64-channel pitch)
+__global__ void __launch_bounds__(256) rt_extract_channel_kernel(const __half* __restrict__ x, size_t pixels, int cp, int ch, float mul,
+                                                                 float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < pixels) out[i] = __half2float(x[i * cp + ch]) * mul;
+}
+
 // max |x| over a tensor (calibration of the per-tensor scales): *out is the bit pattern of a non-negative float, so
 // an unsigned atomicMax orders it; inf / NaN patterns compare above every finite value.
 __global__ void __launch_bounds__(256) rt_absmax_kernel(const __half* __restrict__ x, size_t n8, unsigned int* __restrict__ out) {

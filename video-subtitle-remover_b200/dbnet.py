@@ -305,6 +305,11 @@ class _DeviceRuntime:
         _capi.check(self.L.vsr_rt_download(self.h, t.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))
         return host
 
+    def download_channel(self, t, ch) -> np.ndarray:
+        host = np.empty((t.h, t.w), np.float32)
+        _capi.check(self.L.vsr_rt_download_channel(self.h, t.ptr, t.pixels, t.cp, ch, 1.0 / t.scale, host.ctypes.data_as(C.POINTER(C.c_float))))
+        return host
+
     @property
     def launch_count(self) -> int:
         return int(self.L.vsr_rt_launch_count(self.h))
@@ -567,15 +572,15 @@ class TextDetector:
             self._calibrate(prog)        # runs the network once, layer by layer
         else:
             rt.graph_launch(prog.graph)
-        host = rt.download(prog.out)
-        if rt.overflow():                # a frame whose activations outgrew the calibrated scales: shrink them and redo
-            self._calibrate(prog)
-            host = rt.download(prog.out)
-            if rt.overflow():
-                raise _capi.VsrError("detector activations overflow fp16 even after rescaling")
         out = prog.out
         ch = int(out.perm[0]) if out.perm is not None else 0
-        return host[:, :, ch].astype(np.float32)
+        host = rt.download_channel(out, ch)
+        if rt.overflow():                # a frame whose activations outgrew the calibrated scales: shrink them and redo
+            self._calibrate(prog)
+            host = rt.download_channel(out, ch)
+            if rt.overflow():
+                raise _capi.VsrError("detector activations overflow fp16 even after rescaling")
+        return host
 
     def _calibrate(self, prog: _Compiled):
         """Choose the per-tensor scales on the frame that is in `prog.inp` and record the CUDA graph.

@@ -2,7 +2,7 @@
 detector runs on the B200 (vsr_b200.dbnet.TextDetector instead of paddleocr's CPU TextDetection), the sampling /
 gap-fill / unify / interval logic is vsr_b200.subtitle_plan (bit-exact restatements)."""
 import os
-from typing import Dict, List
+from typing import Dict, Iterable, List
 
 from . import subtitle_plan as P
 from .dbnet import TextDetector
@@ -49,21 +49,13 @@ class SubtitleDetect:
             out.extend(P.filter_boxes(P.get_coordinates(polys.tolist()), self.sub_areas))
         return out
 
-    def find_subtitle_frame_no(self, sub_remover=None) -> Dict[int, List[P.Box]]:
-        """subtitle_detect.py:84-132: detect every SAMPLE_STEP-th frame (1-based keys), fill gaps of at most
-        2*SAMPLE_STEP between hits, unify near-identical boxes, drop empty entries."""
-        import cv2
-
+    def scan_frames(self, frames: Iterable, sections=None, on_frame=None) -> Dict[int, List[P.Box]]:
+        """The loop body of subtitle_detect.py:96-132 over any frame iterator: detect every SAMPLE_STEP-th frame
+        (1-based keys), fill gaps of at most 2*SAMPLE_STEP between hits, unify near-identical boxes, drop empty entries."""
         from .sttn_auto_inpaint import _in_ab_sections
 
-        cap = cv2.VideoCapture(self.video_path)
-        total = cap.get(cv2.CAP_PROP_FRAME_COUNT)
-        sections = getattr(sub_remover, "ab_sections", None)
         sampled, no = {}, 0
-        while cap.isOpened():
-            ok, frame = cap.read()
-            if not ok:
-                break
+        for frame in frames:
             no += 1
             if not _in_ab_sections(no - 1, sections):
                 continue
@@ -71,10 +63,32 @@ class SubtitleDetect:
                 boxes = self.detect_subtitle(frame)
                 if boxes:
                     sampled[no] = boxes
+            if on_frame is not None:
+                on_frame(no)
+        return P.drop_empty(P.unify_regions(P.gap_fill(sampled, self.SAMPLE_STEP)))
+
+    def find_subtitle_frame_no(self, sub_remover=None) -> Dict[int, List[P.Box]]:
+        """subtitle_detect.py:84-132 on `self.video_path`."""
+        import cv2
+
+        cap = cv2.VideoCapture(self.video_path)
+        total = cap.get(cv2.CAP_PROP_FRAME_COUNT)
+
+        def frames():
+            while cap.isOpened():
+                ok, frame = cap.read()
+                if not ok:
+                    break
+                yield frame
+
+        def progress(no):
             if sub_remover is not None and total:
                 sub_remover.progress_total = (100 * float(no) / float(total)) // 2
-        cap.release()
-        return P.drop_empty(P.unify_regions(P.gap_fill(sampled, self.SAMPLE_STEP)))
+
+        try:
+            return self.scan_frames(frames(), getattr(sub_remover, "ab_sections", None), progress)
+        finally:
+            cap.release()
 
     # the static interval helpers keep their reference names
     find_continuous_ranges = staticmethod(P.find_continuous_ranges)
