@@ -263,6 +263,76 @@ def run_det(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_dbnet(args, rank, world, local):
+    """Secondary line: the DBNet text detector on 1080p frames — `SubtitleDetect.detect_subtitle`'s
+    `TextDetection.predict` on the B200 against the oracle interpreter of the same PIR program on the host cores."""
+    import torch
+    import torch.distributed as dist
+    from vsr_b200.dbnet import TextDetector
+
+    model_dir = os.path.join(ROOT, "weights", "V5", "ch_det")
+    if not os.path.exists(os.path.join(model_dir, "inference.pdiparams")):
+        raise SystemExit("bench.py --workload dbnet needs weights/V5/ch_det (tools/stage_weights.py)")
+    import cv2
+
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    frames = []
+    for i in range(4):
+        img = np.stack([96 + 60 * np.sin(xx / 211 + c + i) + 50 * np.cos(yy / 173 - c) for c in range(3)], -1).clip(0, 255).astype(np.uint8)
+        for txt, org in ((f"The quick brown fox {i}123", (400, 1000)), ("second line of a subtitle", (500, 930))):
+            cv2.putText(img, txt, org, cv2.FONT_HERSHEY_SIMPLEX, 2.0, (0, 0, 0), 9, cv2.LINE_AA)
+            cv2.putText(img, txt, org, cv2.FONT_HERSHEY_SIMPLEX, 2.0, (255, 255, 255), 4, cv2.LINE_AA)
+        frames.append(img)
+    det = TextDetector(model_dir, torch.device("cuda", local))
+    for _ in range(max(args.warmup, 3)):
+        for f in frames:
+            det.predict(f)
+    per = 8
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    net_ms = det.time_network(args.steps * per)
+    l0 = det.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for j in range(per):
+            boxes = det.predict(frames[j % len(frames)])[0]["dt_polys"]
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([net_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    net_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import dbnet_oracle as D
+
+        g = D.Graph(model_dir)
+        D.detect_subtitle(g, frames[0])
+        c0 = time.perf_counter()
+        for f in frames[:3]:
+            D.detect_subtitle(g, f)
+        cpu = {"value": 3 / (time.perf_counter() - c0), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "3 of the 1080p frames through the oracle interpreter of the same PIR program (torch fp32) + DB post-process"}
+    burst, sustained, _, src = peaks()
+    if rank == 0:
+        n = world * args.steps * per
+        flop = 267.6e9   # SURVEY §8d: 133.8 GMAC per [1,3,544,960] frame
+        print(json.dumps({
+            "metric": "text-detected frames/sec at 1080p (DBNet PP-OCRv5_server_det)", "value": world * 1e3 / net_ms, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": net_ms * per, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic 1080p frames with two rendered text lines; reference model files V5/ch_det",
+            "config": {"workload": "DBNet detection of 1080p frames (detection half of BASELINE config 4): resize to 544x960, network, DB post-process",
+                       "frame": [H, W], "frames_per_step": per, "boxes_last_frame": int(len(boxes))},
+            "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": per * H * W * 3, "d2h_bytes_per_step": per * 544 * 960 * 4,
+                    "api": "TextDetector.predict(bgr_frame) -> dt_polys, synchronous, host post-process included"},
+            "gpu_launches": int(args.steps * per * 247 + (det.launch_count - l0)),
+            "roofline": {"bound": "tensor", "kernel": "whole network graph (247 launches, latency-bound small layers)", "achieved": flop / net_ms / 1e9,
+                         "peak": sustained, "unit": "TFLOP/s", "frac": flop / net_ms / 1e9 / sustained, "traffic": None, "peak_source": f"{src} (sustained bf16)"},
+            "cpu_baseline": cpu}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -270,8 +340,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det"],
-                    help="sttn-auto = BASELINE config 2 (the contract line); sttn-det = the inpaint half of config 4 (46-frame batches)")
+    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det", "dbnet"],
+                    help="sttn-auto = BASELINE config 2 (the contract line); sttn-det / dbnet = the inpaint / detection halves of config 4")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -297,6 +367,9 @@ def main():
             dist.barrier()
 
     _capi.build_library()
+    if args.workload == "dbnet":
+        run_dbnet(args, rank, world, local)
+        return
     if args.workload == "sttn-det":
         return run_det(args, rank, world, local)
     w, wdesc = load_weights()

@@ -1,4 +1,5 @@
-"""Layer-by-layer comparison of the device detector with the oracle interpreter (run on a GPU box)."""
+"""Layer-by-layer comparison of the device detector with the oracle interpreter, plus per-step device times
+(diagnostic script, run on a GPU box: `python tests/diag_dbnet.py [H W] [-r] [-v]`; not collected by pytest)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

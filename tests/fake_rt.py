@@ -182,6 +182,9 @@ class FakeRuntime:
         v[:, :, :3] = x
         self.launches += 1
 
+    def sync(self):
+        pass
+
     def download_channel(self, t, ch):
         return (self._view(t)[:, :, ch] / t.scale).astype(np.float32)
 

@@ -305,6 +305,9 @@ class _DeviceRuntime:
         _capi.check(self.L.vsr_rt_download(self.h, t.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))
         return host
 
+    def sync(self):
+        _capi.check(self.L.vsr_rt_sync(self.h))
+
     def download_channel(self, t, ch) -> np.ndarray:
         host = np.empty((t.h, t.w), np.float32)
         _capi.check(self.L.vsr_rt_download_channel(self.h, t.ptr, t.pixels, t.cp, ch, 1.0 / t.scale, host.ctypes.data_as(C.POINTER(C.c_float))))
@@ -581,6 +584,22 @@ class TextDetector:
             if rt.overflow():
                 raise _capi.VsrError("detector activations overflow fp16 even after rescaling")
         return host
+
+    def time_network(self, iters: int = 20) -> float:
+        """ms per replay of the recorded network graph of the last-used resolution (input already on the device)."""
+        import time
+
+        prog = next(reversed(self._programs.values()))
+        if prog.graph is None:
+            raise _capi.VsrError("run probability_map once before timing")
+        rt = self._rt
+        rt.graph_launch(prog.graph)
+        rt.sync()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            rt.graph_launch(prog.graph)
+        rt.sync()
+        return (time.perf_counter() - t0) / iters * 1e3
 
     def _calibrate(self, prog: _Compiled):
         """Choose the per-tensor scales on the frame that is in `prog.inp` and record the CUDA graph.
