@@ -333,6 +333,72 @@ def run_dbnet(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_lama(args, rank, world, local):
+    """Secondary line: LAMA (BASELINE config 1 / SURVEY §8a L1-L3) through `LamaInpaint.__call__` on 1080p frames: the strip
+    of int(1920*3/16) = 360 rows around the subtitle goes through big-lama at native resolution, frame by frame."""
+    import torch
+    import torch.distributed as dist
+    from oracle import sttn_oracle as O
+    from vsr_b200 import LamaInpaint
+
+    npz = os.path.join(ROOT, "weights", "big-lama", "big-lama.npz")
+    if os.path.exists(npz):
+        eng, wdesc, wsrc = LamaInpaint(torch.device("cuda", local), npz), "reference big-lama weights (conv kernels stored fp16)", npz
+    else:
+        from oracle import lama_oracle as LO
+
+        wsrc = {k: v.numpy() for k, v in LO.random_weights(3).items()}
+        eng, wdesc = LamaInpaint(torch.device("cuda", local), wsrc), "seeded random-init weights of the big-lama architecture"
+    T = 4
+    frames = O.synthetic_clip(T, H, W, seed=200 + rank)
+    mask = O.default_mask(H, W)
+    for _ in range(max(args.warmup, 3)):
+        eng(frames[:1], mask)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    net_ms = eng.model.time_network(args.steps * T)
+    l0 = eng.model.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = eng(frames, mask)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([net_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    net_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import lama_oracle as LO
+
+        w = LO.load_weights(wsrc) if isinstance(wsrc, str) else {k: torch.from_numpy(v) for k, v in wsrc.items()}
+        LO.lama_call(w, frames[:1], mask)
+        c0 = time.perf_counter()
+        LO.lama_call(w, frames[:2], mask)
+        cpu = {"value": 2 / (time.perf_counter() - c0), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "2 of the 1080p frames through the oracle (torch fp32 restatement, bit-identical to the TorchScript module)"}
+    burst, sustained, _, src = peaks()
+    if rank == 0:
+        n = world * args.steps * T
+        sh = int(W * 3 / 16)
+        flop = 1158e9   # SURVEY §8d: conv FLOPs of one 360x1920 strip frame (+36 rfft2/irfft2 pairs)
+        print(json.dumps({
+            "metric": "inpainted frames/sec at 1080p (LAMA big-lama)", "value": world * 1e3 / net_ms, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": net_ms * T, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": f"synthetic 1080p clip; {wdesc}",
+            "config": {"workload": "LAMA inpaint of 1080p frames (BASELINE config 1 model on the video strip path): strip 360x1920 per frame",
+                       "frame": [H, W], "frames_per_step": T, "strip_h": sh},
+            "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": T * (sh * W * 3 + sh * W), "d2h_bytes_per_step": T * sh * W * 3,
+                    "api": "LamaInpaint.__call__(frames, mask), synchronous, copy semantics"},
+            "gpu_launches": int(eng.model.launch_count - l0 + args.steps * T * 560),
+            "roofline": {"bound": "tensor", "kernel": "whole network graph (~560 launches on a 45x240 feature grid: latency-bound at one frame per launch)",
+                         "achieved": flop / net_ms / 1e9, "peak": sustained, "unit": "TFLOP/s", "frac": flop / net_ms / 1e9 / sustained, "traffic": None,
+                         "peak_source": f"{src} (sustained bf16)"},
+            "cpu_baseline": cpu}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,8 +406,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det", "dbnet"],
-                    help="sttn-auto = BASELINE config 2 (the contract line); sttn-det / dbnet = the inpaint / detection halves of config 4")
+    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det", "dbnet", "lama"],
+                    help="sttn-auto = BASELINE config 2 (the contract line); sttn-det / dbnet = the inpaint / detection halves of config 4; "
+                         "lama = the big-lama model of config 1 on 1080p strips")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -369,6 +436,9 @@ def main():
     _capi.build_library()
     if args.workload == "dbnet":
         run_dbnet(args, rank, world, local)
+        return
+    if args.workload == "lama":
+        run_lama(args, rank, world, local)
         return
     if args.workload == "sttn-det":
         return run_det(args, rank, world, local)

@@ -141,6 +141,29 @@ int vsr_rt_conv_create(vsr_rt_t* h, const float* w, const float* bias, int cout,
  * bias_scale = s_out (1, 1 for unscaled tensors).  Every scaled store that leaves fp16 raises the overflow flag. */
 int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu,
                 float alpha, float bias_scale);
+/* vsr_rt_conv whose output tensor [out_h, out_w] is the window starting at (crop_t, crop_l) of the computed H x W grid:
+ * a dense conv over a reflect-padded input keeps only the interior (LAMA's padding_mode='reflect', ReflectionPad2d). */
+int vsr_rt_conv_ex(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu,
+                   float alpha, float bias_scale, int crop_t, int crop_l, int out_h, int out_w);
+/* ---- LAMA: what the TorchScript big-lama forward needs beyond the detector's operators ---- */
+/* out[OH,OW] = in[H,W] shifted by (top, left), reflected at the borders (reflect = 1) or zero filled (0) */
+int vsr_rt_pad(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left, int reflect);
+/* zero insertion [2H, 2W]: a stride-2 transposed conv is a dense conv of it with the flipped kernel */
+int vsr_rt_zero_upsample2x(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out);
+/* out[p][0..channels) = f(a[p][..]*alpha + b[p][..]*beta) on channel slices (pointers already offset) with their own pitches */
+int vsr_rt_add_slices(vsr_rt_t* h, int relu, uint64_t a, int pitch_a, uint64_t b, int pitch_b, uint64_t out, int pitch_out, int channels,
+                      int64_t pixels, float alpha, float beta);
+/* residual stream with an fp32 master: x32 (+)= y16, x16 = half(x32); init != 0 starts x32 from x16 (FFCResnetBlock's id + x) */
+int vsr_rt_residual_add(vsr_rt_t* h, uint64_t x32, uint64_t y16, uint64_t x16, int64_t n_elems, int init);
+/* FourierUnit (ffc.py): rfftn(norm='ortho') of C channels of in [H,W,cp_in] -> out [H, W/2+1, 2C] with (re, im) interleaved
+ * on the channel axis; the inverse takes that layout back to [H,W,cp_out] (C real channels).  cuFFT, fp32 inside. */
+int vsr_rt_fft_r2c(vsr_rt_t* h, uint64_t in, int H, int W, int C, int cp_in, uint64_t out);
+int vsr_rt_fft_c2r(vsr_rt_t* h, uint64_t in, int H, int W, int C, uint64_t out, int cp_out);
+/* lama_util.py:12-80 + the head of big-lama's forward: host u8 image [h,w,3] and mask [h,w] -> NHWC fp16 [H,W,cp]
+ * (img/255*(1-m), m), symmetric padding up to H x W.  The image and mask stay staged on the device for vsr_rt_lama_output:
+ * m*pred + (1-m)*img/255 -> trunc(clip(.*255)) -> host u8 [h,w,3] (lama_inpaint.py:25-27). */
+int vsr_rt_lama_input(vsr_rt_t* h, const uint8_t* img, const uint8_t* mask, int ih, int iw, uint64_t out, int H, int W, int cp);
+int vsr_rt_lama_output(vsr_rt_t* h, uint64_t pred, int W, int cp, float inv_scale, int ih, int iw, uint8_t* out);
 /* max |x| of a tensor (inf when it holds a non-finite value): calibration of the scales.  Synchronises. */
 int vsr_rt_absmax(vsr_rt_t* h, uint64_t dev_ptr, int64_t n_elems, float* out);
 /* host[i] = tensor[i][channel] * mul as fp32, i < pixels (the probability map: one channel of a 64-pitch tensor). */

@@ -80,7 +80,8 @@ class FakeRuntime:
         return h
 
     def _view(self, t):
-        return self.bufs[t.ptr][: t.h * t.w * t.cp].reshape(t.h, t.w, t.cp)
+        base, c0 = t.ptr - t.ptr % 0x1000, (t.ptr % 0x1000) // 2      # channel-slice views advance the pointer by 2*c0 bytes
+        return self.bufs[base][: t.h * t.w * t.cp].reshape(t.h, t.w, t.cp)[:, :, c0:]
 
     def conv_create(self, w, bias, cout, cin, cin_pitch, kh, kw, stride, pad_t, pad_l, dil, groups, transposed):
         w = np.array(w, np.float32)
@@ -101,12 +102,23 @@ class FakeRuntime:
                                 stride=stride, pad_t=pad_t, pad_l=pad_l, dil=dil, groups=groups, transposed=transposed))
         return len(self.layers) - 1
 
-    def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0):
-        if self._recording("conv", lid, x, y, relu, alpha, bias_scale):
+    def conv_ex(self, lid, x, y, relu, out_coff=0, crop=(0, 0)):
+        self.conv(lid, x, y, relu, 1.0, 1.0, out_coff, crop)
+
+    def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0, out_coff=0, crop=None):
+        if self._recording("conv", lid, x, y, relu, alpha, bias_scale, out_coff, crop):
             return
         L = self.layers[lid]
         xin = torch.from_numpy(self._view(x)[:, :, : L["cin"]].copy()).permute(2, 0, 1)[None]
-        if L["transposed"]:
+        if crop is not None:   # 'same' conv on the (padded) input grid, keep the window [crop, crop + y.hw)
+            assert not L["transposed"] and L["groups"] == 1 and L["cin"] >= 16 and L["cout"] >= 8, "cropped output needs a tensor-core conv"
+            p = (L["kh"] - 1) * L["dil"] // 2
+            assert (L["pad_t"], L["pad_l"]) == (p, p)
+            if L["stride"] == 2:
+                assert x.h % 2 == 0 and x.w % 2 == 0
+            full = F.conv2d(F.pad(xin, (p, p, p, p)), L["w"], None, stride=L["stride"], dilation=L["dil"])
+            out = full[:, :, crop[0]:crop[0] + y.h, crop[1]:crop[1] + y.w]
+        elif L["transposed"]:
             out = F.conv_transpose2d(xin, L["w"], None, stride=2)
         else:
             eff_h, eff_w = (L["kh"] - 1) * L["dil"] + 1, (L["kw"] - 1) * L["dil"] + 1
@@ -120,10 +132,84 @@ class FakeRuntime:
         out = out * alpha + (L["b"] * bias_scale)[None, :, None, None]
         if relu:
             out = out.relu()
-        full = np.zeros((y.h, y.w, y.cp), np.float32)
-        full[:, :, : L["cout"]] = out[0].permute(1, 2, 0).numpy()
-        self._store(y, full)
+        res = out[0].permute(1, 2, 0).numpy()
+        if np.abs(res).max(initial=0.0) > 65504.0 or not np.isfinite(res).all():
+            self._flag = True
+        v = self._view(y)
+        if out_coff == 0 and crop is None:
+            v[:] = 0           # the device kernels write zeros into the channel padding of a plain output tensor
+        v[:, :, out_coff:out_coff + L["cout"]] = res
         self.launches += 1
+
+    # ---- LAMA-only entry points
+    def pad(self, x, y, top, left, reflect=1):
+        if self._recording("pad", x, y, top, left, reflect):
+            return
+        bottom, right = y.h - x.h - top, y.w - x.w - left
+        self._view(y)[:] = np.pad(self._view(x), ((top, bottom), (left, right), (0, 0)), mode="reflect" if reflect else "constant")
+        self.launches += 1
+
+    def zero_upsample(self, x, y):
+        if self._recording("zero_upsample", x, y):
+            return
+        v = self._view(y)
+        v[:] = 0
+        v[::2, ::2] = self._view(x)
+        self.launches += 1
+
+    def add_slices(self, relu, a, b, y, channels):
+        if self._recording("add_slices", relu, a, b, y, channels):
+            return
+        r = self._view(a)[:, :, :channels] + self._view(b)[:, :, :channels]
+        self._view(y)[:, :, :channels] = np.maximum(r, 0) if relu else r
+        self.launches += 1
+
+    def residual_add(self, x32, y, x, init):
+        if self._recording("residual_add", x32, y, x, init):
+            return
+        master = self.bufs[x32]          # alloc() gave one fp32 per 2 bytes: the first pixels*cp entries are the fp32 master
+        n = x.pixels * x.cp
+        if init:
+            master[:n] = self.bufs[x.ptr][:n]
+        master[:n] += self.bufs[y.ptr][:n]
+        self.bufs[x.ptr][:n] = master[:n]
+        self.launches += 1
+
+    def fft_r2c(self, x, y):
+        if self._recording("fft_r2c", x, y):
+            return
+        f = np.fft.rfft2(self._view(x)[:, :, : x.c].astype(np.float64), axes=(0, 1), norm="ortho")
+        out = np.stack([f.real, f.imag], -1).reshape(y.h, y.w, 2 * x.c)       # channel 2c + {re, im}
+        self._view(y)[:, :, : 2 * x.c] = out.astype(np.float32)
+        self.launches += 3
+
+    def fft_c2r(self, x, y):
+        if self._recording("fft_c2r", x, y):
+            return
+        v = self._view(x)[:, :, : 2 * y.c].astype(np.float64).reshape(x.h, x.w, y.c, 2)
+        out = np.fft.irfft2(v[..., 0] + 1j * v[..., 1], s=(y.h, y.w), axes=(0, 1), norm="ortho")
+        self._view(y)[:, :, : y.c] = out.astype(np.float32)
+        self.launches += 3
+
+    def lama_input(self, img, mask, y):
+        assert self._rec is None
+        h, w = mask.shape
+        m = (np.pad(mask, ((0, y.h - h), (0, y.w - w)), mode="symmetric") > 0).astype(np.float32)
+        im = np.pad(img.astype(np.float32) / np.float32(255), ((0, y.h - h), (0, y.w - w), (0, 0)), mode="symmetric")
+        v = self._view(y)
+        v[:] = 0
+        v[:, :, :3] = im * (1 - m)[:, :, None]
+        v[:, :, 3] = m
+        self._staged = (img.copy(), mask.copy())
+        self.launches += 1
+
+    def lama_output(self, pred, ih, iw):
+        assert self._rec is None
+        img, mask = self._staged
+        m = (mask > 0).astype(np.float32)[:, :, None]
+        res = m * self._view(pred)[:ih, :iw, :3] + (1 - m) * (img.astype(np.float32) / np.float32(255))
+        self.launches += 1
+        return np.clip(res * 255, 0, 255).astype(np.uint8)
 
     def elementwise(self, op, a, b, y, scale=0, shift=0, alpha=1.0, beta=1.0):
         if self._recording("elementwise", op, a, b, y, scale, shift, alpha, beta):

@@ -14,7 +14,43 @@ FILES = {"sttn-auto/infer_model.pth": "backend/models/sttn-auto/infer_model.pth"
          "V5/ch_det/inference.yml": "backend/models/V5/ch_det/inference.yml"}
 
 
+def stage_lama(quiet=False):
+    """big-lama: concatenate the 5 parts in fs_manifest.csv order into the TorchScript file (kept out of gpurun snapshots by
+    .gpurunignore) and export its generator tensors as an fp16 .npz (102 MB) that travels to the GPU box."""
+    src = os.path.join(REF, "backend", "models", "big-lama")
+    dst = os.path.join(ROOT, "weights", "big-lama")
+    pt, npz = os.path.join(dst, "big-lama.pt"), os.path.join(dst, "big-lama.npz")
+    if not os.path.isdir(src):
+        if not quiet:
+            print(f"skip big-lama: {src} not found")
+        return
+    os.makedirs(dst, exist_ok=True)
+    if not os.path.exists(pt):
+        import csv
+
+        with open(os.path.join(src, "fs_manifest.csv")) as f:
+            parts = [r["filename"] for r in csv.DictReader(f)]
+        with open(pt, "wb") as out:
+            for part in parts:
+                with open(os.path.join(src, part), "rb") as f:
+                    shutil.copyfileobj(f, out)
+        if not quiet:
+            print(f"staged {pt}")
+    if not os.path.exists(npz):
+        import numpy as np
+        import torch
+
+        sd = torch.jit.load(pt, map_location="cpu").state_dict()
+        pre = "model.generator.model."
+        np.savez(npz, **{k[len(pre):]: v.numpy().astype(np.float16 if v.dim() == 4 else np.float32) for k, v in sd.items()
+                         if k.startswith(pre) and not k.endswith("num_batches_tracked")})   # conv kernels fp16, batch-norm vectors fp32
+        if not quiet:
+            print(f"staged {npz}")
+
+
 def main(quiet=False):
+    if "--lama" in sys.argv:
+        stage_lama(quiet)
     for dst, src in FILES.items():
         s = os.path.join(REF, src)
         d = os.path.join(ROOT, "weights", dst)

@@ -5,6 +5,7 @@ Public surface (same names / call conventions as the reference back-ends):
     STTNInpaint(device, model_path)(frames, mask)                 backend/inpaint/sttn_auto_inpaint.py:28
     STTNAutoInpaint(device, model_path, video_path, ...)(...)     backend/inpaint/sttn_auto_inpaint.py:167
     STTNDetInpaint(device, model_path)(frames, mask)              backend/inpaint/sttn_det_inpaint.py:23
+    LamaInpaint(device, model_path)(frames, mask) / .inpaint      backend/inpaint/lama_inpaint.py:11
     SubtitleDetect(video_path, sub_areas).detect_subtitle(img)    backend/tools/subtitle_detect.py:16
     create_mask / get_inpaint_area_by_mask / batch_generator      backend/tools/inpaint_tools.py
     InpaintMode                                                   backend/tools/constant.py:4
@@ -17,6 +18,7 @@ from .inpaint_tools import batch_generator, create_mask, get_inpaint_area_by_mas
 from .sttn_auto_inpaint import STTNAutoInpaint, STTNInpaint  # noqa: F401
 from .sttn_det_inpaint import STTNDetInpaint  # noqa: F401
 from .subtitle_detect import SubtitleDetect  # noqa: F401
+from .lama_inpaint import LamaInpaint  # noqa: F401
 
-__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "SubtitleDetect", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
+__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "LamaInpaint", "SubtitleDetect", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
            "batch_generator"]

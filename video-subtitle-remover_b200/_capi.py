@@ -27,7 +27,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
             return LIB_PATH
     LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
     nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, str(CSRC / "engine.cu"), "-o", str(LIB_PATH)]
+    cmd = [nvcc, *NVCC_FLAGS, str(CSRC / "engine.cu"), "-o", str(LIB_PATH), "-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -88,6 +88,17 @@ _PROTOS = {
                                      C.c_int, C.c_int, C.c_int, _i32p]),
     "vsr_rt_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
                               C.c_float]),
+    "vsr_rt_conv_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                 C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vsr_rt_pad": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vsr_rt_zero_upsample2x": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_add_slices": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int64,
+                                    C.c_float, C.c_float]),
+    "vsr_rt_residual_add": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int]),
+    "vsr_rt_fft_r2c": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_fft_c2r": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "vsr_rt_lama_input": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]),
+    "vsr_rt_lama_output": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
     "vsr_rt_absmax": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.POINTER(C.c_float)]),
     "vsr_rt_download_channel": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_float, _f32p]),
     "vsr_rt_overflow": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

@@ -48,6 +48,9 @@ struct ConvParams {
   // stored fp16 value leaves the format
   float alpha, bias_scale;
   int* overflow;
+  // the output tensor is the window [crop_t, crop_t + out_H) x [crop_l, crop_l + out_W) of the computed grid (a conv over a
+  // reflect-padded input stores only the interior); out_H = H, out_W = W, crop 0 for plain convs
+  int crop_t, crop_l, out_H, out_W;
 };
 
 template <int BN_>
@@ -113,8 +116,9 @@ struct ConvPolicy {
     c.t = t.t;
     c.y = t.y0 + ry;
     c.x = t.x0 + rx;
-    c.valid = (ry < p.tile_h) && (c.y < p.H) && (c.x < p.W);
-    c.pix = ((size_t)t.t * p.H + c.y) * p.W + c.x;
+    const int oy = c.y - p.crop_t, ox = c.x - p.crop_l;
+    c.valid = (ry < p.tile_h) && (c.y < p.H) && (c.x < p.W) && ((unsigned)oy < (unsigned)p.out_H) && ((unsigned)ox < (unsigned)p.out_W);
+    c.pix = ((size_t)t.t * p.out_H + oy) * p.out_W + ox;
     return c;
   }
   __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}

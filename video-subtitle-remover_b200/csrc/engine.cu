@@ -15,6 +15,8 @@
 #include <thread>
 #include <vector>
 
+#include <cufft.h>
+
 #include "../../include/vsr_b200.h"
 #include "attention.cuh"
 #include "conv_igemm.cuh"
@@ -192,6 +194,7 @@ static void launch_tc2(Ctx& c, const typename P::Params& prm, int ntiles) {
 struct ConvLayer {
   DevBuf w, b;
   int cin = 0, cout = 0, cout_pad = 0, ntaps = 0, K = 0, bn = 0;
+  int pitch = 0;  // channel pitch of the input tensor when it differs from cin (a channel-slice view); 0 = cin
   int8_t dy[81] = {0}, dx[81] = {0};
 };
 
@@ -260,16 +263,18 @@ static void pack_conv_s2d(ConvLayer& L, const float* w, const float* bias, int c
 // input tensor has `cin_pitch` (multiple of 64) channels of which the first `cin` are real.
 static void pack_conv_general(ConvLayer& L, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw,
                               int dil, int pad_t, int pad_l, cudaStream_t s) {
-  REQUIRE(cin_pitch % 64 == 0 && cin <= cin_pitch, "input channel pitch must be a multiple of 64");
+  REQUIRE(cin_pitch % 8 == 0 && cin <= cin_pitch, "input channel pitch must be a multiple of 8 (16-byte TMA strides)");
   REQUIRE(kh * kw <= 81, "kernels up to 81 taps");
-  L.cin = cin_pitch; L.cout = cout; L.cout_pad = pad_cout(cout); L.ntaps = kh * kw; L.K = kh * kw * cin_pitch;
+  const int cin_k = (cin + 63) / 64 * 64;  // K extent per tap: whole 64-channel TMA boxes (weights beyond cin are zero)
+  REQUIRE(cin_k <= cin_pitch || cin_pitch % 64 == 0, "a channel slice must end on the tensor's 64-channel grid");
+  L.cin = cin_k; L.pitch = cin_pitch; L.cout = cout; L.cout_pad = pad_cout(cout); L.ntaps = kh * kw; L.K = kh * kw * cin_k;
   L.bn = L.cout_pad < 256 ? L.cout_pad : 256;
   std::vector<__half> hw((size_t)L.cout_pad * L.K, __float2half(0.f));
   for (int co = 0; co < cout; ++co)
     for (int ci = 0; ci < cin; ++ci)
       for (int ky = 0; ky < kh; ++ky)
         for (int kx = 0; kx < kw; ++kx)
-          hw[(size_t)co * L.K + (size_t)(ky * kw + kx) * cin_pitch + ci] = __float2half_rn(w[(((size_t)co * cin + ci) * kh + ky) * kw + kx]);
+          hw[(size_t)co * L.K + (size_t)(ky * kw + kx) * cin_k + ci] = __float2half_rn(w[(((size_t)co * cin + ci) * kh + ky) * kw + kx]);
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx) {
       L.dy[ky * kw + kx] = (int8_t)(ky * dil - pad_t);
@@ -339,6 +344,7 @@ struct ConvIO {
   const uchar4* det_rgb = nullptr;
   float alpha = 1.f, bias_scale = 1.f;  // CONV_SCALED (graph runtime)
   int* overflow = nullptr;
+  int crop_t = 0, crop_l = 0, out_H = 0, out_W = 0;  // out_H == 0: the output grid is the input grid
 };
 
 static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
@@ -347,8 +353,9 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   int tw, th;
   choose_tile(io.H, io.W, tw, th);
   {
+    const uint64_t pitch = L.pitch ? L.pitch : L.cin;
     const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)io.W, (uint64_t)io.H, (uint64_t)io.T};
-    const uint64_t str[3] = {(uint64_t)L.cin * 2, (uint64_t)io.W * L.cin * 2, (uint64_t)io.H * io.W * L.cin * 2};
+    const uint64_t str[3] = {pitch * 2, (uint64_t)io.W * pitch * 2, (uint64_t)io.H * io.W * pitch * 2};
     const uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
     p.in_map = make_map_f16(io.in, 4, dims, str, box);
   }
@@ -384,6 +391,10 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   p.alpha = io.alpha;
   p.bias_scale = io.bias_scale;
   p.overflow = io.overflow;
+  p.crop_t = io.crop_t;
+  p.crop_l = io.crop_l;
+  p.out_H = io.out_H ? io.out_H : io.H;
+  p.out_W = io.out_W ? io.out_W : io.W;
   if (io.flags & CONV_S2D_STORE) {
     REQUIRE(io.H % 2 == 0 && io.W % 2 == 0, "s2d store needs even H, W");
     p.out16_pitch = 4 * L.cout;
@@ -1199,6 +1210,14 @@ struct vsr_rt {
   std::vector<std::unique_ptr<DevBuf>> bufs;
   std::vector<std::unique_ptr<RtLayer>> layers;
   DevBuf image;    // BGR u8 staging of the pre-processing
+  DevBuf mask8;    // u8 mask staging (LAMA)
+  struct FftPlan {
+    cufftHandle r2c = 0, c2r = 0;
+    std::shared_ptr<DevBuf> re, sp;  // fp32 staging of the real side [H][W][pitch] and of the spectrum [H][W/2+1][C] complex
+  };
+  std::map<std::array<int, 4>, FftPlan> fft_plans;  // (H, W, C, pitch of the real side)
+  void* out_host = nullptr;  // pinned u8 staging of vsr_rt_lama_output
+  size_t out_host_bytes = 0;
   DevBuf plane;    // fp32 single-channel staging of vsr_rt_download_channel
   void* plane_host = nullptr;  // pinned mirror of `plane`
   size_t plane_host_bytes = 0;
@@ -1211,6 +1230,11 @@ struct vsr_rt {
     for (auto g : graphs)
       if (g) cudaGraphExecDestroy(g);
     if (plane_host) cudaFreeHost(plane_host);
+    if (out_host) cudaFreeHost(out_host);
+    for (auto& kv : fft_plans) {
+      if (kv.second.r2c) cufftDestroy(kv.second.r2c);
+      if (kv.second.c2r) cufftDestroy(kv.second.c2r);
+    }
   }
 };
 
@@ -1633,6 +1657,154 @@ int vsr_rt_absmax(vsr_rt_t* h, uint64_t dev_ptr, int64_t n_elems, float* out) {
   });
 }
 
+int vsr_rt_pad(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left, int reflect) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(cp % 8 == 0 && OH > 0 && OW > 0 && H > 1 && W > 1, "bad arguments");
+    const size_t n = (size_t)T * OH * OW * (cp / 8);
+    rt_pad_kernel<<<blocks_for(n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, T, H, W, cp, (__half*)(uintptr_t)out, OH, OW, top, left,
+                                                            reflect);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_zero_upsample2x(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(cp % 8 == 0, "bad arguments");
+    const size_t n = (size_t)T * 4 * H * W * (cp / 8);
+    rt_zero_upsample2x_kernel<<<blocks_for(n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, T, H, W, cp, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_add_slices(vsr_rt_t* h, int relu, uint64_t a, int pitch_a, uint64_t b, int pitch_b, uint64_t out, int pitch_out, int channels,
+                      int64_t pixels, float alpha, float beta) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(channels % 8 == 0 && pitch_a % 8 == 0 && pitch_b % 8 == 0 && pitch_out % 8 == 0 && pixels > 0, "8-channel granularity");
+    REQUIRE(a % 16 == 0 && b % 16 == 0 && out % 16 == 0, "16-byte aligned slices");
+    rt_add_slices_kernel<<<blocks_for((size_t)pixels * (channels / 8)), 256, 0, h->ctx.stream>>>(
+        relu, (const __half*)(uintptr_t)a, pitch_a, (const __half*)(uintptr_t)b, pitch_b, (__half*)(uintptr_t)out, pitch_out, channels / 8,
+        (size_t)pixels, alpha, beta, h->overflow());
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_residual_add(vsr_rt_t* h, uint64_t x32, uint64_t y16, uint64_t x16, int64_t n_elems, int init) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(x32 && y16 && x16 && n_elems > 0 && n_elems % 8 == 0, "bad arguments");
+    rt_residual_add_kernel<<<blocks_for((size_t)n_elems / 8), 256, 0, h->ctx.stream>>>((float*)(uintptr_t)x32, (const __half*)(uintptr_t)y16,
+                                                                                      (__half*)(uintptr_t)x16, (size_t)n_elems / 8, init, h->overflow());
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+namespace vsr {
+static void cufft_ck(cufftResult r, const char* what) {
+  if (r != CUFFT_SUCCESS) throw Error(VSR_ERR_CUDA, std::string(what) + " -> cuFFT error " + std::to_string((int)r));
+}
+// plans of the FourierUnit transforms over C interleaved channels: real side [H][W][pitch], spectrum [H][W/2+1][C] complex
+static vsr_rt::FftPlan& fft_plan(vsr_rt* h, int H, int W, int C, int pitch) {
+  const std::array<int, 4> key{H, W, C, pitch};
+  auto it = h->fft_plans.find(key);
+  if (it != h->fft_plans.end()) return it->second;
+  if (h->capturing) throw Error(VSR_ERR_ARG, "FFT plans must be created by a run before graph capture");
+  vsr_rt::FftPlan p;
+  int n[2] = {H, W}, re_embed[2] = {H, W}, sp_embed[2] = {H, W / 2 + 1};
+  cufft_ck(cufftPlanMany(&p.r2c, 2, n, re_embed, pitch, 1, sp_embed, C, 1, CUFFT_R2C, C), "cufftPlanMany(R2C)");
+  cufft_ck(cufftPlanMany(&p.c2r, 2, n, sp_embed, C, 1, re_embed, pitch, 1, CUFFT_C2R, C), "cufftPlanMany(C2R)");
+  cufft_ck(cufftSetStream(p.r2c, h->ctx.stream), "cufftSetStream");
+  cufft_ck(cufftSetStream(p.c2r, h->ctx.stream), "cufftSetStream");
+  p.re = std::make_shared<DevBuf>();
+  p.sp = std::make_shared<DevBuf>();
+  p.re->ensure((size_t)H * W * pitch * 4);
+  p.sp->ensure((size_t)H * (W / 2 + 1) * 2 * C * 4);
+  return h->fft_plans[key] = p;
+}
+}  // namespace vsr
+
+int vsr_rt_fft_r2c(vsr_rt_t* h, uint64_t in, int H, int W, int C, int cp_in, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(H > 0 && W > 1 && C > 0 && C <= cp_in && cp_in % 8 == 0 && (2 * C) % 8 == 0, "bad arguments");
+    const int Wc = W / 2 + 1;
+    const size_t n_in = (size_t)H * W * cp_in, n_out = (size_t)H * Wc * 2 * C;
+    auto& plan = fft_plan(h, H, W, C, cp_in);
+    cudaStream_t s = h->ctx.stream;
+    rt_half_to_float_kernel<<<blocks_for(n_in / 8), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.re->as<float>(), n_in / 8);
+    CK(cudaGetLastError());
+    cufft_ck(cufftExecR2C(plan.r2c, plan.re->as<float>(), plan.sp->as<cufftComplex>()), "cufftExecR2C");
+    rt_float_to_half_kernel<<<blocks_for(n_out / 8), 256, 0, s>>>(plan.sp->as<float>(), (__half*)(uintptr_t)out, n_out / 8,
+                                                                   1.0f / sqrtf((float)H * (float)W), h->overflow());
+    CK(cudaGetLastError());
+    h->ctx.launches += 3;
+  });
+}
+
+int vsr_rt_fft_c2r(vsr_rt_t* h, uint64_t in, int H, int W, int C, uint64_t out, int cp_out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(H > 0 && W > 1 && C > 0 && C <= cp_out && cp_out % 8 == 0 && (2 * C) % 8 == 0, "bad arguments");
+    const int Wc = W / 2 + 1;
+    const size_t n_sp = (size_t)H * Wc * 2 * C, n_re = (size_t)H * W * cp_out;
+    auto& plan = fft_plan(h, H, W, C, cp_out);
+    cudaStream_t s = h->ctx.stream;
+    rt_half_to_float_kernel<<<blocks_for(n_sp / 8), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.sp->as<float>(), n_sp / 8);
+    CK(cudaGetLastError());
+    cufft_ck(cufftExecC2R(plan.c2r, plan.sp->as<cufftComplex>(), plan.re->as<float>()), "cufftExecC2R");
+    rt_float_to_half_kernel<<<blocks_for(n_re / 8), 256, 0, s>>>(plan.re->as<float>(), (__half*)(uintptr_t)out, n_re / 8,
+                                                                  1.0f / sqrtf((float)H * (float)W), h->overflow());
+    CK(cudaGetLastError());
+    h->ctx.launches += 3;
+  });
+}
+
+int vsr_rt_lama_input(vsr_rt_t* h, const uint8_t* img, const uint8_t* mask, int ih, int iw, uint64_t out, int H, int W, int cp) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(img && mask && ih > 0 && iw > 0 && H >= ih && W >= iw && H - ih < ih && W - iw < iw && cp >= 8 && !h->capturing, "bad arguments");
+    cudaStream_t s = h->ctx.stream;
+    h->image.ensure((size_t)ih * iw * 3);
+    h->mask8.ensure((size_t)ih * iw);
+    CK(cudaMemcpyAsync(h->image.p, img, (size_t)ih * iw * 3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->mask8.p, mask, (size_t)ih * iw, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync((void*)(uintptr_t)out, 0, (size_t)H * W * cp * 2, s));
+    rt_lama_input_kernel<<<dim3((W + 255) / 256, H), 256, 0, s>>>(h->image.as<uint8_t>(), h->mask8.as<uint8_t>(), ih, iw, (__half*)(uintptr_t)out, H,
+                                                                 W, cp);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_lama_output(vsr_rt_t* h, uint64_t pred, int W, int cp, float inv_scale, int ih, int iw, uint8_t* out) {
+  return guarded([&] {
+    rt_check(h);
+    const size_t bytes = (size_t)ih * iw * 3;
+    REQUIRE(out && ih > 0 && iw > 0 && iw <= W && h->image.n >= bytes && h->mask8.n >= (size_t)ih * iw && !h->capturing, "bad arguments");
+    cudaStream_t s = h->ctx.stream;
+    h->plane.ensure(bytes);
+    if (h->out_host_bytes < bytes) {
+      if (h->out_host) cudaFreeHost(h->out_host);
+      h->out_host = nullptr;
+      CK(cudaMallocHost(&h->out_host, bytes));
+      h->out_host_bytes = bytes;
+    }
+    rt_lama_output_kernel<<<dim3((iw + 255) / 256, ih), 256, 0, s>>>((const __half*)(uintptr_t)pred, W, cp, inv_scale, h->image.as<uint8_t>(),
+                                                                   h->mask8.as<uint8_t>(), ih, iw, h->plane.as<uint8_t>());
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+    CK(cudaMemcpyAsync(h->out_host, h->plane.p, bytes, cudaMemcpyDeviceToHost, s));
+    rt_sync(h);
+    memcpy(out, h->out_host, bytes);
+  });
+}
+
 int vsr_rt_download_channel(vsr_rt_t* h, uint64_t dev_ptr, int64_t pixels, int cp, int channel, float mul, float* host) {
   return guarded([&] {
     rt_check(h);
@@ -1772,6 +1944,11 @@ int vsr_rt_conv_create(vsr_rt_t* h, const float* w, const float* bias, int cout,
 
 int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu,
                 float alpha, float bias_scale) {
+  return vsr_rt_conv_ex(h, layer_id, in_ptr, T, H, W, out_ptr, out_pitch, out_coff, relu, alpha, bias_scale, 0, 0, 0, 0);
+}
+
+int vsr_rt_conv_ex(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu,
+                   float alpha, float bias_scale, int crop_t, int crop_l, int out_h, int out_w) {
   return guarded([&] {
     rt_check(h);
     REQUIRE(layer_id >= 0 && layer_id < (int)h->layers.size(), "layer id");
@@ -1782,11 +1959,15 @@ int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W,
     Ctx& c = h->ctx;
     const RtScale sc{alpha, bias_scale, h->overflow()};
     const int tc_flags = (relu ? CONV_RELU : 0) | CONV_SCALED;
+    const bool cropped = out_h > 0 || crop_t || crop_l;
+    REQUIRE(!cropped || L.kind == RtLayer::DENSE || L.kind == RtLayer::DENSE_S2, "cropped output needs a tensor-core conv");
+    REQUIRE(!cropped || (out_h > 0 && out_w > 0 && crop_t >= 0 && crop_l >= 0), "bad crop window");
     switch (L.kind) {
       case RtLayer::DENSE: {
         ConvIO io;
         io.in = in; io.T = T; io.H = H; io.W = W; io.flags = tc_flags; io.out16 = out; io.out16_pitch = out_pitch; io.out16_coff = out_coff;
         io.alpha = alpha; io.bias_scale = bias_scale; io.overflow = sc.overflow;
+        io.crop_t = crop_t; io.crop_l = crop_l; io.out_H = out_h; io.out_W = out_w;
         run_conv(c, L.tc, io);
         break;
       }
@@ -1806,6 +1987,7 @@ int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W,
         io.in = stage->as<__half>(); io.T = T; io.H = H / 2; io.W = W / 2; io.flags = tc_flags; io.out16 = out;
         io.out16_pitch = out_pitch; io.out16_coff = out_coff;
         io.alpha = alpha; io.bias_scale = bias_scale; io.overflow = sc.overflow;
+        io.crop_t = crop_t; io.crop_l = crop_l; io.out_H = out_h; io.out_W = out_w;
         run_conv(c, L.tc, io);
         break;
       }

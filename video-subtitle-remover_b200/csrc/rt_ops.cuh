@@ -77,6 +77,173 @@ __global__ void __launch_bounds__(256) rt_elementwise_kernel(int op, const __hal
   reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
 }
 
+// ---- LAMA ---------------------------------------------------------------------------------------
+// out[oy][ox] = in[r(oy - top)][r(ox - left)], r = reflection without repeating the edge (nn.ReflectionPad2d /
+// padding_mode='reflect'); mode 0 writes zeros outside instead.  8 channels per thread.
+__global__ void __launch_bounds__(256) rt_pad_kernel(const __half* __restrict__ in, int T, int H, int W, int cp, __half* __restrict__ out,
+                                                     int OH, int OW, int top, int left, int reflect) {
+  const int c8n = cp >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)T * OH * OW * c8n) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int ox = r % OW;
+  r /= OW;
+  const int oy = r % OH;
+  const int t = r / OH;
+  int y = oy - top, x = ox - left;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (reflect) {
+    y = y < 0 ? -y : y;
+    x = x < 0 ? -x : x;
+    y = y >= H ? 2 * (H - 1) - y : y;
+    x = x >= W ? 2 * (W - 1) - x : x;
+    y = min(max(y, 0), H - 1);   // alignment rows beyond one reflection are never read by a kept output
+    x = min(max(x, 0), W - 1);
+    v = *reinterpret_cast<const uint4*>(in + (((size_t)t * H + y) * W + x) * cp + c8 * 8);
+  } else if (y >= 0 && y < H && x >= 0 && x < W) {
+    v = *reinterpret_cast<const uint4*>(in + (((size_t)t * H + y) * W + x) * cp + c8 * 8);
+  }
+  *reinterpret_cast<uint4*>(out + idx * 8) = v;
+}
+
+// zero insertion for a stride-2 transposed conv: out[2y][2x] = in[y][x], 0 elsewhere ([T,2H,2W,cp])
+__global__ void __launch_bounds__(256) rt_zero_upsample2x_kernel(const __half* __restrict__ in, int T, int H, int W, int cp,
+                                                                 __half* __restrict__ out) {
+  const int c8n = cp >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)T * 4 * H * W * c8n) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int ox = r % (2 * W);
+  r /= 2 * W;
+  const int oy = r % (2 * H);
+  const int t = r / (2 * H);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (((ox | oy) & 1) == 0) v = *reinterpret_cast<const uint4*>(in + (((size_t)t * H + (oy >> 1)) * W + (ox >> 1)) * cp + c8 * 8);
+  *reinterpret_cast<uint4*>(out + idx * 8) = v;
+}
+
+// out[p][co + c] = f(a[p][ca + c] * alpha + b[p][cb + c] * beta), c < 8*c8n: add / add+relu between channel slices of
+// tensors with different pitches (op 0 or 2 of RtEltOp)
+__global__ void __launch_bounds__(256) rt_add_slices_kernel(int relu, const __half* __restrict__ a, int pa, const __half* __restrict__ b, int pb,
+                                                            __half* __restrict__ out, int po, int c8n, size_t pixels, float alpha, float beta,
+                                                            int* overflow) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pixels * c8n) return;
+  const int c8 = idx % c8n;
+  const size_t p = idx / c8n;
+  const uint4 va = *reinterpret_cast<const uint4*>(a + p * pa + c8 * 8);
+  const uint4 vb = *reinterpret_cast<const uint4*>(b + p * pb + c8 * 8);
+  const __half2* ha = reinterpret_cast<const __half2*>(&va);
+  const __half2* hb = reinterpret_cast<const __half2*>(&vb);
+  __align__(16) __half2 o[4];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 x = __half22float2(ha[j]), y = __half22float2(hb[j]);
+    float u = fmaf(x.x, alpha, y.x * beta), w = fmaf(x.y, alpha, y.y * beta);
+    if (relu) { u = fmaxf(u, 0.f); w = fmaxf(w, 0.f); }
+    bad |= !(fabsf(u) <= 65504.f) | !(fabsf(w) <= 65504.f);
+    o[j] = __floats2half2_rn(u, w);
+  }
+  if (bad && overflow) *overflow = 1;
+  *reinterpret_cast<uint4*>(out + p * po + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// residual stream with an fp32 master copy: x32 (+)= y16, x16 = half(x32); init = 1 takes x16 as the initial value of x32.
+// 18 residual blocks then round the stream to fp16 once per block for the next conv instead of accumulating in fp16.
+__global__ void __launch_bounds__(256) rt_residual_add_kernel(float* __restrict__ x32, const __half* __restrict__ y16, __half* __restrict__ x16,
+                                                              size_t n8, int init, int* overflow) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 vy = reinterpret_cast<const uint4*>(y16)[i];
+  const __half2* hy = reinterpret_cast<const __half2*>(&vy);
+  float v[8];
+  if (init) {
+    const uint4 vx = reinterpret_cast<const uint4*>(x16)[i];
+    const __half2* hx = reinterpret_cast<const __half2*>(&vx);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hx[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  } else {
+    const float4 a = reinterpret_cast<const float4*>(x32)[2 * i], b = reinterpret_cast<const float4*>(x32)[2 * i + 1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __align__(16) __half2 o[4];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(hy[j]);
+    v[2 * j] += f.x;
+    v[2 * j + 1] += f.y;
+    bad |= !(fabsf(v[2 * j]) <= 65504.f) | !(fabsf(v[2 * j + 1]) <= 65504.f);
+    o[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  }
+  if (bad && overflow) *overflow = 1;
+  reinterpret_cast<float4*>(x32)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(x32)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+  reinterpret_cast<uint4*>(x16)[i] = *reinterpret_cast<const uint4*>(o);
+}
+
+// fp16 <-> fp32 staging around cuFFT (its half-precision transforms are power-of-two only): out = in * mul
+__global__ void __launch_bounds__(256) rt_half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t n8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = reinterpret_cast<const uint4*>(in)[i];
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+  reinterpret_cast<float4*>(out)[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+  reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+}
+__global__ void __launch_bounds__(256) rt_float_to_half_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n8, float mul,
+                                                               int* overflow) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+  const float v[8] = {a.x * mul, a.y * mul, a.z * mul, a.w * mul, b.x * mul, b.y * mul, b.z * mul, b.w * mul};
+  __align__(16) __half2 o[4];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bad |= !(fabsf(v[2 * j]) <= 65504.f) | !(fabsf(v[2 * j + 1]) <= 65504.f);
+    o[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  }
+  if (bad && overflow) *overflow = 1;
+  reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
+}
+
+// L1 (lama_util.py:12-80) + the head of the script's forward: u8 image [h,w,3] (channel order untouched) and u8 mask
+// [h,w] -> NHWC fp16 [H,W,cp]: channels 0..2 = img/255 * (1 - m), channel 3 = m, m = mask > 0; rows / columns beyond
+// h, w are the symmetric padding of pad_img_to_modulo (edge sample repeated first).
+__global__ void __launch_bounds__(256) rt_lama_input_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, int h, int w,
+                                                            __half* __restrict__ out, int H, int W, int cp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int sy = y < h ? y : 2 * h - 1 - y, sx = x < w ? x : 2 * w - 1 - x;
+  const float m = mask[(size_t)sy * w + sx] > 0 ? 1.f : 0.f;
+  __half* o = out + ((size_t)y * W + x) * cp;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = __float2half_rn(__fmul_rn(__fdiv_rn((float)img[((size_t)sy * w + sx) * 3 + c], 255.f), 1.f - m));
+  o[3] = __float2half_rn(m);
+}
+
+// the tail of the script's forward + lama_inpaint.py:25-27: result = m*pred + (1-m)*img/255 (separate fp32 ops, no
+// contraction, like torch), u8 = trunc(clip(result*255, 0, 255)), cropped to [h,w].
+__global__ void __launch_bounds__(256) rt_lama_output_kernel(const __half* __restrict__ pred, int W, int cp, float inv_scale,
+                                                             const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, int h, int w,
+                                                             uint8_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const float m = mask[(size_t)y * w + x] > 0 ? 1.f : 0.f;
+  const __half* p = pred + ((size_t)y * W + x) * cp;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float im = __fdiv_rn((float)img[((size_t)y * w + x) * 3 + c], 255.f);
+    const float r = __fadd_rn(__fmul_rn(m, __half2float(p[c]) * inv_scale), __fmul_rn(1.f - m, im));
+    out[((size_t)y * w + x) * 3 + c] = (uint8_t)fminf(fmaxf(__fmul_rn(r, 255.f), 0.f), 255.f);
+  }
+}
+
 // one channel of an NHWC fp16 tensor -> dense fp32 [pixels], divided by the tensor scale (the probability map leaves the
 // device as 4 bytes per pixel instead of the whole 64-channel pitch)
 __global__ void __launch_bounds__(256) rt_extract_channel_kernel(const __half* __restrict__ x, size_t pixels, int cp, int ch, float mul,
