@@ -156,14 +156,16 @@ int vsr_rt_add_slices(vsr_rt_t* h, int relu, uint64_t a, int pitch_a, uint64_t b
 /* residual stream with an fp32 master: x32 (+)= y16, x16 = half(x32); init != 0 starts x32 from x16 (FFCResnetBlock's id + x) */
 int vsr_rt_residual_add(vsr_rt_t* h, uint64_t x32, uint64_t y16, uint64_t x16, int64_t n_elems, int init);
 /* FourierUnit (ffc.py): rfftn(norm='ortho') of C channels of in [H,W,cp_in] -> out [H, W/2+1, 2C] with (re, im) interleaved
- * on the channel axis; the inverse takes that layout back to [H,W,cp_out] (C real channels).  cuFFT, fp32 inside. */
-int vsr_rt_fft_r2c(vsr_rt_t* h, uint64_t in, int H, int W, int C, int cp_in, uint64_t out);
-int vsr_rt_fft_c2r(vsr_rt_t* h, uint64_t in, int H, int W, int C, uint64_t out, int cp_out);
+ * on the channel axis; the inverse takes that layout back to [H,W,cp_out] (C real channels).  cuFFT, fp32 inside; T images
+ * ([T,H,W,..] tensors) go through one batched plan. */
+int vsr_rt_fft_r2c(vsr_rt_t* h, uint64_t in, int T, int H, int W, int C, int cp_in, uint64_t out);
+int vsr_rt_fft_c2r(vsr_rt_t* h, uint64_t in, int T, int H, int W, int C, uint64_t out, int cp_out);
 /* lama_util.py:12-80 + the head of big-lama's forward: host u8 image [h,w,3] and mask [h,w] -> NHWC fp16 [H,W,cp]
- * (img/255*(1-m), m), symmetric padding up to H x W.  The image and mask stay staged on the device for vsr_rt_lama_output:
+ * (img/255*(1-m), m), symmetric padding up to H x W.  The image and mask stay staged on the device in `slot` (one per image
+ * of a batch; `out` / `pred` point at that image of the batched tensor) for vsr_rt_lama_output:
  * m*pred + (1-m)*img/255 -> trunc(clip(.*255)) -> host u8 [h,w,3] (lama_inpaint.py:25-27). */
-int vsr_rt_lama_input(vsr_rt_t* h, const uint8_t* img, const uint8_t* mask, int ih, int iw, uint64_t out, int H, int W, int cp);
-int vsr_rt_lama_output(vsr_rt_t* h, uint64_t pred, int W, int cp, float inv_scale, int ih, int iw, uint8_t* out);
+int vsr_rt_lama_input(vsr_rt_t* h, const uint8_t* img, const uint8_t* mask, int ih, int iw, uint64_t out, int H, int W, int cp, int slot);
+int vsr_rt_lama_output(vsr_rt_t* h, uint64_t pred, int W, int cp, float inv_scale, int ih, int iw, int slot, uint8_t* out);
 /* max |x| of a tensor (inf when it holds a non-finite value): calibration of the scales.  Synchronises. */
 int vsr_rt_absmax(vsr_rt_t* h, uint64_t dev_ptr, int64_t n_elems, float* out);
 /* host[i] = tensor[i][channel] * mul as fp32, i < pixels (the probability map: one channel of a 64-pitch tensor). */

@@ -27,4 +27,9 @@ for name, (H, W) in (("small", (120, 256)), ("strip1080p", (360, 1920))):
         eng.inpaint(img, mask)
     res[name]["e2e_ms"] = (time.perf_counter() - t0) / N * 1e3
     res[name]["network_ms"] = eng.model.time_network(10)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng._inpaint_batch([img] * 8, [mask] * 8)
+    res[name]["batch4_e2e_ms_per_frame"] = (time.perf_counter() - t0) / 24 * 1e3
+    res[name]["batch4_network_ms_per_frame"] = eng.model.time_network(10) / 4
 print(json.dumps(res, indent=1))

@@ -79,9 +79,15 @@ class FakeRuntime:
         self.bufs[h] = np.array(arr, np.float32)
         return h
 
+    def _v4(self, t):
+        """[n, h, w, channels from the view's first channel on] (channel-slice views advance the pointer by 2*c0 bytes)."""
+        base, c0 = t.ptr - t.ptr % 0x1000, (t.ptr % 0x1000) // 2
+        n = getattr(t, "n", 1)
+        return self.bufs[base][: n * t.h * t.w * t.cp].reshape(n, t.h, t.w, t.cp)[:, :, :, c0:]
+
     def _view(self, t):
-        base, c0 = t.ptr - t.ptr % 0x1000, (t.ptr % 0x1000) // 2      # channel-slice views advance the pointer by 2*c0 bytes
-        return self.bufs[base][: t.h * t.w * t.cp].reshape(t.h, t.w, t.cp)[:, :, c0:]
+        v = self._v4(t)
+        return v[0] if v.shape[0] == 1 else v.reshape(v.shape[0] * v.shape[1], v.shape[2], v.shape[3])   # element-wise ops: images stacked on rows
 
     def conv_create(self, w, bias, cout, cin, cin_pitch, kh, kw, stride, pad_t, pad_l, dil, groups, transposed):
         w = np.array(w, np.float32)
@@ -109,7 +115,7 @@ class FakeRuntime:
         if self._recording("conv", lid, x, y, relu, alpha, bias_scale, out_coff, crop):
             return
         L = self.layers[lid]
-        xin = torch.from_numpy(self._view(x)[:, :, : L["cin"]].copy()).permute(2, 0, 1)[None]
+        xin = torch.from_numpy(self._v4(x)[:, :, :, : L["cin"]].copy()).permute(0, 3, 1, 2)
         if crop is not None:   # 'same' conv on the (padded) input grid, keep the window [crop, crop + y.hw)
             assert not L["transposed"] and L["groups"] == 1 and L["cin"] >= 16 and L["cout"] >= 8, "cropped output needs a tensor-core conv"
             p = (L["kh"] - 1) * L["dil"] // 2
@@ -132,13 +138,13 @@ class FakeRuntime:
         out = out * alpha + (L["b"] * bias_scale)[None, :, None, None]
         if relu:
             out = out.relu()
-        res = out[0].permute(1, 2, 0).numpy()
+        res = out.permute(0, 2, 3, 1).numpy()
         if np.abs(res).max(initial=0.0) > 65504.0 or not np.isfinite(res).all():
             self._flag = True
-        v = self._view(y)
+        v = self._v4(y)
         if out_coff == 0 and crop is None:
             v[:] = 0           # the device kernels write zeros into the channel padding of a plain output tensor
-        v[:, :, out_coff:out_coff + L["cout"]] = res
+        v[:, :, :, out_coff:out_coff + L["cout"]] = res
         self.launches += 1
 
     # ---- LAMA-only entry points
@@ -146,15 +152,15 @@ class FakeRuntime:
         if self._recording("pad", x, y, top, left, reflect):
             return
         bottom, right = y.h - x.h - top, y.w - x.w - left
-        self._view(y)[:] = np.pad(self._view(x), ((top, bottom), (left, right), (0, 0)), mode="reflect" if reflect else "constant")
+        self._v4(y)[:] = np.pad(self._v4(x), ((0, 0), (top, bottom), (left, right), (0, 0)), mode="reflect" if reflect else "constant")
         self.launches += 1
 
     def zero_upsample(self, x, y):
         if self._recording("zero_upsample", x, y):
             return
-        v = self._view(y)
+        v = self._v4(y)
         v[:] = 0
-        v[::2, ::2] = self._view(x)
+        v[:, ::2, ::2] = self._v4(x)
         self.launches += 1
 
     def add_slices(self, relu, a, b, y, channels):
@@ -178,36 +184,37 @@ class FakeRuntime:
     def fft_r2c(self, x, y):
         if self._recording("fft_r2c", x, y):
             return
-        f = np.fft.rfft2(self._view(x)[:, :, : x.c].astype(np.float64), axes=(0, 1), norm="ortho")
-        out = np.stack([f.real, f.imag], -1).reshape(y.h, y.w, 2 * x.c)       # channel 2c + {re, im}
-        self._view(y)[:, :, : 2 * x.c] = out.astype(np.float32)
+        f = np.fft.rfft2(self._v4(x)[..., : x.c].astype(np.float64), axes=(1, 2), norm="ortho")
+        out = np.stack([f.real, f.imag], -1).reshape(f.shape[0], y.h, y.w, 2 * x.c)       # channel 2c + {re, im}
+        self._v4(y)[..., : 2 * x.c] = out.astype(np.float32)
         self.launches += 3
 
     def fft_c2r(self, x, y):
         if self._recording("fft_c2r", x, y):
             return
-        v = self._view(x)[:, :, : 2 * y.c].astype(np.float64).reshape(x.h, x.w, y.c, 2)
-        out = np.fft.irfft2(v[..., 0] + 1j * v[..., 1], s=(y.h, y.w), axes=(0, 1), norm="ortho")
-        self._view(y)[:, :, : y.c] = out.astype(np.float32)
+        v = self._v4(x)[..., : 2 * y.c].astype(np.float64).reshape(-1, x.h, x.w, y.c, 2)
+        out = np.fft.irfft2(v[..., 0] + 1j * v[..., 1], s=(y.h, y.w), axes=(1, 2), norm="ortho")
+        self._v4(y)[..., : y.c] = out.astype(np.float32)
         self.launches += 3
 
-    def lama_input(self, img, mask, y):
+    def lama_input(self, img, mask, y, slot=0):
         assert self._rec is None
         h, w = mask.shape
         m = (np.pad(mask, ((0, y.h - h), (0, y.w - w)), mode="symmetric") > 0).astype(np.float32)
         im = np.pad(img.astype(np.float32) / np.float32(255), ((0, y.h - h), (0, y.w - w), (0, 0)), mode="symmetric")
-        v = self._view(y)
+        v = self._v4(y)[slot]
         v[:] = 0
         v[:, :, :3] = im * (1 - m)[:, :, None]
         v[:, :, 3] = m
-        self._staged = (img.copy(), mask.copy())
+        self._staged = getattr(self, "_staged", {})
+        self._staged[slot] = (img.copy(), mask.copy())
         self.launches += 1
 
-    def lama_output(self, pred, ih, iw):
+    def lama_output(self, pred, ih, iw, slot=0):
         assert self._rec is None
-        img, mask = self._staged
+        img, mask = self._staged[slot]
         m = (mask > 0).astype(np.float32)[:, :, None]
-        res = m * self._view(pred)[:ih, :iw, :3] + (1 - m) * (img.astype(np.float32) / np.float32(255))
+        res = m * self._v4(pred)[slot, :ih, :iw, :3] + (1 - m) * (img.astype(np.float32) / np.float32(255))
         self.launches += 1
         return np.clip(res * 255, 0, 255).astype(np.uint8)
 

@@ -156,7 +156,7 @@ def test_inpaint_vs_oracle_random_weights(lama_rand):
 
 def test_call_strips_vs_oracle_random_weights(lama_rand):
     eng, w = lama_rand
-    H, W, T = 270, 480, 3
+    H, W, T = 270, 480, 6          # strips go through the network 4 + 2 per launch
     frames = O.synthetic_clip(T, H, W, seed=31)
     keep = [f.copy() for f in frames]
     mask = O.default_mask(H, W)
@@ -167,6 +167,9 @@ def test_call_strips_vs_oracle_random_weights(lama_rand):
     for o, r, f in zip(out, want, keep):
         assert np.array_equal(o[:y0], f[:y0]) and np.array_equal(o[y1:], f[y1:])
         _check(o[y0:y1], r[y0:y1], f[y0:y1], mask[y0:y1])
+    assert sorted(k[0] for k in eng.model._programs if k[1:] == (96, 480)) == [2, 4]
+    single = eng.inpaint(keep[5][y0:y1], mask[y0:y1])                 # batching does not change a frame's result
+    assert np.abs(single.astype(np.int32) - out[5][y0:y1]).max() <= 1
 
 
 def test_golden_real_weights(capi):

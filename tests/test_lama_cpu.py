@@ -30,3 +30,28 @@ def test_lama_builder_on_cpu_runtime(hw):
     n0 = rt.launch_count
     again = eng.inpaint(img, mask)                            # second call replays the recorded graph
     assert np.array_equal(again, got) and rt.launch_count - n0 < 560   # 18 blocks x (2 x 14 + 1) launches + stem, downs, ups, head
+
+
+def test_lama_batches_and_strip_call():
+    """`__call__` on 6 frames: strips go through the network 4 + 2 per launch (two compiled batch sizes); every frame equals
+    its own single-image result, and the oracle's `lama_call`."""
+    from fake_rt import FakeRuntime
+    from oracle import sttn_oracle as O
+    from vsr_b200.lama_inpaint import LamaInpaint
+
+    w = L.random_weights(4)
+    eng = LamaInpaint("cuda:0", {k: v.numpy() for k, v in w.items()}, runtime=FakeRuntime())
+    H, W = 128, 160
+    frames = O.synthetic_clip(6, H, W, seed=41)
+    keep = [f.copy() for f in frames]
+    mask = O.create_mask((H, W), [(30, 130, 96, 118)])
+    out = eng(frames, mask)
+    assert all(np.array_equal(a, b) for a, b in zip(frames, keep))
+    assert sorted(k[0] for k in eng.model._programs) == [2, 4]
+    want = L.lama_call(w, frames, mask)
+    for o, r in zip(out, want):
+        d = np.abs(o.astype(np.int32) - r)
+        assert d.max() <= 1 and (d > 0).mean() < 0.01
+    (y0, y1, _, _), = O.get_inpaint_area_by_mask(W, H, int(W * 3 / 16), mask)
+    single = eng.inpaint(frames[4][y0:y1], mask[y0:y1])
+    assert np.abs(single.astype(np.int32) - out[4][y0:y1]).max() <= 1

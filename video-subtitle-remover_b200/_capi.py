@@ -95,10 +95,10 @@ _PROTOS = {
     "vsr_rt_add_slices": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int64,
                                     C.c_float, C.c_float]),
     "vsr_rt_residual_add": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int]),
-    "vsr_rt_fft_r2c": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
-    "vsr_rt_fft_c2r": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
-    "vsr_rt_lama_input": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]),
-    "vsr_rt_lama_output": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
+    "vsr_rt_fft_r2c": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_fft_c2r": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "vsr_rt_lama_input": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vsr_rt_lama_output": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _u8p]),
     "vsr_rt_absmax": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.POINTER(C.c_float)]),
     "vsr_rt_download_channel": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_float, _f32p]),
     "vsr_rt_overflow": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

@@ -1210,7 +1210,7 @@ struct vsr_rt {
   std::vector<std::unique_ptr<DevBuf>> bufs;
   std::vector<std::unique_ptr<RtLayer>> layers;
   DevBuf image;    // BGR u8 staging of the pre-processing
-  DevBuf mask8;    // u8 mask staging (LAMA)
+  std::vector<std::pair<std::unique_ptr<DevBuf>, std::unique_ptr<DevBuf>>> lama_slots;  // u8 image + mask staging per batch slot (LAMA)
   struct FftPlan {
     cufftHandle r2c = 0, c2r = 0;
     std::shared_ptr<DevBuf> re, sp;  // fp32 staging of the real side [H][W][pitch] and of the spectrum [H][W/2+1][C] complex
@@ -1729,64 +1729,72 @@ static vsr_rt::FftPlan& fft_plan(vsr_rt* h, int H, int W, int C, int pitch) {
 }
 }  // namespace vsr
 
-int vsr_rt_fft_r2c(vsr_rt_t* h, uint64_t in, int H, int W, int C, int cp_in, uint64_t out) {
+int vsr_rt_fft_r2c(vsr_rt_t* h, uint64_t in, int T, int H, int W, int C, int cp_in, uint64_t out) {
   return guarded([&] {
     rt_check(h);
-    REQUIRE(H > 0 && W > 1 && C > 0 && C <= cp_in && cp_in % 8 == 0 && (2 * C) % 8 == 0, "bad arguments");
+    REQUIRE(T > 0 && H > 0 && W > 1 && C > 0 && C <= cp_in && cp_in % 8 == 0 && (2 * C) % 8 == 0, "bad arguments");
+    REQUIRE(T == 1 || C == cp_in, "batched FourierUnit needs a dense channel pitch");
     const int Wc = W / 2 + 1;
-    const size_t n_in = (size_t)H * W * cp_in, n_out = (size_t)H * Wc * 2 * C;
-    auto& plan = fft_plan(h, H, W, C, cp_in);
+    auto& plan = fft_plan(h, H, W, T * C, T * cp_in);
     cudaStream_t s = h->ctx.stream;
-    rt_half_to_float_kernel<<<blocks_for(n_in / 8), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.re->as<float>(), n_in / 8);
+    const size_t n_in = (size_t)T * H * W * cp_in, n_out = (size_t)T * H * Wc * 2 * C;
+    rt_half_to_float_kernel<<<blocks_for(n_in / 8), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.re->as<float>(), T, (size_t)H * W, cp_in / 8);
     CK(cudaGetLastError());
     cufft_ck(cufftExecR2C(plan.r2c, plan.re->as<float>(), plan.sp->as<cufftComplex>()), "cufftExecR2C");
-    rt_float_to_half_kernel<<<blocks_for(n_out / 8), 256, 0, s>>>(plan.sp->as<float>(), (__half*)(uintptr_t)out, n_out / 8,
+    rt_float_to_half_kernel<<<blocks_for(n_out / 8), 256, 0, s>>>(plan.sp->as<float>(), (__half*)(uintptr_t)out, T, (size_t)H * Wc, 2 * C / 8,
                                                                    1.0f / sqrtf((float)H * (float)W), h->overflow());
     CK(cudaGetLastError());
     h->ctx.launches += 3;
   });
 }
 
-int vsr_rt_fft_c2r(vsr_rt_t* h, uint64_t in, int H, int W, int C, uint64_t out, int cp_out) {
+int vsr_rt_fft_c2r(vsr_rt_t* h, uint64_t in, int T, int H, int W, int C, uint64_t out, int cp_out) {
   return guarded([&] {
     rt_check(h);
-    REQUIRE(H > 0 && W > 1 && C > 0 && C <= cp_out && cp_out % 8 == 0 && (2 * C) % 8 == 0, "bad arguments");
+    REQUIRE(T > 0 && H > 0 && W > 1 && C > 0 && C <= cp_out && cp_out % 8 == 0 && (2 * C) % 8 == 0, "bad arguments");
+    REQUIRE(T == 1 || C == cp_out, "batched FourierUnit needs a dense channel pitch");
     const int Wc = W / 2 + 1;
-    const size_t n_sp = (size_t)H * Wc * 2 * C, n_re = (size_t)H * W * cp_out;
-    auto& plan = fft_plan(h, H, W, C, cp_out);
+    auto& plan = fft_plan(h, H, W, T * C, T * cp_out);
     cudaStream_t s = h->ctx.stream;
-    rt_half_to_float_kernel<<<blocks_for(n_sp / 8), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.sp->as<float>(), n_sp / 8);
+    const size_t n_sp = (size_t)T * H * Wc * 2 * C, n_re = (size_t)T * H * W * cp_out;
+    rt_half_to_float_kernel<<<blocks_for(n_sp / 8), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.sp->as<float>(), T, (size_t)H * Wc, 2 * C / 8);
     CK(cudaGetLastError());
     cufft_ck(cufftExecC2R(plan.c2r, plan.sp->as<cufftComplex>(), plan.re->as<float>()), "cufftExecC2R");
-    rt_float_to_half_kernel<<<blocks_for(n_re / 8), 256, 0, s>>>(plan.re->as<float>(), (__half*)(uintptr_t)out, n_re / 8,
+    rt_float_to_half_kernel<<<blocks_for(n_re / 8), 256, 0, s>>>(plan.re->as<float>(), (__half*)(uintptr_t)out, T, (size_t)H * W, cp_out / 8,
                                                                   1.0f / sqrtf((float)H * (float)W), h->overflow());
     CK(cudaGetLastError());
     h->ctx.launches += 3;
   });
 }
 
-int vsr_rt_lama_input(vsr_rt_t* h, const uint8_t* img, const uint8_t* mask, int ih, int iw, uint64_t out, int H, int W, int cp) {
+int vsr_rt_lama_input(vsr_rt_t* h, const uint8_t* img, const uint8_t* mask, int ih, int iw, uint64_t out, int H, int W, int cp, int slot) {
   return guarded([&] {
     rt_check(h);
     REQUIRE(img && mask && ih > 0 && iw > 0 && H >= ih && W >= iw && H - ih < ih && W - iw < iw && cp >= 8 && !h->capturing, "bad arguments");
+    REQUIRE(slot >= 0 && slot < 64, "staging slot");
     cudaStream_t s = h->ctx.stream;
-    h->image.ensure((size_t)ih * iw * 3);
-    h->mask8.ensure((size_t)ih * iw);
-    CK(cudaMemcpyAsync(h->image.p, img, (size_t)ih * iw * 3, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->mask8.p, mask, (size_t)ih * iw, cudaMemcpyHostToDevice, s));
+    while ((int)h->lama_slots.size() <= slot) h->lama_slots.emplace_back(std::make_unique<DevBuf>(), std::make_unique<DevBuf>());
+    DevBuf& dimg = *h->lama_slots[slot].first;
+    DevBuf& dmask = *h->lama_slots[slot].second;
+    dimg.ensure((size_t)ih * iw * 3);
+    dmask.ensure((size_t)ih * iw);
+    CK(cudaMemcpyAsync(dimg.p, img, (size_t)ih * iw * 3, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dmask.p, mask, (size_t)ih * iw, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync((void*)(uintptr_t)out, 0, (size_t)H * W * cp * 2, s));
-    rt_lama_input_kernel<<<dim3((W + 255) / 256, H), 256, 0, s>>>(h->image.as<uint8_t>(), h->mask8.as<uint8_t>(), ih, iw, (__half*)(uintptr_t)out, H,
-                                                                 W, cp);
+    rt_lama_input_kernel<<<dim3((W + 255) / 256, H), 256, 0, s>>>(dimg.as<uint8_t>(), dmask.as<uint8_t>(), ih, iw, (__half*)(uintptr_t)out, H, W, cp);
     CK(cudaGetLastError());
     ++h->ctx.launches;
   });
 }
 
-int vsr_rt_lama_output(vsr_rt_t* h, uint64_t pred, int W, int cp, float inv_scale, int ih, int iw, uint8_t* out) {
+int vsr_rt_lama_output(vsr_rt_t* h, uint64_t pred, int W, int cp, float inv_scale, int ih, int iw, int slot, uint8_t* out) {
   return guarded([&] {
     rt_check(h);
     const size_t bytes = (size_t)ih * iw * 3;
-    REQUIRE(out && ih > 0 && iw > 0 && iw <= W && h->image.n >= bytes && h->mask8.n >= (size_t)ih * iw && !h->capturing, "bad arguments");
+    REQUIRE(out && ih > 0 && iw > 0 && iw <= W && slot >= 0 && slot < (int)h->lama_slots.size() && !h->capturing, "bad arguments");
+    DevBuf& dimg = *h->lama_slots[slot].first;
+    DevBuf& dmask = *h->lama_slots[slot].second;
+    REQUIRE(dimg.n >= bytes && dmask.n >= (size_t)ih * iw, "vsr_rt_lama_input was not called for this slot");
     cudaStream_t s = h->ctx.stream;
     h->plane.ensure(bytes);
     if (h->out_host_bytes < bytes) {
@@ -1795,8 +1803,8 @@ int vsr_rt_lama_output(vsr_rt_t* h, uint64_t pred, int W, int cp, float inv_scal
       CK(cudaMallocHost(&h->out_host, bytes));
       h->out_host_bytes = bytes;
     }
-    rt_lama_output_kernel<<<dim3((iw + 255) / 256, ih), 256, 0, s>>>((const __half*)(uintptr_t)pred, W, cp, inv_scale, h->image.as<uint8_t>(),
-                                                                   h->mask8.as<uint8_t>(), ih, iw, h->plane.as<uint8_t>());
+    rt_lama_output_kernel<<<dim3((iw + 255) / 256, ih), 256, 0, s>>>((const __half*)(uintptr_t)pred, W, cp, inv_scale, dimg.as<uint8_t>(),
+                                                                   dmask.as<uint8_t>(), ih, iw, h->plane.as<uint8_t>());
     CK(cudaGetLastError());
     ++h->ctx.launches;
     CK(cudaMemcpyAsync(h->out_host, h->plane.p, bytes, cudaMemcpyDeviceToHost, s));

@@ -185,21 +185,33 @@ __global__ void __launch_bounds__(256) rt_residual_add_kernel(float* __restrict_
   reinterpret_cast<uint4*>(x16)[i] = *reinterpret_cast<const uint4*>(o);
 }
 
-// fp16 <-> fp32 staging around cuFFT (its half-precision transforms are power-of-two only): out = in * mul
-__global__ void __launch_bounds__(256) rt_half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t n8) {
+// fp16 <-> fp32 staging around cuFFT (its half-precision transforms are power-of-two only).  The fp16 side is [T][P][K]
+// (T images of P pixels, K channels), the fp32 side [P][T][K]: folding the image index into the channel axis lets ONE
+// batched cuFFT plan (stride T*K between pixels, distance 1 between channels) transform all T images.  out = in * mul.
+__global__ void __launch_bounds__(256) rt_half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, int T, size_t P, int K8) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
+  if (i >= (size_t)T * P * K8) return;
+  const int k = i % K8;
+  const size_t tp = i / K8;
+  const size_t p = tp % P;
+  const int t = tp / P;
   const uint4 v = reinterpret_cast<const uint4*>(in)[i];
   const __half2* h = reinterpret_cast<const __half2*>(&v);
   const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
-  reinterpret_cast<float4*>(out)[2 * i] = make_float4(a.x, a.y, b.x, b.y);
-  reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+  float4* o = reinterpret_cast<float4*>(out) + 2 * ((p * T + t) * K8 + k);
+  o[0] = make_float4(a.x, a.y, b.x, b.y);
+  o[1] = make_float4(c.x, c.y, d.x, d.y);
 }
-__global__ void __launch_bounds__(256) rt_float_to_half_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n8, float mul,
-                                                               int* overflow) {
+__global__ void __launch_bounds__(256) rt_float_to_half_kernel(const float* __restrict__ in, __half* __restrict__ out, int T, size_t P, int K8,
+                                                               float mul, int* overflow) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+  if (i >= (size_t)T * P * K8) return;
+  const int k = i % K8;
+  const size_t tp = i / K8;
+  const size_t p = tp % P;
+  const int t = tp / P;
+  const float4* src = reinterpret_cast<const float4*>(in) + 2 * ((p * T + t) * K8 + k);
+  const float4 a = src[0], b = src[1];
   const float v[8] = {a.x * mul, a.y * mul, a.z * mul, a.w * mul, b.x * mul, b.y * mul, b.z * mul, b.w * mul};
   __align__(16) __half2 o[4];
   bool bad = false;

@@ -110,13 +110,13 @@ class _Tensor:
     The buffer holds value * scale (a power of two, see `_calibrate`); `follow` ties the scale to another tensor's
     (ReLU, pooling, up-sampling and concat are positively homogeneous: they keep the scale of their input)."""
 
-    def __init__(self, ptr, c, h, w, cp, perm=None, follow=None):
-        self.ptr, self.c, self.h, self.w, self.cp, self.perm = ptr, c, h, w, cp, perm
+    def __init__(self, ptr, c, h, w, cp, perm=None, follow=None, n=1):
+        self.ptr, self.c, self.h, self.w, self.cp, self.perm, self.n = ptr, c, h, w, cp, perm, n   # n images [n,h,w,cp]
         self._scale, self.follow = 1.0, follow
 
     @property
     def pixels(self):
-        return self.h * self.w
+        return self.n * self.h * self.w
 
     @property
     def scale(self):

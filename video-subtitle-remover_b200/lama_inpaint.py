@@ -49,16 +49,16 @@ def load_lama_weights(path_or_dict) -> Dict[str, np.ndarray]:
 
 
 class _LamaRuntime(_DeviceRuntime):
-    """The detector's runtime wrapper plus the LAMA-only entry points."""
+    """The detector's runtime wrapper plus the LAMA-only entry points; tensors are [n, h, w, cp] batches."""
 
     def conv_ex(self, lid, x, y, relu, out_coff=0, crop=(0, 0)):
-        _capi.check(self.L.vsr_rt_conv_ex(self.h, lid, x.ptr, 1, x.h, x.w, y.ptr, y.cp, out_coff, relu, 1.0, 1.0, crop[0], crop[1], y.h, y.w))
+        _capi.check(self.L.vsr_rt_conv_ex(self.h, lid, x.ptr, x.n, x.h, x.w, y.ptr, y.cp, out_coff, relu, 1.0, 1.0, crop[0], crop[1], y.h, y.w))
 
     def pad(self, x, y, top, left, reflect=1):
-        _capi.check(self.L.vsr_rt_pad(self.h, x.ptr, 1, x.h, x.w, x.cp, y.ptr, y.h, y.w, top, left, reflect))
+        _capi.check(self.L.vsr_rt_pad(self.h, x.ptr, x.n, x.h, x.w, x.cp, y.ptr, y.h, y.w, top, left, reflect))
 
     def zero_upsample(self, x, y):
-        _capi.check(self.L.vsr_rt_zero_upsample2x(self.h, x.ptr, 1, x.h, x.w, x.cp, y.ptr))
+        _capi.check(self.L.vsr_rt_zero_upsample2x(self.h, x.ptr, x.n, x.h, x.w, x.cp, y.ptr))
 
     def add_slices(self, relu, a, b, y, channels):
         _capi.check(self.L.vsr_rt_add_slices(self.h, relu, a.ptr, a.cp, b.ptr, b.cp, y.ptr, y.cp, channels, y.pixels, 1.0, 1.0))
@@ -67,24 +67,25 @@ class _LamaRuntime(_DeviceRuntime):
         _capi.check(self.L.vsr_rt_residual_add(self.h, x32, y.ptr, x.ptr, x.pixels * x.cp, 1 if init else 0))
 
     def fft_r2c(self, x, y):
-        _capi.check(self.L.vsr_rt_fft_r2c(self.h, x.ptr, x.h, x.w, x.c, x.cp, y.ptr))
+        _capi.check(self.L.vsr_rt_fft_r2c(self.h, x.ptr, x.n, x.h, x.w, x.c, x.cp, y.ptr))
 
     def fft_c2r(self, x, y):
-        _capi.check(self.L.vsr_rt_fft_c2r(self.h, x.ptr, y.h, y.w, y.c, y.ptr, y.cp))
+        _capi.check(self.L.vsr_rt_fft_c2r(self.h, x.ptr, y.n, y.h, y.w, y.c, y.ptr, y.cp))
 
-    def lama_input(self, img, mask, y):
-        _capi.check(self.L.vsr_rt_lama_input(self.h, _capi.ptr(img, C.c_uint8), _capi.ptr(mask, C.c_uint8), img.shape[0], img.shape[1], y.ptr,
-                                             y.h, y.w, y.cp))
+    def lama_input(self, img, mask, y, slot=0):
+        _capi.check(self.L.vsr_rt_lama_input(self.h, _capi.ptr(img, C.c_uint8), _capi.ptr(mask, C.c_uint8), img.shape[0], img.shape[1],
+                                             y.ptr + slot * y.h * y.w * y.cp * 2, y.h, y.w, y.cp, slot))
 
-    def lama_output(self, pred, ih, iw) -> np.ndarray:
+    def lama_output(self, pred, ih, iw, slot=0) -> np.ndarray:
         out = np.empty((ih, iw, 3), np.uint8)
-        _capi.check(self.L.vsr_rt_lama_output(self.h, pred.ptr, pred.w, pred.cp, 1.0, ih, iw, _capi.ptr(out, C.c_uint8)))
+        _capi.check(self.L.vsr_rt_lama_output(self.h, pred.ptr + slot * pred.h * pred.w * pred.cp * 2, pred.w, pred.cp, 1.0, ih, iw, slot,
+                                              _capi.ptr(out, C.c_uint8)))
         return out
 
 
 def _view(t: _Tensor, c0: int, c: int) -> _Tensor:
     """channels [c0, c0 + c) of an NHWC tensor: same pitch, pointer advanced by c0 fp16 elements."""
-    return _Tensor(t.ptr + 2 * c0, c, t.h, t.w, t.cp)
+    return _Tensor(t.ptr + 2 * c0, c, t.h, t.w, t.cp, n=t.n)
 
 
 def _bn_fold(w, p):
@@ -124,16 +125,15 @@ class LamaNetwork:
                                                                        cin, cin_pitch, kh, kw, stride, pad, pad, 1, 1, False)
         return lid
 
-    def _new(self, c, h, w) -> _Tensor:
-        cp = _r(c, 64)
-        return _Tensor(self._rt.alloc(h * w * cp * 2), c, h, w, cp)
-
-    def _compile(self, H: int, W: int) -> _Program:
+    def _compile(self, N: int, H: int, W: int) -> _Program:
         if H % 8 or W % 8 or H < 16 or W < 16:
             raise _capi.VsrError("LAMA input must be padded to multiples of 8 (>= 16)")
         rt, w, prog = self._rt, self.w, _Program()
         run = prog.steps.append
-        new = self._new
+
+        def new(c, h, wd) -> _Tensor:
+            cp = _r(c, 64)
+            return _Tensor(rt.alloc(N * h * wd * cp * 2), c, h, wd, cp, n=N)
 
         # model.0/1: ReflectionPad2d(3) + conv7x7 4->64 + BN + ReLU.  The 4 input channels sit in a 16-channel tensor.
         prog.inp = new(16, H, W)
@@ -235,26 +235,40 @@ class LamaNetwork:
             prog.graph = rt.capture_end()
         return prog
 
+    MAX_BATCH = 4   # the reference's mini-batch (lama_inpaint.py:38); one CUDA graph per (batch, H, W)
+
     def forward_u8(self, image: np.ndarray, mask: np.ndarray) -> np.ndarray:
         """`LamaInpaint.inpaint` minus the model loading: image HxWx3 u8 (channel order untouched, lama_util.py:12-28),
         mask HxW u8 (> 0 = hole) -> HxWx3 u8."""
-        image = np.ascontiguousarray(image, np.uint8)
-        mask = np.ascontiguousarray(mask if mask.ndim == 2 else mask[:, :, 0], np.uint8)
-        if image.ndim != 3 or image.shape[2] != 3 or mask.shape != image.shape[:2]:
-            raise ValueError("expected image [H,W,3] and mask [H,W] of the same size")
-        h, wd = mask.shape
+        return self.forward_batch([image], [mask])[0]
+
+    def forward_batch(self, images: Sequence[np.ndarray], masks: Sequence[np.ndarray]) -> List[np.ndarray]:
+        """Same-size images through the network, MAX_BATCH per graph launch (batch-norm is in eval mode: the result of an
+        image does not depend on what it is batched with)."""
+        imgs = [np.ascontiguousarray(i, np.uint8) for i in images]
+        msks = [np.ascontiguousarray(m if m.ndim == 2 else m[:, :, 0], np.uint8) for m in masks]
+        if len(imgs) != len(msks) or not imgs:
+            raise ValueError("one mask per image")
+        h, wd = msks[0].shape
+        for i, m in zip(imgs, msks):
+            if i.ndim != 3 or i.shape != (h, wd, 3) or m.shape != (h, wd):
+                raise ValueError("expected images [H,W,3] and masks [H,W] of one common size")
         H, W = _r(h, 8), _r(wd, 8)
         if H - h >= h or W - wd >= wd:
             raise ValueError("image too small for symmetric padding to a multiple of 8")
-        prog = self._programs.get((H, W))
-        if prog is None:
-            prog = self._programs[(H, W)] = self._compile(H, W)
-        rt = self._rt
-        rt.lama_input(image, mask, prog.inp)
-        rt.graph_launch(prog.graph)
-        out = rt.lama_output(prog.out, h, wd)
-        if rt.overflow():
-            raise _capi.VsrError("LAMA activations left the fp16 range on this frame")
+        rt, out = self._rt, []
+        for s0 in range(0, len(imgs), self.MAX_BATCH):
+            n = min(self.MAX_BATCH, len(imgs) - s0)
+            prog = self._programs.get((n, H, W))
+            if prog is None:
+                prog = self._programs[(n, H, W)] = self._compile(n, H, W)
+            self._last = prog
+            for j in range(n):
+                rt.lama_input(imgs[s0 + j], msks[s0 + j], prog.inp, j)
+            rt.graph_launch(prog.graph)
+            out.extend(rt.lama_output(prog.out, h, wd, j) for j in range(n))
+            if rt.overflow():
+                raise _capi.VsrError("LAMA activations left the fp16 range on this frame")
         return out
 
     @property
@@ -262,10 +276,10 @@ class LamaNetwork:
         return self._rt.launch_count
 
     def time_network(self, iters: int = 10) -> float:
-        """ms per replay of the network graph of the last-used size (input already on the device)."""
+        """ms per replay of the network graph of the last-used (batch, size) (inputs already on the device)."""
         import time
 
-        prog = next(reversed(self._programs.values()))
+        prog = self._last
         rt = self._rt
         rt.graph_launch(prog.graph)
         rt.sync()
@@ -288,9 +302,8 @@ class LamaInpaint:
         return self.model.forward_u8(np.array(image), np.array(mask))
 
     def _inpaint_batch(self, images: Sequence[np.ndarray], masks: Sequence[np.ndarray]) -> List[np.ndarray]:
-        """lama_inpaint.py:30-66.  The reference's mini-batches of 4 only bound its memory use: batch-norm runs in eval
-        mode, so every frame's result is independent of the batching; frames go through the recorded graph one by one."""
-        return [self.inpaint(i, m) for i, m in zip(images, masks)]
+        """lama_inpaint.py:30-66: mini-batches of 4 frames per network launch, like the reference."""
+        return self.model.forward_batch([np.array(i) for i in images], [np.array(m) for m in masks])
 
     def __call__(self, input_frames: List[np.ndarray], input_mask: np.ndarray) -> List[np.ndarray]:
         """lama_inpaint.py:68-114: strips of height int(W*3/16) around the mask rows at native resolution; each strip is
@@ -300,9 +313,10 @@ class LamaInpaint:
         areas = get_inpaint_area_by_mask(W, H, int(W * 3 / 16), mask)
         frames = [f.copy() for f in input_frames]
         for (y0, y1, _, _) in areas:
-            strip_mask = np.ascontiguousarray(mask[y0:y1])
-            for f in frames:
-                f[y0:y1] = self.inpaint(np.ascontiguousarray(f[y0:y1]), strip_mask)
+            strip_mask = mask[y0:y1]
+            comps = self._inpaint_batch([f[y0:y1] for f in frames], [strip_mask] * len(frames))
+            for f, c in zip(frames, comps):
+                f[y0:y1] = c
         return frames
 
 
