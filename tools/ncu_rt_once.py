@@ -14,4 +14,5 @@ else:
     strip = np.ascontiguousarray(img[700:1060])
     mask = np.zeros((360, 1920), np.uint8)
     mask[200:320, 300:1600] = 255
-    LamaInpaint("cuda:0", os.path.join("weights", "big-lama", "big-lama.npz")).inpaint(strip, mask)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    LamaInpaint("cuda:0", os.path.join("weights", "big-lama", "big-lama.npz"))._inpaint_batch([strip] * n, [mask] * n)

@@ -1709,22 +1709,23 @@ namespace vsr {
 static void cufft_ck(cufftResult r, const char* what) {
   if (r != CUFFT_SUCCESS) throw Error(VSR_ERR_CUDA, std::string(what) + " -> cuFFT error " + std::to_string((int)r));
 }
-// plans of the FourierUnit transforms over C interleaved channels: real side [H][W][pitch], spectrum [H][W/2+1][C] complex
-static vsr_rt::FftPlan& fft_plan(vsr_rt* h, int H, int W, int C, int pitch) {
-  const std::array<int, 4> key{H, W, C, pitch};
+// plans of the FourierUnit transforms: `batch` contiguous planar signals [H][W] real <-> [H][W/2+1] complex
+static vsr_rt::FftPlan& fft_plan(vsr_rt* h, int H, int W, int batch, int planes) {
+  const std::array<int, 4> key{H, W, batch, planes};
   auto it = h->fft_plans.find(key);
   if (it != h->fft_plans.end()) return it->second;
   if (h->capturing) throw Error(VSR_ERR_ARG, "FFT plans must be created by a run before graph capture");
   vsr_rt::FftPlan p;
-  int n[2] = {H, W}, re_embed[2] = {H, W}, sp_embed[2] = {H, W / 2 + 1};
-  cufft_ck(cufftPlanMany(&p.r2c, 2, n, re_embed, pitch, 1, sp_embed, C, 1, CUFFT_R2C, C), "cufftPlanMany(R2C)");
-  cufft_ck(cufftPlanMany(&p.c2r, 2, n, sp_embed, C, 1, re_embed, pitch, 1, CUFFT_C2R, C), "cufftPlanMany(C2R)");
+  int n[2] = {H, W};
+  const int Wc = W / 2 + 1;
+  cufft_ck(cufftPlanMany(&p.r2c, 2, n, nullptr, 1, H * W, nullptr, 1, H * Wc, CUFFT_R2C, batch), "cufftPlanMany(R2C)");
+  cufft_ck(cufftPlanMany(&p.c2r, 2, n, nullptr, 1, H * Wc, nullptr, 1, H * W, CUFFT_C2R, batch), "cufftPlanMany(C2R)");
   cufft_ck(cufftSetStream(p.r2c, h->ctx.stream), "cufftSetStream");
   cufft_ck(cufftSetStream(p.c2r, h->ctx.stream), "cufftSetStream");
   p.re = std::make_shared<DevBuf>();
   p.sp = std::make_shared<DevBuf>();
-  p.re->ensure((size_t)H * W * pitch * 4);
-  p.sp->ensure((size_t)H * (W / 2 + 1) * 2 * C * 4);
+  p.re->ensure((size_t)planes * H * W * 4);
+  p.sp->ensure((size_t)batch * H * Wc * 8);
   return h->fft_plans[key] = p;
 }
 }  // namespace vsr
@@ -1737,12 +1738,13 @@ int vsr_rt_fft_r2c(vsr_rt_t* h, uint64_t in, int T, int H, int W, int C, int cp_
     const int Wc = W / 2 + 1;
     auto& plan = fft_plan(h, H, W, T * C, T * cp_in);
     cudaStream_t s = h->ctx.stream;
-    const size_t n_in = (size_t)T * H * W * cp_in, n_out = (size_t)T * H * Wc * 2 * C;
-    rt_half_to_float_kernel<<<blocks_for(n_in / 8), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.re->as<float>(), T, (size_t)H * W, cp_in / 8);
+    const size_t P = (size_t)H * W, Pc = (size_t)H * Wc;
+    rt_nhwc_to_planar_kernel<1><<<dim3((unsigned)((P + 31) / 32), (cp_in + 31) / 32, T), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.re->as<float>(), P,
+                                                                                                     cp_in);
     CK(cudaGetLastError());
     cufft_ck(cufftExecR2C(plan.r2c, plan.re->as<float>(), plan.sp->as<cufftComplex>()), "cufftExecR2C");
-    rt_float_to_half_kernel<<<blocks_for(n_out / 8), 256, 0, s>>>(plan.sp->as<float>(), (__half*)(uintptr_t)out, T, (size_t)H * Wc, 2 * C / 8,
-                                                                   1.0f / sqrtf((float)H * (float)W), h->overflow());
+    rt_planar_to_nhwc_kernel<2><<<dim3((unsigned)((Pc + 31) / 32), (C + 31) / 32, T), 256, 0, s>>>(plan.sp->as<float>(), (__half*)(uintptr_t)out, Pc, C,
+                                                                                                  1.0f / sqrtf((float)H * (float)W), h->overflow());
     CK(cudaGetLastError());
     h->ctx.launches += 3;
   });
@@ -1756,12 +1758,14 @@ int vsr_rt_fft_c2r(vsr_rt_t* h, uint64_t in, int T, int H, int W, int C, uint64_
     const int Wc = W / 2 + 1;
     auto& plan = fft_plan(h, H, W, T * C, T * cp_out);
     cudaStream_t s = h->ctx.stream;
-    const size_t n_sp = (size_t)T * H * Wc * 2 * C, n_re = (size_t)T * H * W * cp_out;
-    rt_half_to_float_kernel<<<blocks_for(n_sp / 8), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.sp->as<float>(), T, (size_t)H * Wc, 2 * C / 8);
+    const size_t P = (size_t)H * W, Pc = (size_t)H * Wc;
+    rt_nhwc_to_planar_kernel<2><<<dim3((unsigned)((Pc + 31) / 32), (C + 31) / 32, T), 256, 0, s>>>((const __half*)(uintptr_t)in, plan.sp->as<float>(), Pc, C);
     CK(cudaGetLastError());
     cufft_ck(cufftExecC2R(plan.c2r, plan.sp->as<cufftComplex>(), plan.re->as<float>()), "cufftExecC2R");
-    rt_float_to_half_kernel<<<blocks_for(n_re / 8), 256, 0, s>>>(plan.re->as<float>(), (__half*)(uintptr_t)out, T, (size_t)H * W, cp_out / 8,
-                                                                  1.0f / sqrtf((float)H * (float)W), h->overflow());
+    // planes C..cp_out-1 of the staging are never written by the transform (zero from allocation): the padding channels stay 0
+    rt_planar_to_nhwc_kernel<1><<<dim3((unsigned)((P + 31) / 32), (cp_out + 31) / 32, T), 256, 0, s>>>(plan.re->as<float>(), (__half*)(uintptr_t)out, P,
+                                                                                                      cp_out, 1.0f / sqrtf((float)H * (float)W),
+                                                                                                      h->overflow());
     CK(cudaGetLastError());
     h->ctx.launches += 3;
   });

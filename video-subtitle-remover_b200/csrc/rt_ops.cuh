@@ -185,43 +185,56 @@ __global__ void __launch_bounds__(256) rt_residual_add_kernel(float* __restrict_
   reinterpret_cast<uint4*>(x16)[i] = *reinterpret_cast<const uint4*>(o);
 }
 
-// fp16 <-> fp32 staging around cuFFT (its half-precision transforms are power-of-two only).  The fp16 side is [T][P][K]
-// (T images of P pixels, K channels), the fp32 side [P][T][K]: folding the image index into the channel axis lets ONE
-// batched cuFFT plan (stride T*K between pixels, distance 1 between channels) transform all T images.  out = in * mul.
-__global__ void __launch_bounds__(256) rt_half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, int T, size_t P, int K8) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)T * P * K8) return;
-  const int k = i % K8;
-  const size_t tp = i / K8;
-  const size_t p = tp % P;
-  const int t = tp / P;
-  const uint4 v = reinterpret_cast<const uint4*>(in)[i];
-  const __half2* h = reinterpret_cast<const __half2*>(&v);
-  const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
-  float4* o = reinterpret_cast<float4*>(out) + 2 * ((p * T + t) * K8 + k);
-  o[0] = make_float4(a.x, a.y, b.x, b.y);
-  o[1] = make_float4(c.x, c.y, d.x, d.y);
+// fp16 NHWC <-> fp32 planar staging around cuFFT (its half-precision transforms are power-of-two only, and its kernels
+// want unit-stride signals: the first version handed it the interleaved-channel layout through istride = channels and spent
+// 40 % of the LAMA frame in strided FFT kernels).  NHWC side: [T][P][Kc][E] halves (P pixels, Kc channel units of E = 1
+// real or E = 2 (re, im) values); planar side: [(t*Kc + kc)][P][E] floats = one contiguous signal per channel.  32 x 32
+// (pixel x unit) tiles go through shared memory so that both sides are accessed along their contiguous axis.
+template <int E>
+__global__ void __launch_bounds__(256) rt_nhwc_to_planar_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t P, int Kc) {
+  __shared__ float tile[32][32 * E + 1];
+  const int t = blockIdx.z;
+  const size_t p0 = (size_t)blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  const int W = 32 * E;
+  for (int i = threadIdx.x; i < 32 * W; i += 256) {       // read: consecutive threads walk the channel axis of one pixel
+    const int pp = i / W, e = i - pp * W;
+    const size_t p = p0 + pp;
+    const int ku = k0 + e / E;
+    tile[pp][e] = (p < P && ku < Kc) ? __half2float(in[((size_t)t * P + p) * Kc * E + (size_t)k0 * E + e]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * W; i += 256) {       // write: consecutive threads walk the pixel axis of one channel
+    const int ku = i / W, r = i - ku * W;                   // r = pixel * E + e
+    const size_t p = p0 + r / E;
+    if (p < P && k0 + ku < Kc) out[(((size_t)t * Kc + k0 + ku) * P + p) * E + (r % E)] = tile[r / E][ku * E + (r % E)];
+  }
 }
-__global__ void __launch_bounds__(256) rt_float_to_half_kernel(const float* __restrict__ in, __half* __restrict__ out, int T, size_t P, int K8,
-                                                               float mul, int* overflow) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)T * P * K8) return;
-  const int k = i % K8;
-  const size_t tp = i / K8;
-  const size_t p = tp % P;
-  const int t = tp / P;
-  const float4* src = reinterpret_cast<const float4*>(in) + 2 * ((p * T + t) * K8 + k);
-  const float4 a = src[0], b = src[1];
-  const float v[8] = {a.x * mul, a.y * mul, a.z * mul, a.w * mul, b.x * mul, b.y * mul, b.z * mul, b.w * mul};
-  __align__(16) __half2 o[4];
+template <int E>
+__global__ void __launch_bounds__(256) rt_planar_to_nhwc_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t P, int Kc, float mul,
+                                                                int* overflow) {
+  __shared__ float tile[32][32 * E + 1];
+  const int t = blockIdx.z;
+  const size_t p0 = (size_t)blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  const int W = 32 * E;
+  for (int i = threadIdx.x; i < 32 * W; i += 256) {
+    const int ku = i / W, r = i - ku * W;
+    const size_t p = p0 + r / E;
+    tile[r / E][ku * E + (r % E)] = (p < P && k0 + ku < Kc) ? in[(((size_t)t * Kc + k0 + ku) * P + p) * E + (r % E)] * mul : 0.f;
+  }
+  __syncthreads();
   bool bad = false;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    bad |= !(fabsf(v[2 * j]) <= 65504.f) | !(fabsf(v[2 * j + 1]) <= 65504.f);
-    o[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+  for (int i = threadIdx.x; i < 32 * W; i += 256) {
+    const int pp = i / W, e = i - pp * W;
+    const size_t p = p0 + pp;
+    if (p < P && k0 + e / E < Kc) {
+      const float v = tile[pp][e];
+      bad |= !(fabsf(v) <= 65504.f);
+      out[((size_t)t * P + p) * Kc * E + (size_t)k0 * E + e] = __float2half_rn(v);
+    }
   }
   if (bad && overflow) *overflow = 1;
-  reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
 }
 
 // L1 (lama_util.py:12-80) + the head of the script's forward: u8 image [h,w,3] (channel order untouched) and u8 mask
