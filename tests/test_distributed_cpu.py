@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vsr_b200.distributed import chunk_ranges, chunks_for_rank, inpaint_clip_sharded, max_over_ranks
+from vsr_b200.distributed import (batches_for_rank, chunk_ranges, chunks_for_rank, detect_video_sharded, inpaint_clip_sharded, max_over_ranks,
+                                  sampled_frames_for_rank)
 
 
 def test_chunk_ranges_match_reference_loop():
@@ -64,3 +65,40 @@ def test_two_rank_gloo_sharding():
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_worker, args=(2, port, 230, 50), nprocs=2, join=True)
+
+
+class _FakeDetector:
+    """Stand-in for SubtitleDetect: frame i (0-based) carries a subtitle box iff 10 <= i < 40, jittered by i % 3 pixels."""
+
+    def detect_subtitle(self, frame):
+        i = int(frame[0])
+        return [(100 + i % 3, 400, 300, 330 + i % 2)] if 10 <= i < 40 else []
+
+
+def _detect_worker(rank, world, port, n, step):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        frames = [torch.tensor([i]) for i in range(n)]
+        got = detect_video_sharded(_FakeDetector(), frames, step, rank, world)
+        want = detect_video_sharded(_FakeDetector(), frames, step, 0, 1)      # the single-process plan
+        assert got == want and min(got) == 13 and len(got) > 20               # first sampled hit: frame number 13 (0-based 12)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_detection_sharding_two_processes_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_detect_worker, args=(2, port, 60, 3), nprocs=2, join=True)
+
+
+def test_sampled_frames_and_batches_partition():
+    for n, step, world in ((100, 3, 4), (7, 2, 8), (60, 4, 2)):
+        allf = sorted(f for r in range(world) for f in sampled_frames_for_rank(n, step, r, world))
+        assert allf == list(range(1, n + 1, step))
+    for n, mb, world in ((300, 46, 4), (50, 46, 2), (7, 46, 3)):
+        spans = sorted(b for r in range(world) for b in batches_for_rank(n, mb, r, world))
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

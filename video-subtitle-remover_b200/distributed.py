@@ -37,3 +37,56 @@ def inpaint_clip_sharded(engine, frames, mask, clip_gap: int, rank: int, world: 
     for _, (s, e) in mine:
         engine.inpaint_inplace(frames[s:e], mask)
     return mine
+
+
+# ---- detection + per-interval inpainting (BASELINE config 4 / LAMA): frames and batches are independent units ----------
+def sampled_frames_for_rank(n_frames: int, step: int, rank: int, world: int) -> List[int]:
+    """1-based numbers of the frames this rank runs the text detector on: the sampled frames 1, 1+step, ...
+    (subtitle_detect.py:105) dealt round-robin, so every rank gets an even spread over the video."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    sampled = list(range(1, n_frames + 1, max(step, 1)))
+    return sampled[rank::world]
+
+
+def gather_detections(local: dict) -> dict:
+    """Union of the per-rank {frame number: boxes} dictionaries on every rank.  This is the one real exchange step of the
+    detection pass: gap filling and `unify_regions` (subtitle_detect.py:112-215) walk the whole dictionary in key order."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return dict(local)
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, local)
+    merged = {}
+    for p in parts:
+        merged.update(p)
+    return dict(sorted(merged.items()))
+
+
+def detect_video_sharded(detector, frames, step: int, rank: int, world: int) -> dict:
+    """`SubtitleDetect.scan_frames` over an in-memory clip with the sampled frames sharded across ranks: every rank
+    detects its share, the hits are exchanged, and every rank finishes with the same planned dictionary."""
+    from . import subtitle_plan as P
+
+    local = {}
+    for no in sampled_frames_for_rank(len(frames), step, rank, world):
+        boxes = detector.detect_subtitle(frames[no - 1])
+        if boxes:
+            local[no] = boxes
+    return P.drop_empty(P.unify_regions(P.gap_fill(gather_detections(local), step)))
+
+
+def batches_for_rank(n_items: int, max_batch: int, rank: int, world: int) -> List[Tuple[int, int]]:
+    """(start, end) of the `batch_generator` batches (inpaint_tools.py:7-29) of one interval that `rank` inpaints: sttn-det
+    and LAMA treat every batch independently (main.py:323-326), so batches are dealt round-robin."""
+    from .inpaint_tools import batch_generator
+
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    out, s = [], 0
+    for i, b in enumerate(batch_generator(list(range(n_items)), max_batch)):
+        if i % world == rank:
+            out.append((s, s + len(b)))
+        s += len(b)
+    return out
