@@ -145,6 +145,13 @@ int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W,
  * a dense conv over a reflect-padded input keeps only the interior (LAMA's padding_mode='reflect', ReflectionPad2d). */
 int vsr_rt_conv_ex(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu,
                    float alpha, float bias_scale, int crop_t, int crop_l, int out_h, int out_w);
+/* ---- PP-OCRv5 mobile detector (backend/models/V5/ch_det_fast): hardswish + the exported learnable scalar affine, and the
+ * squeeze-and-excitation gate (global average pool -> 1x1 conv -> relu -> 1x1 conv -> hardsigmoid), which is applied with
+ * vsr_rt_elementwise op 4 (per-channel scale = gate).  residual != 0 gives 1 + gate (RSELayer: x + x * gate). */
+int vsr_rt_hswish_affine(vsr_rt_t* h, uint64_t in, uint64_t out, int64_t n_elems, float inv_scale_in, float a, float c);
+int vsr_rt_se_create(vsr_rt_t* h, const float* w1, const float* b1, const float* w2, const float* b2, int C, int mid, float slope, float offset,
+                     int residual, int* se_id);     /* w1 [mid][C], w2 [C][mid] */
+int vsr_rt_se_gate(vsr_rt_t* h, int se_id, uint64_t x, int64_t pixels, int cp, float inv_scale, uint64_t gate_dev);   /* gate: fp32 [cp] */
 /* ---- LAMA: what the TorchScript big-lama forward needs beyond the detector's operators ---- */
 /* out[OH,OW] = in[H,W] shifted by (top, left), reflected at the borders (reflect = 1) or zero filled (0) */
 int vsr_rt_pad(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left, int reflect);

@@ -147,6 +147,31 @@ class FakeRuntime:
         v[:, :, :, out_coff:out_coff + L["cout"]] = res
         self.launches += 1
 
+    # ---- mobile detector
+    def hswish_affine(self, x, y, inv_scale_in, a, c):
+        if self._recording("hswish_affine", x, y, inv_scale_in, a, c):
+            return
+        v = self._view(x) * inv_scale_in
+        self._store(y, a * (v * np.clip(v + 3.0, 0.0, 6.0) / 6.0) + c)
+        self.launches += 1
+
+    def se_create(self, w1, b1, w2, b2, slope, offset, residual):
+        self.layers.append(dict(se=(np.array(w1, np.float32), np.array(b1, np.float32), np.array(w2, np.float32), np.array(b2, np.float32), slope, offset,
+                                    residual)))
+        return len(self.layers) - 1
+
+    def se_gate(self, se_id, x, inv_scale, gate_ptr):
+        if self._recording("se_gate", se_id, x, inv_scale, gate_ptr):
+            return
+        w1, b1, w2, b2, slope, offset, residual = self.layers[se_id]["se"]
+        C = w1.shape[1]
+        mean = self._view(x)[:, :, :C].reshape(-1, C).mean(0) * inv_scale
+        g = np.clip(slope * (w2 @ np.maximum(w1 @ mean + b1, 0) + b2) + offset, 0.0, 1.0)
+        out = np.zeros_like(self.bufs[gate_ptr])
+        out[:C] = 1.0 + g if residual else g
+        self.bufs[gate_ptr][:] = out
+        self.launches += 2
+
     # ---- LAMA-only entry points
     def pad(self, x, y, top, left, reflect=1):
         if self._recording("pad", x, y, top, left, reflect):

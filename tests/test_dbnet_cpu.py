@@ -90,3 +90,26 @@ def test_graph_compiler_on_cpu_runtime(hw):
     third = det.probability_map(img)
     assert rt.launch_count - n1 > 400        # the graph run plus the layer-by-layer recalibration
     assert np.abs(third - want).max() < 2e-4
+
+
+def test_mobile_detector_compiles_on_cpu_runtime():
+    """PP-OCRv5_mobile_det (backend/models/V5/ch_det_fast, model_config.py:17-18): re-parameterised PPLCNetV3 blocks (conv + bias
+    + learnable scalar affine folded into one launch, hardswish + affine as one element-wise launch), squeeze-and-excitation
+    as a fused gate, RSEFPN with residual gates, 42/18/12-channel convs padded to the 8-channel store granularity."""
+    import cv2
+    from fake_rt import FakeRuntime
+    from vsr_b200.dbnet import TextDetector
+
+    d = os.path.join(ROOT, "weights", "V5", "ch_det_fast")
+    if not os.path.exists(os.path.join(d, "inference.pdiparams")):
+        pytest.skip("mobile detector not staged under weights/V5/ch_det_fast")
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 255, (96, 160, 3), dtype=np.uint8)
+    cv2.putText(img, "Ab3", (10, 76), cv2.FONT_HERSHEY_SIMPLEX, 1.5, (255, 255, 255), 3)
+    rt = FakeRuntime()
+    det = TextDetector(d, runtime=rt)
+    got = det.probability_map(img)
+    want = D.forward(D.Graph(d), D.preprocess(img))[0, 0].numpy()
+    assert got.shape == want.shape == (96, 160) and np.abs(got - want).max() < 2e-4
+    n0 = rt.launch_count
+    assert np.array_equal(det.probability_map(img), got) and rt.launch_count - n0 < 130     # 683 PIR ops

@@ -142,3 +142,25 @@ def test_config4_chain_detect_plan_mask_inpaint(detector, capi):
     ref = DET.det_call(w, frames, mask)
     got, exp = np.stack(out).astype(np.float32), np.stack(ref).astype(np.float32)
     assert O.psnr_u8(got, exp) >= 45.0 and np.abs(got - exp).max() <= 6
+
+
+def test_mobile_detector_matches_oracle(capi):
+    """PP-OCRv5_mobile_det (V5/ch_det_fast): same bar as the server model."""
+    d = os.path.join(ROOT, "weights", "V5", "ch_det_fast")
+    if not os.path.exists(os.path.join(d, "inference.pdiparams")):
+        pytest.skip("mobile detector not staged under weights/V5/ch_det_fast")
+    from vsr_b200.dbnet import TextDetector
+
+    det, graph = TextDetector(d, "cuda:0"), D.Graph(d)
+    for hw, seed in (((720, 1280), 0), ((360, 640), 4)):
+        img = _text_frame(*hw, seed=seed)
+        got = det.probability_map(img)
+        want = D.forward(graph, D.preprocess(img))[0, 0].numpy()
+        d_ = np.abs(got - want)
+        assert got.shape == want.shape and np.isfinite(got).all()
+        assert d_.mean() <= 5e-4 and (d_ > 0.05).mean() <= 2e-3, (float(d_.mean()), float((d_ > 0.05).mean()), float(d_.max()))
+        assert ((got > 0.3) != (want > 0.3)).mean() < 1e-3
+        a = sorted(D.get_coordinates(det.predict(img)[0]["dt_polys"].tolist()))
+        b = sorted(D.get_coordinates(D.postprocess(want, *hw).tolist()))
+        assert len(a) == len(b) >= 2 and all(max(abs(p - q) for p, q in zip(x, y)) <= 3 for x, y in zip(a, b)), (a, b)
+    assert det.time_network(5) > 0

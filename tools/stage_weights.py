@@ -11,7 +11,10 @@ FILES = {"sttn-auto/infer_model.pth": "backend/models/sttn-auto/infer_model.pth"
          "sttn-det/sttn.pth": "backend/models/sttn-det/sttn.pth",
          "V5/ch_det/inference.json": "backend/models/V5/ch_det/inference.json",
          "V5/ch_det/inference.pdiparams": "backend/models/V5/ch_det/inference.pdiparams",
-         "V5/ch_det/inference.yml": "backend/models/V5/ch_det/inference.yml"}
+         "V5/ch_det/inference.yml": "backend/models/V5/ch_det/inference.yml",
+         "V5/ch_det_fast/inference.json": "backend/models/V5/ch_det_fast/inference.json",
+         "V5/ch_det_fast/inference.pdiparams": "backend/models/V5/ch_det_fast/inference.pdiparams",
+         "V5/ch_det_fast/inference.yml": "backend/models/V5/ch_det_fast/inference.yml"}
 
 
 def stage_lama(quiet=False):

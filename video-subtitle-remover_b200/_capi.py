@@ -94,6 +94,9 @@ _PROTOS = {
     "vsr_rt_zero_upsample2x": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_add_slices": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int64,
                                     C.c_float, C.c_float]),
+    "vsr_rt_hswish_affine": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_float, C.c_float, C.c_float]),
+    "vsr_rt_se_create": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_int)]),
+    "vsr_rt_se_gate": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_float, C.c_uint64]),
     "vsr_rt_residual_add": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int]),
     "vsr_rt_fft_r2c": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_fft_c2r": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),

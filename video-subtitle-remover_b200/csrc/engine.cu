@@ -1211,6 +1211,12 @@ struct vsr_rt {
   std::vector<std::unique_ptr<RtLayer>> layers;
   DevBuf image;    // BGR u8 staging of the pre-processing
   std::vector<std::pair<std::unique_ptr<DevBuf>, std::unique_ptr<DevBuf>>> lama_slots;  // u8 image + mask staging per batch slot (LAMA)
+  struct SeLayer {
+    DevBuf w1, b1, w2, b2, mean;
+    int C = 0, mid = 0, residual = 0;
+    float slope = 0.f, offset = 0.f;
+  };
+  std::vector<std::unique_ptr<SeLayer>> se_layers;
   struct FftPlan {
     cufftHandle r2c = 0, c2r = 0;
     std::shared_ptr<DevBuf> re, sp;  // fp32 staging of the real side [H][W][pitch] and of the spectrum [H][W/2+1][C] complex
@@ -1691,6 +1697,51 @@ int vsr_rt_add_slices(vsr_rt_t* h, int relu, uint64_t a, int pitch_a, uint64_t b
         (size_t)pixels, alpha, beta, h->overflow());
     CK(cudaGetLastError());
     ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_hswish_affine(vsr_rt_t* h, uint64_t in, uint64_t out, int64_t n_elems, float inv_scale_in, float a, float c) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(in && out && n_elems > 0 && n_elems % 8 == 0, "bad arguments");
+    rt_hswish_affine_kernel<<<blocks_for((size_t)n_elems / 8), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, (__half*)(uintptr_t)out,
+                                                                                       (size_t)n_elems / 8, inv_scale_in, a, c, h->overflow());
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_se_create(vsr_rt_t* h, const float* w1, const float* b1, const float* w2, const float* b2, int C, int mid, float slope, float offset,
+                     int residual, int* se_id) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(w1 && b1 && w2 && b2 && se_id && C > 0 && mid > 0 && mid <= 1024, "bad arguments");
+    auto L = std::make_unique<vsr_rt::SeLayer>();
+    L->C = C; L->mid = mid; L->residual = residual; L->slope = slope; L->offset = offset;
+    cudaStream_t s = h->ctx.stream;
+    upload(L->w1, std::vector<float>(w1, w1 + (size_t)mid * C), s);
+    upload(L->b1, std::vector<float>(b1, b1 + mid), s);
+    upload(L->w2, std::vector<float>(w2, w2 + (size_t)C * mid), s);
+    upload(L->b2, std::vector<float>(b2, b2 + C), s);
+    L->mean.ensure((size_t)((C + 7) / 8 * 8) * 4);
+    *se_id = (int)h->se_layers.size();
+    h->se_layers.push_back(std::move(L));
+  });
+}
+
+int vsr_rt_se_gate(vsr_rt_t* h, int se_id, uint64_t x, int64_t pixels, int cp, float inv_scale, uint64_t gate_dev) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(se_id >= 0 && se_id < (int)h->se_layers.size() && x && gate_dev && pixels > 0 && cp % 8 == 0, "bad arguments");
+    auto& L = *h->se_layers[se_id];
+    REQUIRE(L.C <= cp, "channel count exceeds the tensor pitch");
+    cudaStream_t s = h->ctx.stream;
+    rt_channel_mean_kernel<<<(L.C + 7) / 8, 256, 0, s>>>((const __half*)(uintptr_t)x, (size_t)pixels, cp, 1.0f / (float)pixels, L.mean.as<float>());
+    CK(cudaGetLastError());
+    rt_se_fc_kernel<<<1, 256, (size_t)L.mid * 4, s>>>(L.mean.as<float>(), L.w1.as<float>(), L.b1.as<float>(), L.w2.as<float>(), L.b2.as<float>(), L.C,
+                                                       L.mid, L.slope, L.offset, inv_scale, L.residual, (float*)(uintptr_t)gate_dev);
+    CK(cudaGetLastError());
+    h->ctx.launches += 2;
   });
 }
 

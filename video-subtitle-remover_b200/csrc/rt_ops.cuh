@@ -277,6 +277,80 @@ __global__ void __launch_bounds__(256) rt_extract_channel_kernel(const __half* _
   if (i < pixels) out[i] = __half2float(x[i * cp + ch]) * mul;
 }
 
+// ---- PP-OCRv5 mobile detector (PPLCNetV3 + RSEFPN) ------------------------------------------------------------------
+// hardswish followed by the learnable scalar affine of the exported blocks: out = a * hswish(x * inv_s) + c with
+// hswish(v) = v * clamp(v + 3, 0, 6) / 6 (not homogeneous: the input scale is divided out first; a and c carry the output scale)
+__global__ void __launch_bounds__(256) rt_hswish_affine_kernel(const __half* __restrict__ in, __half* __restrict__ out, size_t n8, float inv_s, float a,
+                                                               float c, int* overflow) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 v = reinterpret_cast<const uint4*>(in)[i];
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  __align__(16) __half2 o[4];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __half22float2(h[j]);
+    f.x *= inv_s;
+    f.y *= inv_s;
+    const float u = fmaf(a, f.x * fminf(fmaxf(f.x + 3.f, 0.f), 6.f) * (1.f / 6.f), c);
+    const float w = fmaf(a, f.y * fminf(fmaxf(f.y + 3.f, 0.f), 6.f) * (1.f / 6.f), c);
+    bad |= !(fabsf(u) <= 65504.f) | !(fabsf(w) <= 65504.f);
+    o[j] = __floats2half2_rn(u, w);
+  }
+  if (bad && overflow) *overflow = 1;
+  reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
+}
+
+// squeeze-and-excitation gate: (1) per-channel mean over the pixels (one block per 8 channels), (2) gate = hardsigmoid(W2 *
+// relu(W1 * mean + b1) + b2) in one block; residual != 0 stores 1 + gate (RSELayer: x + x * gate).  The gate then multiplies the
+// tensor through the per-channel affine operator.
+__global__ void __launch_bounds__(256) rt_channel_mean_kernel(const __half* __restrict__ x, size_t pixels, int cp, float inv_count,
+                                                              float* __restrict__ mean) {
+  __shared__ float part[8][8];
+  const int c8 = blockIdx.x;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (size_t p = threadIdx.x; p < pixels; p += blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(x + p * cp + c8 * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      acc[2 * j] += f.x;
+      acc[2 * j + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int j = 0; j < 8; ++j) part[warp][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += part[w][threadIdx.x];
+    mean[c8 * 8 + threadIdx.x] = s * inv_count;
+  }
+}
+__global__ void __launch_bounds__(256) rt_se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2, int C, int mid, float slope,
+                                                       float offset, float inv_scale, int residual, float* __restrict__ gate) {
+  extern __shared__ float hid[];
+  for (int m = threadIdx.x; m < mid; m += blockDim.x) {
+    float s = b1[m];
+    for (int c = 0; c < C; ++c) s = fmaf(w1[(size_t)m * C + c], mean[c] * inv_scale, s);
+    hid[m] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = b2[c];
+    for (int m = 0; m < mid; ++m) s = fmaf(w2[(size_t)c * mid + m], hid[m], s);
+    const float g = fminf(fmaxf(fmaf(slope, s, offset), 0.f), 1.f);
+    gate[c] = residual ? 1.f + g : g;
+  }
+}
+
 // max |x| over a tensor (calibration of the per-tensor scales): *out is the bit pattern of a non-negative float, so
 // an unsigned atomicMax orders it; inf / NaN patterns compare above every finite value.
 __global__ void __launch_bounds__(256) rt_absmax_kernel(const __half* __restrict__ x, size_t n8, unsigned int* __restrict__ out) {

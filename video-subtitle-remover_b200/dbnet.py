@@ -167,6 +167,31 @@ class _Unary:
             rt.elementwise(self.op, self.x, None, self.y)
 
 
+class _HSwish:
+    """hardswish followed by the exported learnable scalar affine: out = a * hswish(x) + c (PPLCNetV3's Act + LearnableAffineBlock).
+    Not homogeneous, so the output has its own scale: stored = s_out * (a * hswish(stored_in / s_in) + c)."""
+    rescalable = True
+
+    def __init__(self, x, y, a=1.0, c=0.0):
+        self.x, self.y, self.a, self.c = x, y, a, c
+
+    def run(self, rt):
+        rt.hswish_affine(self.x, self.y, 1.0 / self.x.scale, self.a * self.y.scale, self.c * self.y.scale)
+
+
+class _SE:
+    """squeeze-and-excitation: gate = hardsigmoid(fc2(relu(fc1(mean(x))))), y = x * gate (SEModule) or x + x * gate (RSELayer).
+    Homogeneous in x for a given gate: y keeps the scale of x."""
+    rescalable = False
+
+    def __init__(self, se_id, x, y, gate, zeros):
+        self.se_id, self.x, self.y, self.gate, self.zeros = se_id, x, y, gate, zeros
+
+    def run(self, rt):
+        rt.se_gate(self.se_id, self.x, 1.0 / self.x.scale, self.gate)
+        rt.elementwise(4, self.x, None, self.y, scale=self.gate, shift=self.zeros)
+
+
 class _Affine:
     """per-channel x*sc + sh (+ ReLU) for a batch-norm / bias that has no convolution to fold into."""
     rescalable = False
@@ -259,6 +284,19 @@ class _DeviceRuntime:
 
     def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0):
         _capi.check(self.L.vsr_rt_conv(self.h, lid, x.ptr, 1, x.h, x.w, y.ptr, y.cp, 0, relu, alpha, bias_scale))
+
+    def hswish_affine(self, x, y, inv_scale_in, a, c):
+        _capi.check(self.L.vsr_rt_hswish_affine(self.h, x.ptr, y.ptr, x.pixels * x.cp, inv_scale_in, a, c))
+
+    def se_create(self, w1, b1, w2, b2, slope, offset, residual) -> int:
+        w1, b1, w2, b2 = (np.ascontiguousarray(v, np.float32) for v in (w1, b1, w2, b2))
+        f32p, sid = C.POINTER(C.c_float), C.c_int()
+        _capi.check(self.L.vsr_rt_se_create(self.h, w1.ctypes.data_as(f32p), b1.ctypes.data_as(f32p), w2.ctypes.data_as(f32p), b2.ctypes.data_as(f32p),
+                                            w1.shape[1], w1.shape[0], slope, offset, 1 if residual else 0, C.byref(sid)))
+        return int(sid.value)
+
+    def se_gate(self, se_id, x, inv_scale, gate_ptr):
+        _capi.check(self.L.vsr_rt_se_gate(self.h, se_id, x.ptr, x.pixels, x.cp, inv_scale, gate_ptr))
 
     def absmax(self, t) -> float:
         out = C.c_float()
@@ -384,6 +422,30 @@ class TextDetector:
             c = const_of(other[0])
             return np.asarray(c, np.float32).reshape(-1) if isinstance(c, np.ndarray) else None
 
+        def scalar_of(v):
+            """value of a one-element constant (a learnable scalar of the exported blocks), else None"""
+            c = const_of(v)
+            if isinstance(c, np.ndarray) and c.size == 1:
+                return float(c.reshape(-1)[0])
+            return None
+
+        def scalar_affine(cur):
+            """`multiply(scalar, x)` then `add(., scalar)` hanging off value `cur` as single consumers: (a, c, nodes, out id)."""
+            a, c, used = 1.0, 0.0, []
+            u = single_user(cur, "multiply")
+            if u is not None:
+                k = [scalar_of(i) for i in u.ins if i != cur]
+                if len(k) == 1 and k[0] is not None:
+                    a, cur = k[0], u.out
+                    used.append(u)
+            u = single_user(cur, "add")
+            if u is not None:
+                k = [scalar_of(i) for i in u.ins if i != cur]
+                if len(k) == 1 and k[0] is not None:
+                    c, cur = k[0], u.out
+                    used.append(u)
+            return a, c, used, cur
+
         def emit_conv(n: _Node):
             x: _Tensor = val[n.ins[0]]
             w = np.asarray(val[n.ins[1]], np.float32)
@@ -421,11 +483,21 @@ class TextDetector:
                 bias = (bias - mean) * s + beta
                 done.add(id(u))
                 cur = u.out
+            a_s, c_s, used, nxt = scalar_affine(cur)     # LearnableAffineBlock after the (re-parameterised) conv
+            if used:
+                w *= np.float32(a_s)
+                bias = bias * np.float32(a_s) + np.float32(c_s)
+                done.update(id(m) for m in used)
+                cur = nxt
             u = single_user(cur, "relu")
             if u is not None:
                 relu = 1
                 done.add(id(u))
                 cur = u.out
+            if groups == 1 and not transposed and cout >= 8 and cout % 8:   # the tensor-core conv stores 8-channel groups
+                pad = _r(cout, 8) - cout
+                w = np.concatenate([w, np.zeros((pad,) + w.shape[1:], np.float32)])
+                bias = np.concatenate([bias, np.zeros(pad, np.float32)])
             cin_l = w.shape[0] if transposed else w.shape[1] * (groups if groups > 1 else 1)
             if groups == 1 and x.perm is not None:  # logical input channel l lives at physical channel perm[l]
                 wp = np.zeros((w.shape[0], x.cp) + w.shape[2:], np.float32) if not transposed else None
@@ -442,7 +514,7 @@ class TextDetector:
             else:
                 oh, ow = x.h, x.w
             y = self._new(cout, oh, ow)
-            lid = rt.conv_create(w, bias, cout, int(cin_eff), x.cp, kh, kw, stride, pad_t, pad_l, dil, groups, transposed)
+            lid = rt.conv_create(w, bias, int(bias.size), int(cin_eff), x.cp, kh, kw, stride, pad_t, pad_l, dil, groups, transposed)
             prog.steps.append(_Conv(lid, x, y, relu))
             val[cur] = y
 
@@ -481,6 +553,12 @@ class TextDetector:
                 x = val[n.ins[0]]
                 val[n.out] = self._new(x.c, x.h, x.w, x.perm, follow=x)
                 prog.steps.append(_Unary(1, x, val[n.out]))
+            elif k == "hardswish":
+                x = val[n.ins[0]]
+                a_s, c_s, used, cur = scalar_affine(n.out)
+                done.update(id(m) for m in used)
+                val[cur] = self._new(x.c, x.h, x.w, x.perm)
+                prog.steps.append(_HSwish(x, val[cur], a_s, c_s))
             elif k == "sigmoid":
                 x = val[n.ins[0]]
                 val[n.out] = self._new(x.c, x.h, x.w, x.perm)
@@ -534,6 +612,41 @@ class TextDetector:
                 y = _Tensor(rt.alloc(x.pixels * s * s * x.cp * 2), x.c, x.h * s, x.w * s, x.cp, x.perm, follow=x)
                 prog.steps.append(_Call("upsample", x, y, s))
                 val[n.out] = y
+            elif k == "pool2d" and n.attrs.get("adaptive") and n.attrs.get("pooling_type") == "avg":
+                # squeeze-and-excitation: pool(1x1) -> conv1x1 + bias -> relu -> conv1x1 + bias -> hardsigmoid -> x * gate [-> x + .]
+                x = val[n.ins[0]]
+                if [int(v) for v in val[n.ins[1]]] != [1, 1] or x.perm is not None:
+                    raise _capi.VsrError("only global average pooling of a plain tensor is supported")
+
+                def conv_bias(node):
+                    wt = np.asarray(val[node.ins[1]], np.float32)
+                    u = single_user(node.out, "add")
+                    b = bias_operand(u, node.out) if u is not None else None
+                    if wt.shape[2:] != (1, 1) or b is None:
+                        raise _capi.VsrError("unexpected squeeze-and-excitation layout")
+                    return wt[:, :, 0, 0], b, u
+
+                c1 = single_user(n.out, "conv2d")
+                w1, b1, a1 = conv_bias(c1)
+                r = single_user(a1.out, "relu")
+                c2 = single_user(r.out, "conv2d") if r is not None else None
+                if c2 is None:
+                    raise _capi.VsrError("unexpected squeeze-and-excitation layout")
+                w2, b2, a2 = conv_bias(c2)
+                hs = single_user(a2.out, "hardsigmoid")
+                mul = single_user(hs.out, "multiply") if hs is not None else None
+                if mul is None or n.ins[0] not in mul.ins:
+                    raise _capi.VsrError("unexpected squeeze-and-excitation layout")
+                cur, residual = mul.out, False
+                u = single_user(cur, "add")
+                if u is not None and n.ins[0] in u.ins:          # RSELayer: x + x * gate
+                    cur, residual = u.out, True
+                    done.add(id(u))
+                done.update(id(m) for m in (c1, a1, r, c2, a2, hs, mul))
+                se_id = rt.se_create(w1, b1, w2, b2, float(hs.attrs["slope"]), float(hs.attrs["offset"]), residual)
+                y = self._new(x.c, x.h, x.w, follow=x)
+                prog.steps.append(_SE(se_id, x, y, rt.upload_f32(np.zeros(x.cp, np.float32)), rt.upload_f32(np.zeros(x.cp, np.float32))))
+                val[cur] = y
             elif k == "pool2d":
                 x = val[n.ins[0]]
                 ks = [int(v) for v in val[n.ins[1]]]
