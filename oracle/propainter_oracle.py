@@ -1,4 +1,6 @@
-"""CPU oracle for the ProPainter path — TEST INFRASTRUCTURE ONLY, PARTIAL.
+"""CPU oracle for the ProPainter path — TEST INFRASTRUCTURE ONLY.  This file: the host / integer
+rows and the image propagation; RAFT is oracle/raft_oracle.py (P3), flow completion oracle/rfc_oracle.py (P4), the generator
+and the whole `inpaint` / `__call__` chain oracle/propainter_gen_oracle.py (P6).
 
 Restated and pinned against the unmodified reference (tests/golden/propainter_real.npz, tools/make_golden_propainter.py):
   P1  strips for PropainterInpaint.__call__              backend/inpaint/propainter_inpaint.py:363-418
@@ -6,9 +8,9 @@ Restated and pinned against the unmodified reference (tests/golden/propainter_re
   P5  InpaintGenerator.img_propagation (learnable=False) video/model/propainter.py:24-33,107-193,316-319;
       flow_warp                                          video/model/modules/flow_loss_utils.py:6-45
   P7  window loop, get_ref_index, composite + blend      propainter_inpaint.py:120-135,318-361
-NOT restated yet — "parity unpinned" for them; their reference outputs are already stored in the golden file as the pins
-for the next round: P3 RAFT (gt_flows_*), P4 RecurrentFlowCompleteNet + combine_flow (pred_flows_*), P6 InpaintGenerator.forward
-(comp / call).  `oracle/deform_conv.py` is the pure-torch `deform_conv2d` P4 and P6 need (torchvision's CPU kernel crashes here).
+Parity: PINNED.  The chained oracle reproduces the reference's final frames of `inpaint` and `__call__` up to 1 grey level on
+2e-5 of the pixels (fp32 re-association before the u8 truncation).  `oracle/deform_conv.py` is the pure-torch `deform_conv2d`
+P4 and P6 need (torchvision's CPU kernel crashes on the reference's shapes in this image).
 """
 from typing import Dict, List, Sequence, Tuple
 

@@ -76,3 +76,84 @@ def test_image_propagation_and_composite_against_reference_taps():
     c = P.composite([None] * 2, np.full((2, 4, 4, 3), 200.7, np.float32), np.ones((2, 4, 4, 1), np.uint8), [np.zeros((4, 4, 3), np.uint8)] * 2, [0, 1])
     c = P.composite(c, np.full((1, 4, 4, 3), 101.9, np.float32), np.ones((1, 4, 4, 1), np.uint8), [np.zeros((4, 4, 3), np.uint8)] * 2, [1])
     assert c[0][0, 0, 0] == 200 and c[1][0, 0, 0] == 150 and c[1].dtype == np.uint8
+
+
+def test_raft_oracle_matches_reference_flows():
+    """P3: the RAFT restatement against RAFT_bi of the unmodified reference (golden gt_flows, stored as fp16)."""
+    path = os.path.join(ROOT, "weights", "propainter", "raft-things.pth")
+    if not os.path.exists(path):
+        pytest.skip("raft-things.pth not staged under weights/propainter")
+    from make_golden_propainter import inputs
+    from oracle import raft_oracle as R
+
+    z = np.load(os.path.join(GOLDEN, "propainter_real.npz"))
+    frames = inputs()[0][:3]
+    x = torch.from_numpy(np.stack([f[:, :, ::-1] for f in frames]).astype(np.float32) / 255).permute(0, 3, 1, 2)[None] * 2 - 1
+    ff, fb = R.raft_bi(R.load_weights(path), x, iters=20)
+    for got, key in ((ff, "gt_flows_f"), (fb, "gt_flows_b")):
+        want = torch.from_numpy(z[key][:, :2].astype(np.float32))
+        assert (got - want).abs().max() < 4e-3          # fp16 storage of flows of magnitude ~3 px: half an ulp is 1e-3
+
+
+def test_flow_completion_oracle_matches_reference():
+    """P4: RecurrentFlowCompleteNet restated (with the pure-torch deformable conv) against the reference's completed flows."""
+    path = os.path.join(ROOT, "weights", "propainter", "recurrent_flow_completion.pth")
+    if not os.path.exists(path):
+        pytest.skip("recurrent_flow_completion.pth not staged under weights/propainter")
+    from make_golden_propainter import inputs
+    from oracle import rfc_oracle as C
+
+    z = np.load(os.path.join(GOLDEN, "propainter_real.npz"))
+    frames, mask = inputs()[:2]
+    fm, _ = P.read_mask(mask, len(frames))
+    masks = torch.from_numpy(np.stack(fm).astype(np.float32) / 255)[None, :, None]
+    gf, gb = (torch.from_numpy(z[k].astype(np.float32)) for k in ("gt_flows_f", "gt_flows_b"))
+    pf, pb = C.complete_bidirectional(C.load_weights(path), gf, gb, masks)
+    for got, key in ((pf, "pred_flows_f"), (pb, "pred_flows_b")):
+        want = torch.from_numpy(z[key].astype(np.float32))
+        assert (got - want).abs().max() < 2e-2, float((got - want).abs().max())     # inputs and pins are fp16 roundings (~2e-3 each)
+    hole = masks[:, :-1].expand_as(pf) > 0
+    assert (pf[hole] - gf[hole]).abs().mean() > 1e-3 and torch.equal(pf[~hole], gf[~hole])
+
+
+def _all_weights():
+    d = os.path.join(ROOT, "weights", "propainter")
+    if not all(os.path.exists(os.path.join(d, f)) for f in ("ProPainter.pth", "raft-things.pth", "recurrent_flow_completion.pth")):
+        pytest.skip("ProPainter weights not staged under weights/propainter")
+    from oracle import propainter_gen_oracle as G
+    from oracle import raft_oracle as R
+    from oracle import rfc_oracle as C
+
+    return G, dict(raft=R.load_weights(os.path.join(d, "raft-things.pth")), rfc=C.load_weights(os.path.join(d, "recurrent_flow_completion.pth")),
+                   gen=G.load_weights(os.path.join(d, "ProPainter.pth")))
+
+
+@pytest.mark.slow
+def test_whole_inpaint_chain_matches_reference_frames():
+    """P2 -> P3 -> P4 -> P5 -> P6 -> P7 restated end to end against `PropainterInpaint.inpaint` of the unmodified reference."""
+    from make_golden_propainter import inputs
+
+    G, weights = _all_weights()
+    z = np.load(os.path.join(GOLDEN, "propainter_real.npz"))
+    frames, mask = inputs()[:2]
+    taps = {}
+    out = np.stack(G.inpaint(weights, frames, mask, taps=taps))
+    for k in ("gt_flows_f", "pred_flows_f", "prop_frames"):
+        assert (taps[k] - torch.from_numpy(z[k].astype(np.float32))).abs().max() < 2e-2
+    d = np.abs(out.astype(np.int32) - z["comp"])
+    assert d.max() <= 2 and (d > 0).mean() < 5e-3, (int(d.max()), float((d > 0).mean()))     # fp32 re-association before the u8 truncation
+
+
+@pytest.mark.slow
+def test_call_strips_match_reference_frames():
+    """P1 + the chain: `PropainterInpaint.__call__` (strip of 128 rows at 704 px width)."""
+    from make_golden_propainter import inputs
+
+    G, weights = _all_weights()
+    z = np.load(os.path.join(GOLDEN, "propainter_real.npz"))
+    _, _, big, big_mask = inputs()
+    keep = [f.copy() for f in big]
+    out = np.stack(G.propainter_call(weights, big, big_mask))
+    assert all(np.array_equal(a, b) for a, b in zip(big, keep))
+    d = np.abs(out.astype(np.int32) - z["call"])
+    assert d.max() <= 2 and (d > 0).mean() < 5e-3, (int(d.max()), float((d > 0).mean()))
