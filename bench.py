@@ -399,6 +399,61 @@ def run_lama(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_config4(args, rank, world, local):
+    """BASELINE config 4 end to end on an in-memory 1080p clip: DBNet detection of the sampled frames -> interval planning ->
+    create_mask -> STTN-det on batch_generator batches, through `vsr_b200.video_inpaint_frames` (the loop of
+    SubtitleRemover.video_inpaint, main.py:260-333).  The reference arm of this line is the CPU port of the same chain."""
+    import cv2
+    import torch
+    import torch.distributed as dist
+    from oracle import sttn_oracle as O
+    from vsr_b200 import STTNDetInpaint, SubtitleDetect, video_inpaint_frames
+
+    T = 120
+    frames = O.synthetic_clip(T, H, W, seed=300 + rank)
+    for i, f in enumerate(frames):          # a subtitle on frames 11..110 (1-based), text changing every 48 frames
+        if 10 <= i < 110:
+            txt = f"subtitle line number {i // 48} of the clip"
+            cv2.putText(f, txt, (420, 1020), cv2.FONT_HERSHEY_SIMPLEX, 1.8, (0, 0, 0), 9, cv2.LINE_AA)
+            cv2.putText(f, txt, (420, 1020), cv2.FONT_HERSHEY_SIMPLEX, 1.8, (255, 255, 255), 4, cv2.LINE_AA)
+    dev = torch.device("cuda", local)
+    p = os.path.join(ROOT, "weights", "sttn-det", "sttn.pth")
+    model = STTNDetInpaint(dev, p if os.path.exists(p) else {k: v.numpy() for k, v in O.random_weights(1).items()})
+    det = SubtitleDetect("", model_dir=os.path.join(ROOT, "weights", "V5", "ch_det"), device=dev)
+    det.SAMPLE_STEP = 3                     # 30 fps video (subtitle_detect.py:29-39)
+    for _ in range(max(min(args.warmup, 2), 1)):
+        out, sub, se = video_inpaint_frames(frames, det, model)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = model.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, sub, se = video_inpaint_frames(frames, det, model)
+    e2e_s = time.perf_counter() - t0
+    launches = model.launch_count - l0 + args.steps * len(range(1, T + 1, 3)) * 249   # + the detector's graph (247 kernels), pre-process, map extraction
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    n_inpainted = sum(e - s + 1 for s, e in se.items())
+    if rank == 0:
+        n = world * args.steps * T
+        print(json.dumps({
+            "metric": "frames/sec at 1080p, detection + STTN-det (BASELINE config 4)", "value": n / e2e_s, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(min(args.warmup, 2), 1), "ms_per_step": e2e_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic 1080p clip with rendered subtitles; reference model files",
+            "config": {"workload": "config 4 chain on a 120-frame 1080p clip: DBNet on every 3rd frame, planning, create_mask, STTN-det batches",
+                       "frame": [H, W], "frames": T, "detected_frames": len(range(1, T + 1, 3)), "inpainted_frames": n_inpainted,
+                       "intervals": {str(k): v for k, v in se.items()}},
+            "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": len(range(1, T + 1, 3)) * H * W * 3 + n_inpainted * int(W * 5 / 18) * W * 3,
+                    "d2h_bytes_per_step": n_inpainted * int(W * 5 / 18) * W * 3, "api": "vsr_b200.video_inpaint_frames(frames, SubtitleDetect, STTNDetInpaint)"},
+            "gpu_launches": int(launches), "note": "host-timed whole chain (inputs are host numpy frames); the per-stage device numbers are the "
+                                                   "sttn-det and dbnet workloads"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -406,7 +461,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det", "dbnet", "lama"],
+    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det", "dbnet", "lama", "config4"],
                     help="sttn-auto = BASELINE config 2 (the contract line); sttn-det / dbnet = the inpaint / detection halves of config 4; "
                          "lama = the big-lama model of config 1 on 1080p strips")
     args = ap.parse_args()
@@ -439,6 +494,9 @@ def main():
         return
     if args.workload == "lama":
         run_lama(args, rank, world, local)
+        return
+    if args.workload == "config4":
+        run_config4(args, rank, world, local)
         return
     if args.workload == "sttn-det":
         return run_det(args, rank, world, local)

@@ -47,3 +47,35 @@ def test_sampling_and_filtering_rules():
     assert P.filter_boxes(boxes, None) == boxes and P.filter_boxes(boxes, []) == boxes
     assert P.filter_boxes(boxes, area + [(0, 100, 0, 100)]) == boxes[:2]
     assert P.filter_and_merge_intervals([], 10) == [] and P.expand_frame_ranges([], 3, 3) == []
+
+
+def test_video_inpaint_frames_loop_on_cpu():
+    """The in-memory mirror of SubtitleRemover.video_inpaint (main.py:260-333) with stand-in detector / model: interval map,
+    mask per interval, batch_generator batching and pass-through of the frames outside every interval."""
+    import numpy as np
+    from vsr_b200 import pipeline as PL
+    from vsr_b200 import subtitle_plan as P
+    from vsr_b200.config import config
+
+    class Det:
+        SAMPLE_STEP = 3
+
+        def scan_frames(self, frames):
+            sampled = {no: [(100, 400, 300, 330)] for no in range(1, len(frames) + 1, 3) if 20 <= no <= 130}
+            return P.drop_empty(P.unify_regions(P.gap_fill(sampled, 3)))
+
+    calls = []
+
+    def model(batch, mask):
+        calls.append((len(batch), int(mask[315, 250]), int(mask[10, 10])))
+        return [b + 1 for b in batch]
+
+    frames = [np.full((360, 480, 3), i % 200, np.uint8) for i in range(160)]
+    out, sub, se = PL.video_inpaint_frames(frames, Det(), model)
+    (s, e), = se.items()
+    assert (s, e) == (min(sub) - 3, max(sub) + 3) and len(out) == 160          # expanded by 3 frames on both sides
+    assert [c[0] for c in calls] == [len(b) for b in PL.batch_generator(list(range(e - s + 1)), config.getSttnMaxLoadNum())]
+    assert all(c[1] == 255 and c[2] == 0 for c in calls)
+    for i, (o, f) in enumerate(zip(out, frames), 1):
+        assert np.array_equal(o, f + 1 if s <= i <= e else f)
+    assert PL.plan_intervals({}, 10) == {} and PL.interval_boxes({5: [(0, 10, 0, 100)]}, 5, 6) == []   # tall box dropped

@@ -23,6 +23,7 @@ class _Config:
         self.subtitleAreaPixelToleranceXPixel = _v(20)  # :66
         self.subtitleTimelineBackwardFrameCount = _v(3)  # :67
         self.subtitleTimelineForwardFrameCount = _v(3)   # :68
+        self.subtitleYXAxisDifferencePixel = _v(10)      # :59
 
     def getSttnMaxLoadNum(self):                 # :94
         return max(self.sttnMaxLoadNum.value, self.sttnNeighborStride.value * self.sttnReferenceLength.value)
@@ -30,7 +31,7 @@ class _Config:
     def adopt(self, other):
         for k in ("sttnNeighborStride", "sttnReferenceLength", "sttnMaxLoadNum", "subtitleAreaDeviationPixel",
                   "subtitleAreaPixelToleranceYPixel", "subtitleAreaPixelToleranceXPixel", "subtitleTimelineBackwardFrameCount",
-                  "subtitleTimelineForwardFrameCount"):
+                  "subtitleTimelineForwardFrameCount", "subtitleYXAxisDifferencePixel"):
             if hasattr(other, k):
                 getattr(self, k).value = getattr(other, k).value
 
