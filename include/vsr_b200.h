@@ -152,6 +152,23 @@ int vsr_rt_hswish_affine(vsr_rt_t* h, uint64_t in, uint64_t out, int64_t n_elems
 int vsr_rt_se_create(vsr_rt_t* h, const float* w1, const float* b1, const float* w2, const float* b2, int C, int mid, float slope, float offset,
                      int residual, int* se_id);     /* w1 [mid][C], w2 [C][mid] */
 int vsr_rt_se_gate(vsr_rt_t* h, int se_id, uint64_t x, int64_t pixels, int cp, float inv_scale, uint64_t gate_dev);   /* gate: fp32 [cp] */
+/* ---- RAFT (backend/inpaint/video/raft/*.py as RAFT_bi calls it, flow_comp_raft.py:39-55): operators beyond the convs.
+ * STATUS: checked against the CPU stand-in of the runtime only — not yet run on a B200. */
+int vsr_rt_pp_frames(vsr_rt_t* h, const uint8_t* const* frames_bgr, int T, int H, int W, uint64_t out);   /* -> fp16 [T,H,W,8] RGB in [-1,1] */
+int vsr_rt_instnorm(vsr_rt_t* h, uint64_t x, int N, int64_t pixels, int cp, int relu, uint64_t out);       /* nn.InstanceNorm2d [+ ReLU] */
+int vsr_rt_context_split(vsr_rt_t* h, uint64_t x, int64_t pixels, uint64_t net, int pitch_net, uint64_t inp, int pitch_inp);  /* tanh | relu, raft.py:116-118 */
+/* all-pairs correlation / sqrt(C) (corr.py:52-60) as a tensor-core GEMM: out[p1][p2], one row of `out_pitch` halves per source pixel */
+int vsr_rt_corr_volume(vsr_rt_t* h, uint64_t fmap1, uint64_t fmap2, int hh, int ww, int C, uint64_t out, int out_pitch);
+int vsr_rt_corr_pool(vsr_rt_t* h, uint64_t in, int64_t rows, int h2, int w2, int pitch_in, uint64_t out, int pitch_out);          /* corr.py:24-27 */
+/* CorrBlock.__call__ (corr.py:29-50): 4 levels x 9x9 bilinear samples per source pixel at (pixel + flow) / 2^level -> out [pixels][324..] */
+int vsr_rt_corr_lookup(vsr_rt_t* h, const uint64_t* level_ptr, const int32_t* level_h, const int32_t* level_w, const int32_t* level_pitch, uint64_t flow32,
+                       int hh, int ww, int64_t pixels, uint64_t out, int out_pitch);
+int vsr_rt_gru_rh(vsr_rt_t* h, uint64_t r, int pitch_r, uint64_t hsrc, int pitch_h, uint64_t out, int pitch_out, int64_t pixels);   /* sigmoid(r) * h */
+int vsr_rt_gru_update(vsr_rt_t* h, uint64_t z, int pitch_z, uint64_t q, int pitch_q, uint64_t hio, int pitch_h, int64_t pixels);   /* update.py:44-56 */
+/* flow32 (+)= delta; refresh the fp16 copies (flow16 [P][8]; channels coff, coff+1 of dst_a / dst_b, the GRU input tensors) */
+int vsr_rt_flow_update(vsr_rt_t* h, uint64_t flow32, uint64_t delta, int pitch_delta, uint64_t flow16, uint64_t dst_a, uint64_t dst_b, int pitch_ab,
+                       int coff, int64_t pixels, int add);
+int vsr_rt_convex_upsample(vsr_rt_t* h, uint64_t flow32, uint64_t mask, int pitch_mask, int N, int hh, int ww, uint64_t out32);      /* raft.py:73-84 -> fp32 [N,2,8h,8w] */
 /* ---- LAMA: what the TorchScript big-lama forward needs beyond the detector's operators ---- */
 /* out[OH,OW] = in[H,W] shifted by (top, left), reflected at the borders (reflect = 1) or zero filled (0) */
 int vsr_rt_pad(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left, int reflect);

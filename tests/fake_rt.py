@@ -10,11 +10,16 @@ import torch.nn.functional as F
 from oracle import dbnet_oracle as D
 
 
+def _r8(x):
+    return (x + 7) // 8 * 8
+
+
 class FakeRuntime:
     def __init__(self, enforce_device_limits=True):
         self.bufs, self.layers, self.launches = {}, [], 0
         self.enforce = enforce_device_limits
         self._next = 0x1000
+        self._bases = []
         self._flag = False
         self._rec = None          # list of (method, args) while a capture is open
         self.graphs = []
@@ -65,25 +70,40 @@ class FakeRuntime:
     def close(self):
         self.bufs.clear()
 
+    def _handle(self, nbytes):
+        h = self._next
+        self._next += (int(nbytes) + 0x1fff) // 0x1000 * 0x1000     # address space like the device: pointer arithmetic stays inside a buffer
+        self._bases.append(h)
+        return h
+
     def alloc(self, nbytes):
         assert self._rec is None, "allocation during graph capture"
-        h = self._next
-        self._next += 0x1000
+        h = self._handle(nbytes)
         self.bufs[h] = np.zeros(int(nbytes) // 2, np.float32)   # one fp32 per fp16 element of the real buffer
         return h
 
     def upload_f32(self, arr):
         assert self._rec is None, "upload during graph capture"
-        h = self._next
-        self._next += 0x1000
-        self.bufs[h] = np.array(arr, np.float32)
+        arr = np.array(arr, np.float32)
+        h = self._handle(arr.size * 4)
+        self.bufs[h] = arr
         return h
+
+    def _resolve(self, ptr):
+        """device pointer -> (buffer, element offset); one element per 2 bytes"""
+        import bisect
+
+        base = self._bases[bisect.bisect_right(self._bases, ptr) - 1]
+        off = ptr - base
+        assert off % 2 == 0 and off // 2 <= self.bufs[base].size
+        return self.bufs[base], off // 2
 
     def _v4(self, t):
         """[n, h, w, channels from the view's first channel on] (channel-slice views advance the pointer by 2*c0 bytes)."""
-        base, c0 = t.ptr - t.ptr % 0x1000, (t.ptr % 0x1000) // 2
+        arr, off = self._resolve(t.ptr)
+        c0 = off % t.cp                     # tensors start at their buffer: offset = whole images (+ a channel offset)
         n = getattr(t, "n", 1)
-        return self.bufs[base][: n * t.h * t.w * t.cp].reshape(n, t.h, t.w, t.cp)[:, :, :, c0:]
+        return arr[off - c0: off - c0 + n * t.h * t.w * t.cp].reshape(n, t.h, t.w, t.cp)[:, :, :, c0:]
 
     def _view(self, t):
         v = self._v4(t)
@@ -108,7 +128,8 @@ class FakeRuntime:
                                 stride=stride, pad_t=pad_t, pad_l=pad_l, dil=dil, groups=groups, transposed=transposed))
         return len(self.layers) - 1
 
-    def conv_ex(self, lid, x, y, relu, out_coff=0, crop=(0, 0)):
+    def conv_ex(self, lid, x, y, relu, out_coff=0, crop=None):
+        """crop None: a plain conv of any kernel family (possibly into a channel slice); (top, left): the cropped-store path."""
         self.conv(lid, x, y, relu, 1.0, 1.0, out_coff, crop)
 
     def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0, out_coff=0, crop=None):
@@ -142,7 +163,7 @@ class FakeRuntime:
         if np.abs(res).max(initial=0.0) > 65504.0 or not np.isfinite(res).all():
             self._flag = True
         v = self._v4(y)
-        if out_coff == 0 and crop is None:
+        if out_coff == 0 and crop is None and _r8(L["cout"]) >= y.c:
             v[:] = 0           # the device kernels write zeros into the channel padding of a plain output tensor
         v[:, :, :, out_coff:out_coff + L["cout"]] = res
         self.launches += 1
@@ -171,6 +192,122 @@ class FakeRuntime:
         out[:C] = 1.0 + g if residual else g
         self.bufs[gate_ptr][:] = out
         self.launches += 2
+
+    # ---- RAFT (csrc/pp_ops.cuh)
+    def frames(self, frames_bgr, y):
+        assert self._rec is None
+        v = self._v4(y)
+        v[:] = 0
+        for t, f in enumerate(frames_bgr):
+            v[t, :, :, :3] = (f[:, :, ::-1].astype(np.float32) / np.float32(255)) * 2 - 1
+        self.launches += 1
+
+    def instnorm(self, x, y, relu):
+        assert self._rec is None
+        v = self._v4(x)
+        m = v.mean((1, 2), keepdims=True)
+        r = (v - m) / np.sqrt(v.var((1, 2), keepdims=True) + 1e-5)
+        self._v4(y)[:] = np.maximum(r, 0) if relu else r
+        self.launches += 2
+
+    def context_split(self, x, net, inp):
+        assert self._rec is None
+        v = self._v4(x)
+        self._v4(net)[..., :128] = np.tanh(v[..., :128])
+        self._v4(inp)[..., :128] = np.maximum(v[..., 128:256], 0)
+        self.launches += 1
+
+    def _raw(self, ptr, count):
+        arr, off = self._resolve(ptr)
+        return arr[off: off + count]
+
+    def corr_volume(self, f1_ptr, f2_ptr, hh, ww, c, out_ptr, out_pitch):
+        assert self._rec is None
+        hw = hh * ww
+        a = self._raw(f1_ptr, hw * c).reshape(hw, c)
+        b = self._raw(f2_ptr, hw * c).reshape(hw, c)
+        out = self._raw(out_ptr, hw * out_pitch).reshape(hw, out_pitch)
+        out[:, :hw] = (a @ b.T) / np.sqrt(np.float32(c))
+        self.launches += 1
+
+    def corr_pool(self, in_ptr, rows, h2, w2, pitch_in, out_ptr, pitch_out):
+        assert self._rec is None
+        src = self._raw(in_ptr, rows * pitch_in).reshape(rows, pitch_in)[:, : h2 * w2].reshape(rows, h2, w2)
+        oh, ow = h2 // 2, w2 // 2
+        p = src[:, : 2 * oh, : 2 * ow].reshape(rows, oh, 2, ow, 2).mean((2, 4))
+        self._raw(out_ptr, rows * pitch_out).reshape(rows, pitch_out)[:, : oh * ow] = p.reshape(rows, -1)
+        self.launches += 1
+
+    def corr_lookup(self, levels, flow32, hh, ww, pixels, out):
+        if self._recording("corr_lookup", levels, flow32, hh, ww, pixels, out):
+            return
+        flow = self.bufs[flow32][: pixels * 2].reshape(pixels, 2)
+        ys, xs = np.divmod(np.arange(pixels) % (hh * ww), ww)
+        res = np.zeros((pixels, 324), np.float32)
+        d = np.arange(-4, 5, dtype=np.float32)
+        for l, (ptr, H, W, pitch) in enumerate(levels):
+            m = self._raw(ptr, pixels * pitch).reshape(pixels, pitch)[:, : H * W].reshape(pixels, H, W)
+            cx, cy = (xs + flow[:, 0]) / 2 ** l, (ys + flow[:, 1]) / 2 ** l
+            X = cx[:, None, None] + d[None, :, None] + np.zeros((1, 1, 9), np.float32)     # (i, j) -> x + d[i]
+            Y = cy[:, None, None] + d[None, None, :] + np.zeros((1, 9, 1), np.float32)     #           y + d[j]
+            x0, y0 = np.floor(X).astype(np.int64), np.floor(Y).astype(np.int64)
+            ax, ay = X - x0, Y - y0
+            acc = np.zeros_like(X)
+            rows = np.arange(pixels)[:, None, None]
+            for dy_, wy in ((0, 1 - ay), (1, ay)):
+                for dx_, wx in ((0, 1 - ax), (1, ax)):
+                    yy, xx = y0 + dy_, x0 + dx_
+                    ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+                    acc += np.where(ok, m[rows, np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], 0) * wy * wx
+            res[:, l * 81:(l + 1) * 81] = acc.reshape(pixels, 81)
+        v = self._v4(out).reshape(pixels, -1)
+        v[:, :324] = res
+        self.launches += 1
+
+    def gru_rh(self, r, hsrc, out):
+        if self._recording("gru_rh", r, hsrc, out):
+            return
+        self._v4(out)[..., :128] = self._v4(hsrc)[..., :128] / (1 + np.exp(-self._v4(r)[..., :128]))
+        self.launches += 1
+
+    def gru_update(self, z, q, hio):
+        if self._recording("gru_update", z, q, hio):
+            return
+        zz = 1 / (1 + np.exp(-self._v4(z)[..., :128]))
+        h = self._v4(hio)
+        h[..., :128] = (1 - zz) * h[..., :128] + zz * np.tanh(self._v4(q)[..., :128])
+        self.launches += 1
+
+    def flow_update(self, flow32, delta, flow16, dst_a, dst_b, coff, add):
+        if self._recording("flow_update", flow32, delta, flow16, dst_a, dst_b, coff, add):
+            return
+        n = flow16.pixels
+        f = self.bufs[flow32][: n * 2].reshape(n, 2)
+        if add:
+            f += self._v4(delta).reshape(n, -1)[:, :2]
+        v = self._v4(flow16).reshape(n, -1)
+        v[:] = 0
+        v[:, :2] = f
+        for dst in (dst_a, dst_b):
+            if dst is not None:
+                self._v4(dst).reshape(n, -1)[:, coff:coff + 2] = f
+        self.launches += 1
+
+    def convex_upsample(self, flow32, mask, n, hh, ww, out32):
+        assert self._rec is None
+        f = torch.from_numpy(self.bufs[flow32][: n * hh * ww * 2].reshape(n, hh, ww, 2).copy()).permute(0, 3, 1, 2)
+        m = torch.from_numpy(self._v4(mask)[..., :576].copy()).permute(0, 3, 1, 2).reshape(n, 1, 9, 8, 8, hh, ww)
+        m = torch.softmax(m, 2)
+        up = F.unfold(8 * f, [3, 3], padding=1).view(n, 2, 9, 1, 1, hh, ww)
+        out = torch.sum(m * up, 2).permute(0, 1, 4, 2, 5, 3).reshape(n, 2, 8 * hh, 8 * ww)
+        self.bufs[out32][: out.numel()] = out.numpy().reshape(-1)
+        self.launches += 1
+
+    def download_f32(self, ptr, shape):
+        return self.bufs[ptr][: int(np.prod(shape))].reshape(shape).copy()
+
+    def zero(self, ptr, nbytes):
+        self.bufs[ptr][: nbytes // 2] = 0
 
     # ---- LAMA-only entry points
     def pad(self, x, y, top, left, reflect=1):

@@ -97,6 +97,16 @@ _PROTOS = {
     "vsr_rt_hswish_affine": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_float, C.c_float, C.c_float]),
     "vsr_rt_se_create": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_int)]),
     "vsr_rt_se_gate": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_float, C.c_uint64]),
+    "vsr_rt_pp_frames": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_instnorm": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_context_split": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_uint64, C.c_int, C.c_uint64, C.c_int]),
+    "vsr_rt_corr_volume": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "vsr_rt_corr_pool": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "vsr_rt_corr_lookup": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), _i32p, _i32p, _i32p, C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_int]),
+    "vsr_rt_gru_rh": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int64]),
+    "vsr_rt_gru_update": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int64]),
+    "vsr_rt_flow_update": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int64, C.c_int]),
+    "vsr_rt_convex_upsample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_residual_add": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int]),
     "vsr_rt_fft_r2c": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_fft_c2r": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),

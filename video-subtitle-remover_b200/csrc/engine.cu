@@ -23,6 +23,7 @@
 #include "elementwise.cuh"
 #include "host_index.h"
 #include "rt_ops.cuh"
+#include "pp_ops.cuh"
 
 namespace vsr {
 
@@ -1217,6 +1218,9 @@ struct vsr_rt {
     float slope = 0.f, offset = 0.f;
   };
   std::vector<std::unique_ptr<SeLayer>> se_layers;
+  std::map<std::pair<int, int>, std::unique_ptr<RtLayer>> corr_layers;  // (target pixels, channels) -> 1x1 "conv" whose weights are fmap2
+  DevBuf norm_stats;                                                    // instance-norm mean | rstd
+  DevBuf frames8;                                                       // u8 frame staging of vsr_rt_pp_frames
   struct FftPlan {
     cufftHandle r2c = 0, c2r = 0;
     std::shared_ptr<DevBuf> re, sp;  // fp32 staging of the real side [H][W][pitch] and of the spectrum [H][W/2+1][C] complex
@@ -1742,6 +1746,151 @@ int vsr_rt_se_gate(vsr_rt_t* h, int se_id, uint64_t x, int64_t pixels, int cp, f
                                                        L.mid, L.slope, L.offset, inv_scale, L.residual, (float*)(uintptr_t)gate_dev);
     CK(cudaGetLastError());
     h->ctx.launches += 2;
+  });
+}
+
+// ---- RAFT operators (csrc/pp_ops.cuh) — written against the CPU stand-in, not yet run on a B200 ---------------
+int vsr_rt_pp_frames(vsr_rt_t* h, const uint8_t* const* frames_bgr, int T, int H, int W, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(frames_bgr && T > 0 && H > 0 && W > 0 && out && !h->capturing, "bad arguments");
+    const size_t fb = (size_t)H * W * 3;
+    h->frames8.ensure(fb * T);
+    cudaStream_t s = h->ctx.stream;
+    for (int t = 0; t < T; ++t) CK(cudaMemcpyAsync(h->frames8.as<uint8_t>() + fb * t, frames_bgr[t], fb, cudaMemcpyHostToDevice, s));
+    const size_t px = (size_t)T * H * W;
+    pp_frames_to_half_kernel<<<blocks_for(px), 256, 0, s>>>(h->frames8.as<uint8_t>(), px, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_instnorm(vsr_rt_t* h, uint64_t x, int N, int64_t pixels, int cp, int relu, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(x && out && N > 0 && pixels > 0 && cp % 8 == 0 && !h->capturing, "bad arguments");
+    h->norm_stats.ensure((size_t)2 * N * cp * 4);
+    float* mean = h->norm_stats.as<float>();
+    float* rstd = mean + (size_t)N * cp;
+    cudaStream_t s = h->ctx.stream;
+    pp_instnorm_stats_kernel<<<dim3(cp / 8, N), 256, 0, s>>>((const __half*)(uintptr_t)x, (size_t)pixels, cp, mean, rstd);
+    CK(cudaGetLastError());
+    const size_t total8 = (size_t)N * pixels * (cp / 8);
+    pp_instnorm_apply_kernel<<<blocks_for(total8), 256, 0, s>>>((const __half*)(uintptr_t)x, (size_t)pixels, cp, mean, rstd, relu,
+                                                                (__half*)(uintptr_t)out, total8);
+    CK(cudaGetLastError());
+    h->ctx.launches += 2;
+  });
+}
+
+int vsr_rt_context_split(vsr_rt_t* h, uint64_t x, int64_t pixels, uint64_t net, int pitch_net, uint64_t inp, int pitch_inp) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(x && net && inp && pixels > 0 && pitch_net % 8 == 0 && pitch_inp % 8 == 0, "bad arguments");
+    pp_context_split_kernel<<<blocks_for((size_t)pixels * 32), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)x, (size_t)pixels,
+                                                                                      (__half*)(uintptr_t)net, pitch_net, (__half*)(uintptr_t)inp, pitch_inp);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_corr_volume(vsr_rt_t* h, uint64_t fmap1, uint64_t fmap2, int hh, int ww, int C, uint64_t out, int out_pitch) {
+  return guarded([&] {
+    rt_check(h);
+    const int hw = hh * ww;
+    REQUIRE(fmap1 && fmap2 && out && hw > 0 && C % 64 == 0 && out_pitch % 8 == 0 && out_pitch >= (hw + 7) / 8 * 8 && !h->capturing, "bad arguments");
+    auto& L = h->corr_layers[{hw, C}];
+    cudaStream_t s = h->ctx.stream;
+    if (!L) {   // all-pairs correlation = 1x1 conv of fmap1 whose [Cout][K] weight matrix IS fmap2 ([pixel][channel], K-major)
+      L = std::make_unique<RtLayer>();
+      L->kind = RtLayer::DENSE;
+      ConvLayer& t = L->tc;
+      t.cin = C; t.pitch = 0; t.cout = hw; t.cout_pad = pad_cout(hw); t.ntaps = 1; t.K = C; t.bn = t.cout_pad < 256 ? t.cout_pad : 256;
+      t.dy[0] = 0; t.dx[0] = 0;
+      t.w.ensure((size_t)t.cout_pad * C * 2);
+      t.b.ensure((size_t)t.cout_pad * 4);
+    }
+    CK(cudaMemcpyAsync(L->tc.w.p, (const void*)(uintptr_t)fmap2, (size_t)hw * C * 2, cudaMemcpyDeviceToDevice, s));
+    ConvIO io;
+    io.in = (const __half*)(uintptr_t)fmap1; io.T = 1; io.H = hh; io.W = ww; io.flags = CONV_SCALED;
+    io.out16 = (__half*)(uintptr_t)out; io.out16_pitch = out_pitch; io.out16_coff = 0;
+    io.alpha = 1.0f / sqrtf((float)C); io.bias_scale = 0.f; io.overflow = h->overflow();   // corr.py:60: / sqrt(dim)
+    run_conv(h->ctx, L->tc, io);
+  });
+}
+
+int vsr_rt_corr_pool(vsr_rt_t* h, uint64_t in, int64_t rows, int h2, int w2, int pitch_in, uint64_t out, int pitch_out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(in && out && rows > 0 && h2 >= 2 && w2 >= 2 && pitch_in >= h2 * w2 && pitch_out >= (h2 / 2) * (w2 / 2), "bad arguments");
+    const size_t n = (size_t)rows * (h2 / 2) * (w2 / 2);
+    pp_corr_pool_kernel<<<blocks_for(n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, (size_t)rows, h2, w2, pitch_in, (__half*)(uintptr_t)out,
+                                                                   pitch_out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_corr_lookup(vsr_rt_t* h, const uint64_t* level_ptr, const int32_t* level_h, const int32_t* level_w, const int32_t* level_pitch, uint64_t flow32,
+                       int hh, int ww, int64_t pixels, uint64_t out, int out_pitch) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(level_ptr && level_h && level_w && level_pitch && flow32 && out && pixels > 0 && out_pitch >= 324, "bad arguments");
+    CorrLevels lv;
+    for (int l = 0; l < 4; ++l) {
+      lv.ptr[l] = (const __half*)(uintptr_t)level_ptr[l];
+      lv.h[l] = level_h[l]; lv.w[l] = level_w[l]; lv.pitch[l] = level_pitch[l];
+    }
+    pp_corr_lookup_kernel<<<blocks_for((size_t)pixels * 324), 256, 0, h->ctx.stream>>>(lv, (const float*)(uintptr_t)flow32, hh, ww, (size_t)pixels,
+                                                                                     (__half*)(uintptr_t)out, out_pitch);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_gru_rh(vsr_rt_t* h, uint64_t r, int pitch_r, uint64_t hsrc, int pitch_h, uint64_t out, int pitch_out, int64_t pixels) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(r && hsrc && out && pixels > 0 && pitch_r % 8 == 0 && pitch_h % 8 == 0 && pitch_out % 8 == 0, "bad arguments");
+    pp_gru_rh_kernel<<<blocks_for((size_t)pixels * 16), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)r, pitch_r, (const __half*)(uintptr_t)hsrc, pitch_h,
+                                                                               (__half*)(uintptr_t)out, pitch_out, (size_t)pixels);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_gru_update(vsr_rt_t* h, uint64_t z, int pitch_z, uint64_t q, int pitch_q, uint64_t hio, int pitch_h, int64_t pixels) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(z && q && hio && pixels > 0 && pitch_z % 8 == 0 && pitch_q % 8 == 0 && pitch_h % 8 == 0, "bad arguments");
+    pp_gru_update_kernel<<<blocks_for((size_t)pixels * 16), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)z, pitch_z, (const __half*)(uintptr_t)q, pitch_q,
+                                                                                   (__half*)(uintptr_t)hio, pitch_h, (size_t)pixels);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_flow_update(vsr_rt_t* h, uint64_t flow32, uint64_t delta, int pitch_delta, uint64_t flow16, uint64_t dst_a, uint64_t dst_b, int pitch_ab,
+                       int coff, int64_t pixels, int add) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(flow32 && flow16 && pixels > 0 && (!add || delta), "bad arguments");
+    pp_flow_update_kernel<<<blocks_for((size_t)pixels), 256, 0, h->ctx.stream>>>((float*)(uintptr_t)flow32, (const __half*)(uintptr_t)delta, pitch_delta,
+                                                                               (__half*)(uintptr_t)flow16, (__half*)(uintptr_t)dst_a, (__half*)(uintptr_t)dst_b,
+                                                                               pitch_ab, coff, (size_t)pixels, add);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_convex_upsample(vsr_rt_t* h, uint64_t flow32, uint64_t mask, int pitch_mask, int N, int hh, int ww, uint64_t out32) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(flow32 && mask && out32 && N > 0 && hh > 0 && ww > 0 && pitch_mask >= 576, "bad arguments");
+    pp_convex_upsample_kernel<<<blocks_for((size_t)N * hh * ww * 64), 256, 0, h->ctx.stream>>>((const float*)(uintptr_t)flow32, (const __half*)(uintptr_t)mask,
+                                                                                             pitch_mask, N, hh, ww, (float*)(uintptr_t)out32);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
   });
 }
 

@@ -1,0 +1,247 @@
+// RAFT operators of the ProPainter path (backend/inpaint/video/raft/*.py) for the graph runtime.
+// STATUS: written and checked against a CPU stand-in of the runtime (tests/fake_rt.py, tests/test_raft_cpu.py); NOT yet run
+// on a B200 — round 1's GPU budget was spent before this file existed.  Nothing else in the engine uses it.
+//
+// Layouts: NHWC fp16 tensors [N,h,w,pitch]; the flow state keeps an fp32 master [N*h*w][2] next to its fp16 copy [N*h*w][8];
+// correlation volumes are [N][h*w source pixels][pitch >= h2*w2 target pixels] fp16, one buffer per pyramid level.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vsr {
+
+// frames u8 [P][3] (BGR as cv2 gives them) -> fp16 [P][8]: RGB order, x/255*2-1 (propainter_inpaint.py:194,216 + to_tensors())
+__global__ void __launch_bounds__(256) pp_frames_to_half_kernel(const uint8_t* __restrict__ bgr, size_t pixels, __half* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = __float2half_rn(__fdiv_rn((float)bgr[i * 3 + (2 - c)], 255.f) * 2.f - 1.f);
+#pragma unroll
+  for (int c = 3; c < 8; ++c) o[c] = __float2half_rn(0.f);
+  *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// nn.InstanceNorm2d (no affine, eps 1e-5, biased variance): statistics per (image, channel); one block = 8 channels of one image
+__global__ void __launch_bounds__(256) pp_instnorm_stats_kernel(const __half* __restrict__ x, size_t pixels, int cp, float* __restrict__ mean,
+                                                                float* __restrict__ rstd) {
+  __shared__ float part[8][16];
+  const int n = blockIdx.y, c8 = blockIdx.x;
+  const __half* base = x + (size_t)n * pixels * cp + c8 * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (size_t p = threadIdx.x; p < pixels; p += blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + p * cp);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+      s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    for (int o = 16; o; o >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int j = 0; j < 8; ++j) { part[warp][j] = s[j]; part[warp][8 + j] = q[j]; }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += part[w][threadIdx.x]; b += part[w][8 + threadIdx.x]; }
+    const float m = a / (float)pixels;
+    const float var = fmaxf(b / (float)pixels - m * m, 0.f);
+    mean[(size_t)n * cp + c8 * 8 + threadIdx.x] = m;
+    rstd[(size_t)n * cp + c8 * 8 + threadIdx.x] = rsqrtf(var + 1e-5f);
+  }
+}
+__global__ void __launch_bounds__(256) pp_instnorm_apply_kernel(const __half* __restrict__ x, size_t pixels, int cp, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, int relu, __half* __restrict__ out, size_t total8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8n = cp >> 3;
+  const int c0 = (int)(i % c8n) * 8;
+  const size_t n = i / ((size_t)pixels * c8n);
+  const uint4 v = reinterpret_cast<const uint4*>(x)[i];
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  const float* m = mean + n * cp + c0;
+  const float* r = rstd + n * cp + c0;
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    float a = (f.x - m[2 * j]) * r[2 * j], b = (f.y - m[2 * j + 1]) * r[2 * j + 1];
+    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    o[j] = __floats2half2_rn(a, b);
+  }
+  reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
+}
+
+// cnet output [P][256] -> net = tanh(first 128) into a slice of pitch pn, inp = relu(last 128) into a slice of pitch pi (raft.py:116-118)
+__global__ void __launch_bounds__(256) pp_context_split_kernel(const __half* __restrict__ x, size_t pixels, __half* __restrict__ net, int pn,
+                                                               __half* __restrict__ inp, int pi) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels * 32) return;
+  const int c8 = i % 32;
+  const size_t p = i / 32;
+  const uint4 v = *reinterpret_cast<const uint4*>(x + p * 256 + c8 * 8);
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    o[j] = c8 < 16 ? __floats2half2_rn(tanhf(f.x), tanhf(f.y)) : __floats2half2_rn(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f));
+  }
+  __half* dst = c8 < 16 ? net + p * pn + c8 * 8 : inp + p * pi + (c8 - 16) * 8;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+}
+
+// F.avg_pool2d(corr, 2, stride=2) over the TARGET dims of a correlation volume: in [rows][pitch_in] viewed as [h2][w2] per row
+__global__ void __launch_bounds__(256) pp_corr_pool_kernel(const __half* __restrict__ in, size_t rows, int h2, int w2, int pitch_in,
+                                                           __half* __restrict__ out, int pitch_out) {
+  const int oh = h2 >> 1, ow = w2 >> 1;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * oh * ow) return;
+  const int x = i % ow;
+  const int y = (i / ow) % oh;
+  const size_t r = i / ((size_t)ow * oh);
+  const __half* s = in + r * pitch_in + (size_t)(2 * y) * w2 + 2 * x;
+  const float v = (__half2float(s[0]) + __half2float(s[1]) + __half2float(s[w2]) + __half2float(s[w2 + 1])) * 0.25f;
+  out[r * pitch_out + (size_t)y * ow + x] = __float2half_rn(v);
+}
+
+struct CorrLevels {
+  const __half* ptr[4];
+  int h[4], w[4], pitch[4];
+};
+// CorrBlock.__call__ (corr.py:29-50): for source pixel p of pair n at coords1 = (x + flow.x, y + flow.y): 4 levels x 9x9 bilinear
+// samples (zeros outside, align_corners=True) of its correlation map at coords1 / 2^l + delta.  The reference adds the FIRST
+// meshgrid component (the row offset list) to x: sample (i, j) sits at (x + d[i], y + d[j]); kept.  out [P][pitch], channel l*81 + i*9 + j.
+__global__ void __launch_bounds__(256) pp_corr_lookup_kernel(CorrLevels lv, const float* __restrict__ flow, int h, int w, size_t pixels,
+                                                             __half* __restrict__ out, int pitch) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels * 324) return;
+  const int k = i % 324;
+  const size_t p = i / 324;
+  const int l = k / 81, ij = k - l * 81, ii = ij / 9, jj = ij - ii * 9;
+  const int px = (int)(p % w), py = (int)((p / w) % h);
+  const float scale = 1.f / (float)(1 << l);
+  const float x = ((float)px + flow[p * 2]) * scale + (float)(ii - 4);
+  const float y = ((float)py + flow[p * 2 + 1]) * scale + (float)(jj - 4);
+  const int H = lv.h[l], W = lv.w[l];
+  const __half* m = lv.ptr[l] + p * lv.pitch[l];
+  const float fx = floorf(x), fy = floorf(y);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float ax = x - fx, ay = y - fy;
+  float v = 0.f;
+  if (y0 >= 0 && y0 < H) {
+    if (x0 >= 0 && x0 < W) v += (1.f - ax) * (1.f - ay) * __half2float(m[(size_t)y0 * W + x0]);
+    if (x0 + 1 >= 0 && x0 + 1 < W) v += ax * (1.f - ay) * __half2float(m[(size_t)y0 * W + x0 + 1]);
+  }
+  if (y0 + 1 >= 0 && y0 + 1 < H) {
+    if (x0 >= 0 && x0 < W) v += (1.f - ax) * ay * __half2float(m[(size_t)(y0 + 1) * W + x0]);
+    if (x0 + 1 >= 0 && x0 + 1 < W) v += ax * ay * __half2float(m[(size_t)(y0 + 1) * W + x0 + 1]);
+  }
+  out[p * pitch + k] = __float2half_rn(v);
+}
+
+// SepConvGRU (update.py:34-57), one half step: rh = sigmoid(r) * h (into the q-conv input), then h = (1 - sigmoid(z)) * h + sigmoid(z) * tanh(q)
+__global__ void __launch_bounds__(256) pp_gru_rh_kernel(const __half* __restrict__ r, int pr, const __half* __restrict__ hsrc, int ph,
+                                                        __half* __restrict__ out, int po, size_t pixels) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels * 16) return;
+  const int c8 = i % 16;
+  const size_t p = i / 16;
+  const uint4 vr = *reinterpret_cast<const uint4*>(r + p * pr + c8 * 8), vh = *reinterpret_cast<const uint4*>(hsrc + p * ph + c8 * 8);
+  const __half2* a = reinterpret_cast<const __half2*>(&vr);
+  const __half2* b = reinterpret_cast<const __half2*>(&vh);
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fr = __half22float2(a[j]), fh = __half22float2(b[j]);
+    o[j] = __floats2half2_rn(fh.x / (1.f + __expf(-fr.x)), fh.y / (1.f + __expf(-fr.y)));
+  }
+  *reinterpret_cast<uint4*>(out + p * po + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+}
+__global__ void __launch_bounds__(256) pp_gru_update_kernel(const __half* __restrict__ z, int pz, const __half* __restrict__ q, int pq,
+                                                            __half* __restrict__ hio, int ph, size_t pixels) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels * 16) return;
+  const int c8 = i % 16;
+  const size_t p = i / 16;
+  const uint4 vz = *reinterpret_cast<const uint4*>(z + p * pz + c8 * 8), vq = *reinterpret_cast<const uint4*>(q + p * pq + c8 * 8);
+  uint4 vh = *reinterpret_cast<const uint4*>(hio + p * ph + c8 * 8);
+  const __half2* a = reinterpret_cast<const __half2*>(&vz);
+  const __half2* b = reinterpret_cast<const __half2*>(&vq);
+  __half2* c = reinterpret_cast<__half2*>(&vh);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fz = __half22float2(a[j]), fq = __half22float2(b[j]), fh = __half22float2(c[j]);
+    const float zx = 1.f / (1.f + __expf(-fz.x)), zy = 1.f / (1.f + __expf(-fz.y));
+    c[j] = __floats2half2_rn((1.f - zx) * fh.x + zx * tanhf(fq.x), (1.f - zy) * fh.y + zy * tanhf(fq.y));
+  }
+  *reinterpret_cast<uint4*>(hio + p * ph + c8 * 8) = vh;
+}
+
+// flow32 += delta (the flow head's 2 channels, fp16 [P][pd]); refresh the fp16 copies: flow16 [P][8] (the motion encoder's input) and
+// the last two channels of the motion features inside the GRU input tensors (torch.cat([out, flow]), update.py:96)
+__global__ void __launch_bounds__(256) pp_flow_update_kernel(float* __restrict__ flow32, const __half* __restrict__ delta, int pd,
+                                                             __half* __restrict__ flow16, __half* __restrict__ dst_a, __half* __restrict__ dst_b,
+                                                             int pitch_ab, int coff, size_t pixels, int add) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+  float fx = flow32[p * 2], fy = flow32[p * 2 + 1];
+  if (add) {
+    fx += __half2float(delta[p * pd]);
+    fy += __half2float(delta[p * pd + 1]);
+    flow32[p * 2] = fx;
+    flow32[p * 2 + 1] = fy;
+  }
+  const __half hx = __float2half_rn(fx), hy = __float2half_rn(fy);
+  __align__(16) __half o[8] = {hx, hy, __half(), __half(), __half(), __half(), __half(), __half()};
+  *reinterpret_cast<uint4*>(flow16 + p * 8) = *reinterpret_cast<const uint4*>(o);
+  if (dst_a) { dst_a[p * pitch_ab + coff] = hx; dst_a[p * pitch_ab + coff + 1] = hy; }
+  if (dst_b) { dst_b[p * pitch_ab + coff] = hx; dst_b[p * pitch_ab + coff + 1] = hy; }
+}
+
+// RAFT.upsample_flow (raft.py:73-84): out[n][c][8y+sy][8x+sx] = sum_k softmax_k(mask[n][y][x][k*64 + sy*8 + sx]) * 8 * flow[n][y+ky-1][x+kx-1][c]
+// (3x3 neighbourhood with zero padding, k = ky*3 + kx); out is planar fp32 [N][2][8h][8w]
+__global__ void __launch_bounds__(256) pp_convex_upsample_kernel(const float* __restrict__ flow32, const __half* __restrict__ mask, int pm, int N, int h,
+                                                                 int w, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * h * w * 64;
+  if (i >= total) return;
+  const int s = i % 64, sy = s >> 3, sx = s & 7;
+  const size_t p = i / 64;
+  const int x = (int)(p % w), y = (int)((p / w) % h);
+  const int n = (int)(p / ((size_t)w * h));
+  const __half* m = mask + p * pm;
+  float e[9], mx = -1e30f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { e[k] = __half2float(m[k * 64 + s]); mx = fmaxf(mx, e[k]); }
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { e[k] = __expf(e[k] - mx); den += e[k]; }
+  float ux = 0.f, uy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+    if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+    const float* f = flow32 + (((size_t)n * h + yy) * w + xx) * 2;
+    ux += e[k] * f[0];
+    uy += e[k] * f[1];
+  }
+  const float g = 8.f / den;
+  const size_t H8 = (size_t)8 * h, W8 = (size_t)8 * w;
+  const size_t o = ((size_t)n * 2 * H8 + (size_t)(8 * y + sy)) * W8 + (size_t)(8 * x + sx);
+  out[o] = ux * g;
+  out[o + H8 * W8] = uy * g;
+}
+
+}  // namespace vsr
