@@ -169,6 +169,12 @@ int vsr_rt_gru_update(vsr_rt_t* h, uint64_t z, int pitch_z, uint64_t q, int pitc
 int vsr_rt_flow_update(vsr_rt_t* h, uint64_t flow32, uint64_t delta, int pitch_delta, uint64_t flow16, uint64_t dst_a, uint64_t dst_b, int pitch_ab,
                        int coff, int64_t pixels, int add);
 int vsr_rt_convex_upsample(vsr_rt_t* h, uint64_t flow32, uint64_t mask, int pitch_mask, int N, int hh, int ww, uint64_t out32);      /* raft.py:73-84 -> fp32 [N,2,8h,8w] */
+/* ---- ProPainter image propagation (propainter.py:107-193 with learnable=False, propainter_inpaint.py:283,311).
+ * State tensors are fp16 [T,H,W,8]: channels 0..2 the frame in [-1,1], channel 3 the mask; flows are planar fp32 [2][H][W].
+ * STATUS: checked against the CPU stand-in only. */
+int vsr_rt_img_prop_step(vsr_rt_t* h, uint64_t prev, uint64_t cur, uint64_t flow_prop, uint64_t flow_check, int H, int W, uint64_t out);
+/* prop == 0: state = frame * (1 - m) | m from frames [T,H,W,8] and one device u8 mask [H,W];  else: frame * (1 - m) + prop * m | prop's mask */
+int vsr_rt_prop_state(vsr_rt_t* h, uint64_t frames, uint64_t mask_u8, uint64_t prop, int T, int H, int W, uint64_t out);
 /* ---- LAMA: what the TorchScript big-lama forward needs beyond the detector's operators ---- */
 /* out[OH,OW] = in[H,W] shifted by (top, left), reflected at the borders (reflect = 1) or zero filled (0) */
 int vsr_rt_pad(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left, int reflect);

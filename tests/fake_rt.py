@@ -309,6 +309,76 @@ class FakeRuntime:
     def zero(self, ptr, nbytes):
         self.bufs[ptr][: nbytes // 2] = 0
 
+    # ---- ProPainter image propagation (P5)
+    def upload_bytes(self, arr):
+        arr = np.ascontiguousarray(arr)
+        h = self._handle(max(arr.nbytes, 16))
+        if arr.dtype == np.float32:        # one slot per 2 bytes: an fp32 element occupies two slots (value, unused), so byte offsets stay valid
+            slots = np.zeros(2 * arr.size, np.float32)
+            slots[0::2] = arr.reshape(-1)
+            self.bufs[h] = slots
+        else:                              # u8 masks: no pointer arithmetic on them, one slot per element
+            self.bufs[h] = arr.astype(np.float32).reshape(-1)
+        return h
+
+    def _raw32(self, ptr, count):
+        arr, off = self._resolve(ptr)
+        return arr[off: off + 2 * count: 2]
+
+    def prop_state(self, frames, mask_u8, prop, out):
+        assert self._rec is None
+        f = self._v4(frames)
+        m = (self.bufs[mask_u8][: frames.h * frames.w].reshape(1, frames.h, frames.w) > 0)
+        o = self._v4(out)
+        o[:] = f
+        if prop is None:
+            o[..., :3] = np.where(m[..., None], 0.0, f[..., :3])
+            o[..., 3] = m
+        else:
+            p = self._v4(prop)
+            o[..., :3] = np.where(m[..., None], p[..., :3], f[..., :3])
+            o[..., 3] = p[..., 3]
+        self.launches += 1
+
+    def img_prop_step(self, prev, cur, flow_prop, flow_check, out):
+        """numpy transcription of pp_img_prop_step_kernel (NOT of the torch reference): hand-written bilinear / nearest sampling, so
+        that the CPU test checks the kernel's arithmetic against the oracle."""
+        assert self._rec is None
+        H, W = cur.h, cur.w
+        fp = self._raw32(flow_prop, 2 * H * W).reshape(2, H, W)
+        fc = self._raw32(flow_check, 2 * H * W).reshape(2, H, W)
+        pv, cu = self._v4(prev)[0], self._v4(cur)[0]
+        ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+        sx, sy = xs + fp[0], ys + fp[1]
+
+        def bilinear(m):
+            x0, y0 = np.floor(sx), np.floor(sy)
+            ax, ay = sx - x0, sy - y0
+            x0, y0 = x0.astype(np.int64), y0.astype(np.int64)
+            acc = np.zeros((H, W), np.float32)
+            for dy, wy in ((0, 1 - ay), (1, ay)):
+                for dx, wx in ((0, 1 - ax), (1, ax)):
+                    yy, xx = y0 + dy, x0 + dx
+                    ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+                    acc += np.where(ok, m[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], 0) * wy * wx
+            return acc
+
+        bx, by = bilinear(fc[0]), bilinear(fc[1])
+        dx, dy = fp[0] + bx, fp[1] + by
+        valid = dx * dx + dy * dy < 0.01 * (fp[0] ** 2 + fp[1] ** 2 + bx * bx + by * by) + 0.5
+        hole_there = bilinear(pv[..., 3]) > 0.1
+        cur_hole = cu[..., 3] > 0.1
+        fill = valid & ~hole_there
+        nx, ny = np.rint(sx).astype(np.int64), np.rint(sy).astype(np.int64)       # round half to even, like nearbyintf
+        inside = (nx >= 0) & (nx < W) & (ny >= 0) & (ny < H)
+        warped = np.where(inside[..., None], pv[np.clip(ny, 0, H - 1), np.clip(nx, 0, W - 1), :3], 0)
+        o = self._v4(out)[0]
+        o[:] = cu
+        take = cur_hole & fill
+        o[..., :3] = np.where(take[..., None], warped, cu[..., :3])
+        o[..., 3] = (cur_hole & ~fill).astype(np.float32)
+        self.launches += 1
+
     # ---- LAMA-only entry points
     def pad(self, x, y, top, left, reflect=1):
         if self._recording("pad", x, y, top, left, reflect):

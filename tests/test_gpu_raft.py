@@ -27,3 +27,28 @@ def test_raft_flows_vs_oracle(capi):
     for got, want in ((ff, wf[0].numpy()), (fb, wb[0].numpy())):
         epe = np.sqrt(((got - want) ** 2).sum(1))
         assert np.isfinite(got).all() and epe.mean() <= 0.05 and epe.max() <= 0.5, (float(epe.mean()), float(epe.max()))
+
+
+def test_image_propagation_vs_oracle(capi):
+    """P5 on the device (gated like the RAFT test): exact mask agreement and fp16-level frame agreement with the oracle."""
+    import sys
+
+    from conftest import GOLDEN
+    from oracle import propainter_oracle as P
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_propainter import inputs
+    from vsr_b200.flow_propagation import _PropRuntime, propagate_images_host
+
+    z = np.load(os.path.join(GOLDEN, "propainter_real.npz"))
+    frames, mask = inputs()[:2]
+    _, md = P.read_mask(mask, len(frames))
+    ff, fb = z["pred_flows_f"][0].astype(np.float32), z["pred_flows_b"][0].astype(np.float32)
+    rt = _PropRuntime("cuda:0")
+    upd, um = propagate_images_host(rt, frames, md[0], ff, fb)
+    rt.close()
+    x = torch.from_numpy(np.stack([f[:, :, ::-1] for f in frames]).astype(np.float32) / 255).permute(0, 3, 1, 2)[None] * 2 - 1
+    masks = torch.from_numpy(np.stack(md).astype(np.float32) / 255)[None, :, None]
+    prop, want_m = P.img_propagation(x * (1 - masks), torch.from_numpy(ff)[None], torch.from_numpy(fb)[None], masks)
+    want = P.updated_frames(x, masks, prop)[0].numpy()
+    assert (um != want_m[0].numpy()).mean() < 1e-4 and np.abs(upd - want).max() < 2e-3

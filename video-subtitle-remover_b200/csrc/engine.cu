@@ -1894,6 +1894,34 @@ int vsr_rt_convex_upsample(vsr_rt_t* h, uint64_t flow32, uint64_t mask, int pitc
   });
 }
 
+int vsr_rt_img_prop_step(vsr_rt_t* h, uint64_t prev, uint64_t cur, uint64_t flow_prop, uint64_t flow_check, int H, int W, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(prev && cur && flow_prop && flow_check && out && H > 0 && W > 0, "bad arguments");
+    pp_img_prop_step_kernel<<<dim3((W + 255) / 256, H), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)prev, (const __half*)(uintptr_t)cur,
+                                                                               (const float*)(uintptr_t)flow_prop, (const float*)(uintptr_t)flow_check, H, W,
+                                                                               (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_prop_state(vsr_rt_t* h, uint64_t frames, uint64_t mask_u8, uint64_t prop, int T, int H, int W, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(frames && mask_u8 && out && T > 0 && H > 0 && W > 0, "bad arguments");
+    const size_t plane = (size_t)H * W, px = plane * T;
+    if (prop)
+      pp_state_compose_kernel<<<blocks_for(px), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)frames, (const uint8_t*)(uintptr_t)mask_u8,
+                                                                        (const __half*)(uintptr_t)prop, plane, px, (__half*)(uintptr_t)out);
+    else
+      pp_state_init_kernel<<<blocks_for(px), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)frames, (const uint8_t*)(uintptr_t)mask_u8, plane, px,
+                                                                     (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
 int vsr_rt_residual_add(vsr_rt_t* h, uint64_t x32, uint64_t y16, uint64_t x16, int64_t n_elems, int init) {
   return guarded([&] {
     rt_check(h);

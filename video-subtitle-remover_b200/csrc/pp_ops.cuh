@@ -244,4 +244,90 @@ __global__ void __launch_bounds__(256) pp_convex_upsample_kernel(const float* __
   out[o + H8 * W8] = uy * g;
 }
 
+// ---- P5: InpaintGenerator.img_propagation = BidirectionalPropagation(learnable=False) (propainter.py:107-193) ---------------------
+// One step of the sequential propagation for one frame.  State pixels are 8 halves: channels 0..2 the (masked) frame in [-1, 1],
+// channel 3 the mask (1 = still missing).  prev = the propagated previous frame of this pass, cur = this frame of the pass input;
+// flow_prop / flow_check: planar fp32 [2][H][W] (x then y).  Per pixel (all of :160-176):
+//   valid = |f + bilinear(flow_check)(p + f)|^2 < 0.01 (|f|^2 + |.|^2) + 0.5            fbConsistencyCheck :24-33
+//   warped = nearest(prev frame)(p + f), hole_there = bilinear(prev mask)(p + f) > 0.1    flow_warp(.., 'nearest') / default bilinear
+//   use = cur mask & valid & !hole_there;  out frame = use ? warped : cur;  out mask = cur mask & !(valid & !hole_there)
+// grid_sample semantics: align_corners=True (pixel coordinates), zeros outside, nearest = round half to even.
+__device__ __forceinline__ float pp_bilinear_plane(const float* __restrict__ m, int H, int W, float x, float y) {
+  const float fx = floorf(x), fy = floorf(y);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float ax = x - fx, ay = y - fy;
+  float v = 0.f;
+  if (y0 >= 0 && y0 < H) {
+    if (x0 >= 0 && x0 < W) v += (1.f - ax) * (1.f - ay) * m[(size_t)y0 * W + x0];
+    if (x0 + 1 >= 0 && x0 + 1 < W) v += ax * (1.f - ay) * m[(size_t)y0 * W + x0 + 1];
+  }
+  if (y0 + 1 >= 0 && y0 + 1 < H) {
+    if (x0 >= 0 && x0 < W) v += (1.f - ax) * ay * m[(size_t)(y0 + 1) * W + x0];
+    if (x0 + 1 >= 0 && x0 + 1 < W) v += ax * ay * m[(size_t)(y0 + 1) * W + x0 + 1];
+  }
+  return v;
+}
+__global__ void __launch_bounds__(256) pp_img_prop_step_kernel(const __half* __restrict__ prev, const __half* __restrict__ cur, const float* __restrict__ flow_prop,
+                                                               const float* __restrict__ flow_check, int H, int W, __half* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const size_t p = (size_t)y * W + x, plane = (size_t)H * W;
+  const float fx = flow_prop[p], fy = flow_prop[plane + p];
+  const float sx = (float)x + fx, sy = (float)y + fy;
+  const float bx = pp_bilinear_plane(flow_check, H, W, sx, sy), by = pp_bilinear_plane(flow_check + plane, H, W, sx, sy);
+  const float dx = fx + bx, dy = fy + by;
+  const bool valid = dx * dx + dy * dy < 0.01f * (fx * fx + fy * fy + bx * bx + by * by) + 0.5f;
+  // bilinear sample of the previous mask (channel 3 of the state)
+  float hole = 0.f;
+  {
+    const float gx = floorf(sx), gy = floorf(sy);
+    const int x0 = (int)gx, y0 = (int)gy;
+    const float ax = sx - gx, ay = sy - gy;
+    auto mk = [&](int yy, int xx) { return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __half2float(prev[((size_t)yy * W + xx) * 8 + 3]) : 0.f; };
+    hole = (1.f - ax) * (1.f - ay) * mk(y0, x0) + ax * (1.f - ay) * mk(y0, x0 + 1) + (1.f - ax) * ay * mk(y0 + 1, x0) + ax * ay * mk(y0 + 1, x0 + 1);
+  }
+  const bool hole_there = hole > 0.1f;
+  uint4 c = *reinterpret_cast<const uint4*>(cur + p * 8);
+  __half* ch = reinterpret_cast<__half*>(&c);
+  const bool cur_hole = __half2float(ch[3]) > 0.1f;
+  const bool fill = valid && !hole_there;
+  if (cur_hole && fill) {
+    const int nx = (int)nearbyintf(sx), ny = (int)nearbyintf(sy);      // nearest, round half to even
+    float w3[3] = {0.f, 0.f, 0.f};
+    if (nx >= 0 && nx < W && ny >= 0 && ny < H) {
+      const __half* q = prev + ((size_t)ny * W + nx) * 8;
+      w3[0] = __half2float(q[0]); w3[1] = __half2float(q[1]); w3[2] = __half2float(q[2]);
+    }
+    ch[0] = __float2half_rn(w3[0]); ch[1] = __float2half_rn(w3[1]); ch[2] = __float2half_rn(w3[2]);
+  }
+  ch[3] = __float2half_rn((cur_hole && !fill) ? 1.f : 0.f);
+  *reinterpret_cast<uint4*>(out + p * 8) = c;
+}
+
+// state pixels from frames and masks: frame * (1 - m) | m  (propainter_inpaint.py:283), frames fp16 [P][8] RGB in [-1,1], mask u8 [H][W] shared
+// by all frames (> 0 = hole) ; and the inverse composition  updated = frame * (1 - m) + prop * m  (:311) into channels 0..2 (+ updated mask in 3)
+__global__ void __launch_bounds__(256) pp_state_init_kernel(const __half* __restrict__ frames, const uint8_t* __restrict__ mask, size_t plane, size_t pixels,
+                                                            __half* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  uint4 v = *reinterpret_cast<const uint4*>(frames + i * 8);
+  __half* h = reinterpret_cast<__half*>(&v);
+  const bool m = mask[i % plane] > 0;
+  if (m) { h[0] = __float2half_rn(0.f); h[1] = h[0]; h[2] = h[0]; }
+  h[3] = __float2half_rn(m ? 1.f : 0.f);
+  *reinterpret_cast<uint4*>(out + i * 8) = v;
+}
+__global__ void __launch_bounds__(256) pp_state_compose_kernel(const __half* __restrict__ frames, const uint8_t* __restrict__ mask, const __half* __restrict__ prop,
+                                                               size_t plane, size_t pixels, __half* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+  uint4 f = *reinterpret_cast<const uint4*>(frames + i * 8);
+  const uint4 q = *reinterpret_cast<const uint4*>(prop + i * 8);
+  __half* h = reinterpret_cast<__half*>(&f);
+  const __half* g = reinterpret_cast<const __half*>(&q);
+  if (mask[i % plane] > 0) { h[0] = g[0]; h[1] = g[1]; h[2] = g[2]; }
+  h[3] = g[3];
+  *reinterpret_cast<uint4*>(out + i * 8) = f;
+}
+
 }  // namespace vsr
