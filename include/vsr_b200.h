@@ -175,6 +175,17 @@ int vsr_rt_convex_upsample(vsr_rt_t* h, uint64_t flow32, uint64_t mask, int pitc
 int vsr_rt_img_prop_step(vsr_rt_t* h, uint64_t prev, uint64_t cur, uint64_t flow_prop, uint64_t flow_check, int H, int W, uint64_t out);
 /* prop == 0: state = frame * (1 - m) | m from frames [T,H,W,8] and one device u8 mask [H,W];  else: frame * (1 - m) + prop * m | prop's mask */
 int vsr_rt_prop_state(vsr_rt_t* h, uint64_t frames, uint64_t mask_u8, uint64_t prop, int T, int H, int W, uint64_t out);
+/* ---- ProPainter flow completion (video/model/recurrent_flow_completion.py): operators beyond the convs.
+ * STATUS: checked against the CPU stand-in only. */
+int vsr_rt_rfc_input(vsr_rt_t* h, uint64_t flow32, uint64_t mask_u8, int N, int H, int W, int reverse, uint64_t out);      /* [f*(1-m), m] -> fp16 [N,H,W,8] */
+int vsr_rt_pad_replicate(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left);
+int vsr_rt_leaky_relu(vsr_rt_t* h, uint64_t x, int64_t n_elems, float slope);                                               /* in place */
+int vsr_rt_temporal_taps(vsr_rt_t* h, uint64_t in, int T, int64_t pixels, int cp_in, uint64_t out, int cp_out);             /* frames t-2, t, t+2 side by side */
+/* gather half of torchvision.ops.deform_conv2d (3x3, pad 1, modulated, G offset groups): cols [pixels][9*C]; the 1x1 conv over cols finishes it */
+int vsr_rt_deform_cols(vsr_rt_t* h, uint64_t xa, int pitch_a, int Ca, uint64_t xb, int pitch_b, int C, int G, uint64_t om, int pitch_om, float max_residue,
+                       uint64_t flow32, int H, int W, int64_t pixels, uint64_t cols, int pitch_cols);
+int vsr_rt_rfc_combine(vsr_rt_t* h, uint64_t pred, int pitch_pred, uint64_t flow32, uint64_t mask_u8, int N, int H, int W, int reverse, uint64_t out32);
+int vsr_rt_upsample2x_bilinear(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out);   /* F.interpolate(x2, bilinear, align_corners=True) */
 /* ---- LAMA: what the TorchScript big-lama forward needs beyond the detector's operators ---- */
 /* out[OH,OW] = in[H,W] shifted by (top, left), reflected at the borders (reflect = 1) or zero filled (0) */
 int vsr_rt_pad(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left, int reflect);

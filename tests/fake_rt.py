@@ -309,6 +309,94 @@ class FakeRuntime:
     def zero(self, ptr, nbytes):
         self.bufs[ptr][: nbytes // 2] = 0
 
+    # ---- ProPainter flow completion (P4): transcriptions of the pp_ops.cuh kernels
+    def rfc_input(self, flow32, mask_u8, n, hh, ww, reverse, out):
+        assert self._rec is None
+        f = self._raw32(flow32, n * 2 * hh * ww).reshape(n, 2, hh, ww)
+        if reverse:
+            f = f[::-1]
+        m = (self.bufs[mask_u8][: hh * ww].reshape(hh, ww) > 0).astype(np.float32)
+        v = self._v4(out)
+        v[:] = 0
+        v[..., 0], v[..., 1], v[..., 2] = f[:, 0] * (1 - m), f[:, 1] * (1 - m), m
+        self.launches += 1
+
+    def pad_replicate(self, x, y, top, left):
+        assert self._rec is None
+        self._v4(y)[:] = np.pad(self._v4(x), ((0, 0), (top, y.h - x.h - top), (left, y.w - x.w - left), (0, 0)), mode="edge")
+        self.launches += 1
+
+    def leaky(self, x, slope):
+        assert self._rec is None
+        v = self._v4(x)
+        v[:] = np.where(v > 0, v, v * slope)
+        self.launches += 1
+
+    def temporal_taps(self, x, y):
+        assert self._rec is None
+        v, o = self._v4(x), self._v4(y)
+        o[:] = 0
+        T = v.shape[0]
+        for k in range(3):
+            for t in range(T):
+                ts = t + 2 * (k - 1)
+                if 0 <= ts < T:
+                    o[t, :, :, k * x.cp: (k + 1) * x.cp] = v[ts]
+        self.launches += 1
+
+    def deform_cols(self, xa, ca, xb, c, groups, om, max_residue, flow32, cols):
+        assert self._rec is None
+        H, W = xa.h, xa.w
+        a = self._v4(xa)[..., :ca]
+        x = a if xb is None else np.concatenate([a, self._v4(xb)[..., : c - ca]], -1)       # [n,H,W,C]
+        o = self._v4(om)
+        n = x.shape[0]
+        gk = groups * 9
+        off = max_residue * np.tanh(o[..., : 2 * gk]).reshape(n, H, W, gk, 2)
+        if flow32:
+            fl = self.bufs[flow32][: n * H * W * 2].reshape(n, H, W, 1, 2)
+            off = off + fl[..., ::-1]                                                            # (dy, dx) += (flow.y, flow.x)
+        msk = 1 / (1 + np.exp(-o[..., 2 * gk: 3 * gk]))
+        ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+        out = np.zeros((n, H, W, 9, c), np.float32)
+        cpg = c // groups
+        for g in range(groups):
+            xg = x[..., g * cpg:(g + 1) * cpg]
+            for k in range(9):
+                ky, kx = divmod(k, 3)
+                sy = ys[None] - 1 + ky + off[:, :, :, g * 9 + k, 0]
+                sx = xs[None] - 1 + kx + off[:, :, :, g * 9 + k, 1]
+                y0, x0 = np.floor(sy), np.floor(sx)
+                ay, ax = sy - y0, sx - x0
+                y0, x0 = y0.astype(np.int64), x0.astype(np.int64)
+                acc = np.zeros((n, H, W, cpg), np.float32)
+                nn = np.arange(n)[:, None, None]
+                for dy, wy in ((0, 1 - ay), (1, ay)):
+                    for dx, wx in ((0, 1 - ax), (1, ax)):
+                        yy, xx = y0 + dy, x0 + dx
+                        ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+                        acc += np.where(ok[..., None], xg[nn, np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], 0) * (wy * wx)[..., None]
+                out[:, :, :, k, g * cpg:(g + 1) * cpg] = acc * msk[:, :, :, g * 9 + k, None]
+        self._v4(cols)[..., : 9 * c] = out.reshape(n, H, W, 9 * c)
+        self.launches += 1
+
+    def rfc_combine(self, pred, flow32, mask_u8, n, hh, ww, reverse, out32):
+        assert self._rec is None
+        p = self._v4(pred)[..., :2]
+        if reverse:
+            p = p[::-1]
+        f = self._raw32(flow32, n * 2 * hh * ww).reshape(n, 2, hh, ww)
+        m = (self.bufs[mask_u8][: hh * ww].reshape(hh, ww) > 0).astype(np.float32)
+        res = p.transpose(0, 3, 1, 2) * m + f * (1 - m)
+        self.bufs[out32][: res.size] = res.reshape(-1)          # alloc()-ed fp32 outputs are read back contiguously (download_f32)
+        self.launches += 1
+
+    def upsample2x(self, x, y):
+        assert self._rec is None
+        v = torch.from_numpy(self._v4(x).copy()).permute(0, 3, 1, 2)
+        self._v4(y)[:] = F.interpolate(v, scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1).numpy()
+        self.launches += 1
+
     # ---- ProPainter image propagation (P5)
     def upload_bytes(self, arr):
         arr = np.ascontiguousarray(arr)

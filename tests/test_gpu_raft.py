@@ -52,3 +52,28 @@ def test_image_propagation_vs_oracle(capi):
     prop, want_m = P.img_propagation(x * (1 - masks), torch.from_numpy(ff)[None], torch.from_numpy(fb)[None], masks)
     want = P.updated_frames(x, masks, prop)[0].numpy()
     assert (um != want_m[0].numpy()).mean() < 1e-4 and np.abs(upd - want).max() < 2e-3
+
+
+def test_flow_completion_vs_oracle(capi):
+    """P4 on the device (gated).  Tolerance to establish: completed flows within 0.1 px of the oracle inside the hole."""
+    import sys
+
+    from conftest import GOLDEN
+    from oracle import propainter_oracle as P
+    from oracle import rfc_oracle as C
+
+    path = os.path.join(ROOT, "weights", "propainter", "recurrent_flow_completion.pth")
+    if not os.path.exists(path):
+        pytest.skip("recurrent_flow_completion.pth not staged")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_propainter import inputs
+    from vsr_b200.flow_completion import FlowCompletion
+
+    z = np.load(os.path.join(GOLDEN, "propainter_real.npz"))
+    frames, mask = inputs()[:2]
+    fm, _ = P.read_mask(mask, len(frames))
+    gf, gb = z["gt_flows_f"][0].astype(np.float32), z["gt_flows_b"][0].astype(np.float32)
+    pf, pb = FlowCompletion(path, "cuda:0").complete_host(gf, gb, fm[0])
+    masks = torch.from_numpy(np.stack(fm).astype(np.float32) / 255)[None, :, None]
+    wf, wb = C.complete_bidirectional(C.load_weights(path), torch.from_numpy(gf)[None], torch.from_numpy(gb)[None], masks)
+    assert np.abs(pf - wf[0].numpy()).max() < 0.1 and np.abs(pb - wb[0].numpy()).max() < 0.1

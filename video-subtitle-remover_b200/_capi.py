@@ -109,6 +109,14 @@ _PROTOS = {
     "vsr_rt_convex_upsample": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_img_prop_step": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_prop_state": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_rfc_input": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_pad_replicate": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vsr_rt_leaky_relu": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_float]),
+    "vsr_rt_temporal_taps": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int64, C.c_int, C.c_uint64, C.c_int]),
+    "vsr_rt_deform_cols": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_float, C.c_uint64,
+                                     C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_int]),
+    "vsr_rt_rfc_combine": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_upsample2x_bilinear": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_residual_add": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int]),
     "vsr_rt_fft_r2c": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_fft_c2r": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),

@@ -1922,6 +1922,87 @@ int vsr_rt_prop_state(vsr_rt_t* h, uint64_t frames, uint64_t mask_u8, uint64_t p
   });
 }
 
+int vsr_rt_rfc_input(vsr_rt_t* h, uint64_t flow32, uint64_t mask_u8, int N, int H, int W, int reverse, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(flow32 && mask_u8 && out && N > 0 && H > 0 && W > 0, "bad arguments");
+    const size_t plane = (size_t)H * W;
+    pp_rfc_input_kernel<<<blocks_for(plane * N), 256, 0, h->ctx.stream>>>((const float*)(uintptr_t)flow32, (const uint8_t*)(uintptr_t)mask_u8, N, plane, reverse,
+                                                                        (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_pad_replicate(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(in && out && cp % 8 == 0 && OH > 0 && OW > 0, "bad arguments");
+    const size_t n = (size_t)T * OH * OW * (cp / 8);
+    pp_pad_replicate_kernel<<<blocks_for(n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, T, H, W, cp, (__half*)(uintptr_t)out, OH, OW, top, left);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_leaky_relu(vsr_rt_t* h, uint64_t x, int64_t n_elems, float slope) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(x && n_elems > 0 && n_elems % 8 == 0, "bad arguments");
+    pp_leaky_relu_kernel<<<blocks_for((size_t)n_elems / 8), 256, 0, h->ctx.stream>>>((__half*)(uintptr_t)x, (size_t)n_elems / 8, slope);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_temporal_taps(vsr_rt_t* h, uint64_t in, int T, int64_t pixels, int cp_in, uint64_t out, int cp_out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(in && out && T > 0 && pixels > 0 && cp_in % 8 == 0 && cp_out >= 3 * cp_in && cp_out % 8 == 0, "bad arguments");
+    const size_t n = (size_t)T * pixels * 3 * (cp_in / 8);
+    pp_temporal_taps_kernel<<<blocks_for(n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, T, (size_t)pixels, cp_in, (__half*)(uintptr_t)out, cp_out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_deform_cols(vsr_rt_t* h, uint64_t xa, int pitch_a, int Ca, uint64_t xb, int pitch_b, int C, int G, uint64_t om, int pitch_om, float max_residue,
+                       uint64_t flow32, int H, int W, int64_t pixels, uint64_t cols, int pitch_cols) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(xa && om && cols && C > 0 && G > 0 && C % G == 0 && Ca > 0 && Ca <= C && (Ca == C || xb) && pitch_om >= 27 * G && pitch_cols >= 9 * C && pixels > 0,
+            "bad arguments");
+    pp_deform_cols_kernel<<<blocks_for((size_t)pixels * G * 9), 256, 0, h->ctx.stream>>>(
+        (const __half*)(uintptr_t)xa, pitch_a, Ca, (const __half*)(uintptr_t)xb, pitch_b, C, G, (const __half*)(uintptr_t)om, pitch_om, max_residue,
+        (const float*)(uintptr_t)flow32, H, W, (size_t)pixels, (__half*)(uintptr_t)cols, pitch_cols);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_rfc_combine(vsr_rt_t* h, uint64_t pred, int pitch_pred, uint64_t flow32, uint64_t mask_u8, int N, int H, int W, int reverse, uint64_t out32) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(pred && flow32 && mask_u8 && out32 && N > 0 && H > 0 && W > 0, "bad arguments");
+    const size_t plane = (size_t)H * W;
+    pp_rfc_combine_kernel<<<blocks_for(plane * N), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)pred, pitch_pred, (const float*)(uintptr_t)flow32,
+                                                                          (const uint8_t*)(uintptr_t)mask_u8, N, plane, reverse, (float*)(uintptr_t)out32);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_upsample2x_bilinear(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(in && out && T > 0 && H > 1 && W > 1 && cp % 8 == 0, "bad arguments");
+    const size_t n = (size_t)T * 4 * H * W * (cp / 8);
+    upsample2x_kernel<<<blocks_for(n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, T, H, W, cp, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
 int vsr_rt_residual_add(vsr_rt_t* h, uint64_t x32, uint64_t y16, uint64_t x16, int64_t n_elems, int init) {
   return guarded([&] {
     rt_check(h);

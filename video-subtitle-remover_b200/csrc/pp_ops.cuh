@@ -330,4 +330,127 @@ __global__ void __launch_bounds__(256) pp_state_compose_kernel(const __half* __r
   *reinterpret_cast<uint4*>(out + i * 8) = f;
 }
 
+// ---- P4: RecurrentFlowCompleteNet (video/model/recurrent_flow_completion.py) ----------------------------------------------------
+// network input (:305-317): per frame [fx * (1 - m), fy * (1 - m), m] from planar fp32 flows [N][2][H][W] and one u8 mask [H][W];
+// reverse != 0 reads the flows in reversed time order (the backward direction runs the same network on the flipped sequence)
+__global__ void __launch_bounds__(256) pp_rfc_input_kernel(const float* __restrict__ flow, const uint8_t* __restrict__ mask, int N, size_t plane, int reverse,
+                                                           __half* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * plane) return;
+  const size_t n = i / plane, p = i % plane;
+  const float* f = flow + (size_t)(reverse ? N - 1 - n : n) * 2 * plane;
+  const float m = mask[p] > 0 ? 1.f : 0.f;
+  __align__(16) __half o[8];
+  o[0] = __float2half_rn(f[p] * (1.f - m));
+  o[1] = __float2half_rn(f[plane + p] * (1.f - m));
+  o[2] = __float2half_rn(m);
+#pragma unroll
+  for (int c = 3; c < 8; ++c) o[c] = __float2half_rn(0.f);
+  *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// padding_mode='replicate' of the first Conv3d (:213-214): out[OH][OW] = in[clamp(y - top)][clamp(x - left)], 8 channels per thread
+__global__ void __launch_bounds__(256) pp_pad_replicate_kernel(const __half* __restrict__ in, int T, int H, int W, int cp, __half* __restrict__ out, int OH, int OW,
+                                                               int top, int left) {
+  const int c8n = cp >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)T * OH * OW * c8n) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int ox = r % OW;
+  r /= OW;
+  const int oy = r % OH;
+  const int t = r / OH;
+  const int y = min(max(oy - top, 0), H - 1), x = min(max(ox - left, 0), W - 1);
+  *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(in + (((size_t)t * H + y) * W + x) * cp + c8 * 8);
+}
+
+// LeakyReLU(slope) in place over a whole tensor
+__global__ void __launch_bounds__(256) pp_leaky_relu_kernel(__half* __restrict__ x, size_t n8, float slope) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  uint4 v = reinterpret_cast<uint4*>(x)[i];
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __half22float2(h[j]);
+    f.x = f.x > 0.f ? f.x : f.x * slope;
+    f.y = f.y > 0.f ? f.y : f.y * slope;
+    h[j] = __floats2half2_rn(f.x, f.y);
+  }
+  reinterpret_cast<uint4*>(x)[i] = v;
+}
+
+// temporal taps of P3DBlock.conv2 (Conv3d (3,1,1), dilation (2,1,1), padding (2,0,0), :164-165): out[t][p][k*C + c] = in[t + 2(k-1)][p][c], zero
+// outside the clip; the 1x1 conv that follows is the temporal conv.  C = cp_in (multiple of 8), out pitch >= 3*C.
+__global__ void __launch_bounds__(256) pp_temporal_taps_kernel(const __half* __restrict__ in, int T, size_t pixels, int cp_in, __half* __restrict__ out, int cp_out) {
+  const int c8n = cp_in >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)T * pixels * 3 * c8n) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int k = r % 3;
+  r /= 3;
+  const size_t p = r % pixels;
+  const int t = (int)(r / pixels);
+  const int ts = t + 2 * (k - 1);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (ts >= 0 && ts < T) v = *reinterpret_cast<const uint4*>(in + ((size_t)ts * pixels + p) * cp_in + c8 * 8);
+  *reinterpret_cast<uint4*>(out + ((size_t)t * pixels + p) * cp_out + (size_t)k * cp_in + c8 * 8) = v;
+}
+
+// modulated deformable 3x3 conv, pad 1, stride 1 (torchvision.ops.deform_conv2d as called at :44-46 / propainter.py:69-72), gather half:
+// cols[p][k*C + c] = sigmoid(om[p][2*G*9 + g*9 + k]) * bilinear(x[:, c])(y - 1 + ky + dy, x - 1 + kx + dx), g = c / (C / G),
+// (dy, dx) = max_res * tanh(om[p][2*(g*9+k) + {0,1}]) (+ (flow.y, flow.x) when flow != nullptr, propainter.py:64).  x = [xa | xb] channel-wise
+// (two sources of Ca and C - Ca channels; xb may be nullptr when Ca == C).  The 1x1 conv over cols (K = 9*C) is the rest of the operator.
+__global__ void __launch_bounds__(256) pp_deform_cols_kernel(const __half* __restrict__ xa, int pa, int Ca, const __half* __restrict__ xb, int pb, int C, int G,
+                                                             const __half* __restrict__ om, int pom, float max_res, const float* __restrict__ flow, int H, int W,
+                                                             size_t pixels, __half* __restrict__ cols, int pcols) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups_k = G * 9;
+  if (idx >= pixels * groups_k) return;
+  const int gk = idx % groups_k;
+  const size_t p = idx / groups_k;
+  const int g = gk / 9, k = gk - g * 9, ky = k / 3, kx = k - ky * 3;
+  const int px = (int)(p % W), py = (int)((p / W) % H);
+  const size_t img = p / ((size_t)W * H) * ((size_t)W * H);
+  const __half* o = om + p * pom;
+  float dy = max_res * tanhf(__half2float(o[2 * gk])), dx = max_res * tanhf(__half2float(o[2 * gk + 1]));
+  if (flow) { dy += flow[p * 2 + 1]; dx += flow[p * 2]; }
+  const float m = 1.f / (1.f + __expf(-__half2float(o[2 * groups_k + gk])));
+  const float sy = (float)(py - 1 + ky) + dy, sx = (float)(px - 1 + kx) + dx;
+  const float fy = floorf(sy), fx = floorf(sx);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const float ay = sy - fy, ax = sx - fx;
+  const float w00 = (1.f - ay) * (1.f - ax) * m, w01 = (1.f - ay) * ax * m, w10 = ay * (1.f - ax) * m, w11 = ay * ax * m;
+  const bool v00 = y0 >= 0 && y0 < H && x0 >= 0 && x0 < W, v01 = y0 >= 0 && y0 < H && x0 + 1 >= 0 && x0 + 1 < W;
+  const bool v10 = y0 + 1 >= 0 && y0 + 1 < H && x0 >= 0 && x0 < W, v11 = y0 + 1 >= 0 && y0 + 1 < H && x0 + 1 >= 0 && x0 + 1 < W;
+  const int cpg = C / G;
+  for (int cc = 0; cc < cpg; ++cc) {
+    const int c = g * cpg + cc;
+    const __half* src = c < Ca ? xa + c : xb + (c - Ca);
+    const int pitch = c < Ca ? pa : pb;
+    float v = 0.f;
+    if (v00) v += w00 * __half2float(src[(img + (size_t)y0 * W + x0) * pitch]);
+    if (v01) v += w01 * __half2float(src[(img + (size_t)y0 * W + x0 + 1) * pitch]);
+    if (v10) v += w10 * __half2float(src[(img + (size_t)(y0 + 1) * W + x0) * pitch]);
+    if (v11) v += w11 * __half2float(src[(img + (size_t)(y0 + 1) * W + x0 + 1) * pitch]);
+    cols[p * pcols + (size_t)k * C + c] = __float2half_rn(v);
+  }
+}
+
+// combine_flow (:338-348): out[n] = pred[n'] * m + flow[n] * (1 - m), planar fp32; reverse: the network ran on the flipped sequence (n' = N-1-n)
+__global__ void __launch_bounds__(256) pp_rfc_combine_kernel(const __half* __restrict__ pred, int pp, const float* __restrict__ flow, const uint8_t* __restrict__ mask,
+                                                             int N, size_t plane, int reverse, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * plane) return;
+  const size_t n = i / plane, p = i % plane;
+  const __half* q = pred + ((size_t)(reverse ? N - 1 - n : n) * plane + p) * pp;
+  const float m = mask[p] > 0 ? 1.f : 0.f;
+  const float* f = flow + n * 2 * plane;
+  float* o = out + n * 2 * plane;
+  o[p] = __half2float(q[0]) * m + f[p] * (1.f - m);
+  o[plane + p] = __half2float(q[1]) * m + f[plane + p] * (1.f - m);
+}
+
 }  // namespace vsr

@@ -32,17 +32,44 @@ class _PropRuntime(_RaftRuntime):
         return p
 
 
+class _Arena:
+    """Replays the allocation sequence of an eager graph: the first call with a key allocates, later calls with the same key get the
+    same buffers back in the same order (the runtime frees nothing before it is destroyed, and zero-initialises only fresh buffers —
+    every launch sequence here rewrites exactly the regions it wrote the first time)."""
+
+    def __init__(self, rt):
+        self.rt, self.seqs, self.cur, self.i = rt, {}, None, 0
+
+    def begin(self, key):
+        self.cur, self.i = self.seqs.setdefault(key, []), 0
+
+    def alloc(self, nbytes: int) -> int:
+        if self.i < len(self.cur):
+            size, ptr = self.cur[self.i]
+            if size != nbytes:
+                raise _capi.VsrError("allocation sequence changed between calls with the same shape key")
+        else:
+            ptr = self.rt.alloc(nbytes)
+            self.cur.append((nbytes, ptr))
+        self.i += 1
+        return ptr
+
+
 def _image(t: _Tensor, k: int) -> _Tensor:
     """image k of a [n,h,w,cp] tensor as a 1-image tensor"""
     return _Tensor(t.ptr + k * t.h * t.w * t.cp * 2, t.c, t.h, t.w, t.cp, n=1)
 
 
-def propagate_images(rt, frames: _Tensor, mask_u8: int, flows_f: int, flows_b: int) -> _Tensor:
+def propagate_images(rt, frames: _Tensor, mask_u8: int, flows_f: int, flows_b: int, arena: "_Arena" = None) -> _Tensor:
     """frames: fp16 [T,H,W,8] RGB in [-1,1] (vsr_rt_pp_frames); mask_u8: device u8 [H,W] (the dilated mask, > 0 = hole);
     flows_f / flows_b: device fp32 [T-1,2,H,W] (completed flows t -> t+1 and t+1 -> t).
     Returns the state tensor [T,H,W,8]: channels 0..2 = frame*(1-m) + propagated*m (`updated_frames`), channel 3 = `updated_masks`."""
     T, H, W = frames.n, frames.h, frames.w
-    new = lambda: _Tensor(rt.alloc(T * H * W * 8 * 2), 4, H, W, 8, n=T)   # noqa: E731
+    alloc = rt.alloc
+    if arena is not None:
+        arena.begin(("prop", T, H, W))
+        alloc = arena.alloc
+    new = lambda: _Tensor(alloc(T * H * W * 8 * 2), 4, H, W, 8, n=T)   # noqa: E731
     s0, sb, sf, out = new(), new(), new(), new()
     fl = lambda base, i: base + i * 2 * H * W * 4                         # noqa: E731
     rt.prop_state(frames, mask_u8, None, s0)
