@@ -186,6 +186,14 @@ int vsr_rt_deform_cols(vsr_rt_t* h, uint64_t xa, int pitch_a, int Ca, uint64_t x
                        uint64_t flow32, int H, int W, int64_t pixels, uint64_t cols, int pitch_cols);
 int vsr_rt_rfc_combine(vsr_rt_t* h, uint64_t pred, int pitch_pred, uint64_t flow32, uint64_t mask_u8, int N, int H, int W, int reverse, uint64_t out32);
 int vsr_rt_upsample2x_bilinear(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out);   /* F.interpolate(x2, bilinear, align_corners=True) */
+/* ---- ProPainter generator, front half (propainter.py:321-378: encoder input, 1/4 flows and masks, the condition tensor of
+ * the learnable feature propagation).  STATUS: checked against the CPU stand-in only. */
+int vsr_rt_gen_input(vsr_rt_t* h, uint64_t state, uint64_t mask_u8, uint64_t ids_dev, int n, int H, int W, uint64_t out);       /* [rgb, m_in, m_updated] */
+int vsr_rt_flow_down4(vsr_rt_t* h, uint64_t flow32, uint64_t ids_dev, int n, int H, int W, uint64_t out32);                       /* -> fp32 [n*h*w][2] */
+int vsr_rt_prop_masks(vsr_rt_t* h, uint64_t gen_in, int n, int H, int W, uint64_t out);                                           /* -> fp16 [n*h*w][8] (m_in, m_upd) */
+int vsr_rt_featprop_cond(vsr_rt_t* h, uint64_t prop, uint64_t cur, int C, uint64_t flow_prop, uint64_t flow_check, uint64_t masks, int H, int W, uint64_t cond,
+                         int pitch);
+int vsr_rt_write_extra(vsr_rt_t* h, uint64_t src, uint64_t dst, int pitch, int coff, int nch, int64_t pixels);
 /* ---- LAMA: what the TorchScript big-lama forward needs beyond the detector's operators ---- */
 /* out[OH,OW] = in[H,W] shifted by (top, left), reflected at the borders (reflect = 1) or zero filled (0) */
 int vsr_rt_pad(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left, int reflect);

@@ -183,13 +183,18 @@ def _up(w, p, x):
     return _c2(w, f"{p}.conv", F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True))
 
 
-def generator(w, masked_frames, flows_f, flows_b, masks_in, masks_updated, l_t):
-    """InpaintGenerator.forward in eval mode -> [b, l_t, 3, H, W] in [-1, 1]."""
+def generator(w, masked_frames, flows_f, flows_b, masks_in, masks_updated, l_t, taps: dict | None = None):
+    """InpaintGenerator.forward in eval mode -> [b, l_t, 3, H, W] in [-1, 1].  `taps` receives stage outputs (device bring-up)."""
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t.clone()
+
     with torch.no_grad():
         b, t, _, H, W = masked_frames.shape
         enc = encoder(w, torch.cat((masked_frames.view(b * t, 3, H, W), masks_in.view(b * t, 1, H, W), masks_updated.view(b * t, 1, H, W)), 1))
         c, h, wd = enc.shape[1:]
         enc = enc.view(b, t, c, h, wd)
+        tap("enc", enc)
         ds_f = F.interpolate(flows_f.reshape(-1, 2, H, W), scale_factor=1 / 4, mode="bilinear", align_corners=False).view(b, l_t - 1, 2, h, wd) / 4.0
         ds_b = F.interpolate(flows_b.reshape(-1, 2, H, W), scale_factor=1 / 4, mode="bilinear", align_corners=False).view(b, l_t - 1, 2, h, wd) / 4.0
         ds_in = F.interpolate(masks_in.reshape(-1, 1, H, W), scale_factor=1 / 4, mode="nearest").view(b, t, 1, h, wd)
@@ -198,12 +203,18 @@ def generator(w, masked_frames, flows_f, flows_b, masks_in, masks_updated, l_t):
         pool = pool.view(b, l_t, 1, pool.shape[-2], pool.shape[-1]).permute(0, 1, 3, 4, 2).contiguous()
         local = feature_propagation(w, enc[:, :l_t], ds_f, ds_b, torch.cat((ds_in[:, :l_t], ds_up), 2))
         enc = torch.cat((local, enc[:, l_t:]), 1)
+        tap("ds_flows_f", ds_f)
+        tap("pool_mask", pool)
+        tap("enc_prop", enc)
         tok = F.unfold(enc.view(-1, c, h, wd), **T2T).permute(0, 2, 1)
         tok = _lin(w, "ss.embedding", tok).view(b, -1, pool.shape[2], pool.shape[3], 512)
+        tap("tokens_in", tok)
         tok = transformer(w, tok, (h, wd), pool)
+        tap("tokens_out", tok)
         z = _lin(w, "sc.embedding", tok.view(b, -1, 512))
         z = F.fold(z.view(b * t, -1, z.shape[-1]).permute(0, 2, 1), (h, wd), **T2T)
         enc = enc + _c2(w, "sc.bias_conv", z).view(b, t, c, h, wd)
+        tap("enc_trans", enc)
         y = enc[:, :l_t].reshape(-1, c, h, wd)
         y = F.leaky_relu(_up(w, "decoder.0", y), 0.2)
         y = F.leaky_relu(_c2(w, "decoder.2", y), 0.2)

@@ -354,7 +354,7 @@ class FakeRuntime:
         gk = groups * 9
         off = max_residue * np.tanh(o[..., : 2 * gk]).reshape(n, H, W, gk, 2)
         if flow32:
-            fl = self.bufs[flow32][: n * H * W * 2].reshape(n, H, W, 1, 2)
+            fl = self._flow_at(flow32, n * H, W).reshape(n, H, W, 1, 2)
             off = off + fl[..., ::-1]                                                            # (dy, dx) += (flow.y, flow.x)
         msk = 1 / (1 + np.exp(-o[..., 2 * gk: 3 * gk]))
         ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
@@ -395,6 +395,77 @@ class FakeRuntime:
         assert self._rec is None
         v = torch.from_numpy(self._v4(x).copy()).permute(0, 3, 1, 2)
         self._v4(y)[:] = F.interpolate(v, scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1).numpy()
+        self.launches += 1
+
+    # ---- ProPainter generator, front half (P6): transcriptions of the pp_ops.cuh kernels
+    def gen_input(self, state, mask_u8, ids_dev, n, out):
+        assert self._rec is None
+        ids = self.bufs[ids_dev][:n].astype(np.int64)
+        st = self._v4(state)
+        m = (self.bufs[mask_u8][: state.h * state.w].reshape(state.h, state.w) > 0).astype(np.float32)
+        o = self._v4(out)
+        o[:] = 0
+        o[..., :3] = st[ids][..., :3]
+        o[..., 3] = m
+        o[..., 4] = st[ids][..., 3]
+        self.launches += 1
+
+    def flow_down4(self, flow32, ids_dev, n, hh, ww, out32):
+        assert self._rec is None
+        ids = self.bufs[ids_dev][:n].astype(np.int64)
+        total = int(ids.max()) + 1
+        f = self._raw32(flow32, total * 2 * hh * ww).reshape(total, 2, hh, ww)[ids]
+        blk = (f[:, :, 1::4, 1::4] + f[:, :, 1::4, 2::4] + f[:, :, 2::4, 1::4] + f[:, :, 2::4, 2::4]) * 0.25 * 0.25
+        res = blk.transpose(0, 2, 3, 1).reshape(-1)
+        self.bufs[out32][: res.size] = res            # alloc()-ed fp32 buffer used contiguously ([P][2])
+        self.launches += 1
+
+    def prop_masks(self, gen_in, out):
+        assert self._rec is None
+        g = self._v4(gen_in)
+        o = self._v4(out)
+        o[:] = 0
+        o[..., 0], o[..., 1] = g[:, ::4, ::4, 3], g[:, ::4, ::4, 4]
+        self.launches += 1
+
+    def _flow_at(self, ptr, hh, ww):
+        """fp32 [P][2] flow stored contiguously in an alloc()-ed buffer, addressed with byte offsets (4 bytes = 2 slots per float)"""
+        arr, off = self._resolve(ptr)
+        assert off % 2 == 0
+        return arr[off // 2: off // 2 + hh * ww * 2].reshape(hh, ww, 2)
+
+    def featprop_cond(self, prop, cur, flow_prop, flow_check, masks, cond):
+        assert self._rec is None
+        H, W, C = cur.h, cur.w, cur.cp
+        fp, fc = self._flow_at(flow_prop, H, W), self._flow_at(flow_check, H, W)
+        pv, cv, mk = self._v4(prop)[0], self._v4(cur)[0], self._v4(masks)[0]
+        ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+        sx, sy = xs + fp[..., 0], ys + fp[..., 1]
+        x0, y0 = np.floor(sx), np.floor(sy)
+        ax, ay = sx - x0, sy - y0
+        x0, y0 = x0.astype(np.int64), y0.astype(np.int64)
+        warped = np.zeros((H, W, C), np.float32)
+        b = np.zeros((H, W, 2), np.float32)
+        for dy, wy in ((0, 1 - ay), (1, ay)):
+            for dx, wx in ((0, 1 - ax), (1, ax)):
+                yy, xx = y0 + dy, x0 + dx
+                ok = ((yy >= 0) & (yy < H) & (xx >= 0) & (xx < W))[..., None]
+                wgt = (wy * wx)[..., None]
+                warped += np.where(ok, pv[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], 0) * wgt
+                b += np.where(ok, fc[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], 0) * wgt
+        d = fp + b
+        valid = (d ** 2).sum(-1) < 0.01 * ((fp ** 2).sum(-1) + (b ** 2).sum(-1)) + 0.5
+        o = self._v4(cond)[0]
+        o[..., :C] = cv
+        o[..., C:2 * C] = warped
+        o[..., 2 * C:2 * C + 2] = fp
+        o[..., 2 * C + 2] = valid
+        o[..., 2 * C + 3:2 * C + 5] = mk[..., :2]
+        self.launches += 1
+
+    def write_extra(self, src, dst, coff, nch):
+        assert self._rec is None
+        self._v4(dst)[..., coff:coff + nch] = self._v4(src)[..., :nch]
         self.launches += 1
 
     # ---- ProPainter image propagation (P5)

@@ -117,6 +117,11 @@ _PROTOS = {
                                      C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_int]),
     "vsr_rt_rfc_combine": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_upsample2x_bilinear": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_gen_input": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_flow_down4": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_prop_masks": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_featprop_cond": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "vsr_rt_write_extra": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int64]),
     "vsr_rt_residual_add": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int]),
     "vsr_rt_fft_r2c": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_fft_c2r": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),

@@ -2003,6 +2003,63 @@ int vsr_rt_upsample2x_bilinear(vsr_rt_t* h, uint64_t in, int T, int H, int W, in
   });
 }
 
+int vsr_rt_gen_input(vsr_rt_t* h, uint64_t state, uint64_t mask_u8, uint64_t ids_dev, int n, int H, int W, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(state && mask_u8 && ids_dev && out && n > 0 && H > 0 && W > 0, "bad arguments");
+    const size_t plane = (size_t)H * W;
+    pp_gen_input_kernel<<<blocks_for(plane * n), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)state, (const uint8_t*)(uintptr_t)mask_u8,
+                                                                        (const int*)(uintptr_t)ids_dev, n, plane, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_flow_down4(vsr_rt_t* h, uint64_t flow32, uint64_t ids_dev, int n, int H, int W, uint64_t out32) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(flow32 && ids_dev && out32 && n > 0 && H % 4 == 0 && W % 4 == 0, "bad arguments");
+    pp_flow_down4_kernel<<<blocks_for((size_t)n * (H / 4) * (W / 4)), 256, 0, h->ctx.stream>>>((const float*)(uintptr_t)flow32, (const int*)(uintptr_t)ids_dev, n,
+                                                                                             H, W, (float*)(uintptr_t)out32);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_prop_masks(vsr_rt_t* h, uint64_t gen_in, int n, int H, int W, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(gen_in && out && n > 0 && H % 4 == 0 && W % 4 == 0, "bad arguments");
+    pp_prop_masks_kernel<<<blocks_for((size_t)n * (H / 4) * (W / 4)), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)gen_in, n, H, W, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_featprop_cond(vsr_rt_t* h, uint64_t prop, uint64_t cur, int C, uint64_t flow_prop, uint64_t flow_check, uint64_t masks, int H, int W, uint64_t cond,
+                         int pitch) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(prop && cur && flow_prop && flow_check && masks && cond && C % 8 == 0 && pitch >= 2 * C + 5, "bad arguments");
+    pp_featprop_cond_kernel<<<blocks_for((size_t)H * W * (C / 8)), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)prop, (const __half*)(uintptr_t)cur, C,
+                                                                                          (const float*)(uintptr_t)flow_prop, (const float*)(uintptr_t)flow_check,
+                                                                                          (const __half*)(uintptr_t)masks, H, W, (__half*)(uintptr_t)cond, pitch);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_write_extra(vsr_rt_t* h, uint64_t src, uint64_t dst, int pitch, int coff, int nch, int64_t pixels) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(src && dst && nch > 0 && nch <= 8 && coff >= 0 && coff + nch <= pitch && pixels > 0, "bad arguments");
+    pp_write_extra_kernel<<<blocks_for((size_t)pixels), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)src, (__half*)(uintptr_t)dst, pitch, coff, nch,
+                                                                               (size_t)pixels);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
 int vsr_rt_residual_add(vsr_rt_t* h, uint64_t x32, uint64_t y16, uint64_t x16, int64_t n_elems, int init) {
   return guarded([&] {
     rt_check(h);

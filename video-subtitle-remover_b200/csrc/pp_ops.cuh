@@ -439,6 +439,116 @@ __global__ void __launch_bounds__(256) pp_deform_cols_kernel(const __half* __res
   }
 }
 
+// ---- P6: InpaintGenerator.forward (video/model/propainter.py:321-378), front half ---------------------------------------------------
+// encoder input (:333-335): frame ids[i] of the propagation state [T][H][W][8] (rgb | updated mask) + the dilated input mask ->
+// [rgb, m_in, m_updated, 0, 0, 0] fp16 [n][H][W][8]
+__global__ void __launch_bounds__(256) pp_gen_input_kernel(const __half* __restrict__ state, const uint8_t* __restrict__ mask, const int* __restrict__ ids, int n,
+                                                           size_t plane, __half* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * plane) return;
+  const size_t k = i / plane, p = i % plane;
+  uint4 v = *reinterpret_cast<const uint4*>(state + ((size_t)ids[k] * plane + p) * 8);
+  __half* h = reinterpret_cast<__half*>(&v);
+  h[4] = h[3];
+  h[3] = __float2half_rn(mask[p] > 0 ? 1.f : 0.f);
+  h[5] = h[6] = h[7] = __float2half_rn(0.f);
+  *reinterpret_cast<uint4*>(out + i * 8) = v;
+}
+
+// F.interpolate(flow, scale_factor=1/4, mode='bilinear', align_corners=False) / 4 (:341-344): the sample point of output (y, x) is
+// (4y + 1.5, 4x + 1.5), i.e. the mean of the 2x2 block at (4y+1, 4x+1).  in planar fp32 [n][2][H][W] (frame ids[i]) -> out fp32 [n*h*w][2]
+__global__ void __launch_bounds__(256) pp_flow_down4_kernel(const float* __restrict__ flow, const int* __restrict__ ids, int n, int H, int W,
+                                                            float* __restrict__ out) {
+  const int h = H / 4, w = W / 4;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * h * w) return;
+  const int x = i % w, y = (i / w) % h;
+  const size_t k = i / ((size_t)w * h);
+  const float* f = flow + (size_t)ids[k] * 2 * H * W;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float* q = f + (size_t)c * H * W + (size_t)(4 * y + 1) * W + 4 * x + 1;
+    out[i * 2 + c] = (q[0] + q[1] + q[W] + q[W + 1]) * 0.25f * 0.25f;
+  }
+}
+
+// prop_mask_in (:345-359): nearest 1/4 down-sampling (source pixel (4y, 4x)) of the input mask and of the frames' updated masks
+// (channel 4 of the generator input) -> fp16 [n*h*w][8] with channels (m_in, m_updated)
+__global__ void __launch_bounds__(256) pp_prop_masks_kernel(const __half* __restrict__ gen_in, int n, int H, int W, __half* __restrict__ out) {
+  const int h = H / 4, w = W / 4;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * h * w) return;
+  const int x = i % w, y = (i / w) % h;
+  const size_t k = i / ((size_t)w * h);
+  const __half* s = gen_in + ((k * H + (size_t)4 * y) * W + (size_t)4 * x) * 8;
+  __align__(16) __half o[8] = {s[3], s[4], __half(), __half(), __half(), __half(), __half(), __half()};
+  *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// condition tensor of the learnable feature propagation (:160-167): [cur (C), bilinear warp of prop by flow_prop (C), flow_prop (2), valid (1),
+// masks of the current frame (2)] -> cond [P][pitch]; flows fp32 [P][2] at feature resolution; valid as in fbConsistencyCheck.  One thread =
+// (pixel, 8 channels of the warp); the scalars ride on the first thread of a pixel.
+__global__ void __launch_bounds__(256) pp_featprop_cond_kernel(const __half* __restrict__ prop, const __half* __restrict__ cur, int C, const float* __restrict__ fprop,
+                                                               const float* __restrict__ fcheck, const __half* __restrict__ masks, int H, int W,
+                                                               __half* __restrict__ cond, int pitch) {
+  const int c8n = C >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)H * W * c8n) return;
+  const int c8 = idx % c8n;
+  const size_t p = idx / c8n;
+  const int x = (int)(p % W), y = (int)(p / W);
+  const float fx = fprop[p * 2], fy = fprop[p * 2 + 1];
+  const float sx = (float)x + fx, sy = (float)y + fy;
+  const float gx = floorf(sx), gy = floorf(sy);
+  const int x0 = (int)gx, y0 = (int)gy;
+  const float ax = sx - gx, ay = sy - gy;
+  const float wgt[4] = {(1.f - ax) * (1.f - ay), ax * (1.f - ay), (1.f - ax) * ay, ax * ay};
+  const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (xs[k] < 0 || xs[k] >= W || ys[k] < 0 || ys[k] >= H) continue;
+    const uint4 v = *reinterpret_cast<const uint4*>(prop + ((size_t)ys[k] * W + xs[k]) * C + c8 * 8);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      acc[2 * j] += wgt[k] * f.x;
+      acc[2 * j + 1] += wgt[k] * f.y;
+    }
+  }
+  __half* o = cond + p * pitch;
+  *reinterpret_cast<uint4*>(o + c8 * 8) = *reinterpret_cast<const uint4*>(cur + p * C + c8 * 8);
+  __align__(16) __half2 wv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wv[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+  *reinterpret_cast<uint4*>(o + C + c8 * 8) = *reinterpret_cast<const uint4*>(wv);
+  if (c8 == 0) {
+    float b[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (xs[k] < 0 || xs[k] >= W || ys[k] < 0 || ys[k] >= H) continue;
+      const float* q = fcheck + ((size_t)ys[k] * W + xs[k]) * 2;
+      b[0] += wgt[k] * q[0];
+      b[1] += wgt[k] * q[1];
+    }
+    const float dx = fx + b[0], dy = fy + b[1];
+    const bool valid = dx * dx + dy * dy < 0.01f * (fx * fx + fy * fy + b[0] * b[0] + b[1] * b[1]) + 0.5f;
+    o[2 * C] = __float2half_rn(fx);
+    o[2 * C + 1] = __float2half_rn(fy);
+    o[2 * C + 2] = __float2half_rn(valid ? 1.f : 0.f);
+    o[2 * C + 3] = masks[p * 8];
+    o[2 * C + 4] = masks[p * 8 + 1];
+  }
+}
+
+// dst[p][coff .. coff+nch) = src[p][0 .. nch) for an 8-channel fp16 source (the 2 mask channels behind a feature concat)
+__global__ void __launch_bounds__(256) pp_write_extra_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int pitch, int coff, int nch, size_t pixels) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+  for (int c = 0; c < nch; ++c) dst[p * pitch + coff + c] = src[p * 8 + c];
+}
+
 // combine_flow (:338-348): out[n] = pred[n'] * m + flow[n] * (1 - m), planar fp32; reverse: the network ran on the flipped sequence (n' = N-1-n)
 __global__ void __launch_bounds__(256) pp_rfc_combine_kernel(const __half* __restrict__ pred, int pp, const float* __restrict__ flow, const uint8_t* __restrict__ mask,
                                                              int N, size_t plane, int reverse, float* __restrict__ out) {
