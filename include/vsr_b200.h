@@ -194,6 +194,15 @@ int vsr_rt_prop_masks(vsr_rt_t* h, uint64_t gen_in, int n, int H, int W, uint64_
 int vsr_rt_featprop_cond(vsr_rt_t* h, uint64_t prop, uint64_t cur, int C, uint64_t flow_prop, uint64_t flow_check, uint64_t masks, int H, int W, uint64_t cond,
                          int pitch);
 int vsr_rt_write_extra(vsr_rt_t* h, uint64_t src, uint64_t dst, int pitch, int coff, int nch, int64_t pixels);
+/* ---- ProPainter generator, back half (sparse_transformer.py): soft split / composition, layer norm, pooled tokens, the sparse window
+ * attention core, the u8 conversion of the decoder output.  STATUS: checked against the CPU stand-in only. */
+int vsr_rt_unfold7s3(vsr_rt_t* h, uint64_t in, int n, int hh, int ww, int C, uint64_t out, int pitch, int gelu);       /* nn.Unfold(7,3,3), tap-major */
+int vsr_rt_fold7s3(vsr_rt_t* h, uint64_t tok, int n, int hh, int ww, int C, int pitch, int normalise, uint64_t out);   /* F.fold(7,3,3) [/ overlap count] */
+int vsr_rt_layernorm(vsr_rt_t* h, uint64_t x, int64_t tokens, int C, uint64_t gamma_dev, uint64_t beta_dev, uint64_t out);
+int vsr_rt_pool4(vsr_rt_t* h, uint64_t x, int n, int H, int W, int C, uint64_t w_dev, uint64_t b_dev, uint64_t out);   /* depthwise 4x4 stride 4 */
+int vsr_rt_window_attention(vsr_rt_t* h, uint64_t q, uint64_t k, uint64_t v, uint64_t kp, uint64_t vp, int T, int Hn, int Wn, int C, int ph, int pw,
+                            uint64_t valid_ind_dev, int n_valid, uint64_t t_ind_dev, int n_tind, uint64_t win_masked_dev, uint64_t out);
+int vsr_rt_pred_to_rgb8(vsr_rt_t* h, uint64_t x, int cp, int64_t pixels, uint8_t* host_out);                           /* trunc((tanh(x)+1)/2*255) */
 /* ---- LAMA: what the TorchScript big-lama forward needs beyond the detector's operators ---- */
 /* out[OH,OW] = in[H,W] shifted by (top, left), reflected at the borders (reflect = 1) or zero filled (0) */
 int vsr_rt_pad(vsr_rt_t* h, uint64_t in, int T, int H, int W, int cp, uint64_t out, int OH, int OW, int top, int left, int reflect);

@@ -468,6 +468,103 @@ class FakeRuntime:
         self._v4(dst)[..., coff:coff + nch] = self._v4(src)[..., :nch]
         self.launches += 1
 
+    # ---- ProPainter generator, back half: transcriptions of the pp_ops.cuh kernels
+    def upload_ints(self, arr):
+        return self.upload_bytes(np.asarray(arr, np.int32))
+
+    def unfold7s3(self, x, out, gelu=False):
+        assert self._rec is None
+        from math import erf
+
+        v = self._v4(x)[..., : x.cp]
+        n, h, w, C = v.shape
+        fh, fw = (h + 6 - 7) // 3 + 1, (w + 6 - 7) // 3 + 1
+        p = np.pad(v, ((0, 0), (3, 3 + 3), (3, 3 + 3), (0, 0)))
+        o = self._v4(out)
+        for k in range(49):
+            ky, kx = divmod(k, 7)
+            blk = p[:, ky: ky + 3 * fh: 3, kx: kx + 3 * fw: 3]
+            if gelu:
+                blk = 0.5 * blk * (1 + np.vectorize(erf)(blk * 0.70710678))
+            o[..., k * C:(k + 1) * C] = blk
+        self.launches += 1
+
+    def fold7s3(self, tok, out, channels, normalise):
+        assert self._rec is None
+        t = self._v4(tok)
+        n, fh, fw, _ = t.shape
+        h, w, C = out.h, out.w, channels
+        acc = np.zeros((n, h + 12, w + 12, C), np.float32)
+        cnt = np.zeros((h + 12, w + 12), np.float32)
+        for k in range(49):
+            ky, kx = divmod(k, 7)
+            acc[:, ky: ky + 3 * fh: 3, kx: kx + 3 * fw: 3] += t[..., k * C:(k + 1) * C]
+            cnt[ky: ky + 3 * fh: 3, kx: kx + 3 * fw: 3] += 1
+        acc, cnt = acc[:, 3: 3 + h, 3: 3 + w], cnt[3: 3 + h, 3: 3 + w]
+        if normalise:
+            acc = acc / np.maximum(cnt, 1)[None, :, :, None]
+        self._v4(out)[..., :C] = acc
+        self.launches += 1
+
+    def layernorm(self, x, gamma, beta, out):
+        assert self._rec is None
+        v = self._v4(x)
+        m = v.mean(-1, keepdims=True)
+        r = 1 / np.sqrt(np.maximum((v * v).mean(-1, keepdims=True) - m * m, 0) + 1e-5)
+        self._v4(out)[:] = (v - m) * r * self.bufs[gamma][: x.cp] + self.bufs[beta][: x.cp]
+        self.launches += 1
+
+    def pool4(self, x, w_dev, b_dev, out):
+        assert self._rec is None
+        v = self._v4(x)
+        n, H, W, C = v.shape
+        ph, pw = H // 4, W // 4
+        wt = self.bufs[w_dev][: C * 16].reshape(C, 4, 4)
+        blk = v[:, : 4 * ph, : 4 * pw].reshape(n, ph, 4, pw, 4, C)
+        self._v4(out)[:] = np.einsum("nyaxbc,cab->nyxc", blk, wt) + self.bufs[b_dev][:C]
+        self.launches += 1
+
+    def window_attention(self, q, k, v, kp, vp, valid_dev, n_valid, tind_dev, n_tind, masked_dev, out):
+        assert self._rec is None
+        Q, K, V, KP, VP = (self._v4(t) for t in (q, k, v, kp, vp))
+        T, Hn, Wn, C = Q.shape
+        valid = self.bufs[valid_dev][:n_valid].astype(np.int64)
+        tind = self.bufs[tind_dev][:n_tind].astype(np.int64)
+        nwh, nww = Hn // 5, Wn // 9
+        masked = self.bufs[masked_dev][: nwh * nww] > 0
+        eh, ew = 3, 5
+        O = self._v4(out)
+        O[:] = 0
+        own = [(s // 9, s % 9) for s in range(45)]
+        rolled = []
+        for idv in valid:
+            rr, o = divmod(int(idv), 45)
+            rolled.append((o // 9, o % 9, -eh if rr < 2 else eh, ew if rr & 1 else -ew))
+        for win in range(nwh * nww):
+            wy0, wx0 = (win // nww) * 5, (win % nww) * 9
+            ys = np.array([wy0 + a for a, _ in own])
+            xs = np.array([wx0 + b for _, b in own])
+            ry = np.array([(wy0 + a - sy) % Hn for a, _, sy, _ in rolled])
+            rx = np.array([(wx0 + b - sx) % Wn for _, b, _, sx in rolled])
+            for hd in range(C // 128):
+                cs = slice(hd * 128, (hd + 1) * 128)
+                for tq in range(T):
+                    qq = Q[tq, ys, xs, cs]                                     # [45, 128]
+                    if masked[win]:
+                        kk = np.concatenate([np.concatenate([K[t, ys, xs, cs], K[t, ry, rx, cs], KP[t].reshape(-1, C)[:, cs]]) for t in tind])
+                        vv = np.concatenate([np.concatenate([V[t, ys, xs, cs], V[t, ry, rx, cs], VP[t].reshape(-1, C)[:, cs]]) for t in tind])
+                    else:
+                        kk, vv = K[tq, ys, xs, cs], V[tq, ys, xs, cs]
+                    a = (qq @ kk.T) * 0.08838834764831845
+                    a = np.exp(a - a.max(1, keepdims=True))
+                    O[tq, ys, xs, cs] = (a / a.sum(1, keepdims=True)) @ vv
+        self.launches += 1
+
+    def pred_to_rgb8(self, x):
+        assert self._rec is None
+        v = self._v4(x)[..., :3]
+        return np.clip((np.tanh(v) + 1) / 2 * 255, 0, 255).astype(np.uint8)
+
     # ---- ProPainter image propagation (P5)
     def upload_bytes(self, arr):
         arr = np.ascontiguousarray(arr)
@@ -543,7 +640,11 @@ class FakeRuntime:
         if self._recording("pad", x, y, top, left, reflect):
             return
         bottom, right = y.h - x.h - top, y.w - x.w - left
-        self._v4(y)[:] = np.pad(self._v4(x), ((0, 0), (top, bottom), (left, right), (0, 0)), mode="reflect" if reflect else "constant")
+        if bottom < 0 or right < 0:                       # zero-mode window smaller than the input: a crop (out[oy][ox] = in[oy - top][ox - left])
+            assert not reflect and top == 0 and left == 0
+            self._v4(y)[:] = self._v4(x)[:, : y.h, : y.w]
+        else:
+            self._v4(y)[:] = np.pad(self._v4(x), ((0, 0), (top, bottom), (left, right), (0, 0)), mode="reflect" if reflect else "constant")
         self.launches += 1
 
     def zero_upsample(self, x, y):

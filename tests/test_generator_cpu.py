@@ -52,3 +52,9 @@ def test_encoder_and_feature_propagation_on_cpu_runtime():
     scale = np.abs(want).max()
     assert np.abs(got[len(nb):] - want[len(nb):]).max() < 1e-4 * scale          # reference frames: encoder only
     assert np.abs(got[:len(nb)] - want[:len(nb)]).max() < 2e-3 * scale          # local frames: + deformable propagation
+    # back half: soft split, 8 sparse-window transformer blocks, soft composition, decoder -> u8 predictions
+    pred = gen.transform_and_decode(enc, len(nb), md[0], H, W)
+    ref = G.generator(G.load_weights(PATH), updated[:, ids], tf[:, nb[:-1]], tb[:, nb[:-1]], mt[:, ids], upd[:, ids], len(nb))
+    want8 = (((ref.view(-1, 3, H, W) + 1) / 2).permute(0, 2, 3, 1).numpy() * 255).astype(np.uint8)
+    d = np.abs(pred.astype(np.int32) - want8)
+    assert pred.shape == want8.shape and d.max() <= 2 and (d > 0).mean() < 0.02, (int(d.max()), float((d > 0).mean()))

@@ -122,6 +122,13 @@ _PROTOS = {
     "vsr_rt_prop_masks": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_featprop_cond": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "vsr_rt_write_extra": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int64]),
+    "vsr_rt_unfold7s3": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int]),
+    "vsr_rt_fold7s3": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "vsr_rt_layernorm": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "vsr_rt_pool4": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "vsr_rt_window_attention": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64]),
+    "vsr_rt_pred_to_rgb8": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int64, _u8p]),
     "vsr_rt_residual_add": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int]),
     "vsr_rt_fft_r2c": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "vsr_rt_fft_c2r": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),

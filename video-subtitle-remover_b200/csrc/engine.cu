@@ -2060,6 +2060,83 @@ int vsr_rt_write_extra(vsr_rt_t* h, uint64_t src, uint64_t dst, int pitch, int c
   });
 }
 
+int vsr_rt_unfold7s3(vsr_rt_t* h, uint64_t in, int n, int hh, int ww, int C, uint64_t out, int pitch, int gelu) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(in && out && n > 0 && C % 8 == 0 && pitch >= 49 * C, "bad arguments");
+    const int fh = (hh + 6 - 7) / 3 + 1, fw = (ww + 6 - 7) / 3 + 1;
+    pp_unfold7s3_kernel<<<blocks_for((size_t)n * fh * fw * 49 * (C / 8)), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)in, n, hh, ww, C, fh, fw,
+                                                                                                 (__half*)(uintptr_t)out, pitch, gelu);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_fold7s3(vsr_rt_t* h, uint64_t tok, int n, int hh, int ww, int C, int pitch, int normalise, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(tok && out && n > 0 && C % 8 == 0 && pitch >= 49 * C, "bad arguments");
+    const int fh = (hh + 6 - 7) / 3 + 1, fw = (ww + 6 - 7) / 3 + 1;
+    pp_fold7s3_kernel<<<blocks_for((size_t)n * hh * ww * (C / 8)), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)tok, n, fh, fw, pitch, C, hh, ww, normalise,
+                                                                                          (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_layernorm(vsr_rt_t* h, uint64_t x, int64_t tokens, int C, uint64_t gamma_dev, uint64_t beta_dev, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(x && out && gamma_dev && beta_dev && tokens > 0 && C > 0, "bad arguments");
+    pp_layernorm_kernel<<<(unsigned)((tokens + 7) / 8), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)x, (size_t)tokens, C, (const float*)(uintptr_t)gamma_dev,
+                                                                               (const float*)(uintptr_t)beta_dev, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_pool4(vsr_rt_t* h, uint64_t x, int n, int H, int W, int C, uint64_t w_dev, uint64_t b_dev, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(x && out && w_dev && b_dev && n > 0 && H >= 4 && W >= 4, "bad arguments");
+    pp_pool4_kernel<<<blocks_for((size_t)n * (H / 4) * (W / 4) * C), 256, 0, h->ctx.stream>>>((const __half*)(uintptr_t)x, n, H, W, C, (const float*)(uintptr_t)w_dev,
+                                                                                            (const float*)(uintptr_t)b_dev, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_window_attention(vsr_rt_t* h, uint64_t q, uint64_t k, uint64_t v, uint64_t kp, uint64_t vp, int T, int Hn, int Wn, int C, int ph, int pw,
+                            uint64_t valid_ind_dev, int n_valid, uint64_t t_ind_dev, int n_tind, uint64_t win_masked_dev, uint64_t out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(q && k && v && kp && vp && out && valid_ind_dev && t_ind_dev && win_masked_dev && T > 0 && Hn % PP_WH == 0 && Wn % PP_WW == 0 && C % 128 == 0,
+            "bad arguments");
+    dim3 grid((Hn / PP_WH) * (Wn / PP_WW), C / 128, T);
+    pp_window_attention_kernel<<<grid, 192, 0, h->ctx.stream>>>((const __half*)(uintptr_t)q, (const __half*)(uintptr_t)k, (const __half*)(uintptr_t)v,
+                                                                (const __half*)(uintptr_t)kp, (const __half*)(uintptr_t)vp, T, Hn, Wn, C, ph, pw,
+                                                                (const int*)(uintptr_t)valid_ind_dev, n_valid, (const int*)(uintptr_t)t_ind_dev, n_tind,
+                                                                (const int*)(uintptr_t)win_masked_dev, (__half*)(uintptr_t)out);
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+  });
+}
+
+int vsr_rt_pred_to_rgb8(vsr_rt_t* h, uint64_t x, int cp, int64_t pixels, uint8_t* host_out) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(x && host_out && pixels > 0 && cp >= 3 && !h->capturing, "bad arguments");
+    const size_t bytes = (size_t)pixels * 3;
+    h->plane.ensure(bytes);
+    cudaStream_t s = h->ctx.stream;
+    pp_pred_to_rgb8_kernel<<<blocks_for((size_t)pixels), 256, 0, s>>>((const __half*)(uintptr_t)x, cp, (size_t)pixels, h->plane.as<uint8_t>());
+    CK(cudaGetLastError());
+    ++h->ctx.launches;
+    CK(cudaMemcpyAsync(host_out, h->plane.p, bytes, cudaMemcpyDeviceToHost, s));
+    rt_sync(h);
+  });
+}
+
 int vsr_rt_residual_add(vsr_rt_t* h, uint64_t x32, uint64_t y16, uint64_t x16, int64_t n_elems, int init) {
   return guarded([&] {
     rt_check(h);

@@ -549,6 +549,204 @@ __global__ void __launch_bounds__(256) pp_write_extra_kernel(const __half* __res
   for (int c = 0; c < nch; ++c) dst[p * pitch + coff + c] = src[p * 8 + c];
 }
 
+// ---- P6 back half: soft split / composition, the sparse-window transformer (video/model/modules/sparse_transformer.py) -------------
+// nn.Unfold(7, stride 3, padding 3) in TAP-MAJOR order: out[n][ty][tx][k*C + c] = in[n][3*ty - 3 + ky][3*tx - 3 + kx][c] (0 outside),
+// k = ky*7 + kx.  (torch's order is c*49 + k; the linear layers that consume / produce it have their weights permuted on the host.)
+__global__ void __launch_bounds__(256) pp_unfold7s3_kernel(const __half* __restrict__ in, int n, int h, int w, int C, int fh, int fw, __half* __restrict__ out,
+                                                           int pitch, int gelu) {
+  const int c8n = C >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * fh * fw * 49 * c8n) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int k = r % 49;
+  r /= 49;
+  const int tx = r % fw;
+  r /= fw;
+  const int ty = r % fh;
+  const int img = r / fh;
+  const int y = 3 * ty - 3 + k / 7, x = 3 * tx - 3 + k % 7;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (y >= 0 && y < h && x >= 0 && x < w) {
+    v = *reinterpret_cast<const uint4*>(in + (((size_t)img * h + y) * w + x) * C + c8 * 8);
+    if (gelu) {   // F.gelu (erf form) of FusionFeedForward.fc2[0], applied while the folded map is unfolded again
+      __half2* h2 = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(h2[j]);
+        f.x = 0.5f * f.x * (1.f + erff(f.x * 0.70710678f));
+        f.y = 0.5f * f.y * (1.f + erff(f.y * 0.70710678f));
+        h2[j] = __floats2half2_rn(f.x, f.y);
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)img * fh + ty) * fw + tx) * pitch + (size_t)k * C + c8 * 8) = v;
+}
+
+// F.fold(kernel 7, stride 3, padding 3) of tap-major tokens: out[n][y][x][c] = sum over the (token, tap) pairs that cover pixel (y, x) of
+// tok[n][ty][tx][k*C + c]; normalise != 0 divides by the number of covering pairs (FusionFeedForward :96-108), else plain sum (SoftComp :61-66)
+__global__ void __launch_bounds__(256) pp_fold7s3_kernel(const __half* __restrict__ tok, int n, int fh, int fw, int pitch, int C, int h, int w, int normalise,
+                                                         __half* __restrict__ out) {
+  const int c8n = C >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * h * w * c8n) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int x = r % w;
+  r /= w;
+  const int y = r % h;
+  const int img = r / h;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int cnt = 0;
+  for (int ky = (y + 3) % 3; ky < 7; ky += 3) {
+    const int ty = (y + 3 - ky) / 3;
+    if (ty < 0 || ty >= fh) continue;
+    for (int kx = (x + 3) % 3; kx < 7; kx += 3) {
+      const int tx = (x + 3 - kx) / 3;
+      if (tx < 0 || tx >= fw) continue;
+      ++cnt;
+      const uint4 v = *reinterpret_cast<const uint4*>(tok + (((size_t)img * fh + ty) * fw + tx) * pitch + (size_t)(ky * 7 + kx) * C + c8 * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+  const float s = (normalise && cnt > 0) ? 1.f / (float)cnt : 1.f;
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = __floats2half2_rn(acc[2 * j] * s, acc[2 * j + 1] * s);
+  *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// nn.LayerNorm(512) over the channel axis of tokens [P][C] (eps 1e-5); one warp per token
+__global__ void __launch_bounds__(256) pp_layernorm_kernel(const __half* __restrict__ x, size_t tokens, int C, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, __half* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= tokens) return;
+  const __half* src = x + t * C;
+  float s = 0.f, q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = __half2float(src[c]);
+    s += v;
+    q += v * v;
+  }
+  for (int o = 16; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const float m = s / (float)C, r = rsqrtf(fmaxf(q / (float)C - m * m, 0.f) + 1e-5f);
+  for (int c = lane; c < C; c += 32) out[t * C + c] = __float2half_rn((__half2float(src[c]) - m) * r * gamma[c] + beta[c]);
+}
+
+// SparseWindowAttention.pool_layer: depthwise Conv2d(C, C, 4, stride 4, groups C) with its own (trained) weights w[c][4][4], bias b[c]
+__global__ void __launch_bounds__(256) pp_pool4_kernel(const __half* __restrict__ x, int n, int H, int W, int C, const float* __restrict__ wgt,
+                                                       const float* __restrict__ bias, __half* __restrict__ out) {
+  const int ph = H / 4, pw = W / 4;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * ph * pw * C) return;
+  const int c = idx % C;
+  size_t r = idx / C;
+  const int px = r % pw;
+  r /= pw;
+  const int py = r % ph;
+  const int img = r / ph;
+  float acc = bias[c];
+  for (int ky = 0; ky < 4; ++ky)
+    for (int kx = 0; kx < 4; ++kx) acc += wgt[c * 16 + ky * 4 + kx] * __half2float(x[(((size_t)img * H + 4 * py + ky) * W + 4 * px + kx) * C + c]);
+  out[idx] = __float2half_rn(acc);
+}
+
+// SparseWindowAttention core (:168-283) after the q/k/v projections, on padded token maps [T][Hn][Wn][C] (C = heads * 128).
+// One block = (window, head, query frame): its wh*ww = 45 queries attend
+//   masked window   : for every frame in t_ind: the window's own 45 tokens, the 148 valid tokens of the four rolled windows (valid_ind indexes the
+//                     concatenation tl | tr | bl | br, each in window order) and all pooled tokens of that frame (kp / vp [T][ph][pw][C]);
+//   unmasked window : the 45 tokens of the same window and the same frame only.
+// torch.roll(k, (sy, sx)) puts token ((Y - sy) mod Hn, (X - sx) mod Wn) at (Y, X); the four shifts are (-eh,-ew), (-eh,+ew), (+eh,-ew), (+eh,+ew).
+// Thread = (query, quarter of the 128 head dims); online softmax in fp32; scale 1/sqrt(128).
+#define PP_WH 5
+#define PP_WW 9
+#define PP_WT (PP_WH * PP_WW)
+__global__ void __launch_bounds__(192) pp_window_attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
+                                                                  const __half* __restrict__ kp, const __half* __restrict__ vp, int T, int Hn, int Wn, int C,
+                                                                  int ph, int pw, const int* __restrict__ valid_ind, int n_valid, const int* __restrict__ t_ind,
+                                                                  int n_tind, const int* __restrict__ win_masked, __half* __restrict__ out) {
+  const int nww = Wn / PP_WW;
+  const int win = blockIdx.x, head = blockIdx.y, tq = blockIdx.z;
+  const int wy0 = (win / nww) * PP_WH, wx0 = (win % nww) * PP_WW;
+  const int qi = threadIdx.x >> 2, part = threadIdx.x & 3;        // query 0..47 (45 used), 32 dims each
+  const bool active = qi < PP_WT;
+  const int eh = (PP_WH + 1) / 2, ew = (PP_WW + 1) / 2;
+  const size_t plane = (size_t)Hn * Wn;
+  const int c0 = head * 128 + part * 32;
+  float qv[32], acc[32];
+  float mx = -1e30f, den = 0.f;
+  {   // idle threads (queries 45..47) run along with zero queries so that the warp shuffles below stay convergent; they never store
+    const __half* src = q + (((size_t)tq * Hn + wy0 + (active ? qi / PP_WW : 0)) * Wn + wx0 + (active ? qi % PP_WW : 0)) * C + c0;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) { qv[d] = active ? __half2float(src[d]) : 0.f; acc[d] = 0.f; }
+  }
+  const bool masked = win_masked[win] != 0;
+  const int n_pool = ph * pw;
+  const int per_frame = masked ? PP_WT + n_valid + n_pool : PP_WT;
+  const int n_frames = masked ? n_tind : 1;
+  const float scale = 0.08838834764831845f;     // 1 / sqrt(128)
+  for (int fi = 0; fi < n_frames; ++fi) {
+    const int tk = masked ? t_ind[fi] : tq;
+    for (int s = 0; s < per_frame; ++s) {
+      const __half *kr, *vr;
+      if (s < PP_WT + n_valid) {
+        int wy, wx, sy = 0, sx = 0;
+        if (s < PP_WT) { wy = s / PP_WW; wx = s % PP_WW; }
+        else {
+          const int id = valid_ind[s - PP_WT], rr = id / PP_WT, o = id % PP_WT;
+          wy = o / PP_WW; wx = o % PP_WW;
+          sy = (rr < 2) ? -eh : eh;
+          sx = (rr & 1) ? ew : -ew;
+        }
+        const int Y = ((wy0 + wy - sy) % Hn + Hn) % Hn, X = ((wx0 + wx - sx) % Wn + Wn) % Wn;
+        const size_t off = ((size_t)tk * plane + (size_t)Y * Wn + X) * C + c0;
+        kr = k + off; vr = v + off;
+      } else {
+        const size_t off = ((size_t)tk * n_pool + (s - PP_WT - n_valid)) * C + c0;
+        kr = kp + off; vr = vp + off;
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) dot += qv[d] * __half2float(kr[d]);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot *= scale;
+      const float nm = fmaxf(mx, dot), corr = __expf(mx - nm), pe = __expf(dot - nm);
+      den = den * corr + pe;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) acc[d] = acc[d] * corr + pe * __half2float(vr[d]);
+      mx = nm;
+    }
+  }
+  if (active) {
+    __half* dst = out + (((size_t)tq * Hn + wy0 + qi / PP_WW) * Wn + wx0 + qi % PP_WW) * C + c0;
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) dst[d] = __float2half_rn(acc[d] * inv);
+  }
+}
+
+// decoder output -> (tanh(x) + 1) / 2 * 255 truncated to u8, RGB [n][H][W][3] (propainter_inpaint.py:340-347 before the mask composite)
+__global__ void __launch_bounds__(256) pp_pred_to_rgb8_kernel(const __half* __restrict__ x, int cp, size_t pixels, uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fmul_rn(__fdiv_rn(__fadd_rn(tanhf(__half2float(x[i * cp + c])), 1.f), 2.f), 255.f);
+    out[i * 3 + c] = (uint8_t)fminf(fmaxf(v, 0.f), 255.f);
+  }
+}
+
 // combine_flow (:338-348): out[n] = pred[n'] * m + flow[n] * (1 - m), planar fp32; reverse: the network ran on the flipped sequence (n' = N-1-n)
 __global__ void __launch_bounds__(256) pp_rfc_combine_kernel(const __half* __restrict__ pred, int pp, const float* __restrict__ flow, const uint8_t* __restrict__ mask,
                                                              int N, size_t plane, int reverse, float* __restrict__ out) {

@@ -1,13 +1,18 @@
-"""ProPainter's InpaintGenerator on the device runtime — FRONT HALF: encoder and learnable feature propagation.
+"""ProPainter's InpaintGenerator on the device runtime.
 
-STATUS: equal to the oracle's stage taps (oracle/propainter_gen_oracle.py, pinned to the reference's frames) on the CPU stand-in of
-the runtime (tests/test_generator_cpu.py); kernels compile for sm_100a; NOT yet run on a B200; the back half (soft split, the 8
-sparse-window transformer blocks, soft composition, decoder) is not written yet.
+STATUS: equal to the oracle (oracle/propainter_gen_oracle.py, pinned to the reference's frames) on the CPU stand-in of the runtime
+(tests/test_generator_cpu.py: stage taps and final u8 predictions); kernels compile for sm_100a; NOT yet run on a B200.
 
 Mirrors video/model/propainter.py:196-235 (Encoder: grouped convs over [x0 | out] re-interleaved per group — laid out with channel
 copies, each group a tensor-core conv over a channel-slice view), :321-359 (inputs, 1/4 flows and masks) and :75-193 with
 learnable=True (flow-guided deformable alignment: one fused kernel builds the 261-channel condition tensor = current features,
 bilinear-warped propagated features, flow, consistency bit, masks; `deform_cols` + a K = 1152 GEMM is the deformable conv).
+Back half (sparse_transformer.py): soft split = tap-major unfold + a K = 6272 GEMM (the linear layers around unfold / fold have their
+weights permuted on the host from torch's channel-major c*49+k order to k*C+c); per block: layer norm, zero padding to 5x9 windows
+BEFORE the q/k/v projections (padded tokens carry the biases, like the reference), a depthwise 4x4 pooling + the same projections
+for the pooled tokens, ONE attention kernel that resolves own / rolled / pooled keys by index arithmetic (masked windows: every 2nd
+frame, all keys; unmasked windows: the 45 tokens of the same frame), projection, residual; the fusion feed-forward as fc1 -> fold
+with overlap normalisation -> unfold + GELU -> fc2.  The first version of the attention runs on CUDA cores (online softmax).
 """
 from typing import Dict, List, Sequence
 
@@ -44,6 +49,29 @@ class _GenRuntime(_RfcRuntime):
     def write_extra(self, src, dst, coff, nch):
         _capi.check(self.L.vsr_rt_write_extra(self.h, src.ptr, dst.ptr, dst.cp, coff, nch, dst.pixels))
 
+    def unfold7s3(self, x, out, gelu=False):
+        _capi.check(self.L.vsr_rt_unfold7s3(self.h, x.ptr, x.n, x.h, x.w, x.cp, out.ptr, out.cp, 1 if gelu else 0))
+
+    def fold7s3(self, tok, out, channels, normalise):
+        _capi.check(self.L.vsr_rt_fold7s3(self.h, tok.ptr, out.n, out.h, out.w, channels, tok.cp, 1 if normalise else 0, out.ptr))
+
+    def layernorm(self, x, gamma, beta, out):
+        _capi.check(self.L.vsr_rt_layernorm(self.h, x.ptr, x.pixels, x.cp, gamma, beta, out.ptr))
+
+    def pool4(self, x, w_dev, b_dev, out):
+        _capi.check(self.L.vsr_rt_pool4(self.h, x.ptr, x.n, x.h, x.w, x.cp, w_dev, b_dev, out.ptr))
+
+    def window_attention(self, q, k, v, kp, vp, valid_dev, n_valid, tind_dev, n_tind, masked_dev, out):
+        _capi.check(self.L.vsr_rt_window_attention(self.h, q.ptr, k.ptr, v.ptr, kp.ptr, vp.ptr, q.n, q.h, q.w, q.cp, kp.h, kp.w, valid_dev, n_valid, tind_dev,
+                                                   n_tind, masked_dev, out.ptr))
+
+    def pred_to_rgb8(self, x) -> np.ndarray:
+        import ctypes as C
+
+        out = np.empty((x.n, x.h, x.w, 3), np.uint8)
+        _capi.check(self.L.vsr_rt_pred_to_rgb8(self.h, x.ptr, x.cp, x.pixels, _capi.ptr(out, C.c_uint8)))
+        return out
+
 
 class Generator:
     def __init__(self, weights, device="cuda:0", runtime=None):
@@ -51,6 +79,14 @@ class Generator:
         self._rt = runtime if runtime is not None else _GenRuntime(device)
         self._layers: Dict[tuple, int] = {}
         self._arena = _Arena(self._rt)
+        self._consts: Dict[tuple, int] = {}
+
+    def _const(self, key, arr) -> int:
+        """device copy of a small constant array, uploaded once"""
+        if key not in self._consts:
+            arr = np.ascontiguousarray(arr)
+            self._consts[key] = self._rt.upload_f32(arr) if arr.dtype == np.float32 else self._rt.upload_bytes(arr)
+        return self._consts[key]
 
     def __del__(self):
         rt = getattr(self, "_rt", None)
@@ -197,6 +233,127 @@ class Generator:
         prop = self._feature_propagation(local, df, db, masks, new)
         rt.copy_channels(prop, local, 0, 128)                                     # enc_feat = cat(local_feat, ref_feat)
         return enc, masks
+
+
+    # ------------------------------------------------------------------------------------------------ back half
+    @staticmethod
+    def token_mask(mask: np.ndarray) -> np.ndarray:
+        """mask_pool_l of one local frame (:350-358): nearest 1/4 of the input mask, MaxPool2d(7, 3, 3) -> [fh, fw] in {0, 1}."""
+        ds = (np.asarray(mask)[::4, ::4] > 0).astype(np.uint8)
+        h, w = ds.shape
+        fh, fw = (h + 6 - 7) // 3 + 1, (w + 6 - 7) // 3 + 1
+        p = np.pad(ds, 3)
+        out = np.zeros((fh, fw), np.uint8)
+        for ty in range(fh):
+            for tx in range(fw):
+                out[ty, tx] = p[3 * ty:3 * ty + 7, 3 * tx:3 * tx + 7].max()
+        return out
+
+    def _lin(self, key, weight, bias, x: _Tensor, y: _Tensor):
+        """nn.Linear over the channel axis of a token map = 1x1 conv"""
+        self._rt.conv_ex(self._conv(key, np.ascontiguousarray(weight[:, :, None, None], np.float32), bias, x.cp, 1, 0), x, y, 0)
+
+    def transform_and_decode(self, enc: _Tensor, l_t: int, mask: np.ndarray, H: int, W: int) -> np.ndarray:
+        """enc: [n,h,w,128] after feature propagation; mask: the host u8 mask of the strip -> u8 predictions [l_t,H,W,3] (RGB, before the
+        mask composite of P7)."""
+        rt, w = self._rt, self.w
+        n, h, wd = enc.n, enc.h, enc.w
+        self._arena.begin(("back", n, l_t, H, W))
+        alloc = self._arena.alloc
+
+        def new(c, hh, ww, k=n, cp=None):
+            cp = cp or _r(c, 64)
+            return _Tensor(alloc(k * hh * ww * cp * 2), c, hh, ww, cp, n=k)
+
+        fh, fw = (h + 6 - 7) // 3 + 1, (wd + 6 - 7) // 3 + 1
+        Hn, Wn = -(-fh // 5) * 5, -(-fw // 9) * 9
+        tm = np.zeros((Hn, Wn), np.uint8)
+        tm[:fh, :fw] = self.token_mask(mask)
+        win_masked = tm.reshape(Hn // 5, 5, Wn // 9, 9).max((1, 3)).reshape(-1).astype(np.int32)     # the same for every local frame
+        masked_dev = self._const(("masked", win_masked.tobytes()), win_masked)
+        t_inds = [np.arange(i, n, 2, dtype=np.int32) for i in range(2)]
+        tind_dev = [self._const(("tind", n, i), t) for i, t in enumerate(t_inds)]
+
+        def tapmajor_cols(wt, C):      # [out, C*49] (c*49 + k) -> [out, 49*C] (k*C + c)
+            return np.ascontiguousarray(wt.reshape(wt.shape[0], C, 49).transpose(0, 2, 1).reshape(wt.shape[0], 49 * C))
+
+        def tapmajor_rows(wt, b, C):   # rows c*49 + k -> k*C + c
+            return (np.ascontiguousarray(wt.reshape(C, 49, wt.shape[1]).transpose(1, 0, 2).reshape(49 * C, wt.shape[1])),
+                    np.ascontiguousarray(b.reshape(C, 49).T.reshape(-1)))
+
+        # SoftSplit (:7-32)
+        u = new(6272, fh, fw)
+        rt.unfold7s3(enc, u)
+        tok = new(512, fh, fw)
+        self._lin("ss", tapmajor_cols(w["ss.embedding.weight"], 128), w["ss.embedding.bias"], u, tok)
+        for i in range(8):
+            p = f"transformers.transformer.{i}"
+            g1, b1 = self._const((p, "g1"), w[f"{p}.norm1.weight"]), self._const((p, "b1"), w[f"{p}.norm1.bias"])
+            y = new(512, fh, fw)
+            rt.layernorm(tok, g1, b1, y)
+            yp = y
+            if (Hn, Wn) != (fh, fw):
+                yp = new(512, Hn, Wn)
+                rt.pad(y, yp, 0, 0, 0)                                             # zeros at the bottom / right BEFORE the projections
+            q, k, v = new(512, Hn, Wn), new(512, Hn, Wn), new(512, Hn, Wn)
+            a = f"{p}.attention"
+            for name, dst in (("query", q), ("key", k), ("value", v)):
+                self._lin((a, name), w[f"{a}.{name}.weight"], w[f"{a}.{name}.bias"], yp, dst)
+            ph, pw = Hn // 4, Wn // 4
+            pooled = new(512, ph, pw)
+            rt.pool4(yp, self._const((a, "pw"), w[f"{a}.pool_layer.weight"].reshape(512, 16)), self._const((a, "pb"), w[f"{a}.pool_layer.bias"]), pooled)
+            kp, vp = new(512, ph, pw), new(512, ph, pw)
+            self._lin((a, "key"), w[f"{a}.key.weight"], w[f"{a}.key.bias"], pooled, kp)
+            self._lin((a, "value"), w[f"{a}.value.weight"], w[f"{a}.value.bias"], pooled, vp)
+            att = new(512, Hn, Wn)
+            valid = np.asarray(w[f"{a}.valid_ind_rolled"], np.int32)
+            rt.window_attention(q, k, v, kp, vp, self._const((a, "valid"), valid), int(valid.size), tind_dev[i % 2], int(t_inds[i % 2].size), masked_dev, att)
+            ac = att
+            if (Hn, Wn) != (fh, fw):
+                ac = new(512, fh, fw)
+                rt.pad(att, ac, 0, 0, 0)                                           # crop back
+            pr = new(512, fh, fw)
+            self._lin((a, "proj"), w[f"{a}.proj.weight"], w[f"{a}.proj.bias"], ac, pr)
+            rt.elementwise(0, tok, pr, tok)
+            g2, b2 = self._const((p, "g2"), w[f"{p}.norm2.weight"]), self._const((p, "b2"), w[f"{p}.norm2.bias"])
+            y2 = new(512, fh, fw)
+            rt.layernorm(tok, g2, b2, y2)
+            w1, bb1 = tapmajor_rows(w[f"{p}.mlp.fc1.0.weight"], w[f"{p}.mlp.fc1.0.bias"], 40)
+            f1 = new(1960, fh, fw)
+            self._lin((p, "fc1"), w1, bb1, y2, f1)
+            fm = new(40, h, wd, cp=40)
+            rt.fold7s3(f1, fm, 40, True)
+            f2 = new(1960, fh, fw)
+            rt.unfold7s3(fm, f2, gelu=True)
+            o = new(512, fh, fw)
+            self._lin((p, "fc2"), tapmajor_cols(w[f"{p}.mlp.fc2.1.weight"], 40), w[f"{p}.mlp.fc2.1.bias"], f2, o)
+            rt.elementwise(0, tok, o, tok)
+        # SoftComp (:35-66) + residual
+        ws, bs = tapmajor_rows(w["sc.embedding.weight"], w["sc.embedding.bias"], 128)
+        z = new(6272, fh, fw)
+        self._lin("sc", ws, bs, tok, z)
+        zf = new(128, h, wd)
+        rt.fold7s3(z, zf, 128, False)
+        zc = new(128, h, wd)
+        rt.conv_ex(self._conv("sc.bias_conv", w["sc.bias_conv.weight"], w["sc.bias_conv.bias"], zf.cp, 1, 1), zf, zc, 0)
+        rt.elementwise(0, enc, zc, zc)
+        # decoder on the local frames (:370-376)
+        y = _Tensor(zc.ptr, 128, h, wd, zc.cp, n=l_t)
+        for name, up in (("decoder.0.conv", True), ("decoder.2", False), ("decoder.4.conv", True)):
+            if up:
+                u2 = new(y.c, 2 * y.h, 2 * y.w, l_t)
+                rt.upsample2x(y, u2)
+                y = u2
+            wt = w[f"{name}.weight"]
+            o = new(wt.shape[0], y.h, y.w, l_t)
+            rt.conv_ex(self._conv(name, wt, w[f"{name}.bias"], y.cp, 1, 1), y, o, 0)
+            rt.leaky(o, 0.2)
+            y = o
+        o = new(8, y.h, y.w, l_t)
+        rt.conv_ex(self._conv("decoder.6", w["decoder.6.weight"], w["decoder.6.bias"], y.cp, 1, 1), y, o, 0)
+        if rt.overflow():
+            raise _capi.VsrError("generator activations left the fp16 range")
+        return rt.pred_to_rgb8(o)
 
 
 __all__ = ["Generator", "load_generator_weights"]
