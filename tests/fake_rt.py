@@ -241,7 +241,7 @@ class FakeRuntime:
     def corr_lookup(self, levels, flow32, hh, ww, pixels, out):
         if self._recording("corr_lookup", levels, flow32, hh, ww, pixels, out):
             return
-        flow = self.bufs[flow32][: pixels * 2].reshape(pixels, 2)
+        flow = self._raw32(flow32, pixels * 2).reshape(pixels, 2)
         ys, xs = np.divmod(np.arange(pixels) % (hh * ww), ww)
         res = np.zeros((pixels, 324), np.float32)
         d = np.arange(-4, 5, dtype=np.float32)
@@ -282,7 +282,7 @@ class FakeRuntime:
         if self._recording("flow_update", flow32, delta, flow16, dst_a, dst_b, coff, add):
             return
         n = flow16.pixels
-        f = self.bufs[flow32][: n * 2].reshape(n, 2)
+        f = self._raw32(flow32, n * 2).reshape(n, 2)          # strided view into the buffer: in-place updates land in it
         if add:
             f += self._v4(delta).reshape(n, -1)[:, :2]
         v = self._v4(flow16).reshape(n, -1)
@@ -295,16 +295,16 @@ class FakeRuntime:
 
     def convex_upsample(self, flow32, mask, n, hh, ww, out32):
         assert self._rec is None
-        f = torch.from_numpy(self.bufs[flow32][: n * hh * ww * 2].reshape(n, hh, ww, 2).copy()).permute(0, 3, 1, 2)
+        f = torch.from_numpy(self._raw32(flow32, n * hh * ww * 2).reshape(n, hh, ww, 2).copy()).permute(0, 3, 1, 2)
         m = torch.from_numpy(self._v4(mask)[..., :576].copy()).permute(0, 3, 1, 2).reshape(n, 1, 9, 8, 8, hh, ww)
         m = torch.softmax(m, 2)
         up = F.unfold(8 * f, [3, 3], padding=1).view(n, 2, 9, 1, 1, hh, ww)
         out = torch.sum(m * up, 2).permute(0, 1, 4, 2, 5, 3).reshape(n, 2, 8 * hh, 8 * ww)
-        self.bufs[out32][: out.numel()] = out.numpy().reshape(-1)
+        self._raw32(out32, out.numel())[:] = out.numpy().reshape(-1)
         self.launches += 1
 
     def download_f32(self, ptr, shape):
-        return self.bufs[ptr][: int(np.prod(shape))].reshape(shape).copy()
+        return self._raw32(ptr, int(np.prod(shape))).reshape(shape).copy()
 
     def zero(self, ptr, nbytes):
         self.bufs[ptr][: nbytes // 2] = 0
@@ -388,7 +388,7 @@ class FakeRuntime:
         f = self._raw32(flow32, n * 2 * hh * ww).reshape(n, 2, hh, ww)
         m = (self.bufs[mask_u8][: hh * ww].reshape(hh, ww) > 0).astype(np.float32)
         res = p.transpose(0, 3, 1, 2) * m + f * (1 - m)
-        self.bufs[out32][: res.size] = res.reshape(-1)          # alloc()-ed fp32 outputs are read back contiguously (download_f32)
+        self._raw32(out32, res.size)[:] = res.reshape(-1)
         self.launches += 1
 
     def upsample2x(self, x, y):
@@ -417,7 +417,7 @@ class FakeRuntime:
         f = self._raw32(flow32, total * 2 * hh * ww).reshape(total, 2, hh, ww)[ids]
         blk = (f[:, :, 1::4, 1::4] + f[:, :, 1::4, 2::4] + f[:, :, 2::4, 1::4] + f[:, :, 2::4, 2::4]) * 0.25 * 0.25
         res = blk.transpose(0, 2, 3, 1).reshape(-1)
-        self.bufs[out32][: res.size] = res            # alloc()-ed fp32 buffer used contiguously ([P][2])
+        self._raw32(out32, res.size)[:] = res
         self.launches += 1
 
     def prop_masks(self, gen_in, out):
@@ -429,10 +429,8 @@ class FakeRuntime:
         self.launches += 1
 
     def _flow_at(self, ptr, hh, ww):
-        """fp32 [P][2] flow stored contiguously in an alloc()-ed buffer, addressed with byte offsets (4 bytes = 2 slots per float)"""
-        arr, off = self._resolve(ptr)
-        assert off % 2 == 0
-        return arr[off // 2: off // 2 + hh * ww * 2].reshape(hh, ww, 2)
+        """fp32 [P][2] flow at a byte-offset pointer (one float per two slots, like every fp32 buffer of this stand-in)"""
+        return self._raw32(ptr, hh * ww * 2).reshape(hh, ww, 2)
 
     def featprop_cond(self, prop, cur, flow_prop, flow_check, masks, cond):
         assert self._rec is None
@@ -576,6 +574,17 @@ class FakeRuntime:
         else:                              # u8 masks: no pointer arithmetic on them, one slot per element
             self.bufs[h] = arr.astype(np.float32).reshape(-1)
         return h
+
+    def upload_to(self, ptr, arr):
+        arr = np.ascontiguousarray(arr)
+        need = 2 * arr.size if arr.dtype == np.float32 else arr.size
+        if self.bufs[ptr].size < need:            # alloc() sized the slots for fp16 data; byte / int payloads need one slot per element here
+            self.bufs[ptr] = np.zeros(need, np.float32)
+        buf = self.bufs[ptr]
+        if arr.dtype == np.float32:
+            buf[: 2 * arr.size: 2] = arr.reshape(-1)
+        else:
+            buf[: arr.size] = arr.reshape(-1)
 
     def _raw32(self, ptr, count):
         arr, off = self._resolve(ptr)

@@ -207,7 +207,8 @@ class FlowCompletion:
     def complete(self, flows_f: int, flows_b: int, mask_u8: int, N: int, H: int, W: int):
         """device fp32 [N,2,H,W] flows + device u8 [H,W] flow mask -> two new device fp32 [N,2,H,W] buffers (completed flows)."""
         rt = self._rt
-        out_f, out_b = rt.alloc(N * 2 * H * W * 4), rt.alloc(N * 2 * H * W * 4)
+        self._arena.begin(("out", N, H, W))
+        out_f, out_b = self._arena.alloc(N * 2 * H * W * 4), self._arena.alloc(N * 2 * H * W * 4)
         self._network(flows_f, mask_u8, N, H, W, False, out_f)
         self._network(flows_b, mask_u8, N, H, W, True, out_b)
         if rt.overflow():

@@ -28,8 +28,13 @@ class _PropRuntime(_RaftRuntime):
     def upload_bytes(self, arr: np.ndarray) -> int:
         arr = np.ascontiguousarray(arr)
         p = self.alloc(max(arr.nbytes, 16))
-        _capi.check(self.L.vsr_rt_upload(self.h, p, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        self.upload_to(p, arr)
         return p
+
+    def upload_to(self, ptr: int, arr: np.ndarray):
+        """host array -> an existing device buffer (buffers live as long as the runtime: per-call inputs go through an _Arena)"""
+        arr = np.ascontiguousarray(arr)
+        _capi.check(self.L.vsr_rt_upload(self.h, ptr, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
 
 
 class _Arena:

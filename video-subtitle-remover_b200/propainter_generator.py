@@ -217,8 +217,8 @@ class Generator:
             cp = _r(c, 64)
             return _Tensor(alloc(k * hh * ww * cp * 2), c, hh, ww, cp, n=k)
 
-        ids_dev = rt.upload_bytes(np.asarray(list(ids), np.int32))
-        flow_ids = rt.upload_bytes(np.asarray(list(ids[:l_t - 1]), np.int32))     # the local flows are those of neighbour ids[:-1]
+        ids_dev = self._const(("ids", tuple(ids)), np.asarray(list(ids), np.int32))
+        flow_ids = self._const(("ids", tuple(ids[:l_t - 1])), np.asarray(list(ids[:l_t - 1]), np.int32))   # local flows: neighbour ids[:-1]
         gin = _Tensor(alloc(n * H * W * 8 * 2), 5, H, W, 8, n=n)
         rt.gen_input(state, mask_u8, ids_dev, n, gin)
         enc = self._encoder(gin, new)
