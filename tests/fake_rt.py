@@ -14,10 +14,37 @@ def _r8(x):
     return (x + 7) // 8 * 8
 
 
+_NOT_OPS = {"alloc", "upload_f32", "upload_bytes", "upload_to", "upload_ints", "download", "download_channel", "download_f32", "capture_begin",
+            "capture_end", "graph_launch", "graph_destroy", "conv_create", "se_create", "overflow", "absmax", "close", "sync", "zero", "launch_count"}
+
+
+def _fp16_storage(cls):
+    """fp16=True mode: after every operator, round every tensor argument to fp16 (what the device buffers hold); fp32 side buffers
+    (flow state, FFT staging, residual masters) are addressed by raw pointers and stay fp32, like on the device."""
+    def wrap(fn):
+        def inner(self, *args, **kw):
+            out = fn(self, *args, **kw)
+            if self.fp16 and self._rec is None:
+                for a in list(args) + list(kw.values()):
+                    if hasattr(a, "ptr") and hasattr(a, "cp") and hasattr(a, "h"):
+                        v = self._v4(a)
+                        v[:] = v.astype(np.float16).astype(np.float32)
+            return out
+        inner.__name__, inner.__doc__ = fn.__name__, fn.__doc__
+        return inner
+
+    for name, fn in list(vars(cls).items()):
+        if callable(fn) and not name.startswith("_") and name not in _NOT_OPS:
+            setattr(cls, name, wrap(fn))
+    return cls
+
+
+@_fp16_storage
 class FakeRuntime:
-    def __init__(self, enforce_device_limits=True):
+    def __init__(self, enforce_device_limits=True, fp16=False):
         self.bufs, self.layers, self.launches = {}, [], 0
         self.enforce = enforce_device_limits
+        self.fp16 = fp16        # simulate fp16 storage + fp16 tensor-core operands (fp32 accumulation): precision forecasts without a GPU
         self._next = 0x1000
         self._bases = []
         self._flag = False
@@ -124,6 +151,8 @@ class FakeRuntime:
                 assert (kh, kw, pad_t, pad_l, dil) == (3, 3, 1, 1, 1) and cin_pitch % 16 == 0 and cout % 8 == 0
             else:
                 assert stride == 1 and cout % 8 == 0 and w.shape == (cout, cin, kh, kw)
+        if self.fp16 and not transposed and groups == 1 and cin >= 16 and cout >= 8:      # tensor-core layers hold fp16 weights; the direct kernels fp32
+            w = w.astype(np.float16).astype(np.float32)
         self.layers.append(dict(w=torch.from_numpy(w), b=torch.from_numpy(np.array(bias, np.float32)), cout=cout, cin=cin, kh=kh, kw=kw,
                                 stride=stride, pad_t=pad_t, pad_l=pad_l, dil=dil, groups=groups, transposed=transposed))
         return len(self.layers) - 1
@@ -228,6 +257,8 @@ class FakeRuntime:
         b = self._raw(f2_ptr, hw * c).reshape(hw, c)
         out = self._raw(out_ptr, hw * out_pitch).reshape(hw, out_pitch)
         out[:, :hw] = (a @ b.T) / np.sqrt(np.float32(c))
+        if self.fp16:
+            out[:] = out.astype(np.float16).astype(np.float32)
         self.launches += 1
 
     def corr_pool(self, in_ptr, rows, h2, w2, pitch_in, out_ptr, pitch_out):
@@ -235,7 +266,10 @@ class FakeRuntime:
         src = self._raw(in_ptr, rows * pitch_in).reshape(rows, pitch_in)[:, : h2 * w2].reshape(rows, h2, w2)
         oh, ow = h2 // 2, w2 // 2
         p = src[:, : 2 * oh, : 2 * ow].reshape(rows, oh, 2, ow, 2).mean((2, 4))
-        self._raw(out_ptr, rows * pitch_out).reshape(rows, pitch_out)[:, : oh * ow] = p.reshape(rows, -1)
+        dst = self._raw(out_ptr, rows * pitch_out).reshape(rows, pitch_out)
+        dst[:, : oh * ow] = p.reshape(rows, -1)
+        if self.fp16:
+            dst[:] = dst.astype(np.float16).astype(np.float32)
         self.launches += 1
 
     def corr_lookup(self, levels, flow32, hh, ww, pixels, out):

@@ -55,3 +55,30 @@ def test_lama_batches_and_strip_call():
     (y0, y1, _, _), = O.get_inpaint_area_by_mask(W, H, int(W * 3 / 16), mask)
     single = eng.inpaint(frames[4][y0:y1], mask[y0:y1])
     assert np.abs(single.astype(np.int32) - out[4][y0:y1]).max() <= 1
+
+
+def test_fp16_storage_simulation_forecasts_gpu_parity():
+    """The stand-in's fp16 mode (fp16 tensor storage + fp16 tensor-core operands, fp32 accumulation / FFT / residual master) predicts
+    the GPU parity: on the 70x100 golden case it gives ~55.6 dB / max 2 where the B200 measured 57.4 dB / max 1 (profiles/lama_r1.json).
+    Used to forecast paths that have not run on a GPU yet (profiles/fp16_forecast_r1.md)."""
+    import os
+    import sys
+
+    from conftest import ROOT
+    from fake_rt import FakeRuntime
+    from oracle import sttn_oracle as O
+    from vsr_b200.lama_inpaint import LamaInpaint
+
+    pt = os.path.join(ROOT, "weights", "big-lama", "big-lama.pt")
+    if not os.path.exists(pt):
+        pytest.skip("big-lama.pt not staged")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_lama import inputs
+
+    w = L.load_weights(pt)
+    img, m = inputs()[:2]
+    got = LamaInpaint("cuda:0", {k: v.numpy() for k, v in w.items()}, runtime=FakeRuntime(fp16=True)).inpaint(img, m)
+    want = L.inpaint(w, img, m)
+    hole = m > 0
+    assert np.array_equal(got[~hole], want[~hole])
+    assert O.psnr_u8(got[hole].astype(np.float32), want[hole].astype(np.float32)) >= 50.0 and np.abs(got.astype(np.int32) - want).max() <= 4
