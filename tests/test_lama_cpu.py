@@ -60,7 +60,7 @@ def test_lama_batches_and_strip_call():
 def test_fp16_storage_simulation_forecasts_gpu_parity():
     """The stand-in's fp16 mode (fp16 tensor storage + fp16 tensor-core operands, fp32 accumulation / FFT / residual master) predicts
     the GPU parity: on the 70x100 golden case it gives ~55.6 dB / max 2 where the B200 measured 57.4 dB / max 1 (profiles/lama_r1.json).
-    Used to forecast paths that have not run on a GPU yet (profiles/fp16_forecast_r1.md)."""
+    Used to forecast paths that have not run on a GPU yet (profiles/fp16_forecast_r1.md, tests/diag_fp16_forecast.py)."""
     import os
     import sys
 
