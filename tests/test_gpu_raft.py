@@ -1,6 +1,7 @@
 """GPU: RAFT on the device runtime against the oracle.  GATED: the device path was written after round 1's
 GPU budget was spent and has not run on a B200 yet; set VSR_RUN_UNVALIDATED=1 to run it (the first thing to do next round).
-Tolerance to establish then (fp16 features, fp32 flow state): mean end-point error <= 0.05 px, max <= 0.5 px on the fixtures."""
+Tolerance (fp16 features, fp32 flow state; the fp16 simulation of the stand-in gives EPE mean 8e-4 / max 7e-3 px on this fixture,
+profiles/fp16_forecast_r1.md): mean end-point error <= 0.01 px, max <= 0.1 px."""
 import os
 
 import numpy as np
@@ -26,7 +27,7 @@ def test_raft_flows_vs_oracle(capi):
     wf, wb = R.raft_bi(R.load_weights(PATH), x)
     for got, want in ((ff, wf[0].numpy()), (fb, wb[0].numpy())):
         epe = np.sqrt(((got - want) ** 2).sum(1))
-        assert np.isfinite(got).all() and epe.mean() <= 0.05 and epe.max() <= 0.5, (float(epe.mean()), float(epe.max()))
+        assert np.isfinite(got).all() and epe.mean() <= 0.01 and epe.max() <= 0.1, (float(epe.mean()), float(epe.max()))
 
 
 def test_image_propagation_vs_oracle(capi):
@@ -55,7 +56,7 @@ def test_image_propagation_vs_oracle(capi):
 
 
 def test_flow_completion_vs_oracle(capi):
-    """P4 on the device (gated).  Tolerance to establish: completed flows within 0.1 px of the oracle inside the hole."""
+    """P4 on the device (gated).  fp16 simulation: 2.4e-3 px; bar: completed flows within 0.03 px of the oracle."""
     import sys
 
     from conftest import GOLDEN
@@ -76,12 +77,12 @@ def test_flow_completion_vs_oracle(capi):
     pf, pb = FlowCompletion(path, "cuda:0").complete_host(gf, gb, fm[0])
     masks = torch.from_numpy(np.stack(fm).astype(np.float32) / 255)[None, :, None]
     wf, wb = C.complete_bidirectional(C.load_weights(path), torch.from_numpy(gf)[None], torch.from_numpy(gb)[None], masks)
-    assert np.abs(pf - wf[0].numpy()).max() < 0.1 and np.abs(pb - wb[0].numpy()).max() < 0.1
+    assert np.abs(pf - wf[0].numpy()).max() < 0.03 and np.abs(pb - wb[0].numpy()).max() < 0.03
 
 
 def test_propainter_pipeline_vs_reference_frames(capi):
-    """The whole device pipeline (gated) against the frames of the unmodified reference.  Tolerance to establish on the GPU: inside the
-    hole PSNR >= 35 dB against the reference's `comp`; outside the dilated mask bit-exact (the reference copies the input there)."""
+    """The whole device pipeline (gated) against the frames of the unmodified reference.  fp16 simulation: 58.9 dB in the hole; bar: PSNR >= 45 dB
+    against the reference's `comp` inside the hole; outside the dilated mask bit-exact (the reference copies the input there)."""
     import sys
 
     from conftest import GOLDEN
@@ -101,4 +102,4 @@ def test_propainter_pipeline_vs_reference_frames(capi):
     keep = np.stack(md) == 0
     assert np.array_equal(out[keep], np.stack(frames)[keep])
     hole = ~keep
-    assert O.psnr_u8(out[hole].astype(np.float32), z["comp"][hole].astype(np.float32)) >= 35.0
+    assert O.psnr_u8(out[hole].astype(np.float32), z["comp"][hole].astype(np.float32)) >= 45.0
