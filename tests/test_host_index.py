@@ -93,3 +93,31 @@ def test_batch_generator_and_schedule_match_oracle(capi):
     for T in (1, 4, 5, 6, 11, 24, 46, 50, 77):
         for stride, ref in ((5, 10), (3, 7), (1, 1)):
             assert window_schedule(T, stride, ref) == [(a, b) for a, b in O.window_schedule(T, stride, ref)]
+
+
+def test_ctypes_prototypes_match_the_header(capi):
+    """Every ctypes prototype has as many arguments as the C declaration, pointers where the header has pointers and 64-bit integers
+    where it has uint64_t / int64_t (a drift here is a crash or silent garbage on the GPU box, not a test failure on the CPU)."""
+    import ctypes as C
+    import re
+
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vsr_b200.h")).read(), flags=re.S)
+    decl = dict(re.findall(r"\b(vsr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text))
+    checked = 0
+    for name, (_, argtypes) in capi._PROTOS.items():
+        params = [p.strip() for p in decl[name].split(",")]
+        params = [] if params == ["void"] else params
+        assert len(params) == len(argtypes), (name, params, argtypes)
+        for p, t in zip(params, argtypes):
+            is_ptr_c = "*" in p
+            is_ptr_py = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) is not None and isinstance(t, type) and issubclass(t, C._Pointer)
+            if is_ptr_c:
+                assert is_ptr_py or t is C.c_uint64 and False, (name, p, t)
+            elif re.search(r"\b(uint64_t|int64_t)\b", p):
+                assert t in (C.c_uint64, C.c_int64), (name, p, t)
+            elif re.search(r"\bfloat\b", p):
+                assert t is C.c_float, (name, p, t)
+            elif re.search(r"\b(int|int32_t)\b", p):
+                assert t in (C.c_int, C.c_int32), (name, p, t)
+            checked += 1
+    assert checked > 600
