@@ -783,15 +783,15 @@ class FakeRuntime:
     def upsample(self, x, y, s):
         if self._recording("upsample", x, y, s):
             return
-        self._view(y)[:] = self._view(x).repeat(s, axis=0).repeat(s, axis=1)
+        self._v4(y)[:] = self._v4(x).repeat(s, axis=1).repeat(s, axis=2)
         self.launches += 1
 
-    def maxpool(self, x, y):   # 2x2 stride 1, SAME: pad 0 top/left, 1 bottom/right
+    def maxpool(self, x, y):   # 2x2 stride 1, SAME: pad 0 top/left, 1 bottom/right (per image)
         if self._recording("maxpool", x, y):
             return
-        v = self._view(x)
-        p = np.pad(v, ((0, 1), (0, 1), (0, 0)), constant_values=-np.inf)
-        self._view(y)[:] = np.maximum(np.maximum(p[:-1, :-1], p[1:, :-1]), np.maximum(p[:-1, 1:], p[1:, 1:]))
+        v = self._v4(x)
+        p = np.pad(v, ((0, 0), (0, 1), (0, 1), (0, 0)), constant_values=-np.inf)
+        self._v4(y)[:] = np.maximum(np.maximum(p[:, :-1, :-1], p[:, 1:, :-1]), np.maximum(p[:, :-1, 1:], p[:, 1:, 1:]))
         self.launches += 1
 
     def copy_channels(self, src, dst, dst_off, channels):
@@ -801,11 +801,11 @@ class FakeRuntime:
         self._view(dst)[:, :, dst_off:dst_off + channels] = self._view(src)[:, :, :channels]
         self.launches += 1
 
-    def preprocess(self, img, inp, rh, rw):
+    def preprocess(self, img, inp, rh, rw, slot=0):
         assert self._rec is None
         x = D.preprocess(img)[0].permute(1, 2, 0).numpy()
         assert x.shape[:2] == (rh, rw)
-        v = self._view(inp)
+        v = self._v4(inp)[slot]
         v[:] = 0
         v[:, :, :3] = x
         self.launches += 1
@@ -813,8 +813,8 @@ class FakeRuntime:
     def sync(self):
         pass
 
-    def download_channel(self, t, ch):
-        return (self._view(t)[:, :, ch] / t.scale).astype(np.float32)
+    def download_channel(self, t, ch, slot=0):
+        return (self._v4(t)[slot, :, :, ch] / t.scale).astype(np.float32)
 
     def download(self, t):
         return self._view(t).copy()

@@ -113,3 +113,24 @@ def test_mobile_detector_compiles_on_cpu_runtime():
     assert got.shape == want.shape == (96, 160) and np.abs(got - want).max() < 2e-4
     n0 = rt.launch_count
     assert np.array_equal(det.probability_map(img), got) and rt.launch_count - n0 < 130     # 683 PIR ops
+
+
+def test_batched_detection_equals_single_frames_on_cpu_runtime():
+    """`probability_maps`: several sampled frames in one launch give each frame's own result (calibration sees the whole batch)."""
+    import cv2
+    from fake_rt import FakeRuntime
+    from vsr_b200.dbnet import TextDetector
+
+    rng = np.random.default_rng(9)
+    imgs = []
+    for i in range(3):
+        img = rng.integers(0, 255, (64, 160, 3), dtype=np.uint8)
+        cv2.putText(img, f"t{i}", (10 + 30 * i, 50), cv2.FONT_HERSHEY_SIMPLEX, 1.2, (255, 255, 255), 3)
+        imgs.append(img)
+    det = TextDetector(MODEL_DIR, runtime=FakeRuntime())
+    maps = det.probability_maps(imgs)
+    g = D.Graph(MODEL_DIR)
+    for m, img in zip(maps, imgs):
+        assert np.abs(m - D.forward(g, D.preprocess(img))[0, 0].numpy()).max() < 2e-4
+    assert np.abs(det.probability_map(imgs[1]) - maps[1]).max() < 1e-5
+    assert sorted(k for k in det._programs if len(k) == 3) == [(3, 64, 160)]

@@ -103,3 +103,26 @@ def test_propainter_pipeline_vs_reference_frames(capi):
     assert np.array_equal(out[keep], np.stack(frames)[keep])
     hole = ~keep
     assert O.psnr_u8(out[hole].astype(np.float32), z["comp"][hole].astype(np.float32)) >= 45.0
+
+
+def test_batched_detection_equals_single_frames(capi):
+    """`TextDetector.probability_maps` (several sampled frames per launch): written after the GPU budget was spent, gated like the rest of this
+    file; bar: every frame's map equals its single-frame map to fp16 noise (the scales may differ between the two programs)."""
+    import cv2
+
+    model = os.path.join(ROOT, "weights", "V5", "ch_det")
+    if not os.path.exists(os.path.join(model, "inference.pdiparams")):
+        pytest.skip("detector model not staged")
+    from vsr_b200.dbnet import TextDetector
+
+    rng = np.random.default_rng(9)
+    imgs = []
+    for i in range(4):
+        img = cv2.GaussianBlur(rng.integers(0, 255, (360, 640, 3), dtype=np.uint8), (0, 0), 9)
+        cv2.putText(img, f"frame {i} text", (80 + 20 * i, 320), cv2.FONT_HERSHEY_SIMPLEX, 1.2, (255, 255, 255), 3, cv2.LINE_AA)
+        imgs.append(img)
+    det = TextDetector(model, "cuda:0")
+    maps = det.probability_maps(imgs)
+    for m, img in zip(maps, imgs):
+        d = np.abs(m - det.probability_map(img))
+        assert d.mean() <= 5e-4 and (d > 0.05).mean() <= 2e-3

@@ -283,7 +283,7 @@ class _DeviceRuntime:
         return int(lid.value)
 
     def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0):
-        _capi.check(self.L.vsr_rt_conv(self.h, lid, x.ptr, 1, x.h, x.w, y.ptr, y.cp, 0, relu, alpha, bias_scale))
+        _capi.check(self.L.vsr_rt_conv(self.h, lid, x.ptr, x.n, x.h, x.w, y.ptr, y.cp, 0, relu, alpha, bias_scale))
 
     def hswish_affine(self, x, y, inv_scale_in, a, c):
         _capi.check(self.L.vsr_rt_hswish_affine(self.h, x.ptr, y.ptr, x.pixels * x.cp, inv_scale_in, a, c))
@@ -327,16 +327,17 @@ class _DeviceRuntime:
                                               alpha, beta))
 
     def upsample(self, x, y, s):
-        _capi.check(self.L.vsr_rt_upsample_nearest(self.h, x.ptr, 1, x.h, x.w, x.cp, s, y.ptr, y.cp, 0))
+        _capi.check(self.L.vsr_rt_upsample_nearest(self.h, x.ptr, x.n, x.h, x.w, x.cp, s, y.ptr, y.cp, 0))
 
     def maxpool(self, x, y):
-        _capi.check(self.L.vsr_rt_maxpool2x2s1(self.h, x.ptr, 1, x.h, x.w, x.cp, y.ptr))
+        _capi.check(self.L.vsr_rt_maxpool2x2s1(self.h, x.ptr, x.n, x.h, x.w, x.cp, y.ptr))
 
     def copy_channels(self, src, dst, dst_off, channels):
         _capi.check(self.L.vsr_rt_copy_channels(self.h, src.ptr, src.cp, dst.ptr, dst.cp, dst_off, channels, src.pixels))
 
-    def preprocess(self, img, inp, rh, rw):
-        _capi.check(self.L.vsr_rt_det_preprocess(self.h, _capi.ptr(img, C.c_uint8), img.shape[0], img.shape[1], inp.ptr, rh, rw, inp.cp))
+    def preprocess(self, img, inp, rh, rw, slot=0):
+        _capi.check(self.L.vsr_rt_det_preprocess(self.h, _capi.ptr(img, C.c_uint8), img.shape[0], img.shape[1], inp.ptr + slot * rh * rw * inp.cp * 2, rh, rw,
+                                                 inp.cp))
 
     def download(self, t) -> np.ndarray:
         host = np.empty((t.h, t.w, t.cp), np.float16)
@@ -346,9 +347,11 @@ class _DeviceRuntime:
     def sync(self):
         _capi.check(self.L.vsr_rt_sync(self.h))
 
-    def download_channel(self, t, ch) -> np.ndarray:
+    def download_channel(self, t, ch, slot=0) -> np.ndarray:
+        """channel `ch` of image `slot` of a [n,h,w,cp] tensor as fp32 [h,w], divided by the tensor scale"""
         host = np.empty((t.h, t.w), np.float32)
-        _capi.check(self.L.vsr_rt_download_channel(self.h, t.ptr, t.pixels, t.cp, ch, 1.0 / t.scale, host.ctypes.data_as(C.POINTER(C.c_float))))
+        _capi.check(self.L.vsr_rt_download_channel(self.h, t.ptr + slot * t.h * t.w * t.cp * 2, t.h * t.w, t.cp, ch, 1.0 / t.scale,
+                                                   host.ctypes.data_as(C.POINTER(C.c_float))))
         return host
 
     @property
@@ -377,13 +380,15 @@ class TextDetector:
     # -------------------------------------------------------------------------------------------- runtime helpers
     def _new(self, c, h, w, perm=None, follow=None) -> _Tensor:
         cp = _r(max(c, 1), 64)
-        return _Tensor(self._rt.alloc(h * w * cp * 2), c, h, w, cp, perm, follow)
+        n = getattr(self, "_n", 1)          # images per launch of the program being compiled
+        return _Tensor(self._rt.alloc(n * h * w * cp * 2), c, h, w, cp, perm, follow, n=n)
 
     def _new_like(self, t: _Tensor) -> _Tensor:
-        return _Tensor(self._rt.alloc(t.pixels * t.cp * 2), t.c, t.h, t.w, t.cp, t.perm)
+        return _Tensor(self._rt.alloc(t.pixels * t.cp * 2), t.c, t.h, t.w, t.cp, t.perm, n=t.n)
 
     # -------------------------------------------------------------------------------------------- graph compiler
-    def _compile(self, H: int, W: int) -> _Compiled:
+    def _compile(self, H: int, W: int, N: int = 1) -> _Compiled:
+        self._n = N
         rt = self._rt
         nodes, params = self._nodes, self._params
         prod = {n.out: n for n in nodes if n.out is not None}
@@ -603,13 +608,13 @@ class TextDetector:
                     perm[lo:lo + p.c] = phys[i] + src
                     lo += p.c
                 y = _Tensor(rt.alloc(parts[0].pixels * _r(off, 64) * 2), total, parts[0].h, parts[0].w, _r(off, 64),
-                            None if np.array_equal(perm, np.arange(total)) else perm)
+                            None if np.array_equal(perm, np.arange(total)) else perm, n=parts[0].n)
                 prog.steps.append(_Concat(parts, [phys[i] for i in range(len(parts))], y, self._new_like))
                 val[n.out] = y
             elif k == "nearest_interp":
                 x = val[n.ins[0]]
                 s = int(round(float((n.attrs.get("scale") or [2.0])[0])))
-                y = _Tensor(rt.alloc(x.pixels * s * s * x.cp * 2), x.c, x.h * s, x.w * s, x.cp, x.perm, follow=x)
+                y = _Tensor(rt.alloc(x.pixels * s * s * x.cp * 2), x.c, x.h * s, x.w * s, x.cp, x.perm, follow=x, n=x.n)
                 prog.steps.append(_Call("upsample", x, y, s))
                 val[n.out] = y
             elif k == "pool2d" and n.attrs.get("adaptive") and n.attrs.get("pooling_type") == "avg":
@@ -617,6 +622,8 @@ class TextDetector:
                 x = val[n.ins[0]]
                 if [int(v) for v in val[n.ins[1]]] != [1, 1] or x.perm is not None:
                     raise _capi.VsrError("only global average pooling of a plain tensor is supported")
+                if x.n != 1:
+                    raise _capi.VsrError("squeeze-and-excitation gates are per image: the mobile detector runs one frame per launch")
 
                 def conv_bias(node):
                     wt = np.asarray(val[node.ins[1]], np.float32)
@@ -697,6 +704,41 @@ class TextDetector:
             if rt.overflow():
                 raise _capi.VsrError("detector activations overflow fp16 even after rescaling")
         return host
+
+    def probability_maps(self, images) -> List[np.ndarray]:
+        """Several same-size frames through ONE launch of the network (the sampled frames of the detection pass, subtitle_detect.py:96-110):
+        the detector's layers are small, so a launch per frame is latency-bound.  NOT yet run on a B200 with more than one image per launch
+        (the direct / depthwise / transposed-conv kernels and the pooling kernels have only been exercised with one): opt-in."""
+        imgs = [np.ascontiguousarray(i, np.uint8) for i in images]
+        if not imgs or any(i.shape != imgs[0].shape or i.ndim != 3 or i.shape[2] != 3 for i in imgs):
+            raise ValueError("expected same-size BGR uint8 images [H,W,3]")
+        if len(imgs) == 1:
+            return [self.probability_map(imgs[0])]
+        N = len(imgs)
+        rh, rw = self.resize_shape(imgs[0].shape[0], imgs[0].shape[1])
+        prog = self._programs.get((N, rh, rw))
+        if prog is None:
+            prog = self._programs[(N, rh, rw)] = self._compile(rh, rw, N)
+        rt = self._rt
+        for j, img in enumerate(imgs):
+            rt.preprocess(img, prog.inp, rh, rw, j)
+        if not prog.calibrated:
+            self._calibrate(prog)
+        else:
+            rt.graph_launch(prog.graph)
+        out = prog.out
+        ch = int(out.perm[0]) if out.perm is not None else 0
+        maps = [rt.download_channel(out, ch, j) for j in range(N)]
+        if rt.overflow():
+            self._calibrate(prog)
+            maps = [rt.download_channel(out, ch, j) for j in range(N)]
+            if rt.overflow():
+                raise _capi.VsrError("detector activations overflow fp16 even after rescaling")
+        return maps
+
+    def predict_batch(self, images):
+        """`predict` for several same-size frames in one launch (see `probability_maps`)."""
+        return [{"dt_polys": db_postprocess(p, i.shape[0], i.shape[1]), "prob_shape": p.shape} for p, i in zip(self.probability_maps(images), images)]
 
     def time_network(self, iters: int = 20) -> float:
         """ms per replay of the recorded network graph of the last-used resolution (input already on the device)."""
