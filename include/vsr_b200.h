@@ -139,6 +139,10 @@ int vsr_rt_conv_create(vsr_rt_t* h, const float* w, const float* bias, int cout,
 /* Per-tensor power-of-two scaling keeps un-normalised activations (the LKPAN neck reaches |x| ~ 1e5) inside fp16: a
  * tensor stores value * s; the layer computes out = acc * alpha + bias * bias_scale with alpha = s_out / s_in and
  * bias_scale = s_out (1, 1 for unscaled tensors).  Every scaled store that leaves fp16 raises the overflow flag. */
+/* a dense stride-1 conv whose fp32 weights are kept as hi + lo fp16 halves (every tap issued twice): ~22-bit weights at fp16 activations,
+ * for layers whose output is limited by weight rounding (the detector's head).  NOT yet run on a B200 (opt-in). */
+int vsr_rt_conv_create_split(vsr_rt_t* h, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw, int pad_t, int pad_l, int dil,
+                             int* layer_id);
 int vsr_rt_conv(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int W, uint64_t out_ptr, int out_pitch, int out_coff, int relu,
                 float alpha, float bias_scale);
 /* vsr_rt_conv whose output tensor [out_h, out_w] is the window starting at (crop_t, crop_l) of the computed H x W grid:

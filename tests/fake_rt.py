@@ -14,7 +14,7 @@ def _r8(x):
     return (x + 7) // 8 * 8
 
 
-_NOT_OPS = {"alloc", "upload_f32", "upload_bytes", "upload_to", "upload_ints", "download", "download_channel", "download_f32", "capture_begin",
+_NOT_OPS = {"conv_create_split", "alloc", "upload_f32", "upload_bytes", "upload_to", "upload_ints", "download", "download_channel", "download_f32", "capture_begin",
             "capture_end", "graph_launch", "graph_destroy", "conv_create", "se_create", "overflow", "absmax", "close", "sync", "zero", "launch_count"}
 
 
@@ -156,6 +156,19 @@ class FakeRuntime:
         self.layers.append(dict(w=torch.from_numpy(w), b=torch.from_numpy(np.array(bias, np.float32)), cout=cout, cin=cin, kh=kh, kw=kw,
                                 stride=stride, pad_t=pad_t, pad_l=pad_l, dil=dil, groups=groups, transposed=transposed))
         return len(self.layers) - 1
+
+    def conv_create_split(self, w, bias, cout, cin, cin_pitch, kh, kw, pad_t, pad_l, dil):
+        """hi + lo fp16 weights: in fp16 mode the layer sees fp16(w) + fp16(w - fp16(w)), otherwise w"""
+        w = np.array(w, np.float32)
+        assert cout >= 8 and cout % 8 == 0 and cin >= 16 and 2 * kh * kw <= 81
+        if self.fp16:
+            hi = w.astype(np.float16).astype(np.float32)
+            w = hi + (w - hi).astype(np.float16).astype(np.float32)
+        f, self.fp16 = self.fp16, False
+        try:
+            return self.conv_create(w, bias, cout, cin, cin_pitch, kh, kw, 1, pad_t, pad_l, dil, 1, False)
+        finally:
+            self.fp16 = f
 
     def conv_ex(self, lid, x, y, relu, out_coff=0, crop=None):
         """crop None: a plain conv of any kernel family (possibly into a channel slice); (top, left): the cropped-store path."""

@@ -86,6 +86,7 @@ _PROTOS = {
     "vsr_rt_launch_count": (C.c_int64, [C.c_void_p]),
     "vsr_rt_conv_create": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_int, _i32p]),
+    "vsr_rt_conv_create_split": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "vsr_rt_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,
                               C.c_float]),
     "vsr_rt_conv_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float,

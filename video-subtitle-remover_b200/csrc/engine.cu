@@ -263,24 +263,32 @@ static void pack_conv_s2d(ConvLayer& L, const float* w, const float* bias, int c
 // General stride-1 dense conv for the graph runtime: kernel kh x kw, dilation, explicit top/left padding; the
 // input tensor has `cin_pitch` (multiple of 64) channels of which the first `cin` are real.
 static void pack_conv_general(ConvLayer& L, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw,
-                              int dil, int pad_t, int pad_l, cudaStream_t s) {
+                              int dil, int pad_t, int pad_l, cudaStream_t s, bool split = false) {
   REQUIRE(cin_pitch % 8 == 0 && cin <= cin_pitch, "input channel pitch must be a multiple of 8 (16-byte TMA strides)");
-  REQUIRE(kh * kw <= 81, "kernels up to 81 taps");
+  const int taps = kh * kw;
+  REQUIRE((split ? 2 : 1) * taps <= 81, "kernels up to 81 taps (40 with split weights)");
   const int cin_k = (cin + 63) / 64 * 64;  // K extent per tap: whole 64-channel TMA boxes (weights beyond cin are zero)
   REQUIRE(cin_k <= cin_pitch || cin_pitch % 64 == 0, "a channel slice must end on the tensor's 64-channel grid");
-  L.cin = cin_k; L.pitch = cin_pitch; L.cout = cout; L.cout_pad = pad_cout(cout); L.ntaps = kh * kw; L.K = kh * kw * cin_k;
+  // split: every tap appears twice with the same offset, once with hi = fp16(w) and once with lo = fp16(w - hi): the tensor cores then see
+  // the weight to ~22 bits while the activations stay fp16 (the detector's head is limited by weight rounding)
+  L.cin = cin_k; L.pitch = cin_pitch; L.cout = cout; L.cout_pad = pad_cout(cout); L.ntaps = (split ? 2 : 1) * taps; L.K = L.ntaps * cin_k;
   L.bn = L.cout_pad < 256 ? L.cout_pad : 256;
   std::vector<__half> hw((size_t)L.cout_pad * L.K, __float2half(0.f));
   for (int co = 0; co < cout; ++co)
     for (int ci = 0; ci < cin; ++ci)
       for (int ky = 0; ky < kh; ++ky)
-        for (int kx = 0; kx < kw; ++kx)
-          hw[(size_t)co * L.K + (size_t)(ky * kw + kx) * cin_k + ci] = __float2half_rn(w[(((size_t)co * cin + ci) * kh + ky) * kw + kx]);
-  for (int ky = 0; ky < kh; ++ky)
-    for (int kx = 0; kx < kw; ++kx) {
-      L.dy[ky * kw + kx] = (int8_t)(ky * dil - pad_t);
-      L.dx[ky * kw + kx] = (int8_t)(kx * dil - pad_l);
-    }
+        for (int kx = 0; kx < kw; ++kx) {
+          const float v = w[(((size_t)co * cin + ci) * kh + ky) * kw + kx];
+          const __half hi = __float2half_rn(v);
+          hw[(size_t)co * L.K + (size_t)(ky * kw + kx) * cin_k + ci] = hi;
+          if (split) hw[(size_t)co * L.K + (size_t)(taps + ky * kw + kx) * cin_k + ci] = __float2half_rn(v - __half2float(hi));
+        }
+  for (int rep = 0; rep < (split ? 2 : 1); ++rep)
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) {
+        L.dy[rep * taps + ky * kw + kx] = (int8_t)(ky * dil - pad_t);
+        L.dx[rep * taps + ky * kw + kx] = (int8_t)(kx * dil - pad_l);
+      }
   std::vector<float> hb(L.cout_pad, 0.f);
   for (int i = 0; i < cout; ++i) hb[i] = bias ? bias[i] : 0.f;
   upload(L.w, hw, s);
@@ -2335,6 +2343,21 @@ int vsr_rt_graph_destroy(vsr_rt_t* h, int graph_id) {
       cudaGraphExecDestroy(h->graphs[graph_id]);
       h->graphs[graph_id] = nullptr;
     }
+  });
+}
+
+int vsr_rt_conv_create_split(vsr_rt_t* h, const float* w, const float* bias, int cout, int cin, int cin_pitch, int kh, int kw, int pad_t, int pad_l, int dil,
+                             int* layer_id) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(w && layer_id && cout >= 8 && cout % 8 == 0 && cin >= 16 && cin_pitch >= cin && cin_pitch % 8 == 0, "split-weight convs are dense tensor-core convs");
+    auto L = std::make_unique<RtLayer>();
+    L->cin = cin; L->cout = cout; L->cin_pitch = cin_pitch; L->kh = kh; L->kw = kw; L->stride = 1; L->pad_t = pad_t; L->pad_l = pad_l;
+    L->kind = RtLayer::DENSE;
+    pack_conv_general(L->tc, w, bias, cout, cin, cin_pitch, kh, kw, dil, pad_t, pad_l, h->ctx.stream, true);
+    L->cout_pitch = cout;
+    *layer_id = (int)h->layers.size();
+    h->layers.push_back(std::move(L));
   });
 }
 

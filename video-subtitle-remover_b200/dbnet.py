@@ -130,14 +130,26 @@ class _Tensor:
 
 
 class _Conv:
-    """conv (+ folded bias / BN / ReLU): stored out = acc * (s_out / s_in) + bias * s_out."""
+    """conv (+ folded bias / BN / ReLU): stored out = acc * (s_out / (s_in * s_w)) + bias * s_out, where the layer's weights were packed
+    multiplied by the power of two s_w (see `_weight_scale`)."""
     rescalable = True
 
-    def __init__(self, lid, x, y, relu):
-        self.lid, self.x, self.y, self.relu = lid, x, y, relu
+    def __init__(self, lid, x, y, relu, wscale=1.0):
+        self.lid, self.x, self.y, self.relu, self.wscale = lid, x, y, relu, wscale
 
     def run(self, rt):
-        rt.conv(self.lid, self.x, self.y, self.relu, self.y.scale / self.x.scale, self.y.scale)
+        rt.conv(self.lid, self.x, self.y, self.relu, self.y.scale / (self.x.scale * self.wscale), self.y.scale)
+
+
+def _weight_scale(w: np.ndarray) -> float:
+    """Power of two that lifts a layer's weights out of fp16's subnormal range.  The convs behind the un-normalised neck fold a tiny
+    batch-norm scale (their inputs reach 1e5): weights of 1e-6 .. 1e-8 round to fp16 subnormals or to zero — that, not ordinary rounding,
+    was the detector's parity limit (max |dp| 0.3 -> 0.06 in the fp16 simulation).  The inverse goes into the epilogue multiplier."""
+    m = float(np.abs(w).max())
+    if m == 0.0 or m >= 2.0 ** -6:
+        return 1.0
+    return float(2.0 ** -int(np.floor(np.log2(m))))
+
 
 
 class _Add:
@@ -282,6 +294,15 @@ class _DeviceRuntime:
                                               pad_t, pad_l, dil, groups, 1 if transposed else 0, C.byref(lid)))
         return int(lid.value)
 
+    def conv_create_split(self, w, bias, cout, cin, cin_pitch, kh, kw, pad_t, pad_l, dil) -> int:
+        w = np.ascontiguousarray(w, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        lid = C.c_int32()
+        f32p = C.POINTER(C.c_float)
+        _capi.check(self.L.vsr_rt_conv_create_split(self.h, w.ctypes.data_as(f32p), bias.ctypes.data_as(f32p), cout, cin, cin_pitch, kh, kw, pad_t, pad_l, dil,
+                                                    C.byref(lid)))
+        return int(lid.value)
+
     def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0):
         _capi.check(self.L.vsr_rt_conv(self.h, lid, x.ptr, x.n, x.h, x.w, y.ptr, y.cp, 0, relu, alpha, bias_scale))
 
@@ -362,7 +383,11 @@ class _DeviceRuntime:
 class TextDetector:
     """Stand-in for `paddleocr.TextDetection(model_name, model_dir, device=...)` (subtitle_detect.py:47-52)."""
 
-    def __init__(self, model_dir: str, device="cuda:0", model_name: Optional[str] = None, runtime=None):
+    def __init__(self, model_dir: str, device="cuda:0", model_name: Optional[str] = None, runtime=None, precise_weights: Optional[bool] = None):
+        """precise_weights: keep the weights of the dense stride-1 convs (up to 40 taps) as hi + lo fp16 halves.  The detector's parity is
+        limited by WEIGHT rounding in its head (fp32 weights + fp16 activations: max |dp| 0.03 instead of 0.34 in the fp16 simulation,
+        profiles/fp16_forecast_r1.md); the path has not run on a B200 yet, so it is opt-in (argument or VSR_DET_PRECISE_WEIGHTS=1)."""
+        self.precise_weights = (os.environ.get("VSR_DET_PRECISE_WEIGHTS") == "1") if precise_weights is None else bool(precise_weights)
         self.model_dir, self.model_name = model_dir, model_name
         self._nodes, self._params = _load_program(model_dir)
         self._rt = runtime if runtime is not None else _DeviceRuntime(device)
@@ -519,8 +544,13 @@ class TextDetector:
             else:
                 oh, ow = x.h, x.w
             y = self._new(cout, oh, ow)
-            lid = rt.conv_create(w, bias, int(bias.size), int(cin_eff), x.cp, kh, kw, stride, pad_t, pad_l, dil, groups, transposed)
-            prog.steps.append(_Conv(lid, x, y, relu))
+            wscale = _weight_scale(w) if (groups == 1 and not transposed and cin_eff >= 16 and bias.size >= 8) else 1.0   # tensor-core layers hold fp16 weights
+            w = w * np.float32(wscale)
+            if self.precise_weights and groups == 1 and not transposed and stride == 1 and cin_eff >= 16 and bias.size >= 8 and 2 * kh * kw <= 81:
+                lid = rt.conv_create_split(w, bias, int(bias.size), int(cin_eff), x.cp, kh, kw, pad_t, pad_l, dil)
+            else:
+                lid = rt.conv_create(w, bias, int(bias.size), int(cin_eff), x.cp, kh, kw, stride, pad_t, pad_l, dil, groups, transposed)
+            prog.steps.append(_Conv(lid, x, y, relu, wscale))
             val[cur] = y
 
         def channel_vectors(x: _Tensor, mul, add):
