@@ -1,0 +1,68 @@
+// Host stand-ins for the pieces of csrc/engine.cu that the extracted vsr_rt_* entry points of the ProPainter path lean on (error plumbing, the
+// runtime handle, the few CUDA runtime calls).  tests/emu/make_abi_emu.py pastes the REAL entry points below this prelude.  TEST INFRASTRUCTURE ONLY.
+#pragma once
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include "cuda_emu.h"
+#include "../../include/vsr_b200.h"              // the extracted definitions must agree with the shipped prototypes
+#include "../../video-subtitle-remover_b200/csrc/pp_ops.cuh"
+
+typedef int cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
+
+namespace vsr {
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline thread_local std::string g_err;
+#define CK(expr) do { if ((expr) != cudaSuccess) throw Error(VSR_ERR_CUDA, #expr); } while (0)
+#define REQUIRE(cond, msg) do { if (!(cond)) throw Error(VSR_ERR_ARG, std::string(msg) + " [" #cond "]"); } while (0)
+template <class F>
+static int guarded(F&& f) {
+  try { f(); return VSR_OK; }
+  catch (const Error& e) { g_err = e.what(); return e.code; }
+  catch (const std::exception& e) { g_err = e.what(); return VSR_ERR_STATE; }
+}
+struct DevBuf {
+  void* p = nullptr;
+  size_t n = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= n) return;
+    std::free(p);
+    p = std::calloc(bytes + 256, 1);
+    n = bytes;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+  ~DevBuf() { std::free(p); }
+};
+struct Ctx { int device = 0; cudaStream_t stream = 0; long launches = 0; };
+static unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
+static inline bool emu_lockstep(const char* kernel) {
+  const std::string k(kernel);
+  return k == "pp_instnorm_stats_kernel" || k == "pp_layernorm_kernel" || k == "pp_window_attention_kernel";
+}
+}  // namespace vsr
+struct vsr_rt {
+  vsr::Ctx ctx;
+  vsr::DevBuf frames8, norm_stats, plane;
+  bool capturing = false;
+};
+namespace vsr {
+static void rt_check(vsr_rt* h) { if (!h) throw Error(VSR_ERR_ARG, "null runtime"); }
+static void rt_sync(vsr_rt*) {}
+}
+using namespace vsr;
+#define EMU_LAUNCH(kernel, grid, threads, ...) emu_launch(dim3(grid), (unsigned)(threads), emu_lockstep(#kernel), [&] { kernel(__VA_ARGS__); })
+extern "C" {
+vsr_rt* emu_rt_create() { return new vsr_rt(); }
+void emu_rt_destroy(vsr_rt* h) { delete h; }
+const char* vsr_last_error(void) { return g_err.c_str(); }
+long emu_launches(vsr_rt* h) { return h->ctx.launches; }
+}
