@@ -20,6 +20,7 @@
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 #define __shared__ static
+#define __grid_constant__
 
 struct dim3 {
   unsigned x = 1, y = 1, z = 1;

@@ -123,7 +123,7 @@ struct CorrLevels {
 // CorrBlock.__call__ (corr.py:29-50): for source pixel p of pair n at coords1 = (x + flow.x, y + flow.y): 4 levels x 9x9 bilinear
 // samples (zeros outside, align_corners=True) of its correlation map at coords1 / 2^l + delta.  The reference adds the FIRST
 // meshgrid component (the row offset list) to x: sample (i, j) sits at (x + d[i], y + d[j]); kept.  out [P][pitch], channel l*81 + i*9 + j.
-__global__ void __launch_bounds__(256) pp_corr_lookup_kernel(CorrLevels lv, const float* __restrict__ flow, int h, int w, size_t pixels,
+__global__ void __launch_bounds__(256) pp_corr_lookup_kernel(const __grid_constant__ CorrLevels lv, const float* __restrict__ flow, int h, int w, size_t pixels,
                                                              __half* __restrict__ out, int pitch) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pixels * 324) return;
