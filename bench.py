@@ -454,6 +454,78 @@ def run_config4(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_propainter(args, rank, world, local):
+    """Secondary line: ProPainter (BASELINE config 3 / SURVEY §8a P1-P7) through `PropainterInpaint.__call__` on a 720p clip: the 240x1280
+    strip around the subtitle goes through RAFT, flow completion, image propagation and the generator, `--pp-frames` frames per call
+    (<= sub_video_length = 80, one reference sub-video).  STATUS: the device pipeline had not run on a B200 when round 1 ended (DESIGN.md §7);
+    this leg exists so that the first GPU session of round 2 measures it with the same contract as the other workloads.  There is no separate
+    device-resident leg yet (flows take a host round trip between RAFT and the completion network): `value` is the same end-to-end rate."""
+    import torch
+    import torch.distributed as dist
+    from oracle import sttn_oracle as O
+    from vsr_b200.propainter_inpaint import PropainterInpaint
+
+    mdir = os.path.join(ROOT, "weights", "propainter")
+    need = ["raft-things.pth", "recurrent_flow_completion.pth", "ProPainter.pth"]
+    if not all(os.path.exists(os.path.join(mdir, f)) for f in need):
+        raise SystemExit("bench.py --workload propainter needs weights/propainter/{raft-things,recurrent_flow_completion,ProPainter}.pth "
+                         "(tools/stage_weights.py; drop weights/propainter from .gpurunignore so that they travel)")
+    Hp, Wp, T = 720, 1280, args.pp_frames
+    frames = O.synthetic_clip(T, Hp, Wp, seed=300 + rank)
+    mask = O.default_mask(Hp, Wp)
+    eng = PropainterInpaint(torch.device("cuda", local), mdir)
+    for _ in range(max(args.warmup, 3)):
+        eng(frames, mask)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng._rt.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng(frames, mask)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    launches = eng._rt.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0].item())
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import propainter_gen_oracle as G
+        from oracle import raft_oracle as R
+        from oracle import rfc_oracle as C
+
+        w = {"raft": R.load_weights(os.path.join(mdir, need[0])), "rfc": C.load_weights(os.path.join(mdir, need[1])), "gen": G.load_weights(os.path.join(mdir, need[2]))}
+        c0 = time.perf_counter()
+        G.propainter_call(w, frames[:4], mask)
+        cpu = {"value": 4 / (time.perf_counter() - c0), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "4 of the 720p frames through the chained oracle (torch fp32 restatement, equal to the unmodified reference's frames)"}
+    if rank == 0:
+        from vsr_b200 import propainter_tools as PT
+
+        (y0, y1, x0, x1), = PT.strip_areas(Wp, Hp, mask)
+        sh, sw = y1 - y0, x1 - x0
+        n = world * args.steps * T
+        print(json.dumps({
+            "metric": "inpainted frames/sec at 720p (ProPainter)", "value": n / e2e_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": e2e_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic 720p clip; reference ProPainter / RAFT / flow-completion weights",
+            "config": {"workload": f"ProPainter on a {T}-frame 720p synthetic clip with optical-flow completion (BASELINE config 3, one sub-video per call)",
+                       "frame": [Hp, Wp], "frames_per_step": T, "strip": [sh, sw], "l2": "inputs larger than L2 (strip frames + feature maps)"},
+            "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": T * sh * sw * 3 + sh * sw, "d2h_bytes_per_step": T * sh * sw * 3,
+                    "api": "PropainterInpaint.__call__(frames, mask), synchronous, copy semantics"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": None, "cpu_baseline": cpu,
+            "status": "bring-up line: no device-resident leg and no roofline yet (DESIGN.md §7)"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -461,9 +533,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det", "dbnet", "lama", "config4"],
+    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det", "dbnet", "lama", "config4", "propainter"],
                     help="sttn-auto = BASELINE config 2 (the contract line); sttn-det / dbnet = the inpaint / detection halves of config 4; "
                          "lama = the big-lama model of config 1 on 1080p strips")
+    ap.add_argument("--pp-frames", type=int, default=40, help="frames per call of the propainter workload (<= 80)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -497,6 +570,9 @@ def main():
         return
     if args.workload == "config4":
         run_config4(args, rank, world, local)
+        return
+    if args.workload == "propainter":
+        run_propainter(args, rank, world, local)
         return
     if args.workload == "sttn-det":
         return run_det(args, rank, world, local)
