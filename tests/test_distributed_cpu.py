@@ -102,3 +102,92 @@ def test_sampled_frames_and_batches_partition():
     for n, mb, world in ((300, 46, 4), (50, 46, 2), (7, 46, 3)):
         spans = sorted(b for r in range(world) for b in batches_for_rank(n, mb, r, world))
         assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+# ---- ProPainter: one sub-video sharded over two ranks (RAFT clips + generator windows round-robin, two exchanges) -----------------
+def _exchange_worker(rank, world, port):
+    import numpy as np
+    from vsr_b200.distributed import Shard
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = Shard(rank, world)
+        mine = {i: np.full((i + 1, 3), i, np.float32 if i % 2 else np.uint8) for i in range(5) if sh.owns(i)}
+        got = sh.exchange(mine)
+        assert sorted(got) == list(range(5))
+        for i, a in got.items():
+            assert a.shape == (i + 1, 3) and a.dtype == (np.float32 if i % 2 else np.uint8) and (a == i).all()
+        assert sh.exchange({}) == {}                                   # nothing to exchange is not a hang
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_exchange_two_processes_gloo():
+    from vsr_b200.distributed import Shard
+    from vsr_b200.propainter_inpaint import flow_clips
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_exchange_worker, args=(2, port), nprocs=2, join=True)
+    assert Shard(0, 1).exchange({3: 1}) == {3: 1}
+    with pytest.raises(ValueError):
+        Shard(2, 2)
+    # propainter_inpaint.py:209-236: clip length by width, clips after the first start one frame early
+    assert flow_clips(7, 192) == [(0, 7)] and flow_clips(30, 640) == [(0, 12), (11, 24), (23, 30)]
+    assert flow_clips(10, 1280) == [(0, 4), (3, 8), (7, 10)] and flow_clips(5, 1920) == [(0, 2), (1, 4), (3, 5)]
+    for n, w in ((30, 640), (80, 1280), (9, 1920)):                  # every consecutive pair is covered exactly once
+        pairs = [p for a, b in flow_clips(n, w) for p in range(a, b - 1)]
+        assert pairs == list(range(n - 1))
+
+
+_PP_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "weights", "propainter")
+
+
+def _propainter_worker(rank, world, port, out_dir):
+    import sys
+
+    import numpy as np
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.join(here, "..", "tools")]
+    from fake_rt import FakeRuntime
+    from make_golden_propainter import inputs
+    from vsr_b200.distributed import Shard
+    from vsr_b200.propainter_inpaint import PropainterInpaint
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        frames, mask = inputs()[:2]                                   # 7 frames: windows at 0 and 5; RAFT clips of 4 -> (0,4) (3,7)
+        eng = PropainterInpaint("cuda:0", _PP_DIR, runtime=FakeRuntime())
+        eng.raft_clip = 4
+        out = np.stack(eng.inpaint(frames, mask, Shard(rank, world)))
+        np.save(os.path.join(out_dir, f"sharded_{rank}.npy"), out)
+        if rank == 0:                                                 # the unsharded result of the same engine, for bit-exactness
+            np.save(os.path.join(out_dir, "single.npy"), np.stack(eng.inpaint(frames, mask)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(not all(os.path.exists(os.path.join(_PP_DIR, f)) for f in ("ProPainter.pth", "raft-things.pth", "recurrent_flow_completion.pth")),
+                    reason="ProPainter weights not staged under weights/propainter")
+def test_propainter_sub_video_sharded_over_two_ranks_equals_single_rank(tmp_path):
+    import numpy as np
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_propainter_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    single = np.load(tmp_path / "single.npy")
+    a, b = np.load(tmp_path / "sharded_0.npy"), np.load(tmp_path / "sharded_1.npy")
+    assert np.array_equal(a, b) and np.array_equal(a, single)
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "propainter_real.npz"))["comp"]
+    d = np.abs(a.astype(np.int32) - golden)
+    assert d.max() <= 3 and (d > 0).mean() < 0.02

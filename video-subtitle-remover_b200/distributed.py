@@ -90,3 +90,40 @@ def batches_for_rank(n_items: int, max_batch: int, rank: int, world: int) -> Lis
             out.append((s, s + len(b)))
         s += len(b)
     return out
+
+
+# ---- ProPainter (BASELINE config 5): one sub-video over several GPUs -------------------------------------------------------------
+class Shard:
+    """rank / world plus the one exchange the sharded ProPainter path needs (propainter_inpaint.PropainterInpaint.inpaint(shard=...)):
+    units (RAFT clips, generator windows) are dealt round-robin, and `exchange` turns the per-rank {unit index: ndarray} dictionaries
+    into the union on every rank.  Arrays travel as torch.distributed broadcasts from their owner — through device memory over NVLink
+    with the NCCL backend, through host memory with gloo (the CPU tests); only their shapes go through the object channel."""
+
+    def __init__(self, rank: int, world: int):
+        if not 0 <= rank < world:
+            raise ValueError("rank out of range")
+        self.rank, self.world = rank, world
+
+    def owns(self, unit: int) -> bool:
+        return unit % self.world == self.rank
+
+    def exchange(self, mine: dict) -> dict:
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return dict(mine)
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("Shard.exchange needs an initialised torch.distributed process group")
+        metas = [None] * self.world
+        dist.all_gather_object(metas, [(k, tuple(v.shape), v.dtype.str) for k, v in sorted(mine.items())])
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        out = {}
+        for src, meta in enumerate(metas):
+            for k, shape, dt in meta:
+                host = np.ascontiguousarray(mine[k]) if src == self.rank else np.empty(shape, np.dtype(dt))
+                t = torch.from_numpy(host).to(device)
+                dist.broadcast(t, src=src)
+                out[k] = t.cpu().numpy() if src != self.rank or device.type != "cpu" else host
+        return out

@@ -25,6 +25,15 @@ from .propainter_generator import Generator, _GenRuntime
 from .raft_flow import ITERS, RaftFlow
 
 
+def flow_clips(n_frames: int, width: int, clip=None) -> List[tuple]:
+    """(first, end) frame ranges RAFT runs on (propainter_inpaint.py:209-236): clips of 12 / 8 / 4 / 2 frames by width, every clip after the
+    first starting one frame early so that consecutive clips share the pair in between."""
+    clip = clip or (12 if width <= 640 else 8 if width <= 720 else 4 if width <= 1280 else 2)
+    if n_frames <= clip:
+        return [(0, n_frames)]
+    return [(max(f - 1, 0), min(n_frames, f + clip)) for f in range(0, n_frames, clip)]
+
+
 class PropainterInpaint:
     def __init__(self, device, model_dir, sub_video_length=80, use_fp16=True, runtime=None):
         """propainter_inpaint.py:139-190.  `use_fp16` is accepted for signature compatibility: the device path multiplies in fp16
@@ -36,22 +45,24 @@ class PropainterInpaint:
         self.model = Generator(os.path.join(model_dir, "ProPainter.pth"), runtime=self._rt)
         self._arena = _Arena(self._rt)
         self.raft_iter = ITERS
+        self.raft_clip = None          # frames per RAFT clip; None = by width like the reference (:209-216)
 
-    def _flows(self, frames: Sequence[np.ndarray]):
-        """propainter_inpaint.py:209-236: RAFT on clips of 12 / 8 / 4 / 2 frames by width, each clip overlapping the previous by one frame."""
-        T, W = len(frames), frames[0].shape[1]
-        clip = 12 if W <= 640 else 8 if W <= 720 else 4 if W <= 1280 else 2
-        if T <= clip:
-            return self.fix_raft(frames, self.raft_iter)
-        ff, fb = [], []
-        for f in range(0, T, clip):
-            a, b = self.fix_raft(frames[max(f - 1, 0):min(T, f + clip)], self.raft_iter)
-            ff.append(a)
-            fb.append(b)
-        return np.concatenate(ff), np.concatenate(fb)
+    def _flows(self, frames: Sequence[np.ndarray], shard=None):
+        """propainter_inpaint.py:209-236: RAFT on clips of 12 / 8 / 4 / 2 frames by width, each clip overlapping the previous by one frame.
+        Clips are independent (a flow depends on its two frames only): with a `shard` every rank runs RAFT on its share of the clips and
+        the flows are exchanged, so that flow completion sees the whole sequence on every rank."""
+        clips = flow_clips(len(frames), frames[0].shape[1], self.raft_clip)
+        mine = {i: np.stack(self.fix_raft(frames[a:b], self.raft_iter)) for i, (a, b) in enumerate(clips) if shard is None or shard.owns(i)}
+        parts = mine if shard is None else shard.exchange(mine)
+        return np.concatenate([parts[i][0] for i in range(len(clips))]), np.concatenate([parts[i][1] for i in range(len(clips))])
 
-    def inpaint(self, frames: Sequence[np.ndarray], mask: np.ndarray) -> List[np.ndarray]:
-        """propainter_inpaint.py:192-361: BGR uint8 frames [H,W,3] (H, W multiples of 8, >= 128) + uint8 mask -> BGR uint8 frames."""
+    def inpaint(self, frames: Sequence[np.ndarray], mask: np.ndarray, shard=None) -> List[np.ndarray]:
+        """propainter_inpaint.py:192-361: BGR uint8 frames [H,W,3] (H, W multiples of 8, >= 128) + uint8 mask -> BGR uint8 frames.
+
+        `shard` (vsr_b200.distributed.Shard) splits one sub-video over the ranks of a process group (BASELINE config 5): RAFT clips and
+        generator windows are dealt round-robin; flow completion and image propagation are sequential over the frames and run replicated;
+        two exchanges (flows after RAFT, the u8 window predictions before the blend) make every rank return the same frames, identical
+        to the unsharded result — windows overlap and P7's 0.5 / 0.5 blend is order dependent, so the blend always runs in schedule order."""
         frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
         T, (H, W) = len(frames), frames[0].shape[:2]
         if T > self.sub_video_length:
@@ -60,7 +71,7 @@ class PropainterInpaint:
             raise _capi.VsrError("ProPainter needs at least two frames (the reference routes single frames to LAMA, main.py:220)")
         rt = self._rt
         flow_masks, masks_dilated = PT.read_mask(mask, T)
-        gf, gb = self._flows(frames)
+        gf, gb = self._flows(frames, shard)
         self._arena.begin(("inpaint", T, H, W))
         up = lambda arr: (lambda p: (rt.upload_to(p, arr), p)[1])(self._arena.alloc(max(np.ascontiguousarray(arr).nbytes, 16)))   # noqa: E731
         ff_dev, fb_dev = up(np.ascontiguousarray(gf, np.float32)), up(np.ascontiguousarray(gb, np.float32))
@@ -72,24 +83,34 @@ class PropainterInpaint:
         comp: List = [None] * T
         binary = (masks_dilated[0] > 0).astype(np.uint8)[None, :, :, None]
         rgb = [np.ascontiguousarray(f[:, :, ::-1]) for f in frames]
-        for nb, refs in PT.window_schedule(T, self.sub_video_length):
-            ids = nb + refs
-            enc, _ = self.model.encode_and_propagate(state, mask_dev, ids, pf_dev, pb_dev, len(nb))
+        schedule = PT.window_schedule(T, self.sub_video_length)
+        preds = {}
+        for wi, (nb, refs) in enumerate(schedule):
+            if shard is not None and not shard.owns(wi):
+                continue
+            enc, _ = self.model.encode_and_propagate(state, mask_dev, nb + refs, pf_dev, pb_dev, len(nb))
             pred = self.model.transform_and_decode(enc, len(nb), masks_dilated[0], H, W)
-            PT.composite(comp, pred, np.repeat(binary, len(nb), 0), rgb, nb)
+            if shard is None:
+                PT.composite(comp, pred, np.repeat(binary, len(nb), 0), rgb, nb)
+            else:
+                preds[wi] = pred
+        if shard is not None:
+            preds = shard.exchange(preds)
+            for wi, (nb, _) in enumerate(schedule):
+                PT.composite(comp, preds[wi], np.repeat(binary, len(nb), 0), rgb, nb)
         return [np.ascontiguousarray(c[:, :, ::-1]) for c in comp]
 
-    def __call__(self, input_frames: List[np.ndarray], input_mask: np.ndarray) -> List[np.ndarray]:
+    def __call__(self, input_frames: List[np.ndarray], input_mask: np.ndarray, shard=None) -> List[np.ndarray]:
         """propainter_inpaint.py:363-418: strips (heights multiples of 8) at native resolution, the first frame's mask for the whole batch,
         every strip replaced whole; the input frames are not modified."""
         mask = input_mask if input_mask.ndim == 2 else input_mask[:, :, 0]
         H, W = mask.shape[:2]
         out = [f.copy() for f in input_frames]
         for (y0, y1, x0, x1) in PT.strip_areas(W, H, mask):
-            comps = self.inpaint([f[y0:y1, x0:x1] for f in out], mask[y0:y1, x0:x1])
+            comps = self.inpaint([f[y0:y1, x0:x1] for f in out], mask[y0:y1, x0:x1], shard)
             for f, c in zip(out, comps):
                 f[y0:y1, x0:x1] = c
         return out
 
 
-__all__ = ["PropainterInpaint"]
+__all__ = ["PropainterInpaint", "flow_clips"]
