@@ -26,7 +26,7 @@ struct dim3 {
   unsigned x = 1, y = 1, z = 1;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
-struct uint4 { unsigned x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };      // 16-byte aligned like on the device: -fsanitize=alignment then flags a misaligned vector access
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
@@ -76,7 +76,7 @@ static inline float __half2float(__half h) {
   std::memcpy(&f, &x, 4);
   return f;
 }
-struct __half2 { __half x, y; };
+struct alignas(4) __half2 { __half x, y; };
 static inline float2 __half22float2(__half2 h) { return float2{__half2float(h.x), __half2float(h.y)}; }
 static inline __half2 __floats2half2_rn(float a, float b) { __half2 r; r.x = __float2half_rn(a); r.y = __float2half_rn(b); return r; }
 

@@ -36,7 +36,7 @@ def backend():
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
         os.makedirs(build, exist_ok=True)
         subprocess.run([sys.executable, srcs[0], os.path.join(CSRC, "engine.cu"), gen], check=True)
-        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-I", os.path.join(EMU, "stubs"), "-I", EMU, gen, "-o", out], check=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", os.path.join(EMU, "stubs"), "-I", EMU, gen, "-o", out], check=True)
     L = C.CDLL(out)
     for name, (res, args) in _capi._PROTOS.items():          # the shipped prototypes, applied to the host build of the same entry points
         if hasattr(L, name):
