@@ -18,7 +18,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 #define __grid_constant__
 

@@ -667,14 +667,20 @@ __global__ void __launch_bounds__(256) pp_pool4_kernel(const __half* __restrict_
 //                     concatenation tl | tr | bl | br, each in window order) and all pooled tokens of that frame (kp / vp [T][ph][pw][C]);
 //   unmasked window : the 45 tokens of the same window and the same frame only.
 // torch.roll(k, (sy, sx)) puts token ((Y - sy) mod Hn, (X - sx) mod Wn) at (Y, X); the four shifts are (-eh,-ew), (-eh,+ew), (+eh,-ew), (+eh,+ew).
-// Thread = (query, quarter of the 128 head dims); online softmax in fp32; scale 1/sqrt(128).
+// Thread = (query, quarter of the 128 head dims); online softmax in fp32; scale 1/sqrt(128).  Keys and values of the head go through
+// shared memory in tiles of PP_KT rows, loaded once per block with 16-byte accesses and converted to fp32 there (every row is consumed by
+// all 45 queries: straight from global memory that is 45 x 64 two-byte loads per row and thread quarter).  Reads of a tile are warp
+// broadcasts (the 8 queries of a warp read the same 4 segments), so the loop is bound by its 64 FMAs per key and thread.
 #define PP_WH 5
 #define PP_WW 9
 #define PP_WT (PP_WH * PP_WW)
+#define PP_KT 32
 __global__ void __launch_bounds__(192) pp_window_attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
                                                                   const __half* __restrict__ kp, const __half* __restrict__ vp, int T, int Hn, int Wn, int C,
                                                                   int ph, int pw, const int* __restrict__ valid_ind, int n_valid, const int* __restrict__ t_ind,
                                                                   int n_tind, const int* __restrict__ win_masked, __half* __restrict__ out) {
+  __shared__ __align__(16) float ks[PP_KT][128];
+  __shared__ __align__(16) float vs[PP_KT][128];
   const int nww = Wn / PP_WW;
   const int win = blockIdx.x, head = blockIdx.y, tq = blockIdx.z;
   const int wy0 = (win / nww) * PP_WH, wx0 = (win % nww) * PP_WW;
@@ -682,13 +688,24 @@ __global__ void __launch_bounds__(192) pp_window_attention_kernel(const __half* 
   const bool active = qi < PP_WT;
   const int eh = (PP_WH + 1) / 2, ew = (PP_WW + 1) / 2;
   const size_t plane = (size_t)Hn * Wn;
-  const int c0 = head * 128 + part * 32;
+  const int ch = head * 128;
   float qv[32], acc[32];
   float mx = -1e30f, den = 0.f;
-  {   // idle threads (queries 45..47) run along with zero queries so that the warp shuffles below stay convergent; they never store
-    const __half* src = q + (((size_t)tq * Hn + wy0 + (active ? qi / PP_WW : 0)) * Wn + wx0 + (active ? qi % PP_WW : 0)) * C + c0;
+  {   // idle threads (queries 45..47) run along with zero queries: they take part in the tile loads, the barriers and the shuffles, and never store
+    const __half* src = q + (((size_t)tq * Hn + wy0 + (active ? qi / PP_WW : 0)) * Wn + wx0 + (active ? qi % PP_WW : 0)) * C + ch + part * 32;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) { qv[d] = active ? __half2float(src[d]) : 0.f; acc[d] = 0.f; }
+    for (int d8 = 0; d8 < 4; ++d8) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + d8 * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        qv[d8 * 8 + 2 * j] = active ? f.x : 0.f;
+        qv[d8 * 8 + 2 * j + 1] = active ? f.y : 0.f;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
   }
   const bool masked = win_masked[win] != 0;
   const int n_pool = ph * pw;
@@ -697,42 +714,66 @@ __global__ void __launch_bounds__(192) pp_window_attention_kernel(const __half* 
   const float scale = 0.08838834764831845f;     // 1 / sqrt(128)
   for (int fi = 0; fi < n_frames; ++fi) {
     const int tk = masked ? t_ind[fi] : tq;
-    for (int s = 0; s < per_frame; ++s) {
-      const __half *kr, *vr;
-      if (s < PP_WT + n_valid) {
-        int wy, wx, sy = 0, sx = 0;
-        if (s < PP_WT) { wy = s / PP_WW; wx = s % PP_WW; }
-        else {
-          const int id = valid_ind[s - PP_WT], rr = id / PP_WT, o = id % PP_WT;
-          wy = o / PP_WW; wx = o % PP_WW;
-          sy = (rr < 2) ? -eh : eh;
-          sx = (rr & 1) ? ew : -ew;
+    for (int s0 = 0; s0 < per_frame; s0 += PP_KT) {
+      const int nk = min(PP_KT, per_frame - s0);
+      for (int e = threadIdx.x; e < nk * 16; e += blockDim.x) {      // one 8-channel group of one key / value row per step
+        const int row = e >> 4, c8 = (e & 15) * 8, s = s0 + row;
+        size_t off;
+        const __half *kb, *vb;
+        if (s < PP_WT + n_valid) {
+          int wy, wx, sy = 0, sx = 0;
+          if (s < PP_WT) { wy = s / PP_WW; wx = s % PP_WW; }
+          else {
+            const int id = valid_ind[s - PP_WT], rr = id / PP_WT, o = id % PP_WT;
+            wy = o / PP_WW; wx = o % PP_WW;
+            sy = (rr < 2) ? -eh : eh;
+            sx = (rr & 1) ? ew : -ew;
+          }
+          const int Y = ((wy0 + wy - sy) % Hn + Hn) % Hn, X = ((wx0 + wx - sx) % Wn + Wn) % Wn;
+          off = ((size_t)tk * plane + (size_t)Y * Wn + X) * C + ch + c8;
+          kb = k; vb = v;
+        } else {
+          off = ((size_t)tk * n_pool + (s - PP_WT - n_valid)) * C + ch + c8;
+          kb = kp; vb = vp;
         }
-        const int Y = ((wy0 + wy - sy) % Hn + Hn) % Hn, X = ((wx0 + wx - sx) % Wn + Wn) % Wn;
-        const size_t off = ((size_t)tk * plane + (size_t)Y * Wn + X) * C + c0;
-        kr = k + off; vr = v + off;
-      } else {
-        const size_t off = ((size_t)tk * n_pool + (s - PP_WT - n_valid)) * C + c0;
-        kr = kp + off; vr = vp + off;
+        const uint4 rk = *reinterpret_cast<const uint4*>(kb + off), rv = *reinterpret_cast<const uint4*>(vb + off);
+        const __half2 *hk = reinterpret_cast<const __half2*>(&rk), *hv = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fk = __half22float2(hk[j]), fv = __half22float2(hv[j]);
+          ks[row][c8 + 2 * j] = fk.x; ks[row][c8 + 2 * j + 1] = fk.y;
+          vs[row][c8 + 2 * j] = fv.x; vs[row][c8 + 2 * j + 1] = fv.y;
+        }
       }
-      float dot = 0.f;
+      __syncthreads();
+      for (int r = 0; r < nk; ++r) {
+        const float* kr = &ks[r][part * 32];
+        const float* vr = &vs[r][part * 32];
+        float dot = 0.f;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) dot += qv[d] * __half2float(kr[d]);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-      dot *= scale;
-      const float nm = fmaxf(mx, dot), corr = __expf(mx - nm), pe = __expf(dot - nm);
-      den = den * corr + pe;
+        for (int d = 0; d < 32; ++d) dot += qv[d] * kr[d];
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot *= scale;
+        const float nm = fmaxf(mx, dot), corr = __expf(mx - nm), pe = __expf(dot - nm);
+        den = den * corr + pe;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) acc[d] = acc[d] * corr + pe * __half2float(vr[d]);
-      mx = nm;
+        for (int d = 0; d < 32; ++d) acc[d] = acc[d] * corr + pe * vr[d];
+        mx = nm;
+      }
+      __syncthreads();
     }
   }
   if (active) {
-    __half* dst = out + (((size_t)tq * Hn + wy0 + qi / PP_WW) * Wn + wx0 + qi % PP_WW) * C + c0;
+    __half* dst = out + (((size_t)tq * Hn + wy0 + qi / PP_WW) * Wn + wx0 + qi % PP_WW) * C + ch + part * 32;
     const float inv = 1.f / den;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) dst[d] = __float2half_rn(acc[d] * inv);
+    for (int d8 = 0; d8 < 4; ++d8) {
+      __align__(16) __half o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(acc[d8 * 8 + j] * inv);
+      *reinterpret_cast<uint4*>(dst + d8 * 8) = *reinterpret_cast<const uint4*>(o);
+    }
   }
 }
 
