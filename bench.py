@@ -84,13 +84,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def load_weights():
-    from oracle import sttn_oracle as O
-
+def weights_source():
+    """(what the product's constructor gets, description).  With the reference checkpoint staged the product loads it with its own loader;
+    without it the tensors are seeded random-init values of the architecture — the table of shapes lives with the oracle, and that is the
+    only thing the device legs ever take from `oracle/` (a data generator, no arithmetic of the path)."""
     p = os.path.join(ROOT, "weights", "sttn-auto", "infer_model.pth")
     if os.path.exists(p):
-        return O.load_weights(p), "reference checkpoint sttn-auto/infer_model.pth"
-    return O.random_weights(0), "seeded random-init weights of the sttn-auto architecture"
+        return p, "reference checkpoint sttn-auto/infer_model.pth"
+    return _random_init("sttn_oracle", 0), "seeded random-init weights of the sttn-auto architecture"
+
+
+def _random_init(module, seed):
+    import importlib
+
+    return {k: v.numpy() for k, v in importlib.import_module("oracle." + module).random_weights(seed).items()}
+
+
+def oracle_weights(src):
+    """the same weights as torch tensors for the CPU port (cpu_baseline / --impl reference legs only)"""
+    import torch
+    from oracle import sttn_oracle as O
+
+    return O.load_weights(src) if isinstance(src, str) else {k: torch.from_numpy(v) for k, v in src.items()}
 
 
 def cpu_port_fps(w, frames, mask, threads, calibrate=False):
@@ -169,7 +184,8 @@ def run_reference(args, rank, world):
 
     if rank != 0:
         return
-    w, wdesc = load_weights()
+    src, wdesc = weights_source()
+    w = oracle_weights(src)
     frames = O.synthetic_clip(CHUNK, H, W, seed=0)
     mask = O.default_mask(H, W)
     threads = best_cpu_threads(w, frames, mask)  # doubles as warm-up
@@ -197,18 +213,18 @@ def run_det(args, rank, world, local):
     interval, batch_generator 46x6+24 — SURVEY §8a D-rows), device-resident and through the host call."""
     import torch
     import torch.distributed as dist
-    from oracle import sttn_oracle as O
     from vsr_b200 import STTNDetInpaint
+    from vsr_b200 import synthetic as S
 
     p = os.path.join(ROOT, "weights", "sttn-det", "sttn.pth")
     if os.path.exists(p):
         eng, wdesc = STTNDetInpaint(torch.device("cuda", local), p), "reference checkpoint sttn-det/sttn.pth"
     else:
-        eng = STTNDetInpaint(torch.device("cuda", local), {k: v.numpy() for k, v in O.random_weights(1).items()})
+        eng = STTNDetInpaint(torch.device("cuda", local), _random_init("sttn_oracle", 1))
         wdesc = "seeded random-init weights of the sttn-det architecture"
     T = 46
-    frames = O.synthetic_clip(T, H, W, seed=100 + rank)
-    mask = O.default_mask(H, W)
+    frames = S.synthetic_clip(T, H, W, seed=100 + rank)
+    mask = S.default_mask(H, W)
     stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local))
     work = [f.copy() for f in frames]
     for _ in range(max(args.warmup, 3)):
@@ -338,20 +354,18 @@ def run_lama(args, rank, world, local):
     of int(1920*3/16) = 360 rows around the subtitle goes through big-lama at native resolution, frame by frame."""
     import torch
     import torch.distributed as dist
-    from oracle import sttn_oracle as O
     from vsr_b200 import LamaInpaint
+    from vsr_b200 import synthetic as S
 
     npz = os.path.join(ROOT, "weights", "big-lama", "big-lama.npz")
     if os.path.exists(npz):
         eng, wdesc, wsrc = LamaInpaint(torch.device("cuda", local), npz), "reference big-lama weights (conv kernels stored fp16)", npz
     else:
-        from oracle import lama_oracle as LO
-
-        wsrc = {k: v.numpy() for k, v in LO.random_weights(3).items()}
+        wsrc = _random_init("lama_oracle", 3)
         eng, wdesc = LamaInpaint(torch.device("cuda", local), wsrc), "seeded random-init weights of the big-lama architecture"
     T = 4
-    frames = O.synthetic_clip(T, H, W, seed=200 + rank)
-    mask = O.default_mask(H, W)
+    frames = S.synthetic_clip(T, H, W, seed=200 + rank)
+    mask = S.default_mask(H, W)
     for _ in range(max(args.warmup, 3)):
         eng(frames, mask)
     if world > 1:
@@ -406,11 +420,11 @@ def run_config4(args, rank, world, local):
     import cv2
     import torch
     import torch.distributed as dist
-    from oracle import sttn_oracle as O
     from vsr_b200 import STTNDetInpaint, SubtitleDetect, video_inpaint_frames
+    from vsr_b200 import synthetic as S
 
     T = 120
-    frames = O.synthetic_clip(T, H, W, seed=300 + rank)
+    frames = S.synthetic_clip(T, H, W, seed=300 + rank)
     for i, f in enumerate(frames):          # a subtitle on frames 11..110 (1-based), text changing every 48 frames
         if 10 <= i < 110:
             txt = f"subtitle line number {i // 48} of the clip"
@@ -418,7 +432,7 @@ def run_config4(args, rank, world, local):
             cv2.putText(f, txt, (420, 1020), cv2.FONT_HERSHEY_SIMPLEX, 1.8, (255, 255, 255), 4, cv2.LINE_AA)
     dev = torch.device("cuda", local)
     p = os.path.join(ROOT, "weights", "sttn-det", "sttn.pth")
-    model = STTNDetInpaint(dev, p if os.path.exists(p) else {k: v.numpy() for k, v in O.random_weights(1).items()})
+    model = STTNDetInpaint(dev, p if os.path.exists(p) else _random_init("sttn_oracle", 1))
     det = SubtitleDetect("", model_dir=os.path.join(ROOT, "weights", "V5", "ch_det"), device=dev)
     det.SAMPLE_STEP = 3                     # 30 fps video (subtitle_detect.py:29-39)
     for _ in range(max(min(args.warmup, 2), 1)):
@@ -462,7 +476,7 @@ def run_propainter(args, rank, world, local):
     device-resident leg yet (flows take a host round trip between RAFT and the completion network): `value` is the same end-to-end rate."""
     import torch
     import torch.distributed as dist
-    from oracle import sttn_oracle as O
+    from vsr_b200 import synthetic as S
     from vsr_b200.propainter_inpaint import PropainterInpaint
 
     mdir = os.path.join(ROOT, "weights", "propainter")
@@ -471,8 +485,8 @@ def run_propainter(args, rank, world, local):
         raise SystemExit("bench.py --workload propainter needs weights/propainter/{raft-things,recurrent_flow_completion,ProPainter}.pth "
                          "(tools/stage_weights.py; drop weights/propainter from .gpurunignore so that they travel)")
     Hp, Wp, T = 720, 1280, args.pp_frames
-    frames = O.synthetic_clip(T, Hp, Wp, seed=300 + rank)
-    mask = O.default_mask(Hp, Wp)
+    frames = S.synthetic_clip(T, Hp, Wp, seed=300 + rank)
+    mask = S.default_mask(Hp, Wp)
     eng = PropainterInpaint(torch.device("cuda", local), mdir)
     for _ in range(max(args.warmup, 3)):
         eng(frames, mask)
@@ -548,8 +562,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import sttn_oracle as O
     from vsr_b200 import STTNInpaint, _capi
+    from vsr_b200 import synthetic as S
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: vsr_b200 has no CPU fallback")
@@ -576,10 +590,10 @@ def main():
         return
     if args.workload == "sttn-det":
         return run_det(args, rank, world, local)
-    w, wdesc = load_weights()
-    eng = STTNInpaint(torch.device("cuda", local), {k: v.numpy() for k, v in w.items()})
-    frames = O.synthetic_clip(CHUNK, H, W, seed=rank)  # each rank its own chunk (weak scaling)
-    mask = O.default_mask(H, W)
+    src, wdesc = weights_source()
+    eng = STTNInpaint(torch.device("cuda", local), src)
+    frames = S.synthetic_clip(CHUNK, H, W, seed=rank)  # each rank its own chunk (weak scaling)
+    mask = S.default_mask(H, W)
     stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local))
     strip_bytes = CHUNK * int(W * 3 / 16) * W * 3
 
@@ -672,6 +686,7 @@ def main():
     # ---- CPU port on a bounded sample (rank 0, N = 1 only) -------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
+        w = oracle_weights(src)
         threads = best_cpu_threads(w, frames, mask)
         fps, dt = cpu_port_fps(w, frames, mask, threads)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",

@@ -121,3 +121,14 @@ def test_ctypes_prototypes_match_the_header(capi):
                 assert t in (C.c_int, C.c_int32), (name, p, t)
             checked += 1
     assert checked > 600
+
+
+def test_bench_input_generators_equal_the_oracle_generators():
+    """bench.py's device legs take their frames and masks from vsr_b200.synthetic (nothing under oracle/ on the measured path); the goldens
+    and the CPU baseline use the oracle's generators — same pixels."""
+    from oracle import sttn_oracle as O
+    from vsr_b200 import synthetic as S
+
+    for n, H, W, seed in ((5, 128, 192, 23), (2, 1080, 1920, 0), (3, 720, 1280, 301)):
+        assert all(np.array_equal(a, b) for a, b in zip(O.synthetic_clip(n, H, W, seed=seed), S.synthetic_clip(n, H, W, seed=seed)))
+        assert np.array_equal(O.default_mask(H, W), S.default_mask(H, W))
