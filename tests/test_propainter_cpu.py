@@ -31,3 +31,21 @@ def test_propainter_pipeline_on_cpu_runtime_equals_reference_frames():
     assert out.shape == z["comp"].shape and d.max() <= 3 and (d > 0).mean() < 0.02, (int(d.max()), float((d > 0).mean()))
     hole = z["comp"] != np.stack(frames)
     assert hole.any() and np.abs(out[hole].astype(np.int32) - np.stack(frames)[hole]).mean() > 3        # the hole really was repainted
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(os.environ.get("VSR_SLOW_TESTS") != "1", reason="about a minute on the CPU stand-in: set VSR_SLOW_TESTS=1 (last run: 1 grey level on 3e-5 of the pixels)")
+def test_propainter_call_strips_on_cpu_runtime_equal_reference_frames():
+    """`PropainterInpaint.__call__` (P1: strips with heights that are multiples of 8, first-frame mask, strip written back whole) against the
+    unmodified reference's output for the 200x704 fixture (`call` in the golden file)."""
+    from fake_rt import FakeRuntime
+    from make_golden_propainter import inputs
+    from vsr_b200.propainter_inpaint import PropainterInpaint
+
+    z = np.load(os.path.join(GOLDEN, "propainter_real.npz"))
+    big, big_mask = inputs()[2:]
+    keep = [f.copy() for f in big]
+    out = np.stack(PropainterInpaint("cuda:0", DIR, runtime=FakeRuntime())(big, big_mask))
+    assert all(np.array_equal(a, b) for a, b in zip(big, keep))
+    d = np.abs(out.astype(np.int32) - z["call"])
+    assert out.shape == z["call"].shape and d.max() <= 3 and (d > 0).mean() < 0.02, (int(d.max()), float((d > 0).mean()))
