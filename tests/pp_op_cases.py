@@ -6,11 +6,52 @@
 Every case runs one operator twice: on the numpy stand-in of the runtime (tests/fake_rt.py, the thing the CPU pipeline tests are built on) and
 through the product's wrapper class -> ctypes prototypes -> `vsr_rt_*` entry point -> kernel, and compares the two."""
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
 
+from conftest import ROOT
 from fake_rt import FakeRuntime
+
+EMU = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "video-subtitle-remover_b200", "csrc")
+
+
+def load_emu_library():
+    """Build (when stale) and load the host build of the ProPainter entry points: tests/emu/make_abi_emu.py cuts them out of csrc/engine.cu,
+    g++ compiles them with csrc/pp_ops.cuh over tests/emu/cuda_emu.h; the alignment sanitizer aborts on a misaligned 16-byte access.  The
+    shipped ctypes prototypes (vsr_b200/_capi.py) are applied to it."""
+    from vsr_b200 import _capi
+
+    build = os.path.join(EMU, "build")
+    out, gen = os.path.join(build, "libabi_emu.so"), os.path.join(build, "abi_emu.cpp")
+    srcs = [os.path.join(EMU, f) for f in ("make_abi_emu.py", "abi_prelude.h", "cuda_emu.h")] + [os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "pp_ops.cuh"),
+                                                                                                os.path.join(ROOT, "include", "vsr_b200.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in srcs):
+        os.makedirs(build, exist_ok=True)
+        subprocess.run([sys.executable, srcs[0], os.path.join(CSRC, "engine.cu"), gen], check=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I",
+                        os.path.join(EMU, "stubs"), "-I", EMU, gen, "-o", out], check=True)
+    L = C.CDLL(out)
+    for name, (res, args) in _capi._PROTOS.items():
+        if hasattr(L, name):
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+    L.emu_rt_create.restype = C.c_void_p
+    L.emu_launches.restype, L.emu_launches.argtypes = C.c_long, [C.c_void_p]
+    return L
+
+
+def bind_wrapper(lib):
+    """the product's wrapper class (_GenRuntime and its bases) bound to the host build of the C ABI"""
+    from vsr_b200.propainter_generator import _GenRuntime
+
+    rt = object.__new__(_GenRuntime)
+    rt.L, rt.h = lib, C.c_void_p(lib.emu_rt_create())
+    return rt
 
 
 class HostBackend:
@@ -20,11 +61,7 @@ class HostBackend:
         self.lib = lib
 
     def runtime(self):
-        from vsr_b200.propainter_generator import _GenRuntime
-
-        rt = object.__new__(_GenRuntime)                         # the product wrapper class, bound to the host build of the C ABI
-        rt.L, rt.h = self.lib, C.c_void_p(self.lib.emu_rt_create())
-        return rt
+        return bind_wrapper(self.lib)
 
     def launches(self, rt):
         return self.lib.emu_launches(rt.h)
