@@ -223,12 +223,12 @@ def case_frames_and_states(make):
     st2.check("prop_state (compose)", ulps=0)
 
 
-def case_instnorm(make, relu):
+def case_instnorm(make, relu, cp=64):
     d = make(1)
-    x = d.tensor(2, 9, 13, 64, scale=3.0)
-    x.view[:] += np.linspace(-2, 2, 64, dtype=np.float32)
+    x = d.tensor(2, 9, 13, cp, scale=3.0)
+    x.view[:] += np.linspace(-2, 2, cp, dtype=np.float32)
     x.push()
-    y = d.tensor(2, 9, 13, 64, fill=False)
+    y = d.tensor(2, 9, 13, cp, fill=False)
     d.call("instnorm", x, y, relu)
     y.check("instnorm", ulps=3, atol=1e-3)
 
@@ -420,9 +420,9 @@ def case_layernorm_pool(make):
     out.check("pool4", ulps=3, atol=1e-3)
 
 
-def case_window_attention(make):
+def case_window_attention(make, heads=1):
     d = make(14)
-    T, Hn, Wn, Cc, ph, pw = 3, 10, 18, 128, 2, 2
+    T, Hn, Wn, Cc, ph, pw = 3, 10, 18, 128 * heads, 2, 2
     q, k, v = (d.tensor(T, Hn, Wn, Cc, 1.5) for _ in range(3))
     kp, vp = d.tensor(T, ph, pw, Cc, 1.5), d.tensor(T, ph, pw, Cc, 1.5)
     valid = d.ints(np.sort(d.rng.choice(180, 23, replace=False)))
@@ -454,7 +454,7 @@ def case_entry_points_reject_bad_arguments(make):
 
 CASES = [
     ("frames_and_states", case_frames_and_states, ()),
-    ("instnorm", case_instnorm, (0,)), ("instnorm_relu", case_instnorm, (1,)),
+    ("instnorm", case_instnorm, (0,)), ("instnorm_relu", case_instnorm, (1,)), ("instnorm_128ch", case_instnorm, (1, 128)),
     ("context_split_and_gru", case_context_split_and_gru, ()),
     ("corr_pool_and_lookup", case_corr_pool_and_lookup, ()),
     ("flow_update_refresh", case_flow_update, (0,)), ("flow_update_add", case_flow_update, (1,)),
@@ -467,7 +467,7 @@ CASES = [
     ("featprop_cond", case_featprop_cond, ()),
     ("unfold_fold", case_unfold_fold, (False,)), ("unfold_fold_gelu", case_unfold_fold, (True,)),
     ("layernorm_pool", case_layernorm_pool, ()),
-    ("window_attention", case_window_attention, ()),
+    ("window_attention", case_window_attention, ()), ("window_attention_two_heads", case_window_attention, (2,)),
     ("pred_to_rgb8", case_pred_to_rgb8, ()),
     ("entry_points_reject_bad_arguments", case_entry_points_reject_bad_arguments, ()),
 ]
