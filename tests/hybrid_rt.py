@@ -93,17 +93,19 @@ class _Images:
             # parameter vectors, masks and index lists are read-only
 
 
-# kernels with warp shuffles / __syncthreads run one OS thread per CUDA thread in the host build: fine for the operator cases, minutes per
-# launch at pipeline sizes.  They stay on the numpy transcription unless `lockstep=True` (tests/pp_op_cases.py covers them one by one).
-_LOCKSTEP = {"instnorm", "layernorm", "window_attention"}
+# Kernels with warp shuffles / __syncthreads run one OS thread per CUDA thread in the host build: affordable in the operator cases
+# (tests/pp_op_cases.py covers each of them), slow at pipeline sizes — instance norm and layer norm synchronise a handful of times per thread
+# and add ~3.5 minutes to the 7-frame fixture, the window attention shuffles twice per key and would take minutes per launch.  `on_numpy`
+# names the operators that stay on the numpy transcription.
+_LOCKSTEP = ("instnorm", "layernorm", "window_attention")
 
 
 class HybridRuntime(FakeRuntime):
-    def __init__(self, lib, lockstep=False, **kw):
+    def __init__(self, lib, on_numpy=_LOCKSTEP, **kw):
         super().__init__(fp16=True, **kw)
         self.real = bind_wrapper(lib)
         self.lib = lib
-        self.lockstep = lockstep
+        self.on_numpy = set(on_numpy)
         self.real_calls = {}
 
     def _run_real(self, op, args):
@@ -134,7 +136,7 @@ class HybridRuntime(FakeRuntime):
 
 def _route(op):
     def method(self, *args, **kw):
-        if self._rec is not None or (op in _LOCKSTEP and not self.lockstep):   # graph capture: the stand-in records (or refuses) the call; replay comes back here
+        if self._rec is not None or op in self.on_numpy:   # graph capture: the stand-in records (or refuses) the call; replay comes back here
             return getattr(FakeRuntime, op)(self, *args, **kw)
         assert not kw or op == "unfold7s3", (op, kw)
         if op == "unfold7s3" and kw:
