@@ -344,12 +344,12 @@ def case_pad_leaky_taps_extra(make):
     dst.check("write_extra", ulps=0)
 
 
-def case_deform_cols(make, two_inputs, with_flow):
+def case_deform_cols(make, two_inputs, with_flow, G=4):
     d = make(9)
-    n, H, W, Cc, G = 2, 6, 7, 32, 4
+    n, H, W, Cc = 2, 6, 7, 32                    # G = 4: 8 channels per group, the 16-byte path; G = 8: the scalar path
     xa = d.tensor(n, H, W, 64)
     xb = d.tensor(n, H, W, 64) if two_inputs else None
-    om = d.tensor(n, H, W, 128, 0.7)
+    om = d.tensor(n, H, W, max(128, (27 * G + 7) // 8 * 8), 0.7)
     cols = d.tensor(n, H, W, 9 * Cc + 32)
     fl = d.f32(d.rng.standard_normal((n * H * W, 2)) * 2) if with_flow else 0
     d.call("deform_cols", xa, 16 if two_inputs else Cc, xb, Cc, G, om, 3.0, fl, cols)
@@ -463,6 +463,7 @@ CASES = [
     ("rfc_input_combine", case_rfc_input_combine, (False,)), ("rfc_input_combine_reversed", case_rfc_input_combine, (True,)),
     ("pad_leaky_taps_extra", case_pad_leaky_taps_extra, ()),
     ("deform_cols", case_deform_cols, (False, False)), ("deform_cols_two_inputs_flow", case_deform_cols, (True, True)),
+    ("deform_cols_4_channel_groups", case_deform_cols, (True, True, 8)),
     ("gen_input_flow_down_masks", case_gen_input_flow_down_masks, ()),
     ("featprop_cond", case_featprop_cond, ()),
     ("unfold_fold", case_unfold_fold, (False,)), ("unfold_fold_gelu", case_unfold_fold, (True,)),

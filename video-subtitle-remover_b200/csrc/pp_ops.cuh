@@ -426,6 +426,33 @@ __global__ void __launch_bounds__(256) pp_deform_cols_kernel(const __half* __res
   const bool v00 = y0 >= 0 && y0 < H && x0 >= 0 && x0 < W, v01 = y0 >= 0 && y0 < H && x0 + 1 >= 0 && x0 + 1 < W;
   const bool v10 = y0 + 1 >= 0 && y0 + 1 < H && x0 >= 0 && x0 < W, v11 = y0 + 1 >= 0 && y0 + 1 < H && x0 + 1 >= 0 && x0 + 1 < W;
   const int cpg = C / G;
+  if (cpg == 8 && (Ca & 7) == 0 && (pa & 7) == 0 && (pb & 7) == 0 && (C & 7) == 0 && (pcols & 7) == 0) {
+    // the networks' case (128 channels, 16 groups): the 8 channels of a group are one 16-byte load per corner and one 16-byte store
+    const int c = g * 8;
+    const __half* src = c < Ca ? xa + c : xb + (c - Ca);
+    const int pitch = c < Ca ? pa : pb;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    auto corner = [&](bool ok, float wgt, int yy, int xx) {
+      if (!ok) return;
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + (img + (size_t)yy * W + xx) * pitch);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        acc[2 * j] += wgt * f.x;
+        acc[2 * j + 1] += wgt * f.y;
+      }
+    };
+    corner(v00, w00, y0, x0);
+    corner(v01, w01, y0, x0 + 1);
+    corner(v10, w10, y0 + 1, x0);
+    corner(v11, w11, y0 + 1, x0 + 1);
+    __align__(16) __half o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(acc[j]);
+    *reinterpret_cast<uint4*>(cols + p * pcols + (size_t)k * C + c) = *reinterpret_cast<const uint4*>(o);
+    return;
+  }
   for (int cc = 0; cc < cpg; ++cc) {
     const int c = g * cpg + cc;
     const __half* src = c < Ca ? xa + c : xb + (c - Ca);
