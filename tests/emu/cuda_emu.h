@@ -88,7 +88,109 @@ static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 using std::max;
 using std::min;
 
-// ---- lockstep execution of one block
+// ---- lockstep execution of one block (kernels with warp shuffles / __syncthreads)
+// Default: one FIBER per CUDA thread on the calling OS thread — a hand-rolled x86-64 context switch (callee-saved registers + stack pointer),
+// round-robin scheduling, a fiber yields while it waits at a barrier.  Deterministic and ~100x cheaper per synchronisation than OS threads,
+// which is what makes the window attention affordable at pipeline sizes.  -DEMU_OS_THREADS selects one std::thread per CUDA thread with
+// std::barrier instead: the mode for ThreadSanitizer (real concurrency) and AddressSanitizer (no foreign stacks).
+#ifndef EMU_OS_THREADS
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+__asm__(
+    ".text\n.globl emu_switch\n.type emu_switch,@function\nemu_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
+    ".size emu_switch, .-emu_switch\n");
+
+struct EmuBarrier {
+  int expected = 0, count = 0;
+  unsigned gen = 0;
+};
+struct EmuFiber {
+  void* sp = nullptr;
+  unsigned tid = 0;
+  bool done = false;
+  std::unique_ptr<char[]> stack;
+};
+struct EmuBlock {
+  EmuBarrier block_bar;
+  std::vector<EmuBarrier> warp_bar;
+  std::vector<float> slots[2];
+  std::vector<unsigned char> parity;       // per thread: which slot array its next shuffle uses
+  std::vector<EmuFiber> fibers;
+  EmuFiber* current = nullptr;
+  void* sched_sp = nullptr;
+  const std::function<void()>* kernel = nullptr;
+};
+inline EmuBlock* g_emu_block = nullptr;
+
+static inline void emu_yield() { emu_switch(&g_emu_block->current->sp, g_emu_block->sched_sp); }
+static inline void emu_barrier_wait(EmuBarrier& b) {
+  const unsigned gen = b.gen;
+  if (++b.count == b.expected) { b.count = 0; ++b.gen; return; }
+  while (b.gen == gen) emu_yield();
+}
+static inline void emu_barrier_drop(EmuBarrier& b) {       // a thread that returned no longer takes part
+  --b.expected;
+  if (b.expected > 0 && b.count == b.expected) { b.count = 0; ++b.gen; }
+}
+static inline void __syncthreads() { emu_barrier_wait(g_emu_block->block_bar); }
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  EmuBlock& blk = *g_emu_block;
+  const unsigned tid = blk.current->tid;
+  const unsigned char p = blk.parity[tid];
+  blk.parity[tid] = p ^ 1;                 // alternate slot arrays: a lane can only overwrite a slot after every lane has passed the NEXT barrier
+  blk.slots[p][tid] = v;
+  emu_barrier_wait(blk.warp_bar[tid >> 5]);
+  return blk.slots[p][tid ^ (unsigned)lane_mask];
+}
+extern "C" inline void emu_fiber_main() {
+  EmuBlock& blk = *g_emu_block;
+  EmuFiber* self = blk.current;
+  (*blk.kernel)();
+  emu_barrier_drop(blk.warp_bar[self->tid >> 5]);
+  emu_barrier_drop(blk.block_bar);
+  self->done = true;
+  for (;;) emu_yield();
+}
+
+static inline void emu_run_block_lockstep(unsigned threads, const std::function<void()>& kernel) {
+  constexpr size_t kStack = 256 * 1024;
+  EmuBlock blk;
+  blk.block_bar.expected = (int)threads;
+  blk.warp_bar.resize((threads + 31) / 32);
+  for (unsigned w = 0; w < blk.warp_bar.size(); ++w) blk.warp_bar[w].expected = (int)std::min(32u, threads - 32 * w);
+  blk.slots[0].assign(threads, 0.f);
+  blk.slots[1].assign(threads, 0.f);
+  blk.parity.assign(threads, 0);
+  blk.kernel = &kernel;
+  blk.fibers.resize(threads);
+  for (unsigned t = 0; t < threads; ++t) {
+    EmuFiber& f = blk.fibers[t];
+    f.tid = t;
+    f.stack.reset(new char[kStack]);
+    uintptr_t top = ((uintptr_t)f.stack.get() + kStack) & ~(uintptr_t)63;
+    void** sp = (void**)top;
+    *--sp = nullptr;                       // keeps the entry's stack 16-byte aligned after the `ret` below (as after a call)
+    *--sp = (void*)&emu_fiber_main;        // `ret` of the first switch jumps here
+    for (int i = 0; i < 6; ++i) *--sp = nullptr;   // rbp rbx r12 r13 r14 r15
+    f.sp = sp;
+  }
+  g_emu_block = &blk;
+  for (unsigned alive = threads; alive;) {
+    alive = 0;
+    for (unsigned t = 0; t < threads; ++t) {
+      EmuFiber& f = blk.fibers[t];
+      if (f.done) continue;
+      blk.current = &f;
+      threadIdx = dim3(t);
+      emu_switch(&blk.sched_sp, f.sp);
+      if (!f.done) ++alive;
+    }
+  }
+  g_emu_block = nullptr;
+}
+#else
 struct EmuBlock {
   std::unique_ptr<std::barrier<>> block_bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
@@ -104,32 +206,35 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   g_emu_block->warp_bar[warp]->arrive_and_wait();
   return r;
 }
+static inline void emu_run_block_lockstep(unsigned threads, const std::function<void()>& kernel) {
+  const dim3 bi = blockIdx, bd = blockDim, gd = gridDim;
+  EmuBlock blk;
+  blk.block_bar = std::make_unique<std::barrier<>>(threads);
+  for (unsigned w = 0; w < (threads + 31) / 32; ++w) blk.warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, threads - 32 * w)));
+  blk.slots.assign(threads, 0.f);
+  g_emu_block = &blk;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      blockIdx = bi; blockDim = bd; gridDim = gd; threadIdx = dim3(t);
+      kernel();
+      blk.warp_bar[t >> 5]->arrive_and_drop();     // a thread that returned no longer takes part in shuffles / barriers
+      blk.block_bar->arrive_and_drop();
+    });
+  for (auto& th : pool) th.join();
+  g_emu_block = nullptr;
+}
+#endif
 
 // grid / block are 1-D..3-D in the grid and 1-D in the block (all kernels of pp_ops.cuh); lockstep = kernel uses shuffles or __syncthreads
 static inline void emu_launch(dim3 grid, unsigned threads, bool lockstep, const std::function<void()>& kernel) {
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        if (!lockstep) {
-          blockIdx = dim3(bx, by, bz); blockDim = dim3(threads); gridDim = grid;
+        blockIdx = dim3(bx, by, bz); blockDim = dim3(threads); gridDim = grid;
+        if (lockstep) emu_run_block_lockstep(threads, kernel);
+        else
           for (unsigned t = 0; t < threads; ++t) { threadIdx = dim3(t); kernel(); }
-          continue;
-        }
-        EmuBlock blk;
-        blk.block_bar = std::make_unique<std::barrier<>>(threads);
-        for (unsigned w = 0; w < (threads + 31) / 32; ++w) blk.warp_bar.push_back(std::make_unique<std::barrier<>>(std::min(32u, threads - 32 * w)));
-        blk.slots.assign(threads, 0.f);
-        g_emu_block = &blk;
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < threads; ++t)
-          pool.emplace_back([&, t] {
-            blockIdx = dim3(bx, by, bz); blockDim = dim3(threads); gridDim = grid; threadIdx = dim3(t);
-            kernel();
-            blk.warp_bar[t >> 5]->arrive_and_drop();     // a thread that returned no longer takes part in shuffles / barriers
-            blk.block_bar->arrive_and_drop();
-          });
-        for (auto& th : pool) th.join();
-        g_emu_block = nullptr;
       }
 }
 static inline unsigned emu_blocks(size_t n) { return (unsigned)((n + 255) / 256); }

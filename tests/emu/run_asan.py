@@ -3,7 +3,8 @@ every out-of-bounds read or write of a kernel — on the numpy buffers that stan
 
     python tests/emu/run_asan.py            # re-executes itself with libasan preloaded
 
-Last run (round 1): 23 operator cases and 732 kernel launches of the pipeline at its own shapes, no report.  TEST INFRASTRUCTURE ONLY."""
+Last run (round 1): 24 operator cases and 732 kernel launches of the pipeline at its own shapes, no report.  The host build uses one OS thread
+per CUDA thread here (-DEMU_OS_THREADS; the default fibers switch stacks by hand, which AddressSanitizer cannot follow).  TEST INFRASTRUCTURE ONLY."""
 import ctypes as C
 import os
 import subprocess
@@ -27,7 +28,7 @@ def main():
 
     K.load_emu_library()                                   # (re)generates tests/emu/build/abi_emu.cpp
     lib = os.path.join(HERE, "build", "libabi_emu_asan.so")
-    subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-fsanitize=address,alignment", "-fno-sanitize-recover=alignment",
+    subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-DEMU_OS_THREADS", "-fsanitize=address,alignment", "-fno-sanitize-recover=alignment",
                     "-I", os.path.join(HERE, "stubs"), "-I", HERE, os.path.join(HERE, "build", "abi_emu.cpp"), "-o", lib], check=True)
     L = C.CDLL(lib)
     for name, (res, args) in _capi._PROTOS.items():
@@ -45,12 +46,12 @@ def main():
         print("ok", name, flush=True)
     d = os.path.join(ROOT, "weights", "propainter")
     if all(os.path.exists(os.path.join(d, f)) for f in ("ProPainter.pth", "raft-things.pth", "recurrent_flow_completion.pth")):
-        from hybrid_rt import HybridRuntime
+        from hybrid_rt import _LOCKSTEP, HybridRuntime
         from make_golden_propainter import inputs
         from vsr_b200.propainter_inpaint import PropainterInpaint
 
         frames, mask = inputs()[:2]
-        rt = HybridRuntime(L)
+        rt = HybridRuntime(L, on_numpy=_LOCKSTEP)      # one OS thread per CUDA thread here: the shuffle kernels are covered by their cases above
         t = time.time()
         np.stack(PropainterInpaint("cuda:0", d, runtime=rt).inpaint(frames, mask))
         print(f"ok pipeline: {sum(rt.real_calls.values())} kernel launches in {time.time() - t:.0f} s", flush=True)

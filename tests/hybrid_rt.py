@@ -1,7 +1,7 @@
 """The CPU stand-in of the runtime with the ProPainter operators replaced by the REAL kernels (test infrastructure, never shipped).
 
 `HybridRuntime` is `FakeRuntime(fp16=True)` — convolutions, the correlation GEMM and the element-wise operators of the validated runtime stay
-numpy — but every operator of csrc/pp_ops.cuh is executed from its real source: the buffers the call touches are turned into the fp16 / fp32 /
+numpy — but every operator of csrc/pp_ops.cuh (all 30 kernels) is executed from its real source: the buffers the call touches are turned into the fp16 / fp32 /
 u8 / int32 images the device would hold, the product's wrapper method calls the host build of the `vsr_rt_*` entry point (tests/emu/), and
 the images are written back.  Driving `PropainterInpaint` on it runs the kernels at the pipeline's own shapes, pitches, channel-slice views
 and index lists, with fp16 storage between the operators: the closest thing to the device available without one."""
@@ -93,15 +93,13 @@ class _Images:
             # parameter vectors, masks and index lists are read-only
 
 
-# Kernels with warp shuffles / __syncthreads run one OS thread per CUDA thread in the host build: affordable in the operator cases
-# (tests/pp_op_cases.py covers each of them), slow at pipeline sizes — instance norm and layer norm synchronise a handful of times per thread
-# and add ~3.5 minutes to the 7-frame fixture, the window attention shuffles twice per key and would take minutes per launch.  `on_numpy`
-# names the operators that stay on the numpy transcription.
+# `on_numpy` names operators that stay on the numpy transcription (none by default: the fibers of tests/emu/cuda_emu.h make the kernels with
+# warp shuffles / __syncthreads — instance norm, layer norm, window attention — affordable at pipeline sizes; with -DEMU_OS_THREADS they are not).
 _LOCKSTEP = ("instnorm", "layernorm", "window_attention")
 
 
 class HybridRuntime(FakeRuntime):
-    def __init__(self, lib, on_numpy=_LOCKSTEP, **kw):
+    def __init__(self, lib, on_numpy=(), **kw):
         super().__init__(fp16=True, **kw)
         self.real = bind_wrapper(lib)
         self.lib = lib

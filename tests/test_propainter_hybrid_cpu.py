@@ -1,10 +1,8 @@
 """CPU: the whole ProPainter pipeline with the REAL kernels in it.  `HybridRuntime` (tests/hybrid_rt.py) is the fp16-storage stand-in of the
-runtime whose ProPainter operators execute the real source of csrc/pp_ops.cuh through the product's wrappers and the real `vsr_rt_*` entry
-points (host build, tests/emu/), at the pipeline's own shapes, pitches, channel-slice views and index lists; convolutions stay numpy, and so do the kernels that
-need lockstep warps (one OS thread per CUDA thread in the host build): by default instance norm, layer norm and the window attention, in the
-opt-in variant only the window attention (all three are covered one by one in tests/test_pp_abi_emulated.py).  Output against the frames
-of the UNMODIFIED reference (fp32): >= 50 dB in the hole (last runs 59.2 dB / max 6 grey levels with 27 kernels, 60.7 dB / max 5 with 29),
-bit-exact outside it."""
+runtime whose ProPainter operators — all 30 kernels of csrc/pp_ops.cuh — execute from their real source through the product's wrappers and
+the real `vsr_rt_*` entry points (host build, tests/emu/), at the pipeline's own shapes, pitches, channel-slice views and index lists; only
+the tensor-core convolutions (and the correlation GEMM) stay numpy, with fp16 operands and fp16 storage.  Output against the frames of the
+UNMODIFIED reference (fp32): >= 50 dB in the hole (last run 60.7 dB, max 5 grey levels on 5e-5 of the pixels), bit-exact outside it."""
 import os
 import sys
 
@@ -20,11 +18,7 @@ pytestmark = pytest.mark.skipif(not all(os.path.exists(os.path.join(DIR, f)) for
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("on_numpy", [("instnorm", "layernorm", "window_attention"),
-                                      pytest.param(("window_attention",), marks=pytest.mark.skipif(os.environ.get("VSR_SLOW_TESTS") != "1", reason="4.5 minutes: set "
-                                                   "VSR_SLOW_TESTS=1 (last run: 60.7 dB in the hole, max 5 grey levels)"))],
-                         ids=["27_kernels", "29_kernels"])
-def test_pipeline_with_real_kernels_reproduces_reference_frames(on_numpy):
+def test_pipeline_with_real_kernels_reproduces_reference_frames():
     from hybrid_rt import _SIG, HybridRuntime
     from make_golden_propainter import inputs
     from oracle import propainter_oracle as P
@@ -38,11 +32,11 @@ def test_pipeline_with_real_kernels_reproduces_reference_frames(on_numpy):
     try:
         z = np.load(os.path.join(GOLDEN, "propainter_real.npz"))
         frames, mask = inputs()[:2]
-        rt = HybridRuntime(lib, on_numpy=on_numpy)
+        rt = HybridRuntime(lib)
         out = np.stack(PropainterInpaint("cuda:0", DIR, runtime=rt).inpaint(frames, mask))
     finally:
         _capi._lib = saved
-    assert set(rt.real_calls) == set(_SIG) - set(on_numpy), sorted(set(_SIG) - set(on_numpy) - set(rt.real_calls))     # every kernel really ran
+    assert set(rt.real_calls) == set(_SIG), sorted(set(_SIG) - set(rt.real_calls))     # every kernel really ran
     assert not rt._flag                                                                                         # no fp16 overflow anywhere
     hole = np.stack(P.read_mask(mask, len(frames))[1]) > 0
     assert np.array_equal(out[~hole], np.stack(frames)[~hole])
