@@ -16,6 +16,8 @@ pytestmark = pytest.mark.skipif(not all(os.path.exists(os.path.join(DIR, f)) for
 
 
 @pytest.mark.slow
+@pytest.mark.skipif(os.environ.get("VSR_SLOW_TESTS") != "1", reason="the same run and the same check are part of tests/test_distributed_cpu.py (rank 0 of the "
+                    "sharded-vs-single test) and tests/test_propainter_hybrid_cpu.py repeats it with the real kernels: set VSR_SLOW_TESTS=1 to run it alone")
 def test_propainter_pipeline_on_cpu_runtime_equals_reference_frames():
     from fake_rt import FakeRuntime
     from make_golden_propainter import inputs
