@@ -5,8 +5,6 @@ numpy — but every operator of csrc/pp_ops.cuh (all 30 kernels) is executed fro
 u8 / int32 images the device would hold, the product's wrapper method calls the host build of the `vsr_rt_*` entry point (tests/emu/), and
 the images are written back.  Driving `PropainterInpaint` on it runs the kernels at the pipeline's own shapes, pitches, channel-slice views
 and index lists, with fp16 storage between the operators: the closest thing to the device available without one."""
-import ctypes as C
-
 import numpy as np
 
 from fake_rt import FakeRuntime
