@@ -1813,7 +1813,10 @@ int vsr_rt_corr_volume(vsr_rt_t* h, uint64_t fmap1, uint64_t fmap2, int hh, int 
       L = std::make_unique<RtLayer>();
       L->kind = RtLayer::DENSE;
       ConvLayer& t = L->tc;
-      t.cin = C; t.pitch = 0; t.cout = hw; t.cout_pad = pad_cout(hw); t.ntaps = 1; t.K = C; t.bn = t.cout_pad < 256 ? t.cout_pad : 256;
+      // Cout rounded up to the 8-channel store granularity: the extra weight rows stay zero (fresh buffers are zero-filled and only hw rows are
+      // ever copied in), the extra columns land in the padding of the volume's pitch (>= round8(hw), checked above) — odd map sizes such as
+      // 25 x 135 (a 1080-wide portrait strip) would otherwise be refused by the conv launcher
+      t.cin = C; t.pitch = 0; t.cout = (hw + 7) / 8 * 8; t.cout_pad = pad_cout(t.cout); t.ntaps = 1; t.K = C; t.bn = t.cout_pad < 256 ? t.cout_pad : 256;
       t.dy[0] = 0; t.dx[0] = 0;
       t.w.ensure((size_t)t.cout_pad * C * 2);
       t.b.ensure((size_t)t.cout_pad * 4);
