@@ -160,10 +160,12 @@ class FakeRuntime:
                 assert (kh, kw, pad_t, pad_l, dil) == (3, 3, 1, 1, 1) and cin_pitch % 16 == 0 and cout % 8 == 0
             else:
                 assert stride == 1 and cout % 8 == 0 and w.shape == (cout, cin, kh, kw)
+                cin_k = (cin + 63) // 64 * 64          # pack_conv_general: whole 64-channel TMA boxes per tap, at most 81 taps
+                assert kh * kw <= 81 and (cin_k <= cin_pitch or cin_pitch % 64 == 0), "a channel slice must end on the tensor's 64-channel grid"
         if self.fp16 and not transposed and groups == 1 and cin >= 16 and cout >= 8:      # tensor-core layers hold fp16 weights; the direct kernels fp32
             w = w.astype(np.float16).astype(np.float32)
         self.layers.append(dict(w=torch.from_numpy(w), b=torch.from_numpy(np.array(bias, np.float32)), cout=cout, cin=cin, kh=kh, kw=kw,
-                                stride=stride, pad_t=pad_t, pad_l=pad_l, dil=dil, groups=groups, transposed=transposed))
+                                stride=stride, pad_t=pad_t, pad_l=pad_l, dil=dil, groups=groups, transposed=transposed, cin_pitch=cin_pitch))
         return len(self.layers) - 1
 
     def conv_create_split(self, w, bias, cout, cin, cin_pitch, kh, kw, pad_t, pad_l, dil):
@@ -187,6 +189,21 @@ class FakeRuntime:
         if self._recording("conv", lid, x, y, relu, alpha, bias_scale, out_coff, crop):
             return
         L = self.layers[lid]
+        if self.enforce:
+            # the layer was packed for ONE input pitch (TMA strides / kernel arguments are built from it): a tensor of another pitch would be
+            # read with the wrong strides on the device, silently; 16-byte stores need aligned bases, pitches and channel offsets
+            assert x.cp == L["cin_pitch"], f"conv created for input pitch {L['cin_pitch']}, called with {x.cp}"
+            assert x.ptr % 16 == 0 and y.ptr % 16 == 0 and y.cp % 8 == 0 and out_coff % 8 == 0, "16-byte accesses would fault on the device"
+        if self.enforce and not (L["groups"] == 1 and not L["transposed"] and L["cin"] >= 16 and L["cout"] >= 8):
+            # the run-time checks of vsr_rt_conv_ex for the depthwise / direct / transposed kernels: plain output tensors, symmetric padding
+            assert out_coff == 0 and y.cp % 8 == 0 and crop is None, "direct / depthwise / transposed convs store whole tensors"
+            if L["groups"] > 1:
+                assert y.cp == x.cp
+            else:
+                assert y.cp >= _r8(L["cout"])
+            if not L["transposed"]:
+                assert (y.h, y.w) == ((x.h + 2 * L["pad_t"] - L["kh"]) // L["stride"] + 1, (x.w + 2 * L["pad_l"] - L["kw"]) // L["stride"] + 1), \
+                    "these kernels derive the output size from symmetric padding"
         xin = torch.from_numpy(self._v4(x)[:, :, :, : L["cin"]].copy()).permute(0, 3, 1, 2)
         if crop is not None:   # 'same' conv on the (padded) input grid, keep the window [crop, crop + y.hw)
             assert not L["transposed"] and L["groups"] == 1 and L["cin"] >= 16 and L["cout"] >= 8, "cropped output needs a tensor-core conv"
