@@ -18,20 +18,14 @@ _NOT_OPS = {"conv_create_split", "alloc", "upload_f32", "upload_bytes", "upload_
             "capture_end", "graph_launch", "graph_destroy", "conv_create", "se_create", "overflow", "absmax", "close", "sync", "zero", "launch_count"}
 
 
-_VECTOR_OPS = {"instnorm", "context_split", "gru_rh", "gru_update", "flow_update", "prop_state", "img_prop_step", "rfc_input", "pad_replicate", "leaky",
-               "temporal_taps", "deform_cols", "gen_input", "prop_masks", "featprop_cond", "unfold7s3", "fold7s3", "layernorm", "window_attention", "frames",
-               "corr_lookup", "convex_upsample", "rfc_combine", "write_extra", "pool4", "pred_to_rgb8"}
-
-
 def _fp16_storage(cls):
     """fp16=True mode: after every operator, round every tensor argument to fp16 (what the device buffers hold); fp32 side buffers
     (flow state, FFT staging, residual masters) are addressed by raw pointers and stay fp32, like on the device."""
     def wrap(fn):
         def inner(self, *args, **kw):
-            if fn.__name__ in _VECTOR_OPS:        # the device kernels behind these move 8 halves (16 bytes) at a time
-                for a in list(args) + list(kw.values()):
-                    if hasattr(a, "ptr") and hasattr(a, "cp"):
-                        assert a.ptr % 16 == 0 and a.cp % 8 == 0, f"{fn.__name__}: tensor at +{a.ptr % 16} bytes, pitch {a.cp}: 16-byte accesses would fault on the device"
+            for a in list(args) + list(kw.values()):       # every device kernel moves 8 halves (16 bytes) at a time on its tensor arguments
+                if hasattr(a, "ptr") and hasattr(a, "cp"):
+                    assert a.ptr % 16 == 0 and a.cp % 8 == 0, f"{fn.__name__}: tensor at +{a.ptr % 16} bytes, pitch {a.cp}: 16-byte accesses would fault on the device"
             out = fn(self, *args, **kw)
             if self.fp16 and self._rec is None:
                 for a in list(args) + list(kw.values()):
