@@ -165,3 +165,25 @@ def test_weight_scaling_and_split_weights_in_fp16_simulation():
     assert unscaled.max() > 0.15 and scaled.max() < 0.1 and scaled.mean() < unscaled.mean() / 2
     assert split.max() <= scaled.max() and split.mean() <= scaled.mean() * 1.05
     assert dbnet._weight_scale(np.array([3e-7, -1e-8], np.float32)) == 2.0 ** 22 and dbnet._weight_scale(np.array([0.3], np.float32)) == 1.0
+
+
+def test_batched_mobile_detector_gates_each_image_on_cpu_runtime():
+    """The mobile model's squeeze-and-excitation gates are per-image statistics: in a batch they are computed image by image (a dark and
+    a bright frame in one launch keep their own gates)."""
+    import cv2
+    from fake_rt import FakeRuntime
+    from vsr_b200.dbnet import TextDetector
+
+    d = os.path.join(ROOT, "weights", "V5", "ch_det_fast")
+    if not os.path.exists(os.path.join(d, "inference.pdiparams")):
+        pytest.skip("mobile detector not staged under weights/V5/ch_det_fast")
+    rng = np.random.default_rng(9)
+    imgs = []
+    for i in range(2):
+        img = rng.integers(0, 255, (64, 160, 3), dtype=np.uint8) // (1 + 3 * i)
+        cv2.putText(img, f"t{i}", (10 + 30 * i, 50), cv2.FONT_HERSHEY_SIMPLEX, 1.2, (255, 255, 255), 3)
+        imgs.append(img)
+    det = TextDetector(d, runtime=FakeRuntime())
+    g = D.Graph(d)
+    for m, img in zip(det.probability_maps(imgs), imgs):
+        assert np.abs(m - D.forward(g, D.preprocess(img))[0, 0].numpy()).max() < 2e-4

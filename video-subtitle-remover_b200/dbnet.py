@@ -200,8 +200,15 @@ class _SE:
         self.se_id, self.x, self.y, self.gate, self.zeros = se_id, x, y, gate, zeros
 
     def run(self, rt):
-        rt.se_gate(self.se_id, self.x, 1.0 / self.x.scale, self.gate)
-        rt.elementwise(4, self.x, None, self.y, scale=self.gate, shift=self.zeros)
+        for j in range(self.x.n):          # the gate is a per-image statistic: one image of the batch at a time (same stream, one gate buffer)
+            xj, yj = _image(self.x, j), _image(self.y, j)
+            rt.se_gate(self.se_id, xj, 1.0 / self.x.scale, self.gate)
+            rt.elementwise(4, xj, None, yj, scale=self.gate, shift=self.zeros)
+
+
+def _image(t, j):
+    """image j of a batch tensor as a single-image view"""
+    return t if t.n == 1 else _Tensor(t.ptr + j * t.h * t.w * t.cp * 2, t.c, t.h, t.w, t.cp, t.perm, n=1)
 
 
 class _Affine:
@@ -652,8 +659,6 @@ class TextDetector:
                 x = val[n.ins[0]]
                 if [int(v) for v in val[n.ins[1]]] != [1, 1] or x.perm is not None:
                     raise _capi.VsrError("only global average pooling of a plain tensor is supported")
-                if x.n != 1:
-                    raise _capi.VsrError("squeeze-and-excitation gates are per image: the mobile detector runs one frame per launch")
 
                 def conv_bias(node):
                     wt = np.asarray(val[node.ins[1]], np.float32)
