@@ -394,7 +394,7 @@ def case_unfold_fold(make, gelu):
     x = d.tensor(n, h, w, Cc)
     tok = d.tensor(n, fh, fw, 49 * Cc + 8)
     d.call("unfold7s3", x, tok, gelu)
-    tok.check("unfold7s3", ulps=2)
+    tok.check("unfold7s3", ulps=2, atol=2e-4 if gelu else 0.0)      # 1 + erf(x / sqrt 2) cancels for x < -3: erff implementations differ there
     tok.push()
     for norm in (False, True):
         out = d.tensor(n, h, w, Cc, fill=False)
