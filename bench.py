@@ -496,13 +496,13 @@ def run_propainter(args, rank, world, local):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = eng._rt.launch_count()
+    l0 = eng._rt.launch_count
     t0 = time.perf_counter()
     for _ in range(args.steps):
         eng(frames, mask)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    launches = eng._rt.launch_count() - l0
+    launches = eng._rt.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <vector>
+#include <memory>
 #include "cuda_emu.h"
 #include "../../include/vsr_b200.h"              // the extracted definitions must agree with the shipped prototypes
 #include "../../video-subtitle-remover_b200/csrc/pp_ops.cuh"
@@ -52,6 +54,7 @@ static inline bool emu_lockstep(const char* kernel) {
 struct vsr_rt {
   vsr::Ctx ctx;
   vsr::DevBuf frames8, norm_stats, plane;
+  std::vector<std::unique_ptr<vsr::DevBuf>> bufs;     // "device" allocations of vsr_rt_alloc below
   bool capturing = false;
 };
 namespace vsr {
@@ -61,6 +64,22 @@ static void rt_sync(vsr_rt*) {}
 using namespace vsr;
 #define EMU_LAUNCH(kernel, grid, threads, ...) emu_launch(dim3(grid), (unsigned)(threads), emu_lockstep(#kernel), [&] { kernel(__VA_ARGS__); })
 extern "C" {
+// host restatements of the runtime's memory entry points (malloc / memcpy), so that the DEVICE flavour of the operator suite
+// (tests/pp_op_cases.py DeviceBackend: alloc, upload, launch, download) can be rehearsed on the CPU as well
+int vsr_rt_create(vsr_rt_t** out, int) { *out = new vsr_rt(); return VSR_OK; }
+void vsr_rt_destroy(vsr_rt_t* h) { delete h; }
+int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr) {
+  return guarded([&] {
+    REQUIRE(h && bytes > 0 && dev_ptr, "bad arguments");
+    h->bufs.push_back(std::make_unique<DevBuf>());
+    h->bufs.back()->ensure((size_t)bytes);
+    *dev_ptr = (uint64_t)(uintptr_t)h->bufs.back()->p;
+  });
+}
+int vsr_rt_upload(vsr_rt_t*, uint64_t dev_ptr, const void* host, int64_t bytes) { std::memcpy((void*)(uintptr_t)dev_ptr, host, (size_t)bytes); return VSR_OK; }
+int vsr_rt_download(vsr_rt_t*, uint64_t dev_ptr, void* host, int64_t bytes) { std::memcpy(host, (const void*)(uintptr_t)dev_ptr, (size_t)bytes); return VSR_OK; }
+int vsr_rt_sync(vsr_rt_t*) { return VSR_OK; }
+int64_t vsr_rt_launch_count(vsr_rt_t* h) { return h->ctx.launches; }
 vsr_rt* emu_rt_create() { return new vsr_rt(); }
 void emu_rt_destroy(vsr_rt* h) { delete h; }
 const char* vsr_last_error(void) { return g_err.c_str(); }

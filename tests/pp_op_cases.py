@@ -85,7 +85,7 @@ class DeviceBackend:
         return _GenRuntime("cuda:0")
 
     def launches(self, rt):
-        return rt.launch_count()
+        return rt.launch_count
 
     def place(self, rt, host):
         p = rt.alloc(max(host.nbytes, 16))

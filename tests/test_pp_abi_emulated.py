@@ -29,3 +29,24 @@ def backend():
 @pytest.mark.parametrize("name,case,params", CASES, ids=[c[0] for c in CASES])
 def test_operator(backend, name, case, params):
     case(lambda seed: Dual(backend, seed), *params)
+
+
+@pytest.mark.parametrize("name,case,params", CASES, ids=[c[0] for c in CASES])
+def test_device_flavour_of_the_suite_rehearsed_on_the_host_build(backend, monkeypatch, name, case, params):
+    """tests/test_gpu_zz_pp_ops.py drives the cases through `DeviceBackend` (vsr_rt_create / alloc / upload / launch / download); the host build
+    restates those memory entry points with malloc / memcpy, so that this code path — not only the zero-copy one above — runs on the CPU too."""
+    from pp_op_cases import DeviceBackend
+    from vsr_b200 import dbnet
+
+    monkeypatch.setattr(dbnet, "_device_index", lambda device: 0)
+    made = []
+
+    def make(seed):
+        made.append(Dual(DeviceBackend(), seed))
+        return made[-1]
+
+    try:
+        case(make, *params)
+    finally:
+        for d in made:
+            d.close()
