@@ -33,7 +33,7 @@ def _fp16_storage(cls):
                         v = self._v4(a)
                         v[:] = v.astype(np.float16).astype(np.float32)
             return out
-        inner.__name__, inner.__doc__ = fn.__name__, fn.__doc__
+        inner.__name__, inner.__doc__, inner.__wrapped__ = fn.__name__, fn.__doc__, fn
         return inner
 
     for name, fn in list(vars(cls).items()):
@@ -177,11 +177,14 @@ class FakeRuntime:
 
     def conv_ex(self, lid, x, y, relu, out_coff=0, crop=None):
         """crop None: a plain conv of any kernel family (possibly into a channel slice); (top, left): the cropped-store path."""
-        self.conv(lid, x, y, relu, 1.0, 1.0, out_coff, crop)
+        if not self._recording("conv_ex", lid, x, y, relu, out_coff, crop):
+            self._conv(lid, x, y, relu, 1.0, 1.0, out_coff, crop)
 
-    def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0, out_coff=0, crop=None):
-        if self._recording("conv", lid, x, y, relu, alpha, bias_scale, out_coff, crop):
-            return
+    def conv(self, lid, x, y, relu, alpha=1.0, bias_scale=1.0):
+        if not self._recording("conv", lid, x, y, relu, alpha, bias_scale):
+            self._conv(lid, x, y, relu, alpha, bias_scale, 0, None)
+
+    def _conv(self, lid, x, y, relu, alpha, bias_scale, out_coff, crop):
         L = self.layers[lid]
         if self.enforce:
             # the layer was packed for ONE input pitch (TMA strides / kernel arguments are built from it): a tensor of another pitch would be

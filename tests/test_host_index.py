@@ -132,3 +132,31 @@ def test_bench_input_generators_equal_the_oracle_generators():
     for n, H, W, seed in ((5, 128, 192, 23), (2, 1080, 1920, 0), (3, 720, 1280, 301)):
         assert all(np.array_equal(a, b) for a, b in zip(O.synthetic_clip(n, H, W, seed=seed), S.synthetic_clip(n, H, W, seed=seed)))
         assert np.array_equal(O.default_mask(H, W), S.default_mask(H, W))
+
+
+def test_runtime_stand_in_has_the_interface_of_the_device_runtime():
+    """The pipelines are developed against tests/fake_rt.py and shipped against the ctypes wrapper classes (`_DeviceRuntime` ... `_GenRuntime`):
+    duck typing hides a method that is a property on one side, or takes other arguments, until the first run on a GPU.  Every public member of
+    the stand-in must exist on the device wrapper with the same kind and the same parameters (names, order, defaults)."""
+    import inspect
+
+    from fake_rt import FakeRuntime
+    from vsr_b200.propainter_generator import _GenRuntime
+
+    only_stand_in = {"upload_ints", "launches", "bufs", "layers", "graphs", "rescaled", "enforce", "fp16"}
+    problems = []
+    for name in dir(FakeRuntime):
+        if name.startswith("_") or name in only_stand_in:
+            continue
+        fake, real = inspect.getattr_static(FakeRuntime, name), inspect.getattr_static(_GenRuntime, name, None)
+        if real is None:
+            problems.append(f"{name}: missing on the device wrapper")
+        elif isinstance(fake, property) != isinstance(real, property):
+            problems.append(f"{name}: property on one side, method on the other")
+        elif not isinstance(fake, property):
+            fs, rs = inspect.signature(inspect.unwrap(fake)), inspect.signature(real)
+            fp = [(p.name, p.default) for p in fs.parameters.values()]
+            rp = [(p.name, p.default) for p in rs.parameters.values()]
+            if fp != rp:
+                problems.append(f"{name}: stand-in {fs} != device wrapper {rs}")
+    assert not problems, "\n".join(problems)
