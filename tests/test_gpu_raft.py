@@ -18,11 +18,12 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.path.exists(PATH), reason="raft-things.pth not staged under weights/propainter")]
 
 
-def test_raft_flows_vs_oracle(capi):
+def check_raft_flows(runtime=None):
+    """the stage check itself; `runtime` = None runs on cuda:0, tests/test_stage_checks_rehearsed_cpu.py passes the hybrid CPU runtime"""
     from vsr_b200.raft_flow import RaftFlow
 
     frames = O.synthetic_clip(3, 128, 192, seed=23)
-    ff, fb = RaftFlow(PATH, "cuda:0")(frames)
+    ff, fb = RaftFlow(PATH, "cuda:0", runtime=runtime)(frames)
     x = torch.from_numpy(np.stack([f[:, :, ::-1] for f in frames]).astype(np.float32) / 255).permute(0, 3, 1, 2)[None] * 2 - 1
     wf, wb = R.raft_bi(R.load_weights(PATH), x)
     for got, want in ((ff, wf[0].numpy()), (fb, wb[0].numpy())):
@@ -30,8 +31,12 @@ def test_raft_flows_vs_oracle(capi):
         assert np.isfinite(got).all() and epe.mean() <= 0.01 and epe.max() <= 0.1, (float(epe.mean()), float(epe.max()))
 
 
-def test_image_propagation_vs_oracle(capi):
-    """P5 on the device (gated like the RAFT test): exact mask agreement and fp16-level frame agreement with the oracle."""
+def test_raft_flows_vs_oracle(capi):
+    check_raft_flows()
+
+
+def check_image_propagation(runtime=None):
+    """P5: exact mask agreement and fp16-level frame agreement with the oracle."""
     import sys
 
     from conftest import GOLDEN
@@ -45,7 +50,7 @@ def test_image_propagation_vs_oracle(capi):
     frames, mask = inputs()[:2]
     _, md = P.read_mask(mask, len(frames))
     ff, fb = z["pred_flows_f"][0].astype(np.float32), z["pred_flows_b"][0].astype(np.float32)
-    rt = _PropRuntime("cuda:0")
+    rt = runtime if runtime is not None else _PropRuntime("cuda:0")
     upd, um = propagate_images_host(rt, frames, md[0], ff, fb)
     rt.close()
     x = torch.from_numpy(np.stack([f[:, :, ::-1] for f in frames]).astype(np.float32) / 255).permute(0, 3, 1, 2)[None] * 2 - 1
@@ -55,8 +60,13 @@ def test_image_propagation_vs_oracle(capi):
     assert (um != want_m[0].numpy()).mean() < 1e-4 and np.abs(upd - want).max() < 2e-3
 
 
-def test_flow_completion_vs_oracle(capi):
-    """P4 on the device (gated).  fp16 simulation: 2.4e-3 px; bar: completed flows within 0.03 px of the oracle."""
+def test_image_propagation_vs_oracle(capi):
+    """P5 on the device (gated like the RAFT test)."""
+    check_image_propagation()
+
+
+def check_flow_completion(runtime=None):
+    """P4.  fp16 simulation: 2.4e-3 px; bar: completed flows within 0.03 px of the oracle."""
     import sys
 
     from conftest import GOLDEN
@@ -74,10 +84,15 @@ def test_flow_completion_vs_oracle(capi):
     frames, mask = inputs()[:2]
     fm, _ = P.read_mask(mask, len(frames))
     gf, gb = z["gt_flows_f"][0].astype(np.float32), z["gt_flows_b"][0].astype(np.float32)
-    pf, pb = FlowCompletion(path, "cuda:0").complete_host(gf, gb, fm[0])
+    pf, pb = FlowCompletion(path, "cuda:0", runtime=runtime).complete_host(gf, gb, fm[0])
     masks = torch.from_numpy(np.stack(fm).astype(np.float32) / 255)[None, :, None]
     wf, wb = C.complete_bidirectional(C.load_weights(path), torch.from_numpy(gf)[None], torch.from_numpy(gb)[None], masks)
     assert np.abs(pf - wf[0].numpy()).max() < 0.03 and np.abs(pb - wb[0].numpy()).max() < 0.03
+
+
+def test_flow_completion_vs_oracle(capi):
+    """P4 on the device (gated)."""
+    check_flow_completion()
 
 
 def test_propainter_pipeline_vs_reference_frames(capi):
