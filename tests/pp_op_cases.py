@@ -248,9 +248,8 @@ def case_context_split_and_gru(make):
     hio.check("gru_update")
 
 
-def case_corr_pool_and_lookup(make):
-    d = make(3)
-    hh, ww = 8, 12                      # 1/8-resolution map; level l has (hh >> l, ww >> l) targets per source pixel
+def case_corr_pool_and_lookup(make, hh=8, ww=12):
+    d = make(3)                         # hh x ww: the 1/8-resolution map; level l has (hh >> l, ww >> l) targets per source pixel (odd sizes drop a row / column)
     px = hh * ww
     H, W = hh, ww
     pitch = (H * W + 7) // 8 * 8
@@ -296,9 +295,8 @@ def case_convex_upsample(make):
     assert np.abs(out.host).max() > 1
 
 
-def case_img_prop_step(make):
+def case_img_prop_step(make, H=12, W=20):
     d = make(6)
-    H, W = 12, 20
     prev, cur = d.tensor(1, H, W, 8), d.tensor(1, H, W, 8)
     prev.view[..., 3] = d.rng.random((1, H, W)) > 0.93       # few holes left in the source frame, half of the current frame missing
     cur.view[..., 3] = d.rng.random((1, H, W)) > 0.5
@@ -344,11 +342,11 @@ def case_pad_leaky_taps_extra(make):
     dst.check("write_extra", ulps=0)
 
 
-def case_deform_cols(make, two_inputs, with_flow, G=4):
+def case_deform_cols(make, two_inputs, with_flow, G=4, Cc=32):
     d = make(9)
-    n, H, W, Cc = 2, 6, 7, 32                    # G = 4: 8 channels per group, the 16-byte path; G = 8: the scalar path
-    xa = d.tensor(n, H, W, 64)
-    xb = d.tensor(n, H, W, 64) if two_inputs else None
+    n, H, W = 2, 6, 7                            # 8 channels per group (Cc / G): the 16-byte path; otherwise the scalar path
+    xa = d.tensor(n, H, W, max(64, Cc))
+    xb = d.tensor(n, H, W, max(64, Cc)) if two_inputs else None
     om = d.tensor(n, H, W, max(128, (27 * G + 7) // 8 * 8), 0.7)
     cols = d.tensor(n, H, W, 9 * Cc + 32)
     fl = d.f32(d.rng.standard_normal((n * H * W, 2)) * 2) if with_flow else 0
@@ -387,9 +385,9 @@ def case_featprop_cond(make):
     assert 0.05 < cond.view[..., 2 * Cc + 2].mean() < 0.95
 
 
-def case_unfold_fold(make, gelu):
+def case_unfold_fold(make, gelu, h=10, w=13):
     d = make(12)
-    n, h, w, Cc = 2, 10, 13, 8
+    n, Cc = 2, 8
     fh, fw = (h + 6 - 7) // 3 + 1, (w + 6 - 7) // 3 + 1
     x = d.tensor(n, h, w, Cc)
     tok = d.tensor(n, fh, fw, 49 * Cc + 8)
@@ -420,15 +418,16 @@ def case_layernorm_pool(make):
     out.check("pool4", ulps=3, atol=1e-3)
 
 
-def case_window_attention(make, heads=1):
+def case_window_attention(make, heads=1, Hn=10, Wn=18, ph=2, pw=2, n_valid=23):
     d = make(14)
-    T, Hn, Wn, Cc, ph, pw = 3, 10, 18, 128 * heads, 2, 2
+    T, Cc = 3, 128 * heads
     q, k, v = (d.tensor(T, Hn, Wn, Cc, 1.5) for _ in range(3))
     kp, vp = d.tensor(T, ph, pw, Cc, 1.5), d.tensor(T, ph, pw, Cc, 1.5)
-    valid = d.ints(np.sort(d.rng.choice(180, 23, replace=False)))
-    tind, masked = d.ints([0, 2]), d.ints([1, 0, 0, 1])
+    valid = d.ints(np.sort(d.rng.choice(180, n_valid, replace=False)))
+    n_win = (Hn // 5) * (Wn // 9)
+    tind, masked = d.ints([0, 2]), d.ints([(i * 7 + 1) % 3 != 0 for i in range(n_win)])
     out = d.tensor(T, Hn, Wn, Cc, fill=False)
-    d.call("window_attention", q, k, v, kp, vp, valid, 23, tind, 2, masked, out)
+    d.call("window_attention", q, k, v, kp, vp, valid, n_valid, tind, 2, masked, out)
     out.check("window_attention", ulps=4, atol=2e-3)
 
 
@@ -456,19 +455,21 @@ CASES = [
     ("frames_and_states", case_frames_and_states, ()),
     ("instnorm", case_instnorm, (0,)), ("instnorm_relu", case_instnorm, (1,)), ("instnorm_128ch", case_instnorm, (1, 128)),
     ("context_split_and_gru", case_context_split_and_gru, ()),
-    ("corr_pool_and_lookup", case_corr_pool_and_lookup, ()),
+    ("corr_pool_and_lookup", case_corr_pool_and_lookup, ()), ("corr_pool_and_lookup_odd_map", case_corr_pool_and_lookup, (9, 17)),
     ("flow_update_refresh", case_flow_update, (0,)), ("flow_update_add", case_flow_update, (1,)),
     ("convex_upsample", case_convex_upsample, ()),
-    ("img_prop_step", case_img_prop_step, ()),
+    ("img_prop_step", case_img_prop_step, ()), ("img_prop_step_wider_than_a_block", case_img_prop_step, (5, 300)),
     ("rfc_input_combine", case_rfc_input_combine, (False,)), ("rfc_input_combine_reversed", case_rfc_input_combine, (True,)),
     ("pad_leaky_taps_extra", case_pad_leaky_taps_extra, ()),
     ("deform_cols", case_deform_cols, (False, False)), ("deform_cols_two_inputs_flow", case_deform_cols, (True, True)),
-    ("deform_cols_4_channel_groups", case_deform_cols, (True, True, 8)),
+    ("deform_cols_4_channel_groups", case_deform_cols, (True, True, 8)), ("deform_cols_128ch_16_groups", case_deform_cols, (True, True, 16, 128)),
     ("gen_input_flow_down_masks", case_gen_input_flow_down_masks, ()),
     ("featprop_cond", case_featprop_cond, ()),
-    ("unfold_fold", case_unfold_fold, (False,)), ("unfold_fold_gelu", case_unfold_fold, (True,)),
+    ("unfold_fold", case_unfold_fold, (False,)), ("unfold_fold_gelu", case_unfold_fold, (True,)), ("unfold_fold_11x15", case_unfold_fold, (False, 11, 15)),
+    ("unfold_fold_pipeline_map", case_unfold_fold, (False, 32, 48)),
     ("layernorm_pool", case_layernorm_pool, ()),
     ("window_attention", case_window_attention, ()), ("window_attention_two_heads", case_window_attention, (2,)),
+    ("window_attention_pipeline_geometry", case_window_attention, (1, 15, 27, 3, 4, 148)),
     ("pred_to_rgb8", case_pred_to_rgb8, ()),
     ("entry_points_reject_bad_arguments", case_entry_points_reject_bad_arguments, ()),
 ]
