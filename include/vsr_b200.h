@@ -128,6 +128,7 @@ void vsr_rt_destroy(vsr_rt_t* h);
 int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr);             /* zero-initialised, freed with the runtime */
 int vsr_rt_upload(vsr_rt_t* h, uint64_t dev_ptr, const void* host, int64_t bytes);
 int vsr_rt_download(vsr_rt_t* h, uint64_t dev_ptr, void* host, int64_t bytes);
+int vsr_rt_copy(vsr_rt_t* h, uint64_t dst, uint64_t src, int64_t bytes);         /* device -> device on the runtime's stream (ProPainter: chunk results of propainter_inpaint.py:254-304 into the whole-sequence buffers) */
 int vsr_rt_sync(vsr_rt_t* h);
 int64_t vsr_rt_launch_count(vsr_rt_t* h);
 /* conv2d / depthwise_conv2d / conv2d_transpose of the PIR program with batch-norm and bias already folded into

@@ -222,10 +222,22 @@ def generator(w, masked_frames, flows_f, flows_b, masks_in, masks_updated, l_t, 
         return torch.tanh(_c2(w, "decoder.6", y)).view(b, l_t, 3, H, W)
 
 
+def sub_ranges(length: int, sub: int, pad: int) -> List[tuple]:
+    """The overlapped chunks of :254-272 / :284-304: for f = 0, sub, 2 sub, ...: run on [s, e) = [f - pad, f + sub + pad) clipped to the
+    sequence and keep the part [keep_s, keep_e) of the chunk's result that belongs to [f, f + sub).  -> [(s, e, keep_s, keep_e)]"""
+    out = []
+    for f in range(0, length, sub):
+        s, e = max(0, f - pad), min(length, f + sub + pad)
+        out.append((s, e, f - s, (e - s) - (e - min(length, f + sub))))
+    return out
+
+
 def inpaint(weights: Dict[str, Dict[str, torch.Tensor]], frames_bgr: Sequence[np.ndarray], mask: np.ndarray, raft_iters: int = P.RAFT_ITERS,
-            taps: dict | None = None) -> List[np.ndarray]:
-    """PropainterInpaint.inpaint (propainter_inpaint.py:192-361) for len(frames) <= sub_video_length (= 80) and the RAFT
-    clip lengths of :209-236; `weights` = {"raft": ..., "rfc": ..., "gen": ...}.  Returns BGR uint8 frames."""
+            taps: dict | None = None, sub_video_length: int = 80) -> List[np.ndarray]:
+    """PropainterInpaint.inpaint (propainter_inpaint.py:192-361) with the RAFT clip lengths of :209-236 and, for sequences longer than
+    `sub_video_length`, the overlapped chunks of flow completion (:251-276, pad 5) and image propagation (:281-312, chunks of
+    min(100, sub_video_length) frames, pad 10) and the capped reference frames of the window loop (:321-324);
+    `weights` = {"raft": ..., "rfc": ..., "gen": ...}.  Returns BGR uint8 frames."""
     from oracle import raft_oracle as R
     from oracle import rfc_oracle as C
 
@@ -246,14 +258,31 @@ def inpaint(weights: Dict[str, Dict[str, torch.Tensor]], frames_bgr: Sequence[np
         gf, gb = torch.cat(ff, 1), torch.cat(fb, 1)
     else:
         gf, gb = R.raft_bi(weights["raft"], x, raft_iters)
-    pf, pb = C.complete_bidirectional(weights["rfc"], gf, gb, flow_masks)
-    prop, upd = P.img_propagation(x * (1 - masks), pf, pb, masks)
-    updated = P.updated_frames(x, masks, prop)
+    if gf.shape[1] > sub_video_length:
+        parts = []
+        for s, e, ks, ke in sub_ranges(gf.shape[1], sub_video_length, 5):
+            a, b_ = C.complete_bidirectional(weights["rfc"], gf[:, s:e], gb[:, s:e], flow_masks[:, s:e + 1])
+            parts.append((a[:, ks:ke], b_[:, ks:ke]))
+        pf, pb = torch.cat([a for a, _ in parts], 1), torch.cat([b_ for _, b_ in parts], 1)
+    else:
+        pf, pb = C.complete_bidirectional(weights["rfc"], gf, gb, flow_masks)
+    sub_prop = min(100, sub_video_length)
+    if T > sub_prop:
+        ups, ums = [], []
+        for s, e, ks, ke in sub_ranges(T, sub_prop, 10):
+            pr, um = P.img_propagation((x * (1 - masks))[:, s:e], pf[:, s:e - 1], pb[:, s:e - 1], masks[:, s:e])
+            ups.append(P.updated_frames(x[:, s:e], masks[:, s:e], pr)[:, ks:ke])
+            ums.append(um[:, ks:ke])
+        updated, upd = torch.cat(ups, 1), torch.cat(ums, 1)
+        prop = None
+    else:
+        prop, upd = P.img_propagation(x * (1 - masks), pf, pb, masks)
+        updated = P.updated_frames(x, masks, prop)
     if taps is not None:
         taps.update(gt_flows_f=gf, gt_flows_b=gb, pred_flows_f=pf, pred_flows_b=pb, prop_frames=prop, prop_masks=upd)
     comp: List = [None] * T
     binary = masks[0].permute(0, 2, 3, 1).numpy().astype(np.uint8)
-    for nb, refs in P.window_schedule(T):
+    for nb, refs in P.window_schedule(T, sub_video_length):
         ids = nb + refs
         pred = generator(weights["gen"], updated[:, ids], pf[:, nb[:-1]], pb[:, nb[:-1]], masks[:, ids], upd[:, ids], len(nb))
         pred = ((pred.view(-1, 3, H, W) + 1) / 2).permute(0, 2, 3, 1).numpy() * 255

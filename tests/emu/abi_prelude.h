@@ -78,6 +78,7 @@ int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr) {
 }
 int vsr_rt_upload(vsr_rt_t*, uint64_t dev_ptr, const void* host, int64_t bytes) { std::memcpy((void*)(uintptr_t)dev_ptr, host, (size_t)bytes); return VSR_OK; }
 int vsr_rt_download(vsr_rt_t*, uint64_t dev_ptr, void* host, int64_t bytes) { std::memcpy(host, (const void*)(uintptr_t)dev_ptr, (size_t)bytes); return VSR_OK; }
+int vsr_rt_copy(vsr_rt_t*, uint64_t dst, uint64_t src, int64_t bytes) { std::memmove((void*)(uintptr_t)dst, (const void*)(uintptr_t)src, (size_t)bytes); return VSR_OK; }
 int vsr_rt_sync(vsr_rt_t*) { return VSR_OK; }
 int64_t vsr_rt_launch_count(vsr_rt_t* h) { return h->ctx.launches; }
 vsr_rt* emu_rt_create() { return new vsr_rt(); }

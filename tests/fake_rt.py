@@ -14,7 +14,7 @@ def _r8(x):
     return (x + 7) // 8 * 8
 
 
-_NOT_OPS = {"conv_create_split", "alloc", "upload_f32", "upload_bytes", "upload_to", "upload_ints", "download", "download_channel", "download_f32", "capture_begin",
+_NOT_OPS = {"copy_bytes", "conv_create_split", "alloc", "upload_f32", "upload_bytes", "upload_to", "upload_ints", "download", "download_channel", "download_f32", "capture_begin",
             "capture_end", "graph_launch", "graph_destroy", "conv_create", "se_create", "overflow", "absmax", "close", "sync", "zero", "launch_count"}
 
 
@@ -644,6 +644,12 @@ class FakeRuntime:
         else:                              # u8 masks: no pointer arithmetic on them, one slot per element
             self.bufs[h] = arr.astype(np.float32).reshape(-1)
         return h
+
+    def copy_bytes(self, src, dst, nbytes):
+        assert self._rec is None and src % 2 == 0 and dst % 2 == 0 and nbytes % 2 == 0
+        a, ao = self._resolve(src)
+        b, bo = self._resolve(dst)
+        b[bo: bo + nbytes // 2] = a[ao: ao + nbytes // 2]          # slots are 2 bytes of device memory each, whatever they hold
 
     def upload_to(self, ptr, arr):
         arr = np.ascontiguousarray(arr)

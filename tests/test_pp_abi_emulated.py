@@ -50,3 +50,14 @@ def test_device_flavour_of_the_suite_rehearsed_on_the_host_build(backend, monkey
     finally:
         for d in made:
             d.close()
+
+
+def test_copy_bytes_through_the_wrapper(backend):
+    import numpy as np
+
+    from pp_op_cases import bind_wrapper
+
+    rt = bind_wrapper(backend.lib)
+    src, dst = np.arange(64, dtype=np.float32), np.zeros(64, np.float32)
+    rt.copy_bytes(src.ctypes.data + 32, dst.ctypes.data + 64, 96)                 # (src, dst, bytes): 24 floats from src[8:] to dst[16:]
+    assert np.array_equal(dst[16:40], src[8:32]) and not dst[:16].any() and not dst[40:].any()

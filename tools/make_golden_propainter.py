@@ -78,5 +78,28 @@ def main():
     print(p, os.path.getsize(p), {k: tuple(v.shape) for k, v in taps.items()}, np.stack(comp).shape, np.stack(call).shape)
 
 
+def long_inputs():
+    """14 frames with sub_video_length = 4: the overlapped chunks of flow completion and image propagation (propainter_inpaint.py:251-312)
+    and the capped reference frames of the window loop (:321-324) all take their long-sequence branches."""
+    H, W, T = 128, 192, 14
+    return O.synthetic_clip(T, H, W, seed=25), O.create_mask((H, W), [(40, 150, 84, 104)]), 4
+
+
+def main_long():
+    import torchvision
+
+    torchvision.ops.deform_conv2d = deform_conv2d
+    ref_import.install()
+    from backend.inpaint.propainter_inpaint import PropainterInpaint
+
+    torch.manual_seed(0)
+    frames, mask, sub = long_inputs()
+    m = PropainterInpaint(torch.device("cpu"), os.path.join(ROOT, "weights", "propainter"), sub_video_length=sub, use_fp16=False)
+    comp = m.inpaint([f.copy() for f in frames], mask)
+    p = os.path.join(ROOT, "tests", "golden", "propainter_long.npz")
+    np.savez_compressed(p, comp=np.stack(comp))
+    print(p, os.path.getsize(p), np.stack(comp).shape)
+
+
 if __name__ == "__main__":
-    main()
+    main_long() if sys.argv[1:] == ["long"] else main()

@@ -82,6 +82,7 @@ _PROTOS = {
     "vsr_rt_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
     "vsr_rt_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]),
     "vsr_rt_download": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]),
+    "vsr_rt_copy": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64]),
     "vsr_rt_sync": (C.c_int, [C.c_void_p]),
     "vsr_rt_launch_count": (C.c_int64, [C.c_void_p]),
     "vsr_rt_conv_create": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -1649,6 +1649,13 @@ int vsr_rt_download(vsr_rt_t* h, uint64_t dev_ptr, void* host, int64_t bytes) {
     rt_sync(h);
   });
 }
+int vsr_rt_copy(vsr_rt_t* h, uint64_t dst, uint64_t src, int64_t bytes) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(dst && src && bytes > 0, "bad arguments");
+    CK(cudaMemcpyAsync((void*)(uintptr_t)dst, (const void*)(uintptr_t)src, (size_t)bytes, cudaMemcpyDeviceToDevice, h->ctx.stream));
+  });
+}
 int vsr_rt_sync(vsr_rt_t* h) {
   return guarded([&] {
     rt_check(h);

@@ -25,6 +25,10 @@ class _PropRuntime(_RaftRuntime):
     def prop_state(self, frames, mask_u8, prop, out):
         _capi.check(self.L.vsr_rt_prop_state(self.h, frames.ptr, mask_u8, prop.ptr if prop is not None else 0, frames.n, frames.h, frames.w, out.ptr))
 
+    def copy_bytes(self, src: int, dst: int, nbytes: int):
+        """device -> device, in stream order"""
+        _capi.check(self.L.vsr_rt_copy(self.h, dst, src, nbytes))
+
     def upload_bytes(self, arr: np.ndarray) -> int:
         arr = np.ascontiguousarray(arr)
         p = self.alloc(max(arr.nbytes, 16))

@@ -7,9 +7,9 @@ all kernels compile for sm_100a, but the class has NOT run on a B200 yet (round 
 
 Stages (one shared device runtime): read_mask (host, propainter_tools) -> RaftFlow (P3, raft_flow.py) -> FlowCompletion (P4,
 flow_completion.py) -> propagate_images (P5, flow_propagation.py) -> per window: Generator.encode_and_propagate + transform_and_decode
-(P6, propainter_generator.py) -> composite / blend (P7, host, propainter_tools).  Clips longer than `sub_video_length` (the reference
-chunks flow completion and propagation with overlaps there, propainter_inpaint.py:244-306) are not supported yet: `video_inpaint`
-feeds batches of at most `propainterMaxLoadNum` frames, which is what `sub_video_length` is set to (main.py:171).
+(P6, propainter_generator.py) -> composite / blend (P7, host, propainter_tools).  Clips longer than `sub_video_length` go through the
+reference's overlapped chunks of flow completion and image propagation and its capped reference frames (propainter_inpaint.py:251-324);
+`video_inpaint` itself feeds batches of at most `propainterMaxLoadNum` frames, which is what `sub_video_length` is set to (main.py:171).
 """
 import os
 from typing import List, Sequence
@@ -65,8 +65,6 @@ class PropainterInpaint:
         to the unsharded result — windows overlap and P7's 0.5 / 0.5 blend is order dependent, so the blend always runs in schedule order."""
         frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
         T, (H, W) = len(frames), frames[0].shape[:2]
-        if T > self.sub_video_length:
-            raise _capi.VsrError(f"{T} frames > sub_video_length {self.sub_video_length}: chunked completion / propagation is not supported yet")
         if T < 2:
             raise _capi.VsrError("ProPainter needs at least two frames (the reference routes single frames to LAMA, main.py:220)")
         rt = self._rt
@@ -76,10 +74,25 @@ class PropainterInpaint:
         up = lambda arr: (lambda p: (rt.upload_to(p, arr), p)[1])(self._arena.alloc(max(np.ascontiguousarray(arr).nbytes, 16)))   # noqa: E731
         ff_dev, fb_dev = up(np.ascontiguousarray(gf, np.float32)), up(np.ascontiguousarray(gb, np.float32))
         fmask_dev, mask_dev = up(flow_masks[0]), up(masks_dilated[0])
-        pf_dev, pb_dev = self.fix_flow_complete.complete(ff_dev, fb_dev, fmask_dev, T - 1, H, W)
-        x = _Tensor(self._arena.alloc(T * H * W * 8 * 2), 3, H, W, 8, n=T)
+        N, fbytes, sbytes = T - 1, 2 * H * W * 4, H * W * 8 * 2         # flows, bytes of one flow field / of one frame of the state tensor
+        if N > self.sub_video_length:                                       # :251-276: overlapped chunks (pad 5), the middle of each kept
+            pf_dev, pb_dev = self._arena.alloc(N * fbytes), self._arena.alloc(N * fbytes)
+            for s, e, ks, ke in PT.sub_ranges(N, self.sub_video_length, 5):
+                a, b = self.fix_flow_complete.complete(ff_dev + s * fbytes, fb_dev + s * fbytes, fmask_dev, e - s, H, W)
+                rt.copy_bytes(a + ks * fbytes, pf_dev + (s + ks) * fbytes, (ke - ks) * fbytes)   # before the next chunk reuses the buffers
+                rt.copy_bytes(b + ks * fbytes, pb_dev + (s + ks) * fbytes, (ke - ks) * fbytes)
+        else:
+            pf_dev, pb_dev = self.fix_flow_complete.complete(ff_dev, fb_dev, fmask_dev, N, H, W)
+        x = _Tensor(self._arena.alloc(T * sbytes), 3, H, W, 8, n=T)
         rt.frames(frames, x)
-        state = propagate_images(rt, x, mask_dev, pf_dev, pb_dev, self._arena)
+        sub_prop = min(100, self.sub_video_length)
+        if T > sub_prop:                                                    # :281-312: chunks of min(100, sub_video_length) frames, pad 10
+            state = _Tensor(self._arena.alloc(T * sbytes), 4, H, W, 8, n=T)
+            for s, e, ks, ke in PT.sub_ranges(T, sub_prop, 10):
+                part = propagate_images(rt, _Tensor(x.ptr + s * sbytes, 3, H, W, 8, n=e - s), mask_dev, pf_dev + s * fbytes, pb_dev + s * fbytes, self._arena)
+                rt.copy_bytes(part.ptr + ks * sbytes, state.ptr + (s + ks) * sbytes, (ke - ks) * sbytes)
+        else:
+            state = propagate_images(rt, x, mask_dev, pf_dev, pb_dev, self._arena)
         comp: List = [None] * T
         binary = (masks_dilated[0] > 0).astype(np.uint8)[None, :, :, None]
         rgb = [np.ascontiguousarray(f[:, :, ::-1]) for f in frames]

@@ -58,6 +58,17 @@ def get_ref_index(mid: int, neighbor_ids: Sequence[int], length: int, ref_stride
     return out
 
 
+def sub_ranges(length: int, sub: int, pad: int) -> List[Tuple[int, int, int, int]]:
+    """The overlapped chunks a long sequence is processed in (flow completion :254-272 with pad 5, image propagation :284-304 with pad 10):
+    chunk k covers [s, e) = [k*sub - pad, (k+1)*sub + pad) clipped to the sequence, and [keep_s, keep_e) of ITS result is what belongs to
+    [k*sub, (k+1)*sub).  -> [(s, e, keep_s, keep_e)]"""
+    out = []
+    for f in range(0, length, sub):
+        s, e = max(0, f - pad), min(length, f + sub + pad)
+        out.append((s, e, f - s, (e - s) - (e - min(length, f + sub))))
+    return out
+
+
 def window_schedule(video_length: int, sub_video_length: int = 80) -> List[Tuple[List[int], List[int]]]:
     """P7 — the window loop (:318-333): (neighbor_ids, ref_ids) per window, a window every NEIGHBOR_LENGTH // 2 frames."""
     stride = NEIGHBOR_LENGTH // 2
