@@ -19,7 +19,7 @@ from .sttn_auto_inpaint import STTNAutoInpaint, STTNInpaint  # noqa: F401
 from .sttn_det_inpaint import STTNDetInpaint  # noqa: F401
 from .subtitle_detect import SubtitleDetect  # noqa: F401
 from .lama_inpaint import LamaInpaint  # noqa: F401
-from .pipeline import video_inpaint_frames  # noqa: F401
+from .pipeline import propainter_mode_frames, video_inpaint_frames  # noqa: F401
 
-__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "LamaInpaint", "SubtitleDetect", "video_inpaint_frames", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
+__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "LamaInpaint", "SubtitleDetect", "video_inpaint_frames", "propainter_mode_frames", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
            "batch_generator"]

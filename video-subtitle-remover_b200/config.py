@@ -24,6 +24,7 @@ class _Config:
         self.subtitleTimelineBackwardFrameCount = _v(3)  # :67
         self.subtitleTimelineForwardFrameCount = _v(3)   # :68
         self.subtitleYXAxisDifferencePixel = _v(10)      # :59
+        self.propainterMaxLoadNum = _v(70)               # :100
 
     def getSttnMaxLoadNum(self):                 # :94
         return max(self.sttnMaxLoadNum.value, self.sttnNeighborStride.value * self.sttnReferenceLength.value)
@@ -31,7 +32,7 @@ class _Config:
     def adopt(self, other):
         for k in ("sttnNeighborStride", "sttnReferenceLength", "sttnMaxLoadNum", "subtitleAreaDeviationPixel",
                   "subtitleAreaPixelToleranceYPixel", "subtitleAreaPixelToleranceXPixel", "subtitleTimelineBackwardFrameCount",
-                  "subtitleTimelineForwardFrameCount", "subtitleYXAxisDifferencePixel"):
+                  "subtitleTimelineForwardFrameCount", "subtitleYXAxisDifferencePixel", "propainterMaxLoadNum"):
             if hasattr(other, k):
                 getattr(self, k).value = getattr(other, k).value
 

@@ -60,3 +60,45 @@ def video_inpaint_frames(frames: Sequence[np.ndarray], detector, model: Callable
                 out.extend(model(batch, mask))
         i = e + 1
     return out, sub_list, start_end
+
+
+def propainter_mode_frames(frames: Sequence[np.ndarray], sub_list: Dict[int, List[P.Box]], propainter: Callable, lama, scene_points: Sequence[int] = ()) -> List[np.ndarray]:
+    """In-memory mirror of `SubtitleRemover.propainter_mode` (backend/main.py:150-246), the loop of BASELINE configs 3 and 5, from the detected
+    frame dictionary on: frames without a detection pass through; an interval of frames with the same mask (`find_continuous_ranges_with_same_mask`,
+    split at `scene_points`; the reference finds those with the third-party scenedetect, main.py:165) is cut into `batch_generator` batches of
+    at most `propainterMaxLoadNum` frames that go through `propainter(batch, mask)` with the mask of the interval's FIRST frame; a single
+    frame — an interval or a batch of one — goes to `lama.inpaint(frame, mask)` instead.  Kept from the reference: in the batch-of-one
+    branch it is the LAST frame read of the interval that is inpainted (`frame`, :229-231; batches of one are last batches, so this is
+    the frame of the batch), and a detected frame that starts no interval is neither processed nor written (:190 has no else).
+    Returns the frames in the order the reference writes them."""
+    size = frames[0].shape[:2]
+    ranges = P.split_range_by_scene(P.find_continuous_ranges_with_same_mask(sub_list), list(scene_points))
+    out: List[np.ndarray] = []
+    index, n = 0, len(frames)
+    while index < n:
+        index += 1
+        frame = frames[index - 1]
+        if index not in sub_list:
+            out.append(frame)
+            continue
+        if not any(s == index for s, _ in ranges):
+            continue
+        start = index
+        end = next((e for s, e in ranges if s <= index <= e), -1)
+        if end == -1:
+            continue
+        temp = [frame]
+        while index < end and index < n:
+            index += 1
+            frame = frames[index - 1]
+            temp.append(frame)
+        if len(temp) == 1:
+            out.append(lama.inpaint(frame, create_mask(size, sub_list[index])))
+            continue
+        mask = create_mask(size, sub_list[start])
+        for batch in batch_generator(temp, config.propainterMaxLoadNum.value):
+            if len(batch) == 1:
+                out.append(lama.inpaint(frame, mask))
+            elif len(batch) > 1:
+                out.extend(propainter(batch, mask))
+    return out
