@@ -671,10 +671,10 @@ def main():
     ms = eng.time_conv(Tw, 20)
     conv_ms = float(np.median(ms))
     conv_flop = 2.0 * Tw * 30 * 160 * 2304 * 256
-    burst, sustained, hbm, src = peaks()
+    burst, sustained, hbm, peak_src = peaks()
     roof = {"bound": "tensor", "kernel": f"tcgen05 implicit-GEMM 3x3 conv 256->256, {Tw}x30x160 px ({'CTA-pair 256x256' if os.environ.get('VSR_CONV_2CTA', '1') != '0' else '128x256'} tiles)",
             "achieved": conv_flop / (conv_ms * 1e-3) / 1e12, "peak": burst, "unit": "TFLOP/s",
-            "frac": conv_flop / (conv_ms * 1e-3) / 1e12 / burst, "traffic": None, "peak_source": f"{src} (burst bf16)",
+            "frac": conv_flop / (conv_ms * 1e-3) / 1e12 / burst, "traffic": None, "peak_source": f"{peak_src} (burst bf16)",
             "ms_per_launch": conv_ms, "flop_per_launch": conv_flop,
             "whole_step_frac_of_sustained": (FLOP_PER_FRAME * CHUNK * args.steps / (dev_ms * 1e-3)) / 1e12 / sustained}
 

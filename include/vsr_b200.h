@@ -125,7 +125,8 @@ int vsr_window_schedule(int T, int stride, int ref_length, int32_t* ids, int32_t
 typedef struct vsr_rt vsr_rt_t;
 int vsr_rt_create(vsr_rt_t** out, int device);
 void vsr_rt_destroy(vsr_rt_t* h);
-int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr);             /* zero-initialised, freed with the runtime */
+int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr);             /* zero-initialised, freed with the runtime or by vsr_rt_free */
+int vsr_rt_free(vsr_rt_t* h, uint64_t dev_ptr);                                /* waits for the runtime's stream, then releases one vsr_rt_alloc buffer (ProPainter: work buffers of a batch length that propainter_mode, main.py:229-241, no longer feeds) */
 int vsr_rt_upload(vsr_rt_t* h, uint64_t dev_ptr, const void* host, int64_t bytes);
 int vsr_rt_download(vsr_rt_t* h, uint64_t dev_ptr, void* host, int64_t bytes);
 int vsr_rt_copy(vsr_rt_t* h, uint64_t dst, uint64_t src, int64_t bytes);         /* device -> device on the runtime's stream (ProPainter: chunk results of propainter_inpaint.py:254-304 into the whole-sequence buffers) */

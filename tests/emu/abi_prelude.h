@@ -76,6 +76,13 @@ int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr) {
     *dev_ptr = (uint64_t)(uintptr_t)h->bufs.back()->p;
   });
 }
+int vsr_rt_free(vsr_rt_t* h, uint64_t dev_ptr) {
+  return guarded([&] {
+    for (size_t i = 0; i < h->bufs.size(); ++i)
+      if ((uint64_t)(uintptr_t)h->bufs[i]->p == dev_ptr) { h->bufs.erase(h->bufs.begin() + (long)i); return; }
+    throw Error(VSR_ERR_ARG, "vsr_rt_free: not a pointer returned by vsr_rt_alloc");
+  });
+}
 int vsr_rt_upload(vsr_rt_t*, uint64_t dev_ptr, const void* host, int64_t bytes) { std::memcpy((void*)(uintptr_t)dev_ptr, host, (size_t)bytes); return VSR_OK; }
 int vsr_rt_download(vsr_rt_t*, uint64_t dev_ptr, void* host, int64_t bytes) { std::memcpy(host, (const void*)(uintptr_t)dev_ptr, (size_t)bytes); return VSR_OK; }
 int vsr_rt_copy(vsr_rt_t*, uint64_t dst, uint64_t src, int64_t bytes) { std::memmove((void*)(uintptr_t)dst, (const void*)(uintptr_t)src, (size_t)bytes); return VSR_OK; }

@@ -112,6 +112,11 @@ class FakeRuntime:
         self.bufs[h] = np.zeros(int(nbytes) // 2, np.float32)   # one fp32 per fp16 element of the real buffer
         return h
 
+    def free(self, ptr):
+        assert self._rec is None, "free during graph capture"
+        del self.bufs[ptr]
+        self._bases.remove(ptr)
+
     def upload_f32(self, arr):
         assert self._rec is None, "upload during graph capture"
         arr = np.array(arr, np.float32)

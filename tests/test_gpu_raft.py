@@ -1,5 +1,4 @@
-"""GPU: RAFT on the device runtime against the oracle.  GATED: the device path was written after round 1's
-GPU budget was spent and has not run on a B200 yet; set VSR_RUN_UNVALIDATED=1 to run it (the first thing to do next round).
+"""GPU: the ProPainter stages on the device runtime against the oracle and the unmodified reference's frames.
 Tolerance (fp16 features, fp32 flow state; the fp16 simulation of the stand-in gives EPE mean 8e-4 / max 7e-3 px on this fixture,
 profiles/fp16_forecast_r1.md): mean end-point error <= 0.01 px, max <= 0.1 px."""
 import os
@@ -14,7 +13,6 @@ from oracle import sttn_oracle as O
 
 PATH = os.path.join(ROOT, "weights", "propainter", "raft-things.pth")
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VSR_RUN_UNVALIDATED") != "1", reason="RAFT device path not yet validated on a B200 (DESIGN.md §7)"),
               pytest.mark.skipif(not os.path.exists(PATH), reason="raft-things.pth not staged under weights/propainter")]
 
 

@@ -121,6 +121,46 @@ def test_async_pipeline_equals_sync(rand_engine):
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
+def test_graph_replay_across_batch_lengths(capi, monkeypatch):
+    """Batches of different lengths and strip geometries interleaved (A,A,B,A,A,B,C,A: what batch_generator's ragged tail and the
+    A/B sections produce): every geometry keeps its own captured graph and its own window-schedule / resize-tap tables, so a
+    replayed graph must give the bytes of the eager path (VSR_NO_GRAPH=1)."""
+    from vsr_b200 import STTNInpaint
+
+    w = {k: v.numpy() for k, v in O.random_weights(0).items()}
+    H, W = 270, 480
+    mask_a = O.default_mask(H, W)
+    mask_c = O.create_mask((H, W), [(60, 400, 30, 60)])          # another strip position
+    jobs = [(7, mask_a, 1), (7, mask_a, 2), (5, mask_a, 3), (7, mask_a, 4), (7, mask_a, 5), (5, mask_a, 6), (7, mask_c, 7), (7, mask_a, 8),
+            (5, mask_a, 9), (7, mask_c, 10)]
+    clips = [O.synthetic_clip(T, H, W, seed=60 + sd) for T, _, sd in jobs]
+    monkeypatch.setenv("VSR_NO_GRAPH", "1")
+    eager = STTNInpaint("cuda:0", w)
+    want = [eager(c, m) for c, (_, m, _) in zip(clips, jobs)]
+    monkeypatch.delenv("VSR_NO_GRAPH")
+    eng = STTNInpaint("cuda:0", w)
+    for i, (c, (_, m, _)) in enumerate(zip(clips, jobs)):
+        got = eng(c, m)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want[i])), f"job {i} differs from the eager path"
+
+
+def test_overlapping_strips_inplace(rand_engine):
+    """Two subtitle bands closer than a strip height give overlapping strips; the reference crops every strip from the untouched
+    frames (sttn_auto_inpaint.py:66-73), also when the result is written into the input frames themselves."""
+    eng, w = rand_engine
+    H, W = 270, 480
+    frames = O.synthetic_clip(3, H, W, seed=8)
+    mask = O.create_mask((H, W), [(60, 400, 100, 120), (60, 400, 150, 175)])
+    areas = O.get_inpaint_area_by_mask(W, H, int(W * 3 / 16), (mask > 127).astype(np.uint8))
+    assert len(areas) == 2 and areas[0][1] > areas[1][0], areas
+    want = O.sttn_call(w, frames, mask)
+    out = eng(frames, mask)
+    work = [f.copy() for f in frames]
+    eng.inpaint_inplace(work, mask)
+    assert all(np.array_equal(a, b) for a, b in zip(out, work))
+    _check_images(out, want)
+
+
 def test_edge_cases(rand_engine):
     eng, w = rand_engine
     H, W = 270, 480

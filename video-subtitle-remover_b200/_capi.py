@@ -80,6 +80,7 @@ _PROTOS = {
     "vsr_rt_create": (C.c_int, [_pp, C.c_int]),
     "vsr_rt_destroy": (None, [C.c_void_p]),
     "vsr_rt_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
+    "vsr_rt_free": (C.c_int, [C.c_void_p, C.c_uint64]),
     "vsr_rt_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]),
     "vsr_rt_download": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]),
     "vsr_rt_copy": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64]),

@@ -3,6 +3,7 @@
 // sm_100a kernels, this file is the host runtime around them.
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -69,7 +70,10 @@ static std::string device_error_report() {
 }
 
 // ------------------------------------------------------------------------------------------------ device memory
-static uint64_t g_alloc_generation = 0;  // bumped on every (re)allocation: captured CUDA graphs bake pointers in
+// bumped on every (re)allocation: captured CUDA graphs bake pointers in.  Process-wide (any engine's reallocation makes every
+// engine re-capture, which is only conservative) and atomic, so engines on different threads do not race on it; one engine
+// itself is single-threaded (one Python thread per GPU).
+static std::atomic<uint64_t> g_alloc_generation{0};
 
 struct DevBuf {
   void* p = nullptr;
@@ -682,10 +686,29 @@ struct vsr_sttn {
   ConvLayer enc2, enc3, enc4, dec0, dec2, dec4, dec6;
   ConvLayer qkv[8], outl[8], ff0[8], ff1[8];
   // activations
-  DevBuf strips, rgb8, e1, e2s, e3, feats16, feats32, xw16, xw32, qkvb, att16, ffn16, up1, d1, d2, up2, d3, comps, visits_d,
-      sched_d, mask_d, msmall;  // msmall: sttn-det resized mask [model_h, model_w]
+  DevBuf strips, rgb8, e1, e2s, e3, feats16, feats32, xw16, xw32, qkvb, att16, ffn16, up1, d1, d2, up2, d3, comps,
+      mask_d, msmall;  // msmall: sttn-det resized mask [model_h, model_w]
   AttnWorkspace attn;
-  DevTaps pre_x, pre_y, post_x, post_y, mpre_x, mpre_y;
+  // Everything a captured chunk graph reads that depends on the job's geometry (T, strip width, strip rows) lives in a
+  // per-geometry record with its own device tables, so that a graph captured for one geometry never sees tables that a
+  // later job of another geometry rewrote in place (window schedule / first-visit tables, resize taps).
+  struct Geom {
+    std::vector<Window> sched;
+    std::vector<int> visits_h;
+    DevBuf sched_d, visits_d;
+    DevTaps pre_x, pre_y, post_x, post_y, mpre_x, mpre_y;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_gen = 0, warm_gen = 0;
+    bool warm = false;
+    int64_t graph_launches = 0;
+    uint64_t last_use = 0;
+    ~Geom() {
+      if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    }
+  };
+  std::map<std::array<int, 4>, std::unique_ptr<Geom>> geoms;
+  Geom* g = nullptr;  // geometry of the job being enqueued
+  uint64_t geom_clock = 0;
   // staged job
   int T = 0, H = 0, W = 0, split_h = 0;
   std::vector<std::array<int, 4>> areas;
@@ -693,9 +716,6 @@ struct vsr_sttn {
   std::vector<uint8_t> mask_h;  // last mask seen (host copy) — the whole-video driver passes the same mask per chunk
   int mask_H = 0;
   int staged_area = -1;
-  std::vector<int> visits_h;
-  int sched_T = -1;
-  std::vector<Window> sched;
   uint8_t* pinned = nullptr;
   size_t pinned_n = 0;
   // two-deep asynchronous pipeline (vsr_sttn_submit / vsr_sttn_collect): H2D of chunk i+1 and D2H of chunk i-1
@@ -715,12 +735,8 @@ struct vsr_sttn {
   // CUDA graph of one chunk's compute (launch-bound inner loop: ~630 kernels + ~200 D2D copies)
   bool use_graph = true;
   size_t window_group = 2;  // windows sharing each launch (VSR_WINDOW_GROUP, 1..2)
-  cudaGraphExec_t graph_exec = nullptr;
-  std::array<int, 4> graph_key{{-1, -1, -1, -1}}, warm_key{{-1, -1, -1, -1}};
-  uint64_t graph_gen = 0, warm_gen = 0;
-  int64_t graph_launches = 0;
   ~vsr_sttn() {
-    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    geoms.clear();
     for (auto& sl : slot) {
       if (sl.pin_in) cudaFreeHost(sl.pin_in);
       if (sl.pin_out) cudaFreeHost(sl.pin_out);
@@ -797,34 +813,35 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
   const int MW = h->cfg.model_w, MH = h->cfg.model_h, FH = h->FH, FW = h->FW, C = 256;
   cudaStream_t s = c.stream;
   REQUIRE(T >= 1, "need at least one frame");
-  if (h->sched_T != T) {
-    h->sched = host_window_schedule(T, h->cfg.neighbor_stride, h->cfg.ref_length);
+  REQUIRE(h->g, "run_network without a geometry record");
+  vsr_sttn::Geom& G = *h->g;
+  if (G.sched.empty()) {
+    G.sched = host_window_schedule(T, h->cfg.neighbor_stride, h->cfg.ref_length);
     // per window: frame_idx[32], first_visit[32]
-    std::vector<int> tab(h->sched.size() * 64, 0);
+    std::vector<int> tab(G.sched.size() * 64, 0);
     std::vector<int> visits(T, 0);
-    for (size_t wi = 0; wi < h->sched.size(); ++wi) {
-      REQUIRE(h->sched[wi].neighbors.size() <= 32, "neighbour window larger than 32 frames");
-      for (size_t i = 0; i < h->sched[wi].neighbors.size(); ++i) {
-        const int f = h->sched[wi].neighbors[i];
+    for (size_t wi = 0; wi < G.sched.size(); ++wi) {
+      REQUIRE(G.sched[wi].neighbors.size() <= 32, "neighbour window larger than 32 frames");
+      for (size_t i = 0; i < G.sched[wi].neighbors.size(); ++i) {
+        const int f = G.sched[wi].neighbors[i];
         tab[wi * 64 + i] = f;
         tab[wi * 64 + 32 + i] = visits[f] == 0;
         ++visits[f];
       }
     }
-    upload(h->sched_d, tab, s);
-    upload(h->visits_d, visits, s);
-    h->visits_h = visits;
-    h->sched_T = T;
+    upload(G.sched_d, tab, s);
+    upload(G.visits_d, visits, s);
+    G.visits_h = visits;
   }
   size_t maxw = 0;
-  for (size_t w0 = 0; w0 < h->sched.size(); w0 += h->window_group) {
+  for (size_t w0 = 0; w0 < G.sched.size(); w0 += h->window_group) {
     size_t sum = 0;
-    for (size_t wi = w0; wi < std::min(h->sched.size(), w0 + h->window_group); ++wi)
-      sum += h->sched[wi].neighbors.size() + h->sched[wi].refs.size();
+    for (size_t wi = w0; wi < std::min(G.sched.size(), w0 + h->window_group); ++wi)
+      sum += G.sched[wi].neighbors.size() + G.sched[wi].refs.size();
     maxw = std::max(maxw, sum);
   }
   size_t maxn = 0;
-  for (auto& w : h->sched) maxn = std::max(maxn, w.neighbors.size());
+  for (auto& w : G.sched) maxn = std::max(maxn, w.neighbors.size());
   const size_t fpix = (size_t)FH * FW;
   h->rgb8.ensure((size_t)T * MH * MW * 4);
   h->e1.ensure((size_t)T * (MH / 2) * (MW / 2) * 64 * 2);
@@ -846,21 +863,21 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
   if (h->cfg.mode == 1) h->msmall.ensure((size_t)MH * MW);
 
   // A3/A4 pre-processing
-  h->pre_x.build(sw, MW, false, s);
-  h->pre_y.build(sh, MH, true, s);
+  G.pre_x.build(sw, MW, false, s);
+  G.pre_y.build(sh, MH, true, s);
   strip_downscale_kernel<<<dim3((MW + 255) / 256, MH, T), 256, 0, s>>>(h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh,
-                                                                        h->rgb8.as<uint8_t>(), MW, MH, T, h->pre_x.view(),
-                                                                        h->pre_y.view());
+                                                                        h->rgb8.as<uint8_t>(), MW, MH, T, G.pre_x.view(),
+                                                                        G.pre_y.view());
   CK(cudaGetLastError());
   ++c.launches;
   const bool det = h->cfg.mode == 1;
   if (det) {
     h->msmall.ensure((size_t)MH * MW);
     if (mask_strip) {  // D1: the mask strip goes through the same cv2.resize as the frames (sttn_det_inpaint.py:73)
-      h->mpre_x.build(sw, MW, false, s);
-      h->mpre_y.build(sh, MH, true, s);
+      G.mpre_x.build(sw, MW, false, s);
+      G.mpre_y.build(sh, MH, true, s);
       mask_downscale_kernel<<<dim3((MW + 255) / 256, MH), 256, 0, s>>>(mask_strip, sw, sh, h->msmall.as<uint8_t>(), MW, MH,
-                                                                       h->mpre_x.view(), h->mpre_y.view());
+                                                                       G.mpre_x.view(), G.mpre_y.view());
       CK(cudaGetLastError());
       ++c.launches;
     }
@@ -890,12 +907,12 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
   // into comps is ordered), so `group` consecutive windows share every conv / attention launch: at T=15 a
   // single window is 4.05 waves of 128x256 tiles (81 % wave efficiency), two windows are 7.8 (98 %).
   const size_t f16b = fpix * C * 2, f32b = fpix * C * 4;
-  for (size_t w0 = 0; w0 < h->sched.size(); w0 += h->window_group) {
-    const size_t w1 = std::min(h->sched.size(), w0 + h->window_group);
+  for (size_t w0 = 0; w0 < G.sched.size(); w0 += h->window_group) {
+    const size_t w1 = std::min(G.sched.size(), w0 + h->window_group);
     std::vector<AttnSegment> segs;
     int Tg = 0;
     for (size_t wi = w0; wi < w1; ++wi) {
-      const Window& w = h->sched[wi];
+      const Window& w = G.sched[wi];
       const int nn = (int)w.neighbors.size();
       // gather feats[neighbor_ids + ref_ids] (sttn_auto_inpaint.py:148)
       CK(cudaMemcpyAsync(h->xw16.as<uint8_t>() + (size_t)Tg * f16b, h->feats16.as<uint8_t>() + (size_t)w.neighbors[0] * f16b,
@@ -936,7 +953,7 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
     // A10 decoder on the neighbour frames only (sttn_auto_inpaint.py:150), window by window in schedule
     // order (the 0.5/0.5 blend of :159-162 is order dependent)
     for (size_t wi = w0; wi < w1; ++wi) {
-      const int nn = (int)h->sched[wi].neighbors.size();
+      const int nn = (int)G.sched[wi].neighbors.size();
       const __half* xin = h->xw16.as<__half>() + (size_t)segs[wi - w0].first * fpix * C;
       size_t total = (size_t)nn * (2 * FH) * (2 * FW) * (C / 8);
       upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(xin, nn, FH, FW, C, h->up1.as<__half>());
@@ -959,8 +976,8 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
       ConvIO e;
       e.in = h->d3.as<__half>(); e.T = nn; e.H = MH; e.W = MW; e.flags = CONV_FINAL;
       e.comps = h->comps.as<float>();
-      e.frame_idx = h->sched_d.as<int>() + wi * 64;
-      e.first_visit = h->sched_d.as<int>() + wi * 64 + 32;
+      e.frame_idx = G.sched_d.as<int>() + wi * 64;
+      e.first_visit = G.sched_d.as<int>() + wi * 64 + 32;
       e.det_mask = det_mask;
       e.det_rgb = h->rgb8.as<uchar4>();
       run_conv(c, h->dec6, e);
@@ -1009,15 +1026,38 @@ static void sync_stream(vsr_sttn* h) {
 }
 
 // upload strip k of the staged frames, run, composite, leave strips on device
-static void stage_area(vsr_sttn* h, int k) {
+// `snapshot` (optional): the strip rows of every frame, [T][sh*sw*3], saved before an earlier strip was written back
+// into frames that alias the inputs (the reference crops every strip from the untouched frames, sttn_auto_inpaint.py:66-73).
+static void stage_area(vsr_sttn* h, int k, const uint8_t* snapshot = nullptr) {
   const int y0 = h->areas[k][0], y1 = h->areas[k][1];
   const int sh = y1 - y0, sw = h->W;
   const size_t sb = (size_t)sh * sw * 3;
   h->strips.ensure(sb * h->T);
   ensure_pinned(h, sb * h->T);
-  parallel_for(h->T, [&](int t) { memcpy(h->pinned + t * sb, h->in_ptrs[t] + (size_t)y0 * sw * 3, sb); });
+  parallel_for(h->T, [&](int t) {
+    memcpy(h->pinned + t * sb, snapshot ? snapshot + t * sb : h->in_ptrs[t] + (size_t)y0 * sw * 3, sb);
+  });
   CK(cudaMemcpyAsync(h->strips.p, h->pinned, sb * h->T, cudaMemcpyHostToDevice, h->ctx.stream));
   h->staged_area = k;
+}
+
+// The geometry record of a job: created on first use, at most 16 kept (least recently used evicted together with its graph).
+static vsr_sttn::Geom& select_geom(vsr_sttn* h, int T, int sw, int y0, int y1) {
+  const std::array<int, 4> key{{T, sw, y0, y1}};
+  auto it = h->geoms.find(key);
+  if (it == h->geoms.end()) {
+    if (h->geoms.size() >= 16) {
+      auto victim = h->geoms.begin();
+      for (auto j = h->geoms.begin(); j != h->geoms.end(); ++j)
+        if (j->second->last_use < victim->second->last_use) victim = j;
+      CK(cudaStreamSynchronize(h->ctx.stream));  // its tables may still be read by enqueued work
+      h->geoms.erase(victim);
+    }
+    it = h->geoms.emplace(key, std::make_unique<vsr_sttn::Geom>()).first;
+  }
+  it->second->last_use = ++h->geom_clock;
+  h->g = it->second.get();
+  return *h->g;
 }
 
 static void enqueue_area(vsr_sttn* h, int k) {
@@ -1026,35 +1066,38 @@ static void enqueue_area(vsr_sttn* h, int k) {
   cudaStream_t s = h->ctx.stream;
   const bool det = h->cfg.mode == 1;
   const uint8_t* mask_strip = h->mask_d.as<uint8_t>() + (size_t)y0 * sw;
+  vsr_sttn::Geom& G = *h->g;
   run_network(h, h->T, sw, sh, det ? mask_strip : nullptr);
-  h->post_x.build(h->cfg.model_w, sw, false, s);
-  h->post_y.build(h->cfg.model_h, sh, true, s);
+  G.post_x.build(h->cfg.model_w, sw, false, s);
+  G.post_y.build(h->cfg.model_h, sh, true, s);
   // sttn-auto: mask ? comp : frame (sttn_auto_inpaint.py:91);  sttn-det: the whole strip is replaced (sttn_det_inpaint.py:93)
   strip_composite_kernel<<<dim3((sw + 255) / 256, sh, h->T), 256, 0, s>>>(
-      h->comps.as<float>(), h->cfg.model_w, h->cfg.model_h, h->visits_d.as<int>(), det ? nullptr : mask_strip, sw,
-      h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh, h->T, h->post_x.view(), h->post_y.view());
+      h->comps.as<float>(), h->cfg.model_w, h->cfg.model_h, G.visits_d.as<int>(), det ? nullptr : mask_strip, sw,
+      h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh, h->T, G.post_x.view(), G.post_y.view());
   CK(cudaGetLastError());
   ++h->ctx.launches;
 }
 
 // First call with a given (T, strip geometry): eager (sizes the workspace, uploads tables).  Second call:
-// captured into a CUDA graph.  Later calls: one cudaGraphLaunch.  Any reallocation invalidates the graph.
+// captured into a CUDA graph.  Later calls: one cudaGraphLaunch.  Any reallocation invalidates the graph; the
+// geometry-dependent tables are per record, so graphs of different geometries (A/B sections, ragged batches of
+// batch_generator) coexist and stay valid across each other's runs.
 static void compute_area(vsr_sttn* h, int k) {
-  const std::array<int, 4> key{{h->T, h->W, h->areas[k][0], h->areas[k][1]}};
+  vsr_sttn::Geom& G = select_geom(h, h->T, h->W, h->areas[k][0], h->areas[k][1]);
   cudaStream_t s = h->ctx.stream;
   if (!h->use_graph) {
     enqueue_area(h, k);
     return;
   }
-  if (h->graph_exec && h->graph_key == key && h->graph_gen == g_alloc_generation) {
-    CK(cudaGraphLaunch(h->graph_exec, s));
-    h->ctx.launches += h->graph_launches;
+  if (G.graph_exec && G.graph_gen == g_alloc_generation) {
+    CK(cudaGraphLaunch(G.graph_exec, s));
+    h->ctx.launches += G.graph_launches;
     return;
   }
-  if (h->warm_key == key && h->warm_gen == g_alloc_generation) {
-    if (h->graph_exec) {
-      cudaGraphExecDestroy(h->graph_exec);
-      h->graph_exec = nullptr;
+  if (G.warm && G.warm_gen == g_alloc_generation) {
+    if (G.graph_exec) {
+      cudaGraphExecDestroy(G.graph_exec);
+      G.graph_exec = nullptr;
     }
     const int64_t l0 = h->ctx.launches;
     cudaGraph_t g = nullptr;
@@ -1067,21 +1110,20 @@ static void compute_area(vsr_sttn* h, int k) {
       throw;
     }
     CK(cudaStreamEndCapture(s, &g));
-    h->graph_launches = h->ctx.launches - l0;
-    cudaError_t e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    G.graph_launches = h->ctx.launches - l0;
+    cudaError_t e = cudaGraphInstantiate(&G.graph_exec, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) {
-      h->graph_exec = nullptr;
+      G.graph_exec = nullptr;
       throw Error(VSR_ERR_CUDA, std::string("cudaGraphInstantiate -> ") + cudaGetErrorString(e));
     }
-    h->graph_key = key;
-    h->graph_gen = g_alloc_generation;
-    CK(cudaGraphLaunch(h->graph_exec, s));
+    G.graph_gen = g_alloc_generation;
+    CK(cudaGraphLaunch(G.graph_exec, s));
     return;
   }
   enqueue_area(h, k);
-  h->warm_key = key;
-  h->warm_gen = g_alloc_generation;
+  G.warm = true;
+  G.warm_gen = g_alloc_generation;
 }
 
 static void fetch_area(vsr_sttn* h, int k, uint8_t* const* out) {
@@ -1389,11 +1431,12 @@ int vsr_sttn_inpaint_strip(vsr_sttn_t* h, const uint8_t* frames_bgr, int T, floa
     const size_t sb = (size_t)MH * MW * 3;
     h->strips.ensure(sb * T);
     CK(cudaMemcpyAsync(h->strips.p, frames_bgr, sb * T, cudaMemcpyHostToDevice, h->ctx.stream));
+    select_geom(h, T, MW, 0, MH);
     run_network(h, T, MW, MH);
     CK(cudaMemcpyAsync(comps_out, h->comps.p, sb * T * sizeof(float), cudaMemcpyDeviceToHost, h->ctx.stream));
     sync_stream(h);
     if (visits_out)
-      for (int t = 0; t < T; ++t) visits_out[t] = h->visits_h[t];
+      for (int t = 0; t < T; ++t) visits_out[t] = h->g->visits_h[t];
   });
 }
 
@@ -1409,11 +1452,12 @@ int vsr_sttn_inpaint_strip_masked(vsr_sttn_t* h, const uint8_t* frames_bgr, cons
     h->msmall.ensure((size_t)MH * MW);
     CK(cudaMemcpyAsync(h->strips.p, frames_bgr, sb * T, cudaMemcpyHostToDevice, h->ctx.stream));
     CK(cudaMemcpyAsync(h->msmall.p, mask_small, (size_t)MH * MW, cudaMemcpyHostToDevice, h->ctx.stream));
+    select_geom(h, T, MW, 0, MH);
     run_network(h, T, MW, MH, nullptr);
     CK(cudaMemcpyAsync(comps_out, h->comps.p, sb * T * sizeof(float), cudaMemcpyDeviceToHost, h->ctx.stream));
     sync_stream(h);
     if (visits_out)
-      for (int t = 0; t < T; ++t) visits_out[t] = h->visits_h[t];
+      for (int t = 0; t < T; ++t) visits_out[t] = h->g->visits_h[t];
   });
 }
 
@@ -1440,10 +1484,18 @@ int vsr_sttn_fetch(vsr_sttn_t* h, uint8_t* const* frames_out) {
       if (frames_out[t] != h->in_ptrs[t]) memcpy(frames_out[t], h->in_ptrs[t], fb);  // the copy at sttn_auto_inpaint.py:58
     });
     if (h->areas.empty()) return;
-    fetch_area(h, 0, frames_out);
-    // further strips (rare: several disjoint subtitle bands) run back to back
+    // further strips (rare: several subtitle bands) run back to back.  Strips may overlap, and frames_out may be the input
+    // frames themselves: save the input rows of the later strips before the first strip is written back.
+    std::vector<std::vector<uint8_t>> snap(h->areas.size());
     for (size_t k = 1; k < h->areas.size(); ++k) {
-      stage_area(h, (int)k);
+      const int y0 = h->areas[k][0];
+      const size_t sb = (size_t)(h->areas[k][1] - y0) * h->W * 3;
+      snap[k].resize(sb * h->T);
+      parallel_for(h->T, [&](int t) { memcpy(snap[k].data() + t * sb, h->in_ptrs[t] + (size_t)y0 * h->W * 3, sb); });
+    }
+    fetch_area(h, 0, frames_out);
+    for (size_t k = 1; k < h->areas.size(); ++k) {
+      stage_area(h, (int)k, snap[k].data());
       compute_area(h, (int)k);
       fetch_area(h, (int)k, frames_out);
     }
@@ -1633,6 +1685,20 @@ int vsr_rt_alloc(vsr_rt_t* h, int64_t bytes, uint64_t* dev_ptr) {
     b->ensure((size_t)bytes);
     *dev_ptr = (uint64_t)(uintptr_t)b->p;
     h->bufs.push_back(std::move(b));
+  });
+}
+int vsr_rt_free(vsr_rt_t* h, uint64_t dev_ptr) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(!h->capturing, "vsr_rt_free during graph capture");
+    for (size_t i = 0; i < h->bufs.size(); ++i)
+      if ((uint64_t)(uintptr_t)h->bufs[i]->p == dev_ptr) {
+        rt_sync(h);  // enqueued work may still use it
+        h->bufs.erase(h->bufs.begin() + (long)i);
+        ++g_alloc_generation;
+        return;
+      }
+    throw Error(VSR_ERR_ARG, "vsr_rt_free: not a pointer returned by vsr_rt_alloc");
   });
 }
 int vsr_rt_upload(vsr_rt_t* h, uint64_t dev_ptr, const void* host, int64_t bytes) {

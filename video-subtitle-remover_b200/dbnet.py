@@ -286,6 +286,9 @@ class _DeviceRuntime:
         _capi.check(self.L.vsr_rt_alloc(self.h, int(nbytes), C.byref(p)))
         return int(p.value)
 
+    def free(self, ptr: int) -> None:
+        _capi.check(self.L.vsr_rt_free(self.h, int(ptr)))
+
     def upload_f32(self, arr: np.ndarray) -> int:
         arr = np.ascontiguousarray(arr, np.float32)
         p = self.alloc(arr.nbytes)

@@ -46,11 +46,25 @@ class _Arena:
     same buffers back in the same order (the runtime frees nothing before it is destroyed, and zero-initialises only fresh buffers —
     every launch sequence here rewrites exactly the regions it wrote the first time)."""
 
+    KEEP = 1   # epochs a shape key survives without being used
+
     def __init__(self, rt):
         self.rt, self.seqs, self.cur, self.i = rt, {}, None, 0
+        self.epoch, self.used = 0, {}
+
+    def tick(self):
+        """A new top-level call (one batch of `propainter_mode`, main.py:229-241) starts.  Batch lengths differ per interval and every
+        length costs GBs of work buffers at a 1080p strip, while the runtime itself frees nothing before it is destroyed: release the
+        buffers of the shape keys that the last KEEP + 1 calls did not touch.  Nothing of an earlier call is live at this point."""
+        self.epoch += 1
+        for key in [k for k, e in self.used.items() if e < self.epoch - self.KEEP]:
+            for _, ptr in self.seqs.pop(key):
+                self.rt.free(ptr)
+            del self.used[key]
 
     def begin(self, key):
         self.cur, self.i = self.seqs.setdefault(key, []), 0
+        self.used[key] = self.epoch
 
     def alloc(self, nbytes: int) -> int:
         if self.i < len(self.cur):

@@ -26,10 +26,18 @@ def get_inpaint_area_by_mask(W, H, h, mask, multiple=1):
     m = np.ascontiguousarray((m > 0).astype(np.uint8))
     if m.shape != (H, W):
         raise ValueError(f"mask shape {m.shape} != {(H, W)}")
-    out = np.zeros((max(16, H), 4), dtype=np.int32)
-    n = _capi.check(_capi.lib().vsr_inpaint_area_by_mask(int(W), int(H), int(h), _capi.ptr(m, C.c_uint8), int(multiple),
-                                                         _capi.ptr(out, C.c_int32), out.shape[0]))
-    return [tuple(int(v) for v in out[i]) for i in range(n)]
+    cap = max(16, H)
+    while True:     # the reference returns however many areas the mask produces: grow the buffer until they fit
+        out = np.zeros((cap, 4), dtype=np.int32)
+        try:
+            n = _capi.check(_capi.lib().vsr_inpaint_area_by_mask(int(W), int(H), int(h), _capi.ptr(m, C.c_uint8), int(multiple),
+                                                                 _capi.ptr(out, C.c_int32), cap))
+        except _capi.VsrError as e:
+            if "areas buffer too small" not in str(e) or cap > 64 * max(16, H * W):
+                raise
+            cap *= 4
+            continue
+        return [tuple(int(v) for v in out[i]) for i in range(n)]
 
 
 def batch_generator(data, max_batch_size):

@@ -68,6 +68,8 @@ class PropainterInpaint:
         if T < 2:
             raise _capi.VsrError("ProPainter needs at least two frames (the reference routes single frames to LAMA, main.py:220)")
         rt = self._rt
+        for arena in (self._arena, self.fix_flow_complete._arena, self.model._arena):
+            arena.tick()
         flow_masks, masks_dilated = PT.read_mask(mask, T)
         gf, gb = self._flows(frames, shard)
         self._arena.begin(("inpaint", T, H, W))
