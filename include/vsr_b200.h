@@ -93,6 +93,22 @@ int vsr_sttn_collect(vsr_sttn_t* h, int64_t ticket, uint8_t* const* frames_out);
 void* vsr_sttn_stream(vsr_sttn_t* h);
 /* kernels launched by this engine since creation (bench.py `gpu_launches`) */
 int64_t vsr_sttn_launch_count(vsr_sttn_t* h);
+/* In-situ profile of one chunk (bench.py `roofline`): runs the staged job once eagerly (no CUDA graph) with a pair of CUDA events
+ * around every launch group, and returns per class the summed device time (ms) and the number of groups.  Classes: */
+enum {
+  VSR_PROF_CONV3 = 0,      /* transformer-block 3x3 conv 256->256, fp16 out (feed_forward.conv.0, auto_sttn.py:215) */
+  VSR_PROF_CONV3_RES = 1,  /* ... with the fp32 residual stream in the epilogue (output_linear :163, feed_forward.conv.2 :217) */
+  VSR_PROF_QKV = 2,        /* fused Q,K,V 1x1 projections (:172-174) */
+  VSR_PROF_SCORE = 3,      /* Q.K^T (:143) */
+  VSR_PROF_SOFTMAX = 4,    /* softmax rows (:144) */
+  VSR_PROF_PV = 5,         /* P.V + un-patch (:145, :201-202) */
+  VSR_PROF_ENCODER = 6,    /* :75-84 */
+  VSR_PROF_DECODER = 7,    /* :87-95 + tanh / quantise / blend (sttn_auto_inpaint.py:150-162) */
+  VSR_PROF_GATHER = 8,     /* feats[neighbor_ids + ref_ids] (sttn_auto_inpaint.py:148) */
+  VSR_PROF_PREPOST = 9,    /* crop / resize in, resize back / composite (sttn_auto_inpaint.py:269-271, 312-315) */
+  VSR_PROF_CLASSES = 10
+};
+int vsr_sttn_profile(vsr_sttn_t* h, float* ms_by_class, int64_t* scopes_by_class, int n_classes);
 /* Time the dominant kernel family of the last compute: fills ms_out[0..n) with CUDA-event durations
  * of n back-to-back launches of the transformer-block 3x3 conv (tcgen05 implicit GEMM) on T frames. */
 int vsr_sttn_time_conv(vsr_sttn_t* h, int T, int n, float* ms_out);

@@ -27,6 +27,11 @@ WINDOW, HEADS, POOL, DEPTH, T2T = (5, 9), 4, (4, 4), 8, dict(kernel_size=(7, 7),
 
 
 def load_weights(path: str) -> Dict[str, torch.Tensor]:
+    import os
+
+    alt = path[:-4] + ".f16.pth"     # tools/stage_weights.py: the compact copy that travels to the GPU box (matrices stored fp16)
+    if not os.path.exists(path) and os.path.exists(alt):
+        path = alt
     return {k: (v.float() if v.is_floating_point() else v) for k, v in torch.load(path, map_location="cpu").items()}
 
 

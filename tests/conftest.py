@@ -29,3 +29,11 @@ def real_weights_path():
 
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# The GPU box receives the compact ProPainter checkpoint only (tools/stage_weights.py, snapshot cap): give it the name the tests look for.
+_pp = os.path.join(ROOT, "weights", "propainter", "ProPainter.pth")
+if not os.path.exists(_pp) and os.path.exists(_pp[:-4] + ".f16.pth"):
+    try:
+        os.symlink("ProPainter.f16.pth", _pp)
+    except OSError:
+        pass

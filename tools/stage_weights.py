@@ -51,9 +51,26 @@ def stage_lama(quiet=False):
             print(f"staged {npz}")
 
 
+def stage_propainter_compact(quiet=False):
+    """ProPainter.pth (158 MB fp32) -> ProPainter.f16.pth (79 MB): the same state dict with every tensor of two or more dimensions stored
+    in fp16 (the device path rounds them to fp16 for the tensor cores anyway), vectors fp32.  The fp32 file is listed in .gpurunignore
+    (snapshot cap 512 MiB); loaders fall back to the compact file when the fp32 one is absent."""
+    d = os.path.join(ROOT, "weights", "propainter")
+    src, dst = os.path.join(d, "ProPainter.pth"), os.path.join(d, "ProPainter.f16.pth")
+    if not os.path.exists(src) or (os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src)):
+        return
+    import torch
+
+    sd = torch.load(src, map_location="cpu")
+    torch.save({k: (v.half() if v.is_floating_point() and v.dim() >= 2 else v) for k, v in sd.items()}, dst)
+    if not quiet:
+        print(f"staged {dst}")
+
+
 def main(quiet=False):
     if "--lama" in sys.argv:
         stage_lama(quiet)
+    stage_propainter_compact(quiet)
     for dst, src in FILES.items():
         s = os.path.join(REF, src)
         d = os.path.join(ROOT, "weights", dst)

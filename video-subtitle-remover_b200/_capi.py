@@ -72,6 +72,7 @@ _PROTOS = {
     "vsr_sttn_launch_count": (C.c_int64, [C.c_void_p]),
     "vsr_debug_tc_profile": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "vsr_sttn_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, _f32p, C.c_int64]),
+    "vsr_sttn_profile": (C.c_int, [C.c_void_p, _f32p, _i64p, C.c_int]),
     "vsr_sttn_time_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p]),
     "vsr_create_mask": (C.c_int, [_u8p, C.c_int, C.c_int, _i32p, C.c_int, C.c_int]),
     "vsr_inpaint_area_by_mask": (C.c_int, [C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _i32p, C.c_int]),

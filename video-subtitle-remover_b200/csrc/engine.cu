@@ -157,6 +157,28 @@ struct Ctx {
   bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
   bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
+  // In-situ profile (vsr_sttn_profile): with `prof` set, every ProfScope brackets its launches with a pair of events on the
+  // stream; classes are the VSR_PROF_* ids of include/vsr_b200.h.
+  bool prof = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+};
+
+struct ProfScope {
+  Ctx& c;
+  Ctx::ProfRec r{0, nullptr, nullptr};
+  ProfScope(Ctx& ctx, int cls) : c(ctx) {
+    if (!c.prof) return;
+    r.cls = cls;
+    CK(cudaEventCreate(&r.a));
+    CK(cudaEventCreate(&r.b));
+    CK(cudaEventRecord(r.a, c.stream));
+  }
+  ~ProfScope() {
+    if (!r.a) return;
+    cudaEventRecord(r.b, c.stream);
+    c.prof_recs.push_back(r);
+  }
 };
 
 static bool env_flag(const char* name, bool dflt) {
@@ -625,9 +647,13 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   sp.totalB = workB;
   sp.totalB2 = workB2;
   sp.pass = 0;  // pass A: per-tile row maxima (fused problems) / fp32 S slabs (split-K problems)
-  if (c.attn_2cta) launch_tc2<Score2Policy>(c, sp, score_work2);
-  else launch_tc<ScorePolicy>(c, sp, score_work);
+  {
+    ProfScope ps_(c, VSR_PROF_SCORE);
+    if (c.attn_2cta) launch_tc2<Score2Policy>(c, sp, score_work2);
+    else launch_tc<ScorePolicy>(c, sp, score_work);
+  }
   if (any_unfused) {
+    ProfScope ps_(c, VSR_PROF_SOFTMAX);
     int max_cols = 0, rows_total = 0;
     for (int s2 = 0; s2 < nent; ++s2) {
       sp.softmax_row_begin[s2] = rows_total;
@@ -648,10 +674,12 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     ++c.launches;
   }
   if (workB > 0) {
+    ProfScope ps_(c, VSR_PROF_SCORE);
     sp.pass = 1;  // pass B: recompute the scores, write P and partial row sums
     if (c.attn_2cta) launch_tc2<Score2Policy>(c, sp, workB2);
     else launch_tc<ScorePolicy>(c, sp, workB);
   }
+  ProfScope ps_(c, VSR_PROF_PV);
   if (c.attn_2cta) launch_tc2<PV2Policy>(c, pp, pv_work2);
   else launch_tc<PVPolicy>(c, pp, pv_work);
 }
@@ -863,6 +891,7 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
   if (h->cfg.mode == 1) h->msmall.ensure((size_t)MH * MW);
 
   // A3/A4 pre-processing
+  std::unique_ptr<ProfScope> region = std::make_unique<ProfScope>(c, VSR_PROF_PREPOST);
   G.pre_x.build(sw, MW, false, s);
   G.pre_y.build(sh, MH, true, s);
   strip_downscale_kernel<<<dim3((MW + 255) / 256, MH, T), 256, 0, s>>>(h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh,
@@ -884,7 +913,9 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
   }
   const uint8_t* det_mask = det ? h->msmall.as<uint8_t>() : nullptr;
   // A5 encoder
+  region.reset();
   {
+    ProfScope ps_(c, VSR_PROF_ENCODER);
     const int total = T * (MH / 2) * (MW / 2);
     stem_conv_kernel<<<(total + 63) / 64, 256, 0, s>>>(h->rgb8.as<uchar4>(), MH, MW, h->stem_w.as<float>(), h->stem_b.as<float>(),
                                                         h->e1.as<__half>(), total, det_mask);
@@ -911,6 +942,7 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
     const size_t w1 = std::min(G.sched.size(), w0 + h->window_group);
     std::vector<AttnSegment> segs;
     int Tg = 0;
+    region = std::make_unique<ProfScope>(c, VSR_PROF_GATHER);
     for (size_t wi = w0; wi < w1; ++wi) {
       const Window& w = G.sched[wi];
       const int nn = (int)w.neighbors.size();
@@ -928,11 +960,15 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
       segs.push_back({Tg, nn + (int)w.refs.size()});
       Tg += nn + (int)w.refs.size();
     }
+    region.reset();
     for (int b = 0; b < 8; ++b) {
       // A7: Q,K,V 1x1 projections in one GEMM (auto_sttn.py:172-174)
       ConvIO q;
       q.in = h->xw16.as<__half>(); q.T = Tg; q.H = FH; q.W = FW; q.out16 = h->qkvb.as<__half>(); q.out16_pitch = 3 * C;
-      run_conv(c, h->qkv[b], q);
+      {
+        ProfScope ps_(c, VSR_PROF_QKV);
+        run_conv(c, h->qkv[b], q);
+      }
       // A8: patch attention, one problem per (window, patch geometry)
       run_attention(c, h->attn, h->qkvb.as<__half>(), 3 * C, 0, C, 2 * C, segs, FH, FW, C, h->cfg.n_patch, h->cfg.patch_w,
                     h->cfg.patch_h, h->att16.as<__half>(), C);
@@ -940,18 +976,28 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
       ConvIO o;
       o.in = h->att16.as<__half>(); o.T = Tg; o.H = FH; o.W = FW; o.flags = CONV_LRELU | CONV_RESIDUAL;
       o.out16 = h->xw16.as<__half>(); o.out32 = h->xw32.as<float>(); o.res32 = h->xw32.as<float>();
-      run_conv(c, h->outl[b], o);
+      {
+        ProfScope ps_(c, VSR_PROF_CONV3_RES);
+        run_conv(c, h->outl[b], o);
+      }
       // A9: feed forward + residual (auto_sttn.py:215-218, 238)
       ConvIO f0;
       f0.in = h->xw16.as<__half>(); f0.T = Tg; f0.H = FH; f0.W = FW; f0.flags = CONV_LRELU; f0.out16 = h->ffn16.as<__half>();
-      run_conv(c, h->ff0[b], f0);
+      {
+        ProfScope ps_(c, VSR_PROF_CONV3);
+        run_conv(c, h->ff0[b], f0);
+      }
       ConvIO f1;
       f1.in = h->ffn16.as<__half>(); f1.T = Tg; f1.H = FH; f1.W = FW; f1.flags = CONV_LRELU | CONV_RESIDUAL;
       f1.out16 = h->xw16.as<__half>(); f1.out32 = h->xw32.as<float>(); f1.res32 = h->xw32.as<float>();
-      run_conv(c, h->ff1[b], f1);
+      {
+        ProfScope ps_(c, VSR_PROF_CONV3_RES);
+        run_conv(c, h->ff1[b], f1);
+      }
     }
     // A10 decoder on the neighbour frames only (sttn_auto_inpaint.py:150), window by window in schedule
     // order (the 0.5/0.5 blend of :159-162 is order dependent)
+    ProfScope ps_dec(c, VSR_PROF_DECODER);
     for (size_t wi = w0; wi < w1; ++wi) {
       const int nn = (int)G.sched[wi].neighbors.size();
       const __half* xin = h->xw16.as<__half>() + (size_t)segs[wi - w0].first * fpix * C;
@@ -1068,6 +1114,7 @@ static void enqueue_area(vsr_sttn* h, int k) {
   const uint8_t* mask_strip = h->mask_d.as<uint8_t>() + (size_t)y0 * sw;
   vsr_sttn::Geom& G = *h->g;
   run_network(h, h->T, sw, sh, det ? mask_strip : nullptr);
+  ProfScope ps_(h->ctx, VSR_PROF_PREPOST);
   G.post_x.build(h->cfg.model_w, sw, false, s);
   G.post_y.build(h->cfg.model_h, sh, true, s);
   // sttn-auto: mask ? comp : frame (sttn_auto_inpaint.py:91);  sttn-det: the whole strip is replaced (sttn_det_inpaint.py:93)
@@ -1571,6 +1618,39 @@ int vsr_sttn_debug_read(vsr_sttn_t* h, const char* name, float* out, int64_t n) 
     } else {
       CK(cudaMemcpy(out, b->p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     }
+  });
+}
+
+int vsr_sttn_profile(vsr_sttn_t* h, float* ms_by_class, int64_t* scopes_by_class, int n_classes) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(h->T > 0 && !h->areas.empty(), "nothing staged");
+    REQUIRE(ms_by_class && scopes_by_class && n_classes >= VSR_PROF_CLASSES, "need VSR_PROF_CLASSES output slots");
+    if (h->staged_area != 0) stage_area(h, 0);
+    const bool graph = h->use_graph;
+    h->use_graph = false;
+    h->ctx.prof = true;
+    h->ctx.prof_recs.clear();
+    try {
+      compute_area(h, 0);
+      sync_stream(h);
+    } catch (...) {
+      h->use_graph = graph;
+      h->ctx.prof = false;
+      throw;
+    }
+    h->use_graph = graph;
+    h->ctx.prof = false;
+    for (int i = 0; i < n_classes; ++i) { ms_by_class[i] = 0.f; scopes_by_class[i] = 0; }
+    for (auto& r : h->ctx.prof_recs) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, r.a, r.b));
+      ms_by_class[r.cls] += ms;
+      ++scopes_by_class[r.cls];
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    h->ctx.prof_recs.clear();
   });
 }
 

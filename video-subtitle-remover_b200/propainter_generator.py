@@ -30,7 +30,18 @@ def load_generator_weights(path_or_dict) -> Dict[str, np.ndarray]:
         return {k: np.asarray(v) for k, v in path_or_dict.items()}
     import torch
 
-    return {k: (v.float().numpy() if v.is_floating_point() else v.numpy()) for k, v in torch.load(str(path_or_dict), map_location="cpu").items()}
+    return {k: (v.float().numpy() if v.is_floating_point() else v.numpy()) for k, v in torch.load(compact_checkpoint(path_or_dict), map_location="cpu").items()}
+
+
+def compact_checkpoint(path) -> str:
+    """`ProPainter.pth`, or next to it `ProPainter.f16.pth` (tools/stage_weights.py: the same state dict with its matrices / conv kernels
+    stored in fp16 — what the tensor cores multiply with anyway; vectors stay fp32) when only that one was shipped (the gpurun snapshot is
+    capped at 512 MiB)."""
+    import os
+
+    path = str(path)
+    alt = path[:-4] + ".f16.pth" if path.endswith(".pth") else path
+    return path if os.path.exists(path) or not os.path.exists(alt) else alt
 
 
 class _GenRuntime(_RfcRuntime):

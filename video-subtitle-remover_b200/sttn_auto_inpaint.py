@@ -212,6 +212,15 @@ class STTNInpaint:
         _capi.check(_capi.lib().vsr_sttn_debug_read(self._h, name.encode(), _capi.ptr(out, C.c_float), out.size))
         return out
 
+    PROF_CLASSES = ("conv3x3", "conv3x3_residual", "qkv", "score", "softmax", "pv", "encoder", "decoder", "gather", "prepost")
+
+    def profile(self) -> Dict[str, tuple]:
+        """One eager pass of the staged chunk with CUDA events around every launch group: {class: (ms, groups)}."""
+        n = len(self.PROF_CLASSES)
+        ms, cnt = np.zeros(n, np.float32), np.zeros(n, np.int64)
+        _capi.check(_capi.lib().vsr_sttn_profile(self._h, _capi.ptr(ms, C.c_float), _capi.ptr(cnt, C.c_int64), n))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROF_CLASSES)}
+
     def time_conv(self, T: int, n: int) -> np.ndarray:
         ms = np.zeros(n, np.float32)
         _capi.check(_capi.lib().vsr_sttn_time_conv(self._h, T, n, _capi.ptr(ms, C.c_float)))
