@@ -1,21 +1,24 @@
 #!/usr/bin/env python
 """bench.py — inpainted frames/s at 1080p, STTN (sttn-auto, neighbor_stride 5), BASELINE.json config 2.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ...]
 
-A *step* is one pass of the hot path over one chunk: 50 synthetic 1920x1080 frames + the default-bbox
-mask (`STTNAutoInpaint`'s clip_gap, sttn_auto_inpaint.py:242-245); the 300-frame clip of config 2 is
-K = 6 steps.  Prints ONE JSON line (rank 0):
-  value   frames/s with the chunk's strips already resident in HBM (device work only, CUDA events on the
-          engine's stream)
-  e2e     frames/s through the reference-facing call with HOST numpy frames: host->device copy of the
-          strips, all kernels, device->host copy, composite into the host frames — what
-          STTNAutoInpaint's chunk loop does per chunk
-  roofline  the dominant kernel (transformer-block 3x3 conv, tcgen05 implicit GEMM) timed live
-  cpu_baseline  the oracle port (torch CPU fp32 restatement of the reference) on a bounded sample
-`--impl reference` times only that CPU port, with all host threads, on the same config.
-Under torchrun (N > 1) every rank owns K chunks of its own (weak scaling, no data-path collective:
-chunks are independent units); timing is the max over ranks.
+A *step* is one pass of the hot path over one chunk: 50 synthetic 1920x1080 frames + the default-bbox mask (`STTNAutoInpaint`'s
+clip_gap, sttn_auto_inpaint.py:242-245); the 300-frame clip of config 2 is K = 6 steps.  Prints ONE JSON line (rank 0):
+  value     frames/s with the chunk's strips already resident in HBM (device work only, CUDA events on the engine's stream)
+  e2e       frames/s through the reference-facing call with HOST numpy frames: host->device copy of the strips, all kernels,
+            device->host copy, composite into the host frames — what STTNAutoInpaint's chunk loop does per chunk
+  roofline  the dominant kernel (transformer-block 3x3 conv 256->256, tcgen05 implicit GEMM) AS IT RUNS IN THE CHUNK: one eager pass
+            of the chunk with CUDA events around every launch group (vsr_sttn_profile), algorithmic FLOPs / measured time against
+            the sustained bf16 peak of MEASURED_PEAKS.json; the isolated back-to-back figure is kept beside it
+  cpu_baseline  the reference's own `STTNInpaint.__call__` (oracle/_ref, kind "reference") on a bounded sample on the host cores,
+            or the oracle port when the reference modules did not travel (kind "port")
+`--impl reference` times only that CPU path, with all host threads, on the same config.
+Under torchrun (N > 1) every rank owns K chunks of its own (weak scaling, no data-path collective: chunks are independent units,
+SURVEY.md §8e); timing is the max over ranks.
+
+Everything that touches CUDA goes through `BACKEND` and every engine is built by a `make_*` factory, so that tests/test_bench_dryrun.py
+can run every workload and both arms on the CPU with stand-ins (a name error or a JSON-schema regression fails in `-m "not gpu"`).
 """
 import argparse
 import json
@@ -33,8 +36,8 @@ sys.path.insert(0, ROOT)
 H, W, CHUNK = 1080, 1920, 50
 FLOP_PER_FRAME = 642.8e9  # SURVEY.md §8d / BASELINE.md §3 (2*MAC of conv+matmul per output frame)
 METRIC = "inpainted frames/sec at 1080p (STTN, window=5)"
-CPU_SAMPLE = ("one 50-frame 1080p chunk sampled as: encoder on 50 frames + 5 of its 10 windows (T=10,14,14,15,15; 8 blocks + "
-              "decoder) + pre/post on 5 frames, extrapolated by counts (1,5,4 windows; x10 pre/post)")
+WORKLOAD = "STTN sttn-auto 1080p synthetic clip, fixed subtitle bbox, neighbor_stride=5 (BASELINE config 2); step = one 50-frame chunk"
+CPU_BUDGET_S = 240.0      # wall-clock target of a whole `--impl reference --steps K --warmup W` run
 
 
 def peaks():
@@ -43,6 +46,64 @@ def peaks():
         d = json.load(open(p))
         return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
     return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CUDA / torch.distributed seam
+class CudaBackend:
+    """torch is the container for events, streams and torch.distributed only (the engines own their device memory)."""
+
+    def __init__(self):
+        import torch
+
+        self.torch = torch
+        self.world = 1
+        self.local = 0
+
+    def available(self):
+        return self.torch.cuda.is_available()
+
+    def setup(self, local, world):
+        self.local, self.world = local, world
+        self.torch.cuda.set_device(local)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.torch.device("cuda", local))
+
+    def device(self):
+        return self.torch.device("cuda", self.local)
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def stream(self, ptr):
+        return self.torch.cuda.ExternalStream(ptr, device=self.device())
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def finish(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+BACKEND = None   # set in main(); the dry-run test installs a stand-in
 
 
 class ClockSampler:
@@ -84,158 +145,212 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def weights_source():
-    """(what the product's constructor gets, description).  With the reference checkpoint staged the product loads it with its own loader;
-    without it the tensors are seeded random-init values of the architecture — the table of shapes lives with the oracle, and that is the
-    only thing the device legs ever take from `oracle/` (a data generator, no arithmetic of the path)."""
+# ------------------------------------------------------------------------------------------------ engines (factories = test seam)
+def sttn_weights():
+    """(what the product's constructor gets, description): the reference checkpoint when it is staged, else seeded random-init
+    tensors of the architecture from the package's own shape table."""
     p = os.path.join(ROOT, "weights", "sttn-auto", "infer_model.pth")
     if os.path.exists(p):
         return p, "reference checkpoint sttn-auto/infer_model.pth"
-    return _random_init("sttn_oracle", 0), "seeded random-init weights of the sttn-auto architecture"
+    from vsr_b200 import synthetic as S
+
+    return S.random_sttn_weights(0), "seeded random-init weights of the sttn-auto architecture"
 
 
-def _random_init(module, seed):
-    import importlib
+def make_sttn(device):
+    from vsr_b200 import STTNInpaint
 
-    return {k: v.numpy() for k, v in importlib.import_module("oracle." + module).random_weights(seed).items()}
-
-
-def oracle_weights(src):
-    """the same weights as torch tensors for the CPU port (cpu_baseline / --impl reference legs only)"""
-    import torch
-    from oracle import sttn_oracle as O
-
-    return O.load_weights(src) if isinstance(src, str) else {k: torch.from_numpy(v) for k, v in src.items()}
+    src, desc = sttn_weights()
+    return STTNInpaint(device, src), src, desc
 
 
-def cpu_port_fps(w, frames, mask, threads, calibrate=False):
-    """CPU port (oracle = torch-CPU restatement of the reference) on a BOUNDED sample of one 50-frame 1080p
-    chunk.  Per-frame cost depends on the window length (attention is quadratic in it), so a short clip would
-    flatter the CPU; instead time the real pieces of the chunk and extrapolate by their counts:
-      encoder on all 50 frames + 5 of the 10 windows (T = 10, 14, 14, 15, 15: 8 transformer blocks + decoder +
-      quantise, with their full reference-frame sets) + crop/resize/composite on 5 frames (cv2, as the
-      reference does).  chunk = enc + t10 + 5*t14 + 4*t15 + 10*prepost5   (window lengths
-      10,14,15,14,15,14,15,14,15,14)."""
-    import torch
-    from oracle import sttn_oracle as O
-
-    torch.set_num_threads(threads)
-    t_all0 = time.perf_counter()
-    strip = [np.ascontiguousarray(f[720:1080]) for f in frames]
-    try:
-        import cv2
-        resize = lambda a, w_, h_: cv2.resize(a, (w_, h_))  # noqa: E731
-    except ImportError:  # pragma: no cover
-        resize = lambda a, w_, h_: O.cv2_resize_linear_u8(a, w_, h_)  # noqa: E731
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        small = [resize(s, 640, 120) for s in strip[:5]]
-        t_pre5 = time.perf_counter() - t0
-        small += [resize(s, 640, 120) for s in strip[5:]]
-        if calibrate:  # one 6-frame window is enough to rank thread counts
-            t0 = time.perf_counter()
-            feats = O.encoder(w, O.frames_to_tensor(small[:6]))
-            O.quantise(O.decoder(w, O.infer(w, feats)[:6]))
-            return 1.0 / (time.perf_counter() - t0), 0.0
-        t0 = time.perf_counter()
-        feats = O.encoder(w, O.frames_to_tensor(small))
-        t_enc = time.perf_counter() - t0
-        sched = O.window_schedule(len(frames))
-        t_win, n_win, img = {}, {}, None
-        for nb, refs in sched:  # up to two windows of each distinct length (T = 10, 14, 15): ~6 of the 10 windows
-            T = len(nb) + len(refs)
-            if n_win.get(T, 0) >= 2:
-                continue
-            t0 = time.perf_counter()
-            img = O.quantise(O.decoder(w, O.infer(w, feats[nb + refs])[:len(nb)]))
-            t_win[T] = t_win.get(T, 0.0) + time.perf_counter() - t0
-            n_win[T] = n_win.get(T, 0) + 1
-        t_win = {T: v / n_win[T] for T, v in t_win.items()}
-        t0 = time.perf_counter()
-        for i in range(5):
-            up = resize(img[i % len(img)].astype(np.float32), W, 360).astype(np.uint8)[:, :, ::-1]
-            m = (mask[720:1080] > 127)[:, :, None]
-            strip[i][:] = np.where(m, up, strip[i])
-        t_post5 = time.perf_counter() - t0
-    counts = {}
-    for nb, refs in sched:
-        counts[len(nb) + len(refs)] = counts.get(len(nb) + len(refs), 0) + 1
-    avg = float(np.mean(list(t_win.values())))
-    chunk = t_enc + sum(n * t_win.get(T, avg * T / np.mean(list(t_win))) for T, n in counts.items()) + (t_pre5 + t_post5) * len(frames) / 5
-    return len(frames) / chunk, time.perf_counter() - t_all0
-
-
-def best_cpu_threads(w, frames, mask):
-    """torch's CPU convs do not scale to every core of a 100+-thread host: time one 6-frame window at a few
-    thread counts and keep the fastest, so the baseline is the best the host can do, not the most threads."""
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} | {ncpu})
-    best, best_fps = ncpu, 0.0
-    for c in cands:
-        fps, _ = cpu_port_fps(w, frames, mask, c, calibrate=True)
-        if fps > best_fps:
-            best, best_fps = c, fps
-    return best
-
-
-def run_reference(args, rank, world):
-    import torch
-    from oracle import sttn_oracle as O
-
-    if rank != 0:
-        return
-    src, wdesc = weights_source()
-    w = oracle_weights(src)
-    frames = O.synthetic_clip(CHUNK, H, W, seed=0)
-    mask = O.default_mask(H, W)
-    threads = best_cpu_threads(w, frames, mask)  # doubles as warm-up
-    vals, dts = [], []
-    for _ in range(args.steps):
-        fps, dt = cpu_port_fps(w, frames, mask, threads)
-        vals.append(fps)
-        dts.append(dt)
-    value = float(np.mean(vals))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": f"synthetic 1080p clip; {wdesc}",
-            "config": {"workload": "STTN sttn-auto 1080p synthetic clip, fixed subtitle bbox, neighbor_stride=5 (BASELINE config 2)",
-                       "frame": [H, W], "chunk": CHUNK, "neighbor_stride": 5, "ref_length": 10},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": CPU_SAMPLE + f" (torch {torch.__version__} CPU fp32, {threads} of {os.cpu_count()} threads: "
-                                       "fastest of a sweep)"},
-            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
-
-
-def run_det(args, rank, world, local):
-    """Secondary line: STTNDetInpaint on 46-frame 1080p batches (what `video_inpaint` feeds it for a 300-frame
-    interval, batch_generator 46x6+24 — SURVEY §8a D-rows), device-resident and through the host call."""
-    import torch
-    import torch.distributed as dist
+def make_sttn_det(device):
     from vsr_b200 import STTNDetInpaint
     from vsr_b200 import synthetic as S
 
     p = os.path.join(ROOT, "weights", "sttn-det", "sttn.pth")
     if os.path.exists(p):
-        eng, wdesc = STTNDetInpaint(torch.device("cuda", local), p), "reference checkpoint sttn-det/sttn.pth"
-    else:
-        eng = STTNDetInpaint(torch.device("cuda", local), _random_init("sttn_oracle", 1))
-        wdesc = "seeded random-init weights of the sttn-det architecture"
+        return STTNDetInpaint(device, p), "reference checkpoint sttn-det/sttn.pth"
+    return STTNDetInpaint(device, S.random_sttn_weights(1)), "seeded random-init weights of the sttn-det architecture"
+
+
+def detector_dir():
+    d = os.path.join(ROOT, "weights", "V5", "ch_det")
+    if not os.path.exists(os.path.join(d, "inference.pdiparams")):
+        raise SystemExit("this workload needs weights/V5/ch_det (tools/stage_weights.py)")
+    return d
+
+
+def make_detector(device):
+    from vsr_b200.dbnet import TextDetector
+
+    return TextDetector(detector_dir(), device)
+
+
+def make_subtitle_detect(device):
+    from vsr_b200 import SubtitleDetect
+
+    return SubtitleDetect("", model_dir=detector_dir(), device=device)
+
+
+def make_lama(device):
+    from vsr_b200 import LamaInpaint
+
+    npz = os.path.join(ROOT, "weights", "big-lama", "big-lama.npz")
+    if not os.path.exists(npz):
+        raise SystemExit("bench.py --workload lama needs weights/big-lama/big-lama.npz (tools/stage_weights.py --lama)")
+    return LamaInpaint(device, npz), npz, "reference big-lama weights (conv kernels stored fp16)"
+
+
+def propainter_dir():
+    mdir = os.path.join(ROOT, "weights", "propainter")
+    need = ["raft-things.pth", "recurrent_flow_completion.pth"]
+    ok = all(os.path.exists(os.path.join(mdir, f)) for f in need) and any(os.path.exists(os.path.join(mdir, f)) for f in ("ProPainter.pth", "ProPainter.f16.pth"))
+    if not ok:
+        raise SystemExit("bench.py --workload propainter needs weights/propainter/{raft-things,recurrent_flow_completion,ProPainter}.pth (tools/stage_weights.py)")
+    return mdir
+
+
+def make_propainter(device):
+    from vsr_b200.propainter_inpaint import PropainterInpaint
+
+    return PropainterInpaint(device, propainter_dir())
+
+
+def synthetic():
+    from vsr_b200 import synthetic as S
+
+    return S
+
+
+def chunk_schedule(T, stride=5, ref=10):
+    """[(neighbours, refs)] of a T-frame chunk (sttn_auto_inpaint.py:142-146, get_ref_index :107-120) — pure Python, for FLOP counts."""
+    out = []
+    for f in range(0, T, stride):
+        nb = list(range(max(0, f - stride), min(T, f + stride + 1)))
+        out.append((nb, [i for i in range(0, T, ref) if i not in nb]))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs (reference / port)
+def reference_available():
+    from oracle import ref_import
+
+    return ref_import.available()
+
+
+class CpuReference:
+    """The reference's own CPU implementation of the path: `STTNInpaint(torch.device('cpu'), model_path).__call__(frames, mask)`
+    (backend/inpaint/sttn_auto_inpaint.py:28-97) from the unmodified modules (oracle/ref_import.py), or — when those did not travel —
+    the oracle port of the same call (oracle/sttn_oracle.py `sttn_call`)."""
+
+    def __init__(self, weights_src, threads=None):
+        import torch
+
+        self.torch = torch
+        self.threads = threads or (os.cpu_count() or 1)
+        torch.set_num_threads(self.threads)
+        self.kind = "port"
+        self.model = None
+        if isinstance(weights_src, str) and weights_src.endswith(".pth") and reference_available():
+            try:
+                from oracle import ref_import
+
+                ref_import.install()
+                from backend.inpaint.sttn_auto_inpaint import STTNInpaint as RefSTTNInpaint
+
+                self.model = RefSTTNInpaint(torch.device("cpu"), weights_src)
+                self.kind = "reference"
+            except Exception as e:  # e.g. a module of the reference's environment is missing on this box
+                print(f"[bench] unmodified reference not usable here ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        if self.model is None:
+            from oracle import sttn_oracle as O
+
+            self.O = O
+            self.w = O.load_weights(weights_src) if isinstance(weights_src, str) else {k: torch.from_numpy(v) for k, v in weights_src.items()}
+
+    def __call__(self, frames, mask):
+        with self.torch.no_grad():
+            if self.model is not None:
+                return self.model(frames, mask)
+            return self.O.sttn_call(self.w, frames, mask)
+
+    def fps(self, frames, mask):
+        t0 = time.perf_counter()
+        self(frames, mask)
+        dt = time.perf_counter() - t0
+        return len(frames) / dt, dt
+
+    def describe(self):
+        what = ("unmodified reference STTNInpaint.__call__ (backend/inpaint/sttn_auto_inpaint.py:43-97)" if self.kind == "reference"
+                else "oracle port of STTNInpaint.__call__ (torch CPU fp32 restatement)")
+        return f"{what}, torch {self.torch.__version__} CPU fp32, {self.threads} of {os.cpu_count()} threads"
+
+
+def cpu_sample_frames(est_fps, steps, budget_s):
+    """Frames per CPU step so that `steps` steps fit the budget: between 6 (one two-window call) and a whole 50-frame chunk.  Shorter
+    samples have shorter attention windows, i.e. they are FASTER per frame than a whole chunk: the bias favours the CPU."""
+    return int(min(CHUNK, max(6, budget_s * est_fps / max(steps, 1))))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    S = synthetic()
+    src, wdesc = sttn_weights()
+    cpu = CpuReference(src)
+    frames = S.synthetic_clip(CHUNK, H, W, seed=0)
+    mask = S.default_mask(H, W)
+    est, _ = cpu.fps(frames[:6], mask)                      # calibration call, doubles as the first warm-up
+    n = cpu_sample_frames(est, args.steps + args.warmup, CPU_BUDGET_S)
+    for _ in range(args.warmup):
+        cpu.fps(frames[:n], mask)
+    dts = []
+    for _ in range(args.steps):
+        dts.append(cpu.fps(frames[:n], mask)[1])
+    value = n * len(dts) / float(np.sum(dts))
+    sample = (f"each step = the first {n} frames of the 50-frame 1080p chunk through the {cpu.describe()}; sample sized so that "
+              f"{args.steps}+{args.warmup} steps take ~{CPU_BUDGET_S:.0f} s (shorter windows than a whole chunk: favours the CPU)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": f"synthetic 1080p clip (seeded, generated on host); {wdesc}",
+            "config": {"workload": WORKLOAD, "frame": [H, W], "chunk": CHUNK, "neighbor_stride": 5, "ref_length": 10,
+                       "strip": [720, 1080, 0, 1920], "frames_per_step": n},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cpu.threads, "kind": cpu.kind, "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(src, frames, mask, n_frames):
+    cpu = CpuReference(src)
+    cpu.fps(frames[:4], mask)                               # warm-up (thread pools, oneDNN primitives)
+    fps, dt = cpu.fps(frames[:n_frames], mask)
+    return {"value": fps, "unit": "frames/s", "cores": cpu.threads, "kind": cpu.kind,
+            "sample": f"the first {n_frames} frames of the 50-frame 1080p chunk through the {cpu.describe()}: {dt:.1f} s of CPU work "
+                      "(shorter windows than a whole chunk: favours the CPU)"}
+
+
+# ------------------------------------------------------------------------------------------------ secondary workloads
+def run_det(args, rank, world):
+    """Secondary line: STTNDetInpaint on 46-frame 1080p batches (what `video_inpaint` feeds it for a 300-frame interval,
+    batch_generator 46x6+24 — SURVEY §8a D-rows), device-resident and through the host call."""
+    B, S = BACKEND, synthetic()
+    eng, wdesc = make_sttn_det(B.device())
     T = 46
     frames = S.synthetic_clip(T, H, W, seed=100 + rank)
     mask = S.default_mask(H, W)
-    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local))
+    stream = B.stream(eng.cuda_stream)
     work = [f.copy() for f in frames]
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         eng.stage(work, mask)
         eng.compute()
     eng.sync()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(B.event(), B.event()) for _ in range(args.steps)]
     l0 = eng.launch_count
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    B.barrier()
+    B.sync()
     for a, b in evs:
         eng.stage(work, mask)
         eng.sync()
@@ -243,7 +358,7 @@ def run_det(args, rank, world, local):
         eng.compute()
         b.record(stream)
     eng.sync()
-    torch.cuda.synchronize()
+    B.sync()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     launches = eng.launch_count - l0
     batches = [[f.copy() for f in frames] for _ in range(args.steps)]
@@ -252,90 +367,89 @@ def run_det(args, rank, world, local):
     for b in batches:
         eng.inpaint_inplace(b, mask)
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0].item()), float(t[1].item())
-    Tw = 29
-    conv_ms = float(np.median(eng.time_conv(Tw, 20)))
-    conv_flop = 2.0 * Tw * 60 * 108 * 2304 * 256
-    burst, sustained, _, src = peaks()
+    dev_ms, e2e_s = B.max_over_ranks([dev_ms, e2e_s])
+    eng.stage(work, mask)
+    eng.profile()
+    eng.stage(work, mask)
+    prof = eng.profile()
+    conv_ms = prof["conv3x3"][0] + prof["conv3x3_residual"][0]
+    passes = sum(len(nb) + len(rf) for nb, rf in chunk_schedule(T))
+    conv_flop = 3 * 8 * passes * 60 * 108 * 2.0 * 2304 * 256
+    burst, sustained, _, peak_src = peaks()
     if rank == 0:
         n = world * args.steps * T
         sh = int(W * 5 / 18)
         print(json.dumps({
             "metric": "inpainted frames/sec at 1080p (STTN-det, window=5)", "value": n / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": f"synthetic 1080p clip; {wdesc}",
             "config": {"workload": "STTN sttn-det inpaint on 46-frame 1080p batches (inpaint half of BASELINE config 4; detection not included)",
                        "frame": [H, W], "batch": T, "strip_h": sh},
             "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": T * sh * W * 3, "d2h_bytes_per_step": T * sh * W * 3,
                     "api": "STTNDetInpaint.inpaint_inplace(frames, mask), synchronous"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": f"tcgen05 implicit-GEMM 3x3 conv 256->256, {Tw}x60x108 px", "achieved": conv_flop / conv_ms / 1e9,
-                         "peak": burst, "unit": "TFLOP/s", "frac": conv_flop / conv_ms / 1e9 / burst, "traffic": None, "peak_source": f"{src} (burst bf16)",
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM 3x3 conv 256->256 on 60x108 maps, as it runs in the batch (in-situ events)",
+                         "achieved": conv_flop / (conv_ms * 1e-3) / 1e12, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": conv_flop / (conv_ms * 1e-3) / 1e12 / sustained, "traffic": None, "peak_source": f"{peak_src} (sustained bf16)",
+                         "in_situ_ms": {k: round(v[0], 3) for k, v in prof.items()},
                          "whole_step_frac_of_sustained": 758.2e9 * n / world / (dev_ms * 1e-3) / 1e12 / sustained}}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_dbnet(args, rank, world, local):
-    """Secondary line: the DBNet text detector (SURVEY §8a T2) on 1080p frames — `SubtitleDetect.detect_subtitle`'s
-    `TextDetection.predict` on the B200 against the oracle interpreter of the same PIR program on the host cores."""
-    import torch
-    import torch.distributed as dist
-    from vsr_b200.dbnet import TextDetector
-
-    model_dir = os.path.join(ROOT, "weights", "V5", "ch_det")
-    if not os.path.exists(os.path.join(model_dir, "inference.pdiparams")):
-        raise SystemExit("bench.py --workload dbnet needs weights/V5/ch_det (tools/stage_weights.py)")
+def _text_frames(n):
     import cv2
 
     yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
     frames = []
-    for i in range(4):
+    for i in range(n):
         img = np.stack([96 + 60 * np.sin(xx / 211 + c + i) + 50 * np.cos(yy / 173 - c) for c in range(3)], -1).clip(0, 255).astype(np.uint8)
         for txt, org in ((f"The quick brown fox {i}123", (400, 1000)), ("second line of a subtitle", (500, 930))):
             cv2.putText(img, txt, org, cv2.FONT_HERSHEY_SIMPLEX, 2.0, (0, 0, 0), 9, cv2.LINE_AA)
             cv2.putText(img, txt, org, cv2.FONT_HERSHEY_SIMPLEX, 2.0, (255, 255, 255), 4, cv2.LINE_AA)
         frames.append(img)
-    det = TextDetector(model_dir, torch.device("cuda", local))
-    for _ in range(max(args.warmup, 3)):
+    return frames
+
+
+def run_dbnet(args, rank, world):
+    """Secondary line: the DBNet text detector (SURVEY §8a T2) on 1080p frames — `SubtitleDetect.detect_subtitle`'s
+    `TextDetection.predict` on the B200 against the oracle interpreter of the same PIR program on the host cores."""
+    B = BACKEND
+    frames = _text_frames(4)
+    det = make_detector(B.device())
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         for f in frames:
             det.predict(f)
     per = 8
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    B.barrier()
+    B.sync()
     net_ms = det.time_network(args.steps * per)
     l0 = det.launch_count
     t0 = time.perf_counter()
+    boxes = []
     for _ in range(args.steps):
         for j in range(per):
             boxes = det.predict(frames[j % len(frames)])[0]["dt_polys"]
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([net_ms, e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    net_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    net_ms, e2e_s = B.max_over_ranks([net_ms, e2e_s])
     cpu = None
     if rank == 0 and not args.no_cpu:
+        import torch
         from oracle import dbnet_oracle as D
 
-        g = D.Graph(model_dir)
+        g = D.Graph(detector_dir())
         D.detect_subtitle(g, frames[0])
         c0 = time.perf_counter()
         for f in frames[:3]:
             D.detect_subtitle(g, f)
         cpu = {"value": 3 / (time.perf_counter() - c0), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "3 of the 1080p frames through the oracle interpreter of the same PIR program (torch fp32) + DB post-process"}
-    burst, sustained, _, src = peaks()
+    burst, sustained, _, peak_src = peaks()
     if rank == 0:
         n = world * args.steps * per
         flop = 267.6e9   # SURVEY §8d: 133.8 GMAC per [1,3,544,960] frame
         print(json.dumps({
             "metric": "text-detected frames/sec at 1080p (DBNet PP-OCRv5_server_det)", "value": world * 1e3 / net_ms, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": net_ms * per, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": warm, "ms_per_step": net_ms * per, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic 1080p frames with two rendered text lines; reference model files V5/ch_det",
             "config": {"workload": "DBNet detection of 1080p frames (detection half of BASELINE config 4): resize to 544x960, network, DB post-process",
                        "frame": [H, W], "frames_per_step": per, "boxes_last_frame": int(len(boxes))},
@@ -343,62 +457,49 @@ def run_dbnet(args, rank, world, local):
                     "api": "TextDetector.predict(bgr_frame) -> dt_polys, synchronous, host post-process included"},
             "gpu_launches": int(args.steps * per * 247 + (det.launch_count - l0)),
             "roofline": {"bound": "tensor", "kernel": "whole network graph (247 launches, latency-bound small layers)", "achieved": flop / net_ms / 1e9,
-                         "peak": sustained, "unit": "TFLOP/s", "frac": flop / net_ms / 1e9 / sustained, "traffic": None, "peak_source": f"{src} (sustained bf16)"},
+                         "peak": sustained, "unit": "TFLOP/s", "frac": flop / net_ms / 1e9 / sustained, "traffic": None, "peak_source": f"{peak_src} (sustained bf16)"},
             "cpu_baseline": cpu}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_lama(args, rank, world, local):
+def run_lama(args, rank, world):
     """Secondary line: LAMA (BASELINE config 1 / SURVEY §8a L1-L3) through `LamaInpaint.__call__` on 1080p frames: the strip
     of int(1920*3/16) = 360 rows around the subtitle goes through big-lama at native resolution, frame by frame."""
-    import torch
-    import torch.distributed as dist
-    from vsr_b200 import LamaInpaint
-    from vsr_b200 import synthetic as S
-
-    npz = os.path.join(ROOT, "weights", "big-lama", "big-lama.npz")
-    if os.path.exists(npz):
-        eng, wdesc, wsrc = LamaInpaint(torch.device("cuda", local), npz), "reference big-lama weights (conv kernels stored fp16)", npz
-    else:
-        wsrc = _random_init("lama_oracle", 3)
-        eng, wdesc = LamaInpaint(torch.device("cuda", local), wsrc), "seeded random-init weights of the big-lama architecture"
+    B, S = BACKEND, synthetic()
+    eng, wsrc, wdesc = make_lama(B.device())
     T = 4
     frames = S.synthetic_clip(T, H, W, seed=200 + rank)
     mask = S.default_mask(H, W)
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         eng(frames, mask)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    B.barrier()
+    B.sync()
     net_ms = eng.model.time_network(args.steps * 2) / T      # one graph launch = the strips of T frames
     l0 = eng.model.launch_count
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = eng(frames, mask)
+        eng(frames, mask)
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([net_ms, e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    net_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    net_ms, e2e_s = B.max_over_ranks([net_ms, e2e_s])
     cpu = None
     if rank == 0 and not args.no_cpu:
+        import torch
         from oracle import lama_oracle as LO
 
-        w = LO.load_weights(wsrc) if isinstance(wsrc, str) else {k: torch.from_numpy(v) for k, v in wsrc.items()}
+        w = LO.load_weights(wsrc)
         LO.lama_call(w, frames[:1], mask)
         c0 = time.perf_counter()
         LO.lama_call(w, frames[:2], mask)
         cpu = {"value": 2 / (time.perf_counter() - c0), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "2 of the 1080p frames through the oracle (torch fp32 restatement, bit-identical to the TorchScript module)"}
-    burst, sustained, _, src = peaks()
+    burst, sustained, _, peak_src = peaks()
     if rank == 0:
         n = world * args.steps * T
         sh = int(W * 3 / 16)
         flop = 1158e9   # SURVEY §8d: conv FLOPs of one 360x1920 strip frame (+36 rfft2/irfft2 pairs)
         print(json.dumps({
             "metric": "inpainted frames/sec at 1080p (LAMA big-lama)", "value": world * 1e3 / net_ms, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": net_ms * T, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": warm, "ms_per_step": net_ms * T, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": f"synthetic 1080p clip; {wdesc}",
             "config": {"workload": "LAMA inpaint of 1080p frames (BASELINE config 1 model on the video strip path): strip 360x1920 per frame",
                        "frame": [H, W], "frames_per_step": T, "strip_h": sh},
@@ -407,114 +508,159 @@ def run_lama(args, rank, world, local):
             "gpu_launches": int(eng.model.launch_count - l0 + args.steps * 560),
             "roofline": {"bound": "tensor", "kernel": "whole network graph (~560 launches, 4 strips per launch, 45x240 feature grid)",
                          "achieved": flop / net_ms / 1e9, "peak": sustained, "unit": "TFLOP/s", "frac": flop / net_ms / 1e9 / sustained, "traffic": None,
-                         "peak_source": f"{src} (sustained bf16)"},
+                         "peak_source": f"{peak_src} (sustained bf16)"},
             "cpu_baseline": cpu}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_config4(args, rank, world, local):
+def run_lama512(args, rank, world):
+    """BASELINE config 1 itself: `LamaInpaint.inpaint(image, mask)` (lama_inpaint.py:17-28) on one 512x512 random-texture image with the
+    rectangle mask rows 400-470, cols 60-450."""
+    B, S = BACKEND, synthetic()
+    eng, wsrc, wdesc = make_lama(B.device())
+    img = S.synthetic_clip(1, 512, 512, seed=0)[0]
+    mask = np.zeros((512, 512), np.uint8)
+    mask[400:470, 60:450] = 255
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        out = eng.inpaint(img, mask)
+    B.barrier()
+    B.sync()
+    per = 8
+    l0 = eng.model.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps * per):
+        out = eng.inpaint(img, mask)
+    e2e_s = time.perf_counter() - t0
+    launches = eng.model.launch_count - l0
+    net_ms = eng.model.time_network(args.steps * per)
+    net_ms, e2e_s = B.max_over_ranks([net_ms, e2e_s])
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        import torch
+        from oracle import lama_oracle as LO
+
+        w = LO.load_weights(wsrc)
+        LO.inpaint(w, img, mask)
+        c0 = time.perf_counter()
+        LO.inpaint(w, img, mask)
+        cpu = {"value": 1 / (time.perf_counter() - c0), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "the same 512x512 image through the oracle (torch fp32 restatement, bit-identical to the TorchScript module), once"}
+    burst, sustained, _, peak_src = peaks()
+    if rank == 0:
+        n = world * args.steps * per
+        flop = 439.8e9   # SURVEY §8a L2: conv FLOPs at 512x512
+        print(json.dumps({
+            "metric": "inpainted images/sec, LAMA 512x512 (BASELINE config 1)", "value": world * 1e3 / net_ms, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": net_ms * per, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": f"synthetic 512x512 texture + rectangle mask; {wdesc}",
+            "config": {"workload": "LAMA single-image inpaint 512x512 (BASELINE config 1)", "frame": [512, 512], "images_per_step": per,
+                       "hole_mean": float(np.asarray(out)[400:470, 60:450].mean())},
+            "e2e": {"value": n / e2e_s, "unit": "images/s", "h2d_bytes_per_step": per * (512 * 512 * 4), "d2h_bytes_per_step": per * 512 * 512 * 3,
+                    "api": "LamaInpaint.inpaint(image, mask), synchronous"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "whole network graph, one 64x64 feature grid (latency-bound: ~560 dependent launches)",
+                         "achieved": flop / net_ms / 1e9, "peak": sustained, "unit": "TFLOP/s", "frac": flop / net_ms / 1e9 / sustained, "traffic": None,
+                         "peak_source": f"{peak_src} (sustained bf16)"},
+            "cpu_baseline": cpu}), flush=True)
+
+
+def run_config4(args, rank, world):
     """BASELINE config 4 end to end on an in-memory 1080p clip: DBNet detection of the sampled frames -> interval planning ->
-    create_mask -> STTN-det on batch_generator batches, through `vsr_b200.video_inpaint_frames` (the loop of
-    SubtitleRemover.video_inpaint, main.py:260-333).  The reference arm of this line is the CPU port of the same chain."""
+    create_mask -> STTN-det on batch_generator batches.  N = 1: `vsr_b200.video_inpaint_frames` (the loop of SubtitleRemover.video_inpaint,
+    main.py:260-333).  N > 1 (`--gpus 8`, config 4's frame-batch shard): every rank detects its share of the sampled frames, ONE
+    all_gather_object exchanges the hits, every rank plans identically and inpaints its share of the batches (vsr_b200.distributed)."""
     import cv2
-    import torch
-    import torch.distributed as dist
-    from vsr_b200 import STTNDetInpaint, SubtitleDetect, video_inpaint_frames
-    from vsr_b200 import synthetic as S
 
-    T = 120
-    frames = S.synthetic_clip(T, H, W, seed=300 + rank)
-    for i, f in enumerate(frames):          # a subtitle on frames 11..110 (1-based), text changing every 48 frames
-        if 10 <= i < 110:
+    B, S = BACKEND, synthetic()
+    T = 120 if world == 1 else 300
+    frames = S.synthetic_clip(T, H, W, seed=300)          # the SAME clip on every rank: the job is sharded, not replicated (strong scaling)
+    for i, f in enumerate(frames):                        # a subtitle on frames 11..T-10 (1-based), text changing every 48 frames
+        if 10 <= i < T - 10:
             txt = f"subtitle line number {i // 48} of the clip"
             cv2.putText(f, txt, (420, 1020), cv2.FONT_HERSHEY_SIMPLEX, 1.8, (0, 0, 0), 9, cv2.LINE_AA)
             cv2.putText(f, txt, (420, 1020), cv2.FONT_HERSHEY_SIMPLEX, 1.8, (255, 255, 255), 4, cv2.LINE_AA)
-    dev = torch.device("cuda", local)
-    p = os.path.join(ROOT, "weights", "sttn-det", "sttn.pth")
-    model = STTNDetInpaint(dev, p if os.path.exists(p) else _random_init("sttn_oracle", 1))
-    det = SubtitleDetect("", model_dir=os.path.join(ROOT, "weights", "V5", "ch_det"), device=dev)
-    det.SAMPLE_STEP = 3                     # 30 fps video (subtitle_detect.py:29-39)
-    for _ in range(max(min(args.warmup, 2), 1)):
-        out, sub, se = video_inpaint_frames(frames, det, model)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    model, _ = make_sttn_det(B.device())
+    det = make_subtitle_detect(B.device())
+    det.SAMPLE_STEP = 3                                   # 30 fps video (subtitle_detect.py:29-39)
+    if world == 1:
+        from vsr_b200 import video_inpaint_frames
+
+        run = lambda: video_inpaint_frames(frames, det, model)   # noqa: E731
+    else:
+        from vsr_b200.distributed import video_inpaint_frames_sharded
+
+        run = lambda: video_inpaint_frames_sharded(frames, det, model, rank, world)   # noqa: E731
+    warm = max(min(args.warmup, 2), 1)
+    for _ in range(warm):
+        out, sub, se = run()
+    B.barrier()
+    B.sync()
     l0 = model.launch_count
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out, sub, se = video_inpaint_frames(frames, det, model)
+        out, sub, se = run()
+    B.sync()
+    B.barrier()
     e2e_s = time.perf_counter() - t0
-    launches = model.launch_count - l0 + args.steps * len(range(1, T + 1, 3)) * 249   # + the detector's graph (247 kernels), pre-process, map extraction
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    n_det = len(range(1, T + 1, 3))
+    launches = model.launch_count - l0 + args.steps * (n_det // world) * 249   # + the detector's graph (247 kernels), pre-process, map extraction
+    e2e_s, = B.max_over_ranks([e2e_s])
     n_inpainted = sum(e - s + 1 for s, e in se.items())
     if rank == 0:
-        n = world * args.steps * T
+        n = args.steps * T
         print(json.dumps({
             "metric": "frames/sec at 1080p, detection + STTN-det (BASELINE config 4)", "value": n / e2e_s, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(min(args.warmup, 2), 1), "ms_per_step": e2e_s / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic 1080p clip with rendered subtitles; reference model files",
-            "config": {"workload": "config 4 chain on a 120-frame 1080p clip: DBNet on every 3rd frame, planning, create_mask, STTN-det batches",
-                       "frame": [H, W], "frames": T, "detected_frames": len(range(1, T + 1, 3)), "inpainted_frames": n_inpainted,
+            "steps": args.steps, "warmup": warm, "ms_per_step": e2e_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic 1080p clip with rendered subtitles; reference model files",
+            "config": {"workload": f"config 4 chain on a {T}-frame 1080p clip: DBNet on every 3rd frame, planning, create_mask, STTN-det batches"
+                                   + ("" if world == 1 else f", sampled frames and batches dealt over {world} ranks, one all_gather_object of the detections"),
+                       "frame": [H, W], "frames": T, "detected_frames": n_det, "inpainted_frames": n_inpainted,
                        "intervals": {str(k): v for k, v in se.items()}},
-            "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": len(range(1, T + 1, 3)) * H * W * 3 + n_inpainted * int(W * 5 / 18) * W * 3,
+            "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": n_det * H * W * 3 + n_inpainted * int(W * 5 / 18) * W * 3,
                     "d2h_bytes_per_step": n_inpainted * int(W * 5 / 18) * W * 3, "api": "vsr_b200.video_inpaint_frames(frames, SubtitleDetect, STTNDetInpaint)"},
             "gpu_launches": int(launches), "note": "host-timed whole chain (inputs are host numpy frames); the per-stage device numbers are the "
                                                    "sttn-det and dbnet workloads"}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_propainter(args, rank, world, local):
+def run_propainter(args, rank, world):
     """Secondary line: ProPainter (BASELINE config 3 / SURVEY §8a P1-P7) through `PropainterInpaint.__call__` on a 720p clip: the 240x1280
     strip around the subtitle goes through RAFT, flow completion, image propagation and the generator, `--pp-frames` frames per call
-    (<= sub_video_length = 80, one reference sub-video).  STATUS: the device pipeline had not run on a B200 when round 1 ended (DESIGN.md §7);
-    this leg exists so that the first GPU session of round 2 measures it with the same contract as the other workloads.  There is no separate
-    device-resident leg yet (flows take a host round trip between RAFT and the completion network): `value` is the same end-to-end rate."""
-    import torch
-    import torch.distributed as dist
-    from vsr_b200 import synthetic as S
-    from vsr_b200.propainter_inpaint import PropainterInpaint
-
-    mdir = os.path.join(ROOT, "weights", "propainter")
-    need = ["raft-things.pth", "recurrent_flow_completion.pth", "ProPainter.pth"]
-    if not all(os.path.exists(os.path.join(mdir, f)) for f in need):
-        raise SystemExit("bench.py --workload propainter needs weights/propainter/{raft-things,recurrent_flow_completion,ProPainter}.pth "
-                         "(tools/stage_weights.py; drop weights/propainter from .gpurunignore so that they travel)")
+    (<= sub_video_length = 80, one reference sub-video).  There is no separate device-resident leg (flows take a host round trip between
+    RAFT and the completion network): `value` is the same end-to-end rate."""
+    B, S = BACKEND, synthetic()
+    mdir = propainter_dir()
     Hp, Wp, T = 720, 1280, args.pp_frames
     frames = S.synthetic_clip(T, Hp, Wp, seed=300 + rank)
     mask = S.default_mask(Hp, Wp)
-    eng = PropainterInpaint(torch.device("cuda", local), mdir)
-    for _ in range(max(args.warmup, 3)):
+    eng = make_propainter(B.device())
+    warm = max(args.warmup, 1)
+    for _ in range(warm):
         eng(frames, mask)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    B.barrier()
+    B.sync()
+    sampler = ClockSampler(B.local)
     if rank == 0:
         sampler.start()
     l0 = eng._rt.launch_count
     t0 = time.perf_counter()
     for _ in range(args.steps):
         eng(frames, mask)
-    torch.cuda.synchronize()
+    B.sync()
     e2e_s = time.perf_counter() - t0
     launches = eng._rt.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t[0].item())
+    e2e_s, = B.max_over_ranks([e2e_s])
+    stages = getattr(eng, "stage_seconds", None)
     cpu = None
     if rank == 0 and not args.no_cpu:
+        import torch
         from oracle import propainter_gen_oracle as G
         from oracle import raft_oracle as R
         from oracle import rfc_oracle as C
 
-        w = {"raft": R.load_weights(os.path.join(mdir, need[0])), "rfc": C.load_weights(os.path.join(mdir, need[1])), "gen": G.load_weights(os.path.join(mdir, need[2]))}
+        w = {"raft": R.load_weights(os.path.join(mdir, "raft-things.pth")), "rfc": C.load_weights(os.path.join(mdir, "recurrent_flow_completion.pth")),
+             "gen": G.load_weights(os.path.join(mdir, "ProPainter.pth"))}
         c0 = time.perf_counter()
         G.propainter_call(w, frames[:4], mask)
         cpu = {"value": 4 / (time.perf_counter() - c0), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -525,92 +671,58 @@ def run_propainter(args, rank, world, local):
         (y0, y1, x0, x1), = PT.strip_areas(Wp, Hp, mask)
         sh, sw = y1 - y0, x1 - x0
         n = world * args.steps * T
+        _, sustained, _, peak_src = peaks()
+        flop = 2.52e12 * T      # ~2.52 TFLOP per 720p frame (RAFT 1.35, generator 1.08, completion 0.10; measured at N = 12)
         print(json.dumps({
             "metric": "inpainted frames/sec at 720p (ProPainter)", "value": n / e2e_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": e2e_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": e2e_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic 720p clip; reference ProPainter / RAFT / flow-completion weights",
             "config": {"workload": f"ProPainter on a {T}-frame 720p synthetic clip with optical-flow completion (BASELINE config 3, one sub-video per call)",
                        "frame": [Hp, Wp], "frames_per_step": T, "strip": [sh, sw], "l2": "inputs larger than L2 (strip frames + feature maps)"},
             "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": T * sh * sw * 3 + sh * sw, "d2h_bytes_per_step": T * sh * sw * 3,
                     "api": "PropainterInpaint.__call__(frames, mask), synchronous, copy semantics"},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": None, "cpu_baseline": cpu,
-            "status": "bring-up line: no device-resident leg and no roofline yet (DESIGN.md §7)"}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+            "roofline": {"bound": "tensor", "kernel": "whole pipeline (RAFT + flow completion + propagation + generator), host-timed",
+                         "achieved": flop * args.steps / e2e_s / 1e12, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": flop * args.steps / e2e_s / 1e12 / sustained, "traffic": None, "peak_source": f"{peak_src} (sustained bf16)",
+                         "stage_seconds_last_call": stages},
+            "cpu_baseline": cpu}), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="sttn-auto", choices=["sttn-auto", "sttn-det", "dbnet", "lama", "config4", "propainter"],
-                    help="sttn-auto = BASELINE config 2 (the contract line); sttn-det / dbnet = the inpaint / detection halves of config 4; "
-                         "lama = the big-lama model of config 1 on 1080p strips")
-    ap.add_argument("--pp-frames", type=int, default=40, help="frames per call of the propainter workload (<= 80)")
-    args = ap.parse_args()
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (tools/ncu_summary.py writes it)."""
+    p = os.path.join(ROOT, "profiles", "ncu_r2_conv3x3.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_launch"]), os.path.relpath(p, ROOT)
+    except Exception:
+        return None, None
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
 
-    import torch
-    import torch.distributed as dist
-    from vsr_b200 import STTNInpaint, _capi
-    from vsr_b200 import synthetic as S
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: vsr_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    _capi.build_library()
-    if args.workload == "dbnet":
-        run_dbnet(args, rank, world, local)
-        return
-    if args.workload == "lama":
-        run_lama(args, rank, world, local)
-        return
-    if args.workload == "config4":
-        run_config4(args, rank, world, local)
-        return
-    if args.workload == "propainter":
-        run_propainter(args, rank, world, local)
-        return
-    if args.workload == "sttn-det":
-        return run_det(args, rank, world, local)
-    src, wdesc = weights_source()
-    eng = STTNInpaint(torch.device("cuda", local), src)
+# ------------------------------------------------------------------------------------------------ the contract line: sttn-auto
+def run_sttn_auto(args, rank, world):
+    B, S = BACKEND, synthetic()
+    eng, src, wdesc = make_sttn(B.device())
     frames = S.synthetic_clip(CHUNK, H, W, seed=rank)  # each rank its own chunk (weak scaling)
     mask = S.default_mask(H, W)
-    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=torch.device("cuda", local))
+    stream = B.stream(eng.cuda_stream)
     strip_bytes = CHUNK * int(W * 3 / 16) * W * 3
+    warm = max(args.warmup, 3)
 
     # ---- device-resident leg: strips staged once, K timed chunk passes ------------------------
     work = [f.copy() for f in frames]
     eng.stage(work, mask)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         eng.stage(work, mask)  # restore the original strips (compute composites in place)
         eng.compute()
     eng.sync()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(B.local)
     if rank == 0:
         sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(B.event(), B.event()) for _ in range(args.steps)]
     launches0 = eng.launch_count
-    barrier()
-    torch.cuda.synchronize()
+    B.barrier()
+    B.sync()
     for i in range(args.steps):
         eng.stage(work, mask)   # untimed: H2D of the strips (the timed region starts with inputs in HBM)
         eng.sync()
@@ -618,39 +730,36 @@ def main():
         eng.compute()
         evs[i][1].record(stream)
     eng.sync()
-    torch.cuda.synchronize()
-    barrier()
+    B.sync()
+    B.barrier()
     launches = eng.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    dev_ms, = B.max_over_ranks([dev_ms])
 
     # ---- end-to-end leg: host numpy frames in, host numpy frames out --------------------------
     # (a) the chunk loop of STTNAutoInpaint.__call__: two chunks in flight (submit / collect), every step
     #     still pays its own host->pinned copy, H2D, kernels, D2H and pinned->host copy
     for _ in range(2):
         eng.inpaint_inplace([f.copy() for f in frames], mask)
-    warm = [[f.copy() for f in frames] for _ in range(4)]  # warm both pipeline slots (pinned buffers, graph re-capture)
+    warm_batches = [[f.copy() for f in frames] for _ in range(4)]  # warm both pipeline slots (pinned buffers, graph re-capture)
     prev = None
-    for b in warm:
-        t = eng.submit(b, mask)
+    for b in warm_batches:
+        ticket = eng.submit(b, mask)
         if prev is not None:
             eng.collect(prev[0], prev[1])
-        prev = (t, b)
+        prev = (ticket, b)
     eng.collect(prev[0], prev[1])
-    del warm
+    del warm_batches
     batches = [[f.copy() for f in frames] for _ in range(args.steps)]
-    barrier()
-    torch.cuda.synchronize()
+    B.barrier()
+    B.sync()
     t0 = time.perf_counter()
     prev = None
     for b in batches:
-        t = eng.submit(b, mask)
+        ticket = eng.submit(b, mask)
         if prev is not None:
             eng.collect(prev[0], prev[1])
-        prev = (t, b)
+        prev = (ticket, b)
     eng.collect(prev[0], prev[1])
     e2e_s = time.perf_counter() - t0
     # (b) strictly synchronous calls, one chunk at a time
@@ -659,47 +768,52 @@ def main():
     for b in batches:
         eng.inpaint_inplace(b, mask)
     e2e_sync_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s, e2e_sync_s = float(t[0].item()), float(t[1].item())
+    e2e_s, e2e_sync_s = B.max_over_ranks([e2e_s, e2e_sync_s])
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel (3x3 conv 256->256 on a 15-frame window) --------------
+    # ---- roofline of the dominant kernel, in situ -----------------------------------------------
+    # One eager pass of the same chunk with events around every launch group (the second of two, so that nothing allocates).
+    eng.stage(work, mask)
+    eng.profile()
+    eng.stage(work, mask)
+    prof = eng.profile()
+    conv_ms = prof["conv3x3"][0] + prof["conv3x3_residual"][0]
+    conv_launches = prof["conv3x3"][1] + prof["conv3x3_residual"][1]
+    passes = sum(len(nb) + len(rf) for nb, rf in chunk_schedule(CHUNK))           # 140 frame-passes per 50-frame chunk
+    conv_flop = 3 * 8 * passes * 30 * 160 * 2.0 * 2304 * 256                       # 3 convs x 8 blocks, 2*9*256*256 FLOP per pixel
+    prof_total = sum(v[0] for v in prof.values())
     group = int(os.environ.get("VSR_WINDOW_GROUP", "2"))
     Tw = 29 if group >= 2 else 15  # frames per conv launch in the steady state (windows of 15 + 14 share a launch)
-    ms = eng.time_conv(Tw, 20)
-    conv_ms = float(np.median(ms))
-    conv_flop = 2.0 * Tw * 30 * 160 * 2304 * 256
+    iso_ms = float(np.median(eng.time_conv(Tw, 20)))
+    iso_flop = 2.0 * Tw * 30 * 160 * 2304 * 256
     burst, sustained, hbm, peak_src = peaks()
-    roof = {"bound": "tensor", "kernel": f"tcgen05 implicit-GEMM 3x3 conv 256->256, {Tw}x30x160 px ({'CTA-pair 256x256' if os.environ.get('VSR_CONV_2CTA', '1') != '0' else '128x256'} tiles)",
-            "achieved": conv_flop / (conv_ms * 1e-3) / 1e12, "peak": burst, "unit": "TFLOP/s",
-            "frac": conv_flop / (conv_ms * 1e-3) / 1e12 / burst, "traffic": None, "peak_source": f"{peak_src} (burst bf16)",
-            "ms_per_launch": conv_ms, "flop_per_launch": conv_flop,
+    traffic, traffic_src = ncu_traffic()
+    achieved = conv_flop / (conv_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor",
+            "kernel": "tcgen05 implicit-GEMM 3x3 conv 256->256 on 30x160 maps (transformer blocks: output_linear, feed_forward.conv.0/.2), "
+                      "as it runs in the chunk: CUDA events around each of its launches in one eager pass of the timed chunk",
+            "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{peak_src} (sustained bf16: kernel timed inside a long step)",
+            "launches": int(conv_launches), "ms_per_launch": conv_ms / max(conv_launches, 1), "flop_per_launch": conv_flop / max(conv_launches, 1),
+            "share_of_step": conv_ms / prof_total if prof_total else None,
+            "in_situ_ms": {k: round(v[0], 3) for k, v in prof.items()},
+            "isolated": {"what": f"same kernel, LeakyReLU epilogue only, {Tw} frames, 20 back-to-back launches on the same buffers (L2-warm)",
+                         "achieved": iso_flop / (iso_ms * 1e-3) / 1e12, "frac_of_burst": iso_flop / (iso_ms * 1e-3) / 1e12 / burst, "peak_burst": burst},
             "whole_step_frac_of_sustained": (FLOP_PER_FRAME * CHUNK * args.steps / (dev_ms * 1e-3)) / 1e12 / sustained}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
-    # ---- CPU port on a bounded sample (rank 0, N = 1 only) -------------------------------------
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ---------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        w = oracle_weights(src)
-        threads = best_cpu_threads(w, frames, mask)
-        fps, dt = cpu_port_fps(w, frames, mask, threads)
-        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": CPU_SAMPLE + f" ({dt:.1f} s of CPU work, torch {torch.__version__} CPU fp32, {threads} of {os.cpu_count()} "
-                         "threads: fastest of a sweep)"}
+        cpu = cpu_baseline_leg(src, frames, mask, args.cpu_frames)
 
     total_frames = world * args.steps * CHUNK
     line = {"metric": METRIC, "value": total_frames / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": f"synthetic 1080p clip (seeded, generated on host); {wdesc}",
-            "config": {"workload": "STTN sttn-auto 1080p synthetic clip, fixed subtitle bbox, neighbor_stride=5 (BASELINE config 2); "
-                                   "step = one 50-frame chunk",
-                       "frame": [H, W], "chunk": CHUNK, "neighbor_stride": 5, "ref_length": 10, "strip": [720, 1080, 0, 1920],
+            "config": {"workload": WORKLOAD, "frame": [H, W], "chunk": CHUNK, "neighbor_stride": 5, "ref_length": 10, "strip": [720, 1080, 0, 1920],
                        "l2": "per-step working set (104 MB strips + ~0.9 GB activations) exceeds the 126 MB L2",
                        "parallelism": f"chunk-per-rank x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": total_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": strip_bytes,
@@ -708,8 +822,44 @@ def main():
                     "sync_value": total_frames / e2e_sync_s, "sync_api": "STTNInpaint.inpaint_inplace(frames, mask), one chunk at a time"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+WORKLOADS = {"sttn-auto": run_sttn_auto, "sttn-det": run_det, "dbnet": run_dbnet, "lama": run_lama, "lama512": run_lama512, "config4": run_config4,
+             "propainter": run_propainter}
+
+
+def main(argv=None):
+    global BACKEND
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-frames", type=int, default=20, help="frames of the chunk the cpu_baseline leg runs through the reference (<= 50)")
+    ap.add_argument("--workload", default="sttn-auto", choices=sorted(WORKLOADS),
+                    help="sttn-auto = BASELINE config 2 (the contract line); sttn-det / dbnet = the inpaint / detection halves of config 4; "
+                         "config4 = that chain end to end (sharded over the ranks when N > 1); lama = the big-lama model of config 1 on 1080p "
+                         "strips; lama512 = config 1 itself; propainter = config 3")
+    ap.add_argument("--pp-frames", type=int, default=40, help="frames per call of the propainter workload (<= 80)")
+    args = ap.parse_args(argv)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if BACKEND is None:
+        BACKEND = CudaBackend()
+    if not BACKEND.available():
+        raise SystemExit("bench.py needs a B200: vsr_b200 has no CPU fallback")
+    BACKEND.setup(local, world)
+    try:
+        WORKLOADS[args.workload](args, rank, world)
+    finally:
+        BACKEND.finish()
 
 
 if __name__ == "__main__":

@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE — imports the UNMODIFIED reference from /root/reference (this container only).
+"""TEST INFRASTRUCTURE — imports the UNMODIFIED reference: from /root/reference in this container, from the byte-for-byte copy of its
+Python modules under oracle/_ref (oracle/build_ref.py; git-ignored, travels with the gpurun snapshot) on the GPU box.
 
-Used by tools/make_golden.py and by the `-m "not gpu"` oracle-pinning tests to validate the
-restatements in oracle/ and to (re)generate tests/golden/*.npz.  /root/reference does not exist on
-the GPU box, so nothing in the `-m gpu` tests, __graft_entry__.smoke() or bench.py imports this.
+Used by tools/make_golden*.py and by the `-m "not gpu"` oracle-pinning tests to validate the restatements in oracle/ and to (re)generate
+tests/golden/*.npz, and by bench.py's CPU legs (`--impl reference`, `cpu_baseline` kind "reference") to time the reference's own
+`STTNInpaint.__call__` on the host cores.  The `-m gpu` tests and __graft_entry__.smoke() never import this.
 
 Recipe follows SURVEY.md Appendix A.4: three stub modules (backend.config, matplotlib, fsplit) are
 inserted before anything from `backend` is imported; weights are always passed as explicit paths
@@ -13,7 +14,10 @@ import os
 import sys
 import types
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("VSR_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "backend", "inpaint")) and os.path.isdir(os.path.join(_HERE, "_ref", "backend", "inpaint")):
+    REF_ROOT = os.path.join(_HERE, "_ref")
 
 
 def available() -> bool:

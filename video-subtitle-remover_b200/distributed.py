@@ -92,6 +92,35 @@ def batches_for_rank(n_items: int, max_batch: int, rank: int, world: int) -> Lis
     return out
 
 
+def video_inpaint_frames_sharded(frames, detector, model, rank: int, world: int):
+    """BASELINE config 4 on `world` GPUs (the in-memory loop of SubtitleRemover.video_inpaint, main.py:260-333, like
+    pipeline.video_inpaint_frames): every rank detects its share of the sampled frames, ONE all_gather_object makes the hit dictionary
+    whole, every rank plans the same intervals and masks, and the `batch_generator` batches of all intervals are dealt round-robin —
+    a batch is an independent unit for sttn-det / LAMA (main.py:323-326).  Returns (output frames, frame dictionary, interval map): the
+    frames of this rank's batches are inpainted, all others are the inputs (each rank owns the output segments of its batches)."""
+    from .config import config
+    from .inpaint_tools import batch_generator, create_mask
+    from .pipeline import interval_boxes, plan_intervals
+
+    n = len(frames)
+    sub_list = detect_video_sharded(detector, frames, detector.SAMPLE_STEP, rank, world)
+    start_end = plan_intervals(sub_list, n)
+    size = frames[0].shape[:2]
+    out = list(frames)
+    k = 0
+    for s, e in sorted(start_end.items()):
+        mask = None
+        for batch in batch_generator(list(range(s - 1, e)), config.getSttnMaxLoadNum()):   # 0-based frame indices of the batch
+            if len(batch) < 1:
+                continue
+            if k % world == rank:
+                if mask is None:
+                    mask = create_mask(size, interval_boxes(sub_list, s, e))
+                out[batch[0]:batch[-1] + 1] = model([frames[i] for i in batch], mask)
+            k += 1
+    return out, sub_list, start_end
+
+
 # ---- ProPainter (BASELINE config 5): one sub-video over several GPUs -------------------------------------------------------------
 class Shard:
     """rank / world plus the one exchange the sharded ProPainter path needs (propainter_inpaint.PropainterInpaint.inpaint(shard=...)):

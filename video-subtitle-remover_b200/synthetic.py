@@ -26,3 +26,44 @@ def default_mask(H: int, W: int, area=(0.88, 0.99, 0.15, 0.85)) -> np.ndarray:
     from .inpaint_tools import create_mask
 
     return create_mask((H, W), [(int(W * area[2]), int(W * area[3]), int(H * area[0]), int(H * area[1]))])
+
+
+def sttn_weight_shapes():
+    """Tensor inventory of the sttn-auto / sttn-det generator checkpoint `ckpt['netG']` (auto_sttn.py:64-95,148-222; the two networks
+    differ in patch geometry, not in tensors)."""
+    shapes = {}
+
+    def conv(name, co, ci, k):
+        shapes[name + ".weight"] = (co, ci, k, k)
+        shapes[name + ".bias"] = (co,)
+
+    conv("encoder.0", 64, 3, 3)
+    conv("encoder.2", 64, 64, 3)
+    conv("encoder.4", 128, 64, 3)
+    conv("encoder.6", 256, 128, 3)
+    for b in range(8):
+        p = f"transformer.{b}."
+        conv(p + "attention.query_embedding", 256, 256, 1)
+        conv(p + "attention.value_embedding", 256, 256, 1)
+        conv(p + "attention.key_embedding", 256, 256, 1)
+        conv(p + "attention.output_linear.0", 256, 256, 3)
+        conv(p + "feed_forward.conv.0", 256, 256, 3)
+        conv(p + "feed_forward.conv.2", 256, 256, 3)
+    conv("decoder.0.conv", 128, 256, 3)
+    conv("decoder.2", 64, 128, 3)
+    conv("decoder.4.conv", 64, 64, 3)
+    conv("decoder.6", 3, 64, 3)
+    return shapes
+
+
+def random_sttn_weights(seed: int = 0):
+    """Seeded random-init weights of that architecture (BASELINE's "random-init weights of that architecture" when no checkpoint is
+    staged): gain 1/sqrt(fan_in), biases 0.05 sigma — decoded images use the full 0..255 range while features stay small."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in sttn_weight_shapes().items():
+        if name.endswith(".weight"):
+            out[name] = rng.standard_normal(shape, dtype=np.float32) * np.float32(1.0 / np.sqrt(shape[1] * shape[2] * shape[3]))
+        else:
+            out[name] = rng.standard_normal(shape, dtype=np.float32) * np.float32(0.05)
+    return out
