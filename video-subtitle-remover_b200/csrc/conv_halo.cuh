@@ -1,0 +1,166 @@
+// Haloed-tile implicit-GEMM convolution on CTA pairs (tcgen05 cta_group::2) for k x k stride-1 convs with Cout tiles of 256.
+//
+// Why: the per-tap kernel (conv_igemm.cuh, Conv2Policy) re-fetches the 128-pixel A box of its tile for every tap — 9 x 16 KB per
+// 64-channel chunk for a 3x3 conv — next to 9 x 16 KB of weights, 64 B per SM and cycle at the tensor peak (8192 FLOP/cycle/SM):
+// more than the ~43 B/cycle/SM the L2 delivers when every SM pulls (B300_MICROARCH.md: LTS cap ~6300 B/cycle chip-wide).  ncu showed
+// it (round 1: l1tex__m_xbar2l1tex_read_bytes 1.5 GB per launch for 72 MB of algorithmic operands, tensor pipe 45 %).
+//
+// Here the A operand of ALL taps of a 64-channel chunk is ONE haloed tile in shared memory:
+//   tile = 8 pixels wide x 16 rows (M = 128: UMMA row r = pixel (r / 8, r % 8)), halo h = dilation * (k / 2) <= 4;
+//   one 4-D TMA box {64 ch, 16 px, 16 + 2h rows, 1 frame} at (x0 - h, y0 - h) per chunk (out-of-range pixels zero-filled: the conv
+//   padding), written with SWIZZLE_128B at a row pitch of 16 pixel lines = 2048 B;
+//   the A descriptor of tap (dy, dx) starts at line (dy + h) * 16 + (dx + h): its 8-row groups (one tile row each) are 2048 B apart
+//   (SBO), and because 2048 is a multiple of the 1024-byte swizzle period every group sees the same swizzle phase, which the
+//   descriptor's base-offset field ((start >> 7) & 7) carries.  No data is moved or re-fetched between taps.
+// Operand traffic per 64-channel chunk and CTA drops from 9 x (16 + 16) KB to (36..40) + 9 x 16 KB: 36 B per SM and cycle at peak.
+//
+// Pipeline (per CTA; the leader = cluster rank 0 issues the MMAs of the pair, as in tc_gemm2.cuh):
+//   warp 0 : TMA producer — A ring (NA haloed tiles), B ring (NB stages of this CTA's 128 of the 256 weight rows x 64 K)
+//   warp 1 : MMA issuer (leader only): per chunk wait A, per tap wait B, 4 x tcgen05.mma (K = 16), commit B stage / A buffer
+//   warps 2..5 : epilogue (ConvPolicy<256>::epilogue), accumulators double-buffered in TMEM
+#pragma once
+#include "conv_igemm.cuh"
+
+namespace vsr {
+
+constexpr int HALO_NA = 2;                  // A ring depth
+constexpr int HALO_NB = 7;                  // B ring depth
+constexpr int HALO_A_BYTES = 16 * 24 * 128; // room for h <= 4: 24 haloed rows x 16 lines x 128 B
+constexpr int HALO_B_BYTES = 128 * 128;
+constexpr int HALO_SMEM = HALO_NA * HALO_A_BYTES + HALO_NB * HALO_B_BYTES + 1024;
+
+enum : uint32_t { ERR_HALO_PROD_A = 0x500, ERR_HALO_PROD_B = 0x600, ERR_HALO_MMA_A = 0x700, ERR_HALO_MMA_B = 0x800,
+                  ERR_HALO_MMA_T = 0x900, ERR_HALO_EPI = 0xA00 };
+
+// SWIZZLE_128B K-major descriptor with a start address that is 128-byte- but not 1024-byte-aligned
+__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t saddr, uint32_t sbo_bytes, int with_base_offset) {
+  uint64_t d = umma_desc_sw128(saddr, 16, sbo_bytes);
+  if (with_base_offset) d |= (uint64_t)((saddr >> 7) & 7u) << 49;   // base offset: phase of the start line inside the 8-line swizzle period
+  return d;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams prm) {
+  using Base = ConvPolicy<256>;
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t a_full[HALO_NA], a_empty[HALO_NA], b_full[HALO_NB], b_empty[HALO_NB], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA0 = smem_base, sB0 = smem_base + HALO_NA * HALO_A_BYTES;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < HALO_NA; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 1);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+    for (int s = 0; s < HALO_NB; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 8);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&prm.in_map);
+    tma_prefetch_desc(&prm.w_map_half);
+  }
+  if (warp == 1) tmem_alloc_2cta(smem_u32(&tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int ntiles = Conv2Policy::num_tiles(prm);
+  const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
+  const int halo = prm.halo;
+  const uint32_t a_bytes = (uint32_t)(16 * (16 + 2 * halo) * 128);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      for (int t = first; t < ntiles; t += step) {
+        const Base::Tile tile = Conv2Policy::get_tile(prm, t, rank);
+        for (int kc = 0; kc < prm.cin_chunks; ++kc) {
+          mbar_wait(smem_u32(&a_empty[as]), aph ^ 1, ERR_HALO_PROD_A | as);
+          if (rank == 0) mbar_expect_tx(smem_u32(&a_full[as]), 2u * a_bytes);
+          tma_load_4d_2sm(sA0 + as * HALO_A_BYTES, &prm.in_map, mapa_cluster(smem_u32(&a_full[as]), 0), kc * 64, tile.x0 - halo,
+                          tile.y0 - halo, tile.t);
+          if (++as == HALO_NA) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < prm.ntaps; ++tap) {
+            mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, ERR_HALO_PROD_B | bs);
+            if (rank == 0) mbar_expect_tx(smem_u32(&b_full[bs]), 2u * HALO_B_BYTES);
+            tma_load_2d_2sm(sB0 + bs * HALO_B_BYTES, &prm.w_map_half, mapa_cluster(smem_u32(&b_full[bs]), 0),
+                            (tap * prm.cin_chunks + kc) * 64, tile.n0 + (int)rank * 128);
+            if (++bs == HALO_NB) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
+      const uint32_t idesc = umma_idesc_f16(256, 256, 0, 0);
+      for (int t = first; t < ntiles; t += step) {
+        mbar_wait(smem_u32(&bar_tempty[acc]), accph ^ 1, ERR_HALO_MMA_T | acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kc = 0; kc < prm.cin_chunks; ++kc) {
+          mbar_wait(smem_u32(&a_full[as]), aph, ERR_HALO_MMA_A | as);
+          tc_fence_after();
+          const uint32_t sA = sA0 + as * HALO_A_BYTES;
+          for (int tap = 0; tap < prm.ntaps; ++tap) {
+            mbar_wait(smem_u32(&b_full[bs]), bph, ERR_HALO_MMA_B | bs);
+            tc_fence_after();
+            const uint32_t sB = sB0 + bs * HALO_B_BYTES;
+            const uint32_t a_tap = sA + (uint32_t)(((int)prm.tap_dy[tap] + halo) * 16 + ((int)prm.tap_dx[tap] + halo)) * 128u;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_2cta(d_tmem, umma_desc_sw128_off(a_tap + kk * 32, 2048, prm.halo_base_off), umma_desc_sw128(sB + kk * 32, 16, 1024), idesc,
+                            (kc | tap | kk) != 0);
+            umma_commit_2cta(smem_u32(&b_empty[bs]), 3);
+            if (++bs == HALO_NB) { bs = 0; bph ^= 1; }
+          }
+          umma_commit_2cta(smem_u32(&a_empty[as]), 3);
+          if (++as == HALO_NA) { as = 0; aph ^= 1; }
+        }
+        umma_commit_2cta(smem_u32(&bar_tfull[acc]), 3);
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t quarter = warp & 3;
+    const uint32_t row = quarter * 32 + lane;
+    uint32_t acc = 0, accph = 0;
+    for (int t = first; t < ntiles; t += step) {
+      const Base::Tile tile = Conv2Policy::get_tile(prm, t, rank);
+      mbar_wait(smem_u32(&bar_tfull[acc]), accph, ERR_HALO_EPI | acc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * 256;
+      Base::RowCtx ctx = Conv2Policy::row_begin(prm, tile, row);
+      for (int c = 0; c < 256; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        Base::epilogue(prm, tile, ctx, row, c, v, nullptr);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_tempty[acc]), 0));
+      if (++acc == 2) { acc = 0; accph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be signalling our barriers / reading our smem until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace vsr

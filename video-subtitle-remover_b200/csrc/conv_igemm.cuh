@@ -51,6 +51,9 @@ struct ConvParams {
   // the output tensor is the window [crop_t, crop_t + out_H) x [crop_l, crop_l + out_W) of the computed grid (a conv over a
   // reflect-padded input stores only the interior); out_H = H, out_W = W, crop 0 for plain convs
   int crop_t, crop_l, out_H, out_W;
+  // haloed-tile kernel (conv_halo.cuh): halo = max |tap offset|; in_map is then the box {64, 16, 16 + 2*halo, 1}, tile_w = 8 and
+  // tile_h = the rows of the 16-row tile that are stored (tiles advance by tile_h); base_off = 0 leaves the descriptor's base-offset 0
+  int halo, halo_base_off;
 };
 
 template <int BN_>

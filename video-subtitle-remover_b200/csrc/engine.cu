@@ -21,6 +21,7 @@
 #include "../../include/vsr_b200.h"
 #include "attention.cuh"
 #include "conv_igemm.cuh"
+#include "conv_halo.cuh"
 #include "elementwise.cuh"
 #include "host_index.h"
 #include "rt_ops.cuh"
@@ -154,6 +155,8 @@ struct Ctx {
   int64_t launches = 0;
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
+  bool conv_halo = false;  // haloed-tile kernel for k x k convs with 256-wide Cout tiles (conv_halo.cuh); VSR_CONV_HALO=0 switches it off
+  int conv_halo_base_off = 1;  // VSR_CONV_HALO_BASEOFF (descriptor base-offset field on / off: bring-up switch)
   bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
   bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
@@ -437,6 +440,40 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   if (!(io.flags & CONV_FINAL)) REQUIRE(L.cout % 8 == 0, "Cout must be a multiple of 8");
   if (io.out32) REQUIRE(L.cout == L.cout_pad, "fp32 stream needs Cout == padded Cout");
   const int ntiles = p.T * p.tiles_y * p.tiles_x * p.n_tiles;
+  if (L.bn == 256 && c.conv_2cta && c.conv_halo && !(io.flags & CONV_FINAL) && L.ntaps > 1 && io.W >= 8) {
+    int halo = 0;
+    for (int i = 0; i < L.ntaps; ++i) halo = std::max(halo, std::max(std::abs((int)L.dy[i]), std::abs((int)L.dx[i])));
+    if (halo <= 4) {
+      // tiles of 8 x 16 pixels; tiles advance by the fewest rows that cover H in ceil(H / 16) steps (30 rows -> 2 x 15)
+      const int tiles_y = (io.H + 15) / 16, valid_h = (io.H + tiles_y - 1) / tiles_y;
+      const uint64_t pitch = L.pitch ? L.pitch : L.cin;
+      const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)io.W, (uint64_t)io.H, (uint64_t)io.T};
+      const uint64_t str[3] = {pitch * 2, (uint64_t)io.W * pitch * 2, (uint64_t)io.H * io.W * pitch * 2};
+      const uint32_t box[4] = {64, 16, (uint32_t)(16 + 2 * halo), 1};
+      p.in_map = make_map_f16(io.in, 4, dims, str, box);
+      const uint64_t wd[2] = {(uint64_t)L.K, (uint64_t)L.cout_pad};
+      const uint64_t ws[1] = {(uint64_t)L.K * 2};
+      const uint32_t wb[2] = {64, 128};
+      p.w_map_half = make_map_f16(L.w.p, 2, wd, ws, wb);
+      p.tile_w = 8; p.tile_h = valid_h;
+      p.tiles_x = (io.W + 7) / 8;
+      p.tiles_y = tiles_y;
+      p.halo = halo;
+      p.halo_base_off = c.conv_halo_base_off;
+      static bool configured = false;
+      if (!configured) {
+        CK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM));
+        configured = true;
+      }
+      const int pair_tiles = ((p.T * p.tiles_y * p.tiles_x + 1) / 2) * p.n_tiles;
+      const int pairs = c.sms / 2;
+      const int grid = 2 * (pair_tiles < pairs ? pair_tiles : pairs);
+      conv_halo_kernel<<<grid, TC_THREADS, HALO_SMEM, c.stream>>>(p);
+      CK(cudaGetLastError());
+      ++c.launches;
+      return;
+    }
+  }
   if (L.bn == 256 && c.conv_2cta && !(io.flags & CONV_FINAL)) {
     const uint64_t dims[2] = {(uint64_t)L.K, (uint64_t)L.cout_pad};
     const uint64_t str[1] = {(uint64_t)L.K * 2};
@@ -1434,6 +1471,8 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
     h->use_graph = !env_flag("VSR_NO_GRAPH", false);
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
+    h->ctx.conv_halo = env_flag("VSR_CONV_HALO", true);
+    h->ctx.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", true) ? 1 : 0;
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     h->ctx.attn_lpt = env_flag("VSR_ATTN_LPT", true);
@@ -2741,6 +2780,8 @@ struct OpCtx {
     c.device = device;
     c.sms = prop.multiProcessorCount;
     c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
+    c.conv_halo = env_flag("VSR_CONV_HALO", true);
+    c.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", true) ? 1 : 0;
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     c.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     c.attn_lpt = env_flag("VSR_ATTN_LPT", true);
