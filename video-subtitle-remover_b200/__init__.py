@@ -6,6 +6,7 @@ Public surface (same names / call conventions as the reference back-ends):
     STTNAutoInpaint(device, model_path, video_path, ...)(...)     backend/inpaint/sttn_auto_inpaint.py:167
     STTNDetInpaint(device, model_path)(frames, mask)              backend/inpaint/sttn_det_inpaint.py:23
     LamaInpaint(device, model_path)(frames, mask) / .inpaint      backend/inpaint/lama_inpaint.py:11
+    PropainterInpaint(device, model_dir, sub_video_length)(frames, mask)   backend/inpaint/propainter_inpaint.py:138
     SubtitleDetect(video_path, sub_areas).detect_subtitle(img)    backend/tools/subtitle_detect.py:16
     create_mask / get_inpaint_area_by_mask / batch_generator      backend/tools/inpaint_tools.py
     InpaintMode                                                   backend/tools/constant.py:4
@@ -20,6 +21,7 @@ from .sttn_det_inpaint import STTNDetInpaint  # noqa: F401
 from .subtitle_detect import SubtitleDetect  # noqa: F401
 from .lama_inpaint import LamaInpaint  # noqa: F401
 from .pipeline import propainter_mode_frames, video_inpaint_frames  # noqa: F401
+from .propainter_inpaint import PropainterInpaint  # noqa: F401
 
-__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "LamaInpaint", "SubtitleDetect", "video_inpaint_frames", "propainter_mode_frames", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
+__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "LamaInpaint", "PropainterInpaint", "SubtitleDetect", "video_inpaint_frames", "propainter_mode_frames", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
            "batch_generator"]

@@ -1,9 +1,7 @@
 """ProPainter on the B200: drop-in for backend/inpaint/propainter_inpaint.py `PropainterInpaint`.
 
-STATUS — read this first: every stage is checked on the CPU against the oracle and the frames of the unmodified reference through
-the fp32 stand-in of the device runtime (tests/test_propainter_cpu.py reproduces `PropainterInpaint.inpaint`'s golden output), and
-all kernels compile for sm_100a, but the class has NOT run on a B200 yet (round 1's GPU budget was spent before it existed; DESIGN.md
-§7).  It is therefore not exported from the package's top level, and tests/test_gpu_raft.py is gated on VSR_RUN_UNVALIDATED=1.
+Validated on a B200 in round 2 (tests/test_gpu_raft.py: RAFT end-point error, image propagation, flow completion and the whole pipeline
+against the frames of the unmodified reference, >= 45 dB in the hole, bit-exact outside; profiles/gpu_session_r2_s1_summary.txt).
 
 Stages (one shared device runtime): read_mask (host, propainter_tools) -> RaftFlow (P3, raft_flow.py) -> FlowCompletion (P4,
 flow_completion.py) -> propagate_images (P5, flow_propagation.py) -> per window: Generator.encode_and_propagate + transform_and_decode
@@ -70,8 +68,22 @@ class PropainterInpaint:
         rt = self._rt
         for arena in (self._arena, self.fix_flow_complete._arena, self.model._arena):
             arena.tick()
+        import time
+
+        clock = {"t": time.perf_counter()}
+        self.stage_seconds = getattr(self, "stage_seconds", None) or {}
+
+        def lap(name):      # wall clock per stage (the stages end in a host read or an explicit sync): bench.py reports the last call's
+            rt.sync()
+            now = time.perf_counter()
+            self.stage_seconds[name] = self.stage_seconds.get(name, 0.0) + now - clock["t"]
+            clock["t"] = now
+
+        self.stage_seconds.clear()
         flow_masks, masks_dilated = PT.read_mask(mask, T)
+        lap("read_mask")
         gf, gb = self._flows(frames, shard)
+        lap("raft")
         self._arena.begin(("inpaint", T, H, W))
         up = lambda arr: (lambda p: (rt.upload_to(p, arr), p)[1])(self._arena.alloc(max(np.ascontiguousarray(arr).nbytes, 16)))   # noqa: E731
         ff_dev, fb_dev = up(np.ascontiguousarray(gf, np.float32)), up(np.ascontiguousarray(gb, np.float32))
@@ -85,6 +97,7 @@ class PropainterInpaint:
                 rt.copy_bytes(b + ks * fbytes, pb_dev + (s + ks) * fbytes, (ke - ks) * fbytes)
         else:
             pf_dev, pb_dev = self.fix_flow_complete.complete(ff_dev, fb_dev, fmask_dev, N, H, W)
+        lap("flow_completion")
         x = _Tensor(self._arena.alloc(T * sbytes), 3, H, W, 8, n=T)
         rt.frames(frames, x)
         sub_prop = min(100, self.sub_video_length)
@@ -95,6 +108,7 @@ class PropainterInpaint:
                 rt.copy_bytes(part.ptr + ks * sbytes, state.ptr + (s + ks) * sbytes, (ke - ks) * sbytes)
         else:
             state = propagate_images(rt, x, mask_dev, pf_dev, pb_dev, self._arena)
+        lap("image_propagation")
         comp: List = [None] * T
         binary = (masks_dilated[0] > 0).astype(np.uint8)[None, :, :, None]
         rgb = [np.ascontiguousarray(f[:, :, ::-1]) for f in frames]
@@ -113,6 +127,7 @@ class PropainterInpaint:
             preds = shard.exchange(preds)
             for wi, (nb, _) in enumerate(schedule):
                 PT.composite(comp, preds[wi], np.repeat(binary, len(nb), 0), rgb, nb)
+        lap("generator_and_composite")
         return [np.ascontiguousarray(c[:, :, ::-1]) for c in comp]
 
     def __call__(self, input_frames: List[np.ndarray], input_mask: np.ndarray, shard=None) -> List[np.ndarray]:
