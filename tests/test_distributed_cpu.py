@@ -191,3 +191,58 @@ def test_propainter_sub_video_sharded_over_two_ranks_equals_single_rank(tmp_path
     golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "propainter_real.npz"))["comp"]
     d = np.abs(a.astype(np.int32) - golden)
     assert d.max() <= 3 and (d > 0).mean() < 0.02
+
+
+# ---- BASELINE config 4 sharded: detection + batches of every interval over two ranks == the single-process loop --------------------
+class _SampledDetector(_FakeDetector):
+    SAMPLE_STEP = 3
+
+    def detect_subtitle(self, frame):
+        i = int(frame[0, 0, 0]) * 256 + int(frame[0, 0, 1])
+        return [(100, 400, 300, 330)] if 10 <= i < 130 else []
+
+    def scan_frames(self, frames, sections=None, on_frame=None):
+        return detect_video_sharded(self, frames, self.SAMPLE_STEP, 0, 1)
+
+
+def _mark_model(batch, mask):
+    """stand-in for STTNDetInpaint: output = input + 1 where the mask is set (pure function of its batch)"""
+    import numpy as np
+
+    return [np.where(mask[:, :, None] > 0, f + 1, f).astype(np.uint8) for f in batch]
+
+
+def _config4_worker(rank, world, port, n):
+    import numpy as np
+    from vsr_b200.distributed import video_inpaint_frames_sharded
+    from vsr_b200.pipeline import video_inpaint_frames
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        frames = []
+        for i in range(n):
+            f = np.full((360, 640, 3), 7, np.uint8)
+            f[0, 0, 0], f[0, 0, 1] = i // 256, i % 256
+            frames.append(f)
+        det = _SampledDetector()
+        out, sub, se = video_inpaint_frames_sharded(frames, det, _mark_model, rank, world)
+        want, wsub, wse = video_inpaint_frames(frames, det, _mark_model)
+        assert sub == wsub and se == wse and len(se) >= 1 and len(out) == len(want) == n
+        changed = torch.tensor([int(not np.array_equal(o, f)) for o, f in zip(out, frames)])
+        equal_where_changed = all(np.array_equal(o, w) for o, w, c in zip(out, want, changed) if c)
+        assert equal_where_changed                                     # this rank's batches carry the single-process result
+        total = changed.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)                   # test-only collective: every inpainted frame done by exactly one rank
+        expect = torch.tensor([int(not np.array_equal(w, f)) for w, f in zip(want, frames)])
+        assert torch.equal(total, expect) and int(changed.sum()) > 0 and int(changed.sum()) < int(expect.sum())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_config4_sharded_two_processes_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_config4_worker, args=(2, port, 140), nprocs=2, join=True)

@@ -196,3 +196,21 @@ def test_golden_real_weights(capi):
         # a 48-row strip that is 40 % hole is ill-conditioned: rounding ONLY the conv kernels to fp16 in the fp32 oracle already
         # moves it to 44.3 dB / max 8 (the 70x100 image: 57.4 dB / max 1) — measured on the CPU, DESIGN.md §1.2
         _check(o[y0:y1], r[y0:y1], f[y0:y1], mask[y0:y1], 38.0, 16)
+
+
+def test_config1_vs_reference_golden(capi):
+    """BASELINE config 1: `LamaInpaint.inpaint` on the 512x512 synthetic image (texture seed 0, hole rows 400-470, cols 60-450) and
+    on frame 0 of the reference's test/test.mp4 with test/test.png, against the unmodified reference on the CPU (tools/make_golden_configs.py).
+    Bar: >= 45 dB and |diff| <= 10 inside the hole, bit-exact outside."""
+    path = os.path.join(ROOT, "weights", "big-lama", "big-lama.npz")
+    if not os.path.exists(path):
+        pytest.skip("big-lama weights not staged under weights/big-lama")
+    from vsr_b200.lama_inpaint import LamaInpaint
+
+    eng = LamaInpaint("cuda:0", path)
+    z = np.load(os.path.join(GOLDEN, "config1_lama.npz"))
+    img = O.synthetic_clip(1, 512, 512, seed=0)[0]
+    m = np.zeros((512, 512), np.uint8)
+    m[400:470, 60:450] = 255
+    _check(eng.inpaint(img, m), z["out512"], img, m, 45.0, 10)
+    _check(eng.inpaint(z["test_frame0"], z["test_mask"]), z["test_out"], z["test_frame0"], z["test_mask"], 45.0, 10)

@@ -177,6 +177,30 @@ def test_edge_cases(rand_engine):
         eng(frames, np.zeros((H + 1, W), np.uint8))
 
 
+def test_config2_whole_chunk_vs_reference_golden(real_engine):
+    """BASELINE config 2 at full size: one whole 50-frame 1920x1080 chunk (the chunk bench.py times: synthetic_clip seed 0, default-bbox
+    mask) against the unmodified reference's `STTNInpaint.__call__` on the CPU (tools/make_golden_configs.py): six stored frames pixel by
+    pixel inside the mask's bounding box, all 50 frames through their strip sums, rows outside the strip bit-exact."""
+    eng, _ = real_engine
+    z = np.load(os.path.join(GOLDEN, "config2_sttn_auto_1080p.npz"))
+    H, W, T = int(z["H"]), int(z["W"]), int(z["T"])
+    frames = O.synthetic_clip(T, H, W, seed=int(z["seed"]))
+    mask = O.default_mask(H, W)
+    out = eng(frames, mask)
+    y0, y1, x0, x1 = (int(v) for v in z["box"])
+    got = [out[int(i)][y0:y1, x0:x1] for i in z["frames"]]
+    _check_images(got, list(z["out_box"]))
+    psnr = O.psnr_u8(np.stack(got).astype(np.float32), z["out_box"].astype(np.float32))
+    print(f"config 2 chunk: PSNR {psnr:.2f} dB, max |diff| {np.abs(np.stack(got).astype(np.int32) - z['out_box']).max()}")
+    for o, f in zip(out, frames):
+        assert np.array_equal(o[:720], f[:720])
+        m = mask[720:] > 127
+        assert np.array_equal(o[720:][~m], f[720:][~m])
+    sums = np.array([int(o[720:].astype(np.int64).sum()) for o in out])
+    npx = int((mask > 127).sum()) * 3
+    assert np.abs(sums - z["strip_sums"]).max() / npx < 0.05            # mean error per masked sample of every frame: < 0.05 grey levels
+
+
 def test_full_size_properties_1080p(real_engine):
     """BASELINE config 2 at full size (one 50-frame chunk): size-independent properties."""
     eng, _ = real_engine

@@ -83,3 +83,25 @@ def test_det_vs_reference_golden_real_weights(capi):
     _check(got, list(z["comps"]))
     out = eng(frames, mask)
     _check([o[y0:y1] for o in out], list(z["strip_out_plain"]))
+
+
+def test_config4_whole_batch_vs_reference_golden(capi):
+    """BASELINE config 4 (inpaint half) at full size: one 46-frame 1080p `batch_generator` batch through the unmodified reference's
+    `STTNDetInpaint.__call__` on the CPU (tools/make_golden_configs.py): three stored frames (every second row / column of the 533-row
+    strip) pixel by pixel, all 46 through their strip sums."""
+    p = os.path.join(ROOT, "weights", "sttn-det", "sttn.pth")
+    if not os.path.exists(p):
+        pytest.skip("sttn-det checkpoint not staged under weights/")
+    from vsr_b200 import STTNDetInpaint
+
+    eng = STTNDetInpaint("cuda:0", p)
+    z = np.load(os.path.join(GOLDEN, "config4_sttn_det_1080p.npz"))
+    H, W, T = int(z["H"]), int(z["W"]), int(z["T"])
+    frames = O.synthetic_clip(T, H, W, seed=int(z["seed"]))
+    out = eng(frames, O.default_mask(H, W))
+    y0, y1 = (int(v) for v in z["rows"])
+    _check([out[int(i)][y0:y1:2, ::2] for i in z["frames"]], list(z["out_half"]))
+    for o, f in zip(out, frames):
+        assert np.array_equal(o[:y0], f[:y0]) and np.array_equal(o[y1:], f[y1:])
+    sums = np.array([int(o[y0:y1].astype(np.int64).sum()) for o in out])
+    assert np.abs(sums - z["strip_sums"]).max() / ((y1 - y0) * W * 3) < 0.05

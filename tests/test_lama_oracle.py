@@ -10,6 +10,7 @@ import torch
 
 from conftest import GOLDEN, ROOT
 from oracle import lama_oracle as L
+from oracle import sttn_oracle as O
 
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 PT = os.path.join(ROOT, "weights", "big-lama", "big-lama.pt")
@@ -51,3 +52,16 @@ def test_golden_reference_outputs():
     out = L.lama_call(w, frames, mask)
     assert np.array_equal(np.stack(out), z["call"])
     assert not np.array_equal(np.stack(out), np.stack(frames))
+
+
+@needs_weights
+def test_config1_golden_reference_outputs():
+    """BASELINE config 1 (tests/golden/config1_lama.npz, tools/make_golden_configs.py): the oracle equals the unmodified reference's
+    `LamaInpaint.inpaint` on the 512x512 synthetic image and on frame 0 of test/test.mp4 + test/test.png, byte for byte."""
+    w = L.load_weights(PT)
+    z = np.load(os.path.join(GOLDEN, "config1_lama.npz"))
+    assert np.array_equal(L.inpaint(w, z["test_frame0"], z["test_mask"]), z["test_out"])
+    img = O.synthetic_clip(1, 512, 512, seed=0)[0]
+    m = np.zeros((512, 512), np.uint8)
+    m[400:470, 60:450] = 255
+    assert np.array_equal(L.inpaint(w, img, m), z["out512"])

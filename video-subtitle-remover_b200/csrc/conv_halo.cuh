@@ -39,16 +39,38 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t saddr, uint32_t
   return d;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams prm) {
+// TMA load of a 2-D box into the same smem offset of every CTA in `cta_mask` (multicast through L2); with cta_group::2 the completion
+// of each destination CTA is signalled on the barrier at `bar`'s offset in that CTA or in its pair peer, exactly as the issuing CTA
+// addresses it (here: always the pair's even CTA, the MMA leader).
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(m), "r"(cluster_bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
+// CL = 2: one CTA pair per cluster.  CL = 4: two pairs per cluster work on neighbouring pixel tiles of the same Cout tile and share the
+// weights: every CTA fetches a quarter of the 256 x 64 weight chunk (64 rows) and multicasts it to the CTA of the other pair that
+// needs the same half, so the L2 -> SM weight traffic per CTA halves (16 -> 8 KB per chunk and tap).
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams prm) {
+  static_assert(CL == 2 || CL == 4, "cluster of one or two CTA pairs");
   using Base = ConvPolicy<256>;
   constexpr uint32_t TMEM_COLS = 512;
+  constexpr int NPAIR = CL / 2;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[HALO_NA], a_empty[HALO_NA], b_full[HALO_NB], b_empty[HALO_NB], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;          // rank inside the pair (0 = MMA leader)
+  const uint32_t pair = crank >> 1;         // pair inside the cluster
+  const uint32_t leader = crank & ~1u;      // cluster rank of this pair's leader
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+  const uint16_t all_mask = (uint16_t)((1u << CL) - 1);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base, sB0 = smem_base + HALO_NA * HALO_A_BYTES;
 
@@ -59,7 +81,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     }
     for (int s = 0; s < HALO_NB; ++s) {
       mbar_init(smem_u32(&b_full[s]), 1);
-      mbar_init(smem_u32(&b_empty[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), NPAIR);   // a stage is free when every pair that receives the multicast has consumed it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
@@ -67,34 +89,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     }
     fence_barrier_init();
     tma_prefetch_desc(&prm.in_map);
-    tma_prefetch_desc(&prm.w_map_half);
+    tma_prefetch_desc(CL == 4 ? &prm.w_map_quarter : &prm.w_map_half);
   }
   if (warp == 1) tmem_alloc_2cta(smem_u32(&tmem_slot), TMEM_COLS);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const int ntiles = Conv2Policy::num_tiles(prm);
+  // work list: groups of NPAIR neighbouring pair-tiles x Cout tiles; cluster c takes groups c, c + nclusters, ...
+  const int sub_tiles = prm.T * prm.tiles_y * prm.tiles_x;
+  const int pair_tiles_m = (sub_tiles + 1) >> 1;
+  const int ngroups = ((pair_tiles_m + NPAIR - 1) / NPAIR) * prm.n_tiles;
   const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
   const int halo = prm.halo;
   const uint32_t a_bytes = (uint32_t)(16 * (16 + 2 * halo) * 128);
+  auto tile_of = [&](int g) {   // this CTA's 128-pixel tile of group g (a dummy beyond the end: TMA zero-fills frame index T)
+    Base::Tile t;
+    const int n = g % prm.n_tiles;
+    int sub = ((g / prm.n_tiles) * NPAIR + (int)pair) * 2 + (int)rank;
+    t.n0 = n * 256;
+    t.num_k = prm.ntaps * prm.cin_chunks;
+    t.n_cols = 256;
+    if (sub >= sub_tiles) {
+      t.t = prm.T; t.y0 = 0; t.x0 = 0;
+      return t;
+    }
+    t.x0 = (sub % prm.tiles_x) * prm.tile_w;
+    sub /= prm.tiles_x;
+    t.y0 = (sub % prm.tiles_y) * prm.tile_h;
+    t.t = sub / prm.tiles_y;
+    return t;
+  };
 
   if (warp == 0) {
     if (elect_one()) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-      for (int t = first; t < ntiles; t += step) {
-        const Base::Tile tile = Conv2Policy::get_tile(prm, t, rank);
+      for (int g = first; g < ngroups; g += step) {
+        const Base::Tile tile = tile_of(g);
         for (int kc = 0; kc < prm.cin_chunks; ++kc) {
           mbar_wait(smem_u32(&a_empty[as]), aph ^ 1, ERR_HALO_PROD_A | as);
           if (rank == 0) mbar_expect_tx(smem_u32(&a_full[as]), 2u * a_bytes);
-          tma_load_4d_2sm(sA0 + as * HALO_A_BYTES, &prm.in_map, mapa_cluster(smem_u32(&a_full[as]), 0), kc * 64, tile.x0 - halo,
+          tma_load_4d_2sm(sA0 + as * HALO_A_BYTES, &prm.in_map, mapa_cluster(smem_u32(&a_full[as]), leader), kc * 64, tile.x0 - halo,
                           tile.y0 - halo, tile.t);
           if (++as == HALO_NA) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < prm.ntaps; ++tap) {
             mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, ERR_HALO_PROD_B | bs);
             if (rank == 0) mbar_expect_tx(smem_u32(&b_full[bs]), 2u * HALO_B_BYTES);
-            tma_load_2d_2sm(sB0 + bs * HALO_B_BYTES, &prm.w_map_half, mapa_cluster(smem_u32(&b_full[bs]), 0),
-                            (tap * prm.cin_chunks + kc) * 64, tile.n0 + (int)rank * 128);
+            const uint32_t full = mapa_cluster(smem_u32(&b_full[bs]), leader);
+            const int k0 = (tap * prm.cin_chunks + kc) * 64;
+            if (CL == 4) {   // rows [pair * 64, +64) of this CTA's half, to the CTAs of both pairs with the same in-pair rank
+              tma_load_2d_2sm_mc(sB0 + bs * HALO_B_BYTES + pair * (HALO_B_BYTES / 2), &prm.w_map_quarter, full, k0,
+                                 tile.n0 + (int)rank * 128 + (int)pair * 64, (uint16_t)(5u << rank));
+            } else {
+              tma_load_2d_2sm(sB0 + bs * HALO_B_BYTES, &prm.w_map_half, full, k0, tile.n0 + (int)rank * 128);
+            }
             if (++bs == HALO_NB) { bs = 0; bph ^= 1; }
           }
         }
@@ -105,7 +153,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     if (rank == 0 && elect_one()) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
       const uint32_t idesc = umma_idesc_f16(256, 256, 0, 0);
-      for (int t = first; t < ntiles; t += step) {
+      for (int g = first; g < ngroups; g += step) {
         mbar_wait(smem_u32(&bar_tempty[acc]), accph ^ 1, ERR_HALO_MMA_T | acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -122,13 +170,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
             for (int kk = 0; kk < 4; ++kk)
               umma_f16_2cta(d_tmem, umma_desc_sw128_off(a_tap + kk * 32, 2048, prm.halo_base_off), umma_desc_sw128(sB + kk * 32, 16, 1024), idesc,
                             (kc | tap | kk) != 0);
-            umma_commit_2cta(smem_u32(&b_empty[bs]), 3);
+            umma_commit_2cta(smem_u32(&b_empty[bs]), all_mask);
             if (++bs == HALO_NB) { bs = 0; bph ^= 1; }
           }
-          umma_commit_2cta(smem_u32(&a_empty[as]), 3);
+          umma_commit_2cta(smem_u32(&a_empty[as]), pair_mask);
           if (++as == HALO_NA) { as = 0; aph ^= 1; }
         }
-        umma_commit_2cta(smem_u32(&bar_tfull[acc]), 3);
+        umma_commit_2cta(smem_u32(&bar_tfull[acc]), pair_mask);
         if (++acc == 2) { acc = 0; accph ^= 1; }
       }
     }
@@ -137,8 +185,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
     const uint32_t quarter = warp & 3;
     const uint32_t row = quarter * 32 + lane;
     uint32_t acc = 0, accph = 0;
-    for (int t = first; t < ntiles; t += step) {
-      const Base::Tile tile = Conv2Policy::get_tile(prm, t, rank);
+    for (int g = first; g < ngroups; g += step) {
+      const Base::Tile tile = tile_of(g);
       mbar_wait(smem_u32(&bar_tfull[acc]), accph, ERR_HALO_EPI | acc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * 256;
@@ -150,13 +198,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_tempty[acc]), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_tempty[acc]), leader));
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
   }
 
   tc_fence_before();
-  cluster_sync_all();  // the peer may still be signalling our barriers / reading our smem until here
+  cluster_sync_all();  // the peers may still be signalling our barriers / writing our smem until here
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, TMEM_COLS);

@@ -24,6 +24,7 @@ struct ConvParams {
   CUtensorMap in_map;  // 4-D {C, W, H, T} fp16, box {64, tile_w, tile_h, 1}, SWIZZLE_128B
   CUtensorMap w_map;   // 2-D {K_total, Cout_pad} fp16, box {64, BN}, SWIZZLE_128B
   CUtensorMap w_map_half;  // same tensor, box {64, 128}: the half of B each CTA of a pair loads (Conv2Policy)
+  CUtensorMap w_map_quarter;  // box {64, 64}: what each CTA of a 4-CTA cluster loads and multicasts (conv_halo.cuh, CL = 4)
   int T, H, W;         // output (= input) spatial size
   int tile_w, tile_h, tiles_x, tiles_y;
   int n_tiles;         // Cout_pad / BN

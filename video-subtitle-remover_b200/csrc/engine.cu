@@ -156,6 +156,7 @@ struct Ctx {
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
   bool conv_halo = false;  // haloed-tile kernel for k x k convs with 256-wide Cout tiles (conv_halo.cuh); VSR_CONV_HALO=0 switches it off
+  int conv_cluster = 2;    // VSR_CONV_CLUSTER=4: two CTA pairs per cluster share the weights by TMA multicast (conv_halo.cuh)
   int conv_halo_base_off = 1;  // VSR_CONV_HALO_BASEOFF (descriptor base-offset field on / off: bring-up switch)
   bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
@@ -461,14 +462,36 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
       p.halo = halo;
       p.halo_base_off = c.conv_halo_base_off;
       static bool configured = false;
+      static int max_clusters4 = 0;
       if (!configured) {
-        CK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM));
+        CK(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM));
+        CK(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM));
+        // how many 4-CTA clusters the device holds at once (GPCs with an odd number of TPCs leave SMs without a cluster)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(4 * (c.sms / 4)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = HALO_SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters4, conv_halo_kernel<4>, &cfg) != cudaSuccess || max_clusters4 <= 0) {
+          cudaGetLastError();
+          max_clusters4 = c.sms / 4;
+        }
+        if (getenv("VSR_DEBUG_CLUSTERS")) fprintf(stderr, "[vsr] conv_halo: %d clusters of 4 fit on %d SMs\n", max_clusters4, c.sms);
         configured = true;
       }
-      const int pair_tiles = ((p.T * p.tiles_y * p.tiles_x + 1) / 2) * p.n_tiles;
-      const int pairs = c.sms / 2;
-      const int grid = 2 * (pair_tiles < pairs ? pair_tiles : pairs);
-      conv_halo_kernel<<<grid, TC_THREADS, HALO_SMEM, c.stream>>>(p);
+      const int pair_tiles_m = (p.T * p.tiles_y * p.tiles_x + 1) / 2;
+      if (c.conv_cluster == 4) {
+        const uint32_t qb[2] = {64, 64};
+        p.w_map_quarter = make_map_f16(L.w.p, 2, wd, ws, qb);
+        const int groups = ((pair_tiles_m + 1) / 2) * p.n_tiles;
+        const int grid = 4 * std::min(groups, max_clusters4);
+        conv_halo_kernel<4><<<grid, TC_THREADS, HALO_SMEM, c.stream>>>(p);
+      } else {
+        const int groups = pair_tiles_m * p.n_tiles;
+        const int grid = 2 * std::min(groups, c.sms / 2);
+        conv_halo_kernel<2><<<grid, TC_THREADS, HALO_SMEM, c.stream>>>(p);
+      }
       CK(cudaGetLastError());
       ++c.launches;
       return;
@@ -1473,6 +1496,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     h->ctx.conv_halo = env_flag("VSR_CONV_HALO", true);
     h->ctx.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", true) ? 1 : 0;
+    h->ctx.conv_cluster = getenv("VSR_CONV_CLUSTER") && atoi(getenv("VSR_CONV_CLUSTER")) == 4 ? 4 : 2;
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     h->ctx.attn_lpt = env_flag("VSR_ATTN_LPT", true);
@@ -2782,6 +2806,7 @@ struct OpCtx {
     c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     c.conv_halo = env_flag("VSR_CONV_HALO", true);
     c.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", true) ? 1 : 0;
+    c.conv_cluster = getenv("VSR_CONV_CLUSTER") && atoi(getenv("VSR_CONV_CLUSTER")) == 4 ? 4 : 2;
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     c.attn_fused = env_flag("VSR_ATTN_FUSED", false);
     c.attn_lpt = env_flag("VSR_ATTN_LPT", true);
