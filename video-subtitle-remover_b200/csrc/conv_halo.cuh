@@ -24,10 +24,18 @@
 namespace vsr {
 
 constexpr int HALO_NA = 2;                  // A ring depth
-constexpr int HALO_NB = 7;                  // B ring depth
-constexpr int HALO_A_BYTES = 16 * 24 * 128; // room for h <= 4: 24 haloed rows x 16 lines x 128 B
+constexpr int HALO_NB = 7;                  // B ring depth (at most; ConvParams::halo_nb stages are used)
 constexpr int HALO_B_BYTES = 128 * 128;
-constexpr int HALO_SMEM = HALO_NA * HALO_A_BYTES + HALO_NB * HALO_B_BYTES + 1024;
+constexpr int HALO_EPI_WARPS = 8;           // two per TMEM lane quarter, 128 columns each
+constexpr int HALO_THREADS = 64 + 32 * HALO_EPI_WARPS;
+constexpr int HALO_SCRATCH = HALO_EPI_WARPS * 4096;   // static: the epilogue's transposition scratch (conv_store_coalesced)
+__host__ __device__ constexpr int halo_a_bytes(int halo) { return 16 * (16 + 2 * halo) * 128; }   // haloed rows x 16 lines x 128 B
+// B stages that fit beside the two A buffers, the scratch and the barriers in 227 KB
+inline int halo_b_stages(int halo) {
+  const int room = 232448 - HALO_SCRATCH - 512 - 1024 - HALO_NA * halo_a_bytes(halo);
+  return room / HALO_B_BYTES < HALO_NB ? room / HALO_B_BYTES : HALO_NB;
+}
+inline int halo_smem_bytes(int halo) { return HALO_NA * halo_a_bytes(halo) + halo_b_stages(halo) * HALO_B_BYTES + 1024; }
 
 enum : uint32_t { ERR_HALO_PROD_A = 0x500, ERR_HALO_PROD_B = 0x600, ERR_HALO_MMA_A = 0x700, ERR_HALO_MMA_B = 0x800,
                   ERR_HALO_MMA_T = 0x900, ERR_HALO_EPI = 0xA00 };
@@ -54,7 +62,7 @@ __device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const CUtensorM
 // weights: every CTA fetches a quarter of the 256 x 64 weight chunk (64 rows) and multicasts it to the CTA of the other pair that
 // needs the same half, so the L2 -> SM weight traffic per CTA halves (16 -> 8 KB per chunk and tap).
 template <int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams prm) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams prm) {
   static_assert(CL == 2 || CL == 4, "cluster of one or two CTA pairs");
   using Base = ConvPolicy<256>;
   constexpr uint32_t TMEM_COLS = 512;
@@ -62,6 +70,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[HALO_NA], a_empty[HALO_NA], b_full[HALO_NB], b_empty[HALO_NB], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float epi_scratch[HALO_SCRATCH / 4];
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -72,7 +81,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
   const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
   const uint16_t all_mask = (uint16_t)((1u << CL) - 1);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA0 = smem_base, sB0 = smem_base + HALO_NA * HALO_A_BYTES;
+  const int halo = prm.halo;
+  const uint32_t a_bytes = (uint32_t)halo_a_bytes(halo);
+  const uint32_t NB = (uint32_t)prm.halo_nb;
+  const uint32_t sA0 = smem_base, sB0 = smem_base + HALO_NA * a_bytes;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < HALO_NA; ++s) {
@@ -85,7 +97,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
-      mbar_init(smem_u32(&bar_tempty[s]), 8);
+      mbar_init(smem_u32(&bar_tempty[s]), 2 * HALO_EPI_WARPS);
     }
     fence_barrier_init();
     tma_prefetch_desc(&prm.in_map);
@@ -101,8 +113,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
   const int pair_tiles_m = (sub_tiles + 1) >> 1;
   const int ngroups = ((pair_tiles_m + NPAIR - 1) / NPAIR) * prm.n_tiles;
   const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
-  const int halo = prm.halo;
-  const uint32_t a_bytes = (uint32_t)(16 * (16 + 2 * halo) * 128);
   auto tile_of = [&](int g) {   // this CTA's 128-pixel tile of group g (a dummy beyond the end: TMA zero-fills frame index T)
     Base::Tile t;
     const int n = g % prm.n_tiles;
@@ -129,7 +139,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
         for (int kc = 0; kc < prm.cin_chunks; ++kc) {
           mbar_wait(smem_u32(&a_empty[as]), aph ^ 1, ERR_HALO_PROD_A | as);
           if (rank == 0) mbar_expect_tx(smem_u32(&a_full[as]), 2u * a_bytes);
-          tma_load_4d_2sm(sA0 + as * HALO_A_BYTES, &prm.in_map, mapa_cluster(smem_u32(&a_full[as]), leader), kc * 64, tile.x0 - halo,
+          tma_load_4d_2sm(sA0 + as * a_bytes, &prm.in_map, mapa_cluster(smem_u32(&a_full[as]), leader), kc * 64, tile.x0 - halo,
                           tile.y0 - halo, tile.t);
           if (++as == HALO_NA) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < prm.ntaps; ++tap) {
@@ -143,7 +153,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
             } else {
               tma_load_2d_2sm(sB0 + bs * HALO_B_BYTES, &prm.w_map_half, full, k0, tile.n0 + (int)rank * 128);
             }
-            if (++bs == HALO_NB) { bs = 0; bph ^= 1; }
+            if (++bs == NB) { bs = 0; bph ^= 1; }
           }
         }
       }
@@ -160,7 +170,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
         for (int kc = 0; kc < prm.cin_chunks; ++kc) {
           mbar_wait(smem_u32(&a_full[as]), aph, ERR_HALO_MMA_A | as);
           tc_fence_after();
-          const uint32_t sA = sA0 + as * HALO_A_BYTES;
+          const uint32_t sA = sA0 + as * a_bytes;
           for (int tap = 0; tap < prm.ntaps; ++tap) {
             mbar_wait(smem_u32(&b_full[bs]), bph, ERR_HALO_MMA_B | bs);
             tc_fence_after();
@@ -171,7 +181,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
               umma_f16_2cta(d_tmem, umma_desc_sw128_off(a_tap + kk * 32, 2048, prm.halo_base_off), umma_desc_sw128(sB + kk * 32, 16, 1024), idesc,
                             (kc | tap | kk) != 0);
             umma_commit_2cta(smem_u32(&b_empty[bs]), all_mask);
-            if (++bs == HALO_NB) { bs = 0; bph ^= 1; }
+            if (++bs == NB) { bs = 0; bph ^= 1; }
           }
           umma_commit_2cta(smem_u32(&a_empty[as]), pair_mask);
           if (++as == HALO_NA) { as = 0; aph ^= 1; }
@@ -183,18 +193,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1) conv
     __syncwarp();
   } else {
     const uint32_t quarter = warp & 3;
+    const uint32_t ew = warp - 2;
     const uint32_t row = quarter * 32 + lane;
+    float* scr = epi_scratch + ew * 1024;
+    const int c_begin = (int)(ew >> 2) * 128;
     uint32_t acc = 0, accph = 0;
     for (int g = first; g < ngroups; g += step) {
       const Base::Tile tile = tile_of(g);
+      Base::RowCtx ctx = Conv2Policy::row_begin(prm, tile, row);
       mbar_wait(smem_u32(&bar_tfull[acc]), accph, ERR_HALO_EPI | acc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * 256;
-      Base::RowCtx ctx = Conv2Policy::row_begin(prm, tile, row);
-      for (int c = 0; c < 256; c += 32) {
+      for (int c = c_begin; c < c_begin + 128; c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
-        Base::epilogue(prm, tile, ctx, row, c, v, nullptr);
+        Base::epilogue(prm, tile, ctx, row, c, v, scr);
       }
       tc_fence_before();
       __syncwarp();

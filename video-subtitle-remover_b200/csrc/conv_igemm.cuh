@@ -54,8 +54,53 @@ struct ConvParams {
   int crop_t, crop_l, out_H, out_W;
   // haloed-tile kernel (conv_halo.cuh): halo = max |tap offset|; in_map is then the box {64, 16, 16 + 2*halo, 1}, tile_w = 8 and
   // tile_h = the rows of the 16-row tile that are stored (tiles advance by tile_h); base_off = 0 leaves the descriptor's base-offset 0
-  int halo, halo_base_off;
+  int halo, halo_base_off, halo_nb;
 };
+
+// 32 accumulator columns [ch0, ch0 + 32) of the 32 pixel rows of one epilogue warp (row = lane), after bias / activation:
+// optional fp32 residual add, fp32 store, fp16 store — every global access issued "transposed" (lane = 4 rows x 8 sixteen-byte
+// chunks), data exchanged through the warp's 4 KB scratch with a 16-byte-chunk XOR swizzle (conflict-free both ways).
+// pixv = output pixel index of this lane's row, or -1 when the row stores nothing.
+__device__ __forceinline__ void conv_store_coalesced(const ConvParams& p, int pixv, int ch0, float* v, float* scr) {
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 7, rsub = lane >> 3;
+  float4* s4 = reinterpret_cast<float4*>(scr);
+  const bool live = ch0 + 4 * q < p.cout;   // Cout padded up to the tile width: only the real channels are touched
+  if ((p.flags & CONV_RESIDUAL) && p.out32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rr = 4 * j + rsub;
+      const int pv = __shfl_sync(0xffffffffu, pixv, rr);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pv >= 0 && live) a = *reinterpret_cast<const float4*>(p.res32 + (size_t)pv * p.cout + ch0 + 4 * q);
+      s4[rr * 8 + (q ^ (rr & 7))] = a;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 a = s4[lane * 8 + (i ^ (lane & 7))];
+      v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += a.z; v[4 * i + 3] += a.w;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s4[lane * 8 + (i ^ (lane & 7))] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int rr = 4 * j + rsub;
+    const int pv = __shfl_sync(0xffffffffu, pixv, rr);
+    const float4 a = s4[rr * 8 + (q ^ (rr & 7))];
+    if (pv >= 0 && live) {
+      if (p.out32) *reinterpret_cast<float4*>(p.out32 + (size_t)pv * p.cout + ch0 + 4 * q) = a;
+      if (p.out16) {
+        __align__(8) __half2 h[2] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w)};
+        *reinterpret_cast<uint2*>(p.out16 + (size_t)pv * p.out16_pitch + p.out16_coff + ch0 + 4 * q) = *reinterpret_cast<const uint2*>(h);
+      }
+    }
+  }
+  __syncwarp();
+}
 
 template <int BN_>
 struct ConvPolicy {
@@ -126,8 +171,12 @@ struct ConvPolicy {
     return c;
   }
   __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}
-  __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float*) {
-    if (!c.valid) return;
+  // `scr`: 4 KB of shared memory per epilogue warp, or nullptr.  With it, the fp32 residual read and the fp32 / fp16 stores go through a
+  // 32 x 32 transposition so that every warp-wide memory instruction covers whole 128-byte lines (4 pixel rows x 128 B) instead of
+  // 16 bytes of 32 different lines: the row-per-thread form costs 32 L1TEX wavefronts per instruction, which made the residual
+  // epilogue (20 such instructions per 32 columns) as long as the tile's MMAs (ncu, profiles/ncu_r2a_conv_halo.md: tensor pipe 48 %).
+  __device__ static void epilogue(const Params& p, const Tile& t, RowCtx& c, int row, int col0, float* v, float* scr) {
+    if (scr == nullptr && !c.valid) return;
     constexpr int NV = (BN >= 32) ? 32 : 16;
     const int ch0 = t.n0 + col0;
     if (p.flags & CONV_SCALED) {
@@ -158,10 +207,10 @@ struct ConvPolicy {
       bool bad = false;
 #pragma unroll
       for (int i = 0; i < NV; ++i) bad |= !(fabsf(v[i]) <= 65504.f);
-      if (bad) *p.overflow = 1;
+      if (bad && c.valid) *p.overflow = 1;
     }
     if (p.flags & CONV_FINAL) {
-      if (col0 != 0) return;
+      if (col0 != 0 || !c.valid) return;
       const int f = p.frame_idx[c.t];
       float* dst = p.comps + (((size_t)f * p.H + c.y) * p.W + c.x) * 3;
       const bool first = p.first_visit[c.t] != 0;
@@ -183,6 +232,11 @@ struct ConvPolicy {
       }
       return;
     }
+    if (scr != nullptr && !(p.flags & CONV_S2D_STORE)) {
+      conv_store_coalesced(p, c.valid ? (int)c.pix : -1, ch0, v, scr);
+      return;
+    }
+    if (!c.valid) return;
     if (p.out32) {
       float* o = p.out32 + c.pix * p.cout + ch0;
       if (p.flags & CONV_RESIDUAL) {
@@ -220,7 +274,8 @@ struct ConvPolicy {
 struct Conv2Policy {
   static constexpr int STAGES = 6;
   static constexpr int PROF_ID = 1;
-  static constexpr bool EPI_SCRATCH = false;
+  static constexpr bool EPI_SCRATCH = true;
+  static constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes half of the 256 columns
   static constexpr int B_MN_MAJOR = 0;
   using Base = ConvPolicy<256>;
   using Params = ConvParams;

@@ -157,7 +157,8 @@ struct Ctx {
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
   bool conv_halo = false;  // haloed-tile kernel for k x k convs with 256-wide Cout tiles (conv_halo.cuh); VSR_CONV_HALO=0 switches it off
   int conv_cluster = 2;    // VSR_CONV_CLUSTER=4: two CTA pairs per cluster share the weights by TMA multicast (conv_halo.cuh)
-  int conv_halo_base_off = 1;  // VSR_CONV_HALO_BASEOFF (descriptor base-offset field on / off: bring-up switch)
+  int conv_halo_base_off = 0;  // the descriptor's base-offset field stays 0: the tensor core swizzles on absolute smem address bits
+                               // (measured, profiles/gpu_session_r2_s2_summary.txt: with the field set three conv cases fail)
   bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
   bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
@@ -216,7 +217,7 @@ static void launch_tc2(Ctx& c, const typename P::Params& prm, int ntiles) {
   if (ntiles <= 0) return;
   const int pairs = c.sms / 2;
   const int grid = 2 * (ntiles < pairs ? ntiles : pairs);
-  tc_gemm2_kernel<P><<<grid, TC_THREADS, smem, c.stream>>>(prm);
+  tc_gemm2_kernel<P><<<grid, tc2_threads<P>(), smem, c.stream>>>(prm);
   CK(cudaGetLastError());
   ++c.launches;
 }
@@ -461,36 +462,39 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
       p.tiles_y = tiles_y;
       p.halo = halo;
       p.halo_base_off = c.conv_halo_base_off;
-      static bool configured = false;
-      static int max_clusters4 = 0;
-      if (!configured) {
-        CK(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM));
-        CK(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM));
-        // how many 4-CTA clusters the device holds at once (GPCs with an odd number of TPCs leave SMs without a cluster)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(4 * (c.sms / 4)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = HALO_SMEM;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        if (cudaOccupancyMaxActiveClusters(&max_clusters4, conv_halo_kernel<4>, &cfg) != cudaSuccess || max_clusters4 <= 0) {
-          cudaGetLastError();
-          max_clusters4 = c.sms / 4;
-        }
-        if (getenv("VSR_DEBUG_CLUSTERS")) fprintf(stderr, "[vsr] conv_halo: %d clusters of 4 fit on %d SMs\n", max_clusters4, c.sms);
-        configured = true;
+      p.halo_nb = halo_b_stages(halo);
+      const int smem = halo_smem_bytes(halo);
+      static int configured_smem = 0, max_clusters4 = 0;
+      if (smem > configured_smem) {
+        CK(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_smem = smem;
       }
       const int pair_tiles_m = (p.T * p.tiles_y * p.tiles_x + 1) / 2;
       if (c.conv_cluster == 4) {
+        if (max_clusters4 == 0) {
+          // how many 4-CTA clusters the device holds at once (GPCs with an odd number of TPCs leave SMs without a cluster)
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(4 * (c.sms / 4)); cfg.blockDim = dim3(HALO_THREADS); cfg.dynamicSmemBytes = (size_t)smem;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          if (cudaOccupancyMaxActiveClusters(&max_clusters4, conv_halo_kernel<4>, &cfg) != cudaSuccess || max_clusters4 <= 0) {
+            cudaGetLastError();
+            max_clusters4 = c.sms / 4;
+          }
+          if (getenv("VSR_DEBUG_CLUSTERS")) fprintf(stderr, "[vsr] conv_halo: %d clusters of 4 fit on %d SMs\n", max_clusters4, c.sms);
+        }
         const uint32_t qb[2] = {64, 64};
         p.w_map_quarter = make_map_f16(L.w.p, 2, wd, ws, qb);
         const int groups = ((pair_tiles_m + 1) / 2) * p.n_tiles;
         const int grid = 4 * std::min(groups, max_clusters4);
-        conv_halo_kernel<4><<<grid, TC_THREADS, HALO_SMEM, c.stream>>>(p);
+        conv_halo_kernel<4><<<grid, HALO_THREADS, smem, c.stream>>>(p);
       } else {
         const int groups = pair_tiles_m * p.n_tiles;
         const int grid = 2 * std::min(groups, c.sms / 2);
-        conv_halo_kernel<2><<<grid, TC_THREADS, HALO_SMEM, c.stream>>>(p);
+        conv_halo_kernel<2><<<grid, HALO_THREADS, smem, c.stream>>>(p);
       }
       CK(cudaGetLastError());
       ++c.launches;
@@ -1495,7 +1499,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->use_graph = !env_flag("VSR_NO_GRAPH", false);
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     h->ctx.conv_halo = env_flag("VSR_CONV_HALO", true);
-    h->ctx.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", true) ? 1 : 0;
+    h->ctx.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", false) ? 1 : 0;
     h->ctx.conv_cluster = getenv("VSR_CONV_CLUSTER") && atoi(getenv("VSR_CONV_CLUSTER")) == 4 ? 4 : 2;
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", false);
@@ -2805,7 +2809,7 @@ struct OpCtx {
     c.sms = prop.multiProcessorCount;
     c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     c.conv_halo = env_flag("VSR_CONV_HALO", true);
-    c.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", true) ? 1 : 0;
+    c.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", false) ? 1 : 0;
     c.conv_cluster = getenv("VSR_CONV_CLUSTER") && atoi(getenv("VSR_CONV_CLUSTER")) == 4 ? 4 : 2;
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     c.attn_fused = env_flag("VSR_ATTN_FUSED", false);

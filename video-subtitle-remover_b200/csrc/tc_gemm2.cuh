@@ -18,9 +18,21 @@ constexpr int tc2_smem_bytes() {
   return P::STAGES * (2 * TC_A_BYTES) + 1024;
 }
 
+// Epilogue warps per CTA: 4 (one per TMEM lane quarter) unless the policy asks for 8 (`EPI_WARPS = 8`: two warps per quarter, each
+// taking half of the tile's columns — for policies whose column groups are independent and whose epilogue, not the MMA, is the
+// longer of the two per tile: short-K GEMMs such as the 1x1 Q/K/V projection).
+template <class P, class = void>
+struct tc_epi_warps { static constexpr int value = 4; };
 template <class P>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+struct tc_epi_warps<P, decltype((void)P::EPI_WARPS)> { static constexpr int value = P::EPI_WARPS; };
+template <class P>
+constexpr int tc2_threads() { return 64 + 32 * tc_epi_warps<P>::value; }
+
+template <class P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2_threads<P>(), 1)
     tc_gemm2_kernel(const __grid_constant__ typename P::Params prm) {
+  constexpr int EW = tc_epi_warps<P>::value;
+  static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
   constexpr int BN = 256;
   constexpr int STAGES = P::STAGES;
   constexpr uint32_t STAGE_BYTES = 2 * TC_A_BYTES;  // A: 128 rows, B: this CTA's 128 of the 256 rows
@@ -30,7 +42,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
   // per-epilogue-warp 32x33 fp32 transpose scratch (policies that store row-scattered data coalesce through it)
-  __shared__ float epi_scratch[P::EPI_SCRATCH ? 4 * 32 * 33 : 1];
+  __shared__ __align__(16) float epi_scratch[P::EPI_SCRATCH ? EW * 32 * 33 : 4];
 
   const long long t_kernel0 = TC_PROF_NOW();
   (void)t_kernel0;
@@ -46,7 +58,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
-      mbar_init(smem_u32(&bar_tempty[s]), 8);
+      mbar_init(smem_u32(&bar_tempty[s]), 2 * EW);
     }
     fence_barrier_init();
     P::prefetch(prm);
@@ -119,6 +131,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     __syncwarp();
   } else {
     const uint32_t quarter = warp & 3;
+    const uint32_t ew = warp - 2;             // epilogue warp 0 .. EW-1
     const uint32_t row = quarter * 32 + lane;
     uint32_t as = 0, aphase = 0;
     TC_PROF_DECL(w_tfull);
@@ -133,10 +146,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       (void)e0;
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + as * BN;
       typename P::RowCtx ctx = P::row_begin(prm, tile, row);
-      for (int c = 0; c < tile.n_cols; c += 32) {
+      const int c_begin = (EW == 8) ? (int)(ew >> 2) * (tile.n_cols >> 1) : 0;
+      const int c_end = (EW == 8) ? c_begin + (tile.n_cols >> 1) : tile.n_cols;
+      for (int c = c_begin; c < c_end; c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
-        P::epilogue(prm, tile, ctx, row, c, v, epi_scratch + (P::EPI_SCRATCH ? quarter * 32 * 33 : 0));
+        P::epilogue(prm, tile, ctx, row, c, v, P::EPI_SCRATCH ? epi_scratch + ew * 32 * 33 : nullptr);
       }
       P::row_end(prm, tile, ctx, row);
       tc_fence_before();
