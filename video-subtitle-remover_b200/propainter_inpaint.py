@@ -82,13 +82,18 @@ class PropainterInpaint:
         self.stage_seconds.clear()
         flow_masks, masks_dilated = PT.read_mask(mask, T)
         lap("read_mask")
-        gf, gb = self._flows(frames, shard)
-        lap("raft")
+        N, fbytes, sbytes = T - 1, 2 * H * W * 4, H * W * 8 * 2         # flows, bytes of one flow field / of one frame of the state tensor
         self._arena.begin(("inpaint", T, H, W))
         up = lambda arr: (lambda p: (rt.upload_to(p, arr), p)[1])(self._arena.alloc(max(np.ascontiguousarray(arr).nbytes, 16)))   # noqa: E731
-        ff_dev, fb_dev = up(np.ascontiguousarray(gf, np.float32)), up(np.ascontiguousarray(gb, np.float32))
+        if shard is None:                                                   # RAFT's flows go straight into the completion network's input
+            ff_dev, fb_dev = self._arena.alloc(N * fbytes), self._arena.alloc(N * fbytes)
+            for a, b in flow_clips(T, W, self.raft_clip):                   # clip (a, b) holds the pairs a .. b-2 (clips overlap by one frame)
+                self.fix_raft(frames[a:b], self.raft_iter, dst=(ff_dev + a * fbytes, fb_dev + a * fbytes))
+        else:                                                               # sharded: the clips' flows are exchanged between the ranks
+            gf, gb = self._flows(frames, shard)
+            ff_dev, fb_dev = up(np.ascontiguousarray(gf, np.float32)), up(np.ascontiguousarray(gb, np.float32))
+        lap("raft")
         fmask_dev, mask_dev = up(flow_masks[0]), up(masks_dilated[0])
-        N, fbytes, sbytes = T - 1, 2 * H * W * 4, H * W * 8 * 2         # flows, bytes of one flow field / of one frame of the state tensor
         if N > self.sub_video_length:                                       # :251-276: overlapped chunks (pad 5), the middle of each kept
             pf_dev, pb_dev = self._arena.alloc(N * fbytes), self._arena.alloc(N * fbytes)
             for s, e, ks, ke in PT.sub_ranges(N, self.sub_video_length, 5):

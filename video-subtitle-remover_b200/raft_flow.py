@@ -271,8 +271,10 @@ class RaftFlow:
         prog.N, prog.h, prog.w, prog.hw = N, h, wd, hw
         return prog
 
-    def __call__(self, frames_bgr: Sequence[np.ndarray], iters: int = ITERS) -> Tuple[np.ndarray, np.ndarray]:
-        """-> (forward flows t -> t+1, backward flows t+1 -> t), each float32 [T-1, 2, H, W] (x, y components)."""
+    def __call__(self, frames_bgr: Sequence[np.ndarray], iters: int = ITERS, dst=None):
+        """-> (forward flows t -> t+1, backward flows t+1 -> t), each float32 [T-1, 2, H, W] (x, y components).
+        With `dst = (device pointer forward, device pointer backward)` the flows stay on the device: they are copied there (fp32
+        [T-1,2,H,W] each) on the runtime's stream and nothing is downloaded (the caller hands them to the flow-completion network)."""
         frames = [np.ascontiguousarray(f, np.uint8) for f in frames_bgr]
         T = len(frames)
         if T < 2:
@@ -305,7 +307,11 @@ class RaftFlow:
                     rt.graph_launch(st.graph)
             for s in st.tail:
                 s()
-            out.append(rt.download_f32(st.out32, (prog.N, 2, H, W)))
+            if dst is None:
+                out.append(rt.download_f32(st.out32, (prog.N, 2, H, W)))
+            else:
+                rt.copy_bytes(st.out32, dst[len(out)], prog.N * 2 * H * W * 4)
+                out.append(None)
         if rt.overflow():
             raise _capi.VsrError("RAFT activations left the fp16 range")
         return out[0], out[1]
