@@ -689,6 +689,57 @@ def run_propainter(args, rank, world):
             "cpu_baseline": cpu}), flush=True)
 
 
+def run_sttn_strong(args, rank, world):
+    """Single-clip strong scaling: ONE 300-frame 1080p clip (BASELINE config 2's clip), chunk by chunk, every chunk's windows
+    dealt over all `world` GPUs (`STTNInpaint.inpaint_chunk_sharded`: NCCL all-gather of the reference-frame encoder features and of the
+    window predictions, blend replayed in schedule order — output bit-identical to one GPU).  Host frames in, result strips in host memory
+    on the rank that owns each frame; wall clock, max over ranks."""
+    B, S = BACKEND, synthetic()
+    eng, src, wdesc = make_sttn(B.device())
+    n_chunks = 6
+    frames = S.synthetic_clip(CHUNK, H, W, seed=0)      # the same clip on every rank: the job is sharded, not replicated
+    mask = S.default_mask(H, W)
+    warm = max(min(args.warmup, 3), 1)
+    for _ in range(warm):
+        eng.inpaint_chunk_sharded([f.copy() for f in frames], mask, rank, world)
+    vals = []
+    for _ in range(args.steps):
+        clips = [[f.copy() for f in frames] for _ in range(n_chunks)]
+        l0 = eng.launch_count
+        B.barrier()
+        B.sync()
+        t0 = time.perf_counter()
+        for c in clips:
+            eng.inpaint_chunk_sharded(c, mask, rank, world)
+        B.sync()
+        B.barrier()
+        vals.append(time.perf_counter() - t0)
+        launches = eng.launch_count - l0
+    e2e_s, = B.max_over_ranks([float(np.sum(vals))])
+    if rank == 0:
+        n = args.steps * n_chunks * CHUNK
+        sh = int(W * 3 / 16)
+        _, sustained, _, peak_src = peaks()
+        fpix = 30 * 160 * 256
+        print(json.dumps({
+            "metric": METRIC, "value": n / e2e_s, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": e2e_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+            "data": f"synthetic 1080p clip (seeded, generated on host); {wdesc}",
+            "config": {"workload": "ONE 300-frame 1080p clip (6 chunks of 50), every chunk's 10 windows dealt over the ranks, reference-frame "
+                                   "features and window predictions all-gathered over NVLink (single-clip latency, BASELINE config 2's clip)",
+                       "frame": [H, W], "chunk": CHUNK, "frames_per_step": n_chunks * CHUNK, "neighbor_stride": 5, "ref_length": 10,
+                       "parallelism": f"window-per-rank x{world}",
+                       "collective_bytes_per_chunk": {"reference_features": 5 * fpix * 6, "window_predictions": 10 * 32 * 120 * 640 * 3 * 4}},
+            "e2e": {"value": n / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": n_chunks * CHUNK * sh * W * 3,
+                    "d2h_bytes_per_step": n_chunks * ((CHUNK + world - 1) // world) * sh * W * 3,
+                    "api": "STTNInpaint.inpaint_chunk_sharded(frames, mask, rank, world) per chunk, synchronous (every rank uploads the chunk's strips)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "whole clip, all ranks (eager launches, no CUDA graph in the sharded path)",
+                         "achieved": FLOP_PER_FRAME * n / e2e_s / 1e12, "peak": sustained * world, "unit": "TFLOP/s",
+                         "frac": FLOP_PER_FRAME * n / e2e_s / 1e12 / (sustained * world), "traffic": None, "peak_source": f"{peak_src} (sustained bf16 x ranks)"}}),
+            flush=True)
+
+
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (tools/ncu_summary.py writes it)."""
     p = os.path.join(ROOT, "profiles", "ncu_r2_conv3x3.json")
@@ -824,7 +875,7 @@ def run_sttn_auto(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-WORKLOADS = {"sttn-auto": run_sttn_auto, "sttn-det": run_det, "dbnet": run_dbnet, "lama": run_lama, "lama512": run_lama512, "config4": run_config4,
+WORKLOADS = {"sttn-auto": run_sttn_auto, "sttn-auto-strong": run_sttn_strong, "sttn-det": run_det, "dbnet": run_dbnet, "lama": run_lama, "lama512": run_lama512, "config4": run_config4,
              "propainter": run_propainter}
 
 

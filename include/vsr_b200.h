@@ -89,6 +89,21 @@ int vsr_sttn_sync(vsr_sttn_t* h);
  * and may only change while nothing is in flight. */
 int64_t vsr_sttn_submit(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask);
 int vsr_sttn_collect(vsr_sttn_t* h, int64_t ticket, uint8_t* const* frames_out);
+/* Window-level sharding of ONE chunk over `world` GPUs (single-clip strong scaling).  The windows of the chunk's schedule
+ * (sttn_auto_inpaint.py:142-146) are dealt round-robin (window w on rank w % world).  Call order on every rank, same arguments:
+ *   shard_begin   stages the strips, encodes the frames this rank's windows decode plus the reference frames it is the home of, and packs
+ *                 those references' encoder features into its region of the reference exchange buffer `*ref_buf`
+ *   -> all-gather (in place) of `*ref_buf`: world regions of `*ref_region_bytes` bytes, region r written by rank r — the features of the
+ *      reference frames are the only data a window needs from outside its neighbourhood (get_ref_index, :107-120)
+ *   shard_windows runs this rank's windows, each into its own slot of the prediction exchange buffer `*pred_buf`
+ *   -> all-gather (in place) of `*pred_buf` (world regions of `*pred_region_bytes` bytes)
+ *   shard_finish  replays the ordered 0.5 / 0.5 blend (:159-162) on all predictions (bit-identical to the unsharded chunk), composites,
+ *                 and writes the frames f with f %% world == rank to frames_out[f] (other entries are not touched).
+ * The buffers are device memory owned by the engine; the collectives are the caller's (torch.distributed / NCCL on the raw pointers). */
+int vsr_sttn_shard_begin(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask, int rank, int world,
+                         void** ref_buf, int64_t* ref_region_bytes, void** pred_buf, int64_t* pred_region_bytes);
+int vsr_sttn_shard_windows(vsr_sttn_t* h);
+int vsr_sttn_shard_finish(vsr_sttn_t* h, uint8_t* const* frames_out);
 /* CUDA stream of the engine (cudaStream_t as void*) so callers can bracket it with events. */
 void* vsr_sttn_stream(vsr_sttn_t* h);
 /* kernels launched by this engine since creation (bench.py `gpu_launches`) */

@@ -144,6 +144,60 @@ def test_graph_replay_across_batch_lengths(capi, monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(got, want[i])), f"job {i} differs from the eager path"
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_window_sharded_chunk_equals_single_engine(capi, world):
+    """One chunk with its windows dealt over `world` ranks (vsr_sttn_shard_*): every rank is its own engine (here: threads on one GPU, the two
+    all-gathers done by device-to-device copies between the engines' exchange buffers); the frames each rank hands back equal the
+    unsharded call bit for bit — reference-frame features exchanged, window predictions exchanged, blend replayed in schedule order."""
+    import threading
+
+    import torch
+    from vsr_b200 import STTNInpaint
+    from vsr_b200.sttn_auto_inpaint import _DevicePointer
+
+    w = {k: v.numpy() for k, v in O.random_weights(0).items()}
+    H, W, T = 270, 480, 23
+    frames = O.synthetic_clip(T, H, W, seed=77)
+    mask = O.default_mask(H, W)
+    want = STTNInpaint("cuda:0", w)(frames, mask)
+    engines = [STTNInpaint("cuda:0", w) for _ in range(world)]
+    outs = [[f.copy() for f in frames] for _ in range(world)]
+    barrier, ptrs, errors = threading.Barrier(world), {}, []
+
+    def gather_for(rank):
+        def gather(ptr, nbytes):
+            ptrs[rank] = ptr
+            barrier.wait()
+            mine = torch.as_tensor(_DevicePointer(ptr, nbytes * world), device="cuda:0")
+            for r in range(world):
+                if r != rank:
+                    mine[r * nbytes:(r + 1) * nbytes].copy_(torch.as_tensor(_DevicePointer(ptrs[r], nbytes * world), device="cuda:0")[r * nbytes:(r + 1) * nbytes])
+            torch.cuda.synchronize()
+            barrier.wait()
+        return gather
+
+    def work(rank):
+        try:
+            got = engines[rank].inpaint_chunk_sharded(outs[rank], mask, rank, world, all_gather=gather_for(rank))
+            assert got == list(range(rank, T, world))
+        except BaseException as e:      # noqa: BLE001
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for rank in range(world):
+        for f in range(T):
+            if f % world == rank:
+                assert np.array_equal(outs[rank][f], want[f]), f"rank {rank} frame {f}"
+            else:
+                assert np.array_equal(outs[rank][f], frames[f])
+
+
 def test_overlapping_strips_inplace(rand_engine):
     """Two subtitle bands closer than a strip height give overlapping strips; the reference crops every strip from the untouched
     frames (sttn_auto_inpaint.py:66-73), also when the result is written into the input frames themselves."""

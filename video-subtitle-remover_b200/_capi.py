@@ -67,6 +67,9 @@ _PROTOS = {
     "vsr_sttn_fetch": (C.c_int, [C.c_void_p, _pp]),
     "vsr_sttn_submit": (C.c_int64, [C.c_void_p, _pp, C.c_int, C.c_int, C.c_int, _u8p]),
     "vsr_sttn_collect": (C.c_int, [C.c_void_p, C.c_int64, _pp]),
+    "vsr_sttn_shard_begin": (C.c_int, [C.c_void_p, _pp, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _pp, _i64p, _pp, _i64p]),
+    "vsr_sttn_shard_windows": (C.c_int, [C.c_void_p]),
+    "vsr_sttn_shard_finish": (C.c_int, [C.c_void_p, _pp]),
     "vsr_sttn_sync": (C.c_int, [C.c_void_p]),
     "vsr_sttn_stream": (C.c_void_p, [C.c_void_p]),
     "vsr_sttn_launch_count": (C.c_int64, [C.c_void_p]),

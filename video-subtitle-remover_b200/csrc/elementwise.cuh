@@ -155,6 +155,22 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restric
   *reinterpret_cast<uint4*>(out + (((size_t)t * 2 * h + oy) * 2 * w + ox) * C + c8 * 8) = *reinterpret_cast<const uint4*>(o);
 }
 
+// Sharded windows (vsr_sttn_shard_*): every window was decoded into its own slot `preds[slot][local frame]` (quantised, unblended);
+// this replays the running 0.5 / 0.5 blend of sttn_auto_inpaint.py:159-162 per frame in schedule order — the same two multiplies
+// and one add per visit as the CONV_FINAL epilogue, so the result is bit-identical to the single-GPU chunk.
+// visit_tab[f * 4] = number of visits (<= 3), visit_tab[f * 4 + 1 + k] = slot * 32 + local frame index of visit k.
+__global__ void __launch_bounds__(256) blend_preds_kernel(float* __restrict__ comps, const float* __restrict__ preds,
+                                                          const int* __restrict__ visit_tab, size_t frame_elems) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (e >= frame_elems) return;
+  const int n = visit_tab[f * 4];
+  if (n <= 0) return;
+  float c = preds[(size_t)visit_tab[f * 4 + 1] * frame_elems + e];
+  for (int k = 1; k < n; ++k) c = c * 0.5f + preds[(size_t)visit_tab[f * 4 + 1 + k] * frame_elems + e] * 0.5f;
+  comps[(size_t)f * frame_elems + e] = c;
+}
+
 // A3 tail (sttn_auto_inpaint.py:86-91 / 312-315): comp = cv2.resize(comp, (W, split_h)) [u8 fixed-point
 // path when the frame was decoded once, float path otherwise] -> astype(uint8) -> RGB->BGR ->
 // strip = mask ? comp : strip.  comps [T, ch, cw, 3] fp32 RGB; strips [T, sh, sw, 3] u8 BGR in place.

@@ -824,6 +824,16 @@ struct vsr_sttn {
   } slot[2];
   cudaStream_t copy_stream = nullptr;
   int64_t next_ticket = 0;
+  // window-level sharding of one chunk over several GPUs (vsr_sttn_shard_*)
+  struct ShardJob {
+    int rank = 0, world = 1, T = 0;
+    int ref_slots = 0, win_slots = 0;         // exchange slots per rank
+    std::vector<int> ref_frames;              // reference frames of the chunk: 0, ref_length, 2 ref_length, ...
+    std::vector<int> slot_of_window;          // window -> slot index in the prediction exchange buffer
+    std::vector<int> own_windows;
+    DevBuf refs, preds, visit_tab;            // exchange buffers [world][slots] and the per-frame blend table
+    bool active = false;
+  } shard;
   // CUDA graph of one chunk's compute (launch-bound inner loop: ~630 kernels + ~200 D2D copies)
   bool use_graph = true;
   size_t window_group = 2;  // windows sharing each launch (VSR_WINDOW_GROUP, 1..2)
@@ -896,11 +906,8 @@ static void finalize(vsr_sttn* h) {
   h->ready = true;
 }
 
-// Encoder + window loop + decoder on T strip frames already on the device as u8 [T, sh, sw, 3] BGR
-// (sttn_auto_inpaint.py:122-164).  Leaves comps [T,MH,MW,3] fp32 and visits on the device.
-// `mask_strip` (sttn-det only): the strip rows of the full-resolution mask on the device, pitch sw; when null in
-// det mode the resized mask is taken from h->msmall as is (vsr_sttn_inpaint_strip_masked).
-static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_strip = nullptr) {
+// Window schedule / first-visit tables of the geometry record and every work buffer of a T-frame job.
+static void prepare_network(vsr_sttn* h, int T) {
   Ctx& c = h->ctx;
   const int MW = h->cfg.model_w, MH = h->cfg.model_h, FH = h->FH, FW = h->FW, C = 256;
   cudaStream_t s = c.stream;
@@ -921,6 +928,10 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
         ++visits[f];
       }
     }
+    // one more table: identity frame index + "first visit" everywhere (sharded mode decodes every window into its own slot)
+    const size_t ident = tab.size();
+    tab.resize(ident + 64, 1);
+    for (int i = 0; i < 32; ++i) tab[ident + i] = i;
     upload(G.sched_d, tab, s);
     upload(G.visits_d, visits, s);
     G.visits_h = visits;
@@ -954,8 +965,16 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
   h->comps.ensure((size_t)T * MH * MW * 3 * 4);
   if (h->cfg.mode == 1) h->msmall.ensure((size_t)MH * MW);
 
+}
+
+// A3/A4: crop is already done (strips), cv2-exact down-scale of the T strips (and of the mask strip for sttn-det).
+static void run_pre(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_strip) {
+  Ctx& c = h->ctx;
+  const int MW = h->cfg.model_w, MH = h->cfg.model_h;
+  cudaStream_t s = c.stream;
+  vsr_sttn::Geom& G = *h->g;
   // A3/A4 pre-processing
-  std::unique_ptr<ProfScope> region = std::make_unique<ProfScope>(c, VSR_PROF_PREPOST);
+  ProfScope region(c, VSR_PROF_PREPOST);
   G.pre_x.build(sw, MW, false, s);
   G.pre_y.build(sh, MH, true, s);
   strip_downscale_kernel<<<dim3((MW + 255) / 256, MH, T), 256, 0, s>>>(h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh,
@@ -975,40 +994,68 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
       ++c.launches;
     }
   }
-  const uint8_t* det_mask = det ? h->msmall.as<uint8_t>() : nullptr;
+}
+
+// A5: encoder on frames [f0, f0 + n) of the job -> feats16 / feats32 slots of those frames.
+static void run_encoder(vsr_sttn* h, int f0, int n) {
+  Ctx& c = h->ctx;
+  const int MW = h->cfg.model_w, MH = h->cfg.model_h, FH = h->FH, FW = h->FW, C = 256;
+  cudaStream_t s = c.stream;
+  const uint8_t* det_mask = h->cfg.mode == 1 ? h->msmall.as<uint8_t>() : nullptr;
+  const size_t fpix = (size_t)FH * FW, hpix = (size_t)(MH / 2) * (MW / 2);
+  const int T = n;
+  const uchar4* rgb = h->rgb8.as<uchar4>() + (size_t)f0 * MH * MW;
+  __half* e1 = h->e1.as<__half>() + (size_t)f0 * hpix * 64;
+  __half* e2s = h->e2s.as<__half>() + (size_t)f0 * fpix * 256;
+  __half* e3 = h->e3.as<__half>() + (size_t)f0 * fpix * 128;
+  __half* f16 = h->feats16.as<__half>() + (size_t)f0 * fpix * C;
+  float* f32 = h->feats32.as<float>() + (size_t)f0 * fpix * C;
   // A5 encoder
-  region.reset();
   {
     ProfScope ps_(c, VSR_PROF_ENCODER);
     const int total = T * (MH / 2) * (MW / 2);
-    stem_conv_kernel<<<(total + 63) / 64, 256, 0, s>>>(h->rgb8.as<uchar4>(), MH, MW, h->stem_w.as<float>(), h->stem_b.as<float>(),
-                                                        h->e1.as<__half>(), total, det_mask);
+    stem_conv_kernel<<<(total + 63) / 64, 256, 0, s>>>(rgb, MH, MW, h->stem_w.as<float>(), h->stem_b.as<float>(),
+                                                        e1, total, det_mask);
     CK(cudaGetLastError());
     ++c.launches;
     ConvIO io;
-    io.in = h->e1.as<__half>(); io.T = T; io.H = MH / 2; io.W = MW / 2;
-    io.flags = CONV_LRELU | CONV_S2D_STORE; io.out16 = h->e2s.as<__half>();
+    io.in = e1; io.T = T; io.H = MH / 2; io.W = MW / 2;
+    io.flags = CONV_LRELU | CONV_S2D_STORE; io.out16 = e2s;
     run_conv(c, h->enc2, io);
     ConvIO io3;
-    io3.in = h->e2s.as<__half>(); io3.T = T; io3.H = FH; io3.W = FW;
-    io3.flags = CONV_LRELU; io3.out16 = h->e3.as<__half>();
+    io3.in = e2s; io3.T = T; io3.H = FH; io3.W = FW;
+    io3.flags = CONV_LRELU; io3.out16 = e3;
     run_conv(c, h->enc3, io3);
     ConvIO io4;
-    io4.in = h->e3.as<__half>(); io4.T = T; io4.H = FH; io4.W = FW;
-    io4.flags = CONV_LRELU; io4.out16 = h->feats16.as<__half>(); io4.out32 = h->feats32.as<float>();
+    io4.in = e3; io4.T = T; io4.H = FH; io4.W = FW;
+    io4.flags = CONV_LRELU; io4.out16 = f16; io4.out32 = f32;
     run_conv(c, h->enc4, io4);
   }
+}
+
+// A6-A11 for the windows `wins` of the schedule (all of them, in order, for a whole-chunk job).  preds == nullptr: decode into the
+// running composites `comps` with the 0.5 / 0.5 blend of sttn_auto_inpaint.py:159-162 (windows must then come in schedule order);
+// preds != nullptr (sharded mode): window w's quantised frames go, unblended, to preds + slot_of[w] * 32 frames.
+static void run_windows(vsr_sttn* h, const std::vector<int>& wins, float* preds = nullptr, const std::vector<int>* slot_of = nullptr) {
+  Ctx& c = h->ctx;
+  const int MW = h->cfg.model_w, MH = h->cfg.model_h, FH = h->FH, FW = h->FW, C = 256;
+  cudaStream_t s = c.stream;
+  vsr_sttn::Geom& G = *h->g;
+  const bool det = h->cfg.mode == 1;
+  const uint8_t* det_mask = det ? h->msmall.as<uint8_t>() : nullptr;
+  const size_t fpix = (size_t)FH * FW;
+  std::unique_ptr<ProfScope> region;
   // A6-A11 window loop.  The transformer passes of different windows are independent (only the blend
   // into comps is ordered), so `group` consecutive windows share every conv / attention launch: at T=15 a
   // single window is 4.05 waves of 128x256 tiles (81 % wave efficiency), two windows are 7.8 (98 %).
   const size_t f16b = fpix * C * 2, f32b = fpix * C * 4;
-  for (size_t w0 = 0; w0 < G.sched.size(); w0 += h->window_group) {
-    const size_t w1 = std::min(G.sched.size(), w0 + h->window_group);
+  for (size_t w0 = 0; w0 < wins.size(); w0 += h->window_group) {
+    const size_t w1 = std::min(wins.size(), w0 + h->window_group);
     std::vector<AttnSegment> segs;
     int Tg = 0;
     region = std::make_unique<ProfScope>(c, VSR_PROF_GATHER);
-    for (size_t wi = w0; wi < w1; ++wi) {
-      const Window& w = G.sched[wi];
+    for (size_t k = w0; k < w1; ++k) {
+      const Window& w = G.sched[wins[k]];
       const int nn = (int)w.neighbors.size();
       // gather feats[neighbor_ids + ref_ids] (sttn_auto_inpaint.py:148)
       CK(cudaMemcpyAsync(h->xw16.as<uint8_t>() + (size_t)Tg * f16b, h->feats16.as<uint8_t>() + (size_t)w.neighbors[0] * f16b,
@@ -1062,9 +1109,10 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
     // A10 decoder on the neighbour frames only (sttn_auto_inpaint.py:150), window by window in schedule
     // order (the 0.5/0.5 blend of :159-162 is order dependent)
     ProfScope ps_dec(c, VSR_PROF_DECODER);
-    for (size_t wi = w0; wi < w1; ++wi) {
+    for (size_t k = w0; k < w1; ++k) {
+      const int wi = wins[k];
       const int nn = (int)G.sched[wi].neighbors.size();
-      const __half* xin = h->xw16.as<__half>() + (size_t)segs[wi - w0].first * fpix * C;
+      const __half* xin = h->xw16.as<__half>() + (size_t)segs[k - w0].first * fpix * C;
       size_t total = (size_t)nn * (2 * FH) * (2 * FW) * (C / 8);
       upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(xin, nn, FH, FW, C, h->up1.as<__half>());
       CK(cudaGetLastError());
@@ -1085,14 +1133,33 @@ static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_
       // A11: tanh + quantise + blend fused into the last conv's epilogue
       ConvIO e;
       e.in = h->d3.as<__half>(); e.T = nn; e.H = MH; e.W = MW; e.flags = CONV_FINAL;
-      e.comps = h->comps.as<float>();
-      e.frame_idx = G.sched_d.as<int>() + wi * 64;
-      e.first_visit = G.sched_d.as<int>() + wi * 64 + 32;
+      if (preds) {
+        e.comps = preds + (size_t)(*slot_of)[wi] * 32 * MH * MW * 3;
+        e.frame_idx = G.sched_d.as<int>() + G.sched.size() * 64;
+        e.first_visit = e.frame_idx + 32;
+      } else {
+        e.comps = h->comps.as<float>();
+        e.frame_idx = G.sched_d.as<int>() + wi * 64;
+        e.first_visit = G.sched_d.as<int>() + wi * 64 + 32;
+      }
       e.det_mask = det_mask;
       e.det_rgb = h->rgb8.as<uchar4>();
       run_conv(c, h->dec6, e);
     }
   }
+}
+
+// Encoder + window loop + decoder on T strip frames already on the device as u8 [T, sh, sw, 3] BGR
+// (sttn_auto_inpaint.py:122-164).  Leaves comps [T,MH,MW,3] fp32 and visits on the device.
+// `mask_strip` (sttn-det only): the strip rows of the full-resolution mask on the device, pitch sw; when null in
+// det mode the resized mask is taken from h->msmall as is (vsr_sttn_inpaint_strip_masked).
+static void run_network(vsr_sttn* h, int T, int sw, int sh, const uint8_t* mask_strip = nullptr) {
+  prepare_network(h, T);
+  run_pre(h, T, sw, sh, mask_strip);
+  run_encoder(h, 0, T);
+  std::vector<int> all(h->g->sched.size());
+  for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
+  run_windows(h, all);
 }
 
 // Strided host copies (frame strips <-> pinned staging) on a few threads: one thread moves ~10 GB/s, the
@@ -1351,6 +1418,123 @@ static void collect(vsr_sttn* h, int64_t ticket, uint8_t* const* frames_out) {
     memcpy(frames_out[t] + (size_t)sl.y0 * sl.sw * 3, sl.pin_out + t * sb, sb);
   });
   sl.busy = false;
+}
+
+// ---- window-level sharding of one chunk --------------------------------------------------------------------------
+// The windows of the chunk's schedule (sttn_auto_inpaint.py:142-146) are dealt round-robin: window w runs on rank w % world.  A rank
+// encodes only the frames its own windows decode (their neighbour ranges) plus the reference frames it is the *home* of (reference
+// frame number j, i.e. frame j * ref_length, lives on rank j % world); the encoder features of the reference frames — the only data a
+// window needs from outside its own neighbourhood (get_ref_index :107-120) — are exchanged with ONE all-gather, the quantised window
+// predictions with a second one, and every rank replays the ordered 0.5 / 0.5 blend (:159-162) on the full set.  The two exchange
+// buffers are laid out [world][slots per rank][...] so that both collectives are in-place NCCL all-gathers on device memory
+// (the Python side wraps the raw pointers; nothing passes through the host).
+static size_t shard_ref_bytes(vsr_sttn* h) { return (size_t)h->FH * h->FW * 256 * (2 + 4); }   // fp16 + fp32 features of one frame
+static size_t shard_pred_bytes(vsr_sttn* h) { return (size_t)32 * h->cfg.model_h * h->cfg.model_w * 3 * sizeof(float); }
+
+static void shard_begin(vsr_sttn* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask, int rank, int world) {
+  REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+  stage(h, frames_in, T, H, W, mask);
+  REQUIRE(h->areas.size() == 1, "window sharding handles exactly one strip; use vsr_sttn_inpaint_frames");
+  vsr_sttn::ShardJob& J = h->shard;
+  J.rank = rank; J.world = world; J.T = T;
+  const int y0 = h->areas[0][0], y1 = h->areas[0][1];
+  vsr_sttn::Geom& G = select_geom(h, T, W, y0, y1);
+  prepare_network(h, T);
+  const int nw = (int)G.sched.size();
+  J.ref_frames.clear();
+  for (int f = 0; f < T; f += h->cfg.ref_length) J.ref_frames.push_back(f);
+  J.ref_slots = ((int)J.ref_frames.size() + world - 1) / world;
+  J.win_slots = (nw + world - 1) / world;
+  J.slot_of_window.assign(nw, 0);
+  J.own_windows.clear();
+  for (int w = 0; w < nw; ++w) {
+    J.slot_of_window[w] = (w % world) * J.win_slots + w / world;
+    if (w % world == rank) J.own_windows.push_back(w);
+  }
+  J.refs.ensure((size_t)world * J.ref_slots * shard_ref_bytes(h));
+  J.preds.ensure((size_t)world * J.win_slots * shard_pred_bytes(h));
+  // blend table: the visits of every frame in schedule order
+  std::vector<int> tab((size_t)T * 4, 0);
+  for (int w = 0; w < nw; ++w)
+    for (size_t i = 0; i < G.sched[w].neighbors.size(); ++i) {
+      const int f = G.sched[w].neighbors[i];
+      REQUIRE(tab[f * 4] < 3, "a frame is decoded by more than three windows");
+      tab[f * 4 + 1 + tab[f * 4]++] = J.slot_of_window[w] * 32 + (int)i;
+    }
+  upload(J.visit_tab, tab, h->ctx.stream);
+  // frames this rank encodes: neighbours of its windows + its home reference frames, as maximal contiguous runs
+  std::vector<char> need(T, 0);
+  for (int w : J.own_windows)
+    for (int f : G.sched[w].neighbors) need[f] = 1;
+  for (size_t j = 0; j < J.ref_frames.size(); ++j)
+    if ((int)j % world == rank) need[J.ref_frames[j]] = 1;
+  const int sh = y1 - y0;
+  const bool det = h->cfg.mode == 1;
+  run_pre(h, T, W, sh, det ? h->mask_d.as<uint8_t>() + (size_t)y0 * W : nullptr);
+  for (int f = 0; f < T;) {
+    if (!need[f]) { ++f; continue; }
+    int e = f;
+    while (e < T && need[e]) ++e;
+    run_encoder(h, f, e - f);
+    f = e;
+  }
+  // pack the home reference frames' features into this rank's region of the exchange buffer
+  const size_t fpix = (size_t)h->FH * h->FW, b16 = fpix * 256 * 2, b32 = fpix * 256 * 4;
+  for (size_t j = 0; j < J.ref_frames.size(); ++j) {
+    if ((int)j % world != rank) continue;
+    uint8_t* dst = J.refs.as<uint8_t>() + ((size_t)rank * J.ref_slots + j / world) * (b16 + b32);
+    CK(cudaMemcpyAsync(dst, h->feats16.as<uint8_t>() + (size_t)J.ref_frames[j] * b16, b16, cudaMemcpyDeviceToDevice, h->ctx.stream));
+    CK(cudaMemcpyAsync(dst + b16, h->feats32.as<uint8_t>() + (size_t)J.ref_frames[j] * b32, b32, cudaMemcpyDeviceToDevice, h->ctx.stream));
+  }
+  sync_stream(h);   // the exchange runs on the caller's (NCCL) stream
+  J.active = true;
+}
+
+static void shard_windows(vsr_sttn* h) {
+  vsr_sttn::ShardJob& J = h->shard;
+  REQUIRE(J.active, "vsr_sttn_shard_windows without vsr_sttn_shard_begin");
+  const size_t fpix = (size_t)h->FH * h->FW, b16 = fpix * 256 * 2, b32 = fpix * 256 * 4;
+  for (size_t j = 0; j < J.ref_frames.size(); ++j) {   // every reference frame's features, from whoever encoded them
+    const uint8_t* src = J.refs.as<uint8_t>() + ((size_t)(j % J.world) * J.ref_slots + j / J.world) * (b16 + b32);
+    CK(cudaMemcpyAsync(h->feats16.as<uint8_t>() + (size_t)J.ref_frames[j] * b16, src, b16, cudaMemcpyDeviceToDevice, h->ctx.stream));
+    CK(cudaMemcpyAsync(h->feats32.as<uint8_t>() + (size_t)J.ref_frames[j] * b32, src + b16, b32, cudaMemcpyDeviceToDevice, h->ctx.stream));
+  }
+  run_windows(h, J.own_windows, J.preds.as<float>(), &J.slot_of_window);
+  sync_stream(h);
+}
+
+static void shard_finish(vsr_sttn* h, uint8_t* const* frames_out) {
+  vsr_sttn::ShardJob& J = h->shard;
+  REQUIRE(J.active && frames_out, "vsr_sttn_shard_finish without vsr_sttn_shard_begin");
+  vsr_sttn::Geom& G = *h->g;
+  cudaStream_t s = h->ctx.stream;
+  const int MW = h->cfg.model_w, MH = h->cfg.model_h;
+  const size_t fe = (size_t)MH * MW * 3;
+  blend_preds_kernel<<<dim3((unsigned)((fe + 255) / 256), J.T), 256, 0, s>>>(h->comps.as<float>(), J.preds.as<float>(), J.visit_tab.as<int>(), fe);
+  CK(cudaGetLastError());
+  ++h->ctx.launches;
+  const int y0 = h->areas[0][0], y1 = h->areas[0][1], sh = y1 - y0, sw = h->W;
+  const bool det = h->cfg.mode == 1;
+  const uint8_t* mask_strip = h->mask_d.as<uint8_t>() + (size_t)y0 * sw;
+  G.post_x.build(MW, sw, false, s);
+  G.post_y.build(MH, sh, true, s);
+  strip_composite_kernel<<<dim3((sw + 255) / 256, sh, J.T), 256, 0, s>>>(h->comps.as<float>(), MW, MH, G.visits_d.as<int>(), det ? nullptr : mask_strip,
+                                                                          sw, h->strips.as<uint8_t>(), (size_t)sh * sw * 3, sw, sh, J.T, G.post_x.view(),
+                                                                          G.post_y.view());
+  CK(cudaGetLastError());
+  ++h->ctx.launches;
+  // this rank hands back the frames f with f % world == rank (every rank holds all composites; the output is dealt, not replicated)
+  const size_t sb = (size_t)sh * sw * 3, fb = (size_t)h->H * h->W * 3;
+  ensure_pinned(h, sb * J.T);
+  for (int t = J.rank; t < J.T; t += J.world)
+    CK(cudaMemcpyAsync(h->pinned + t * sb, h->strips.as<uint8_t>() + t * sb, sb, cudaMemcpyDeviceToHost, s));
+  sync_stream(h);
+  parallel_for((J.T - J.rank + J.world - 1) / J.world, [&](int k) {
+    const int t = J.rank + k * J.world;
+    if (frames_out[t] != h->in_ptrs[t]) memcpy(frames_out[t], h->in_ptrs[t], fb);
+    memcpy(frames_out[t] + (size_t)y0 * sw * 3, h->pinned + t * sb, sb);
+  });
+  J.active = false;
 }
 
 }  // namespace vsr
@@ -1633,6 +1817,31 @@ int64_t vsr_sttn_submit(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, i
 
 int vsr_sttn_collect(vsr_sttn_t* h, int64_t ticket, uint8_t* const* frames_out) {
   return guarded([&] { collect(h, ticket, frames_out); });
+}
+
+int vsr_sttn_shard_begin(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask, int rank, int world,
+                         void** ref_buf, int64_t* ref_region_bytes, void** pred_buf, int64_t* pred_region_bytes) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(ref_buf && ref_region_bytes && pred_buf && pred_region_bytes, "null output");
+    shard_begin(h, frames_in, T, H, W, mask, rank, world);
+    *ref_buf = h->shard.refs.p;
+    *ref_region_bytes = (int64_t)((size_t)h->shard.ref_slots * shard_ref_bytes(h));
+    *pred_buf = h->shard.preds.p;
+    *pred_region_bytes = (int64_t)((size_t)h->shard.win_slots * shard_pred_bytes(h));
+  });
+}
+int vsr_sttn_shard_windows(vsr_sttn_t* h) {
+  return guarded([&] {
+    check_ready(h);
+    shard_windows(h);
+  });
+}
+int vsr_sttn_shard_finish(vsr_sttn_t* h, uint8_t* const* frames_out) {
+  return guarded([&] {
+    check_ready(h);
+    shard_finish(h, frames_out);
+  });
 }
 
 int vsr_sttn_sync(vsr_sttn_t* h) {

@@ -199,6 +199,34 @@ class STTNInpaint:
     def sync(self):
         _capi.check(_capi.lib().vsr_sttn_sync(self._h))
 
+    # ---- one chunk over several GPUs: window-level sharding (single-clip strong scaling) --------------------
+    def inpaint_chunk_sharded(self, frames: Sequence[np.ndarray], input_mask: np.ndarray, rank: int, world: int, all_gather=None) -> List[int]:
+        """The windows of one chunk's schedule (sttn_auto_inpaint.py:142-146) dealt over the `world` ranks of a process group: window w runs
+        on rank w % world.  Two in-place all-gathers over NVLink carry the only data that crosses windows — the encoder features of the
+        chunk's reference frames (get_ref_index, :107-120) and, afterwards, the windows' quantised predictions for the ordered 0.5 / 0.5
+        blend (:159-162) — both on device memory of the engine (`all_gather(device_pointer, region_bytes)`, default: NCCL through
+        torch.distributed).  Every rank must call this with the same frames and mask.  The result strips of the frames f with
+        f % world == rank are written into `frames[f]` in place (the other frames are left as they are on this rank); returns those
+        frame indices.  The output equals the unsharded `inpaint_inplace` bit for bit."""
+        frames = list(frames)
+        if not frames:
+            return []
+        H, W, m = self._check_batch(frames, input_mask)
+        pin, keep = self._ptr_array(frames)
+        L = _capi.lib()
+        ref_buf, pred_buf = C.c_void_p(), C.c_void_p()
+        ref_bytes, pred_bytes = C.c_int64(), C.c_int64()
+        _capi.check(L.vsr_sttn_shard_begin(self._h, C.cast(pin, C.POINTER(C.c_void_p)), len(frames), H, W, _capi.ptr(m, C.c_uint8), int(rank), int(world),
+                                           C.byref(ref_buf), C.byref(ref_bytes), C.byref(pred_buf), C.byref(pred_bytes)))
+        gather = all_gather or (lambda ptr, nbytes: _nccl_all_gather_inplace(ptr, nbytes, rank, world, self._dev))
+        if world > 1:
+            gather(int(ref_buf.value), int(ref_bytes.value))
+        _capi.check(L.vsr_sttn_shard_windows(self._h))
+        if world > 1:
+            gather(int(pred_buf.value), int(pred_bytes.value))
+        _capi.check(L.vsr_sttn_shard_finish(self._h, C.cast(pin, C.POINTER(C.c_void_p))))
+        return list(range(rank, len(frames), world))
+
     @property
     def cuda_stream(self) -> int:
         return int(_capi.lib().vsr_sttn_stream(self._h) or 0)
@@ -225,6 +253,24 @@ class STTNInpaint:
         ms = np.zeros(n, np.float32)
         _capi.check(_capi.lib().vsr_sttn_time_conv(self._h, T, n, _capi.ptr(ms, C.c_float)))
         return ms
+
+
+class _DevicePointer:
+    """raw device memory as a CUDA-array-interface object (so that torch can wrap it without a copy)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _nccl_all_gather_inplace(ptr: int, region_bytes: int, rank: int, world: int, device_index: int) -> None:
+    """In-place all-gather of a device buffer laid out [world][region_bytes]: region r is rank r's contribution (NCCL's in-place form:
+    the send buffer is the rank's own region of the receive buffer).  torch only wraps the engine's pointer and issues the collective."""
+    import torch
+    import torch.distributed as dist
+
+    whole = torch.as_tensor(_DevicePointer(ptr, region_bytes * world), device=torch.device("cuda", device_index))
+    dist.all_gather_into_tensor(whole, whole[rank * region_bytes:(rank + 1) * region_bytes])
+    torch.cuda.synchronize(device_index)
 
 
 def _in_ab_sections(frame_no, ab_sections) -> bool:
