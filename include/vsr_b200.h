@@ -23,6 +23,7 @@ extern "C" {
 #define VSR_ERR_CUDA (-2)
 #define VSR_ERR_STATE (-3)
 #define VSR_ERR_NOMEM (-4)
+#define VSR_ERR_RANGE (-5)   /* attention logits beyond the single-pass softmax's range: set option attn_direct = 0 and repeat the call */
 
 typedef struct vsr_sttn vsr_sttn_t;
 
@@ -104,6 +105,9 @@ int vsr_sttn_shard_begin(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, 
                          void** ref_buf, int64_t* ref_region_bytes, void** pred_buf, int64_t* pred_region_bytes);
 int vsr_sttn_shard_windows(vsr_sttn_t* h);
 int vsr_sttn_shard_finish(vsr_sttn_t* h, uint8_t* const* frames_out);
+/* Engine options: "attn_direct" (1: single-pass bf16 softmax for the attention heads without split-K — no score matrix, no softmax
+ * kernel; a job whose logits leave its range fails with VSR_ERR_RANGE and must be repeated with 0), "use_graph" (CUDA graph per chunk). */
+int vsr_sttn_set_option(vsr_sttn_t* h, const char* name, int value);
 /* CUDA stream of the engine (cudaStream_t as void*) so callers can bracket it with events. */
 void* vsr_sttn_stream(vsr_sttn_t* h);
 /* kernels launched by this engine since creation (bench.py `gpu_launches`) */

@@ -18,6 +18,8 @@
 //   its own fp32 slab of S; softmax_rows_kernel adds the slabs in a fixed order and writes P / rowsum.
 //   pv     : O[qp, pos,:] = (sum_kp P[qp,kp] V_pos[kp,:]) / rowsum[qp]  -> written back in NHWC
 #pragma once
+#include <cuda_bf16.h>
+
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
 
@@ -39,7 +41,9 @@ struct AttnHead {
   float* S;
   __half* P;
   float* rowsum;
-  int fused;            // 1: two-pass score kernels (rowmax_part / rowsum_part), 0: split-K slabs + softmax kernel
+  int fused;            // 0: split-K slabs of S + softmax kernel; 1: two-pass score kernels (rowmax_part / rowsum_part);
+                        // 2: "direct" — ONE score pass that writes P = exp2(s * log2e / sqrt(D)) without a row shift, in bf16 (8 exponent
+                        //    bits: no shift needed for any sane logit, softmax is shift invariant), + per-tile row sums; no S, no softmax kernel
   int npairs;           // key tile pairs = ceil(ntt / 2)
   float* rowmax_part;   // [ntt*128][npairs]
   float* rowsum_part;   // [ntt*128][npairs]
@@ -66,6 +70,7 @@ struct ScoreParams {
   const int* order;
   int order_stride;
   int softmax_row_begin[ATTN_MAX_HEADS + 1];  // first softmax block of each problem (fused problems: empty range)
+  int* overflow;   // direct heads: set when an exponent leaves the range that bf16 holds without a row shift (the host then re-runs unfused)
 };
 
 struct ScorePolicy {
@@ -149,7 +154,9 @@ struct ScorePolicy {
     c.dst = h.S + (size_t)t.split * h.slabS + (size_t)(t.qi * 128 + row) * h.ldS + t.kj * 256;
     c.m = -INFINITY;
     c.sum = 0.f;
-    if (h.fused && p.pass == 1 && t.n_cols > 0) {  // row max = max over the key-tile partials of pass A
+    if (h.fused == 2) {
+      c.m = 0.f;   // direct: no shift
+    } else if (h.fused && p.pass == 1 && t.n_cols > 0) {  // row max = max over the key-tile partials of pass A
       const float* pm = h.rowmax_part + (size_t)(t.qi * 128 + row) * h.npairs;
       float m = pm[0];
       for (int j = 1; j < h.npairs; ++j) m = fmaxf(m, pm[j]);
@@ -190,18 +197,35 @@ struct ScorePolicy {
       c.m = m;
       return;
     }
-    // pass B: P = exp2((s - max) * log2(e)/sqrt(D)) in fp16, masked slots = 0; row sums of the rounded values
+    // pass B: P = exp2((s - max) * log2(e)/sqrt(D)) in fp16 (direct heads: bf16, max = 0), masked slots = 0; row sums of the rounded values
     uint32_t* scw = reinterpret_cast<uint32_t*>(scr);
     float sum = c.sum;
+    if (h.fused == 2) {
+      bool big = false;
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const int kp = kp0 + i;
-      const float e0 = (kp < nvalid && (kp & owm) < h.ow) ? exp2f((v[i] - c.m) * h.scale_log2e) : 0.f;
-      const float e1 = (kp + 1 < nvalid && ((kp + 1) & owm) < h.ow) ? exp2f((v[i + 1] - c.m) * h.scale_log2e) : 0.f;
-      const __half2 hh = __floats2half2_rn(e0, e1);
-      const float2 f = __half22float2(hh);
-      sum += f.x + f.y;
-      scw[lane * 17 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+      for (int i = 0; i < 32; i += 2) {
+        const int kp = kp0 + i;
+        const float a0 = v[i] * h.scale_log2e, a1 = v[i + 1] * h.scale_log2e;
+        big |= (a0 > 100.f) | (a1 > 100.f);
+        const float e0 = (kp < nvalid && (kp & owm) < h.ow) ? fast_exp2(fminf(a0, 120.f)) : 0.f;
+        const float e1 = (kp + 1 < nvalid && ((kp + 1) & owm) < h.ow) ? fast_exp2(fminf(a1, 120.f)) : 0.f;
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+        const float2 f = __bfloat1622float2(hh);
+        sum += f.x + f.y;
+        scw[lane * 17 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      if (big && p.overflow) *p.overflow = 1;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int kp = kp0 + i;
+        const float e0 = (kp < nvalid && (kp & owm) < h.ow) ? exp2f((v[i] - c.m) * h.scale_log2e) : 0.f;
+        const float e1 = (kp + 1 < nvalid && ((kp + 1) & owm) < h.ow) ? exp2f((v[i + 1] - c.m) * h.scale_log2e) : 0.f;
+        const __half2 hh = __floats2half2_rn(e0, e1);
+        const float2 f = __half22float2(hh);
+        sum += f.x + f.y;
+        scw[lane * 17 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
     }
     c.sum = sum;
     __syncwarp();
@@ -534,6 +558,8 @@ struct PV2Policy {
     PVPolicy::epilogue(p, t, c, row, col0, v, scr);
   }
   __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}
+  // instruction-descriptor bits of this tile on top of the kernel's: A (= P) is bf16 for the direct heads (a_format, bits [7,10))
+  __device__ static uint32_t idesc_extra(const Params& p, const Tile& t) { return p.h[t.head].fused == 2 ? (1u << 7) : 0u; }
 };
 
 }  // namespace vsr

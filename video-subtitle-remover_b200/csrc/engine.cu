@@ -161,6 +161,7 @@ struct Ctx {
                                // (measured, profiles/gpu_session_r2_s2_summary.txt: with the field set three conv cases fail)
   bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
+  bool attn_direct = true; // single-pass bf16 P for the heads without split-K (no S, no softmax kernel); VSR_ATTN_DIRECT=0: S + softmax kernel
   bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
   // In-situ profile (vsr_sttn_profile): with `prof` set, every ProfScope brackets its launches with a pair of events on the
   // stream; classes are the VSR_PROF_* ids of include/vsr_b200.h.
@@ -525,6 +526,7 @@ struct TileSchedule {
 };
 struct AttnWorkspace {
   DevBuf S[ATTN_MAX_HEADS], P[ATTN_MAX_HEADS], rowsum[ATTN_MAX_HEADS], rowmax_part[ATTN_MAX_HEADS], rowsum_part[ATTN_MAX_HEADS];
+  DevBuf overflow;   // [0]: a direct head met a logit beyond the bf16-safe range
   std::map<std::string, std::unique_ptr<TileSchedule>> schedules;  // LPT tile orders, keyed by the problem shapes
 };
 
@@ -625,13 +627,15 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     const int splits = h.npos > split_target ? (h.npos + split_target - 1) / split_target : 1;
     h.chunks_per_split = (h.npos + splits - 1) / splits;
     h.splits = (h.npos + h.chunks_per_split - 1) / h.chunks_per_split;
-    h.fused = (h.splits == 1 && c.attn_fused) ? 1 : 0;
+    h.fused = (h.splits == 1 && c.attn_direct && c.attn_2cta) ? 2 : (h.splits == 1 && c.attn_fused) ? 1 : 0;
     h.npairs = (h.ntt + 1) / 2;
     any_unfused |= !h.fused;
     h.score_work_begin = score_work;
-    score_work += tiles * h.splits;
     h.score_work_begin2 = score_work2;
-    score_work2 += ((h.ntt + 1) / 2) * ((h.ntt + 1) / 2) * h.splits;
+    if (h.fused != 2) {   // direct heads have no pass A
+      score_work += tiles * h.splits;
+      score_work2 += ((h.ntt + 1) / 2) * ((h.ntt + 1) / 2) * h.splits;
+    }
     h.pv_ntiles = (h.npos + 3) / 4;
     h.pv_work_begin = pv_work;
     pv_work += h.ntt * h.pv_ntiles;
@@ -694,24 +698,29 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     for (int s2 = 0; s2 < nent; ++s2) {
       const AttnHead& h = sp.h[s2];
       key += "|" + std::to_string(h.ntt) + "," + std::to_string(h.npos) + "," + std::to_string(h.splits) + "," + std::to_string(h.nk64);
+      key += h.fused == 2 ? "d" : "";
       const int nq = two ? (h.ntt + 1) / 2 : h.ntt, nk2 = (h.ntt + 1) / 2;
-      for (int q = 0; q < nq; ++q)
+      for (int q = 0; q < nq && h.fused != 2; ++q)
         for (int kj = 0; kj < nk2; ++kj)
           for (int spl = 0; spl < h.splits; ++spl) cs.push_back(std::min(h.chunks_per_split, h.npos - spl * h.chunks_per_split) + 8);
       for (int m = 0; m < nq; ++m)
         for (int ni = 0; ni < h.pv_ntiles; ++ni) cp.push_back(h.nk64 + 3);
     }
-    const TileSchedule& ss = lpt_schedule(ws, "S" + key, cs, std::min(bins, (int)cs.size()), c.stream);
+    if (!cs.empty()) {
+      const TileSchedule& ss = lpt_schedule(ws, "S" + key, cs, std::min(bins, (int)cs.size()), c.stream);
+      sp.order = ss.dev.as<int>();
+      sp.order_stride = ss.stride;
+    }
     const TileSchedule& ps = lpt_schedule(ws, "P" + key, cp, std::min(bins, (int)cp.size()), c.stream);
-    sp.order = ss.dev.as<int>();
-    sp.order_stride = ss.stride;
     pp.order = ps.dev.as<int>();
     pp.order_stride = ps.stride;
   }
   sp.totalB = workB;
   sp.totalB2 = workB2;
+  ws.overflow.ensure(16);
+  sp.overflow = ws.overflow.as<int>();
   sp.pass = 0;  // pass A: per-tile row maxima (fused problems) / fp32 S slabs (split-K problems)
-  {
+  if ((c.attn_2cta ? score_work2 : score_work) > 0) {
     ProfScope ps_(c, VSR_PROF_SCORE);
     if (c.attn_2cta) launch_tc2<Score2Policy>(c, sp, score_work2);
     else launch_tc<ScorePolicy>(c, sp, score_work);
@@ -829,7 +838,7 @@ struct vsr_sttn {
     int rank = 0, world = 1, T = 0;
     int ref_slots = 0, win_slots = 0;         // exchange slots per rank
     std::vector<int> ref_frames;              // reference frames of the chunk: 0, ref_length, 2 ref_length, ...
-    std::vector<int> slot_of_window;          // window -> slot index in the prediction exchange buffer
+    std::vector<int> slot_of_window;          // window -> index of its first frame in the prediction exchange buffer
     std::vector<int> own_windows;
     DevBuf refs, preds, visit_tab;            // exchange buffers [world][slots] and the per-frame blend table
     bool active = false;
@@ -1035,7 +1044,7 @@ static void run_encoder(vsr_sttn* h, int f0, int n) {
 
 // A6-A11 for the windows `wins` of the schedule (all of them, in order, for a whole-chunk job).  preds == nullptr: decode into the
 // running composites `comps` with the 0.5 / 0.5 blend of sttn_auto_inpaint.py:159-162 (windows must then come in schedule order);
-// preds != nullptr (sharded mode): window w's quantised frames go, unblended, to preds + slot_of[w] * 32 frames.
+// preds != nullptr (sharded mode): window w's quantised frames go, unblended, to the frames slot_of[w] ... of `preds`.
 static void run_windows(vsr_sttn* h, const std::vector<int>& wins, float* preds = nullptr, const std::vector<int>* slot_of = nullptr) {
   Ctx& c = h->ctx;
   const int MW = h->cfg.model_w, MH = h->cfg.model_h, FH = h->FH, FW = h->FW, C = 256;
@@ -1134,7 +1143,7 @@ static void run_windows(vsr_sttn* h, const std::vector<int>& wins, float* preds 
       ConvIO e;
       e.in = h->d3.as<__half>(); e.T = nn; e.H = MH; e.W = MW; e.flags = CONV_FINAL;
       if (preds) {
-        e.comps = preds + (size_t)(*slot_of)[wi] * 32 * MH * MW * 3;
+        e.comps = preds + (size_t)(*slot_of)[wi] * MH * MW * 3;
         e.frame_idx = G.sched_d.as<int>() + G.sched.size() * 64;
         e.first_visit = e.frame_idx + 32;
       } else {
@@ -1304,12 +1313,25 @@ static void compute_area(vsr_sttn* h, int k) {
   G.warm_gen = g_alloc_generation;
 }
 
+// The direct attention heads write P = exp2(logit) in bf16 without a row shift; a logit beyond 2^100 would leave even bf16's range.
+// Their kernel clamps and raises a flag; the result of such a job must not be used: the caller switches the engine to the unfused
+// path (vsr_sttn_set_option("attn_direct", 0)) and repeats the call (the Python classes do that).  Call with the stream drained.
+static void check_attn_overflow(vsr_sttn* h) {
+  if (!h->ctx.attn_direct || !h->attn.overflow.p) return;
+  int v = 0;
+  CK(cudaMemcpy(&v, h->attn.overflow.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (!v) return;
+  CK(cudaMemset(h->attn.overflow.p, 0, sizeof(int)));
+  throw Error(VSR_ERR_RANGE, "attention logits beyond the range of the single-pass softmax (attn_direct); repeat with attn_direct = 0");
+}
+
 static void fetch_area(vsr_sttn* h, int k, uint8_t* const* out) {
   const int y0 = h->areas[k][0], y1 = h->areas[k][1];
   const int sh = y1 - y0, sw = h->W;
   const size_t sb = (size_t)sh * sw * 3;
   CK(cudaMemcpyAsync(h->pinned, h->strips.p, sb * h->T, cudaMemcpyDeviceToHost, h->ctx.stream));
   sync_stream(h);
+  check_attn_overflow(h);
   parallel_for(h->T, [&](int t) { memcpy(out[t] + (size_t)y0 * sw * 3, h->pinned + t * sb, sb); });
 }
 
@@ -1412,6 +1434,12 @@ static void collect(vsr_sttn* h, int64_t ticket, uint8_t* const* frames_out) {
   cudaError_t e = cudaEventSynchronize(sl.ev_d2h);
   if (e != cudaSuccess)
     throw Error(VSR_ERR_CUDA, std::string("cudaEventSynchronize -> ") + cudaGetErrorString(e) + device_error_report());
+  try {
+    check_attn_overflow(h);
+  } catch (...) {
+    sl.busy = false;
+    throw;
+  }
   const size_t sb = (size_t)sl.sh * sl.sw * 3, fb = (size_t)h->H * h->W * 3;
   parallel_for(sl.T, [&](int t) {
     if (frames_out[t] != sl.in_ptrs[t]) memcpy(frames_out[t], sl.in_ptrs[t], fb);
@@ -1430,6 +1458,11 @@ static void collect(vsr_sttn* h, int64_t ticket, uint8_t* const* frames_out) {
 // (the Python side wraps the raw pointers; nothing passes through the host).
 static size_t shard_ref_bytes(vsr_sttn* h) { return (size_t)h->FH * h->FW * 256 * (2 + 4); }   // fp16 + fp32 features of one frame
 static size_t shard_pred_bytes(vsr_sttn* h) { return (size_t)32 * h->cfg.model_h * h->cfg.model_w * 3 * sizeof(float); }
+// a rank's region of the prediction exchange buffer: its window slots (32 frames each) + one more frame whose first int carries the
+// rank's softmax-range flag, so that after the all-gather every rank takes the same decision (check_attn_overflow) without another
+// collective; the extra slot is a whole frame so that the buffer stays an array of frames
+static size_t shard_region_frames(vsr_sttn* h) { return (size_t)h->shard.win_slots * 32 + 1; }
+static size_t shard_pred_region(vsr_sttn* h) { return shard_region_frames(h) * (shard_pred_bytes(h) / 32); }
 
 static void shard_begin(vsr_sttn* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask, int rank, int world) {
   REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
@@ -1448,18 +1481,18 @@ static void shard_begin(vsr_sttn* h, const uint8_t* const* frames_in, int T, int
   J.slot_of_window.assign(nw, 0);
   J.own_windows.clear();
   for (int w = 0; w < nw; ++w) {
-    J.slot_of_window[w] = (w % world) * J.win_slots + w / world;
+    J.slot_of_window[w] = (int)((w % world) * shard_region_frames(h) + (size_t)(w / world) * 32);
     if (w % world == rank) J.own_windows.push_back(w);
   }
   J.refs.ensure((size_t)world * J.ref_slots * shard_ref_bytes(h));
-  J.preds.ensure((size_t)world * J.win_slots * shard_pred_bytes(h));
+  J.preds.ensure((size_t)world * shard_pred_region(h));
   // blend table: the visits of every frame in schedule order
   std::vector<int> tab((size_t)T * 4, 0);
   for (int w = 0; w < nw; ++w)
     for (size_t i = 0; i < G.sched[w].neighbors.size(); ++i) {
       const int f = G.sched[w].neighbors[i];
       REQUIRE(tab[f * 4] < 3, "a frame is decoded by more than three windows");
-      tab[f * 4 + 1 + tab[f * 4]++] = J.slot_of_window[w] * 32 + (int)i;
+      tab[f * 4 + 1 + tab[f * 4]++] = J.slot_of_window[w] + (int)i;
     }
   upload(J.visit_tab, tab, h->ctx.stream);
   // frames this rank encodes: neighbours of its windows + its home reference frames, as maximal contiguous runs
@@ -1500,6 +1533,11 @@ static void shard_windows(vsr_sttn* h) {
     CK(cudaMemcpyAsync(h->feats32.as<uint8_t>() + (size_t)J.ref_frames[j] * b32, src + b16, b32, cudaMemcpyDeviceToDevice, h->ctx.stream));
   }
   run_windows(h, J.own_windows, J.preds.as<float>(), &J.slot_of_window);
+  {   // this rank's softmax-range flag travels with its predictions
+    uint8_t* tail = J.preds.as<uint8_t>() + (size_t)J.rank * shard_pred_region(h) + (size_t)J.win_slots * shard_pred_bytes(h);
+    if (h->attn.overflow.p) CK(cudaMemcpyAsync(tail, h->attn.overflow.p, sizeof(int), cudaMemcpyDeviceToDevice, h->ctx.stream));
+    else CK(cudaMemsetAsync(tail, 0, sizeof(int), h->ctx.stream));
+  }
   sync_stream(h);
 }
 
@@ -1529,6 +1567,20 @@ static void shard_finish(vsr_sttn* h, uint8_t* const* frames_out) {
   for (int t = J.rank; t < J.T; t += J.world)
     CK(cudaMemcpyAsync(h->pinned + t * sb, h->strips.as<uint8_t>() + t * sb, sb, cudaMemcpyDeviceToHost, s));
   sync_stream(h);
+  if (h->ctx.attn_direct) {   // any rank's flag stops every rank (they all see the same gathered flags)
+    bool any = false;
+    for (int r = 0; r < J.world; ++r) {
+      int v = 0;
+      CK(cudaMemcpy(&v, J.preds.as<uint8_t>() + (size_t)r * shard_pred_region(h) + (size_t)J.win_slots * shard_pred_bytes(h), sizeof(int),
+                    cudaMemcpyDeviceToHost));
+      any |= v != 0;
+    }
+    if (any) {
+      if (h->attn.overflow.p) CK(cudaMemset(h->attn.overflow.p, 0, sizeof(int)));
+      J.active = false;
+      throw Error(VSR_ERR_RANGE, "attention logits beyond the range of the single-pass softmax (attn_direct) on some rank; repeat with attn_direct = 0");
+    }
+  }
   parallel_for((J.T - J.rank + J.world - 1) / J.world, [&](int k) {
     const int t = J.rank + k * J.world;
     if (frames_out[t] != h->in_ptrs[t]) memcpy(frames_out[t], h->in_ptrs[t], fb);
@@ -1687,6 +1739,7 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->ctx.conv_cluster = getenv("VSR_CONV_CLUSTER") && atoi(getenv("VSR_CONV_CLUSTER")) == 4 ? 4 : 2;
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     h->ctx.attn_fused = env_flag("VSR_ATTN_FUSED", false);
+    h->ctx.attn_direct = env_flag("VSR_ATTN_DIRECT", true);
     h->ctx.attn_lpt = env_flag("VSR_ATTN_LPT", true);
     h->ctx.conv_prefetch = env_flag("VSR_CONV_PREFETCH", false);
     if (getenv("VSR_WINDOW_GROUP")) h->window_group = (size_t)std::min(2, std::max(1, atoi(getenv("VSR_WINDOW_GROUP"))));
@@ -1733,6 +1786,7 @@ int vsr_sttn_inpaint_strip(vsr_sttn_t* h, const uint8_t* frames_bgr, int T, floa
     run_network(h, T, MW, MH);
     CK(cudaMemcpyAsync(comps_out, h->comps.p, sb * T * sizeof(float), cudaMemcpyDeviceToHost, h->ctx.stream));
     sync_stream(h);
+    check_attn_overflow(h);
     if (visits_out)
       for (int t = 0; t < T; ++t) visits_out[t] = h->g->visits_h[t];
   });
@@ -1754,6 +1808,7 @@ int vsr_sttn_inpaint_strip_masked(vsr_sttn_t* h, const uint8_t* frames_bgr, cons
     run_network(h, T, MW, MH, nullptr);
     CK(cudaMemcpyAsync(comps_out, h->comps.p, sb * T * sizeof(float), cudaMemcpyDeviceToHost, h->ctx.stream));
     sync_stream(h);
+    check_attn_overflow(h);
     if (visits_out)
       for (int t = 0; t < T; ++t) visits_out[t] = h->g->visits_h[t];
   });
@@ -1828,7 +1883,7 @@ int vsr_sttn_shard_begin(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, 
     *ref_buf = h->shard.refs.p;
     *ref_region_bytes = (int64_t)((size_t)h->shard.ref_slots * shard_ref_bytes(h));
     *pred_buf = h->shard.preds.p;
-    *pred_region_bytes = (int64_t)((size_t)h->shard.win_slots * shard_pred_bytes(h));
+    *pred_region_bytes = (int64_t)shard_pred_region(h);
   });
 }
 int vsr_sttn_shard_windows(vsr_sttn_t* h) {
@@ -1841,6 +1896,17 @@ int vsr_sttn_shard_finish(vsr_sttn_t* h, uint8_t* const* frames_out) {
   return guarded([&] {
     check_ready(h);
     shard_finish(h, frames_out);
+  });
+}
+
+int vsr_sttn_set_option(vsr_sttn_t* h, const char* name, int value) {
+  return guarded([&] {
+    REQUIRE(h && name, "bad arguments");
+    const std::string n(name);
+    if (n == "attn_direct") h->ctx.attn_direct = value != 0;
+    else if (n == "use_graph") h->use_graph = value != 0;
+    else throw Error(VSR_ERR_ARG, "unknown option " + n);
+    ++g_alloc_generation;   // captured chunk graphs bake the choice in
   });
 }
 
@@ -3022,6 +3088,7 @@ struct OpCtx {
     c.conv_cluster = getenv("VSR_CONV_CLUSTER") && atoi(getenv("VSR_CONV_CLUSTER")) == 4 ? 4 : 2;
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
     c.attn_fused = env_flag("VSR_ATTN_FUSED", false);
+    c.attn_direct = env_flag("VSR_ATTN_DIRECT", true);
     c.attn_lpt = env_flag("VSR_ATTN_LPT", true);
     c.conv_prefetch = env_flag("VSR_CONV_PREFETCH", false);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));

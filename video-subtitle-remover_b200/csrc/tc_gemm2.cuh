@@ -27,6 +27,15 @@ template <class P>
 struct tc_epi_warps<P, decltype((void)P::EPI_WARPS)> { static constexpr int value = P::EPI_WARPS; };
 template <class P>
 constexpr int tc2_threads() { return 64 + 32 * tc_epi_warps<P>::value; }
+// per-tile instruction-descriptor bits (operand formats) for policies that define idesc_extra(prm, tile)
+template <class P, class = void>
+struct tc_idesc_extra {
+  __device__ static uint32_t get(const typename P::Params&, const typename P::Tile&) { return 0u; }
+};
+template <class P>
+struct tc_idesc_extra<P, decltype((void)&P::idesc_extra)> {
+  __device__ static uint32_t get(const typename P::Params& p, const typename P::Tile& t) { return P::idesc_extra(p, t); }
+};
 
 template <class P>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2_threads<P>(), 1)
@@ -100,11 +109,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2_threads<P>(), 1)
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       TC_PROF_DECL(w_full);
       TC_PROF_DECL(w_tempty);
-      const uint32_t idesc = umma_idesc_f16(256, BN, 0, P::B_MN_MAJOR);
+      const uint32_t idesc0 = umma_idesc_f16(256, BN, 0, P::B_MN_MAJOR);
       for (int it = 0;; ++it) {
         const int t = P::tile_at(prm, first, step, it, ntiles);
         if (t < 0) break;
         const typename P::Tile tile = P::get_tile(prm, t, 0);
+        const uint32_t idesc = idesc0 | tc_idesc_extra<P>::get(prm, tile);
         TC_PROF_WAIT(w_tempty, smem_u32(&bar_tempty[as]), aphase ^ 1, ERR_MMA_TEMPTY | as);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;

@@ -112,8 +112,8 @@ class STTNInpaint:
             raise ValueError(f"strip frames must be {(self.model_input_height, self.model_input_width, 3)}, got {x.shape[1:]}")
         comps = np.empty(x.shape, np.float32)
         visits = np.zeros(T, np.int32)
-        _capi.check(_capi.lib().vsr_sttn_inpaint_strip(self._h, _capi.ptr(x, C.c_uint8), T, _capi.ptr(comps, C.c_float),
-                                                       _capi.ptr(visits, C.c_int32)))
+        self._exact_softmax_retry(lambda: _capi.check(_capi.lib().vsr_sttn_inpaint_strip(self._h, _capi.ptr(x, C.c_uint8), T, _capi.ptr(comps, C.c_float),
+                                                                                          _capi.ptr(visits, C.c_int32))))
         return [comps[i].astype(np.uint8) if visits[i] <= 1 else comps[i] for i in range(T)]
 
     def get_ref_index(self, neighbor_ids, length):
@@ -152,7 +152,22 @@ class STTNInpaint:
             raise ValueError(f"mask shape {m.shape} != frame shape {(H, W)}")
         return H, W, np.ascontiguousarray(m, dtype=np.uint8)
 
+    def set_option(self, name: str, value: int) -> None:
+        _capi.check(_capi.lib().vsr_sttn_set_option(self._h, name.encode(), int(value)))
+
+    def _exact_softmax_retry(self, call):
+        """Run `call()`; when the single-pass softmax reports logits beyond its range (never seen with the reference's weights: it would take
+        |logit| > 69), switch this engine to the score-matrix + softmax-kernel path for good and repeat the call."""
+        try:
+            return call()
+        except _capi.VsrRangeError:
+            self.set_option("attn_direct", 0)
+            return call()
+
     def _run(self, frames_in, mask, frames_out):
+        return self._exact_softmax_retry(lambda: self._run_once(frames_in, mask, frames_out))
+
+    def _run_once(self, frames_in, mask, frames_out):
         frames_in = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames_in]
         H, W, m = self._check_batch(frames_in, mask)
         pin, keep_in = self._ptr_array(frames_in)
@@ -192,8 +207,20 @@ class STTNInpaint:
         return t
 
     def collect(self, ticket: int, frames_out) -> None:
-        pout, keep = self._ptr_array(list(frames_out))
-        _capi.check(_capi.lib().vsr_sttn_collect(self._h, ticket, C.cast(pout, C.POINTER(C.c_void_p))))
+        frames_out = list(frames_out)
+        pout, keep = self._ptr_array(frames_out)
+        suspect = getattr(self, "_suspect", set())
+        try:
+            _capi.check(_capi.lib().vsr_sttn_collect(self._h, ticket, C.cast(pout, C.POINTER(C.c_void_p))))
+            redo = ticket in suspect
+        except _capi.VsrRangeError:      # repeat this chunk synchronously on the exact-softmax path (its input frames are still untouched);
+            self.set_option("attn_direct", 0)   # a chunk submitted before the switch shares the (now cleared) flag: repeat it as well
+            self._suspect = suspect | (set(self._inflight) - {ticket})
+            redo = True
+        if redo:
+            src, m = self._inflight[ticket]
+            self._run_once(src, m, frames_out)
+        suspect.discard(ticket)
         self._inflight.pop(ticket, None)
 
     def sync(self):
@@ -224,7 +251,17 @@ class STTNInpaint:
         _capi.check(L.vsr_sttn_shard_windows(self._h))
         if world > 1:
             gather(int(pred_buf.value), int(pred_bytes.value))
-        _capi.check(L.vsr_sttn_shard_finish(self._h, C.cast(pin, C.POINTER(C.c_void_p))))
+        try:
+            _capi.check(L.vsr_sttn_shard_finish(self._h, C.cast(pin, C.POINTER(C.c_void_p))))
+        except _capi.VsrRangeError:
+            if getattr(self, "_in_retry", False):
+                raise
+            self.set_option("attn_direct", 0)      # every rank sees the same logits, i.e. takes this branch together
+            self._in_retry = True
+            try:
+                return self.inpaint_chunk_sharded(frames, input_mask, rank, world, all_gather)
+            finally:
+                self._in_retry = False
         return list(range(rank, len(frames), world))
 
     @property

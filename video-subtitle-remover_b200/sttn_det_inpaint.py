@@ -30,6 +30,6 @@ class STTNDetInpaint(STTNInpaint):
             raise ValueError(f"strip frames must be {(self.model_input_height, self.model_input_width, 3)}, got {x.shape[1:]}")
         comps = np.empty(x.shape, np.float32)
         visits = np.zeros(T, np.int32)
-        _capi.check(_capi.lib().vsr_sttn_inpaint_strip_masked(self._h, _capi.ptr(x, C.c_uint8), _capi.ptr(m, C.c_uint8), T,
-                                                              _capi.ptr(comps, C.c_float), _capi.ptr(visits, C.c_int32)))
+        self._exact_softmax_retry(lambda: _capi.check(_capi.lib().vsr_sttn_inpaint_strip_masked(
+            self._h, _capi.ptr(x, C.c_uint8), _capi.ptr(m, C.c_uint8), T, _capi.ptr(comps, C.c_float), _capi.ptr(visits, C.c_int32))))
         return [comps[i].astype(np.uint8) if visits[i] <= 1 else comps[i] for i in range(T)]
