@@ -167,6 +167,14 @@ int vsr_rt_download(vsr_rt_t* h, uint64_t dev_ptr, void* host, int64_t bytes);
 int vsr_rt_copy(vsr_rt_t* h, uint64_t dst, uint64_t src, int64_t bytes);         /* device -> device on the runtime's stream (ProPainter: chunk results of propainter_inpaint.py:254-304 into the whole-sequence buffers) */
 int vsr_rt_sync(vsr_rt_t* h);
 int64_t vsr_rt_launch_count(vsr_rt_t* h);
+/* Scene-cut scores: what the vendored PySceneDetect ContentDetector computes per frame for SubtitleDetect.get_scene_div_frame_no
+ * (backend/tools/subtitle_detect.py:158-170; backend/scenedetect/scene_manager.py:929-933, detectors/content_detector.py:25-35,155-186): down-scale
+ * by W // 256 like cv2.resize INTER_LINEAR, 8-bit HSV like cv2.cvtColor, sum |delta| of hue / saturation / value against the previous frame.
+ * scene_begin fixes the frame size and forgets the previous frame; scene_frames consumes n consecutive decoded BGR frames (host pointers, H x W x 3)
+ * and returns three int64 sums per frame (zeros for the very first frame of a sequence) — integers, so the float score and the threshold /
+ * min-scene-length logic on the host reproduce the reference bit for bit. */
+int vsr_rt_scene_begin(vsr_rt_t* h, int H, int W);
+int vsr_rt_scene_frames(vsr_rt_t* h, const uint8_t* const* frames_bgr, int n, int64_t* sums_out);
 /* conv2d / depthwise_conv2d / conv2d_transpose of the PIR program with batch-norm and bias already folded into
  * (w, bias): w fp32 in the framework layout ([Cout,Cin/groups,kh,kw]; transposed: [Cin,Cout,2,2]); cin_pitch =
  * channel pitch of the input tensor.  Dense convs with >= 16 input and >= 8 output channels run on the tcgen05

@@ -91,6 +91,8 @@ _PROTOS = {
     "vsr_rt_copy": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64]),
     "vsr_rt_sync": (C.c_int, [C.c_void_p]),
     "vsr_rt_launch_count": (C.c_int64, [C.c_void_p]),
+    "vsr_rt_scene_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vsr_rt_scene_frames": (C.c_int, [C.c_void_p, _pp, C.c_int, _i64p]),
     "vsr_rt_conv_create": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_int, _i32p]),
     "vsr_rt_conv_create_split": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),

@@ -155,6 +155,72 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restric
   *reinterpret_cast<uint4*>(out + (((size_t)t * 2 * h + oy) * 2 * w + ox) * C + c8 * 8) = *reinterpret_cast<const uint4*>(o);
 }
 
+// Scene-cut detection (backend/scenedetect ContentDetector through subtitle_detect.py:158-170): one pass over a decoded BGR
+// frame that (1) down-scales it like the reference's decode thread (cv2.resize INTER_LINEAR in its 11-bit fixed point, or the rounded 2x2
+// mean OpenCV substitutes for an exact 2x down-scale; `mode` 0 = none, 1 = linear, 2 = 2x2 mean), (2) converts the pixel to 8-bit HSV with
+// OpenCV's 12-bit tables (RGB2HSV_b, hue range 180), (3) stores it for the next frame and (4) accumulates |delta| of hue, saturation and
+// value against the previous frame's pixel into three 64-bit integer sums — integers, so the frame score is bit-exact on the host.
+// HBM-bound: the frame is read once (6.2 MB at 1080p), the small HSV images stay in L2.
+__global__ void __launch_bounds__(256) scene_hsv_diff_kernel(const uint8_t* __restrict__ bgr, int sw, int sh, int dw, int dh, int mode,
+                                                             ResizeTaps tx, ResizeTaps ty, const int* __restrict__ sdiv,
+                                                             const int* __restrict__ hdiv, const uchar4* __restrict__ prev,
+                                                             uchar4* __restrict__ cur, int have_prev, unsigned long long* __restrict__ sums) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  int dh_ = 0, ds_ = 0, dv_ = 0;
+  if (x < dw) {
+    int c3[3];
+    if (mode == 0) {
+      const uint8_t* p = bgr + ((size_t)y * sw + x) * 3;
+      c3[0] = p[0]; c3[1] = p[1]; c3[2] = p[2];
+    } else if (mode == 2) {
+      const uint8_t* p0 = bgr + ((size_t)(2 * y) * sw + 2 * x) * 3;
+      const uint8_t* p1 = p0 + (size_t)sw * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) c3[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
+    } else {
+      const int x0 = tx.i0[x] * 3, x1 = tx.i1[x] * 3;
+      const int wx0 = tx.w0[x], wx1 = tx.w1[x], wy0 = ty.w0[y], wy1 = ty.w1[y];
+      const uint8_t* r0 = bgr + (size_t)ty.i0[y] * sw * 3;
+      const uint8_t* r1 = bgr + (size_t)ty.i1[y] * sw * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int s0 = r0[x0 + c] * wx0 + r0[x1 + c] * wx1;
+        const int s1 = r1[x0 + c] * wx0 + r1[x1 + c] * wx1;
+        c3[c] = min(max((((wy0 * (s0 >> 4)) >> 16) + ((wy1 * (s1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+      }
+    }
+    const int b = c3[0], g = c3[1], r = c3[2];
+    const int v = max(max(b, g), r), vmin = min(min(b, g), r), diff = v - vmin;
+    const int s = (diff * sdiv[v] + (1 << 11)) >> 12;
+    int h = (v == r) ? (g - b) : (v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff);
+    h = (h * hdiv[diff] + (1 << 11)) >> 12;
+    h += h < 0 ? 180 : 0;
+    const size_t o = (size_t)y * dw + x;
+    cur[o] = make_uchar4((unsigned char)h, (unsigned char)s, (unsigned char)v, 0);
+    if (have_prev) {
+      const uchar4 q = prev[o];
+      dh_ = abs(h - (int)q.x); ds_ = abs(s - (int)q.y); dv_ = abs(v - (int)q.z);
+    }
+  }
+  if (!have_prev) return;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    dh_ += __shfl_xor_sync(0xffffffffu, dh_, o);
+    ds_ += __shfl_xor_sync(0xffffffffu, ds_, o);
+    dv_ += __shfl_xor_sync(0xffffffffu, dv_, o);
+  }
+  __shared__ int red[3][8];
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = dh_; red[1][threadIdx.x >> 5] = ds_; red[2][threadIdx.x >> 5] = dv_; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    atomicAdd(&sums[threadIdx.x], (unsigned long long)t);
+  }
+}
+
 // Sharded windows (vsr_sttn_shard_*): every window was decoded into its own slot `preds[slot][local frame]` (quantised, unblended);
 // this replays the running 0.5 / 0.5 blend of sttn_auto_inpaint.py:159-162 per frame in schedule order — the same two multiplies
 // and one add per visit as the CONV_FINAL epilogue, so the result is bit-identical to the single-GPU chunk.

@@ -1630,6 +1630,13 @@ struct vsr_rt {
   size_t plane_host_bytes = 0;
   DevBuf flag;     // [0] int overflow flag raised by the scaled epilogues, [1] uint absmax bits
   DevTaps px, py;  // resize tables of the pre-processing
+  struct Scene {      // scene-cut scores (vsr_rt_scene_*)
+    int H = 0, W = 0, dh = 0, dw = 0, mode = 0, have_prev = 0, slot = 0;
+    DevTaps tx, ty;
+    DevBuf sdiv, hdiv, hsv[2], frame[2], sums;
+    uint8_t* pin[2] = {nullptr, nullptr};
+    size_t pin_n = 0;
+  } scene;
   std::vector<cudaGraphExec_t> graphs;
   bool capturing = false;
   int* overflow() { return flag.as<int>(); }
@@ -1638,6 +1645,8 @@ struct vsr_rt {
       if (g) cudaGraphExecDestroy(g);
     if (plane_host) cudaFreeHost(plane_host);
     if (out_host) cudaFreeHost(out_host);
+    for (auto& p : scene.pin)
+      if (p) cudaFreeHost(p);
     for (auto& kv : fft_plans) {
       if (kv.second.r2c) cufftDestroy(kv.second.r2c);
       if (kv.second.c2r) cufftDestroy(kv.second.c2r);
@@ -2151,6 +2160,82 @@ int vsr_rt_sync(vsr_rt_t* h) {
   });
 }
 int64_t vsr_rt_launch_count(vsr_rt_t* h) { return h ? h->ctx.launches : 0; }
+
+/* ---- scene-cut scores ---- */
+int vsr_rt_scene_begin(vsr_rt_t* h, int H, int W) {
+  return guarded([&] {
+    rt_check(h);
+    REQUIRE(H > 0 && W > 0, "bad frame size");
+    vsr_rt::Scene& S = h->scene;
+    S.H = H; S.W = W;
+    // scene_manager.py:132-149, 929-933: factor = W // 256, size (round(W / f), round(H / f)) with Python's round-half-even
+    const int f = W < 256 ? 1 : W / 256;
+    auto pyround = [](double v) { return (int)std::nearbyint(v); };   // default rounding mode: to nearest, ties to even
+    S.dw = f <= 1 ? W : pyround((double)W / f);
+    S.dh = f <= 1 ? H : pyround((double)H / f);
+    S.mode = f <= 1 ? 0 : (W == 2 * S.dw && H == 2 * S.dh) ? 2 : 1;
+    cudaStream_t s = h->ctx.stream;
+    if (S.mode == 1) {
+      S.tx.build(W, S.dw, false, s);
+      S.ty.build(H, S.dh, true, s);
+    }
+    if (!S.sdiv.p) {   // OpenCV's RGB2HSV_b tables: saturate_cast<int>((255 << 12) / (1. * i)), saturate_cast<int>((180 << 12) / (6. * i))
+      std::vector<int> sd(256, 0), hd(256, 0);
+      for (int i = 1; i < 256; ++i) {
+        sd[i] = (int)std::nearbyint((255 << 12) / (1.0 * i));
+        hd[i] = (int)std::nearbyint((180 << 12) / (6.0 * i));
+      }
+      upload(S.sdiv, sd, s);
+      upload(S.hdiv, hd, s);
+    }
+    for (auto& b : S.hsv) b.ensure((size_t)S.dh * S.dw * 4);
+    for (auto& b : S.frame) b.ensure((size_t)H * W * 3);
+    const size_t fb = (size_t)H * W * 3;
+    if (fb > S.pin_n) {
+      for (auto& p : S.pin) {
+        if (p) CK(cudaFreeHost(p));
+        p = nullptr;
+        CK(cudaMallocHost(&p, fb));
+      }
+      S.pin_n = fb;
+    }
+    S.have_prev = 0;
+    S.slot = 0;
+    rt_sync(h);
+  });
+}
+int vsr_rt_scene_frames(vsr_rt_t* h, const uint8_t* const* frames_bgr, int n, int64_t* sums_out) {
+  return guarded([&] {
+    rt_check(h);
+    vsr_rt::Scene& S = h->scene;
+    REQUIRE(S.H > 0 && frames_bgr && sums_out && n >= 0, "vsr_rt_scene_begin first");
+    if (n == 0) return;
+    cudaStream_t s = h->ctx.stream;
+    const size_t fb = (size_t)S.H * S.W * 3;
+    S.sums.ensure((size_t)n * 3 * sizeof(unsigned long long));
+    CK(cudaMemsetAsync(S.sums.p, 0, (size_t)n * 3 * sizeof(unsigned long long), s));
+    cudaEvent_t ev[2];
+    for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int i = 0; i < n; ++i) {
+      const int b = i & 1;
+      if (i >= 2) CK(cudaEventSynchronize(ev[b]));   // the pinned buffer's previous upload has been consumed
+      memcpy(S.pin[b], frames_bgr[i], fb);
+      CK(cudaMemcpyAsync(S.frame[b].p, S.pin[b], fb, cudaMemcpyHostToDevice, s));
+      CK(cudaEventRecord(ev[b], s));
+      const int cur = S.slot, prev = S.slot ^ 1;
+      scene_hsv_diff_kernel<<<dim3((S.dw + 255) / 256, S.dh), 256, 0, s>>>(
+          S.frame[b].as<uint8_t>(), S.W, S.H, S.dw, S.dh, S.mode, S.tx.view(), S.ty.view(), S.sdiv.as<int>(), S.hdiv.as<int>(),
+          S.hsv[prev].as<uchar4>(), S.hsv[cur].as<uchar4>(), S.have_prev, S.sums.as<unsigned long long>() + (size_t)i * 3);
+      CK(cudaGetLastError());
+      ++h->ctx.launches;
+      S.have_prev = 1;
+      S.slot ^= 1;
+    }
+    CK(cudaMemcpyAsync(sums_out, S.sums.p, (size_t)n * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    rt_sync(h);
+    for (auto& e : ev) cudaEventDestroy(e);
+  });
+}
 
 int vsr_rt_absmax(vsr_rt_t* h, uint64_t dev_ptr, int64_t n_elems, float* out) {
   return guarded([&] {

@@ -67,6 +67,14 @@ class SubtitleDetect:
                 on_frame(no)
         return P.drop_empty(P.unify_regions(P.gap_fill(sampled, self.SAMPLE_STEP)))
 
+    @staticmethod
+    def get_scene_div_frame_no(v_path, device="cuda:0"):
+        """subtitle_detect.py:158-170 (frame numbers at which a new scene starts; ProPainter mode splits its intervals there, main.py:165):
+        the ContentDetector scores on the B200 (vsr_b200.scene_detect), threshold / scene-list logic bit-exact on the host."""
+        from .scene_detect import get_scene_div_frame_no
+
+        return get_scene_div_frame_no(v_path, device)
+
     def find_subtitle_frame_no(self, sub_remover=None) -> Dict[int, List[P.Box]]:
         """subtitle_detect.py:84-132 on `self.video_path`."""
         import cv2
