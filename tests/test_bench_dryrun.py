@@ -191,6 +191,9 @@ def test_contract_line_with_cpu_baseline(fake_world, capsys, monkeypatch):
         def fps(self, frames, mask):
             return 1.25, len(frames) / 1.25
 
+        def pick_threads(self, frames, mask):
+            return 1.25
+
         def describe(self):
             return "stand-in"
 
@@ -214,6 +217,9 @@ def test_reference_arm_line(capsys, monkeypatch):
 
         def fps(self, frames, mask):
             return 2.0, len(frames) / 2.0
+
+        def pick_threads(self, frames, mask):
+            return 2.0
 
         def describe(self):
             return "stand-in"

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
   // per-epilogue-warp 32x33 fp32 transpose scratch (policies that store row-scattered data coalesce through it)
-  __shared__ float epi_scratch[P::EPI_SCRATCH ? 4 * 32 * 33 : 1];
+  __shared__ __align__(16) float epi_scratch[P::EPI_SCRATCH ? 4 * 32 * 33 : 4];
 
   const long long t_kernel0 = TC_PROF_NOW();
   (void)t_kernel0;
@@ -151,12 +151,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         for (int c = 0; c < tile.n_cols; c += 32) {
           float v[32];
           tmem_ld32(taddr + c, v);
-          P::epilogue(prm, tile, ctx, row, c, v, epi_scratch + (P::EPI_SCRATCH ? quarter * 32 * 33 : 0));
+          P::epilogue(prm, tile, ctx, row, c, v, (P::EPI_SCRATCH ? epi_scratch + quarter * 32 * 33 : nullptr));
         }
       } else {
         float v[32];
         tmem_ld16(taddr, v);
-        P::epilogue(prm, tile, ctx, row, 0, v, epi_scratch + (P::EPI_SCRATCH ? quarter * 32 * 33 : 0));
+        P::epilogue(prm, tile, ctx, row, 0, v, (P::EPI_SCRATCH ? epi_scratch + quarter * 32 * 33 : nullptr));
       }
       P::row_end(prm, tile, ctx, row);
       tc_fence_before();
