@@ -308,10 +308,24 @@ class CpuReference:
         return f"{what}, torch {self.torch.__version__} CPU fp32, {self.threads} of {os.cpu_count()} threads{sweep}"
 
 
-def cpu_sample_frames(est_fps, steps, budget_s):
-    """Frames per CPU step so that `steps` steps fit the budget: between 6 (one two-window call) and a whole 50-frame chunk.  Shorter
-    samples have shorter attention windows, i.e. they are FASTER per frame than a whole chunk: the bias favours the CPU."""
-    return int(min(CHUNK, max(6, budget_s * est_fps / max(steps, 1))))
+CPU_SAMPLE_SIZES = (6, 10, 16, 25, 50)
+
+
+def cpu_sample_frames(cpu, frames, mask, per_step_s):
+    """Frames per CPU step, chosen by measurement: the largest of CPU_SAMPLE_SIZES whose call fits the per-step budget.  The cost per frame
+    grows with the clip (attention is quadratic in the window length, and windows reach their full 10-15 frames only from ~16 frames on),
+    so a rate measured on a short clip must not be extrapolated: sizes are tried in ascending order (each try doubles as warm-up) until one
+    exceeds the budget or the next is predicted to (quadratic extrapolation).  Shorter samples are FASTER per frame than a whole chunk:
+    the bias favours the CPU."""
+    best, t_prev, n_prev = CPU_SAMPLE_SIZES[0], None, None
+    for n in CPU_SAMPLE_SIZES:
+        if t_prev is not None and t_prev * (n / n_prev) ** 2 > 1.5 * per_step_s:
+            break
+        _, t = cpu.fps(frames[:n], mask)
+        if t > per_step_s and n != CPU_SAMPLE_SIZES[0]:
+            break
+        best, t_prev, n_prev = n, t, n
+    return best
 
 
 def run_reference(args, rank, world):
@@ -322,8 +336,8 @@ def run_reference(args, rank, world):
     cpu = CpuReference(src)
     frames = S.synthetic_clip(CHUNK, H, W, seed=0)
     mask = S.default_mask(H, W)
-    est = cpu.pick_threads(frames, mask)                    # thread-count sweep, doubles as the first warm-up
-    n = cpu_sample_frames(est, args.steps + args.warmup, CPU_BUDGET_S)
+    cpu.pick_threads(frames, mask)                          # thread-count sweep, doubles as the first warm-up
+    n = cpu_sample_frames(cpu, frames, mask, CPU_BUDGET_S / max(args.steps + args.warmup, 1))
     for _ in range(args.warmup):
         cpu.fps(frames[:n], mask)
     dts = []

@@ -105,7 +105,7 @@ int vsr_sttn_shard_begin(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, 
                          void** ref_buf, int64_t* ref_region_bytes, void** pred_buf, int64_t* pred_region_bytes);
 int vsr_sttn_shard_windows(vsr_sttn_t* h);
 int vsr_sttn_shard_finish(vsr_sttn_t* h, uint8_t* const* frames_out);
-/* Engine options: "attn_direct" (1: single-pass bf16 softmax for the attention heads without split-K — no score matrix, no softmax
+/* Engine options: "attn_direct" (1: single-pass softmax (no row shift) for the attention heads without split-K — no score matrix, no softmax
  * kernel; a job whose logits leave its range fails with VSR_ERR_RANGE and must be repeated with 0), "use_graph" (CUDA graph per chunk). */
 int vsr_sttn_set_option(vsr_sttn_t* h, const char* name, int value);
 /* CUDA stream of the engine (cudaStream_t as void*) so callers can bracket it with events. */

@@ -232,7 +232,7 @@ def test_reference_arm_line(capsys, monkeypatch):
     d = _line(capsys)
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "frames/s" and abs(d["value"] - 2.0) < 1e-9
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["config"]["frames_per_step"] == 6
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["config"]["frames_per_step"] in bench.CPU_SAMPLE_SIZES
     # ranks other than 0 print nothing and exit 0
     monkeypatch.setenv("RANK", "1")
     monkeypatch.setenv("WORLD_SIZE", "2")
@@ -257,5 +257,11 @@ def test_cpu_reference_runs_the_unmodified_reference_or_the_port():
 
 
 def test_sample_sizing():
-    assert bench.cpu_sample_frames(1.0, 25, 240.0) == 9 and bench.cpu_sample_frames(100.0, 9, 240.0) == bench.CHUNK and bench.cpu_sample_frames(0.01, 25, 240.0) == 6
+    class Quad:      # a CPU whose call costs 0.05 s per frame squared
+        def fps(self, frames, mask):
+            return 1.0, 0.05 * len(frames) ** 2
+
+    frames = list(range(50))
+    assert bench.cpu_sample_frames(Quad(), frames, None, 9.6) == 10          # 6 -> 1.8 s, 10 -> 5 s, 16 predicted 12.8 s <= 14.4: tried, 12.8 s > budget
+    assert bench.cpu_sample_frames(Quad(), frames, None, 1000.0) == 50 and bench.cpu_sample_frames(Quad(), frames, None, 0.1) == 6
     assert sum(len(a) + len(b) for a, b in bench.chunk_schedule(50)) == 140

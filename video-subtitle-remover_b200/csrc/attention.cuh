@@ -42,8 +42,9 @@ struct AttnHead {
   __half* P;
   float* rowsum;
   int fused;            // 0: split-K slabs of S + softmax kernel; 1: two-pass score kernels (rowmax_part / rowsum_part);
-                        // 2: "direct" — ONE score pass that writes P = exp2(s * log2e / sqrt(D)) without a row shift, in bf16 (8 exponent
-                        //    bits: no shift needed for any sane logit, softmax is shift invariant), + per-tile row sums; no S, no softmax kernel
+                        // 2: "direct" — ONE score pass that writes P = exp2(s * log2e / sqrt(D)) without a row shift (softmax is shift
+                        //    invariant; fp16 holds 2^-24 .. 2^16, the range flag below catches rows outside it) + per-tile row sums;
+                        //    no S, no softmax kernel
   int npairs;           // key tile pairs = ceil(ntt / 2)
   float* rowmax_part;   // [ntt*128][npairs]
   float* rowsum_part;   // [ntt*128][npairs]
@@ -70,7 +71,7 @@ struct ScoreParams {
   const int* order;
   int order_stride;
   int softmax_row_begin[ATTN_MAX_HEADS + 1];  // first softmax block of each problem (fused problems: empty range)
-  int* overflow;   // direct heads: set when an exponent leaves the range that bf16 holds without a row shift (the host then re-runs unfused)
+  int* overflow;   // direct heads: set when an exponent leaves the range fp16 holds without a row shift (the host then re-runs unfused)
 };
 
 struct ScorePolicy {
@@ -197,7 +198,7 @@ struct ScorePolicy {
       c.m = m;
       return;
     }
-    // pass B: P = exp2((s - max) * log2(e)/sqrt(D)) in fp16 (direct heads: bf16, max = 0), masked slots = 0; row sums of the rounded values
+    // pass B: P = exp2((s - max) * log2(e)/sqrt(D)) in fp16 (direct heads: max = 0), masked slots = 0; row sums of the rounded values
     uint32_t* scw = reinterpret_cast<uint32_t*>(scr);
     float sum = c.sum;
     if (h.fused == 2) {
@@ -206,11 +207,11 @@ struct ScorePolicy {
       for (int i = 0; i < 32; i += 2) {
         const int kp = kp0 + i;
         const float a0 = v[i] * h.scale_log2e, a1 = v[i + 1] * h.scale_log2e;
-        big |= (a0 > 100.f) | (a1 > 100.f);
-        const float e0 = (kp < nvalid && (kp & owm) < h.ow) ? fast_exp2(fminf(a0, 120.f)) : 0.f;
-        const float e1 = (kp + 1 < nvalid && ((kp + 1) & owm) < h.ow) ? fast_exp2(fminf(a1, 120.f)) : 0.f;
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
-        const float2 f = __bfloat1622float2(hh);
+        big |= (a0 > 15.5f) | (a1 > 15.5f);
+        const float e0 = (kp < nvalid && (kp & owm) < h.ow) ? fast_exp2(fminf(a0, 15.9f)) : 0.f;
+        const float e1 = (kp + 1 < nvalid && ((kp + 1) & owm) < h.ow) ? fast_exp2(fminf(a1, 15.9f)) : 0.f;
+        const __half2 hh = __floats2half2_rn(e0, e1);
+        const float2 f = __half22float2(hh);
         sum += f.x + f.y;
         scw[lane * 17 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
       }
@@ -334,6 +335,7 @@ struct PVParams {
   long long out_off[ATTN_MAX_HEADS];
   const int* order;  // LPT schedule, see ScoreParams
   int order_stride;
+  int* overflow;     // direct heads: range flag shared with the score kernel
 };
 
 struct PVPolicy {
@@ -415,11 +417,14 @@ struct PVPolicy {
       float rs;
       if (h.fused) {
         const float* ps = h.rowsum_part + (size_t)qp * h.npairs;
+        // direct heads: a row whose largest P is below 2^-12 sits in fp16's subnormals — ask for the exact path
+        // (checked after the sum below)
         rs = ps[0];
         for (int j = 1; j < h.npairs; ++j) rs += ps[j];  // fixed order: deterministic
       } else {
         rs = h.rowsum[qp];
       }
+      if (h.fused == 2 && rs < 2.44140625e-4f && p.overflow) *p.overflow = 1;
       c.inv = 1.0f / rs;
       const int tt = toh / h.oh, ohi = toh - tt * h.oh;
       c.base = p.out + p.out_off[t.head] + (((size_t)tt * p.H + ohi * h.ph) * p.W + owi * h.pw) * p.out_pitch + p.coff[t.head];
@@ -558,8 +563,6 @@ struct PV2Policy {
     PVPolicy::epilogue(p, t, c, row, col0, v, scr);
   }
   __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}
-  // instruction-descriptor bits of this tile on top of the kernel's: A (= P) is bf16 for the direct heads (a_format, bits [7,10))
-  __device__ static uint32_t idesc_extra(const Params& p, const Tile& t) { return p.h[t.head].fused == 2 ? (1u << 7) : 0u; }
 };
 
 }  // namespace vsr

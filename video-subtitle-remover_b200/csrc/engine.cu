@@ -161,7 +161,7 @@ struct Ctx {
                                // (measured, profiles/gpu_session_r2_s2_summary.txt: with the field set three conv cases fail)
   bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
-  bool attn_direct = true; // single-pass bf16 P for the heads without split-K (no S, no softmax kernel); VSR_ATTN_DIRECT=0: S + softmax kernel
+  bool attn_direct = true; // single-pass P = exp2(logit) for the heads without split-K (no S, no softmax kernel); VSR_ATTN_DIRECT=0: S + softmax kernel
   bool attn_fused = false; // VSR_ATTN_FUSED=1: two-pass score kernels without S (measured slower: the P pass is epilogue-bound)
   // In-situ profile (vsr_sttn_profile): with `prof` set, every ProfScope brackets its launches with a pair of events on the
   // stream; classes are the VSR_PROF_* ids of include/vsr_b200.h.
@@ -719,6 +719,7 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   sp.totalB2 = workB2;
   ws.overflow.ensure(16);
   sp.overflow = ws.overflow.as<int>();
+  pp.overflow = ws.overflow.as<int>();
   sp.pass = 0;  // pass A: per-tile row maxima (fused problems) / fp32 S slabs (split-K problems)
   if ((c.attn_2cta ? score_work2 : score_work) > 0) {
     ProfScope ps_(c, VSR_PROF_SCORE);
@@ -1313,7 +1314,7 @@ static void compute_area(vsr_sttn* h, int k) {
   G.warm_gen = g_alloc_generation;
 }
 
-// The direct attention heads write P = exp2(logit) in bf16 without a row shift; a logit beyond 2^100 would leave even bf16's range.
+// The direct attention heads write P = exp2(logit) in fp16 without a row shift; fp16 holds that for row maxima between 2^-12 and 2^15.5.
 // Their kernel clamps and raises a flag; the result of such a job must not be used: the caller switches the engine to the unfused
 // path (vsr_sttn_set_option("attn_direct", 0)) and repeats the call (the Python classes do that).  Call with the stream drained.
 static void check_attn_overflow(vsr_sttn* h) {
