@@ -42,12 +42,14 @@ struct AttnHead {
   __half* P;
   float* rowsum;
   int fused;            // 0: split-K slabs of S + softmax kernel; 1: two-pass score kernels (rowmax_part / rowsum_part);
-                        // 2: "direct" — ONE score pass that writes P = exp2(s * log2e / sqrt(D)) without a row shift (softmax is shift
-                        //    invariant; fp16 holds 2^-24 .. 2^16, the range flag below catches rows outside it) + per-tile row sums;
-                        //    no S, no softmax kernel
+                        // 2: "direct" — ONE score pass that writes P = exp2((s - s_self) * log2e / sqrt(D)) + per-tile row sums, where the
+                        //    row shift s_self = q_i . k_i is the token's logit with itself (attn_diag_kernel; softmax is shift invariant):
+                        //    the row maximum is >= it, so every row holds a 1 and nothing under-flows; a key that beats "self" by more
+                        //    than 2^15.5 raises the range flag.  No S, no row-max pass, no softmax kernel
   int npairs;           // key tile pairs = ceil(ntt / 2)
   float* rowmax_part;   // [ntt*128][npairs]
   float* rowsum_part;   // [ntt*128][npairs]
+  float* rowshift;      // [ntt*128] direct heads: q_i . k_i (un-scaled), 0 for pad rows
   int scoreB_begin, scoreB_begin2;  // pass-B work lists (fused problems only)
 };
 
@@ -156,7 +158,7 @@ struct ScorePolicy {
     c.m = -INFINITY;
     c.sum = 0.f;
     if (h.fused == 2) {
-      c.m = 0.f;   // direct: no shift
+      c.m = t.n_cols > 0 ? h.rowshift[t.qi * 128 + row] : 0.f;   // direct: shift by the token's own logit
     } else if (h.fused && p.pass == 1 && t.n_cols > 0) {  // row max = max over the key-tile partials of pass A
       const float* pm = h.rowmax_part + (size_t)(t.qi * 128 + row) * h.npairs;
       float m = pm[0];
@@ -198,7 +200,8 @@ struct ScorePolicy {
       c.m = m;
       return;
     }
-    // pass B: P = exp2((s - max) * log2(e)/sqrt(D)) in fp16 (direct heads: max = 0), masked slots = 0; row sums of the rounded values
+    // pass B: P = exp2((s - max) * log2(e)/sqrt(D)) in fp16 (direct heads: the token's own logit instead of the max), masked slots = 0;
+    // row sums of the rounded values
     uint32_t* scw = reinterpret_cast<uint32_t*>(scr);
     float sum = c.sum;
     if (h.fused == 2) {
@@ -206,10 +209,11 @@ struct ScorePolicy {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const int kp = kp0 + i;
-        const float a0 = v[i] * h.scale_log2e, a1 = v[i + 1] * h.scale_log2e;
-        big |= (a0 > 15.5f) | (a1 > 15.5f);
-        const float e0 = (kp < nvalid && (kp & owm) < h.ow) ? fast_exp2(fminf(a0, 15.9f)) : 0.f;
-        const float e1 = (kp + 1 < nvalid && ((kp + 1) & owm) < h.ow) ? fast_exp2(fminf(a1, 15.9f)) : 0.f;
+        const float a0 = (v[i] - c.m) * h.scale_log2e, a1 = (v[i + 1] - c.m) * h.scale_log2e;
+        const bool ok0 = kp < nvalid && (kp & owm) < h.ow, ok1 = kp + 1 < nvalid && ((kp + 1) & owm) < h.ow;
+        big |= (ok0 && a0 > 15.5f) | (ok1 && a1 > 15.5f);
+        const float e0 = ok0 ? fast_exp2(fminf(a0, 15.9f)) : 0.f;
+        const float e1 = ok1 ? fast_exp2(fminf(a1, 15.9f)) : 0.f;
         const __half2 hh = __floats2half2_rn(e0, e1);
         const float2 f = __half22float2(hh);
         sum += f.x + f.y;
@@ -324,6 +328,41 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
   }
 }
 
+// Direct heads: the row shift s_self[qp] = q_qp . k_qp over the token's ph*pw patch pixels x 64 channels (un-scaled, fp32), 0 for pad slots.
+// One warp per padded token; lane = channel pair, loop over the patch pixels: 128-byte coalesced reads of Q and K straight from the NHWC
+// projection buffer (the same addresses the TMA views of the score kernel read).  HBM/L2-bound: 2 x 128 B per pixel and head.
+struct DiagParams {
+  const __half* q[ATTN_MAX_HEADS];   // base of this problem's frames + q channel offset of the head
+  const __half* k[ATTN_MAX_HEADS];
+  AttnHead h[ATTN_MAX_HEADS];
+  int row_begin[ATTN_MAX_HEADS + 1]; // prefix sums of ntt*128 over the direct problems (others: empty)
+  int nheads, pitch, W;              // qkv pixel pitch (elements), feature-map width
+};
+__global__ void __launch_bounds__(256) attn_diag_kernel(DiagParams p) {
+  const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  int e = 0;
+  while (e + 1 < p.nheads && gw >= p.row_begin[e + 1]) ++e;
+  const AttnHead& h = p.h[e];
+  const int qp = gw - p.row_begin[e];
+  if (h.fused != 2 || qp >= h.ntt * 128) return;
+  const int toh = qp / h.owp, owi = qp - toh * h.owp;
+  float acc = 0.f;
+  if (owi < h.ow && toh < h.toh_total) {
+    const int tt = toh / h.oh, ohi = toh - tt * h.oh;
+    const size_t pix0 = ((size_t)tt * h.oh * h.ph + (size_t)ohi * h.ph) * p.W + (size_t)owi * h.pw;   // H = oh * ph
+    for (int py = 0; py < h.ph; ++py)
+      for (int px = 0; px < h.pw; ++px) {
+        const size_t o = (pix0 + (size_t)py * p.W + px) * p.pitch + 2 * lane;
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(p.q[e] + o));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(p.k[e] + o));
+        acc = fmaf(a.x, b.x, fmaf(a.y, b.y, acc));
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  }
+  if (lane == 0) h.rowshift[qp] = acc;
+}
+
 struct PVParams {
   CUtensorMap pmap[ATTN_MAX_HEADS], vmap[ATTN_MAX_HEADS];
   AttnHead h[ATTN_MAX_HEADS];
@@ -424,7 +463,7 @@ struct PVPolicy {
       } else {
         rs = h.rowsum[qp];
       }
-      if (h.fused == 2 && rs < 2.44140625e-4f && p.overflow) *p.overflow = 1;
+      if (h.fused == 2 && !(rs >= 0.5f) && p.overflow) *p.overflow = 2;   // a direct row always holds its own 1: anything else is a defect
       c.inv = 1.0f / rs;
       const int tt = toh / h.oh, ohi = toh - tt * h.oh;
       c.base = p.out + p.out_off[t.head] + (((size_t)tt * p.H + ohi * h.ph) * p.W + owi * h.pw) * p.out_pitch + p.coff[t.head];

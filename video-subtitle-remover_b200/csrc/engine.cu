@@ -526,7 +526,8 @@ struct TileSchedule {
 };
 struct AttnWorkspace {
   DevBuf S[ATTN_MAX_HEADS], P[ATTN_MAX_HEADS], rowsum[ATTN_MAX_HEADS], rowmax_part[ATTN_MAX_HEADS], rowsum_part[ATTN_MAX_HEADS];
-  DevBuf overflow;   // [0]: a direct head met a logit beyond the bf16-safe range
+  DevBuf overflow;   // [0]: a direct head met a key that beats the token's own logit by more than fp16 holds
+  DevBuf rowshift[ATTN_MAX_HEADS];
   std::map<std::string, std::unique_ptr<TileSchedule>> schedules;  // LPT tile orders, keyed by the problem shapes
 };
 
@@ -661,6 +662,8 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
     h.P = ws.P[s].as<__half>();
     h.rowsum = ws.rowsum[s].as<float>();
     h.rowmax_part = ws.rowmax_part[s].as<float>();
+    ws.rowshift[s].ensure(rows * sizeof(float));
+    h.rowshift = ws.rowshift[s].as<float>();
     h.rowsum_part = ws.rowsum_part[s].as<float>();
     if ((int)rows > max_rows) max_rows = (int)rows;
     // 5-D views {64 ch, px, ow, py, toh} of this segment's frames
@@ -720,6 +723,28 @@ static void run_attention(Ctx& c, AttnWorkspace& ws, const __half* qkv, int pitc
   ws.overflow.ensure(16);
   sp.overflow = ws.overflow.as<int>();
   pp.overflow = ws.overflow.as<int>();
+  if (workB > 0 && c.attn_direct) {   // row shifts of the direct heads: each token's logit with itself
+    DiagParams dp;
+    memset(&dp, 0, sizeof(dp));
+    int rows_total = 0;
+    for (int s2 = 0; s2 < nent; ++s2) {
+      dp.row_begin[s2] = rows_total;
+      dp.h[s2] = sp.h[s2];
+      const AttnSegment& sg = segs[ents[s2].seg];
+      const __half* base = qkv + (size_t)sg.first * H * W * pitch;
+      dp.q[s2] = base + q_off + ents[s2].patch * dk;
+      dp.k[s2] = base + k_off + ents[s2].patch * dk;
+      if (sp.h[s2].fused == 2) rows_total += sp.h[s2].ntt * 128;
+    }
+    for (int s2 = nent; s2 <= ATTN_MAX_HEADS; ++s2) dp.row_begin[s2] = rows_total;
+    dp.nheads = nent; dp.pitch = pitch; dp.W = W;
+    if (rows_total > 0) {
+      ProfScope ps_(c, VSR_PROF_SOFTMAX);
+      attn_diag_kernel<<<(rows_total * 32 + 255) / 256, 256, 0, c.stream>>>(dp);
+      CK(cudaGetLastError());
+      ++c.launches;
+    }
+  }
   sp.pass = 0;  // pass A: per-tile row maxima (fused problems) / fp32 S slabs (split-K problems)
   if ((c.attn_2cta ? score_work2 : score_work) > 0) {
     ProfScope ps_(c, VSR_PROF_SCORE);
@@ -1314,7 +1339,7 @@ static void compute_area(vsr_sttn* h, int k) {
   G.warm_gen = g_alloc_generation;
 }
 
-// The direct attention heads write P = exp2(logit) in fp16 without a row shift; fp16 holds that for row maxima between 2^-12 and 2^15.5.
+// The direct attention heads write P = exp2(logit - own logit) in fp16: exact unless some key beats the token's own logit by > 2^15.5.
 // Their kernel clamps and raises a flag; the result of such a job must not be used: the caller switches the engine to the unfused
 // path (vsr_sttn_set_option("attn_direct", 0)) and repeats the call (the Python classes do that).  Call with the stream drained.
 static void check_attn_overflow(vsr_sttn* h) {
