@@ -329,8 +329,9 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(ScoreParams p) {
 }
 
 // Direct heads: the row shift s_self[qp] = q_qp . k_qp over the token's ph*pw patch pixels x 64 channels (un-scaled, fp32), 0 for pad slots.
-// One warp per padded token; lane = channel pair, loop over the patch pixels: 128-byte coalesced reads of Q and K straight from the NHWC
-// projection buffer (the same addresses the TMA views of the score kernel read).  HBM/L2-bound: 2 x 128 B per pixel and head.
+// One warp per padded token; a lane reads 16 bytes (8 channels), 8 lanes cover the 64 channels of a pixel, the warp 4 patch pixels per step,
+// 4 steps unrolled (up to 16 pixels x 2 tensors x 128 B in flight per warp): reads straight from the NHWC projection buffer (the same
+// addresses the TMA views of the score kernel read).  HBM/L2-bound: 2 x 128 B per pixel and head.
 struct DiagParams {
   const __half* q[ATTN_MAX_HEADS];   // base of this problem's frames + q channel offset of the head
   const __half* k[ATTN_MAX_HEADS];
@@ -338,6 +339,17 @@ struct DiagParams {
   int row_begin[ATTN_MAX_HEADS + 1]; // prefix sums of ntt*128 over the direct problems (others: empty)
   int nheads, pitch, W;              // qkv pixel pitch (elements), feature-map width
 };
+__device__ __forceinline__ float dot8_f16(const uint4& a, const uint4& b) {
+  const __half2* x = reinterpret_cast<const __half2*>(&a);
+  const __half2* y = reinterpret_cast<const __half2*>(&b);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 u = __half22float2(x[i]), v = __half22float2(y[i]);
+    acc = fmaf(u.x, v.x, fmaf(u.y, v.y, acc));
+  }
+  return acc;
+}
 __global__ void __launch_bounds__(256) attn_diag_kernel(DiagParams p) {
   const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   int e = 0;
@@ -350,13 +362,24 @@ __global__ void __launch_bounds__(256) attn_diag_kernel(DiagParams p) {
   if (owi < h.ow && toh < h.toh_total) {
     const int tt = toh / h.oh, ohi = toh - tt * h.oh;
     const size_t pix0 = ((size_t)tt * h.oh * h.ph + (size_t)ohi * h.ph) * p.W + (size_t)owi * h.pw;   // H = oh * ph
-    for (int py = 0; py < h.ph; ++py)
-      for (int px = 0; px < h.pw; ++px) {
-        const size_t o = (pix0 + (size_t)py * p.W + px) * p.pitch + 2 * lane;
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(p.q[e] + o));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(p.k[e] + o));
-        acc = fmaf(a.x, b.x, fmaf(a.y, b.y, acc));
+    const int sub = lane >> 3, ch = (lane & 7) * 8, npos = h.npos;
+    const __half* qb = p.q[e] + ch;
+    const __half* kb = p.k[e] + ch;
+    for (int i0 = 0; i0 < npos; i0 += 16) {
+      uint4 a[4], b[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 4 * u + sub;
+        ok[u] = i < npos;
+        const int py = ok[u] ? i / h.pw : 0, px = ok[u] ? i - py * h.pw : 0;
+        const size_t o = (pix0 + (size_t)py * p.W + px) * p.pitch;
+        a[u] = ok[u] ? *reinterpret_cast<const uint4*>(qb + o) : make_uint4(0, 0, 0, 0);
+        b[u] = ok[u] ? *reinterpret_cast<const uint4*>(kb + o) : make_uint4(0, 0, 0, 0);
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += dot8_f16(a[u], b[u]);
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   }

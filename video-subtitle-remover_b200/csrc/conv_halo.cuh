@@ -25,17 +25,18 @@ namespace vsr {
 
 constexpr int HALO_NA = 2;                  // A ring depth
 constexpr int HALO_NB = 7;                  // B ring depth (at most; ConvParams::halo_nb stages are used)
-constexpr int HALO_B_BYTES = 128 * 128;
+constexpr int HALO_B_BYTES = 128 * 128;      // one B stage of the 256-wide kernel (this CTA's 128 weight rows x 64 K); BN / 2 rows in general
+__host__ __device__ constexpr int halo_b_bytes(int bn) { return (bn / 2) * 128; }
 constexpr int HALO_EPI_WARPS = 8;           // two per TMEM lane quarter, 128 columns each
 constexpr int HALO_THREADS = 64 + 32 * HALO_EPI_WARPS;
 constexpr int HALO_SCRATCH = HALO_EPI_WARPS * 4096;   // static: the epilogue's transposition scratch (conv_store_coalesced)
 __host__ __device__ constexpr int halo_a_bytes(int halo) { return 16 * (16 + 2 * halo) * 128; }   // haloed rows x 16 lines x 128 B
 // B stages that fit beside the two A buffers, the scratch and the barriers in 227 KB
-inline int halo_b_stages(int halo) {
+inline int halo_b_stages(int halo, int bn = 256) {
   const int room = 232448 - HALO_SCRATCH - 512 - 1024 - HALO_NA * halo_a_bytes(halo);
-  return room / HALO_B_BYTES < HALO_NB ? room / HALO_B_BYTES : HALO_NB;
+  return room / halo_b_bytes(bn) < HALO_NB ? room / halo_b_bytes(bn) : HALO_NB;
 }
-inline int halo_smem_bytes(int halo) { return HALO_NA * halo_a_bytes(halo) + halo_b_stages(halo) * HALO_B_BYTES + 1024; }
+inline int halo_smem_bytes(int halo, int bn = 256) { return HALO_NA * halo_a_bytes(halo) + halo_b_stages(halo, bn) * halo_b_bytes(bn) + 1024; }
 
 enum : uint32_t { ERR_HALO_PROD_A = 0x500, ERR_HALO_PROD_B = 0x600, ERR_HALO_MMA_A = 0x700, ERR_HALO_MMA_B = 0x800,
                   ERR_HALO_MMA_T = 0x900, ERR_HALO_EPI = 0xA00 };
@@ -61,11 +62,16 @@ __device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const CUtensorM
 // CL = 2: one CTA pair per cluster.  CL = 4: two pairs per cluster work on neighbouring pixel tiles of the same Cout tile and share the
 // weights: every CTA fetches a quarter of the 256 x 64 weight chunk (64 rows) and multicasts it to the CTA of the other pair that
 // needs the same half, so the L2 -> SM weight traffic per CTA halves (16 -> 8 KB per chunk and tap).
-template <int CL>
+// BN = Cout tile of the pair (256, 128 or 64): each CTA holds BN / 2 weight rows per stage; the narrow tiles serve the decoder convs
+// (256 -> 128, 128 -> 64, 64 -> 64), whose per-tap kernels re-fetched a 16 KB A box for as little as 1 MFLOP.
+template <int CL, int BN>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvParams prm) {
   static_assert(CL == 2 || CL == 4, "cluster of one or two CTA pairs");
-  using Base = ConvPolicy<256>;
-  constexpr uint32_t TMEM_COLS = 512;
+  static_assert(BN == 256 || BN == 128 || BN == 64, "Cout tile");
+  static_assert(CL == 2 || BN == 256, "the multicast variant is built for 256-wide tiles");
+  using Base = ConvPolicy<BN>;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr uint32_t B_BYTES = (uint32_t)halo_b_bytes(BN);
   constexpr int NPAIR = CL / 2;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[HALO_NA], a_empty[HALO_NA], b_full[HALO_NB], b_empty[HALO_NB], bar_tfull[2], bar_tempty[2];
@@ -114,12 +120,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) co
   const int ngroups = ((pair_tiles_m + NPAIR - 1) / NPAIR) * prm.n_tiles;
   const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
   auto tile_of = [&](int g) {   // this CTA's 128-pixel tile of group g (a dummy beyond the end: TMA zero-fills frame index T)
-    Base::Tile t;
+    typename Base::Tile t;
     const int n = g % prm.n_tiles;
     int sub = ((g / prm.n_tiles) * NPAIR + (int)pair) * 2 + (int)rank;
-    t.n0 = n * 256;
+    t.n0 = n * BN;
     t.num_k = prm.ntaps * prm.cin_chunks;
-    t.n_cols = 256;
+    t.n_cols = BN;
     if (sub >= sub_tiles) {
       t.t = prm.T; t.y0 = 0; t.x0 = 0;
       return t;
@@ -135,7 +141,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) co
     if (elect_one()) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
       for (int g = first; g < ngroups; g += step) {
-        const Base::Tile tile = tile_of(g);
+        const typename Base::Tile tile = tile_of(g);
         for (int kc = 0; kc < prm.cin_chunks; ++kc) {
           mbar_wait(smem_u32(&a_empty[as]), aph ^ 1, ERR_HALO_PROD_A | as);
           if (rank == 0) mbar_expect_tx(smem_u32(&a_full[as]), 2u * a_bytes);
@@ -144,14 +150,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) co
           if (++as == HALO_NA) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < prm.ntaps; ++tap) {
             mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, ERR_HALO_PROD_B | bs);
-            if (rank == 0) mbar_expect_tx(smem_u32(&b_full[bs]), 2u * HALO_B_BYTES);
+            if (rank == 0) mbar_expect_tx(smem_u32(&b_full[bs]), 2u * B_BYTES);
             const uint32_t full = mapa_cluster(smem_u32(&b_full[bs]), leader);
             const int k0 = (tap * prm.cin_chunks + kc) * 64;
             if (CL == 4) {   // rows [pair * 64, +64) of this CTA's half, to the CTAs of both pairs with the same in-pair rank
-              tma_load_2d_2sm_mc(sB0 + bs * HALO_B_BYTES + pair * (HALO_B_BYTES / 2), &prm.w_map_quarter, full, k0,
+              tma_load_2d_2sm_mc(sB0 + bs * B_BYTES + pair * (B_BYTES / 2), &prm.w_map_quarter, full, k0,
                                  tile.n0 + (int)rank * 128 + (int)pair * 64, (uint16_t)(5u << rank));
             } else {
-              tma_load_2d_2sm(sB0 + bs * HALO_B_BYTES, &prm.w_map_half, full, k0, tile.n0 + (int)rank * 128);
+              tma_load_2d_2sm(sB0 + bs * B_BYTES, &prm.w_map_half, full, k0, tile.n0 + (int)rank * (BN / 2));
             }
             if (++bs == NB) { bs = 0; bph ^= 1; }
           }
@@ -162,11 +168,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) co
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0, acc = 0, accph = 0;
-      const uint32_t idesc = umma_idesc_f16(256, 256, 0, 0);
+      const uint32_t idesc = umma_idesc_f16(256, BN, 0, 0);
       for (int g = first; g < ngroups; g += step) {
         mbar_wait(smem_u32(&bar_tempty[acc]), accph ^ 1, ERR_HALO_MMA_T | acc);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kc = 0; kc < prm.cin_chunks; ++kc) {
           mbar_wait(smem_u32(&a_full[as]), aph, ERR_HALO_MMA_A | as);
           tc_fence_after();
@@ -174,7 +180,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) co
           for (int tap = 0; tap < prm.ntaps; ++tap) {
             mbar_wait(smem_u32(&b_full[bs]), bph, ERR_HALO_MMA_B | bs);
             tc_fence_after();
-            const uint32_t sB = sB0 + bs * HALO_B_BYTES;
+            const uint32_t sB = sB0 + bs * B_BYTES;
             const uint32_t a_tap = sA + (uint32_t)(((int)prm.tap_dy[tap] + halo) * 16 + ((int)prm.tap_dx[tap] + halo)) * 128u;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
@@ -196,15 +202,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) co
     const uint32_t ew = warp - 2;
     const uint32_t row = quarter * 32 + lane;
     float* scr = epi_scratch + ew * 1024;
-    const int c_begin = (int)(ew >> 2) * 128;
+    const int c_begin = (int)(ew >> 2) * (BN / 2);
     uint32_t acc = 0, accph = 0;
     for (int g = first; g < ngroups; g += step) {
-      const Base::Tile tile = tile_of(g);
-      Base::RowCtx ctx = Conv2Policy::row_begin(prm, tile, row);
+      const typename Base::Tile tile = tile_of(g);
+      typename Base::RowCtx ctx = Base::row_begin(prm, tile, row);
+      ctx.valid = ctx.valid && tile.t < prm.T;   // dummy half of an odd pair
       mbar_wait(smem_u32(&bar_tfull[acc]), accph, ERR_HALO_EPI | acc);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * 256;
-      for (int c = c_begin; c < c_begin + 128; c += 32) {
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
+      for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
         Base::epilogue(prm, tile, ctx, row, c, v, scr);

@@ -159,6 +159,7 @@ struct Ctx {
   int conv_cluster = 2;    // VSR_CONV_CLUSTER=4: two CTA pairs per cluster share the weights by TMA multicast (conv_halo.cuh)
   int conv_halo_base_off = 0;  // the descriptor's base-offset field stays 0: the tensor core swizzles on absolute smem address bits
                                // (measured, profiles/gpu_session_r2_s2_summary.txt: with the field set three conv cases fail)
+  bool direct_conv_smem = true;  // VSR_DIRECT_CONV_SMEM=0: the tiny-channel direct conv without shared-memory weights (A/B switch)
   bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
   bool attn_direct = true; // single-pass P = exp2(logit) for the heads without split-K (no S, no softmax kernel); VSR_ATTN_DIRECT=0: S + softmax kernel
@@ -443,7 +444,7 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   if (!(io.flags & CONV_FINAL)) REQUIRE(L.cout % 8 == 0, "Cout must be a multiple of 8");
   if (io.out32) REQUIRE(L.cout == L.cout_pad, "fp32 stream needs Cout == padded Cout");
   const int ntiles = p.T * p.tiles_y * p.tiles_x * p.n_tiles;
-  if (L.bn == 256 && c.conv_2cta && c.conv_halo && !(io.flags & CONV_FINAL) && L.ntaps > 1 && io.W >= 8) {
+  if ((L.bn == 256 || L.bn == 128 || L.bn == 64) && c.conv_2cta && c.conv_halo && !(io.flags & (CONV_FINAL | CONV_S2D_STORE)) && L.ntaps > 1 && io.W >= 8) {
     int halo = 0;
     for (int i = 0; i < L.ntaps; ++i) halo = std::max(halo, std::max(std::abs((int)L.dy[i]), std::abs((int)L.dx[i])));
     if (halo <= 4) {
@@ -456,23 +457,27 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
       p.in_map = make_map_f16(io.in, 4, dims, str, box);
       const uint64_t wd[2] = {(uint64_t)L.K, (uint64_t)L.cout_pad};
       const uint64_t ws[1] = {(uint64_t)L.K * 2};
-      const uint32_t wb[2] = {64, 128};
+      const uint32_t wb[2] = {64, (uint32_t)(L.bn / 2)};
       p.w_map_half = make_map_f16(L.w.p, 2, wd, ws, wb);
       p.tile_w = 8; p.tile_h = valid_h;
       p.tiles_x = (io.W + 7) / 8;
       p.tiles_y = tiles_y;
       p.halo = halo;
       p.halo_base_off = c.conv_halo_base_off;
-      p.halo_nb = halo_b_stages(halo);
-      const int smem = halo_smem_bytes(halo);
-      static int configured_smem = 0, max_clusters4 = 0;
-      if (smem > configured_smem) {
-        CK(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured_smem = smem;
-      }
+      p.halo_nb = halo_b_stages(halo, L.bn);
+      const int smem = halo_smem_bytes(halo, L.bn);
+      static int configured_smem[4] = {0, 0, 0, 0}, max_clusters4 = 0;
+      auto configure = [&](int slot, const void* fn) {
+        if (smem > configured_smem[slot]) {
+          CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          configured_smem[slot] = smem;
+        }
+      };
       const int pair_tiles_m = (p.T * p.tiles_y * p.tiles_x + 1) / 2;
-      if (c.conv_cluster == 4) {
+      const int groups = pair_tiles_m * p.n_tiles;
+      const int grid = 2 * std::min(groups, c.sms / 2);
+      if (L.bn == 256 && c.conv_cluster == 4) {
+        configure(3, (const void*)conv_halo_kernel<4, 256>);
         if (max_clusters4 == 0) {
           // how many 4-CTA clusters the device holds at once (GPCs with an odd number of TPCs leave SMs without a cluster)
           cudaLaunchConfig_t cfg = {};
@@ -481,7 +486,7 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
           at[0].id = cudaLaunchAttributeClusterDimension;
           at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
           cfg.attrs = at; cfg.numAttrs = 1;
-          if (cudaOccupancyMaxActiveClusters(&max_clusters4, conv_halo_kernel<4>, &cfg) != cudaSuccess || max_clusters4 <= 0) {
+          if (cudaOccupancyMaxActiveClusters(&max_clusters4, conv_halo_kernel<4, 256>, &cfg) != cudaSuccess || max_clusters4 <= 0) {
             cudaGetLastError();
             max_clusters4 = c.sms / 4;
           }
@@ -489,13 +494,17 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
         }
         const uint32_t qb[2] = {64, 64};
         p.w_map_quarter = make_map_f16(L.w.p, 2, wd, ws, qb);
-        const int groups = ((pair_tiles_m + 1) / 2) * p.n_tiles;
-        const int grid = 4 * std::min(groups, max_clusters4);
-        conv_halo_kernel<4><<<grid, HALO_THREADS, smem, c.stream>>>(p);
+        const int groups4 = ((pair_tiles_m + 1) / 2) * p.n_tiles;
+        conv_halo_kernel<4, 256><<<4 * std::min(groups4, max_clusters4), HALO_THREADS, smem, c.stream>>>(p);
+      } else if (L.bn == 256) {
+        configure(0, (const void*)conv_halo_kernel<2, 256>);
+        conv_halo_kernel<2, 256><<<grid, HALO_THREADS, smem, c.stream>>>(p);
+      } else if (L.bn == 128) {
+        configure(1, (const void*)conv_halo_kernel<2, 128>);
+        conv_halo_kernel<2, 128><<<grid, HALO_THREADS, smem, c.stream>>>(p);
       } else {
-        const int groups = pair_tiles_m * p.n_tiles;
-        const int grid = 2 * std::min(groups, c.sms / 2);
-        conv_halo_kernel<2><<<grid, HALO_THREADS, smem, c.stream>>>(p);
+        configure(2, (const void*)conv_halo_kernel<2, 64>);
+        conv_halo_kernel<2, 64><<<grid, HALO_THREADS, smem, c.stream>>>(p);
       }
       CK(cudaGetLastError());
       ++c.launches;
@@ -2122,6 +2131,8 @@ int vsr_rt_create(vsr_rt_t** out, int device) {
     h->ctx.device = device;
     h->ctx.sms = prop.multiProcessorCount;
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
+    h->ctx.direct_conv_smem = env_flag("VSR_DIRECT_CONV_SMEM", true);
+    h->ctx.conv_halo = env_flag("VSR_RT_CONV_HALO", false);   // haloed-tile convs in the graph runtime: off until every network's GPU tests ran with it
     CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
     h->flag.ensure(16);
     *out = h;
@@ -3092,8 +3103,19 @@ int vsr_rt_conv_ex(vsr_rt_t* h, int layer_id, uint64_t in_ptr, int T, int H, int
         REQUIRE(out_coff == 0 && out_pitch >= L.cout_pitch && out_pitch % 8 == 0, "direct conv output pitch");
         const int OH = (H + 2 * L.pad_t - L.kh) / L.stride + 1, OW = (W + 2 * L.pad_l - L.kw) / L.stride + 1;
         const size_t n = (size_t)T * OH * OW * (L.cout_pitch / 8);
-        rt_direct_conv_kernel<<<blocks_for(n), 256, 0, s>>>(in, T, H, W, L.cin_pitch, L.cin, L.w32.as<float>(), L.b32.as<float>(), L.kh, L.kw,
-                                                            L.stride, L.pad_t, L.pad_l, relu, out, OH, OW, L.cout_pitch, out_pitch, sc);
+        const size_t wbytes = (size_t)L.kh * L.kw * L.cin * L.cout_pitch * sizeof(float);
+        if (wbytes <= 96 * 1024 && c.direct_conv_smem) {   // weights in shared memory, two pixels per thread
+          static size_t configured = 0;
+          if (wbytes > 48 * 1024 && wbytes > configured) {
+            CK(cudaFuncSetAttribute(rt_direct_conv_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            configured = 96 * 1024;
+          }
+          const size_t n2 = (size_t)T * OH * ((OW + 1) / 2) * (L.cout_pitch / 8);
+          rt_direct_conv_smem_kernel<<<blocks_for(n2), 256, wbytes, s>>>(in, T, H, W, L.cin_pitch, L.cin, L.w32.as<float>(), L.b32.as<float>(), L.kh,
+                                                                        L.kw, L.stride, L.pad_t, L.pad_l, relu, out, OH, OW, L.cout_pitch, out_pitch, sc);
+        } else
+          rt_direct_conv_kernel<<<blocks_for(n), 256, 0, s>>>(in, T, H, W, L.cin_pitch, L.cin, L.w32.as<float>(), L.b32.as<float>(), L.kh, L.kw,
+                                                              L.stride, L.pad_t, L.pad_l, relu, out, OH, OW, L.cout_pitch, out_pitch, sc);
         CK(cudaGetLastError());
         ++c.launches;
         break;

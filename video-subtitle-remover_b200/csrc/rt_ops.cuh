@@ -519,6 +519,59 @@ __global__ void __launch_bounds__(256) rt_direct_conv_kernel(const __half* __res
   rt_store8(acc, bias + c8 * 8, sc, relu, out + (idx / c8n) * out_pitch + c8 * 8);
 }
 
+// The same direct conv with its weights in shared memory and two horizontally adjacent output pixels per thread: the kernel above reads
+// every weight from global memory for every FMA group (one L1 load per FMA), which made the 5 -> 64 first layer of the ProPainter encoder
+// and RAFT's 7x7 3 -> 64 stem cost milliseconds at full resolution (profiles/launches_r2_propainter.md: 32 % of the pipeline's kernel
+// time).  Here a block stages the kh*kw*cin*cout_p weights once (dynamic smem, fp32), a thread keeps 2 x 8 accumulators and feeds 16
+// FMAs from two 16-byte shared loads (warp lanes with the same channel group broadcast).  Same arithmetic order per output as above.
+__global__ void __launch_bounds__(256) rt_direct_conv_smem_kernel(const __half* __restrict__ in, int T, int H, int W, int cin_p, int cin,
+                                                                  const float* __restrict__ wgt, const float* __restrict__ bias, int kh, int kw,
+                                                                  int stride, int pad_t, int pad_l, int relu, __half* __restrict__ out, int OH,
+                                                                  int OW, int cout_p, int out_pitch, RtScale sc) {
+  extern __shared__ __align__(16) float sw[];
+  const int nw = kh * kw * cin * cout_p;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = wgt[i];
+  __syncthreads();
+  const int c8n = cout_p >> 3, OWp = (OW + 1) >> 1;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)T * OH * OWp * c8n;
+  if (idx >= total) return;
+  const int c8 = idx % c8n;
+  size_t r = idx / c8n;
+  const int ox = (int)(r % OWp) * 2;
+  r /= OWp;
+  const int oy = r % OH;
+  const int t = r / OH;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int iy = oy * stride + ky - pad_t;
+    if (iy < 0 || iy >= H) continue;
+    const __half* row = in + ((size_t)t * H + iy) * W * cin_p;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int ix0 = ox * stride + kx - pad_l, ix1 = ix0 + stride;
+      const bool ok0 = ix0 >= 0 && ix0 < W, ok1 = ix1 >= 0 && ix1 < W;
+      if (!ok0 && !ok1) continue;
+      const __half* p0 = row + (size_t)(ok0 ? ix0 : 0) * cin_p;
+      const __half* p1 = row + (size_t)(ok1 ? ix1 : 0) * cin_p;
+      const float* wr = sw + (size_t)((ky * kw + kx) * cin) * cout_p + c8 * 8;
+      for (int ci = 0; ci < cin; ++ci) {
+        const float v0 = ok0 ? __half2float(p0[ci]) : 0.f, v1 = ok1 ? __half2float(p1[ci]) : 0.f;
+        const float4 w0 = *reinterpret_cast<const float4*>(wr + (size_t)ci * cout_p);
+        const float4 w1 = *reinterpret_cast<const float4*>(wr + (size_t)ci * cout_p + 4);
+        a0[0] = fmaf(v0, w0.x, a0[0]); a0[1] = fmaf(v0, w0.y, a0[1]); a0[2] = fmaf(v0, w0.z, a0[2]); a0[3] = fmaf(v0, w0.w, a0[3]);
+        a0[4] = fmaf(v0, w1.x, a0[4]); a0[5] = fmaf(v0, w1.y, a0[5]); a0[6] = fmaf(v0, w1.z, a0[6]); a0[7] = fmaf(v0, w1.w, a0[7]);
+        a1[0] = fmaf(v1, w0.x, a1[0]); a1[1] = fmaf(v1, w0.y, a1[1]); a1[2] = fmaf(v1, w0.z, a1[2]); a1[3] = fmaf(v1, w0.w, a1[3]);
+        a1[4] = fmaf(v1, w1.x, a1[4]); a1[5] = fmaf(v1, w1.y, a1[5]); a1[6] = fmaf(v1, w1.z, a1[6]); a1[7] = fmaf(v1, w1.w, a1[7]);
+      }
+    }
+  }
+  const size_t opix = ((size_t)t * OH + oy) * OW + ox;
+  rt_store8(a0, bias + c8 * 8, sc, relu, out + opix * out_pitch + c8 * 8);
+  if (ox + 1 < OW) rt_store8(a1, bias + c8 * 8, sc, relu, out + (opix + 1) * out_pitch + c8 * 8);
+}
+
 // conv2d_transpose 2x2 stride 2 (no overlap): out[2y+dy][2x+dx][co] = bias[co] + sum_ci in[y][x][ci] * w[ci][co][dy][dx].
 // weights repacked as [dy*2+dx][cin][cout_p] fp32.  One thread per (output pixel, 8 output channels).
 __global__ void __launch_bounds__(256) rt_deconv2x2_kernel(const __half* __restrict__ in, int T, int H, int W, int cin_p, int cin,

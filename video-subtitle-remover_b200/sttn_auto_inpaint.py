@@ -241,7 +241,7 @@ class STTNInpaint:
         f % world == rank are written into `frames[f]` in place (the other frames are left as they are on this rank); returns those
         frame indices.  Window by window the arithmetic is the single-GPU one and the blend is replayed in schedule order; the output
         differs from the unsharded call only through the summation order of the split-K attention heads, which depends on which windows
-        share a launch (measured: <= 1 grey level on isolated pixels; with world = 1 bit-identical)."""
+        share a launch (measured: one grey level on about 1 % of the pixels, never more than two; with world = 1 bit-identical)."""
         frames = list(frames)
         if not frames:
             return []
