@@ -144,7 +144,7 @@ def test_graph_replay_across_batch_lengths(capi, monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(got, want[i])), f"job {i} differs from the eager path"
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("world", [1, 2])
 def test_window_sharded_chunk_equals_single_engine(capi, world):
     """One chunk with its windows dealt over `world` ranks (vsr_sttn_shard_*): every rank is its own engine (here: threads on one GPU, the two
     all-gathers done by device-to-device copies between the engines' exchange buffers); reference-frame features exchanged, window
@@ -186,11 +186,12 @@ def test_window_sharded_chunk_equals_single_engine(capi, world):
             errors.append(e)
             barrier.abort()
 
-    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in threads:
         t.start()
     for t in threads:
-        t.join()
+        t.join(timeout=240)
+    assert not any(t.is_alive() for t in threads), "a rank did not finish"
     assert not errors, errors
     for rank in range(world):
         for f in range(T):

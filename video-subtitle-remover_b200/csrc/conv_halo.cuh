@@ -76,7 +76,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) co
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[HALO_NA], a_empty[HALO_NA], b_full[HALO_NB], b_empty[HALO_NB], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float epi_scratch[HALO_SCRATCH / 4];
+  __shared__ __align__(1024) float epi_scratch[HALO_SCRATCH / 4];
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -221,6 +221,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(HALO_THREADS, 1) co
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_tempty[acc]), leader));
       if (++acc == 2) { acc = 0; accph ^= 1; }
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the epilogue's TMA stores read this CTA's smem: finished before exit
   }
 
   tc_fence_before();

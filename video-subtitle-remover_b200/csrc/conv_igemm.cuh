@@ -17,6 +17,7 @@ enum ConvFlags : int {
   CONV_S2D_STORE = 4,  // store out16 space-to-depth: [T, H/2, W/2, 4*Cout], channel = (y&1)*2*Cout + (x&1)*Cout + c
   CONV_RELU = 0x100,   // plain ReLU after bias (graph runtime)
   CONV_SCALED = 0x200, // out = acc * alpha + bias * bias_scale, fp16 overflow reported through *overflow (graph runtime)
+  CONV_TMA_STORE = 0x400,  // fp16 output through a smem-staged TMA store (out_map), see conv_store_tma
   CONV_FINAL = 8,      // decoder.6: tanh -> (x+1)/2*255 -> trunc u8 -> first visit store / 0.5-0.5 blend into comps
 };
 
@@ -55,7 +56,55 @@ struct ConvParams {
   // haloed-tile kernel (conv_halo.cuh): halo = max |tap offset|; in_map is then the box {64, 16, 16 + 2*halo, 1}, tile_w = 8 and
   // tile_h = the rows of the 16-row tile that are stored (tiles advance by tile_h); base_off = 0 leaves the descriptor's base-offset 0
   int halo, halo_base_off, halo_nb;
+  // CONV_TMA_STORE: the fp16 output tensor as a 4-D map {cout, W, H, T} with box {32 ch, tile_w, tile_h, 1}, SWIZZLE_64B; scr_stride =
+  // floats between the scratch areas of consecutive epilogue warps (the 4 warps of a column group pool theirs into two staging tiles)
+  CUtensorMap out_map;
+  int scr_stride;
 };
+
+// ---- TMA-store epilogue ------------------------------------------------------------------------------------------------------------
+// The four epilogue warps that share a column range hold the 128 rows of the tile between them.  Per 32-column chunk each thread packs its
+// row to fp16 (64 B) and writes it into a staging tile [128 rows][64 B] in the 64-byte swizzle TMA expects; one thread then issues ONE
+// cp.async.bulk.tensor store of the box {32 ch, tile_w, tile_h} — the copy engine does the address generation, clips rows outside the
+// tensor (partial tiles, the dummy half of an odd pair: frame index T) and writes whole lines.  Two staging tiles per group (8 KB each,
+// carved from the warps' transposition scratch), so the store of chunk i overlaps the packing of chunk i + 1.  Measured motive: the 1x1
+// Q/K/V projection executed 44 M warp instructions for 103 M outputs and held the tensor pipe at 18 % (profiles/ncu_r2c_gemm2.md).
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// v[32]: this thread's row (tile row `row`), channels [ch0, ch0 + 32) after bias / activation.  `parity` alternates per call (per group).
+__device__ __forceinline__ void conv_store_tma(const ConvParams& p, int x0, int y0, int t, int row, int ch0, const float* v, float* scr, int& parity) {
+  const int lane = threadIdx.x & 31, ew = (int)(threadIdx.x >> 5) - 2;
+  const int wq = ew & 3, grp = ew >> 2;
+  uint8_t* stage = reinterpret_cast<uint8_t*>(scr - wq * p.scr_stride) + parity * 8192;
+  const bool leader = wq == 0 && lane == 0;
+  if (leader) tma_store_wait_read<1>();          // the store that read this staging tile two chunks ago has finished reading it
+  named_bar_sync(1 + grp, 128);
+  uint4* dst = reinterpret_cast<uint4*>(stage + row * 64);
+  const int sw = (row >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __align__(16) __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+    dst[j ^ sw] = *reinterpret_cast<const uint4*>(h);
+  }
+  fence_proxy_async_smem();
+  named_bar_sync(1 + grp, 128);
+  if (leader) {
+    tma_store_4d(&p.out_map, smem_u32(stage), ch0, x0, y0, t);
+    tma_store_commit();
+  }
+  parity ^= 1;
+}
 
 // 32 accumulator columns [ch0, ch0 + 32) of the 32 pixel rows of one epilogue warp (row = lane), after bias / activation:
 // optional fp32 residual add, fp32 store, fp16 store — every global access issued "transposed" (lane = 4 rows x 8 sixteen-byte
@@ -118,6 +167,7 @@ struct ConvPolicy {
     bool valid;
     int t, y, x;
     size_t pix;  // (t*H + y)*W + x
+    int parity;  // CONV_TMA_STORE: which staging tile the next chunk uses (persists across tiles: the caller keeps it)
   };
 
   __device__ static void prefetch(const Params& p) {
@@ -168,6 +218,7 @@ struct ConvPolicy {
     const int oy = c.y - p.crop_t, ox = c.x - p.crop_l;
     c.valid = (ry < p.tile_h) && (c.y < p.H) && (c.x < p.W) && ((unsigned)oy < (unsigned)p.out_H) && ((unsigned)ox < (unsigned)p.out_W);
     c.pix = ((size_t)t.t * p.out_H + oy) * p.out_W + ox;
+    c.parity = 0;   // every tile stores an even number of chunks per column group, so the staging tiles keep alternating across tiles
     return c;
   }
   __device__ static void row_end(const Params&, const Tile&, RowCtx&, int) {}
@@ -232,6 +283,10 @@ struct ConvPolicy {
       }
       return;
     }
+    if (scr != nullptr && (p.flags & CONV_TMA_STORE)) {
+      conv_store_tma(p, t.x0, t.y0, t.t, row, ch0, v, scr, c.parity);
+      return;
+    }
     if (scr != nullptr && !(p.flags & CONV_S2D_STORE)) {
       conv_store_coalesced(p, c.valid ? (int)c.pix : -1, ch0, v, scr);
       return;
@@ -272,7 +327,7 @@ struct ConvPolicy {
 
 // CTA-pair version of ConvPolicy<256>: pair-tile = two consecutive 128-pixel sub-tiles x 256 channels.
 struct Conv2Policy {
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = 5;   // 5 x 32 KB + 34 KB of epilogue staging (6 stages would sit exactly on the 227 KB limit)
   static constexpr int PROF_ID = 1;
   static constexpr bool EPI_SCRATCH = true;
   static constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes half of the 256 columns

@@ -124,7 +124,8 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 // fp16 tensor, dims innermost-first, strides in BYTES for dims 1..rank-1, SWIZZLE_128B, zero OOB fill.
-static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap m;
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
@@ -135,7 +136,7 @@ static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims
     if (i + 1 < rank) gs[i] = strides_bytes[i];
   }
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     std::string s = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") rank " + std::to_string(rank) + " dims";
@@ -156,9 +157,11 @@ struct Ctx {
   bool conv_2cta = true;  // VSR_CONV_2CTA=0 falls back to the single-CTA 128x256 tile kernel (A/B switch)
   bool attn_2cta = true;  // VSR_ATTN_2CTA=0: single-CTA score / PV kernels
   bool conv_halo = false;  // haloed-tile kernel for k x k convs with 256-wide Cout tiles (conv_halo.cuh); VSR_CONV_HALO=0 switches it off
+  bool conv_halo_narrow = false;  // VSR_CONV_HALO_NARROW=1: also the 64 / 128-wide Cout tiles on the haloed kernel (measured slower)
   int conv_cluster = 2;    // VSR_CONV_CLUSTER=4: two CTA pairs per cluster share the weights by TMA multicast (conv_halo.cuh)
   int conv_halo_base_off = 0;  // the descriptor's base-offset field stays 0: the tensor core swizzles on absolute smem address bits
                                // (measured, profiles/gpu_session_r2_s2_summary.txt: with the field set three conv cases fail)
+  bool conv_tma_store = true;   // fp16-only conv outputs leave through a smem-staged TMA store (UTMASTG); VSR_CONV_TMA_STORE=0: per-thread stores
   bool direct_conv_smem = true;  // VSR_DIRECT_CONV_SMEM=0: the tiny-channel direct conv without shared-memory weights (A/B switch)
   bool conv_prefetch = false;  // VSR_CONV_PREFETCH=1: next-tile L2 prefetch in the conv producers (measured neutral)
   bool attn_lpt = true;   // VSR_ATTN_LPT=0: round-robin tile order in the score / PV launches
@@ -443,8 +446,21 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
   }
   if (!(io.flags & CONV_FINAL)) REQUIRE(L.cout % 8 == 0, "Cout must be a multiple of 8");
   if (io.out32) REQUIRE(L.cout == L.cout_pad, "fp32 stream needs Cout == padded Cout");
+  // fp16-only outputs on an un-cropped grid: TMA store epilogue (conv_store_tma); the map is finished below, once the tile shape is known
+  const bool tma_store = c.conv_tma_store && io.out16 && !io.out32 && !(io.flags & (CONV_FINAL | CONV_S2D_STORE | CONV_SCALED)) && io.out_H == 0 &&
+                         io.crop_t == 0 && io.crop_l == 0 && L.bn == 256 && c.conv_2cta && (p.out16_pitch % 8) == 0 && (p.out16_coff % 8) == 0;
+  auto make_out_map = [&](int tw, int th) {
+    const uint64_t od[4] = {(uint64_t)L.cout, (uint64_t)io.W, (uint64_t)io.H, (uint64_t)io.T};
+    const uint64_t os[3] = {(uint64_t)p.out16_pitch * 2, (uint64_t)io.W * p.out16_pitch * 2, (uint64_t)io.H * io.W * p.out16_pitch * 2};
+    const uint32_t ob[4] = {32, (uint32_t)tw, (uint32_t)th, 1};
+    p.out_map = make_map_f16(io.out16 + p.out16_coff, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B);
+    p.flags |= CONV_TMA_STORE;
+  };
   const int ntiles = p.T * p.tiles_y * p.tiles_x * p.n_tiles;
-  if ((L.bn == 256 || L.bn == 128 || L.bn == 64) && c.conv_2cta && c.conv_halo && !(io.flags & (CONV_FINAL | CONV_S2D_STORE)) && L.ntaps > 1 && io.W >= 8) {
+  // 64- and 128-wide Cout tiles (decoder convs) measured SLOWER on the haloed pair kernel than on the per-tap single-CTA one (decoder 6.1 vs
+  // 5.2 ms per chunk, profiles/gpu_session_r2_s4c_summary.txt): kept behind VSR_CONV_HALO_NARROW=1
+  if ((L.bn == 256 || (c.conv_halo_narrow && (L.bn == 128 || L.bn == 64))) && c.conv_2cta && c.conv_halo && !(io.flags & (CONV_FINAL | CONV_S2D_STORE)) &&
+      L.ntaps > 1 && io.W >= 8) {
     int halo = 0;
     for (int i = 0; i < L.ntaps; ++i) halo = std::max(halo, std::max(std::abs((int)L.dy[i]), std::abs((int)L.dx[i])));
     if (halo <= 4) {
@@ -464,6 +480,8 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
       p.tiles_y = tiles_y;
       p.halo = halo;
       p.halo_base_off = c.conv_halo_base_off;
+      p.scr_stride = 1024;
+      if (tma_store && L.bn == 256) make_out_map(8, valid_h);
       p.halo_nb = halo_b_stages(halo, L.bn);
       const int smem = halo_smem_bytes(halo, L.bn);
       static int configured_smem[4] = {0, 0, 0, 0}, max_clusters4 = 0;
@@ -516,6 +534,8 @@ static void run_conv(Ctx& c, const ConvLayer& L, const ConvIO& io) {
     const uint64_t str[1] = {(uint64_t)L.K * 2};
     const uint32_t box[2] = {64, 128};
     p.w_map_half = make_map_f16(L.w.p, 2, dims, str, box);
+    p.scr_stride = 32 * 33;
+    if (tma_store) make_out_map(tw, th);
     launch_tc2<Conv2Policy>(c, p, ((p.T * p.tiles_y * p.tiles_x + 1) / 2) * p.n_tiles);
     return;
   }
@@ -1779,6 +1799,8 @@ int vsr_sttn_create(vsr_sttn_t** out, int device, const vsr_sttn_config* cfg) {
     h->use_graph = !env_flag("VSR_NO_GRAPH", false);
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     h->ctx.conv_halo = env_flag("VSR_CONV_HALO", true);
+    h->ctx.conv_halo_narrow = env_flag("VSR_CONV_HALO_NARROW", false);
+    h->ctx.conv_tma_store = env_flag("VSR_CONV_TMA_STORE", true);
     h->ctx.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", false) ? 1 : 0;
     h->ctx.conv_cluster = getenv("VSR_CONV_CLUSTER") && atoi(getenv("VSR_CONV_CLUSTER")) == 4 ? 4 : 2;
     h->ctx.attn_2cta = env_flag("VSR_ATTN_2CTA", true);
@@ -2132,7 +2154,9 @@ int vsr_rt_create(vsr_rt_t** out, int device) {
     h->ctx.sms = prop.multiProcessorCount;
     h->ctx.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     h->ctx.direct_conv_smem = env_flag("VSR_DIRECT_CONV_SMEM", true);
-    h->ctx.conv_halo = env_flag("VSR_RT_CONV_HALO", false);   // haloed-tile convs in the graph runtime: off until every network's GPU tests ran with it
+    h->ctx.conv_tma_store = false;   // graph runtime: per-thread stores (its convs use scaled epilogues and cropped grids)
+    h->ctx.conv_halo = env_flag("VSR_RT_CONV_HALO", false);   // haloed-tile convs in the graph runtime: LAMA / DBNet / RAFT tests pass with it, but it
+    h->ctx.conv_halo_narrow = h->ctx.conv_halo;               // measured no faster there (LAMA 184 vs 192 frames/s): off by default
     CK(cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking));
     h->flag.ensure(16);
     *out = h;
@@ -3217,6 +3241,8 @@ struct OpCtx {
     c.sms = prop.multiProcessorCount;
     c.conv_2cta = env_flag("VSR_CONV_2CTA", true);
     c.conv_halo = env_flag("VSR_CONV_HALO", true);
+    c.conv_halo_narrow = env_flag("VSR_CONV_HALO_NARROW", false);
+    c.conv_tma_store = env_flag("VSR_CONV_TMA_STORE", true);
     c.conv_halo_base_off = env_flag("VSR_CONV_HALO_BASEOFF", false) ? 1 : 0;
     c.conv_cluster = getenv("VSR_CONV_CLUSTER") && atoi(getenv("VSR_CONV_CLUSTER")) == 4 ? 4 : 2;
     c.attn_2cta = env_flag("VSR_ATTN_2CTA", true);

@@ -51,7 +51,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2_threads<P>(), 1)
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_slot;
   // per-epilogue-warp 32x33 fp32 transpose scratch (policies that store row-scattered data coalesce through it)
-  __shared__ __align__(16) float epi_scratch[P::EPI_SCRATCH ? EW * 32 * 33 : 4];
+  __shared__ __align__(1024) float epi_scratch[P::EPI_SCRATCH ? EW * 32 * 33 : 4];
 
   const long long t_kernel0 = TC_PROF_NOW();
   (void)t_kernel0;
@@ -170,6 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc2_threads<P>(), 1)
       if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&bar_tempty[as]), 0));
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // TMA stores of a policy's epilogue read this CTA's smem: finished before exit
     if (warp == 2 && lane == 0) {
       TC_PROF_ADD(P::PROF_ID, 3, w_tfull);
       TC_PROF_ADD(P::PROF_ID, 4, busy);
