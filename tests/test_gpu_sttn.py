@@ -144,17 +144,16 @@ def test_graph_replay_across_batch_lengths(capi, monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(got, want[i])), f"job {i} differs from the eager path"
 
 
-@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("world", [1, 2, 3])
 def test_window_sharded_chunk_equals_single_engine(capi, world):
-    """One chunk with its windows dealt over `world` ranks (vsr_sttn_shard_*): every rank is its own engine (here: threads on one GPU, the two
-    all-gathers done by device-to-device copies between the engines' exchange buffers); reference-frame features exchanged, window
-    predictions exchanged, blend replayed in schedule order.  world = 1 is bit-identical to the unsharded call; with more ranks other windows
+    """One chunk with its windows dealt over `world` ranks (vsr_sttn_shard_*).  Every rank is its own engine on this one GPU, driven in lock
+    step from this thread through the three phases; the two all-gathers are device-to-device copies between the engines' exchange buffers
+    (under NCCL: tools/run_sharded_check.py).  Reference-frame features exchanged, window predictions exchanged, blend replayed in schedule
+    order.  world = 1 is bit-identical to the unsharded call; with more ranks other windows
     share a launch, the split-K attention heads sum in another order; through the fp16 activations of 8 blocks that moves about 1 % of the
     pixels by one grey level (measured), never more than two."""
-    import threading
-
     import torch
-    from vsr_b200 import STTNInpaint
+    from vsr_b200 import STTNInpaint, _capi
     from vsr_b200.sttn_auto_inpaint import _DevicePointer
 
     w = {k: v.numpy() for k, v in O.random_weights(0).items()}
@@ -163,36 +162,32 @@ def test_window_sharded_chunk_equals_single_engine(capi, world):
     mask = O.default_mask(H, W)
     want = STTNInpaint("cuda:0", w)(frames, mask)
     engines = [STTNInpaint("cuda:0", w) for _ in range(world)]
-    outs = [[f.copy() for f in frames] for _ in range(world)]
-    barrier, ptrs, errors = threading.Barrier(world), {}, []
 
-    def gather_for(rank):
-        def gather(ptr, nbytes):
-            ptrs[rank] = ptr
-            barrier.wait()
-            mine = torch.as_tensor(_DevicePointer(ptr, nbytes * world), device="cuda:0")
-            for r in range(world):
-                if r != rank:
-                    mine[r * nbytes:(r + 1) * nbytes].copy_(torch.as_tensor(_DevicePointer(ptrs[r], nbytes * world), device="cuda:0")[r * nbytes:(r + 1) * nbytes])
-            torch.cuda.synchronize()
-            barrier.wait()
-        return gather
+    def exchange(ptrs, nbytes):
+        views = [torch.as_tensor(_DevicePointer(p, nbytes * world), device="cuda:0") for p in ptrs]
+        for dst in range(world):
+            for src in range(world):
+                if src != dst:
+                    views[dst][src * nbytes:(src + 1) * nbytes].copy_(views[src][src * nbytes:(src + 1) * nbytes])
+        torch.cuda.synchronize()
 
-    def work(rank):
+    for attempt in range(2):
+        outs = [[f.copy() for f in frames] for _ in range(world)]
+        info = [engines[r].shard_begin(outs[r], mask, r, world) for r in range(world)]
+        if world > 1:
+            exchange([i[0] for i in info], info[0][1])
+        for e in engines:
+            e.shard_windows()
+        if world > 1:
+            exchange([i[2] for i in info], info[0][3])
         try:
-            got = engines[rank].inpaint_chunk_sharded(outs[rank], mask, rank, world, all_gather=gather_for(rank))
-            assert got == list(range(rank, T, world))
-        except BaseException as e:      # noqa: BLE001
-            errors.append(e)
-            barrier.abort()
-
-    threads = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join(timeout=240)
-    assert not any(t.is_alive() for t in threads), "a rank did not finish"
-    assert not errors, errors
+            for r in range(world):
+                engines[r].shard_finish(outs[r])
+            break
+        except _capi.VsrRangeError:          # every rank sees the same gathered flags: rank 0 raises first, all repeat on the exact path
+            assert attempt == 0
+            for e in engines:
+                e.set_option("attn_direct", 0)
     for rank in range(world):
         for f in range(T):
             if f % world != rank:

@@ -245,31 +245,44 @@ class STTNInpaint:
         frames = list(frames)
         if not frames:
             return []
-        H, W, m = self._check_batch(frames, input_mask)
-        pin, keep = self._ptr_array(frames)
-        L = _capi.lib()
-        ref_buf, pred_buf = C.c_void_p(), C.c_void_p()
-        ref_bytes, pred_bytes = C.c_int64(), C.c_int64()
-        _capi.check(L.vsr_sttn_shard_begin(self._h, C.cast(pin, C.POINTER(C.c_void_p)), len(frames), H, W, _capi.ptr(m, C.c_uint8), int(rank), int(world),
-                                           C.byref(ref_buf), C.byref(ref_bytes), C.byref(pred_buf), C.byref(pred_bytes)))
+        ref_ptr, ref_bytes, pred_ptr, pred_bytes = self.shard_begin(frames, input_mask, rank, world)
         gather = all_gather or (lambda ptr, nbytes: _nccl_all_gather_inplace(ptr, nbytes, rank, world, self._dev))
         if world > 1:
-            gather(int(ref_buf.value), int(ref_bytes.value))
-        _capi.check(L.vsr_sttn_shard_windows(self._h))
+            gather(ref_ptr, ref_bytes)
+        self.shard_windows()
         if world > 1:
-            gather(int(pred_buf.value), int(pred_bytes.value))
+            gather(pred_ptr, pred_bytes)
         try:
-            _capi.check(L.vsr_sttn_shard_finish(self._h, C.cast(pin, C.POINTER(C.c_void_p))))
+            self.shard_finish(frames)
         except _capi.VsrRangeError:
             if getattr(self, "_in_retry", False):
                 raise
-            self.set_option("attn_direct", 0)      # every rank sees the same logits, i.e. takes this branch together
+            self.set_option("attn_direct", 0)      # the flags travelled with the predictions: every rank takes this branch together
             self._in_retry = True
             try:
                 return self.inpaint_chunk_sharded(frames, input_mask, rank, world, all_gather)
             finally:
                 self._in_retry = False
         return list(range(rank, len(frames), world))
+
+    # the three phases of the sharded chunk (include/vsr_b200.h: vsr_sttn_shard_*); between them the caller all-gathers the two buffers
+    def shard_begin(self, frames: Sequence[np.ndarray], input_mask: np.ndarray, rank: int, world: int):
+        """-> (reference-feature buffer pointer, bytes per rank region, prediction buffer pointer, bytes per rank region)"""
+        H, W, m = self._check_batch(frames, input_mask)
+        pin, keep = self._ptr_array(list(frames))
+        self._shard_keep = (pin, keep, m)
+        ref_buf, pred_buf = C.c_void_p(), C.c_void_p()
+        ref_bytes, pred_bytes = C.c_int64(), C.c_int64()
+        _capi.check(_capi.lib().vsr_sttn_shard_begin(self._h, C.cast(pin, C.POINTER(C.c_void_p)), len(frames), H, W, _capi.ptr(m, C.c_uint8), int(rank),
+                                                     int(world), C.byref(ref_buf), C.byref(ref_bytes), C.byref(pred_buf), C.byref(pred_bytes)))
+        return int(ref_buf.value), int(ref_bytes.value), int(pred_buf.value), int(pred_bytes.value)
+
+    def shard_windows(self) -> None:
+        _capi.check(_capi.lib().vsr_sttn_shard_windows(self._h))
+
+    def shard_finish(self, frames: Sequence[np.ndarray]) -> None:
+        pout, keep = self._ptr_array(list(frames))
+        _capi.check(_capi.lib().vsr_sttn_shard_finish(self._h, C.cast(pout, C.POINTER(C.c_void_p))))
 
     @property
     def cuda_stream(self) -> int:
