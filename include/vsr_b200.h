@@ -94,15 +94,19 @@ int vsr_sttn_collect(vsr_sttn_t* h, int64_t ticket, uint8_t* const* frames_out);
  * (sttn_auto_inpaint.py:142-146) are dealt round-robin (window w on rank w % world).  Call order on every rank, same arguments:
  *   shard_begin   stages the strips, encodes the frames this rank's windows decode plus the reference frames it is the home of, and packs
  *                 those references' encoder features into its region of the reference exchange buffer `*ref_buf`
- *   -> all-gather (in place) of `*ref_buf`: world regions of `*ref_region_bytes` bytes, region r written by rank r — the features of the
+ *   -> all-gather of `*ref_buf`: world regions of `*ref_region_bytes` bytes, region r written by rank r — the features of the
  *      reference frames are the only data a window needs from outside its neighbourhood (get_ref_index, :107-120)
  *   shard_windows runs this rank's windows, each into its own slot of the prediction exchange buffer `*pred_buf`
- *   -> all-gather (in place) of `*pred_buf` (world regions of `*pred_region_bytes` bytes)
+ *   -> all-gather of `*pred_buf` (world regions of `*pred_region_bytes` bytes)
  *   shard_finish  replays the ordered 0.5 / 0.5 blend (:159-162) on all predictions (bit-identical to the unsharded chunk), composites,
  *                 and writes the frames f with f %% world == rank to frames_out[f] (other entries are not touched).
- * The buffers are device memory owned by the engine; the collectives are the caller's (torch.distributed / NCCL on the raw pointers). */
+ * The buffers are device memory owned by the engine; the collectives are the caller's (torch.distributed / NCCL on device tensors that
+ * vsr_sttn_copy fills from / drains into a rank's region: device-to-device, nothing passes through the host). */
 int vsr_sttn_shard_begin(vsr_sttn_t* h, const uint8_t* const* frames_in, int T, int H, int W, const uint8_t* mask, int rank, int world,
                          void** ref_buf, int64_t* ref_region_bytes, void** pred_buf, int64_t* pred_region_bytes);
+/* device -> device copy on the engine's stream, completed on return: moves a rank's region of an exchange buffer into / out of the
+ * caller's collective buffers (torch tensors for torch.distributed / NCCL) without exposing the engine's memory to another allocator */
+int vsr_sttn_copy(vsr_sttn_t* h, void* dst, const void* src, int64_t bytes);
 int vsr_sttn_shard_windows(vsr_sttn_t* h);
 int vsr_sttn_shard_finish(vsr_sttn_t* h, uint8_t* const* frames_out);
 /* Engine options: "attn_direct" (1: single-pass softmax (no row shift) for the attention heads without split-K — no score matrix, no softmax

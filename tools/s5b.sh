@@ -1,0 +1,13 @@
+#!/bin/bash
+# GPU session 5b (2 GPUs): the window-sharded chunk under NCCL (all-gather through torch-owned device tensors) and single-clip strong scaling.
+set -u
+mkdir -p gpurun_out
+sum=gpurun_out/s5b_summary.txt; : > $sum
+N=${1:-2}
+t() { local secs=$1 name=$2; shift 2; local t0=$(date +%s); timeout $secs "$@" > gpurun_out/s5b_$name.log 2> gpurun_out/s5b_$name.err; local rc=$?
+      echo "=== $name rc=$rc $(( $(date +%s) - t0 ))s :: $(grep -v '^\s*$' gpurun_out/s5b_$name.log | tail -n 1 | cut -c1-300)" | tee -a $sum; [ $rc -ne 0 ] && tail -n 12 gpurun_out/s5b_$name.err | cut -c1-300 | tee -a $sum; return $rc; }
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+PYTHONFAULTHANDLER=1 t 300 sharded_check $TR --master-port 29511 tools/run_sharded_check.py
+PYTHONFAULTHANDLER=1 t 300 strong $TR --master-port 29512 bench.py --gpus $N --workload sttn-auto-strong --steps 2 --warmup 1
+t 200 strong1 python bench.py --workload sttn-auto-strong --steps 2 --warmup 1
+cat $sum

@@ -70,6 +70,7 @@ _PROTOS = {
     "vsr_sttn_shard_begin": (C.c_int, [C.c_void_p, _pp, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, _pp, _i64p, _pp, _i64p]),
     "vsr_sttn_shard_windows": (C.c_int, [C.c_void_p]),
     "vsr_sttn_shard_finish": (C.c_int, [C.c_void_p, _pp]),
+    "vsr_sttn_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "vsr_sttn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "vsr_sttn_sync": (C.c_int, [C.c_void_p]),
     "vsr_sttn_stream": (C.c_void_p, [C.c_void_p]),

@@ -1965,6 +1965,15 @@ int vsr_sttn_shard_finish(vsr_sttn_t* h, uint8_t* const* frames_out) {
   });
 }
 
+int vsr_sttn_copy(vsr_sttn_t* h, void* dst, const void* src, int64_t bytes) {
+  return guarded([&] {
+    check_ready(h);
+    REQUIRE(dst && src && bytes >= 0, "bad arguments");
+    CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, h->ctx.stream));
+    sync_stream(h);
+  });
+}
+
 int vsr_sttn_set_option(vsr_sttn_t* h, const char* name, int value) {
   return guarded([&] {
     REQUIRE(h && name, "bad arguments");

@@ -234,10 +234,10 @@ class STTNInpaint:
     # ---- one chunk over several GPUs: window-level sharding (single-clip strong scaling) --------------------
     def inpaint_chunk_sharded(self, frames: Sequence[np.ndarray], input_mask: np.ndarray, rank: int, world: int, all_gather=None) -> List[int]:
         """The windows of one chunk's schedule (sttn_auto_inpaint.py:142-146) dealt over the `world` ranks of a process group: window w runs
-        on rank w % world.  Two in-place all-gathers over NVLink carry the only data that crosses windows — the encoder features of the
+        on rank w % world.  Two all-gathers over NVLink carry the only data that crosses windows — the encoder features of the
         chunk's reference frames (get_ref_index, :107-120) and, afterwards, the windows' quantised predictions for the ordered 0.5 / 0.5
-        blend (:159-162) — both on device memory of the engine (`all_gather(device_pointer, region_bytes)`, default: NCCL through
-        torch.distributed).  Every rank must call this with the same frames and mask.  The result strips of the frames f with
+        blend (:159-162) — both on device memory (`all_gather(device_pointer, region_bytes)`, default: NCCL through torch.distributed
+        on device tensors filled by device-to-device copies).  Every rank must call this with the same frames and mask.  The result strips of the frames f with
         f % world == rank are written into `frames[f]` in place (the other frames are left as they are on this rank); returns those
         frame indices.  Window by window the arithmetic is the single-GPU one and the blend is replayed in schedule order; the output
         differs from the unsharded call only through the summation order of the split-K attention heads, which depends on which windows
@@ -246,7 +246,7 @@ class STTNInpaint:
         if not frames:
             return []
         ref_ptr, ref_bytes, pred_ptr, pred_bytes = self.shard_begin(frames, input_mask, rank, world)
-        gather = all_gather or (lambda ptr, nbytes: _nccl_all_gather_inplace(ptr, nbytes, rank, world, self._dev))
+        gather = all_gather or (lambda ptr, nbytes: _nccl_all_gather(self, ptr, nbytes, rank, world))
         if world > 1:
             gather(ref_ptr, ref_bytes)
         self.shard_windows()
@@ -276,6 +276,10 @@ class STTNInpaint:
         _capi.check(_capi.lib().vsr_sttn_shard_begin(self._h, C.cast(pin, C.POINTER(C.c_void_p)), len(frames), H, W, _capi.ptr(m, C.c_uint8), int(rank),
                                                      int(world), C.byref(ref_buf), C.byref(ref_bytes), C.byref(pred_buf), C.byref(pred_bytes)))
         return int(ref_buf.value), int(ref_bytes.value), int(pred_buf.value), int(pred_bytes.value)
+
+    def copy_device(self, dst: int, src: int, nbytes: int) -> None:
+        """device -> device on the engine's stream, completed on return"""
+        _capi.check(_capi.lib().vsr_sttn_copy(self._h, C.c_void_p(dst), C.c_void_p(src), int(nbytes)))
 
     def shard_windows(self) -> None:
         _capi.check(_capi.lib().vsr_sttn_shard_windows(self._h))
@@ -319,15 +323,24 @@ class _DevicePointer:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def _nccl_all_gather_inplace(ptr: int, region_bytes: int, rank: int, world: int, device_index: int) -> None:
-    """In-place all-gather of a device buffer laid out [world][region_bytes]: region r is rank r's contribution (NCCL's in-place form:
-    the send buffer is the rank's own region of the receive buffer).  torch only wraps the engine's pointer and issues the collective."""
+def _nccl_all_gather(engine, ptr: int, region_bytes: int, rank: int, world: int) -> None:
+    """All-gather of an engine exchange buffer laid out [world][region_bytes] (region r = rank r's contribution) with torch.distributed / NCCL
+    over NVLink: this rank's region goes device-to-device into a torch tensor, `all_gather_into_tensor` fills the gathered tensor, and that
+    comes back device-to-device (vsr_sttn_copy) — the engine's memory is never handed to another allocator, nothing touches the host."""
     import torch
     import torch.distributed as dist
 
-    whole = torch.as_tensor(_DevicePointer(ptr, region_bytes * world), device=torch.device("cuda", device_index))
-    dist.all_gather_into_tensor(whole, whole[rank * region_bytes:(rank + 1) * region_bytes])
-    torch.cuda.synchronize(device_index)
+    dev = torch.device("cuda", engine._dev)
+    cache = engine.__dict__.setdefault("_gather_bufs", {})
+    if cache.get("n") != (region_bytes, world):
+        cache.update(n=(region_bytes, world), send=torch.empty(region_bytes, dtype=torch.uint8, device=dev),
+                     recv=torch.empty(region_bytes * world, dtype=torch.uint8, device=dev))
+    send, recv = cache["send"], cache["recv"]
+    torch.cuda.synchronize(dev)
+    engine.copy_device(send.data_ptr(), ptr + rank * region_bytes, region_bytes)
+    dist.all_gather_into_tensor(recv, send)
+    torch.cuda.synchronize(dev)
+    engine.copy_device(ptr, recv.data_ptr(), region_bytes * world)
 
 
 def _in_ab_sections(frame_no, ab_sections) -> bool:
