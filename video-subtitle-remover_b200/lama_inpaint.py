@@ -312,10 +312,11 @@ class LamaInpaint:
         H, W = mask.shape[:2]
         areas = get_inpaint_area_by_mask(W, H, int(W * 3 / 16), mask)
         frames = [f.copy() for f in input_frames]
-        for (y0, y1, _, _) in areas:
-            strip_mask = mask[y0:y1]
-            comps = self._inpaint_batch([f[y0:y1] for f in frames], [strip_mask] * len(frames))
-            for f, c in zip(frames, comps):
+        # every strip is cropped from the untouched frames and only then are the results written back, in area order (:86-107):
+        # strips may overlap
+        comps = [self._inpaint_batch([f[y0:y1] for f in frames], [mask[y0:y1]] * len(frames)) for (y0, y1, _, _) in areas]
+        for (y0, y1, _, _), strips in zip(areas, comps):
+            for f, c in zip(frames, strips):
                 f[y0:y1] = c
         return frames
 
