@@ -1000,12 +1000,14 @@ static void prepare_network(vsr_sttn* h, int T) {
     upload(G.visits_d, visits, s);
     G.visits_h = visits;
   }
+  // frames of the largest launch group: ANY window_group windows may share a launch (the sharded path groups a rank's own windows,
+  // e.g. windows 4 and 6 of a 50-frame chunk = 30 frames where consecutive pairs never exceed 29), so take the largest ones
   size_t maxw = 0;
-  for (size_t w0 = 0; w0 < G.sched.size(); w0 += h->window_group) {
-    size_t sum = 0;
-    for (size_t wi = w0; wi < std::min(G.sched.size(), w0 + h->window_group); ++wi)
-      sum += G.sched[wi].neighbors.size() + G.sched[wi].refs.size();
-    maxw = std::max(maxw, sum);
+  {
+    std::vector<size_t> sizes;
+    for (auto& w : G.sched) sizes.push_back(w.neighbors.size() + w.refs.size());
+    std::sort(sizes.begin(), sizes.end(), std::greater<size_t>());
+    for (size_t i = 0; i < sizes.size() && i < h->window_group; ++i) maxw += sizes[i];
   }
   size_t maxn = 0;
   for (auto& w : G.sched) maxn = std::max(maxn, w.neighbors.size());
