@@ -922,7 +922,7 @@ def main(argv=None):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-frames", type=int, default=20, help="frames of the chunk the cpu_baseline leg runs through the reference (<= 50)")
+    ap.add_argument("--cpu-frames", type=int, default=32, help="frames of the chunk the cpu_baseline leg runs through the reference (<= 50)")
     ap.add_argument("--workload", default="sttn-auto", choices=sorted(WORKLOADS),
                     help="sttn-auto = BASELINE config 2 (the contract line); sttn-det / dbnet = the inpaint / detection halves of config 4; "
                          "config4 = that chain end to end (sharded over the ranks when N > 1); lama = the big-lama model of config 1 on 1080p "
