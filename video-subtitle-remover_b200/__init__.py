@@ -21,7 +21,8 @@ from .sttn_det_inpaint import STTNDetInpaint  # noqa: F401
 from .subtitle_detect import SubtitleDetect  # noqa: F401
 from .lama_inpaint import LamaInpaint  # noqa: F401
 from .pipeline import propainter_mode_frames, video_inpaint_frames  # noqa: F401
+from .pipeline_async import video_inpaint_frames_overlapped  # noqa: F401
 from .propainter_inpaint import PropainterInpaint  # noqa: F401
 
-__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "LamaInpaint", "PropainterInpaint", "SubtitleDetect", "video_inpaint_frames", "propainter_mode_frames", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
+__all__ = ["STTNInpaint", "STTNAutoInpaint", "STTNDetInpaint", "LamaInpaint", "PropainterInpaint", "SubtitleDetect", "video_inpaint_frames", "video_inpaint_frames_overlapped", "propainter_mode_frames", "InpaintMode", "config", "create_mask", "get_inpaint_area_by_mask",
            "batch_generator"]
