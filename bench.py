@@ -11,7 +11,7 @@ clip_gap, sttn_auto_inpaint.py:242-245); the 300-frame clip of config 2 is K = 6
   roofline  the dominant kernel (transformer-block 3x3 conv 256->256, tcgen05 implicit GEMM) AS IT RUNS IN THE CHUNK: one eager pass
             of the chunk with CUDA events around every launch group (vsr_sttn_profile), algorithmic FLOPs / measured time against
             the sustained bf16 peak of MEASURED_PEAKS.json; the isolated back-to-back figure is kept beside it
-  cpu_baseline  the reference's own `STTNInpaint.__call__` (oracle/_ref, kind "reference") on a bounded sample on the host cores,
+  cpu_baseline  the reference's own `STTNInpaint.__call__` (baseline/_ref, kind "reference") on a bounded sample on the host cores,
             or the oracle port when the reference modules did not travel (kind "port")
 `--impl reference` times only that CPU path, with all host threads, on the same config.
 Under torchrun (N > 1) every rank owns K chunks of its own (weak scaling, no data-path collective: chunks are independent units,

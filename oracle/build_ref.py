@@ -3,12 +3,12 @@
 
 The reference is Python: its "build" is a file copy.  From the sources where they lie under /root/reference this copies the Python
 modules of `backend/inpaint`, `backend/tools` and `backend/scenedetect` (1.2 MB of .py files; no models, no ffmpeg binaries, no GUI)
-into oracle/_ref/backend/, byte for byte.  oracle/_ref/ is listed in .gitignore (the copy never enters the history — reference sources
+into baseline/_ref/backend/ (the place the bench contract reserves for the unmodified reference), byte for byte.  baseline/_ref/ is listed in .gitignore (the copy never enters the history — reference sources
 are not part of this repository) and not in .gpurunignore, so it travels with the snapshot like a compiled `_ref` binary would.
 
 Users: `bench.py --impl reference` and the `cpu_baseline` leg (kind "reference": the reference's own `STTNInpaint.__call__`,
 backend/inpaint/sttn_auto_inpaint.py:43-97, timed on the box's host cores), through oracle/ref_import.py which resolves the reference
-root to /root/reference when that exists and to oracle/_ref otherwise.  Runs only where /root/reference exists (this container)."""
+root to /root/reference when that exists and to baseline/_ref otherwise.  Runs only where /root/reference exists (this container)."""
 import filecmp
 import os
 import shutil
@@ -16,7 +16,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("VSR_REFERENCE_ROOT", "/root/reference")
-DST = os.path.join(HERE, "_ref")
+DST = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
 PACKAGES = ("inpaint", "tools", "scenedetect")
 
 

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE — imports the UNMODIFIED reference: from /root/reference in this container, from the byte-for-byte copy of its
-Python modules under oracle/_ref (oracle/build_ref.py; git-ignored, travels with the gpurun snapshot) on the GPU box.
+Python modules under baseline/_ref (oracle/build_ref.py; git-ignored, travels with the gpurun snapshot) on the GPU box.
 
 Used by tools/make_golden*.py and by the `-m "not gpu"` oracle-pinning tests to validate the restatements in oracle/ and to (re)generate
 tests/golden/*.npz, and by bench.py's CPU legs (`--impl reference`, `cpu_baseline` kind "reference") to time the reference's own
@@ -16,8 +16,9 @@ import types
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("VSR_REFERENCE_ROOT", "/root/reference")
-if not os.path.isdir(os.path.join(REF_ROOT, "backend", "inpaint")) and os.path.isdir(os.path.join(_HERE, "_ref", "backend", "inpaint")):
-    REF_ROOT = os.path.join(_HERE, "_ref")
+_COPY = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+if not os.path.isdir(os.path.join(REF_ROOT, "backend", "inpaint")) and os.path.isdir(os.path.join(_COPY, "backend", "inpaint")):
+    REF_ROOT = _COPY
 
 
 def available() -> bool:

@@ -10,7 +10,7 @@ What the reference computes per decoded frame (backend/scenedetect/):
   :200-222                            cut at frame n when score >= 27.0 and n - last_cut >= 15 (last_cut starts at the first frame number)
   scene_manager.py get_scene_list + subtitle_detect.py:163-169: every scene that does not start at frame 0 contributes start + 1
 Parity pinned: tests/test_scene_oracle.py checks the HSV conversion and the resize against cv2 itself, and the whole function against the
-unmodified reference classes where the reference tree (or oracle/_ref) is present; golden scores / cuts in tests/golden/scene_cuts.npz."""
+unmodified reference classes where the reference tree (or baseline/_ref) is present; golden scores / cuts in tests/golden/scene_cuts.npz."""
 from typing import List, Sequence, Tuple
 
 import numpy as np

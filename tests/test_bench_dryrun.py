@@ -241,7 +241,7 @@ def test_reference_arm_line(capsys, monkeypatch):
 
 
 def test_cpu_reference_runs_the_unmodified_reference_or_the_port():
-    """CpuReference on a tiny clip: kind "reference" when the reference modules are present (oracle/_ref or /root/reference), else the port;
+    """CpuReference on a tiny clip: kind "reference" when the reference modules are present (baseline/_ref or /root/reference), else the port;
     both return frames of the input shape."""
     import os
 

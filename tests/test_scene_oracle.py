@@ -41,7 +41,7 @@ def test_golden_scores_and_cuts():
         assert S.scene_div_frame_no(frames) == [21, 46]
 
 
-@pytest.mark.skipif(not ref_import.available(), reason="reference modules not present (neither /root/reference nor oracle/_ref)")
+@pytest.mark.skipif(not ref_import.available(), reason="reference modules not present (neither /root/reference nor baseline/_ref)")
 def test_against_the_reference_detector():
     import cv2
     from make_golden_scene import clip
