@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Under torchrun (one process per GPU, NCCL): one 1080p chunk with its windows dealt over the ranks (`STTNInpaint.inpaint_chunk_sharded`,
-in-place all-gathers of the reference-frame features and of the window predictions on the engine's device buffers) against the unsharded
+NCCL all-gathers of the reference-frame features and of the window predictions, device to device) against the unsharded
 call computed by the same rank on its own GPU — the frames a rank hands back must equal it (<= 2 grey levels: split-K summation order).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/run_sharded_check.py"""
 import os

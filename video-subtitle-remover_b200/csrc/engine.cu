@@ -1511,8 +1511,8 @@ static void collect(vsr_sttn* h, int64_t ticket, uint8_t* const* frames_out) {
 // frame number j, i.e. frame j * ref_length, lives on rank j % world); the encoder features of the reference frames — the only data a
 // window needs from outside its own neighbourhood (get_ref_index :107-120) — are exchanged with ONE all-gather, the quantised window
 // predictions with a second one, and every rank replays the ordered 0.5 / 0.5 blend (:159-162) on the full set.  The two exchange
-// buffers are laid out [world][slots per rank][...] so that both collectives are in-place NCCL all-gathers on device memory
-// (the Python side wraps the raw pointers; nothing passes through the host).
+// buffers are laid out [world][slots per rank][...]: a rank's region goes out, and the gathered buffer comes back, by device-to-device
+// copies (vsr_sttn_copy) between the engine's memory and the caller's NCCL tensors; nothing passes through the host.
 static size_t shard_ref_bytes(vsr_sttn* h) { return (size_t)h->FH * h->FW * 256 * (2 + 4); }   // fp16 + fp32 features of one frame
 static size_t shard_pred_bytes(vsr_sttn* h) { return (size_t)32 * h->cfg.model_h * h->cfg.model_w * 3 * sizeof(float); }
 // a rank's region of the prediction exchange buffer: its window slots (32 frames each) + one more frame whose first int carries the
